@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py — stereo frames/s of the CODD HITNetMF hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one HITNetMF stereo-only forward over a batch of 8 synthetic 960x540 pairs
+(reflect-padded to 576x960, D=192, random-init weights): BASELINE.json configs[1].  With N GPUs
+every rank runs the same per-GPU batch (frames are independent -> weak scaling, no data-path
+collective; NCCL only broadcasts the weights once and reduces the timing).
+
+One JSON line on stdout (rank 0).  `value` = frames/s with inputs resident in HBM; `e2e` = the
+same metric through the public model(...) call with pinned HOST buffers, host<->device copies
+inside the timed region.  `roofline` describes the dominant kernel of the step (per-launch CUDA
+events in an instrumented pass right after the timed region); `cpu_baseline` is the CPU oracle
+port timed on this box's host cores on a bounded sample.
+
+--impl reference: the reference's own CPU implementation cannot travel to the GPU box (it is a
+Python tree under /root/reference that needs mmcv/mmseg), so this arm times the bit-identical
+oracle port in its reference-form (same torch op sequence, incl. the materialised 5-D
+grid_sample cost volume) on all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+H_IMG, W_IMG = 540, 960
+H_PAD, W_PAD = 576, 960          # reflect-padded to a multiple of 64 (datasets/transforms.py:147-161)
+MAX_DISP = 192
+BATCH = 8
+METRIC = "stereo_frames_per_sec_960x540_D192"
+UNIT = "frames/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
+    return ap.parse_args()
+
+
+def workload_config(batch, n_gpus):
+    return {
+        "workload": f"HITNetMF stereo-only forward, batch={batch} per GPU, 960x540 pairs padded to "
+                    f"{H_PAD}x{W_PAD}, D={MAX_DISP}, random-init weights (BASELINE.json configs[1])",
+        "per_gpu_batch": batch, "global_batch": batch * n_gpus, "max_disp": MAX_DISP,
+        "padded_hw": [H_PAD, W_PAD], "parallelism": f"dp{n_gpus} (batch-sharded, weights broadcast once)",
+    }
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampling (nvidia-smi in the background during the timed region)
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5),
+                              ("sw_power_cap", 6)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        # median of the samples taken under load (upper half: idle samples bracket the region)
+        load = sm[len(sm) // 2:] if sm else []
+        med = load[len(load) // 2] if load else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# reference / CPU arm
+# ----------------------------------------------------------------------------------------------
+def cpu_forward_time(rows, repeats, reference_form=True):
+    """Seconds per pair for the oracle port on a [1,3,rows,960] strip (rows % 64 == 0)."""
+    from oracle import hitnet_oracle as O
+    sd = O.random_hitnet_params(0)
+    left, right = O.synth_pair(1, rows, W_PAD, MAX_DISP, seed=1234, kind="S")
+    ts = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        O.stereo_matching(sd, left, right, MAX_DISP, reference_form=reference_form)
+        ts.append(time.perf_counter() - t0)
+    return ts
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    # bounded sample: one full 576x960 pair per step if the run fits ~4 minutes, else a strip
+    probe = cpu_forward_time(128, 1)[0]                    # 128 rows: smallest valid strip
+    est_full = probe * (H_PAD / 128.0)
+    total = args.steps + args.warmup
+    rows = H_PAD
+    while rows > 128 and est_full * (rows / H_PAD) * total > 240.0:
+        rows -= 64
+    from oracle import hitnet_oracle as O
+    sd = O.random_hitnet_params(0)
+    left, right = O.synth_pair(1, rows, W_PAD, MAX_DISP, seed=1234, kind="S")
+    for _ in range(args.warmup):
+        O.stereo_matching(sd, left, right, MAX_DISP, reference_form=True)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.stereo_matching(sd, left, right, MAX_DISP, reference_form=True)
+    dt = time.perf_counter() - t0
+    frames = args.steps * rows / H_PAD
+    value = frames / dt
+    sample = (f"{args.steps} steps x 1 pair of {rows}x{W_PAD} rows ({rows / H_PAD:.3f} frame each), "
+              f"oracle port in reference form (5-D grid_sample cost volume), torch {torch.__version__} CPU")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.batch, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+    import codd_b200
+    from codd_b200 import ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: codd_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    # model: random init on rank 0, one flat NCCL broadcast of the weights (the reference's DDP wrap)
+    torch.manual_seed(0)
+    model = codd_b200.build_estimator(codd_b200.codd_stereo_config(MAX_DISP)).to(dev)
+    model.eval()
+    if world > 1:
+        flat = torch.cat([p.data.flatten() for p in model.parameters()])
+        dist.broadcast(flat, 0)
+        off = 0
+        for p in model.parameters():
+            p.data.copy_(flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+
+    B = args.batch
+    # Set U of SURVEY §8d would feed right == left (degenerate ties); use independent textured pairs
+    from codd_b200.synth import synth_pair
+    left_h, right_h = synth_pair(B, H_PAD, W_PAD, MAX_DISP, seed=1234 + rank, kind="S")
+    left_h, right_h = left_h.pin_memory(), right_h.pin_memory()
+    left, right = left_h.to(dev), right_h.to(dev)
+    stereo = model.stereo
+
+    def step():
+        return stereo.stereo_matching(left, right)["pred_disp"]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            out = step()
+        torch.cuda.synchronize()
+        n0 = ops.LAUNCHES[0]
+        step()
+        launches_per_step = ops.LAUNCHES[0] - n0
+
+        graph = None
+        if not args.no_graph:
+            # the ~130 launches of a step are captured once and replayed (static shapes)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                step()
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = step()
+
+        def run_step():
+            if graph is not None:
+                graph.replay()
+            else:
+                step()
+
+        for _ in range(3):
+            run_step()
+
+        # ---------------- timed region: device-resident inputs
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+            time.sleep(0.3)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            run_step()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if rank == 0 else None
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+
+        # ---------------- e2e: public API, pinned host buffers, H2D + D2H inside the region
+        img_h = torch.stack([left_h], 1).pin_memory()       # [B, MF=1, 3, H, W]
+        rimg_h = torch.stack([right_h], 1).pin_memory()
+        metas = [[dict(min_disp=1, max_disp=MAX_DISP, ori_shape=(H_IMG, W_IMG), img_shape=(H_IMG, W_IMG))]]
+        res_h = torch.empty((B, 1, H_IMG, W_IMG), dtype=torch.float32).pin_memory()
+
+        def e2e_step():
+            img = img_h.to(dev, non_blocking=True)
+            rimg = rimg_h.to(dev, non_blocking=True)
+            res = model(return_loss=False, rescale=True, evaluate=False, img=[img], img_metas=metas, r_img=[rimg])
+            res_h.copy_(res[0], non_blocking=True)
+
+        e2e_steps = max(3, min(args.steps, 10))
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        e0.record()
+        for _ in range(e2e_steps):
+            e2e_step()
+        e1.record()
+        barrier()
+        e2e_ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([e2e_ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = t.item()
+        h2d = img_h.numel() * 4 + rimg_h.numel() * 4
+        d2h = res_h.numel() * 4
+
+        # ---------------- instrumented pass: per-launch events -> dominant kernel + K1/K4 numbers
+        with ops.profile() as prof:
+            step()
+        kernels = prof.summary()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+
+    total_ms = sum(k["ms"] for k in kernels)
+
+    def roof(k):
+        gbs = k["bytes"] / (k["ms"] * 1e-3) / 1e9
+        return {"kernel": k["kernel"], "bound": "hbm", "achieved": round(gbs, 1), "peak": peak_gbs, "unit": "GB/s",
+                "frac": round(gbs / peak_gbs, 4), "traffic": None, "launches_per_step": k["launches"],
+                "ms_per_step": round(k["ms"], 4), "share_of_step": round(k["ms"] / total_ms, 4),
+                "algorithmic_bytes_per_step": k["bytes"], "peak_source": peak_src,
+                "how": "per-launch CUDA events on the launching stream, instrumented eager pass after the timed region"}
+
+    dominant = roof(kernels[0])
+    named = [roof(k) for k in kernels if k["kernel"].startswith(("cost_volume", "tile_warp_cost"))]
+
+    frames = args.steps * B * world
+    value = frames / (ms * 1e-3)
+    line = {
+        "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": dict(workload_config(B, world),
+                       l2="activations of one step (several GB) exceed the 126 MB L2; no explicit flush",
+                       cuda_graph=graph is not None),
+        "clocks": clocks,
+        "e2e": {"value": round(e2e_steps * B * world / (e2e_ms * 1e-3), 3), "unit": UNIT,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "api": "ConsistentOnlineDynamicDepth.__call__(return_loss=False, evaluate=False, img=[..], r_img=[..])"},
+        "gpu_launches": launches_per_step * args.steps,
+        "gpu_launches_per_step": launches_per_step,
+        "roofline": dominant,
+        "roofline_named_kernels": named,
+        "top_kernels": [{"kernel": k["kernel"], "ms": round(k["ms"], 4), "launches": k["launches"],
+                         "share": round(k["ms"] / total_ms, 4)} for k in kernels[:8]],
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        ts = cpu_forward_time(H_PAD, 3, reference_form=True)      # 1 warm-up + 2 timed pairs (~10-20 s)
+        sec = sum(ts[1:]) / len(ts[1:])
+        fast = cpu_forward_time(H_PAD, 2, reference_form=False)[1]
+        line["cpu_baseline"] = {
+            "value": round(1.0 / sec, 4), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"2 timed forwards of 1 pair {H_PAD}x{W_PAD} D={MAX_DISP} (1/{B} of a step) after 1 warm-up; "
+                      f"oracle port in reference form; the gather-form port runs at {1.0 / fast:.3f} frames/s",
+        }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,451 @@
+// Dense convolutions of the HITNetMF stereo path on NHWC fp32 activations.
+//
+// Replaces every nn.Conv2d / nn.ConvTranspose2d launch of
+//   model/stereo/hitnet/backbone.py:8-39,69-88
+//   model/stereo/hitnet/initialization.py:62-117,119-156
+//   model/stereo/hitnet/propagation.py:89-121,131-150,181-199,258-280,300-323
+// with one register-tiled direct-convolution kernel family:
+//   * CTA tile = 32 output columns x (4*PW) output rows x all output channels,
+//   * each thread owns 4 vertically adjacent pixels x CO_T output channels in registers,
+//   * input channels are streamed through shared memory 8 at a time (pixel-major, padded to
+//     12 floats so the 128-bit activation loads are bank-conflict free), weights for the same
+//     8 channels sit beside them as [tap][ci][co] and are read as warp-uniform broadcasts,
+//   * bias, residual add (full or single-channel broadcast) and the activation are fused into
+//     the epilogue; the "torch.cat" inputs of the reference are two source pointers.
+// fp32 FMA accumulation (tolerance-level parity with the reference, see tests/).
+#include "common.cuh"
+
+namespace {
+
+struct ConvP {
+    const float* in0;
+    const float* in1;
+    const float* w;
+    const float* bias;
+    const float* res;
+    float* out;
+    int N, H, W, C0, ld0, C1, ld1, Cout, ldo, ph, pw, Ho, Wo, act, ldr, res_bcast;
+    int tilesX, tilesY;
+    int vec0, vec1;  // 128-bit loads allowed on in0 / in1
+};
+
+constexpr int CK = 8;    // input channels per shared-memory stage
+constexpr int CP = 12;   // padded per-pixel stride of the stage (floats)
+constexpr int PX = 4;    // output rows per thread
+constexpr int TW = 32;   // output columns per CTA (one per lane)
+
+__device__ __forceinline__ float conv_load1(const ConvP& p, size_t pix, int c) {
+    if (c < p.C0) return __ldg(p.in0 + pix * p.ld0 + c);
+    c -= p.C0;
+    if (c < p.C1) return __ldg(p.in1 + pix * p.ld1 + c);
+    return 0.f;
+}
+
+__device__ __forceinline__ float4 conv_load4(const ConvP& p, size_t pix, int c) {
+    if (c + 3 < p.C0 && p.vec0) return ldg4(p.in0 + pix * p.ld0 + c);
+    if (c >= p.C0 && c - p.C0 + 3 < p.C1 && p.vec1 && ((c - p.C0) & 3) == 0)
+        return ldg4(p.in1 + pix * p.ld1 + (c - p.C0));
+    return make_float4(conv_load1(p, pix, c), conv_load1(p, pix, c + 1), conv_load1(p, pix, c + 2),
+                       conv_load1(p, pix, c + 3));
+}
+
+template <int KH, int KW, int SH, int SW, int DIL, int CO_T>
+__global__ void __launch_bounds__(256, 2) conv_nhwc_kernel(ConvP p) {
+    constexpr int IW = (TW - 1) * SW + (KW - 1) * DIL + 1;
+    const int lane = threadIdx.x, pwi = threadIdx.y, g = threadIdx.z;
+    const int PWn = blockDim.y, G = blockDim.z;
+    const int TH = PWn * PX;
+    const int IH = (TH - 1) * SH + (KH - 1) * DIL + 1;
+    const int COP = G * CO_T;
+    const int nthreads = 32 * PWn * G;
+    const int tid = (g * PWn + pwi) * 32 + lane;
+
+    extern __shared__ float4 smem4[];
+    float* s_in = reinterpret_cast<float*>(smem4);
+    float* s_w = s_in + IH * IW * CP;
+
+    int tile = blockIdx.x;
+    const int tx = tile % p.tilesX;
+    tile /= p.tilesX;
+    const int ty = tile % p.tilesY;
+    const int n = tile / p.tilesY;
+    const int oy0 = ty * TH, ox0 = tx * TW;
+    const int iy0 = oy0 * SH - p.ph, ix0 = ox0 * SW - p.pw;
+    const int Cin = p.C0 + p.C1;
+
+    float acc[PX][CO_T];
+#pragma unroll
+    for (int i = 0; i < PX; ++i)
+#pragma unroll
+        for (int j = 0; j < CO_T; ++j) acc[i][j] = 0.f;
+
+    const float* sa_base = s_in + ((pwi * PX * SH) * IW + lane * SW) * CP;
+
+    for (int c0 = 0; c0 < Cin; c0 += CK) {
+        __syncthreads();
+        // ---- stage activations: IH x IW pixels x 8 channels
+        for (int idx = tid; idx < IH * IW * 2; idx += nthreads) {
+            const int c4 = idx & 1;
+            const int pix = idx >> 1;
+            const int r = pix / IW, cc = pix - r * IW;
+            const int gy = iy0 + r, gx = ix0 + cc;
+            const int c = c0 + c4 * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W && c < Cin)
+                v = conv_load4(p, ((size_t)n * p.H + gy) * p.W + gx, c);
+            *reinterpret_cast<float4*>(s_in + pix * CP + c4 * 4) = v;
+        }
+        // ---- stage weights: [tap][ci][COP]
+        for (int idx = tid; idx < KH * KW * CK * COP; idx += nthreads) {
+            const int co = idx % COP;
+            const int t = idx / COP;
+            const int ci = t % CK, tap = t / CK;
+            float v = 0.f;
+            if (co < p.Cout && c0 + ci < Cin) v = __ldg(p.w + ((size_t)tap * Cin + c0 + ci) * p.Cout + co);
+            s_w[idx] = v;
+        }
+        __syncthreads();
+
+        // taps are NOT unrolled: one tap body is 8 ci x 4 px x CO_T FMAs, plenty of ILP, and
+        // keeping the loop rolled bounds live registers (no spills at 128 regs) and code size.
+#pragma unroll 1
+        for (int ky = 0; ky < KH; ++ky) {
+#pragma unroll 1
+            for (int kx = 0; kx < KW; ++kx) {
+                const float* sa = sa_base + ((ky * DIL) * IW + kx * DIL) * CP;
+                const float* sw = s_w + ((ky * KW + kx) * CK) * COP + g * CO_T;
+#pragma unroll
+                for (int c4 = 0; c4 < 2; ++c4) {
+                    float4 a[PX];
+#pragma unroll
+                    for (int i = 0; i < PX; ++i)
+                        a[i] = *reinterpret_cast<const float4*>(sa + i * SH * IW * CP + c4 * 4);
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+#pragma unroll
+                        for (int o4 = 0; o4 < CO_T / 4; ++o4) {
+                            const float4 wv = *reinterpret_cast<const float4*>(sw + (c4 * 4 + cc) * COP + o4 * 4);
+#pragma unroll
+                            for (int i = 0; i < PX; ++i) {
+                                const float av = cc == 0 ? a[i].x : cc == 1 ? a[i].y : cc == 2 ? a[i].z : a[i].w;
+                                acc[i][o4 * 4 + 0] = fmaf(av, wv.x, acc[i][o4 * 4 + 0]);
+                                acc[i][o4 * 4 + 1] = fmaf(av, wv.y, acc[i][o4 * 4 + 1]);
+                                acc[i][o4 * 4 + 2] = fmaf(av, wv.z, acc[i][o4 * 4 + 2]);
+                                acc[i][o4 * 4 + 3] = fmaf(av, wv.w, acc[i][o4 * 4 + 3]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- epilogue: bias + residual + activation, NHWC store
+    const int ox = ox0 + lane;
+    if (ox >= p.Wo) return;
+    const int cbase = g * CO_T;
+    const bool vec_out = ((p.ldo & 3) == 0) && ((((uintptr_t)p.out) & 15u) == 0);
+#pragma unroll
+    for (int i = 0; i < PX; ++i) {
+        const int oy = oy0 + pwi * PX + i;
+        if (oy >= p.Ho) continue;
+        const size_t opix = ((size_t)n * p.Ho + oy) * p.Wo + ox;
+        float* op = p.out + opix * p.ldo;
+        float rb = 0.f;
+        if (p.res && p.res_bcast) rb = __ldg(p.res + opix * p.ldr);
+#pragma unroll
+        for (int o4 = 0; o4 < CO_T / 4; ++o4) {
+            const int co = cbase + o4 * 4;
+            if (co >= p.Cout) break;
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float t = acc[i][o4 * 4 + e];
+                const int ce = co + e;
+                if (ce < p.Cout) {
+                    if (p.bias) t += __ldg(p.bias + ce);
+                    if (p.res) t += p.res_bcast ? rb : __ldg(p.res + opix * p.ldr + ce);
+                    t = codd_act(t, p.act, ce);
+                }
+                v[e] = t;
+            }
+            if (co + 3 < p.Cout && vec_out) {
+                *reinterpret_cast<float4*>(op + co) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (co + e < p.Cout) op[co + e] = v[e];
+            }
+        }
+    }
+}
+
+template <int KH, int KW, int SH, int SW, int DIL, int CO_T>
+int launch_conv(ConvP p, int PWn, int G, cudaStream_t stream) {
+    constexpr int IW = (TW - 1) * SW + (KW - 1) * DIL + 1;
+    auto smem_for = [&](int pw) {
+        const int IH = (pw * PX - 1) * SH + (KH - 1) * DIL + 1;
+        return (size_t)(IH * IW * CP + KH * KW * CK * G * CO_T) * sizeof(float);
+    };
+    // keep the stage under ~100 KB so two CTAs fit on an SM; shrink the row count if needed
+    while (PWn > 1 && smem_for(PWn) > 100 * 1024) PWn >>= 1;
+    // do not launch row-warps that would only see padding
+    while (PWn > 1 && (PWn / 2) * PX >= p.Ho) PWn >>= 1;
+    const size_t smem = smem_for(PWn);
+    if (smem > 227 * 1024) return CODD_E_UNSUPPORTED;
+    auto kern = conv_nhwc_kernel<KH, KW, SH, SW, DIL, CO_T>;
+    static size_t configured = 48 * 1024;  // per instantiation; set once so graph capture sees no API calls
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = smem;
+    }
+    p.tilesX = codd_ceil_div(p.Wo, TW);
+    p.tilesY = codd_ceil_div(p.Ho, PWn * PX);
+    dim3 block(32, PWn, G);
+    dim3 grid((unsigned)(p.tilesX * p.tilesY * p.N));
+    kern<<<grid, block, smem, stream>>>(p);
+    CODD_RETURN_IF_CUDA_ERROR();
+    return 0;
+}
+
+// FULL: instantiate the narrow per-thread channel tiles too (the geometries that see Cout in
+// {1,3,13,24,34}); the other geometries only ever run with Cout in {16,24,32} and pad to 16s.
+template <int KH, int KW, int SH, int SW, int DIL, bool FULL>
+int dispatch_cout(const ConvP& p, cudaStream_t s) {
+    const int co = p.Cout;
+    if constexpr (FULL) {
+        if (co <= 4) return launch_conv<KH, KW, SH, SW, DIL, 4>(p, 8, 1, s);
+        if (co <= 8) return launch_conv<KH, KW, SH, SW, DIL, 8>(p, 8, 1, s);
+        if (co > 16 && co <= 24) return launch_conv<KH, KW, SH, SW, DIL, 12>(p, 4, 2, s);
+        if (co > 32 && co <= 36) return launch_conv<KH, KW, SH, SW, DIL, 12>(p, 2, 3, s);
+    }
+    if (co <= 16) return launch_conv<KH, KW, SH, SW, DIL, 16>(p, 8, 1, s);
+    if (co <= 32) return launch_conv<KH, KW, SH, SW, DIL, 16>(p, 4, 2, s);
+    if (co <= 48) return launch_conv<KH, KW, SH, SW, DIL, 16>(p, 2, 3, s);
+    if (co <= 64) return launch_conv<KH, KW, SH, SW, DIL, 16>(p, 2, 4, s);
+    return CODD_E_UNSUPPORTED;
+}
+
+// ---------------------------------------------------------------------------------------------
+// first layer: NCHW image (3 ch) -> NHWC, 3x3 pad 1, LeakyReLU
+// ---------------------------------------------------------------------------------------------
+template <int CO>
+__global__ void __launch_bounds__(256) conv3x3_image_kernel(const float* __restrict__ left,
+                                                            const float* __restrict__ right, int n, int h,
+                                                            int w, const float* __restrict__ wgt,
+                                                            const float* __restrict__ bias, int cout,
+                                                            float* __restrict__ out, int ldo) {
+    __shared__ __align__(16) float s_w[27 * CO];
+    __shared__ float s_b[CO];
+    for (int i = threadIdx.x; i < 27 * CO; i += blockDim.x) {
+        const int co = i % CO, t = i / CO;
+        s_w[i] = co < cout ? wgt[t * cout + co] : 0.f;
+    }
+    for (int i = threadIdx.x; i < CO; i += blockDim.x) s_b[i] = i < cout ? bias[i] : 0.f;
+    __syncthreads();
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int s = blockIdx.z;  // sample in [0, 2n)
+    if (x >= w) return;
+    const float* img = (s < n ? left + (size_t)s * 3 * h * w : right + (size_t)(s - n) * 3 * h * w);
+    float acc[CO];
+#pragma unroll
+    for (int i = 0; i < CO; ++i) acc[i] = s_b[i];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int yy = y + ky - 1;
+        if (yy < 0 || yy >= h) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int xx = x + kx - 1;
+            if (xx < 0 || xx >= w) continue;
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) {
+                const float a = __ldg(img + ((size_t)ci * h + yy) * w + xx);
+                const float* wp = s_w + ((ky * 3 + kx) * 3 + ci) * CO;
+#pragma unroll
+                for (int o4 = 0; o4 < CO / 4; ++o4) {
+                    const float4 wv = *reinterpret_cast<const float4*>(wp + o4 * 4);
+                    acc[o4 * 4 + 0] = fmaf(a, wv.x, acc[o4 * 4 + 0]);
+                    acc[o4 * 4 + 1] = fmaf(a, wv.y, acc[o4 * 4 + 1]);
+                    acc[o4 * 4 + 2] = fmaf(a, wv.z, acc[o4 * 4 + 2]);
+                    acc[o4 * 4 + 3] = fmaf(a, wv.w, acc[o4 * 4 + 3]);
+                }
+            }
+        }
+    }
+    float* op = out + (((size_t)s * h + y) * w + x) * ldo;
+    if ((ldo & 3) == 0 && cout == CO && ((((uintptr_t)out) & 15u) == 0)) {
+#pragma unroll
+        for (int o4 = 0; o4 < CO / 4; ++o4)
+            *reinterpret_cast<float4*>(op + o4 * 4) =
+                make_float4(codd_act(acc[o4 * 4], CODD_ACT_LEAKY, 0), codd_act(acc[o4 * 4 + 1], CODD_ACT_LEAKY, 0),
+                            codd_act(acc[o4 * 4 + 2], CODD_ACT_LEAKY, 0), codd_act(acc[o4 * 4 + 3], CODD_ACT_LEAKY, 0));
+    } else {
+        for (int i = 0; i < cout; ++i) op[i] = codd_act(acc[i], CODD_ACT_LEAKY, 0);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ConvTranspose2d k=2 s=2: every output pixel sees exactly one input pixel and one of 4 taps
+// ---------------------------------------------------------------------------------------------
+template <int CO>
+__global__ void __launch_bounds__(256) deconv2x2_kernel(const float* __restrict__ in, int ldi, int n, int h,
+                                                        int w, int cin, const float* __restrict__ wgt,
+                                                        const float* __restrict__ bias, int cout,
+                                                        float* __restrict__ out, int ldo, int act) {
+    extern __shared__ float4 smem4[];
+    float* s_w = reinterpret_cast<float*>(smem4);  // [4][cin][CO]
+    for (int i = threadIdx.x; i < 4 * cin * CO; i += blockDim.x) {
+        const int co = i % CO, t = i / CO;
+        s_w[i] = co < cout ? wgt[(size_t)t * cout + co] : 0.f;
+    }
+    __syncthreads();
+    const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+    const int oy = blockIdx.y;
+    const int s = blockIdx.z;
+    if (ox >= 2 * w) return;
+    const int tap = (oy & 1) * 2 + (ox & 1);
+    const float* ip = in + (((size_t)s * h + (oy >> 1)) * w + (ox >> 1)) * ldi;
+    float acc[CO];
+#pragma unroll
+    for (int i = 0; i < CO; ++i) acc[i] = 0.f;
+    const float* wt = s_w + tap * cin * CO;
+    for (int ci = 0; ci < cin; ci += 4) {
+        const float4 a4 = ldg4(ip + ci);
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const float a = cc == 0 ? a4.x : cc == 1 ? a4.y : cc == 2 ? a4.z : a4.w;
+            const float* wp = wt + (ci + cc) * CO;
+#pragma unroll
+            for (int o4 = 0; o4 < CO / 4; ++o4) {
+                const float4 wv = *reinterpret_cast<const float4*>(wp + o4 * 4);
+                acc[o4 * 4 + 0] = fmaf(a, wv.x, acc[o4 * 4 + 0]);
+                acc[o4 * 4 + 1] = fmaf(a, wv.y, acc[o4 * 4 + 1]);
+                acc[o4 * 4 + 2] = fmaf(a, wv.z, acc[o4 * 4 + 2]);
+                acc[o4 * 4 + 3] = fmaf(a, wv.w, acc[o4 * 4 + 3]);
+            }
+        }
+    }
+    float* op = out + (((size_t)s * 2 * h + oy) * 2 * w + ox) * ldo;
+    for (int i = 0; i < cout; ++i) op[i] = codd_act(acc[i] + __ldg(bias + i), act, i);
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout helpers
+// ---------------------------------------------------------------------------------------------
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, int ldi, int hw, int c, float* __restrict__ out,
+                                    size_t total) {
+    // one thread per output element; reads are strided by ldi but hit the same lines across c
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const size_t pix = i % hw;
+    const size_t t = i / hw;
+    const int ch = (int)(t % c);
+    const size_t s = t / c;
+    out[i] = __ldg(in + (s * hw + pix) * ldi + ch);
+}
+
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, int c, int hw, float* __restrict__ out, int ldo,
+                                    size_t total) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over n*hw*c, c fastest
+    if (i >= total) return;
+    const int ch = (int)(i % c);
+    const size_t t = i / c;
+    const size_t pix = t % hw;
+    const size_t s = t / hw;
+    out[(s * hw + pix) * ldo + ch] = __ldg(in + (s * c + ch) * hw + pix);
+}
+
+}  // namespace
+
+extern "C" int codd_conv2d_nhwc(const codd_conv_desc* d, const float* in0, const float* in1, const float* weight,
+                                const float* bias, const float* residual, float* out, void* stream) {
+    if (!d || !in0 || !weight || !out) return CODD_E_BADARG;
+    if (d->n <= 0 || d->h <= 0 || d->w <= 0 || d->c0 <= 0 || d->cout <= 0 || d->ho <= 0 || d->wo <= 0)
+        return CODD_E_BADARG;
+    if (d->c1 > 0 && !in1) return CODD_E_BADARG;
+    if (d->ld0 < d->c0 || (d->c1 > 0 && d->ld1 < d->c1) || d->ldo < d->cout) return CODD_E_SHAPE;
+    if (residual && d->ldr < (d->res_bcast ? 1 : d->cout)) return CODD_E_SHAPE;
+    // implied bottom/right extent must be consistent with a zero-padded convolution
+    if ((d->ho - 1) * d->sh - d->ph + (d->kh - 1) * d->dil < 0) return CODD_E_SHAPE;
+    ConvP p;
+    p.in0 = in0;
+    p.in1 = d->c1 > 0 ? in1 : nullptr;
+    p.w = weight;
+    p.bias = bias;
+    p.res = residual;
+    p.out = out;
+    p.N = d->n; p.H = d->h; p.W = d->w;
+    p.C0 = d->c0; p.ld0 = d->ld0;
+    p.C1 = d->c1 > 0 ? d->c1 : 0; p.ld1 = d->ld1;
+    p.Cout = d->cout; p.ldo = d->ldo;
+    p.ph = d->ph; p.pw = d->pw; p.Ho = d->ho; p.Wo = d->wo;
+    p.act = d->act; p.ldr = d->ldr; p.res_bcast = d->res_bcast;
+    p.tilesX = p.tilesY = 0;
+    p.vec0 = codd_aligned16(in0) && (d->ld0 % 4 == 0);
+    p.vec1 = p.in1 && codd_aligned16(in1) && (d->ld1 % 4 == 0) && (d->c0 % 4 == 0);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int kh = d->kh, kw = d->kw, sh = d->sh, sw = d->sw, dil = d->dil;
+    if (kh == 1 && kw == 1 && sh == 1 && sw == 1) return dispatch_cout<1, 1, 1, 1, 1, true>(p, s);
+    if (kh == 3 && kw == 3 && sh == 1 && sw == 1 && dil == 1) return dispatch_cout<3, 3, 1, 1, 1, true>(p, s);
+    if (kh == 3 && kw == 3 && sh == 1 && sw == 1 && dil == 3) return dispatch_cout<3, 3, 1, 1, 3, false>(p, s);
+    if (kh == 4 && kw == 4 && sh == 2 && sw == 2 && dil == 1) return dispatch_cout<4, 4, 2, 2, 1, false>(p, s);
+    if (kh == 4 && kw == 4 && sh == 4 && sw == 4 && dil == 1) return dispatch_cout<4, 4, 4, 4, 1, false>(p, s);
+    if (kh == 4 && kw == 4 && sh == 4 && sw == 1 && dil == 1) return dispatch_cout<4, 4, 4, 1, 1, false>(p, s);
+    if (kh == 7 && kw == 7 && sh == 1 && sw == 1 && dil == 1) return dispatch_cout<7, 7, 1, 1, 1, false>(p, s);
+    return CODD_E_UNSUPPORTED;
+}
+
+extern "C" int codd_conv3x3_image(const float* left, const float* right, int n, int h, int w, const float* weight,
+                                  const float* bias, int cout, float* out, int ldo, void* stream) {
+    if (!left || !weight || !bias || !out || n <= 0 || h <= 0 || w <= 0) return CODD_E_BADARG;
+    if (cout <= 0 || cout > 16 || ldo < cout) return CODD_E_SHAPE;
+    dim3 block(128);
+    dim3 grid(codd_ceil_div(w, 128), h, right ? 2 * n : n);
+    conv3x3_image_kernel<16><<<grid, block, 0, (cudaStream_t)stream>>>(left, right ? right : left, n, h, w, weight,
+                                                                        bias, cout, out, ldo);
+    CODD_RETURN_IF_CUDA_ERROR();
+    return 0;
+}
+
+extern "C" int codd_deconv2x2_nhwc(const float* in, int ldi, int n, int h, int w, int cin, const float* weight,
+                                   const float* bias, int cout, float* out, int ldo, int act, void* stream) {
+    if (!in || !weight || !bias || !out || n <= 0 || h <= 0 || w <= 0 || cin <= 0 || cout <= 0) return CODD_E_BADARG;
+    if (cin % 4 != 0 || ldi % 4 != 0 || ldi < cin || ldo < cout || cout > 32) return CODD_E_SHAPE;
+    if (!codd_aligned16(in)) return CODD_E_ALIGN;
+    dim3 block(128);
+    dim3 grid(codd_ceil_div(2 * w, 128), 2 * h, n);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (cout <= 16) {
+        deconv2x2_kernel<16><<<grid, block, 4 * cin * 16 * sizeof(float), s>>>(in, ldi, n, h, w, cin, weight, bias,
+                                                                                 cout, out, ldo, act);
+    } else if (cout <= 24) {
+        deconv2x2_kernel<24><<<grid, block, 4 * cin * 24 * sizeof(float), s>>>(in, ldi, n, h, w, cin, weight, bias,
+                                                                                 cout, out, ldo, act);
+    } else {
+        deconv2x2_kernel<32><<<grid, block, 4 * cin * 32 * sizeof(float), s>>>(in, ldi, n, h, w, cin, weight, bias,
+                                                                                 cout, out, ldo, act);
+    }
+    CODD_RETURN_IF_CUDA_ERROR();
+    return 0;
+}
+
+extern "C" int codd_nhwc_to_nchw(const float* in, int ldi, int n, int h, int w, int c, float* out, void* stream) {
+    if (!in || !out || n <= 0 || h <= 0 || w <= 0 || c <= 0 || ldi < c) return CODD_E_BADARG;
+    const size_t total = (size_t)n * c * h * w;
+    nhwc_to_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, ldi, h * w, c, out,
+                                                                                            total);
+    CODD_RETURN_IF_CUDA_ERROR();
+    return 0;
+}
+
+extern "C" int codd_nchw_to_nhwc(const float* in, int n, int c, int h, int w, float* out, int ldo, void* stream) {
+    if (!in || !out || n <= 0 || h <= 0 || w <= 0 || c <= 0 || ldo < c) return CODD_E_BADARG;
+    const size_t total = (size_t)n * c * h * w;
+    nchw_to_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, c, h * w, out, ldo,
+                                                                                            total);
+    CODD_RETURN_IF_CUDA_ERROR();
+    return 0;
+}

@@ -1,0 +1,428 @@
+// Tile-hypothesis kernels of HITNet's propagation stage (NHWC fp32).
+//
+//   K3  plane_upsample     propagation.py:10-32   (to_plane / upsample)
+//   K4  tile_warp_cost     propagation.py:35-86 (warp, TileWarping), :156-160, :206-219
+//   K5  hyp_select         propagation.py:225-248
+//   --  tile_hyp_init      initialization.py:186-208 (descriptor 1x1 conv + hypothesis concat)
+//
+// The discrete decisions downstream (arg-max of the two confidences) amplify ulp noise, so the
+// sampling arithmetic of K4 restates the reference + torch grid_sample rounding sequence exactly
+// (see oracle/hitnet_oracle.py: warp_coords / warp_right_direct, which is bit-identical to
+// F.grid_sample on CPU): explicit __f*_rn intrinsics, no FMA contraction except where torch's own
+// kernel uses fused multiply-adds (the 4-tap blend).
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// tile_hyp_init
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) tile_hyp_init_kernel(const float* __restrict__ min_cost,
+                                                            const float* __restrict__ min_disp,
+                                                            const float* __restrict__ feat, int ldf, int cf,
+                                                            const float* __restrict__ wgt,
+                                                            const float* __restrict__ bias, size_t npix,
+                                                            float* __restrict__ hyp, int ldh) {
+    extern __shared__ float4 smem4[];
+    float* s_w = reinterpret_cast<float*>(smem4);  // [1+cf][16] transposed, 13 used
+    const int cin = 1 + cf;
+    for (int i = threadIdx.x; i < cin * 16; i += blockDim.x) {
+        const int co = i & 15, ci = i >> 4;
+        s_w[i] = co < 13 ? wgt[co * cin + ci] : 0.f;
+    }
+    __syncthreads();
+    const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= npix) return;
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = i < 13 ? __ldg(bias + i) : 0.f;
+    const float c = __ldg(min_cost + pix);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = fmaf(c, s_w[i], acc[i]);
+    const float* fp = feat + pix * ldf;
+    for (int ci = 0; ci < cf; ci += 4) {
+        const float4 a4 = ldg4(fp + ci);
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const float a = cc == 0 ? a4.x : cc == 1 ? a4.y : cc == 2 ? a4.z : a4.w;
+            const float* wp = s_w + (1 + ci + cc) * 16;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = fmaf(a, wp[i], acc[i]);
+        }
+    }
+    float o[16];
+    o[0] = __ldg(min_disp + pix);
+    o[1] = 0.f;
+    o[2] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 13; ++i) o[3 + i] = codd_act(acc[i], CODD_ACT_LEAKY, 0);
+    float4* op = reinterpret_cast<float4*>(hyp + pix * ldh);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) op[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+}
+
+// ------------------------------------------------------------------------------------------
+// K3 plane_upsample
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) plane_upsample_kernel(const float* __restrict__ in, int ldi, int n, int h,
+                                                             int w, int size, float scale,
+                                                             float* __restrict__ out, int ldo) {
+    const size_t total = (size_t)n * h * size * w * size * 4;  // float4 granules
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c4 = (int)(idx & 3);
+    size_t pix = idx >> 2;
+    const int ow = w * size, oh = h * size;
+    const int x = (int)(pix % ow);
+    const size_t t = pix / ow;
+    const int y = (int)(t % oh);
+    const int s = (int)(t / oh);
+    const float* ip = in + (((size_t)s * h + y / size) * w + x / size) * ldi;
+    float4 v = ldg4(ip + c4 * 4);
+    if (c4 == 0) {
+        const float half = 0.5f * (float)(size - 1);
+        const float cx = (float)(x % size) - half;
+        const float cy = (float)(y % size) - half;
+        // (d + cx*dx) + cy*dy, then * scale  — multiply and add rounded separately
+        const float d = __fadd_rn(__fadd_rn(v.x, __fmul_rn(cx, v.y)), __fmul_rn(cy, v.z));
+        v.x = __fmul_rn(d, scale);
+    }
+    *reinterpret_cast<float4*>(out + pix * ldo + c4 * 4) = v;
+}
+
+// ------------------------------------------------------------------------------------------
+// K4 tile_warp_cost
+// ------------------------------------------------------------------------------------------
+struct WarpP {
+    const float* fl;
+    const float* fr;
+    int ldfl, ldfr, C;
+    const float* cur;
+    int ldc;
+    const float* prev;
+    int ldp;
+    const float* dec_w;
+    const float* dec_b;
+    int N, h, w;
+    float* aug;
+    int ldaug;
+    float* raw;
+};
+
+constexpr int K4_TILES = 16;              // tile columns per CTA
+constexpr int K4_PXW = K4_TILES * 4;      // pixel columns per CTA
+constexpr int K4_THREADS = K4_PXW * 4;    // one thread per pixel of the 4-row strip
+
+struct Taps {
+    // sampling state of one hypothesis plane at one pixel (k = -1, 0, +1)
+    int x0[3];
+    float fw[3], fe[3];
+};
+
+__device__ __forceinline__ void sample_setup(float d, float dx, float dy, float a, float b, int x, float wm1,
+                                             float wdiv, Taps& t) {
+#pragma unroll
+    for (int ki = 0; ki < 3; ++ki) {
+        const float k = (float)(ki - 1);
+        // Eq.(5): ((d + k) + a*dx) + b*dy
+        const float ld = __fadd_rn(__fadd_rn(__fadd_rn(d, k), __fmul_rn(a, dx)), __fmul_rn(b, dy));
+        // reference warp(): 2*(x - d)/max(W-1,1) - 1 ; grid_sample: ((g+1)/2)*(W-1)
+        const float g = __fadd_rn(__fdiv_rn(__fmul_rn(2.f, __fsub_rn((float)x, ld)), wdiv), -1.f);
+        const float ix = __fmul_rn(__fmul_rn(__fadd_rn(g, 1.f), 0.5f), wm1);
+        const float fx = floorf(ix);
+        t.fw[ki] = __fsub_rn(ix, fx);
+        t.fe[ki] = __fsub_rn(1.f, t.fw[ki]);
+        // clamp before the int conversion: anything outside [-2, W] samples only zeros anyway
+        t.x0[ki] = (int)fminf(fmaxf(fx, -2.f), wm1 + 1.f);
+    }
+}
+
+__device__ __forceinline__ float4 ld_tap(const float* rowp, int x, int W, int ld, int c) {
+    if (x < 0 || x >= W) return make_float4(0.f, 0.f, 0.f, 0.f);
+    return ldg4(rowp + (size_t)x * ld + c);
+}
+
+__device__ __forceinline__ float blend2(float A, float B, float nw, float ne) {
+    return __fmaf_rn(B, ne, __fmul_rn(A, nw));
+}
+
+__device__ __forceinline__ void acc_abs4(float& acc, const float4& l, const float4& v) {
+    acc = __fadd_rn(acc, fabsf(__fsub_rn(l.x, v.x)));
+    acc = __fadd_rn(acc, fabsf(__fsub_rn(l.y, v.y)));
+    acc = __fadd_rn(acc, fabsf(__fsub_rn(l.z, v.z)));
+    acc = __fadd_rn(acc, fabsf(__fsub_rn(l.w, v.w)));
+}
+
+template <int NSETS>
+__global__ void __launch_bounds__(K4_THREADS) tile_warp_cost_kernel(WarpP p) {
+    __shared__ __align__(16) float s_raw[NSETS][K4_TILES][64];
+    __shared__ __align__(16) float s_dec[NSETS][K4_TILES][16];
+    __shared__ __align__(16) float s_wt[64][16];
+    __shared__ float s_b[16];
+
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 64 * 16; i += K4_THREADS) {
+        const int co = i & 15, ci = i >> 4;
+        s_wt[ci][co] = __ldg(p.dec_w + co * 64 + ci);
+    }
+    if (tid < 16) s_b[tid] = __ldg(p.dec_b + tid);
+
+    const int nblk = (p.w + K4_TILES - 1) / K4_TILES;
+    int b = blockIdx.x;
+    const int jblk = b % nblk;
+    b /= nblk;
+    const int i = b % p.h;
+    const int n = b / p.h;
+    const int j0 = jblk * K4_TILES;
+
+    const int yo = tid / K4_PXW;
+    const int tx = tid - yo * K4_PXW;
+    const int tl = tx >> 2, xo = tx & 3;
+    const int j = j0 + tl;
+    const int H = 4 * p.h, W = 4 * p.w;
+    const int y = 4 * i + yo, x = 4 * j + xo;
+    const bool on = j < p.w;
+
+    if (on) {
+        const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
+        const float wdiv = (float)max(W - 1, 1), hdiv = (float)max(H - 1, 1);
+        // row coordinate through the same normalise / un-normalise round trip
+        const float gy = __fadd_rn(__fdiv_rn(__fmul_rn(2.f, (float)y), hdiv), -1.f);
+        const float iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.f), 0.5f), hm1);
+        const float fy = floorf(iy);
+        const float fn = __fsub_rn(iy, fy);
+        const float fs = __fsub_rn(1.f, fn);
+        const int y0 = (int)fy;
+        const bool two_rows = fn != 0.f;
+
+        const float a = (float)xo - 1.5f, bb = (float)yo - 1.5f;
+        Taps tp[NSETS];
+        {
+            const float4 c4 = ldg4(p.cur + (((size_t)n * p.h + i) * p.w + j) * p.ldc);
+            sample_setup(c4.x, c4.y, c4.z, a, bb, x, wm1, wdiv, tp[0]);
+        }
+        if (NSETS == 2) {
+            const int hp = p.h >> 1, wp = p.w >> 1;
+            const float4 q4 = ldg4(p.prev + (((size_t)n * hp + (i >> 1)) * wp + (j >> 1)) * p.ldp);
+            const float cx = (float)(j & 1) - 0.5f, cy = (float)(i & 1) - 0.5f;
+            const float du = __fmul_rn(__fadd_rn(__fadd_rn(q4.x, __fmul_rn(cx, q4.y)), __fmul_rn(cy, q4.z)), 2.f);
+            sample_setup(du, q4.y, q4.z, a, bb, x, wm1, wdiv, tp[NSETS - 1]);
+        }
+
+        const float* flp = p.fl + (((size_t)n * H + y) * W + x) * p.ldfl;
+        const float* r0 = (y0 >= 0 && y0 < H) ? p.fr + ((size_t)n * H + y0) * W * p.ldfr : nullptr;
+        const float* r1 = (two_rows && y0 + 1 >= 0 && y0 + 1 < H) ? p.fr + ((size_t)n * H + y0 + 1) * W * p.ldfr : nullptr;
+
+        float cost[NSETS][3];
+        float wnw[NSETS][3], wne[NSETS][3], wsw[NSETS][3], wse[NSETS][3];
+        bool shared_win[NSETS];
+#pragma unroll
+        for (int s = 0; s < NSETS; ++s) {
+#pragma unroll
+            for (int ki = 0; ki < 3; ++ki) {
+                cost[s][ki] = 0.f;
+                wnw[s][ki] = __fmul_rn(fs, tp[s].fe[ki]);
+                wne[s][ki] = __fmul_rn(fs, tp[s].fw[ki]);
+                wsw[s][ki] = __fmul_rn(fn, tp[s].fe[ki]);
+                wse[s][ki] = __fmul_rn(fn, tp[s].fw[ki]);
+            }
+            // k = +1 samples furthest left; normally x0(k=0) = x0(+1)+1 and x0(-1) = x0(+1)+2
+            shared_win[s] = (tp[s].x0[1] == tp[s].x0[2] + 1) && (tp[s].x0[0] == tp[s].x0[2] + 2);
+        }
+        float lnorm = 0.f;
+
+        for (int c = 0; c < p.C; c += 4) {
+            const float4 l4 = ldg4(flp + c);
+            lnorm = __fadd_rn(lnorm, fabsf(l4.x));
+            lnorm = __fadd_rn(lnorm, fabsf(l4.y));
+            lnorm = __fadd_rn(lnorm, fabsf(l4.z));
+            lnorm = __fadd_rn(lnorm, fabsf(l4.w));
+#pragma unroll
+            for (int s = 0; s < NSETS; ++s) {
+                float4 wn[4], ws[4];   // window taps x0(+1) .. x0(+1)+3 on rows y0 / y0+1
+                const int xb = tp[s].x0[2];
+                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (shared_win[s]) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        wn[e] = r0 ? ld_tap(r0, xb + e, W, p.ldfr, c) : z4;
+                        ws[e] = r1 ? ld_tap(r1, xb + e, W, p.ldfr, c) : z4;
+                    }
+                }
+#pragma unroll
+                for (int ki = 0; ki < 3; ++ki) {
+                    float4 A, B, Cc, Dd;
+                    if (shared_win[s]) {
+                        A = wn[2 - ki]; B = wn[3 - ki]; Cc = ws[2 - ki]; Dd = ws[3 - ki];
+                    } else {
+                        const int xx = tp[s].x0[ki];
+                        A = r0 ? ld_tap(r0, xx, W, p.ldfr, c) : z4;
+                        B = r0 ? ld_tap(r0, xx + 1, W, p.ldfr, c) : z4;
+                        Cc = r1 ? ld_tap(r1, xx, W, p.ldfr, c) : z4;
+                        Dd = r1 ? ld_tap(r1, xx + 1, W, p.ldfr, c) : z4;
+                    }
+                    float4 v;
+                    v.x = blend2(A.x, B.x, wnw[s][ki], wne[s][ki]);
+                    v.y = blend2(A.y, B.y, wnw[s][ki], wne[s][ki]);
+                    v.z = blend2(A.z, B.z, wnw[s][ki], wne[s][ki]);
+                    v.w = blend2(A.w, B.w, wnw[s][ki], wne[s][ki]);
+                    if (two_rows) {
+                        v.x = __fmaf_rn(Dd.x, wse[s][ki], __fmaf_rn(Cc.x, wsw[s][ki], v.x));
+                        v.y = __fmaf_rn(Dd.y, wse[s][ki], __fmaf_rn(Cc.y, wsw[s][ki], v.y));
+                        v.z = __fmaf_rn(Dd.z, wse[s][ki], __fmaf_rn(Cc.z, wsw[s][ki], v.z));
+                        v.w = __fmaf_rn(Dd.w, wse[s][ki], __fmaf_rn(Cc.w, wsw[s][ki], v.w));
+                    }
+                    acc_abs4(cost[s][ki], l4, v);
+                }
+            }
+        }
+        const int po = yo * 4 + xo;
+#pragma unroll
+        for (int s = 0; s < NSETS; ++s) {
+            s_raw[s][tl][po] = lnorm;
+#pragma unroll
+            for (int ki = 0; ki < 3; ++ki) s_raw[s][tl][16 + ki * 16 + po] = cost[s][ki];
+        }
+    }
+    __syncthreads();
+
+    // ---- `decrease`: 1x1 conv 64 -> 16 + LeakyReLU per tile and set
+    for (int o = tid; o < NSETS * K4_TILES * 16; o += K4_THREADS) {
+        const int co = o & 15;
+        const int t = (o >> 4) % K4_TILES;
+        const int s = o / (16 * K4_TILES);
+        if (j0 + t < p.w) {
+            float acc = s_b[co];
+            const float* rp = s_raw[s][t];
+#pragma unroll 16
+            for (int ci = 0; ci < 64; ++ci) acc = fmaf(rp[ci], s_wt[ci][co], acc);
+            s_dec[s][t][co] = codd_act(acc, CODD_ACT_LEAKY, 0);
+        }
+    }
+    __syncthreads();
+
+    // ---- write the augmented hypothesis tensor: [cur | cur_cv | up_prev | prev_cv]
+    const int nf4 = NSETS * 8;  // float4 granules per tile
+    for (int o = tid; o < K4_TILES * nf4; o += K4_THREADS) {
+        const int t = o / nf4, f = o - t * nf4;
+        const int jj = j0 + t;
+        if (jj >= p.w) continue;
+        const size_t tpix = ((size_t)n * p.h + i) * p.w + jj;
+        float4 v;
+        if (f < 4) {
+            v = ldg4(p.cur + tpix * p.ldc + f * 4);
+        } else if (f < 8) {
+            v = *reinterpret_cast<const float4*>(&s_dec[0][t][(f - 4) * 4]);
+        } else if (f < 12) {
+            const int hp = p.h >> 1, wp = p.w >> 1;
+            v = ldg4(p.prev + (((size_t)n * hp + (i >> 1)) * wp + (jj >> 1)) * p.ldp + (f - 8) * 4);
+            if (f == 8) {
+                const float cx = (float)(jj & 1) - 0.5f, cy = (float)(i & 1) - 0.5f;
+                v.x = __fmul_rn(__fadd_rn(__fadd_rn(v.x, __fmul_rn(cx, v.y)), __fmul_rn(cy, v.z)), 2.f);
+            }
+        } else {
+            v = *reinterpret_cast<const float4*>(&s_dec[NSETS - 1][t][(f - 12) * 4]);
+        }
+        *reinterpret_cast<float4*>(p.aug + tpix * p.ldaug + f * 4) = v;
+    }
+    if (p.raw) {
+        for (int o = tid; o < K4_TILES * NSETS * 16; o += K4_THREADS) {
+            const int t = o / (NSETS * 16), f = o - t * (NSETS * 16);
+            const int jj = j0 + t;
+            if (jj >= p.w) continue;
+            const size_t tpix = ((size_t)n * p.h + i) * p.w + jj;
+            const int s = f >> 4, e = f & 15;
+            *reinterpret_cast<float4*>(p.raw + tpix * (NSETS * 64) + f * 4) =
+                *reinterpret_cast<const float4*>(&s_raw[s][t][e * 4]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K5 hyp_select
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) hyp_select_kernel(const float* __restrict__ upd, int ldu,
+                                                         const float* __restrict__ aug, int ldaug, size_t npix,
+                                                         float* __restrict__ out, int ldr) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= npix * 4) return;
+    const int c4 = (int)(idx & 3);
+    const size_t pix = idx >> 2;
+    const float* u = upd + pix * ldu;
+    const float conf_prev = __ldg(u), conf_cur = __ldg(u + 1);
+    const bool take_cur = conf_cur > conf_prev;  // arg-max, first index (previous) on ties
+    const float* hyp = aug + pix * ldaug + (take_cur ? 0 : 32) + c4 * 4;
+    const float* del = u + (take_cur ? 18 : 2) + c4 * 4;
+    const float4 hv = ldg4(hyp);
+    float4 r;
+    r.x = __fadd_rn(hv.x, __ldg(del));
+    r.y = __fadd_rn(hv.y, __ldg(del + 1));
+    r.z = __fadd_rn(hv.z, __ldg(del + 2));
+    r.w = __fadd_rn(hv.w, __ldg(del + 3));
+    if (c4 == 0) r.x = fmaxf(r.x, 0.f);
+    *reinterpret_cast<float4*>(out + pix * ldr + c4 * 4) = r;
+}
+
+}  // namespace
+
+extern "C" int codd_tile_hyp_init(const float* min_cost, const float* min_disp, const float* feat, int ldf, int cf,
+                                  const float* weight, const float* bias, int n, int h, int w, float* hyp, int ldh,
+                                  void* stream) {
+    if (!min_cost || !min_disp || !feat || !weight || !bias || !hyp || n <= 0 || h <= 0 || w <= 0) return CODD_E_BADARG;
+    if (cf <= 0 || cf % 4 != 0 || cf > 64 || ldf < cf || ldf % 4 != 0 || ldh < 16 || ldh % 4 != 0) return CODD_E_SHAPE;
+    if (!codd_aligned16(feat) || !codd_aligned16(hyp)) return CODD_E_ALIGN;
+    const size_t npix = (size_t)n * h * w;
+    const size_t smem = (size_t)(1 + cf) * 16 * sizeof(float);
+    tile_hyp_init_kernel<<<(unsigned)((npix + 127) / 128), 128, smem, (cudaStream_t)stream>>>(
+        min_cost, min_disp, feat, ldf, cf, weight, bias, npix, hyp, ldh);
+    CODD_RETURN_IF_CUDA_ERROR();
+    return 0;
+}
+
+extern "C" int codd_plane_upsample(const float* in, int ldi, int n, int h, int w, int size, float scale, float* out,
+                                   int ldo, void* stream) {
+    if (!in || !out || n <= 0 || h <= 0 || w <= 0 || size <= 0) return CODD_E_BADARG;
+    if (ldi < 16 || ldo < 16 || ldi % 4 != 0 || ldo % 4 != 0) return CODD_E_SHAPE;
+    if (!codd_aligned16(in) || !codd_aligned16(out)) return CODD_E_ALIGN;
+    const size_t total = (size_t)n * h * size * w * size * 4;
+    plane_upsample_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, ldi, n, h, w, size,
+                                                                                              scale, out, ldo);
+    CODD_RETURN_IF_CUDA_ERROR();
+    return 0;
+}
+
+extern "C" int codd_tile_warp_cost(const float* fea_l, int ldfl, const float* fea_r, int ldfr, int c,
+                                   const float* cur, int ldc, const float* prev, int ldp, const float* dec_w,
+                                   const float* dec_b, int n, int h, int w, float* aug, int ldaug, float* raw_cv,
+                                   void* stream) {
+    if (!fea_l || !fea_r || !cur || !dec_w || !dec_b || !aug || n <= 0 || h <= 0 || w <= 0) return CODD_E_BADARG;
+    if (c <= 0 || c % 4 != 0 || ldfl < c || ldfr < c || ldfl % 4 || ldfr % 4 || ldc < 16 || ldc % 4) return CODD_E_SHAPE;
+    if (prev && (ldp < 16 || ldp % 4 || (h & 1) || (w & 1))) return CODD_E_SHAPE;
+    if (ldaug < (prev ? 64 : 32) || ldaug % 4) return CODD_E_SHAPE;
+    if (!codd_aligned16(fea_l) || !codd_aligned16(fea_r) || !codd_aligned16(cur) || !codd_aligned16(aug) ||
+        (prev && !codd_aligned16(prev)) || (raw_cv && !codd_aligned16(raw_cv)))
+        return CODD_E_ALIGN;
+    WarpP p;
+    p.fl = fea_l; p.fr = fea_r; p.ldfl = ldfl; p.ldfr = ldfr; p.C = c;
+    p.cur = cur; p.ldc = ldc; p.prev = prev; p.ldp = ldp;
+    p.dec_w = dec_w; p.dec_b = dec_b; p.N = n; p.h = h; p.w = w;
+    p.aug = aug; p.ldaug = ldaug; p.raw = raw_cv;
+    const int nblk = codd_ceil_div(w, K4_TILES);
+    dim3 grid((unsigned)(n * h * nblk)), block(K4_THREADS);
+    if (prev) tile_warp_cost_kernel<2><<<grid, block, 0, (cudaStream_t)stream>>>(p);
+    else tile_warp_cost_kernel<1><<<grid, block, 0, (cudaStream_t)stream>>>(p);
+    CODD_RETURN_IF_CUDA_ERROR();
+    return 0;
+}
+
+extern "C" int codd_hyp_select(const float* update, int ldu, const float* aug, int ldaug, int n, int h, int w,
+                               float* refined, int ldr, void* stream) {
+    if (!update || !aug || !refined || n <= 0 || h <= 0 || w <= 0) return CODD_E_BADARG;
+    if (ldu < 34 || ldaug < 64 || ldaug % 4 || ldr < 16 || ldr % 4) return CODD_E_SHAPE;
+    if (!codd_aligned16(aug) || !codd_aligned16(refined)) return CODD_E_ALIGN;
+    const size_t npix = (size_t)n * h * w;
+    hyp_select_kernel<<<(unsigned)((npix * 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(update, ldu, aug, ldaug,
+                                                                                           npix, refined, ldr);
+    CODD_RETURN_IF_CUDA_ERROR();
+    return 0;
+}

@@ -1,0 +1,286 @@
+"""Tensor-level wrappers over the C ABI.
+
+Every function takes / returns torch CUDA tensors whose *logical* shape is the reference's
+NCHW but whose memory is NHWC (``torch.channels_last``, possibly a channel slice of a wider
+buffer).  Torch is used for allocation, streams and nothing else: all arithmetic happens in
+``libcodd_b200.so``.  Non-CUDA inputs raise — there is no CPU path.
+"""
+import ctypes
+
+import torch
+
+from . import lib as _lib
+from .lib import ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_RELU_CH0, ConvDesc  # noqa: F401
+
+LAUNCHES = [0]  # kernels launched through this module (bench.py reports it as gpu_launches)
+PROFILE = None   # when a list: (tag, algorithmic bytes, start event, end event) per launch
+
+
+def _run(tag, nbytes, call):
+    """Launch bookkeeping: counts the launch and, in a profiling pass, brackets it with CUDA
+    events on the launching stream (torch's current stream)."""
+    LAUNCHES[0] += 1
+    if PROFILE is None:
+        return call()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    rc = call()
+    e.record()
+    PROFILE.append((tag, nbytes, s, e))
+    return rc
+
+
+class profile:
+    """``with ops.profile() as p:`` ... ``p.summary()`` -> per-kernel time / algorithmic bytes."""
+
+    def __enter__(self):
+        global PROFILE
+        self.records = PROFILE = []
+        return self
+
+    def __exit__(self, *exc):
+        global PROFILE
+        PROFILE = None
+        return False
+
+    def summary(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for tag, nbytes, s, e in self.records:
+            a = agg.setdefault(tag, dict(kernel=tag, launches=0, ms=0.0, bytes=0))
+            a["launches"] += 1
+            a["ms"] += s.elapsed_time(e)
+            a["bytes"] += nbytes
+        return sorted(agg.values(), key=lambda a: -a["ms"])
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and (not t.is_cuda or t.dtype != torch.float32):
+            raise _lib.CoddError("codd_b200 ops need float32 CUDA tensors (no CPU fallback)")
+
+
+def empty_nhwc(n, c, h, w, device, ld=None):
+    """Logical [n,c,h,w] tensor backed by NHWC memory with pixel stride ``ld`` (default c)."""
+    ld = c if ld is None else ld
+    buf = torch.empty((n, h, w, ld), device=device, dtype=torch.float32)
+    t = buf.permute(0, 3, 1, 2)
+    return t if ld == c else t[:, :c]
+
+
+def ld_of(t):
+    """Pixel stride of an NHWC-backed logical-NCHW tensor (validates the layout)."""
+    n, c, h, w = t.shape
+    s = t.stride()
+    if c > 1 and s[1] != 1:
+        raise _lib.CoddError(f"tensor is not NHWC-backed (strides {s}); call ops.to_nhwc first")
+    if w > 1:
+        ld = s[3]
+    elif h > 1:
+        ld = s[2]
+    elif n > 1:
+        ld = s[0]
+    else:
+        ld = c
+    ok = (w == 1 or s[3] == ld) and (h == 1 or s[2] == w * ld) and (n == 1 or s[0] == h * w * ld) and ld >= c
+    if not ok:
+        raise _lib.CoddError(f"tensor is not NHWC-backed (shape {tuple(t.shape)}, strides {s})")
+    return ld
+
+
+def to_nhwc(t):
+    """Accept any float32 CUDA NCHW tensor; returns an NHWC-backed equivalent (kernel copy if needed)."""
+    _require_cuda(t)
+    try:
+        ld_of(t)
+        return t
+    except _lib.CoddError:
+        pass
+    t = t.contiguous()
+    n, c, h, w = t.shape
+    out = empty_nhwc(n, c, h, w, t.device)
+    rc = _run("nchw_to_nhwc", 8 * t.numel(),
+              lambda: _lib.load().codd_nchw_to_nhwc(t.data_ptr(), n, c, h, w, out.data_ptr(), c, _stream()))
+    _lib.check(rc, "codd_nchw_to_nhwc")
+    return out
+
+
+def to_nchw(t):
+    """NHWC-backed logical-NCHW tensor -> plain contiguous NCHW tensor."""
+    _require_cuda(t)
+    n, c, h, w = t.shape
+    ld = ld_of(t)
+    out = torch.empty((n, c, h, w), device=t.device, dtype=torch.float32)
+    rc = _run("nhwc_to_nchw", 8 * out.numel(),
+              lambda: _lib.load().codd_nhwc_to_nchw(t.data_ptr(), ld, n, h, w, c, out.data_ptr(), _stream()))
+    _lib.check(rc, "codd_nhwc_to_nchw")
+    return out
+
+
+def pack_conv_weight(w):
+    """torch [Cout,Cin,KH,KW] -> [KH*KW][Cin][Cout] (what codd_conv2d_nhwc reads)."""
+    return w.detach().permute(2, 3, 1, 0).contiguous().float()
+
+
+def pack_deconv_weight(w):
+    """torch ConvTranspose2d [Cin,Cout,2,2] -> [4][Cin][Cout]."""
+    return w.detach().permute(2, 3, 0, 1).contiguous().float()
+
+
+def conv2d(x, wp, bias, cout, k, stride=(1, 1), pad=(0, 0), dil=1, act=ACT_NONE, x2=None, residual=None,
+           res_bcast=False, out=None, out_hw=None, ld_out=None):
+    """act(conv(cat(x, x2)) + bias + residual).  ``wp`` is a packed weight."""
+    _require_cuda(x, x2, wp, bias, residual, out)
+    n, c0, h, w = x.shape
+    kh, kw = (k, k) if isinstance(k, int) else k
+    sh, sw = (stride, stride) if isinstance(stride, int) else stride
+    ph, pw = (pad, pad) if isinstance(pad, int) else pad
+    if out_hw is None:
+        ho = (h + 2 * ph - dil * (kh - 1) - 1) // sh + 1
+        wo = (w + 2 * pw - dil * (kw - 1) - 1) // sw + 1
+    else:
+        ho, wo = out_hw
+    c1 = 0 if x2 is None else x2.shape[1]
+    if wp.numel() != kh * kw * (c0 + c1) * cout:
+        raise _lib.CoddError(f"packed weight has {wp.numel()} elements, expected {kh*kw*(c0+c1)*cout}")
+    if out is None:
+        out = empty_nhwc(n, cout, ho, wo, x.device, ld_out)
+    d = ConvDesc(n=n, h=h, w=w, c0=c0, ld0=ld_of(x), c1=c1, ld1=0 if x2 is None else ld_of(x2), cout=cout,
+                 ldo=ld_of(out), kh=kh, kw=kw, sh=sh, sw=sw, ph=ph, pw=pw, dil=dil, ho=ho, wo=wo, act=act,
+                 ldr=0 if residual is None else ld_of(residual), res_bcast=1 if res_bcast else 0)
+    nbytes = 4 * (n * h * w * (c0 + c1) + n * ho * wo * cout + wp.numel()
+                  + (0 if residual is None else n * ho * wo * (1 if res_bcast else cout)))
+    tag = f"conv{kh}x{kw}_s{sh}{sw}_d{dil}_cin{c0 + c1}_cout{cout}"
+    rc = _run(tag, nbytes, lambda: _lib.load().codd_conv2d_nhwc(
+        ctypes.byref(d), x.data_ptr(), None if x2 is None else x2.data_ptr(), wp.data_ptr(),
+        None if bias is None else bias.data_ptr(), None if residual is None else residual.data_ptr(),
+        out.data_ptr(), _stream()))
+    _lib.check(rc, f"codd_conv2d_nhwc(k={kh}x{kw}, cin={c0}+{c1}, cout={cout})")
+    return out
+
+
+def conv3x3_image(left, right, wp, bias, cout):
+    """First backbone conv on NCHW images; returns the NHWC feature map of cat([left, right])."""
+    _require_cuda(left, right, wp, bias)
+    left = left.contiguous()
+    n, c, h, w = left.shape
+    if c != 3:
+        raise _lib.CoddError("codd_conv3x3_image expects 3-channel images")
+    if right is not None:
+        right = right.contiguous()
+        if right.shape != left.shape:
+            raise _lib.CoddError("left / right image shapes differ")
+    nb = n if right is None else 2 * n
+    out = empty_nhwc(nb, cout, h, w, left.device)
+    rc = _run("conv3x3_image", 4 * nb * h * w * (3 + cout), lambda: _lib.load().codd_conv3x3_image(
+        left.data_ptr(), None if right is None else right.data_ptr(), n, h, w, wp.data_ptr(), bias.data_ptr(), cout,
+        out.data_ptr(), cout, _stream()))
+    _lib.check(rc, "codd_conv3x3_image")
+    return out
+
+
+def deconv2x2(x, wp, bias, cout, act=ACT_LEAKY):
+    _require_cuda(x, wp, bias)
+    n, cin, h, w = x.shape
+    out = empty_nhwc(n, cout, 2 * h, 2 * w, x.device)
+    rc = _run(f"deconv2x2_cin{cin}_cout{cout}", 4 * n * h * w * (cin + 4 * cout),
+              lambda: _lib.load().codd_deconv2x2_nhwc(x.data_ptr(), ld_of(x), n, h, w, cin, wp.data_ptr(),
+                                                      bias.data_ptr(), cout, out.data_ptr(), cout, act, _stream()))
+    _lib.check(rc, "codd_deconv2x2_nhwc")
+    return out
+
+
+def cost_volume(tile_l, tile_r, max_disp, want_cv=False, want_argmin=True):
+    """K1.  Returns (cv or None, min_cost or None, min_disp or None); cv is [N,D,h,w] planar,
+    min_* are [N,1,h,w]."""
+    _require_cuda(tile_l, tile_r)
+    n, c, h, w = tile_l.shape
+    if c != 16 or tile_r.shape != (n, 16, h, 4 * w):
+        raise _lib.CoddError(f"cost_volume expects [N,16,h,w] and [N,16,h,4w], got {tuple(tile_l.shape)} "
+                             f"{tuple(tile_r.shape)}")
+    dev = tile_l.device
+    cv = torch.empty((n, max_disp, h, w), device=dev, dtype=torch.float32) if want_cv else None
+    mc = torch.empty((n, 1, h, w), device=dev, dtype=torch.float32) if want_argmin else None
+    md = torch.empty((n, 1, h, w), device=dev, dtype=torch.float32) if want_argmin else None
+    nbytes = cost_volume_bytes(n, h, w, max_disp, want_cv, want_argmin)
+    tag = "cost_volume_" + ("build" if want_cv else "") + ("argmin" if want_argmin else "")
+    rc = _run(tag, nbytes, lambda: _lib.load().codd_cost_volume(
+        tile_l.data_ptr(), ld_of(tile_l), tile_r.data_ptr(), ld_of(tile_r), n, h, w, max_disp,
+        None if cv is None else cv.data_ptr(), None if mc is None else mc.data_ptr(),
+        None if md is None else md.data_ptr(), _stream()))
+    _lib.check(rc, "codd_cost_volume")
+    return cv, mc, md
+
+
+def cost_volume_bytes(n, h, w, max_disp, want_cv, want_argmin):
+    """Algorithmic HBM bytes of K1: fp32 tile features in (16 ch x (w + 4w)
+    columns), the volume out when materialised (4*D per tile), min cost + arg-min out (8 per tile)."""
+    return n * h * w * (320 + (4 * max_disp if want_cv else 0) + (8 if want_argmin else 0))
+
+
+def tile_hyp_init(min_cost, min_disp, feat, weight, bias):
+    _require_cuda(min_cost, min_disp, feat, weight, bias)
+    n, cf, h, w = feat.shape
+    hyp = empty_nhwc(n, 16, h, w, feat.device)
+    rc = _run("tile_hyp_init", 4 * n * h * w * (2 + cf + 16), lambda: _lib.load().codd_tile_hyp_init(
+        min_cost.data_ptr(), min_disp.data_ptr(), feat.data_ptr(), ld_of(feat), cf, weight.data_ptr(), bias.data_ptr(),
+        n, h, w, hyp.data_ptr(), 16, _stream()))
+    _lib.check(rc, "codd_tile_hyp_init")
+    return hyp
+
+
+def plane_upsample(hyp, scale, size):
+    _require_cuda(hyp)
+    n, c, h, w = hyp.shape
+    if c != 16:
+        raise _lib.CoddError("plane_upsample expects 16-channel hypotheses")
+    out = empty_nhwc(n, 16, h * size, w * size, hyp.device)
+    rc = _run("plane_upsample", 64 * n * h * w * (1 + size * size), lambda: _lib.load().codd_plane_upsample(
+        hyp.data_ptr(), ld_of(hyp), n, h, w, size, float(scale), out.data_ptr(), 16, _stream()))
+    _lib.check(rc, "codd_plane_upsample")
+    return out
+
+
+def tile_warp_cost(fea_l, fea_r, cur, prev, dec_w, dec_b, want_raw=False):
+    """K4.  Returns aug [N,32|64,h,w] (and the raw 64-ch/set decrease input when want_raw)."""
+    _require_cuda(fea_l, fea_r, cur, prev, dec_w, dec_b)
+    n, c, H, W = fea_l.shape
+    _, _, h, w = cur.shape
+    if (H, W) != (4 * h, 4 * w) or fea_r.shape != fea_l.shape or cur.shape[1] != 16:
+        raise _lib.CoddError("tile_warp_cost: feature / hypothesis shapes inconsistent")
+    if prev is not None and prev.shape != (n, 16, h // 2, w // 2):
+        raise _lib.CoddError("tile_warp_cost: previous-level hypotheses must be [N,16,h/2,w/2]")
+    ca = 64 if prev is not None else 32
+    aug = empty_nhwc(n, ca, h, w, cur.device)
+    raw = empty_nhwc(n, 2 * ca, h, w, cur.device) if want_raw else None
+    nbytes = tile_warp_bytes(n, c, h, w, prev is not None)
+    rc = _run(f"tile_warp_cost_c{c}_sets{2 if prev is not None else 1}", nbytes, lambda: _lib.load().codd_tile_warp_cost(
+        fea_l.data_ptr(), ld_of(fea_l), fea_r.data_ptr(), ld_of(fea_r), c, cur.data_ptr(), ld_of(cur),
+        None if prev is None else prev.data_ptr(), 0 if prev is None else ld_of(prev), dec_w.data_ptr(),
+        dec_b.data_ptr(), n, h, w, aug.data_ptr(), ca, None if raw is None else raw.data_ptr(), _stream()))
+    _lib.check(rc, "codd_tile_warp_cost")
+    return (aug, raw) if want_raw else aug
+
+
+def tile_warp_bytes(n, c, h, w, has_prev):
+    """Algorithmic HBM bytes of K4: both feature maps once (2*C per pixel, 16 pixels per tile),
+    the hypotheses in (16 per tile, + the coarser level's 16 per 4 tiles) and the augmented
+    hypothesis tensor out (32 or 64 per tile); fp32."""
+    per_tile = 2 * c * 16 + 16 + (4 + 64 if has_prev else 32)
+    return 4 * n * h * w * per_tile
+
+
+def hyp_select(update, aug):
+    _require_cuda(update, aug)
+    n, cu, h, w = update.shape
+    if cu != 34 or aug.shape != (n, 64, h, w):
+        raise _lib.CoddError("hyp_select expects update [N,34,h,w] and aug [N,64,h,w]")
+    out = empty_nhwc(n, 16, h, w, update.device)
+    rc = _run("hyp_select", 4 * n * h * w * (18 + 16 + 16), lambda: _lib.load().codd_hyp_select(
+        update.data_ptr(), ld_of(update), aug.data_ptr(), ld_of(aug), n, h, w, out.data_ptr(), 16, _stream()))
+    _lib.check(rc, "codd_hyp_select")
+    return out

@@ -1,0 +1,87 @@
+"""TileInitialization — drop-in for model/stereo/hitnet/initialization.py:48-230.
+
+Same constructor (``max_disp``, ``fea_c``) and parameter tree (tile_conv{1x..16x},
+tile_fea_dscrpt{16x..1x}).  ``forward(fea_l_pyramid, fea_r_pyramid)`` returns
+``[init_cv_pyramid, init_hypo_pyramid]`` like the reference; the cost volumes are only
+materialised when asked for (``materialize_cv`` — the reference's eval path computes and
+drops them, hitnet.py:89-94), otherwise the fused arg-min kernel runs and the first list
+holds ``None`` entries.
+"""
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..lib import ACT_LEAKY
+from ..registry import MODELS
+from ._params import PackedWeights
+
+
+def _tile_conv(cin):
+    return nn.Sequential(
+        nn.Conv2d(cin, 16, 4, 4, 0), nn.LeakyReLU(0.2, inplace=True),
+        nn.Conv2d(16, 16, 1, 1, 0), nn.LeakyReLU(0.2, inplace=True))
+
+
+def _dscrpt(cin):
+    return nn.Sequential(nn.Conv2d(cin, 13, 1), nn.LeakyReLU(0.2, inplace=True))
+
+
+@MODELS.register_module(force=True)
+class TileInitialization(nn.Module):
+    def __init__(self, max_disp, fea_c=[16, 16, 24, 24, 32]):
+        super().__init__()
+        self.maxdisp = max_disp
+        fea_c1x, fea_c2x, fea_c4x, fea_c8x, fea_c16x = fea_c
+        self.pad = nn.ZeroPad2d((0, 3, 0, 0))
+        self.tile_conv1x = _tile_conv(fea_c1x)
+        self.tile_conv2x = _tile_conv(fea_c2x)
+        self.tile_conv4x = _tile_conv(fea_c4x)
+        self.tile_conv8x = _tile_conv(fea_c8x)
+        self.tile_conv16x = _tile_conv(fea_c16x)
+        self.tile_fea_dscrpt16x = _dscrpt(17)
+        self.tile_fea_dscrpt8x = _dscrpt(17)
+        self.tile_fea_dscrpt4x = _dscrpt(33)
+        self.tile_fea_dscrpt2x = _dscrpt(25)
+        self.tile_fea_dscrpt1x = _dscrpt(25)
+        self.materialize_cv = None  # None: follow self.training
+        self._pw = PackedWeights()
+
+    def _levels(self):
+        # coarse -> fine, matching the pyramid order the backbone emits
+        return [(self.tile_conv16x, self.tile_fea_dscrpt16x, 16), (self.tile_conv8x, self.tile_fea_dscrpt8x, 8),
+                (self.tile_conv4x, self.tile_fea_dscrpt4x, 4), (self.tile_conv2x, self.tile_fea_dscrpt2x, 2),
+                (self.tile_conv1x, self.tile_fea_dscrpt1x, 1)]
+
+    def _tile_pair(self, seq, fl, fr):
+        """initialization.py:119-124: left 4x4/s4; right the same weights at stride (4,1) over the
+        input zero-padded by 3 columns on the right (expressed as an output width of W)."""
+        w0, b0 = self._pw.conv(seq[0])
+        w1, b1 = self._pw.conv(seq[2])
+        n, c, h, w = fl.shape
+        tl = ops.conv2d(fl, w0, b0, 16, 4, (4, 4), (0, 0), 1, ACT_LEAKY)
+        tl = ops.conv2d(tl, w1, b1, 16, 1, act=ACT_LEAKY)
+        tr = ops.conv2d(fr, w0, b0, 16, 4, (4, 1), (0, 0), 1, ACT_LEAKY, out_hw=(h // 4, w))
+        tr = ops.conv2d(tr, w1, b1, 16, 1, act=ACT_LEAKY)
+        return tl, tr
+
+    def tile_features(self, fea_l, fea_r):
+        fea_l = [ops.to_nhwc(f) for f in fea_l]
+        fea_r = [ops.to_nhwc(f) for f in fea_r]
+        return [list(self._tile_pair(seq, fea_l[k], fea_r[k])) for k, (seq, _, _) in enumerate(self._levels())]
+
+    def tile_hypothesis_pyramid(self, tile_feature_pyramid, fea_l_pyramid):
+        want_cv = self.training if self.materialize_cv is None else self.materialize_cv
+        cvs, hyps = [], []
+        for k, (_, dsc, div) in enumerate(self._levels()):
+            tl, tr = tile_feature_pyramid[k]
+            cv, cost, disp = ops.cost_volume(tl, tr, self.maxdisp // div, want_cv=want_cv)
+            # descriptor input: tile features at 16x / 8x, backbone pyramid [0..2] below (Eq. 4)
+            feat = tl if k < 2 else ops.to_nhwc(fea_l_pyramid[k - 2])
+            w, b = self._pw.raw(dsc[0])
+            hyps.append(ops.tile_hyp_init(cost, disp, feat, w, b))
+            cvs.append(cv)
+        return [cvs, hyps]
+
+    def forward(self, fea_l_pyramid, fea_r_pyramid):
+        tiles = self.tile_features(fea_l_pyramid, fea_r_pyramid)
+        return self.tile_hypothesis_pyramid(tiles, fea_l_pyramid)

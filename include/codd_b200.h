@@ -1,0 +1,165 @@
+/*
+ * codd_b200 — C ABI of the B200-native (sm_100a) CODD stereo hot path.
+ *
+ * This header is the drop-in boundary.  The reference has no native code and
+ * no FFI: its hot path is a chain of PyTorch op launches inside three registry-built
+ * nn.Modules.  Each entry point below replaces one such op sequence; the reference lines it
+ * replaces are cited per function (paths relative to the CODD repository root).
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types in any signature; loaded with ctypes.
+ *   - every pointer is a DEVICE pointer to fp32 unless stated; the caller owns and allocates
+ *     every input, output and workspace buffer (torch's caching allocator on the Python side).
+ *   - activations are NHWC ("channels_last"): element (n,y,x,c) of a tensor with pixel stride
+ *     `ld` floats lives at  base[((n*H + y)*W + x)*ld + c].  ld >= C lets a tensor be a channel
+ *     slice of a wider buffer (how the reference's torch.cat inputs are avoided).
+ *     Images enter as NCHW (the reference's layout); cost volumes are [N,D,h,w] planar.
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises.
+ *   - return value: 0 success; < 0 argument error (CODD_E_*); > 0 a cudaError_t.
+ *   - no global mutable state; thread-safe for concurrent calls on distinct streams.
+ *   - there is no CPU fallback: on a machine without an sm_100 device every call fails.
+ */
+#ifndef CODD_B200_H
+#define CODD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define CODD_API __attribute__((visibility("default")))
+#else
+#define CODD_API
+#endif
+
+#define CODD_E_BADARG (-1)   /* null pointer / non-positive dimension */
+#define CODD_E_SHAPE (-2)    /* dimensions violate a documented constraint */
+#define CODD_E_UNSUPPORTED (-3) /* kernel-geometry not instantiated */
+#define CODD_E_ALIGN (-4)    /* pointer / stride not 16-byte aligned where required */
+
+/* activation codes for the conv epilogues */
+#define CODD_ACT_NONE 0
+#define CODD_ACT_LEAKY 1      /* LeakyReLU(0.2): every activation in HITNetMF */
+#define CODD_ACT_RELU 2
+#define CODD_ACT_RELU_CH0 3   /* ReLU on output channel 0 only (disparity >= 0) */
+#define CODD_ACT_SIGMOID 4
+#define CODD_ACT_MISH 5
+
+CODD_API int codd_version(void);
+CODD_API const char* codd_error_string(int code);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense convolutions (reference: every nn.Conv2d / ConvTranspose2d on the stereo path —
+ * model/stereo/hitnet/backbone.py:8-39,69-88; initialization.py:62-117; propagation.py:89-333).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct codd_conv_desc {
+    int n, h, w;          /* input batch / spatial size */
+    int c0, ld0;          /* first input: channels, pixel stride */
+    int c1, ld1;          /* optional second input, concatenated after the first (0 = none) */
+    int cout, ldo;        /* output channels, output pixel stride */
+    int kh, kw;           /* kernel size */
+    int sh, sw;           /* stride */
+    int ph, pw;           /* zero padding top / left (bottom / right are implied by ho, wo) */
+    int dil;              /* dilation (both axes) */
+    int ho, wo;           /* output spatial size */
+    int act;              /* CODD_ACT_* applied after bias (+ residual) */
+    int ldr;              /* residual pixel stride (ignored when residual == NULL) */
+    int res_bcast;        /* 1: residual has one channel, broadcast over cout */
+} codd_conv_desc;
+
+/* weight is PACKED [kh*kw][c0+c1][cout] (host side: w.permute(2,3,1,0).contiguous()).
+ * out = act(conv(cat(in0,in1)) + bias + residual).  residual may be NULL. */
+CODD_API int codd_conv2d_nhwc(const codd_conv_desc* d, const float* in0, const float* in1,
+                     const float* weight, const float* bias, const float* residual,
+                     float* out, void* stream);
+
+/* First backbone layer (backbone.py:35-39,70): 3x3, pad 1, 3 -> cout (<=16) channels,
+ * LeakyReLU, reading NCHW images and writing NHWC.  `left` and `right` are two [n,3,h,w]
+ * images batches; the output holds 2n samples: left batch first, then right (right may be
+ * NULL -> n samples).  weight PACKED [9][3][cout]. */
+CODD_API int codd_conv3x3_image(const float* left, const float* right, int n, int h, int w,
+                       const float* weight, const float* bias, int cout, float* out, int ldo,
+                       void* stream);
+
+/* ConvTranspose2d(k=2, s=2) + LeakyReLU (backbone.py:17-21).  weight PACKED [4][cin][cout]
+ * with tap = dy*2+dx (host: w.permute(2,3,0,1).contiguous()).  in [n,h,w,cin], out [n,2h,2w,cout]. */
+CODD_API int codd_deconv2x2_nhwc(const float* in, int ldi, int n, int h, int w, int cin,
+                        const float* weight, const float* bias, int cout, float* out, int ldo,
+                        int act, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K1  L1 cost volume + arg-min tile initialisation
+ * (reference: calc_init_disp, initialization.py:18-45; torch.min, :167-171).
+ *   cv[n,d,i,j] = sum_c | L[n,i,j,c] - R[n,i,4j-d,c] |   (R := 0 when 4j-d < 0), c sequential.
+ * tile_l [n,h,w,16], tile_r [n,h,4w,16] NHWC with pixel strides ldl / ldr.
+ * Any of cv / min_cost / min_disp may be NULL (not produced).
+ *   cv        [n,max_disp,h,w] planar   (the reference's init_cv_pyramid entry)
+ *   min_cost  [n,h,w]
+ *   min_disp  [n,h,w]  arg-min as float (first index on ties), as the reference casts it.
+ * max_disp must be a multiple of 4; channels fixed at 16 (TileInitialization always emits 16).
+ * ------------------------------------------------------------------------------------------ */
+CODD_API int codd_cost_volume(const float* tile_l, int ldl, const float* tile_r, int ldr,
+                     int n, int h, int w, int max_disp,
+                     float* cv, float* min_cost, float* min_disp, void* stream);
+
+/* Tile descriptor + hypothesis assembly (initialization.py:186-208):
+ *   hyp[n,i,j,0:16] = [ min_disp, 0, 0, LeakyReLU(W . cat[min_cost, feat] + b) (13 ch) ]
+ * feat [n,h,w,cf] NHWC (ldf); weight is the torch layout [13][1+cf]; hyp pixel stride ldh. */
+CODD_API int codd_tile_hyp_init(const float* min_cost, const float* min_disp, const float* feat, int ldf,
+                       int cf, const float* weight, const float* bias,
+                       int n, int h, int w, float* hyp, int ldh, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3  slanted-plane up-sampling (reference: to_plane / upsample, propagation.py:10-32).
+ * in [n,h,w,16] -> out [n,h*size,w*size,16]; ch0 = ((d + cx*dx) + cy*dy) * scale, others nearest.
+ * ------------------------------------------------------------------------------------------ */
+CODD_API int codd_plane_upsample(const float* in, int ldi, int n, int h, int w, int size, float scale,
+                        float* out, int ldo, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K4  tile warping + local cost volume + `decrease` conv, for the current hypothesis set and
+ * (optionally) the up-sampled previous-level set
+ * (reference: TileWarping.forward, propagation.py:61-86; warp :35-58; TileUpdate0.forward
+ *  :156-160; TileUpdate.forward :206-219).
+ * fea_l / fea_r  [n,H,W,c]  NHWC features of this level (H = 4h, W = 4w), c in {16,24,32}
+ * cur            [n,h,w,16] current hypotheses
+ * prev           [n,h/2,w/2,16] refined hypotheses of the coarser level, or NULL (TileUpdate0)
+ * dec_w [16][64] (torch layout), dec_b [16]: the `decrease` 1x1 conv (input = cat[|fea_l|_1
+ *                unshuffled (16), local cost volume (48)]), LeakyReLU.
+ * aug            [n,h,w,ldaug] receives  [cur(16) | cur_cv(16)]            when prev == NULL
+ *                                        [cur | cur_cv | up_prev(16) | prev_cv(16)] otherwise
+ *                i.e. exactly the tensor the reference feeds to conv0.
+ * raw_cv         optional debug/test output [n,h,w,sets*64]: per set cat[|fea_l|_1 (16), cv48],
+ *                the un-reduced `decrease` input (NULL in production).
+ * ------------------------------------------------------------------------------------------ */
+CODD_API int codd_tile_warp_cost(const float* fea_l, int ldfl, const float* fea_r, int ldfr, int c,
+                        const float* cur, int ldc, const float* prev, int ldp,
+                        const float* dec_w, const float* dec_b,
+                        int n, int h, int w, float* aug, int ldaug, float* raw_cv,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K5  hypothesis selection (reference: TileUpdate.forward, propagation.py:225-248).
+ * update [n,h,w,34] = [conf_prev, conf_cur, dprev(16), dcur(16)];  aug as written by K4.
+ * refined [n,h,w,16] = conf_cur > conf_prev ? relu0(cur + dcur) : relu0(up_prev + dprev).
+ * ------------------------------------------------------------------------------------------ */
+CODD_API int codd_hyp_select(const float* update, int ldu, const float* aug, int ldaug,
+                    int n, int h, int w, float* refined, int ldr, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * layout helpers at the module boundary
+ * ------------------------------------------------------------------------------------------ */
+/* NHWC [n,h,w,c] (pixel stride ldi) -> NCHW contiguous */
+CODD_API int codd_nhwc_to_nchw(const float* in, int ldi, int n, int h, int w, int c, float* out,
+                      void* stream);
+/* NCHW contiguous -> NHWC (pixel stride ldo) */
+CODD_API int codd_nchw_to_nhwc(const float* in, int n, int c, int h, int w, float* out, int ldo,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CODD_B200_H */

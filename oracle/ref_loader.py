@@ -1,0 +1,101 @@
+"""Import the UNMODIFIED CODD reference files in this container.
+
+TEST INFRASTRUCTURE ONLY.  Used by ``oracle/gen_golden.py`` (fixture generation) and
+by the ``-m "not gpu"`` tests that pin the oracle restatement against the reference
+when ``/root/reference`` is present.  Nothing on the product path, in ``-m gpu`` tests,
+``smoke()`` or ``bench.py`` imports this module: the reference does not exist on the GPU box.
+
+The reference needs mmcv / mmseg (registry, BaseModule, init helpers) and imports
+pytorch3d / lietorch at module scope.  None is installable here, so ``oracle/_shim``
+provides import-compatible stand-ins (registry + no-op decorators; the pytorch3d /
+lietorch stubs raise if they are ever *called*).  ``model`` is registered as a
+namespace package so that ``model/__init__.py`` (which imports every sub-package)
+is not executed; the stereo / fusion / utils files themselves run unmodified.
+"""
+import importlib
+import os
+import sys
+import types
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SHIM = os.path.join(_HERE, "_shim")
+
+
+def reference_root():
+    root = os.environ.get("CODD_REF", "/root/reference")
+    return root if os.path.isdir(os.path.join(root, "model", "stereo")) else None
+
+
+def available():
+    return reference_root() is not None
+
+
+_loaded = {}
+
+
+def load():
+    """Returns a namespace with the reference modules (stereo, fusion, utils)."""
+    if "ns" in _loaded:
+        return _loaded["ns"]
+    root = reference_root()
+    if root is None:
+        raise RuntimeError("CODD reference not found (set CODD_REF or mount /root/reference)")
+    for name in ("mmcv", "mmseg"):
+        try:
+            importlib.import_module(name)
+        except ImportError:
+            if _SHIM not in sys.path:
+                sys.path.insert(0, _SHIM)
+    for name in ("pytorch3d", "lietorch", "lietorch_extras"):
+        try:
+            importlib.import_module(name)
+        except ImportError:
+            if _SHIM not in sys.path:
+                sys.path.insert(0, _SHIM)
+    if root not in sys.path:
+        sys.path.insert(0, root)
+
+    def _namespace(modname, path):
+        m = types.ModuleType(modname)
+        m.__path__ = [path]
+        sys.modules[modname] = m
+        return m
+
+    # `model`, `model.stereo`, `model.motion`, `model.fusion` as bare namespaces: their
+    # __init__.py files pull in pytorch3d/lietorch-dependent code at import time.
+    _namespace("model", os.path.join(root, "model"))
+    for sub in ("stereo", "motion", "fusion", "losses"):
+        _namespace(f"model.{sub}", os.path.join(root, "model", sub))
+    _namespace("model.stereo.hitnet", os.path.join(root, "model", "stereo", "hitnet"))
+    _namespace("model.motion.raft3d", os.path.join(root, "model", "motion", "raft3d"))
+    _namespace("model.motion.raft3d.blocks", os.path.join(root, "model", "motion", "raft3d", "blocks"))
+
+    ns = types.SimpleNamespace()
+    ns.builder = importlib.import_module("model.builder")
+    ns.utils = importlib.import_module("utils")
+    ns.warp = importlib.import_module("utils.warp")
+    ns.backbone = importlib.import_module("model.stereo.hitnet.backbone")
+    ns.initialization = importlib.import_module("model.stereo.hitnet.initialization")
+    ns.propagation = importlib.import_module("model.stereo.hitnet.propagation")
+    ns.hitnet = importlib.import_module("model.stereo.hitnet.hitnet")
+    try:
+        ns.fusion = importlib.import_module("model.fusion.fusion")
+    except Exception as e:  # pragma: no cover - informative only
+        ns.fusion = None
+        ns.fusion_error = e
+    _loaded["ns"] = ns
+    return ns
+
+
+def build_hitnet(max_disp=192):
+    """The reference HITNetMF built through its own registry (configs/models/stereo.py:12-25)."""
+    ns = load()
+    cfg = dict(
+        type="HITNetMF",
+        backbone=dict(type="HITUNet"),
+        initialization=dict(type="TileInitialization", max_disp=max_disp),
+        propagation=dict(type="TilePropagation"),
+    )
+    model = ns.builder.ESTIMATORS.build(cfg)  # build_estimator adds train_cfg/test_cfg (codd-level only)
+    model.eval()
+    return model

@@ -1,0 +1,277 @@
+"""Kernel-level parity: every C-ABI entry point against the CPU oracle on the same seeded
+inputs.  Integer / index / discrete outputs and the whole cost-volume + warp arithmetic are
+compared BIT-EXACT; the dense convolutions (fp32 FMA, different summation order than torch's
+CPU kernels) within rtol 2e-5 / atol 2e-5, tolerance stated per test."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import golden_params
+from oracle import hitnet_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+CONV_RTOL, CONV_ATOL = 2e-5, 2e-5
+
+
+@pytest.fixture(scope="module")
+def ops():
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    from codd_b200 import ops as _ops
+    return _ops
+
+
+def dev(x):
+    return x.cuda()
+
+
+def nhwc(ops, x):
+    return ops.to_nhwc(x.cuda().float())
+
+
+def back(ops, t):
+    return ops.to_nchw(t).cpu()
+
+
+def gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+# ------------------------------------------------------------------------------------------
+def test_layout_roundtrip(ops):
+    x = torch.randn(3, 24, 7, 13, generator=gen(0))
+    t = nhwc(ops, x)
+    assert t.shape == x.shape and ops.ld_of(t) == 24
+    assert torch.equal(back(ops, t), x)
+    assert torch.equal(back(ops, t[:, 8:16]), x[:, 8:16])
+    assert torch.equal(back(ops, t[1:]), x[1:])
+
+
+CONV_CASES = [
+    # k, stride, pad, dil, cin, cout, h, w
+    (1, 1, 0, 1, 16, 16, 9, 15), (1, 1, 0, 1, 48, 24, 18, 30), (1, 1, 0, 1, 64, 32, 5, 70), (1, 1, 0, 1, 32, 13, 8, 8),
+    (3, 1, 1, 1, 16, 16, 36, 60), (3, 1, 1, 1, 24, 24, 17, 33), (3, 1, 1, 1, 32, 32, 40, 40), (3, 1, 1, 1, 32, 34, 9, 15),
+    (3, 1, 1, 1, 16, 3, 20, 50), (3, 1, 1, 1, 16, 1, 20, 50), (3, 1, 1, 1, 32, 16, 33, 31), (3, 1, 1, 1, 8, 8, 6, 6),
+    (3, 1, 3, 3, 32, 32, 36, 60), (4, 2, 1, 1, 16, 16, 32, 64), (4, 2, 1, 1, 16, 24, 36, 60), (4, 2, 1, 1, 24, 32, 18, 30),
+    (4, 4, 0, 1, 16, 16, 36, 60), (4, 4, 0, 1, 32, 16, 8, 140), (7, 1, 3, 1, 2, 32, 20, 30), (7, 1, 3, 1, 64, 30, 12, 34),
+    (1, 1, 0, 1, 31, 64, 10, 10), (3, 1, 1, 1, 17, 5, 7, 9),
+]
+
+
+@pytest.mark.parametrize("k,s,p,d,cin,cout,h,w", CONV_CASES)
+def test_conv2d_vs_torch_cpu(ops, k, s, p, d, cin, cout, h, w):
+    from codd_b200.lib import ACT_LEAKY
+    g = gen(k * 1000 + cin * 10 + cout)
+    x = torch.randn(2, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    b = torch.randn(cout, generator=g)
+    ref = F.leaky_relu(F.conv2d(x, wt, b, stride=s, padding=p, dilation=d), 0.2)
+    out = ops.conv2d(nhwc(ops, x), ops.pack_conv_weight(wt).cuda(), b.cuda(), cout, k, s, p, d, ACT_LEAKY)
+    assert out.shape == ref.shape
+    torch.testing.assert_close(back(ops, out), ref, rtol=CONV_RTOL, atol=CONV_ATOL)
+
+
+def test_conv2d_dual_input_residual_slices(ops):
+    from codd_b200.lib import ACT_NONE, ACT_RELU, ACT_RELU_CH0
+    g = gen(5)
+    a = torch.randn(2, 24, 19, 37, generator=g)
+    b2 = torch.randn(2, 16, 19, 37, generator=g)
+    wt = torch.randn(32, 40, 1, 1, generator=g) / 6
+    bias = torch.randn(32, generator=g)
+    ref = F.conv2d(torch.cat([a, b2], 1), wt, bias)
+    # a lives as a channel slice [8:32] of a 48-wide buffer
+    wide = ops.empty_nhwc(2, 48, 19, 37, "cuda")
+    wide[:, 8:32].copy_(a.cuda())
+    out = ops.conv2d(wide[:, 8:32], ops.pack_conv_weight(wt).cuda(), bias.cuda(), 32, 1, act=ACT_NONE,
+                     x2=nhwc(ops, b2))
+    torch.testing.assert_close(back(ops, out), ref, rtol=CONV_RTOL, atol=CONV_ATOL)
+    # residual (full) + relu on channel 0 only, 3x3
+    x = torch.randn(2, 32, 19, 37, generator=g)
+    w3 = torch.randn(16, 32, 3, 3, generator=g) / 17
+    b3 = torch.randn(16, generator=g)
+    res = torch.randn(2, 16, 19, 37, generator=g)
+    r = F.conv2d(x, w3, b3, padding=1) + res
+    r = torch.cat([F.relu(r[:, :1]), r[:, 1:]], 1)
+    out = ops.conv2d(nhwc(ops, x), ops.pack_conv_weight(w3).cuda(), b3.cuda(), 16, 3, 1, 1, 1, ACT_RELU_CH0,
+                     residual=nhwc(ops, res))
+    torch.testing.assert_close(back(ops, out), r, rtol=CONV_RTOL, atol=CONV_ATOL)
+    # broadcast single-channel residual + relu
+    r = F.relu(F.conv2d(x, w3[:3], b3[:3], padding=1) + res[:, :1])
+    out = ops.conv2d(nhwc(ops, x), ops.pack_conv_weight(w3[:3]).cuda(), b3[:3].cuda(), 3, 3, 1, 1, 1, ACT_RELU,
+                     residual=nhwc(ops, res)[:, :1], res_bcast=True)
+    torch.testing.assert_close(back(ops, out), r, rtol=CONV_RTOL, atol=CONV_ATOL)
+
+
+def test_tile_conv_right_stride41(ops):
+    """initialization.py:121-124: stride (4,1) over the input zero-padded 3 columns on the right."""
+    from codd_b200.lib import ACT_LEAKY
+    g = gen(8)
+    x = torch.randn(2, 24, 16, 44, generator=g)
+    wt = torch.randn(16, 24, 4, 4, generator=g) / 20
+    b = torch.randn(16, generator=g)
+    ref = F.leaky_relu(F.conv2d(F.pad(x, (0, 3, 0, 0)), wt, b, stride=(4, 1)), 0.2)
+    out = ops.conv2d(nhwc(ops, x), ops.pack_conv_weight(wt).cuda(), b.cuda(), 16, 4, (4, 1), (0, 0), 1, ACT_LEAKY,
+                     out_hw=(4, 44))
+    assert out.shape == ref.shape
+    torch.testing.assert_close(back(ops, out), ref, rtol=CONV_RTOL, atol=CONV_ATOL)
+
+
+def test_image_conv_and_deconv(ops):
+    g = gen(9)
+    l = torch.randn(2, 3, 21, 45, generator=g)
+    r = torch.randn(2, 3, 21, 45, generator=g)
+    wt = torch.randn(16, 3, 3, 3, generator=g) / 5
+    b = torch.randn(16, generator=g)
+    ref = F.leaky_relu(F.conv2d(torch.cat([l, r]), wt, b, padding=1), 0.2)
+    out = ops.conv3x3_image(l.cuda(), r.cuda(), ops.pack_conv_weight(wt).cuda(), b.cuda(), 16)
+    torch.testing.assert_close(back(ops, out), ref, rtol=CONV_RTOL, atol=CONV_ATOL)
+    for cin, cout in ((32, 24), (24, 24), (24, 16), (16, 16)):
+        x = torch.randn(2, cin, 9, 15, generator=g)
+        wt = torch.randn(cin, cout, 2, 2, generator=g) / cin ** 0.5
+        b = torch.randn(cout, generator=g)
+        ref = F.leaky_relu(F.conv_transpose2d(x, wt, b, stride=2), 0.2)
+        out = ops.deconv2x2(nhwc(ops, x), ops.pack_deconv_weight(wt).cuda(), b.cuda(), cout)
+        torch.testing.assert_close(back(ops, out), ref, rtol=CONV_RTOL, atol=CONV_ATOL)
+
+
+# ------------------------------------------------------------------------------------------
+# K1: bit-exact
+# ------------------------------------------------------------------------------------------
+CV_CASES = [(1, 2, 2, 4), (2, 9, 15, 12), (1, 5, 33, 32), (2, 3, 40, 48), (1, 4, 70, 192), (1, 2, 240, 192),
+            (1, 2, 300, 64), (1, 1, 500, 256), (1, 3, 7, 64)]
+
+
+@pytest.mark.parametrize("n,h,w,d", CV_CASES)
+def test_cost_volume_bit_exact(ops, n, h, w, d):
+    g = gen(n + h * 7 + w * 13 + d)
+    tl = torch.randn(n, 16, h, w, generator=g)
+    tr = torch.randn(n, 16, h, 4 * w, generator=g)
+    for j in range(w):                                   # plant true matches at varying disparities
+        x = 4 * j - (j % 5) * 3
+        if x >= 0:
+            tr[:, :, :, x] = tl[:, :, :, j] + 0.01 * torch.randn(n, 16, h, generator=g)
+    ref = O.cost_volume(tl, tr, d)
+    rc, ri = ref.min(1)
+    for want_cv, want_arg in ((True, True), (False, True), (True, False)):
+        cv, mc, md = ops.cost_volume(nhwc(ops, tl), nhwc(ops, tr), d, want_cv=want_cv, want_argmin=want_arg)
+        if want_cv:
+            assert torch.equal(cv.cpu(), ref), "cost volume not bit-identical"
+        if want_arg:
+            assert torch.equal(mc.cpu()[:, 0], rc), "min cost not bit-identical"
+            assert torch.equal(md.cpu()[:, 0], ri.float()), "arg-min indices differ"
+
+
+def test_cost_volume_all_ties(ops):
+    """right == 0: every disparity costs |L|_1 -> arg-min must be 0 everywhere (first index)."""
+    tl = torch.randn(1, 16, 4, 37, generator=gen(3))
+    tr = torch.zeros(1, 16, 4, 148)
+    cv, mc, md = ops.cost_volume(nhwc(ops, tl), nhwc(ops, tr), 64, want_cv=True)
+    assert torch.count_nonzero(md) == 0
+    assert torch.equal(mc.cpu()[:, 0], O.l1_over_channels(tl)[:, 0])
+    assert torch.equal(cv.cpu(), O.cost_volume(tl, tr, 64))
+
+
+def test_cost_volume_golden(ops, golden_small):
+    fx = golden_small
+    d = int(fx["meta"][3])
+    for k in range(5):
+        tl, tr = torch.from_numpy(fx[f"tile_l{k}"]), torch.from_numpy(fx[f"tile_r{k}"])
+        cv, mc, md = ops.cost_volume(nhwc(ops, tl), nhwc(ops, tr), d // (16 >> k), want_cv=True)
+        assert torch.equal(cv.cpu(), torch.from_numpy(fx[f"cv{k}"]))
+        assert torch.equal(md.cpu()[:, 0], torch.from_numpy(fx[f"hyp{k}"])[:, 0])
+
+
+def test_tile_hyp_init(ops):
+    g = gen(12)
+    for cf in (16, 24, 32):
+        cost = torch.rand(2, 1, 6, 10, generator=g)
+        disp = torch.randint(0, 40, (2, 1, 6, 10), generator=g).float()
+        feat = torch.randn(2, cf, 6, 10, generator=g)
+        w = torch.randn(13, 1 + cf, 1, 1, generator=g) / 5
+        b = torch.randn(13, generator=g)
+        dsc = F.leaky_relu(F.conv2d(torch.cat([cost, feat], 1), w, b), 0.2)
+        ref = torch.cat([disp, torch.zeros_like(disp), torch.zeros_like(disp), dsc], 1)
+        out = ops.tile_hyp_init(cost.cuda(), disp.cuda(), nhwc(ops, feat), w.cuda().contiguous(), b.cuda())
+        got = back(ops, out)
+        assert torch.equal(got[:, :3], ref[:, :3])
+        torch.testing.assert_close(got[:, 3:], ref[:, 3:], rtol=CONV_RTOL, atol=CONV_ATOL)
+
+
+# ------------------------------------------------------------------------------------------
+# K3 / K4 / K5: bit-exact
+# ------------------------------------------------------------------------------------------
+def test_plane_upsample_bit_exact(ops):
+    hyp = torch.randn(2, 16, 5, 9, generator=gen(13)) * 3
+    for scale, size in ((2, 2), (1, 2), (1, 4)):
+        out = ops.plane_upsample(nhwc(ops, hyp), float(scale), size)
+        assert torch.equal(back(ops, out), O.plane_upsample(hyp, scale, size))
+
+
+def _warp_inputs(n, c, h, w, seed, dmax):
+    g = gen(seed)
+    fl = torch.randn(n, c, 4 * h, 4 * w, generator=g)
+    fr = torch.randn(n, c, 4 * h, 4 * w, generator=g)
+    cur = torch.randn(n, 16, h, w, generator=g)
+    cur[:, 0] = torch.rand(n, h, w, generator=g) * dmax - 2.0      # some samples fall off the left edge
+    cur[:, 1:3] = torch.randn(n, 2, h, w, generator=g) * 0.3
+    prev = torch.randn(n, 16, h // 2, w // 2, generator=g)
+    prev[:, 0] = torch.rand(n, h // 2, w // 2, generator=g) * dmax / 2
+    prev[:, 1:3] = torch.randn(n, 2, h // 2, w // 2, generator=g) * 0.3
+    dw = torch.randn(16, 64, 1, 1, generator=g) / 8
+    db = torch.randn(16, generator=g)
+    return fl, fr, cur, prev, dw, db
+
+
+@pytest.mark.parametrize("n,c,h,w,dmax", [(1, 16, 4, 6, 10.0), (2, 24, 6, 18, 40.0), (1, 32, 2, 34, 90.0),
+                                          (1, 16, 10, 16, 30.0), (1, 16, 36, 8, 20.0)])
+def test_tile_warp_cost(ops, n, c, h, w, dmax):
+    fl, fr, cur, prev, dw, db = _warp_inputs(n, c, h, w, c + h + w, dmax)
+    fnorm = F.pixel_unshuffle(O.l1_over_channels(fl), 4)
+    up_prev = O.plane_upsample(prev, 2, 2)
+    raw_cur = torch.cat([fnorm, O.tile_warp_cost(cur[:, :3], fl, fr, direct=True)], 1)
+    raw_prev = torch.cat([fnorm, O.tile_warp_cost(up_prev[:, :3], fl, fr, direct=True)], 1)
+    dec = lambda r: F.leaky_relu(F.conv2d(r, dw, db), 0.2)
+    args = (nhwc(ops, fl), nhwc(ops, fr), nhwc(ops, cur))
+    # two hypothesis sets (TileUpdate)
+    aug, raw = ops.tile_warp_cost(*args, nhwc(ops, prev), dw.cuda().contiguous(), db.cuda(), want_raw=True)
+    raw = back(ops, raw)
+    assert torch.equal(raw[:, :64], raw_cur), "local cost volume (current set) not bit-identical"
+    assert torch.equal(raw[:, 64:], raw_prev), "local cost volume (up-sampled previous set) not bit-identical"
+    aug = back(ops, aug)
+    assert torch.equal(aug[:, :16], cur) and torch.equal(aug[:, 32:48], up_prev)
+    torch.testing.assert_close(aug[:, 16:32], dec(raw_cur), rtol=CONV_RTOL, atol=CONV_ATOL)
+    torch.testing.assert_close(aug[:, 48:], dec(raw_prev), rtol=CONV_RTOL, atol=CONV_ATOL)
+    # one set (TileUpdate0)
+    aug0, raw0 = ops.tile_warp_cost(*args, None, dw.cuda().contiguous(), db.cuda(), want_raw=True)
+    assert torch.equal(back(ops, raw0), raw_cur)
+    aug0 = back(ops, aug0)
+    assert aug0.shape[1] == 32 and torch.equal(aug0[:, :16], cur)
+    torch.testing.assert_close(aug0[:, 16:], dec(raw_cur), rtol=CONV_RTOL, atol=CONV_ATOL)
+
+
+def test_tile_warp_cost_golden(ops, golden_small):
+    """Against the reference's own TileWarping output (grid_sample path), finest level."""
+    fx = golden_small
+    sd = golden_params(fx)
+    out = O.stereo_matching(sd, torch.from_numpy(fx["left"]), torch.from_numpy(fx["right"]), int(fx["meta"][3]),
+                            return_all=True)
+    hyp = torch.from_numpy(fx["hyp4"])
+    dw, db = torch.zeros(16, 64), torch.zeros(16)
+    _, raw = ops.tile_warp_cost(nhwc(ops, out["fea_l"][4]), nhwc(ops, out["fea_r"][4]), nhwc(ops, hyp), None,
+                                dw.cuda(), db.cuda(), want_raw=True)
+    assert torch.equal(back(ops, raw)[:, 16:], torch.from_numpy(fx["local_cv_l4"]))
+
+
+def test_hyp_select_bit_exact(ops):
+    g = gen(21)
+    upd = torch.randn(2, 34, 7, 11, generator=g)
+    upd[0, 1, :2] = upd[0, 0, :2]                      # exact confidence ties -> previous wins
+    cur = torch.randn(2, 16, 7, 11, generator=g)
+    upp = torch.randn(2, 16, 7, 11, generator=g)
+    aug = torch.cat([cur, torch.randn(2, 16, 7, 11, generator=g), upp, torch.randn(2, 16, 7, 11, generator=g)], 1)
+    ref = O.hyp_select(upd, cur, upp)[0]
+    wide = ops.empty_nhwc(2, 34, 7, 11, "cuda", ld=36)
+    wide.copy_(upd.cuda())
+    out = ops.hyp_select(wide, nhwc(ops, aug))
+    assert torch.equal(back(ops, out), ref)

@@ -1,0 +1,70 @@
+"""Pins the oracle against the UNMODIFIED reference files, where they are mounted
+(/root/reference exists in the build container, not on the GPU box -> skipped there)."""
+import warnings
+
+import pytest
+import torch
+
+from oracle import hitnet_oracle as O
+from oracle import ref_loader
+
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="reference not mounted")
+
+
+@pytest.fixture(scope="module")
+def ref_model():
+    warnings.filterwarnings("ignore")
+    m = ref_loader.build_hitnet(64)
+    m.load_state_dict(O.random_hitnet_params(21))
+    return m
+
+
+@pytest.mark.parametrize("kind,shape", [("S", (1, 128, 192)), ("G", (2, 128, 128)), ("U", (1, 192, 128))])
+def test_end_to_end_bitwise(ref_model, kind, shape):
+    n, h, w = shape
+    left, right = O.synth_pair(n, h, w, 64, seed=99, kind=kind)
+    with torch.no_grad():
+        ref = ref_model.stereo_matching(left, right)
+    sd = {k: v.detach() for k, v in ref_model.state_dict().items()}
+    for direct in (False, True):
+        out = O.stereo_matching(sd, left, right, 64, direct=direct)
+        for key in ("pred_disp", "left_feat", "right_feat"):
+            assert torch.equal(out[key], ref[key]), (key, direct)
+
+
+def test_calc_init_disp_bitwise_ragged():
+    ns = ref_loader.load()
+    g = torch.Generator().manual_seed(5)
+    for (n, h, w, d) in [(1, 3, 5, 8), (2, 9, 15, 12), (1, 4, 7, 32), (1, 2, 40, 48)]:
+        tl = torch.randn(n, 16, h, w, generator=g)
+        tr = torch.randn(n, 16, h, 4 * w, generator=g)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref = ns.initialization.calc_init_disp(tl, tr, d)
+        assert torch.equal(O.cost_volume(tl, tr, d), ref)
+
+
+def test_upsample_and_warp_bitwise():
+    ns = ref_loader.load()
+    g = torch.Generator().manual_seed(6)
+    hyp = torch.randn(2, 16, 5, 7, generator=g)
+    assert torch.equal(O.plane_upsample(hyp, 2, 2), ns.propagation.upsample(hyp, 2))
+    assert torch.equal(O.plane_upsample(hyp, 1, 2), ns.propagation.upsample(hyp, 1))
+    assert torch.equal(O.plane_upsample(hyp, 16, 64), ns.propagation.upsample(hyp, 16, 64))
+    fr = torch.randn(2, 24, 20, 28, generator=g)
+    disp = torch.rand(2, 1, 20, 28, generator=g) * 40 - 4
+    ref = ns.propagation.warp(fr, disp)
+    assert torch.equal(O.warp_right(fr, disp), ref)
+    assert torch.equal(O.warp_right_direct(fr, disp), ref)
+
+
+def test_same_seed_same_weights_as_reference():
+    """The drop-in modules consume the RNG in the reference's construction order."""
+    import codd_b200
+    torch.manual_seed(123)
+    mine = codd_b200.MODELS.build(codd_b200.hitnet_config(64))
+    torch.manual_seed(123)
+    ref = ref_loader.build_hitnet(64)
+    a, b = mine.state_dict(), ref.state_dict()
+    assert list(a.keys()) == list(b.keys())
+    assert all(torch.equal(a[k], b[k]) for k in a)
