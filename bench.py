@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--dump-kernels", default=None, help="write the per-kernel table of the instrumented pass (JSON)")
     return ap.parse_args()
 
 
@@ -322,6 +323,8 @@ def run_b200(args):
                 "algorithmic_bytes_per_step": k["bytes"], "peak_source": peak_src,
                 "how": "per-launch CUDA events on the launching stream, instrumented eager pass after the timed region"}
 
+    if args.dump_kernels:
+        json.dump([roof(k) for k in kernels], open(args.dump_kernels, "w"), indent=1)
     dominant = roof(kernels[0])
     named = [roof(k) for k in kernels if k["kernel"].startswith(("cost_volume", "tile_warp_cost"))]
 

@@ -53,7 +53,7 @@ struct CvP {
 template <bool WRITE_CV, bool ARGMIN>
 __global__ void __launch_bounds__(384) cost_volume_kernel(CvP p) {
     extern __shared__ float4 smem4[];
-    const int Dq = p.D >> 2;
+    const int Dq = (p.D + 3) >> 2;   // disparity quads; the last one may be partial
     int b = blockIdx.x;
     const int jblk = b % p.nblk;
     b /= p.nblk;
@@ -161,19 +161,20 @@ __global__ void __launch_bounds__(384) cost_volume_kernel(CvP p) {
                     lo = __fadd2_rn(lo, make_float2(fabsf(d1.x), fabsf(d1.y)));
                 }
                 const float c0 = lo.y, c1 = lo.x, c2 = hi.y, c3 = hi.x;  // r = 0,1,2,3
+                const int nd = p.D - 4 * q;   // valid disparities in this quad (>= 1; < 4 only in the last)
                 if (WRITE_CV) {
                     float* o = cvrow + (size_t)(4 * q) * plane + j;
                     __stcs(o, c0);
-                    __stcs(o + plane, c1);
-                    __stcs(o + 2 * plane, c2);
-                    __stcs(o + 3 * plane, c3);
+                    if (nd > 1) __stcs(o + plane, c1);
+                    if (nd > 2) __stcs(o + 2 * plane, c2);
+                    if (nd > 3) __stcs(o + 3 * plane, c3);
                 }
                 if (ARGMIN) {
                     const float dq = (float)(4 * q);
                     if (c0 < bc) { bc = c0; bd = dq; }
-                    if (c1 < bc) { bc = c1; bd = dq + 1.f; }
-                    if (c2 < bc) { bc = c2; bd = dq + 2.f; }
-                    if (c3 < bc) { bc = c3; bd = dq + 3.f; }
+                    if (nd > 1 && c1 < bc) { bc = c1; bd = dq + 1.f; }
+                    if (nd > 2 && c2 < bc) { bc = c2; bd = dq + 2.f; }
+                    if (nd > 3 && c3 < bc) { bc = c3; bd = dq + 3.f; }
                 }
             }
             if (ARGMIN) {
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(384) cost_volume_kernel(CvP p) {
         if (ARGMIN) {
             // columns still in flight: lane now holds the state of column m + Dq
             const int j = m + Dq;
-            if (lane < 31 && j >= jb && j < je && (m + 1) < je + 0 + 32) {
+            if (lane < 31 && j >= jb && j < je) {
                 pc[warp * LW + (j - jb)] = bc;
                 pd[warp * LW + (j - jb)] = bd;
             }
@@ -212,8 +213,8 @@ __global__ void __launch_bounds__(384) cost_volume_kernel(CvP p) {
         }
     }
     if (WRITE_CV) {
-        // zero-filled region: d >= 4j+4  (only columns j < Dq-1 have one)
-        const int jz = min(nj, max(0, Dq - 1 - jb));   // local columns [0, jz)
+        // zero-filled region: 4j+4 <= d < D  (only columns j < (D-1)/4 have one)
+        const int jz = min(nj, max(0, (p.D - 1) / 4 - jb));   // local columns [0, jz)
         if (jz > 0) {
             for (int idx = tid; idx < p.D * jz; idx += blockDim.x) {
                 const int d = idx / jz, jj = idx - d * jz;
@@ -228,11 +229,11 @@ __global__ void __launch_bounds__(384) cost_volume_kernel(CvP p) {
 extern "C" int codd_cost_volume(const float* tile_l, int ldl, const float* tile_r, int ldr, int n, int h, int w,
                                 int max_disp, float* cv, float* min_cost, float* min_disp, void* stream) {
     if (!tile_l || !tile_r || n <= 0 || h <= 0 || w <= 0 || max_disp <= 0) return CODD_E_BADARG;
-    if (max_disp % 4 != 0 || ldl < CV_C || ldr < CV_C || ldl % 4 != 0 || ldr % 4 != 0) return CODD_E_SHAPE;
+    if (ldl < CV_C || ldr < CV_C || ldl % 4 != 0 || ldr % 4 != 0) return CODD_E_SHAPE;
     if (!codd_aligned16(tile_l) || !codd_aligned16(tile_r)) return CODD_E_ALIGN;
     const bool argmin = (min_cost != nullptr) || (min_disp != nullptr);
     if (!cv && !argmin) return CODD_E_BADARG;
-    const int Dq = max_disp / 4;
+    const int Dq = (max_disp + 3) / 4;
     // columns per CTA: the m-range (JB + Dq - 1 values, one lane each) must fit 12 warps
     const int max_m = 12 * 32;
     int nblk = 1;

@@ -99,7 +99,8 @@ CODD_API int codd_deconv2x2_nhwc(const float* in, int ldi, int n, int h, int w, 
  *   cv        [n,max_disp,h,w] planar   (the reference's init_cv_pyramid entry)
  *   min_cost  [n,h,w]
  *   min_disp  [n,h,w]  arg-min as float (first index on ties), as the reference casts it.
- * max_disp must be a multiple of 4; channels fixed at 16 (TileInitialization always emits 16).
+ * Any max_disp >= 1 (the reference uses max_disp // {16,8,4,2,1}); channels fixed at 16
+ * (TileInitialization always emits 16).
  * ------------------------------------------------------------------------------------------ */
 CODD_API int codd_cost_volume(const float* tile_l, int ldl, const float* tile_r, int ldr,
                      int n, int h, int w, int max_disp,

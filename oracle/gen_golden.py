@@ -55,9 +55,8 @@ def hitnet_fixture(name, n, h, w, max_disp, wseed, dseed, kind, full=True):
             fx[f"fea_l{k}"] = fl[k].numpy()
     if not full:
         del fx["local_cv_l4"]
-    # weights are re-derivable from wseed; a checksum guards against RNG drift
-    flat = torch.cat([sd[k].flatten() for k in sorted(sd)])
-    fx["weights_sum"] = np.array([flat.double().sum().item(), flat.double().abs().sum().item()])
+    # weights are re-derivable from wseed; a digest of the raw bytes guards against RNG drift
+    fx["weights_sha1"] = np.frombuffer(O.params_digest(sd), dtype=np.uint8)
     os.makedirs(OUT, exist_ok=True)
     path = os.path.join(OUT, name)
     np.savez_compressed(path, **fx)

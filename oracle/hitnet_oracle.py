@@ -490,6 +490,15 @@ def random_hitnet_params(seed=0):
     return sd
 
 
+def params_digest(sd):
+    """sha1 over the raw fp32 bytes of a state_dict (key-sorted): exact, order-independent of threads."""
+    import hashlib
+    hsh = hashlib.sha1()
+    for k in sorted(sd):
+        hsh.update(sd[k].detach().contiguous().numpy().tobytes())
+    return hsh.digest()
+
+
 def synth_pair(n, h, w, max_disp, seed=1234, kind="S"):
     """Synthetic stereo pair [N,3,h,w] x2 (h, w already multiples of 64).
 

@@ -35,7 +35,6 @@ def golden_params(fx):
     """Weights of a fixture, re-derived from its seed and checked against the stored checksum."""
     from oracle import hitnet_oracle as O
     sd = O.random_hitnet_params(int(fx["meta"][4]))
-    flat = torch.cat([sd[k].flatten() for k in sorted(sd)])
-    got = np.array([flat.double().sum().item(), flat.double().abs().sum().item()])
-    assert np.array_equal(got, fx["weights_sum"]), "RNG drift: fixture weights cannot be re-derived"
+    got = np.frombuffer(O.params_digest(sd), dtype=np.uint8)
+    assert np.array_equal(got, fx["weights_sha1"]), "RNG drift: fixture weights cannot be re-derived"
     return sd

@@ -138,7 +138,7 @@ def test_image_conv_and_deconv(ops):
 # ------------------------------------------------------------------------------------------
 # K1: bit-exact
 # ------------------------------------------------------------------------------------------
-CV_CASES = [(1, 2, 2, 4), (2, 9, 15, 12), (1, 5, 33, 32), (2, 3, 40, 48), (1, 4, 70, 192), (1, 2, 240, 192),
+CV_CASES = [(1, 2, 2, 4), (1, 2, 5, 2), (2, 3, 9, 6), (1, 2, 40, 21), (2, 9, 15, 12), (1, 5, 33, 32), (2, 3, 40, 48), (1, 4, 70, 192), (1, 2, 240, 192),
             (1, 2, 300, 64), (1, 1, 500, 256), (1, 3, 7, 64)]
 
 

@@ -1,0 +1,68 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[4]: K1 sweep {540p, 720p, 1080p} x D in {64,128,192,256}, 8 samples per
+GPU; achieved algorithmic GB/s (SURVEY.md §8d byte counts) of the materialising and the fused
+arg-min variant, whole 5-level pyramid per measurement, CUDA events, L2 flushed between reps.
+
+    python tools/sweep_cost_volume.py [--out profiles/cost_volume_sweep_rNN.json]
+"""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from codd_b200 import ops  # noqa: E402
+
+SIZES = {"540p": (576, 960), "720p": (768, 1280), "1080p": (1088, 1920)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--out", default=None)
+    a = ap.parse_args()
+    dev = torch.device("cuda")
+    peak = 6650.0
+    try:
+        peak = float(json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:  # noqa: BLE001
+        pass
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    rows = []
+    for name, (H, W) in SIZES.items():
+        for D in (64, 128, 192, 256):
+            levels = []
+            for k in range(5):
+                h, w = (H >> (4 - k)) // 4, (W >> (4 - k)) // 4
+                tl = ops.to_nhwc(torch.randn(a.batch, 16, h, w, device=dev))
+                tr = ops.to_nhwc(torch.randn(a.batch, 16, h, 4 * w, device=dev))
+                levels.append((tl, tr, D // (16 >> k), h, w))
+            for want_cv in (True, False):
+                nbytes = sum(ops.cost_volume_bytes(a.batch, h, w, d, want_cv, True) for _, _, d, h, w in levels)
+                ms = []
+                for r in range(a.reps + 2):
+                    flush.zero_()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for tl, tr, d, _, _ in levels:
+                        ops.cost_volume(tl, tr, d, want_cv=want_cv, want_argmin=True)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    if r >= 2:
+                        ms.append(e0.elapsed_time(e1))
+                t = sorted(ms)[len(ms) // 2]
+                gbs = nbytes / (t * 1e-3) / 1e9
+                rows.append(dict(size=name, padded=[H, W], D=D, batch=a.batch,
+                                 variant="materialise+argmin" if want_cv else "fused argmin",
+                                 algorithmic_mb=round(nbytes / 1e6, 2), ms=round(t, 4), gbs=round(gbs, 1),
+                                 frac_of_measured_peak=round(gbs / peak, 4)))
+                print(rows[-1])
+    if a.out:
+        json.dump(dict(peak_gbs=peak, rows=rows), open(a.out, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
