@@ -335,16 +335,38 @@ __global__ void __launch_bounds__(256) deconv2x2_kernel(const float* __restrict_
 // ---------------------------------------------------------------------------------------------
 // layout helpers
 // ---------------------------------------------------------------------------------------------
-__global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, int ldi, int hw, int c, float* __restrict__ out,
-                                    size_t total) {
-    // one thread per output element; reads are strided by ldi but hit the same lines across c
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const size_t pix = i % hw;
-    const size_t t = i / hw;
-    const int ch = (int)(t % c);
-    const size_t s = t / c;
-    out[i] = __ldg(in + (s * hw + pix) * ldi + ch);
+// NHWC -> planar through a shared-memory tile of 128 pixels x C channels: coalesced 128-bit
+// reads along the channel-contiguous side, coalesced 128-byte row writes on the planar side.
+constexpr int TR_PIX = 128;
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const float* __restrict__ in, int ldi, int hw, int c,
+                                                           float* __restrict__ out) {
+    extern __shared__ float4 smem4[];
+    float* tile = reinterpret_cast<float*>(smem4);   // [c][TR_PIX + 1]
+    const int s = blockIdx.y;
+    const int p0 = blockIdx.x * TR_PIX;
+    const int np = min(TR_PIX, hw - p0);
+    const bool vec = ((ldi & 3) == 0) && ((c & 3) == 0) && ((((uintptr_t)in) & 15u) == 0);
+    if (vec) {
+        const int c4n = c >> 2;
+        for (int idx = threadIdx.x; idx < np * c4n; idx += blockDim.x) {
+            const int pp = idx / c4n, c4 = idx - pp * c4n;
+            const float4 v = ldg4(in + ((size_t)s * hw + p0 + pp) * ldi + c4 * 4);
+            tile[(c4 * 4 + 0) * (TR_PIX + 1) + pp] = v.x;
+            tile[(c4 * 4 + 1) * (TR_PIX + 1) + pp] = v.y;
+            tile[(c4 * 4 + 2) * (TR_PIX + 1) + pp] = v.z;
+            tile[(c4 * 4 + 3) * (TR_PIX + 1) + pp] = v.w;
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < np * c; idx += blockDim.x) {
+            const int pp = idx / c, ch = idx - pp * c;
+            tile[ch * (TR_PIX + 1) + pp] = __ldg(in + ((size_t)s * hw + p0 + pp) * ldi + ch);
+        }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < c * TR_PIX; idx += blockDim.x) {
+        const int ch = idx / TR_PIX, pp = idx - ch * TR_PIX;
+        if (pp < np) out[((size_t)s * c + ch) * hw + p0 + pp] = tile[ch * (TR_PIX + 1) + pp];
+    }
 }
 
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, int c, int hw, float* __restrict__ out, int ldo,
@@ -434,9 +456,17 @@ extern "C" int codd_deconv2x2_nhwc(const float* in, int ldi, int n, int h, int w
 
 extern "C" int codd_nhwc_to_nchw(const float* in, int ldi, int n, int h, int w, int c, float* out, void* stream) {
     if (!in || !out || n <= 0 || h <= 0 || w <= 0 || c <= 0 || ldi < c) return CODD_E_BADARG;
-    const size_t total = (size_t)n * c * h * w;
-    nhwc_to_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, ldi, h * w, c, out,
-                                                                                            total);
+    if (c > 384) return CODD_E_UNSUPPORTED;
+    const int hw = h * w;
+    dim3 grid((unsigned)codd_ceil_div(hw, TR_PIX), (unsigned)n);
+    const size_t smem = (size_t)c * (TR_PIX + 1) * sizeof(float);
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(nhwc_to_nchw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = smem;
+    }
+    nhwc_to_nchw_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(in, ldi, hw, c, out);
     CODD_RETURN_IF_CUDA_ERROR();
     return 0;
 }

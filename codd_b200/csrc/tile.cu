@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(128) tile_hyp_init_kernel(const float* __restr
                                                             const float* __restrict__ feat, int ldf, int cf,
                                                             const float* __restrict__ wgt,
                                                             const float* __restrict__ bias, size_t npix,
-                                                            float* __restrict__ hyp, int ldh) {
+                                                            size_t planar_hw, float* __restrict__ hyp, int ldh) {
     extern __shared__ float4 smem4[];
     float* s_w = reinterpret_cast<float*>(smem4);  // [1+cf][16] transposed, 13 used
     const int cin = 1 + cf;
@@ -39,9 +39,13 @@ __global__ void __launch_bounds__(128) tile_hyp_init_kernel(const float* __restr
     const float c = __ldg(min_cost + pix);
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc[i] = fmaf(c, s_w[i], acc[i]);
-    const float* fp = feat + pix * ldf;
+    const bool planar = (ldf == 0);
+    const size_t hw = planar_hw;
+    const float* fp = planar ? feat + (pix / hw) * (size_t)cf * hw + (pix % hw) : feat + pix * ldf;
     for (int ci = 0; ci < cf; ci += 4) {
-        const float4 a4 = ldg4(fp + ci);
+        const float4 a4 = planar ? make_float4(__ldg(fp + (size_t)ci * hw), __ldg(fp + (size_t)(ci + 1) * hw),
+                                               __ldg(fp + (size_t)(ci + 2) * hw), __ldg(fp + (size_t)(ci + 3) * hw))
+                                 : ldg4(fp + ci);
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
             const float a = cc == 0 ? a4.x : cc == 1 ? a4.y : cc == 2 ? a4.z : a4.w;
@@ -95,8 +99,8 @@ __global__ void __launch_bounds__(256) plane_upsample_kernel(const float* __rest
 // ------------------------------------------------------------------------------------------
 struct WarpP {
     const float* fl;
-    const float* fr;
-    int ldfl, ldfr, C;
+    const float* fr;      // PLANAR [n][C][H][W]
+    int ldfl, C;
     const float* cur;
     int ldc;
     const float* prev;
@@ -119,15 +123,25 @@ struct Taps {
     float fw[3], fe[3];
 };
 
+// a / b rounded to nearest for a fixed, normal divisor b with r = RN(1/b) (Markstein): q0 = RN(a*r),
+// rem = a - q0*b exactly (one FMA), q = RN(q0 + rem*r).  Operands here are pixel coordinates
+// (|a| < 2^20, 1 <= b < 2^20): no overflow / denormal cases, so the two-FMA correction yields the
+// correctly rounded quotient; tests/test_gpu_ops.py compares it bit-for-bit with the oracle.
+__device__ __forceinline__ float div_rn_const(float a, float b, float r) {
+    const float q0 = __fmul_rn(a, r);
+    const float rem = __fmaf_rn(-q0, b, a);
+    return __fmaf_rn(rem, r, q0);
+}
+
 __device__ __forceinline__ void sample_setup(float d, float dx, float dy, float a, float b, int x, float wm1,
-                                             float wdiv, Taps& t) {
+                                             float wdiv, float wrcp, Taps& t) {
 #pragma unroll
     for (int ki = 0; ki < 3; ++ki) {
         const float k = (float)(ki - 1);
         // Eq.(5): ((d + k) + a*dx) + b*dy
         const float ld = __fadd_rn(__fadd_rn(__fadd_rn(d, k), __fmul_rn(a, dx)), __fmul_rn(b, dy));
         // reference warp(): 2*(x - d)/max(W-1,1) - 1 ; grid_sample: ((g+1)/2)*(W-1)
-        const float g = __fadd_rn(__fdiv_rn(__fmul_rn(2.f, __fsub_rn((float)x, ld)), wdiv), -1.f);
+        const float g = __fadd_rn(div_rn_const(__fmul_rn(2.f, __fsub_rn((float)x, ld)), wdiv, wrcp), -1.f);
         const float ix = __fmul_rn(__fmul_rn(__fadd_rn(g, 1.f), 0.5f), wm1);
         const float fx = floorf(ix);
         t.fw[ki] = __fsub_rn(ix, fx);
@@ -137,24 +151,62 @@ __device__ __forceinline__ void sample_setup(float d, float dx, float dy, float 
     }
 }
 
-__device__ __forceinline__ float4 ld_tap(const float* rowp, int x, int W, int ld, int c) {
-    if (x < 0 || x >= W) return make_float4(0.f, 0.f, 0.f, 0.f);
-    return ldg4(rowp + (size_t)x * ld + c);
+// Channel loops of K4.  Every (set, k) plane gathers its own two columns x0, x0+1: the planes of a
+// set are nominally one pixel apart, but for integer disparities (the arg-min initialisation) ix
+// sits within an ulp of an integer and floor() jitters by one independently per plane, so no
+// shared window is assumed.  Out-of-range taps get a zero WEIGHT instead of a zero value —
+// identical cost: torch's blend then only adds (+-0) for them.
+//
+// PAIRED: both columns of every plane are inside the row (0 <= x0 < W-1), so the second tap is the
+// first one's neighbour (one address computation per pair).  Otherwise (a plane touching the
+// image border) the columns are clamped individually.
+template <int NSETS, bool TWO_ROWS, bool PAIRED>
+__device__ __forceinline__ void k4_channels(const float* __restrict__ flp, const float* __restrict__ frn,
+                                            size_t cstride, int C, int rowstep, const int (&offA)[NSETS][3],
+                                            const int (&offB)[NSETS][3], const float (&wA)[NSETS][3],
+                                            const float (&wB)[NSETS][3], const float (&wC)[NSETS][3],
+                                            const float (&wD)[NSETS][3], float (&cost)[NSETS][3], float& lnorm) {
+    for (int c = 0; c < C; c += 4) {
+        const float4 l4 = ldg4(flp + c);
+        const float lv[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const float l = lv[cc];
+            lnorm = __fadd_rn(lnorm, fabsf(l));
+            const float* base = frn + (size_t)(c + cc) * cstride;
+            float tA[NSETS][3], tB[NSETS][3], uA[NSETS][3], uB[NSETS][3];
+#pragma unroll
+            for (int s = 0; s < NSETS; ++s)
+#pragma unroll
+                for (int ki = 0; ki < 3; ++ki) {
+                    const float* pa = base + offA[s][ki];
+                    const float* pb = PAIRED ? pa + 1 : base + offB[s][ki];
+                    tA[s][ki] = __ldg(pa);
+                    tB[s][ki] = __ldg(pb);
+                    if (TWO_ROWS) {
+                        uA[s][ki] = __ldg(pa + rowstep);
+                        uB[s][ki] = __ldg(pb + rowstep);
+                    }
+                }
+#pragma unroll
+            for (int s = 0; s < NSETS; ++s)
+#pragma unroll
+                for (int ki = 0; ki < 3; ++ki) {
+                    // torch's bilinear: fma(se_v, se, fma(sw_v, sw, fma(ne_v, ne, nw_v*nw)))
+                    float v = __fmaf_rn(tB[s][ki], wB[s][ki], __fmul_rn(tA[s][ki], wA[s][ki]));
+                    if (TWO_ROWS) v = __fmaf_rn(uB[s][ki], wD[s][ki], __fmaf_rn(uA[s][ki], wC[s][ki], v));
+                    cost[s][ki] = __fadd_rn(cost[s][ki], fabsf(__fsub_rn(l, v)));
+                }
+        }
+    }
 }
 
-__device__ __forceinline__ float blend2(float A, float B, float nw, float ne) {
-    return __fmaf_rn(B, ne, __fmul_rn(A, nw));
-}
-
-__device__ __forceinline__ void acc_abs4(float& acc, const float4& l, const float4& v) {
-    acc = __fadd_rn(acc, fabsf(__fsub_rn(l.x, v.x)));
-    acc = __fadd_rn(acc, fabsf(__fsub_rn(l.y, v.y)));
-    acc = __fadd_rn(acc, fabsf(__fsub_rn(l.z, v.z)));
-    acc = __fadd_rn(acc, fabsf(__fsub_rn(l.w, v.w)));
-}
-
+// The right features are read PLANAR ([n][C][H][W]): lanes of a warp are horizontally adjacent
+// pixels, so every per-channel tap load is a (nearly) contiguous 128-byte request — one L1
+// wavefront — where the NHWC layout costs 16 (lanes 64 B apart).  The left features stay NHWC:
+// each lane reads its own pixel's channels once.
 template <int NSETS>
-__global__ void __launch_bounds__(K4_THREADS) tile_warp_cost_kernel(WarpP p) {
+__global__ void __launch_bounds__(K4_THREADS, 2) tile_warp_cost_kernel(WarpP p) {
     __shared__ __align__(16) float s_raw[NSETS][K4_TILES][64];
     __shared__ __align__(16) float s_dec[NSETS][K4_TILES][16];
     __shared__ __align__(16) float s_wt[64][16];
@@ -186,95 +238,64 @@ __global__ void __launch_bounds__(K4_THREADS) tile_warp_cost_kernel(WarpP p) {
     if (on) {
         const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
         const float wdiv = (float)max(W - 1, 1), hdiv = (float)max(H - 1, 1);
+        const float wrcp = __frcp_rn(wdiv);
         // row coordinate through the same normalise / un-normalise round trip
         const float gy = __fadd_rn(__fdiv_rn(__fmul_rn(2.f, (float)y), hdiv), -1.f);
         const float iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.f), 0.5f), hm1);
         const float fy = floorf(iy);
         const float fn = __fsub_rn(iy, fy);
         const float fs = __fsub_rn(1.f, fn);
-        const int y0 = (int)fy;
-        const bool two_rows = fn != 0.f;
+        const int y0 = min(max((int)fy, 0), H - 1);
+        const bool two_rows = fn != 0.f;                 // uniform per image row => per warp
+        const bool row1_ok = (y0 + 1 < H);
+        const int rowstep = row1_ok ? W : 0;             // invalid second row: any address, zero weight
 
         const float a = (float)xo - 1.5f, bb = (float)yo - 1.5f;
         Taps tp[NSETS];
         {
             const float4 c4 = ldg4(p.cur + (((size_t)n * p.h + i) * p.w + j) * p.ldc);
-            sample_setup(c4.x, c4.y, c4.z, a, bb, x, wm1, wdiv, tp[0]);
+            sample_setup(c4.x, c4.y, c4.z, a, bb, x, wm1, wdiv, wrcp, tp[0]);
         }
         if (NSETS == 2) {
             const int hp = p.h >> 1, wp = p.w >> 1;
             const float4 q4 = ldg4(p.prev + (((size_t)n * hp + (i >> 1)) * wp + (j >> 1)) * p.ldp);
             const float cx = (float)(j & 1) - 0.5f, cy = (float)(i & 1) - 0.5f;
             const float du = __fmul_rn(__fadd_rn(__fadd_rn(q4.x, __fmul_rn(cx, q4.y)), __fmul_rn(cy, q4.z)), 2.f);
-            sample_setup(du, q4.y, q4.z, a, bb, x, wm1, wdiv, tp[NSETS - 1]);
+            sample_setup(du, q4.y, q4.z, a, bb, x, wm1, wdiv, wrcp, tp[NSETS - 1]);
         }
 
         const float* flp = p.fl + (((size_t)n * H + y) * W + x) * p.ldfl;
-        const float* r0 = (y0 >= 0 && y0 < H) ? p.fr + ((size_t)n * H + y0) * W * p.ldfr : nullptr;
-        const float* r1 = (two_rows && y0 + 1 >= 0 && y0 + 1 < H) ? p.fr + ((size_t)n * H + y0 + 1) * W * p.ldfr : nullptr;
+        const size_t cstride = (size_t)H * W;
+        const float* frn = p.fr + (size_t)n * p.C * cstride;
+        const int rowoff = y0 * W;
 
         float cost[NSETS][3];
-        float wnw[NSETS][3], wne[NSETS][3], wsw[NSETS][3], wse[NSETS][3];
-        bool shared_win[NSETS];
+        float wA[NSETS][3], wB[NSETS][3], wC[NSETS][3], wD[NSETS][3];
+        int offA[NSETS][3], offB[NSETS][3];
+        bool paired = true;
 #pragma unroll
         for (int s = 0; s < NSETS; ++s) {
 #pragma unroll
             for (int ki = 0; ki < 3; ++ki) {
                 cost[s][ki] = 0.f;
-                wnw[s][ki] = __fmul_rn(fs, tp[s].fe[ki]);
-                wne[s][ki] = __fmul_rn(fs, tp[s].fw[ki]);
-                wsw[s][ki] = __fmul_rn(fn, tp[s].fe[ki]);
-                wse[s][ki] = __fmul_rn(fn, tp[s].fw[ki]);
+                const int xa = tp[s].x0[ki];
+                const bool va = (xa >= 0 && xa < W), vb = (xa + 1 >= 0 && xa + 1 < W);
+                paired = paired && va && vb;
+                offA[s][ki] = rowoff + min(max(xa, 0), W - 1);
+                offB[s][ki] = rowoff + min(max(xa + 1, 0), W - 1);
+                wA[s][ki] = va ? __fmul_rn(fs, tp[s].fe[ki]) : 0.f;
+                wB[s][ki] = vb ? __fmul_rn(fs, tp[s].fw[ki]) : 0.f;
+                wC[s][ki] = (va && row1_ok) ? __fmul_rn(fn, tp[s].fe[ki]) : 0.f;
+                wD[s][ki] = (vb && row1_ok) ? __fmul_rn(fn, tp[s].fw[ki]) : 0.f;
             }
-            // k = +1 samples furthest left; normally x0(k=0) = x0(+1)+1 and x0(-1) = x0(+1)+2
-            shared_win[s] = (tp[s].x0[1] == tp[s].x0[2] + 1) && (tp[s].x0[0] == tp[s].x0[2] + 2);
         }
         float lnorm = 0.f;
-
-        for (int c = 0; c < p.C; c += 4) {
-            const float4 l4 = ldg4(flp + c);
-            lnorm = __fadd_rn(lnorm, fabsf(l4.x));
-            lnorm = __fadd_rn(lnorm, fabsf(l4.y));
-            lnorm = __fadd_rn(lnorm, fabsf(l4.z));
-            lnorm = __fadd_rn(lnorm, fabsf(l4.w));
-#pragma unroll
-            for (int s = 0; s < NSETS; ++s) {
-                float4 wn[4], ws[4];   // window taps x0(+1) .. x0(+1)+3 on rows y0 / y0+1
-                const int xb = tp[s].x0[2];
-                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (shared_win[s]) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        wn[e] = r0 ? ld_tap(r0, xb + e, W, p.ldfr, c) : z4;
-                        ws[e] = r1 ? ld_tap(r1, xb + e, W, p.ldfr, c) : z4;
-                    }
-                }
-#pragma unroll
-                for (int ki = 0; ki < 3; ++ki) {
-                    float4 A, B, Cc, Dd;
-                    if (shared_win[s]) {
-                        A = wn[2 - ki]; B = wn[3 - ki]; Cc = ws[2 - ki]; Dd = ws[3 - ki];
-                    } else {
-                        const int xx = tp[s].x0[ki];
-                        A = r0 ? ld_tap(r0, xx, W, p.ldfr, c) : z4;
-                        B = r0 ? ld_tap(r0, xx + 1, W, p.ldfr, c) : z4;
-                        Cc = r1 ? ld_tap(r1, xx, W, p.ldfr, c) : z4;
-                        Dd = r1 ? ld_tap(r1, xx + 1, W, p.ldfr, c) : z4;
-                    }
-                    float4 v;
-                    v.x = blend2(A.x, B.x, wnw[s][ki], wne[s][ki]);
-                    v.y = blend2(A.y, B.y, wnw[s][ki], wne[s][ki]);
-                    v.z = blend2(A.z, B.z, wnw[s][ki], wne[s][ki]);
-                    v.w = blend2(A.w, B.w, wnw[s][ki], wne[s][ki]);
-                    if (two_rows) {
-                        v.x = __fmaf_rn(Dd.x, wse[s][ki], __fmaf_rn(Cc.x, wsw[s][ki], v.x));
-                        v.y = __fmaf_rn(Dd.y, wse[s][ki], __fmaf_rn(Cc.y, wsw[s][ki], v.y));
-                        v.z = __fmaf_rn(Dd.z, wse[s][ki], __fmaf_rn(Cc.z, wsw[s][ki], v.z));
-                        v.w = __fmaf_rn(Dd.w, wse[s][ki], __fmaf_rn(Cc.w, wsw[s][ki], v.w));
-                    }
-                    acc_abs4(cost[s][ki], l4, v);
-                }
-            }
+        if (paired) {
+            if (two_rows) k4_channels<NSETS, true, true>(flp, frn, cstride, p.C, rowstep, offA, offB, wA, wB, wC, wD, cost, lnorm);
+            else k4_channels<NSETS, false, true>(flp, frn, cstride, p.C, rowstep, offA, offB, wA, wB, wC, wD, cost, lnorm);
+        } else {
+            if (two_rows) k4_channels<NSETS, true, false>(flp, frn, cstride, p.C, rowstep, offA, offB, wA, wB, wC, wD, cost, lnorm);
+            else k4_channels<NSETS, false, false>(flp, frn, cstride, p.C, rowstep, offA, offB, wA, wB, wC, wD, cost, lnorm);
         }
         const int po = yo * 4 + xo;
 #pragma unroll
@@ -369,12 +390,13 @@ extern "C" int codd_tile_hyp_init(const float* min_cost, const float* min_disp, 
                                   const float* weight, const float* bias, int n, int h, int w, float* hyp, int ldh,
                                   void* stream) {
     if (!min_cost || !min_disp || !feat || !weight || !bias || !hyp || n <= 0 || h <= 0 || w <= 0) return CODD_E_BADARG;
-    if (cf <= 0 || cf % 4 != 0 || cf > 64 || ldf < cf || ldf % 4 != 0 || ldh < 16 || ldh % 4 != 0) return CODD_E_SHAPE;
-    if (!codd_aligned16(feat) || !codd_aligned16(hyp)) return CODD_E_ALIGN;
+    if (cf <= 0 || cf % 4 != 0 || cf > 64 || ldh < 16 || ldh % 4 != 0) return CODD_E_SHAPE;
+    if (ldf != 0 && (ldf < cf || ldf % 4 != 0)) return CODD_E_SHAPE;
+    if ((ldf != 0 && !codd_aligned16(feat)) || !codd_aligned16(hyp)) return CODD_E_ALIGN;
     const size_t npix = (size_t)n * h * w;
     const size_t smem = (size_t)(1 + cf) * 16 * sizeof(float);
     tile_hyp_init_kernel<<<(unsigned)((npix + 127) / 128), 128, smem, (cudaStream_t)stream>>>(
-        min_cost, min_disp, feat, ldf, cf, weight, bias, npix, hyp, ldh);
+        min_cost, min_disp, feat, ldf, cf, weight, bias, npix, (size_t)h * w, hyp, ldh);
     CODD_RETURN_IF_CUDA_ERROR();
     return 0;
 }
@@ -391,19 +413,20 @@ extern "C" int codd_plane_upsample(const float* in, int ldi, int n, int h, int w
     return 0;
 }
 
-extern "C" int codd_tile_warp_cost(const float* fea_l, int ldfl, const float* fea_r, int ldfr, int c,
+extern "C" int codd_tile_warp_cost(const float* fea_l, int ldfl, const float* fea_r_planar, int c,
                                    const float* cur, int ldc, const float* prev, int ldp, const float* dec_w,
                                    const float* dec_b, int n, int h, int w, float* aug, int ldaug, float* raw_cv,
                                    void* stream) {
+    const float* fea_r = fea_r_planar;
     if (!fea_l || !fea_r || !cur || !dec_w || !dec_b || !aug || n <= 0 || h <= 0 || w <= 0) return CODD_E_BADARG;
-    if (c <= 0 || c % 4 != 0 || ldfl < c || ldfr < c || ldfl % 4 || ldfr % 4 || ldc < 16 || ldc % 4) return CODD_E_SHAPE;
+    if (c <= 0 || c % 4 != 0 || ldfl < c || ldfl % 4 || ldc < 16 || ldc % 4) return CODD_E_SHAPE;
     if (prev && (ldp < 16 || ldp % 4 || (h & 1) || (w & 1))) return CODD_E_SHAPE;
     if (ldaug < (prev ? 64 : 32) || ldaug % 4) return CODD_E_SHAPE;
-    if (!codd_aligned16(fea_l) || !codd_aligned16(fea_r) || !codd_aligned16(cur) || !codd_aligned16(aug) ||
+    if (!codd_aligned16(fea_l) || !codd_aligned16(cur) || !codd_aligned16(aug) ||
         (prev && !codd_aligned16(prev)) || (raw_cv && !codd_aligned16(raw_cv)))
         return CODD_E_ALIGN;
     WarpP p;
-    p.fl = fea_l; p.fr = fea_r; p.ldfl = ldfl; p.ldfr = ldfr; p.C = c;
+    p.fl = fea_l; p.fr = fea_r; p.ldfl = ldfl; p.C = c;
     p.cur = cur; p.ldc = ldc; p.prev = prev; p.ldp = ldp;
     p.dec_w = dec_w; p.dec_b = dec_b; p.N = n; p.h = h; p.w = w;
     p.aug = aug; p.ldaug = ldaug; p.raw = raw_cv;

@@ -31,11 +31,12 @@ SIGNATURES = {
     "codd_conv3x3_image": (c_int, [_FP, _FP, c_int, c_int, c_int, _FP, _FP, c_int, _FP, c_int, c_void_p]),
     "codd_deconv2x2_nhwc": (c_int, [_FP, c_int, c_int, c_int, c_int, c_int, _FP, _FP, c_int, _FP, c_int, c_int,
                                     c_void_p]),
-    "codd_cost_volume": (c_int, [_FP, c_int, _FP, c_int, c_int, c_int, c_int, c_int, _FP, _FP, _FP, c_void_p]),
+    "codd_tile_features": (c_int, [_FP, c_int, c_int, c_int, c_int, c_int, _FP, _FP, _FP, _FP, c_int, _FP, c_void_p]),
+    "codd_cost_volume": (c_int, [_FP, _FP, c_int, c_int, c_int, c_int, _FP, _FP, _FP, c_void_p]),
     "codd_tile_hyp_init": (c_int, [_FP, _FP, _FP, c_int, c_int, _FP, _FP, c_int, c_int, c_int, _FP, c_int,
                                    c_void_p]),
     "codd_plane_upsample": (c_int, [_FP, c_int, c_int, c_int, c_int, c_int, c_float, _FP, c_int, c_void_p]),
-    "codd_tile_warp_cost": (c_int, [_FP, c_int, _FP, c_int, c_int, _FP, c_int, _FP, c_int, _FP, _FP, c_int, c_int,
+    "codd_tile_warp_cost": (c_int, [_FP, c_int, _FP, c_int, _FP, c_int, _FP, c_int, _FP, _FP, c_int, c_int,
                                     c_int, _FP, c_int, _FP, c_void_p]),
     "codd_hyp_select": (c_int, [_FP, c_int, _FP, c_int, c_int, c_int, c_int, _FP, c_int, c_void_p]),
     "codd_nhwc_to_nchw": (c_int, [_FP, c_int, c_int, c_int, c_int, c_int, _FP, c_void_p]),

@@ -110,8 +110,10 @@ def to_nhwc(t):
 
 
 def to_nchw(t):
-    """NHWC-backed logical-NCHW tensor -> plain contiguous NCHW tensor."""
+    """NHWC-backed logical-NCHW tensor -> plain contiguous NCHW tensor (planar input: returned as is)."""
     _require_cuda(t)
+    if _is_planar(t):
+        return t
     n, c, h, w = t.shape
     ld = ld_of(t)
     out = torch.empty((n, c, h, w), device=t.device, dtype=torch.float32)
@@ -194,10 +196,28 @@ def deconv2x2(x, wp, bias, cout, act=ACT_LEAKY):
     return out
 
 
+def tile_features(fea, w0p, b0, w1, b1, right):
+    """K2.  fea [N,C,H,W] NHWC-backed -> PLANAR tile features [N,16,H/4,W/4] (left) or
+    [N,16,H/4,W] (right: stride (4,1) over the input zero-padded 3 columns on the right)."""
+    _require_cuda(fea, w0p, b0, w1, b1)
+    n, c, h, w = fea.shape
+    wo = w if right else w // 4
+    out = torch.empty((n, 16, h // 4, wo), device=fea.device, dtype=torch.float32)
+    flops_bytes = 4 * (n * h * w * c + out.numel())
+    rc = _run("tile_features_" + ("right" if right else "left") + f"_c{c}", flops_bytes,
+              lambda: _lib.load().codd_tile_features(fea.data_ptr(), ld_of(fea), c, n, h, w, w0p.data_ptr(),
+                                                     b0.data_ptr(), w1.data_ptr(), b1.data_ptr(), 1 if right else 0,
+                                                     out.data_ptr(), _stream()))
+    _lib.check(rc, "codd_tile_features")
+    return out
+
+
 def cost_volume(tile_l, tile_r, max_disp, want_cv=False, want_argmin=True):
-    """K1.  Returns (cv or None, min_cost or None, min_disp or None); cv is [N,D,h,w] planar,
-    min_* are [N,1,h,w]."""
+    """K1.  tile_l [N,16,h,w], tile_r [N,16,h,4w] (planar NCHW as K2 writes them; NHWC-backed
+    inputs are transposed first).  Returns (cv or None, min_cost or None, min_disp or None);
+    cv is [N,D,h,w] planar, min_* are [N,1,h,w]."""
     _require_cuda(tile_l, tile_r)
+    tile_l, tile_r = planar(tile_l), planar(tile_r)
     n, c, h, w = tile_l.shape
     if c != 16 or tile_r.shape != (n, 16, h, 4 * w):
         raise _lib.CoddError(f"cost_volume expects [N,16,h,w] and [N,16,h,4w], got {tuple(tile_l.shape)} "
@@ -209,7 +229,7 @@ def cost_volume(tile_l, tile_r, max_disp, want_cv=False, want_argmin=True):
     nbytes = cost_volume_bytes(n, h, w, max_disp, want_cv, want_argmin)
     tag = "cost_volume_" + ("build" if want_cv else "") + ("argmin" if want_argmin else "")
     rc = _run(tag, nbytes, lambda: _lib.load().codd_cost_volume(
-        tile_l.data_ptr(), ld_of(tile_l), tile_r.data_ptr(), ld_of(tile_r), n, h, w, max_disp,
+        tile_l.data_ptr(), tile_r.data_ptr(), n, h, w, max_disp,
         None if cv is None else cv.data_ptr(), None if mc is None else mc.data_ptr(),
         None if md is None else md.data_ptr(), _stream()))
     _lib.check(rc, "codd_cost_volume")
@@ -222,12 +242,18 @@ def cost_volume_bytes(n, h, w, max_disp, want_cv, want_argmin):
     return n * h * w * (320 + (4 * max_disp if want_cv else 0) + (8 if want_argmin else 0))
 
 
+def _is_planar(t):
+    return t.is_contiguous() and not (t.shape[1] > 1 and t.stride(1) == 1)
+
+
 def tile_hyp_init(min_cost, min_disp, feat, weight, bias):
+    """feat may be NHWC-backed or planar NCHW (the K2 tile features)."""
     _require_cuda(min_cost, min_disp, feat, weight, bias)
     n, cf, h, w = feat.shape
     hyp = empty_nhwc(n, 16, h, w, feat.device)
+    ldf = 0 if _is_planar(feat) else ld_of(feat)
     rc = _run("tile_hyp_init", 4 * n * h * w * (2 + cf + 16), lambda: _lib.load().codd_tile_hyp_init(
-        min_cost.data_ptr(), min_disp.data_ptr(), feat.data_ptr(), ld_of(feat), cf, weight.data_ptr(), bias.data_ptr(),
+        min_cost.data_ptr(), min_disp.data_ptr(), feat.data_ptr(), ldf, cf, weight.data_ptr(), bias.data_ptr(),
         n, h, w, hyp.data_ptr(), 16, _stream()))
     _lib.check(rc, "codd_tile_hyp_init")
     return hyp
@@ -245,9 +271,19 @@ def plane_upsample(hyp, scale, size):
     return out
 
 
+def planar(t):
+    """Plain contiguous NCHW copy of a feature map (what K4 wants for the right features);
+    a tensor that already is contiguous NCHW is returned as is."""
+    if _is_planar(t):
+        return t
+    return to_nchw(t)
+
+
 def tile_warp_cost(fea_l, fea_r, cur, prev, dec_w, dec_b, want_raw=False):
-    """K4.  Returns aug [N,32|64,h,w] (and the raw 64-ch/set decrease input when want_raw)."""
+    """K4.  Returns aug [N,32|64,h,w] (and the raw 64-ch/set decrease input when want_raw).
+    ``fea_r`` may be NHWC-backed (transposed here) or already planar NCHW (``ops.planar``)."""
     _require_cuda(fea_l, fea_r, cur, prev, dec_w, dec_b)
+    fea_r = planar(fea_r)
     n, c, H, W = fea_l.shape
     _, _, h, w = cur.shape
     if (H, W) != (4 * h, 4 * w) or fea_r.shape != fea_l.shape or cur.shape[1] != 16:
@@ -259,7 +295,7 @@ def tile_warp_cost(fea_l, fea_r, cur, prev, dec_w, dec_b, want_raw=False):
     raw = empty_nhwc(n, 2 * ca, h, w, cur.device) if want_raw else None
     nbytes = tile_warp_bytes(n, c, h, w, prev is not None)
     rc = _run(f"tile_warp_cost_c{c}_sets{2 if prev is not None else 1}", nbytes, lambda: _lib.load().codd_tile_warp_cost(
-        fea_l.data_ptr(), ld_of(fea_l), fea_r.data_ptr(), ld_of(fea_r), c, cur.data_ptr(), ld_of(cur),
+        fea_l.data_ptr(), ld_of(fea_l), fea_r.data_ptr(), c, cur.data_ptr(), ld_of(cur),
         None if prev is None else prev.data_ptr(), 0 if prev is None else ld_of(prev), dec_w.data_ptr(),
         dec_b.data_ptr(), n, h, w, aug.data_ptr(), ca, None if raw is None else raw.data_ptr(), _stream()))
     _lib.check(rc, "codd_tile_warp_cost")

@@ -54,15 +54,10 @@ class TileInitialization(nn.Module):
 
     def _tile_pair(self, seq, fl, fr):
         """initialization.py:119-124: left 4x4/s4; right the same weights at stride (4,1) over the
-        input zero-padded by 3 columns on the right (expressed as an output width of W)."""
+        input zero-padded by 3 columns on the right.  One fused kernel per side (K2), planar out."""
         w0, b0 = self._pw.conv(seq[0])
-        w1, b1 = self._pw.conv(seq[2])
-        n, c, h, w = fl.shape
-        tl = ops.conv2d(fl, w0, b0, 16, 4, (4, 4), (0, 0), 1, ACT_LEAKY)
-        tl = ops.conv2d(tl, w1, b1, 16, 1, act=ACT_LEAKY)
-        tr = ops.conv2d(fr, w0, b0, 16, 4, (4, 1), (0, 0), 1, ACT_LEAKY, out_hw=(h // 4, w))
-        tr = ops.conv2d(tr, w1, b1, 16, 1, act=ACT_LEAKY)
-        return tl, tr
+        w1, b1 = self._pw.raw(seq[2])
+        return ops.tile_features(fl, w0, b0, w1, b1, right=False), ops.tile_features(fr, w0, b0, w1, b1, right=True)
 
     def tile_features(self, fea_l, fea_r):
         fea_l = [ops.to_nhwc(f) for f in fea_l]

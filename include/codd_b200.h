@@ -91,10 +91,23 @@ CODD_API int codd_deconv2x2_nhwc(const float* in, int ldi, int n, int h, int w, 
                         int act, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * K2  tile features (reference: TileInitialization.tile_features, initialization.py:62-95,119-156)
+ *   out = LeakyReLU(conv1x1(LeakyReLU(conv4x4(in) + b0)) + b1), 16 channels, written PLANAR.
+ * in [n,h_in,w_in,cin] NHWC (ldi); right == 0: 4x4 stride (4,4)  -> out [n,16,h_in/4,w_in/4]
+ *                                  right != 0: stride (4,1) over the input zero-padded by 3 columns
+ *                                              on the right      -> out [n,16,h_in/4,w_in]
+ * w0 PACKED [16 taps][cin][16] (w.permute(2,3,1,0)), w1 torch layout [16][16].
+ * ------------------------------------------------------------------------------------------ */
+CODD_API int codd_tile_features(const float* in, int ldi, int cin, int n, int h_in, int w_in,
+                                const float* w0, const float* b0, const float* w1, const float* b1,
+                                int right, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * K1  L1 cost volume + arg-min tile initialisation
  * (reference: calc_init_disp, initialization.py:18-45; torch.min, :167-171).
- *   cv[n,d,i,j] = sum_c | L[n,i,j,c] - R[n,i,4j-d,c] |   (R := 0 when 4j-d < 0), c sequential.
- * tile_l [n,h,w,16], tile_r [n,h,4w,16] NHWC with pixel strides ldl / ldr.
+ *   cv[n,d,i,j] = sum_c | L[n,c,i,j] - R[n,c,i,4j-d] |   (R := 0 when 4j-d < 0), c sequential.
+ * tile_l [n,16,h,w], tile_r [n,16,h,4w]: PLANAR (contiguous NCHW) tile features as written by
+ * codd_tile_features; tile_r must be 16-byte aligned (rows are staged with bulk-TMA copies).
  * Any of cv / min_cost / min_disp may be NULL (not produced).
  *   cv        [n,max_disp,h,w] planar   (the reference's init_cv_pyramid entry)
  *   min_cost  [n,h,w]
@@ -102,13 +115,14 @@ CODD_API int codd_deconv2x2_nhwc(const float* in, int ldi, int n, int h, int w, 
  * Any max_disp >= 1 (the reference uses max_disp // {16,8,4,2,1}); channels fixed at 16
  * (TileInitialization always emits 16).
  * ------------------------------------------------------------------------------------------ */
-CODD_API int codd_cost_volume(const float* tile_l, int ldl, const float* tile_r, int ldr,
+CODD_API int codd_cost_volume(const float* tile_l, const float* tile_r,
                      int n, int h, int w, int max_disp,
                      float* cv, float* min_cost, float* min_disp, void* stream);
 
 /* Tile descriptor + hypothesis assembly (initialization.py:186-208):
  *   hyp[n,i,j,0:16] = [ min_disp, 0, 0, LeakyReLU(W . cat[min_cost, feat] + b) (13 ch) ]
- * feat [n,h,w,cf] NHWC (ldf); weight is the torch layout [13][1+cf]; hyp pixel stride ldh. */
+ * feat [n,h,w,cf] NHWC (ldf > 0) or PLANAR [n,cf,h,w] (ldf == 0, the K2 tile features);
+ * weight is the torch layout [13][1+cf]; hyp pixel stride ldh. */
 CODD_API int codd_tile_hyp_init(const float* min_cost, const float* min_disp, const float* feat, int ldf,
                        int cf, const float* weight, const float* bias,
                        int n, int h, int w, float* hyp, int ldh, void* stream);
@@ -125,7 +139,10 @@ CODD_API int codd_plane_upsample(const float* in, int ldi, int n, int h, int w, 
  * (optionally) the up-sampled previous-level set
  * (reference: TileWarping.forward, propagation.py:61-86; warp :35-58; TileUpdate0.forward
  *  :156-160; TileUpdate.forward :206-219).
- * fea_l / fea_r  [n,H,W,c]  NHWC features of this level (H = 4h, W = 4w), c in {16,24,32}
+ * fea_l          [n,H,W,c]  NHWC left features of this level (H = 4h, W = 4w), c in {16,24,32}
+ * fea_r_planar   [n,c,H,W]  right features, PLANAR (contiguous NCHW): the warp gathers along x per
+ *                channel, which is a contiguous 128-byte request per warp only in this layout
+ *                (codd_nhwc_to_nchw produces it from the backbone's NHWC map)
  * cur            [n,h,w,16] current hypotheses
  * prev           [n,h/2,w/2,16] refined hypotheses of the coarser level, or NULL (TileUpdate0)
  * dec_w [16][64] (torch layout), dec_b [16]: the `decrease` 1x1 conv (input = cat[|fea_l|_1
@@ -136,7 +153,7 @@ CODD_API int codd_plane_upsample(const float* in, int ldi, int n, int h, int w, 
  * raw_cv         optional debug/test output [n,h,w,sets*64]: per set cat[|fea_l|_1 (16), cv48],
  *                the un-reduced `decrease` input (NULL in production).
  * ------------------------------------------------------------------------------------------ */
-CODD_API int codd_tile_warp_cost(const float* fea_l, int ldfl, const float* fea_r, int ldfr, int c,
+CODD_API int codd_tile_warp_cost(const float* fea_l, int ldfl, const float* fea_r_planar, int c,
                         const float* cur, int ldc, const float* prev, int ldp,
                         const float* dec_w, const float* dec_b,
                         int n, int h, int w, float* aug, int ldaug, float* raw_cv,

@@ -32,9 +32,10 @@ def test_library_exports_every_declared_symbol():
 def test_argument_errors_are_reported_without_touching_the_gpu():
     handle = lib.load()
     # null pointers / bad dims are rejected before any CUDA call
-    assert handle.codd_cost_volume(None, 16, None, 16, 1, 1, 1, 4, None, None, None, None) == lib.E_BADARG
+    assert handle.codd_cost_volume(None, None, 1, 1, 1, 4, None, None, None, None) == lib.E_BADARG
     assert handle.codd_plane_upsample(None, 16, 1, 1, 1, 2, 1.0, None, 16, None) == lib.E_BADARG
-    assert handle.codd_cost_volume(16, 12, 16, 16, 1, 1, 1, 8, 16, None, None, None) == lib.E_SHAPE  # ld < 16
+    assert handle.codd_cost_volume(16, 20, 1, 1, 1, 8, 16, None, None, None) == lib.E_ALIGN  # tile_r misaligned
+    assert handle.codd_tile_features(16, 12, 16, 1, 8, 8, 16, 16, 16, 16, 0, 16, None) == lib.E_SHAPE  # ld < cin
 
 
 def test_ops_refuse_cpu_tensors():

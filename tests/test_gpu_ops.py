@@ -117,6 +117,25 @@ def test_tile_conv_right_stride41(ops):
     torch.testing.assert_close(back(ops, out), ref, rtol=CONV_RTOL, atol=CONV_ATOL)
 
 
+@pytest.mark.parametrize("cin,h,w", [(16, 8, 44), (24, 16, 132), (32, 4, 520), (16, 12, 2052)])
+def test_tile_features_fused(ops, cin, h, w):
+    """K2: conv4x4 (stride 4 / stride (4,1) + right zero pad 3) -> LReLU -> conv1x1 -> LReLU, planar out."""
+    g = gen(cin + h + w)
+    x = torch.randn(2, cin, h, w, generator=g)
+    w0 = torch.randn(16, cin, 4, 4, generator=g) / (cin * 16) ** 0.5
+    b0 = torch.randn(16, generator=g)
+    w1 = torch.randn(16, 16, 1, 1, generator=g) / 4
+    b1 = torch.randn(16, generator=g)
+    sd = {"t.0.weight": w0, "t.0.bias": b0, "t.2.weight": w1, "t.2.bias": b1}
+    ref_l, ref_r = O.tile_features_level(sd, "t", x, x)
+    args = (ops.pack_conv_weight(w0).cuda(), b0.cuda(), w1.cuda().contiguous(), b1.cuda())
+    out_l = ops.tile_features(nhwc(ops, x), *args, right=False)
+    out_r = ops.tile_features(nhwc(ops, x), *args, right=True)
+    assert out_l.is_contiguous() and out_l.shape == ref_l.shape and out_r.shape == ref_r.shape
+    torch.testing.assert_close(out_l.cpu(), ref_l, rtol=CONV_RTOL, atol=CONV_ATOL)
+    torch.testing.assert_close(out_r.cpu(), ref_r, rtol=CONV_RTOL, atol=CONV_ATOL)
+
+
 def test_image_conv_and_deconv(ops):
     g = gen(9)
     l = torch.randn(2, 3, 21, 45, generator=g)
@@ -138,7 +157,7 @@ def test_image_conv_and_deconv(ops):
 # ------------------------------------------------------------------------------------------
 # K1: bit-exact
 # ------------------------------------------------------------------------------------------
-CV_CASES = [(1, 2, 2, 4), (1, 2, 5, 2), (2, 3, 9, 6), (1, 2, 40, 21), (2, 9, 15, 12), (1, 5, 33, 32), (2, 3, 40, 48), (1, 4, 70, 192), (1, 2, 240, 192),
+CV_CASES = [(1, 2, 2, 4), (1, 2, 5, 2), (2, 3, 9, 6), (1, 2, 40, 21), (1, 2, 3, 1), (1, 1, 600, 320), (2, 9, 15, 12), (1, 5, 33, 32), (2, 3, 40, 48), (1, 4, 70, 192), (1, 2, 240, 192),
             (1, 2, 300, 64), (1, 1, 500, 256), (1, 3, 7, 64)]
 
 
@@ -192,10 +211,11 @@ def test_tile_hyp_init(ops):
         b = torch.randn(13, generator=g)
         dsc = F.leaky_relu(F.conv2d(torch.cat([cost, feat], 1), w, b), 0.2)
         ref = torch.cat([disp, torch.zeros_like(disp), torch.zeros_like(disp), dsc], 1)
-        out = ops.tile_hyp_init(cost.cuda(), disp.cuda(), nhwc(ops, feat), w.cuda().contiguous(), b.cuda())
-        got = back(ops, out)
-        assert torch.equal(got[:, :3], ref[:, :3])
-        torch.testing.assert_close(got[:, 3:], ref[:, 3:], rtol=CONV_RTOL, atol=CONV_ATOL)
+        for f in (nhwc(ops, feat), feat.cuda()):      # NHWC-backed and planar feature inputs
+            out = ops.tile_hyp_init(cost.cuda(), disp.cuda(), f, w.cuda().contiguous(), b.cuda())
+            got = back(ops, out)
+            assert torch.equal(got[:, :3], ref[:, :3])
+            torch.testing.assert_close(got[:, 3:], ref[:, 3:], rtol=CONV_RTOL, atol=CONV_ATOL)
 
 
 # ------------------------------------------------------------------------------------------

@@ -37,8 +37,8 @@ def main():
             levels = []
             for k in range(5):
                 h, w = (H >> (4 - k)) // 4, (W >> (4 - k)) // 4
-                tl = ops.to_nhwc(torch.randn(a.batch, 16, h, w, device=dev))
-                tr = ops.to_nhwc(torch.randn(a.batch, 16, h, 4 * w, device=dev))
+                tl = torch.randn(a.batch, 16, h, w, device=dev)          # planar, as K2 writes them
+                tr = torch.randn(a.batch, 16, h, 4 * w, device=dev)
                 levels.append((tl, tr, D // (16 >> k), h, w))
             for want_cv in (True, False):
                 nbytes = sum(ops.cost_volume_bytes(a.batch, h, w, d, want_cv, True) for _, _, d, h, w in levels)
