@@ -188,7 +188,7 @@ int launch_conv(ConvP p, int PWn, int G, cudaStream_t stream) {
         return (size_t)(IH * IW * CP + KH * KW * CK * G * CO_T) * sizeof(float);
     };
     // keep the stage under ~100 KB so two CTAs fit on an SM; shrink the row count if needed
-    while (PWn > 1 && smem_for(PWn) > 100 * 1024) PWn >>= 1;
+    while (PWn > 1 && smem_for(PWn) > 110 * 1024) PWn >>= 1;
     // do not launch row-warps that would only see padding
     while (PWn > 1 && (PWn / 2) * PX >= p.Ho) PWn >>= 1;
     const size_t smem = smem_for(PWn);
@@ -228,14 +228,107 @@ int dispatch_cout(const ConvP& p, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// 1x1 convolutions (merge*.0, conv0, conv1.0): a per-pixel GEMV.  No activation staging: every
+// thread streams its own PX pixels (128-bit loads straight from the two concatenated sources),
+// the whole [Cin][Cout] weight matrix sits in shared memory and is read as warp-uniform
+// broadcasts.  HBM-bound (AI = 2*Cin*Cout / (4*(Cin+Cout)) < 12 flop/B for every layer here).
+// ---------------------------------------------------------------------------------------------
+template <int CO, int PX_T>
+__global__ void __launch_bounds__(256) pointwise_kernel(ConvP p, size_t npix) {
+    extern __shared__ float4 smem4[];
+    float* s_w = reinterpret_cast<float*>(smem4);  // [Cin][CO]
+    const int Cin = p.C0 + p.C1;
+    for (int i = threadIdx.x; i < Cin * CO; i += blockDim.x) {
+        const int co = i % CO, ci = i / CO;
+        s_w[i] = co < p.Cout ? __ldg(p.w + (size_t)ci * p.Cout + co) : 0.f;
+    }
+    __syncthreads();
+    const size_t base = (size_t)blockIdx.x * (blockDim.x * PX_T) + threadIdx.x;
+    float acc[PX_T][CO];
+#pragma unroll
+    for (int q = 0; q < PX_T; ++q)
+#pragma unroll
+        for (int c = 0; c < CO; ++c) acc[q][c] = 0.f;
+    size_t pix[PX_T];
+#pragma unroll
+    for (int q = 0; q < PX_T; ++q) pix[q] = min(base + (size_t)q * blockDim.x, npix - 1);
+
+    for (int c = 0; c < Cin; c += 4) {
+        float4 a[PX_T];
+        const bool first = c < p.C0;
+#pragma unroll
+        for (int q = 0; q < PX_T; ++q)
+            a[q] = first ? ldg4(p.in0 + pix[q] * p.ld0 + c) : ldg4(p.in1 + pix[q] * p.ld1 + (c - p.C0));
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const float* wp = s_w + (c + cc) * CO;
+#pragma unroll
+            for (int o4 = 0; o4 < CO / 4; ++o4) {
+                const float4 wv = *reinterpret_cast<const float4*>(wp + o4 * 4);
+#pragma unroll
+                for (int q = 0; q < PX_T; ++q) {
+                    const float av = cc == 0 ? a[q].x : cc == 1 ? a[q].y : cc == 2 ? a[q].z : a[q].w;
+                    acc[q][o4 * 4 + 0] = fmaf(av, wv.x, acc[q][o4 * 4 + 0]);
+                    acc[q][o4 * 4 + 1] = fmaf(av, wv.y, acc[q][o4 * 4 + 1]);
+                    acc[q][o4 * 4 + 2] = fmaf(av, wv.z, acc[q][o4 * 4 + 2]);
+                    acc[q][o4 * 4 + 3] = fmaf(av, wv.w, acc[q][o4 * 4 + 3]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < PX_T; ++q) {
+        const size_t px = base + (size_t)q * blockDim.x;
+        if (px >= npix) continue;
+        float* op = p.out + px * p.ldo;
+        float rb = 0.f;
+        if (p.res && p.res_bcast) rb = __ldg(p.res + px * p.ldr);
+#pragma unroll
+        for (int o4 = 0; o4 < CO / 4; ++o4) {
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int ce = o4 * 4 + e;
+                float t = acc[q][ce];
+                if (ce < p.Cout) {
+                    if (p.bias) t += __ldg(p.bias + ce);
+                    if (p.res) t += p.res_bcast ? rb : __ldg(p.res + px * p.ldr + ce);
+                    t = codd_act(t, p.act, ce);
+                }
+                v[e] = t;
+            }
+            if (o4 * 4 + 3 < p.Cout) {
+                *reinterpret_cast<float4*>(op + o4 * 4) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (o4 * 4 + e < p.Cout) op[o4 * 4 + e] = v[e];
+            }
+        }
+    }
+}
+
+template <int CO, int PX_T>
+int launch_pointwise(const ConvP& p, cudaStream_t s) {
+    const size_t npix = (size_t)p.N * p.H * p.W;
+    const size_t smem = (size_t)(p.C0 + p.C1) * CO * sizeof(float);
+    const unsigned grid = (unsigned)((npix + 256 * PX_T - 1) / (256 * PX_T));
+    pointwise_kernel<CO, PX_T><<<grid, 256, smem, s>>>(p, npix);
+    CODD_RETURN_IF_CUDA_ERROR();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // first layer: NCHW image (3 ch) -> NHWC, 3x3 pad 1, LeakyReLU
 // ---------------------------------------------------------------------------------------------
 template <int CO>
-__global__ void __launch_bounds__(256) conv3x3_image_kernel(const float* __restrict__ left,
+__global__ void __launch_bounds__(128) conv3x3_image_kernel(const float* __restrict__ left,
                                                             const float* __restrict__ right, int n, int h,
                                                             int w, const float* __restrict__ wgt,
                                                             const float* __restrict__ bias, int cout,
                                                             float* __restrict__ out, int ldo) {
+    // each thread computes 4 horizontally adjacent pixels: one weight broadcast feeds 4 FMAs
+    constexpr int PXI = 4;
     __shared__ __align__(16) float s_w[27 * CO];
     __shared__ float s_b[CO];
     for (int i = threadIdx.x; i < 27 * CO; i += blockDim.x) {
@@ -244,46 +337,60 @@ __global__ void __launch_bounds__(256) conv3x3_image_kernel(const float* __restr
     }
     for (int i = threadIdx.x; i < CO; i += blockDim.x) s_b[i] = i < cout ? bias[i] : 0.f;
     __syncthreads();
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * PXI;
     const int y = blockIdx.y;
     const int s = blockIdx.z;  // sample in [0, 2n)
-    if (x >= w) return;
+    if (x0 >= w) return;
     const float* img = (s < n ? left + (size_t)s * 3 * h * w : right + (size_t)(s - n) * 3 * h * w);
-    float acc[CO];
+    float acc[PXI][CO];
 #pragma unroll
-    for (int i = 0; i < CO; ++i) acc[i] = s_b[i];
+    for (int q = 0; q < PXI; ++q)
+#pragma unroll
+        for (int i = 0; i < CO; ++i) acc[q][i] = s_b[i];
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
         const int yy = y + ky - 1;
         if (yy < 0 || yy >= h) continue;
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-            const int xx = x + kx - 1;
-            if (xx < 0 || xx >= w) continue;
+        for (int ci = 0; ci < 3; ++ci) {
+            const float* rp = img + ((size_t)ci * h + yy) * w;
+            float a[PXI + 2];
 #pragma unroll
-            for (int ci = 0; ci < 3; ++ci) {
-                const float a = __ldg(img + ((size_t)ci * h + yy) * w + xx);
+            for (int e = 0; e < PXI + 2; ++e) {
+                const int xx = x0 + e - 1;
+                a[e] = (xx >= 0 && xx < w) ? __ldg(rp + xx) : 0.f;
+            }
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
                 const float* wp = s_w + ((ky * 3 + kx) * 3 + ci) * CO;
 #pragma unroll
                 for (int o4 = 0; o4 < CO / 4; ++o4) {
                     const float4 wv = *reinterpret_cast<const float4*>(wp + o4 * 4);
-                    acc[o4 * 4 + 0] = fmaf(a, wv.x, acc[o4 * 4 + 0]);
-                    acc[o4 * 4 + 1] = fmaf(a, wv.y, acc[o4 * 4 + 1]);
-                    acc[o4 * 4 + 2] = fmaf(a, wv.z, acc[o4 * 4 + 2]);
-                    acc[o4 * 4 + 3] = fmaf(a, wv.w, acc[o4 * 4 + 3]);
+#pragma unroll
+                    for (int q = 0; q < PXI; ++q) {
+                        acc[q][o4 * 4 + 0] = fmaf(a[q + kx], wv.x, acc[q][o4 * 4 + 0]);
+                        acc[q][o4 * 4 + 1] = fmaf(a[q + kx], wv.y, acc[q][o4 * 4 + 1]);
+                        acc[q][o4 * 4 + 2] = fmaf(a[q + kx], wv.z, acc[q][o4 * 4 + 2]);
+                        acc[q][o4 * 4 + 3] = fmaf(a[q + kx], wv.w, acc[q][o4 * 4 + 3]);
+                    }
                 }
             }
         }
     }
-    float* op = out + (((size_t)s * h + y) * w + x) * ldo;
-    if ((ldo & 3) == 0 && cout == CO && ((((uintptr_t)out) & 15u) == 0)) {
+    const bool vec = (ldo & 3) == 0 && cout == CO && ((((uintptr_t)out) & 15u) == 0);
 #pragma unroll
-        for (int o4 = 0; o4 < CO / 4; ++o4)
-            *reinterpret_cast<float4*>(op + o4 * 4) =
-                make_float4(codd_act(acc[o4 * 4], CODD_ACT_LEAKY, 0), codd_act(acc[o4 * 4 + 1], CODD_ACT_LEAKY, 0),
-                            codd_act(acc[o4 * 4 + 2], CODD_ACT_LEAKY, 0), codd_act(acc[o4 * 4 + 3], CODD_ACT_LEAKY, 0));
-    } else {
-        for (int i = 0; i < cout; ++i) op[i] = codd_act(acc[i], CODD_ACT_LEAKY, 0);
+    for (int q = 0; q < PXI; ++q) {
+        if (x0 + q >= w) break;
+        float* op = out + (((size_t)s * h + y) * w + x0 + q) * ldo;
+        if (vec) {
+#pragma unroll
+            for (int o4 = 0; o4 < CO / 4; ++o4)
+                *reinterpret_cast<float4*>(op + o4 * 4) = make_float4(
+                    codd_act(acc[q][o4 * 4], CODD_ACT_LEAKY, 0), codd_act(acc[q][o4 * 4 + 1], CODD_ACT_LEAKY, 0),
+                    codd_act(acc[q][o4 * 4 + 2], CODD_ACT_LEAKY, 0), codd_act(acc[q][o4 * 4 + 3], CODD_ACT_LEAKY, 0));
+        } else {
+            for (int i = 0; i < cout; ++i) op[i] = codd_act(acc[q][i], CODD_ACT_LEAKY, 0);
+        }
     }
 }
 
@@ -291,10 +398,13 @@ __global__ void __launch_bounds__(256) conv3x3_image_kernel(const float* __restr
 // ConvTranspose2d k=2 s=2: every output pixel sees exactly one input pixel and one of 4 taps
 // ---------------------------------------------------------------------------------------------
 template <int CO>
-__global__ void __launch_bounds__(256) deconv2x2_kernel(const float* __restrict__ in, int ldi, int n, int h,
+__global__ void __launch_bounds__(128) deconv2x2_kernel(const float* __restrict__ in, int ldi, int n, int h,
                                                         int w, int cin, const float* __restrict__ wgt,
                                                         const float* __restrict__ bias, int cout,
                                                         float* __restrict__ out, int ldo, int act) {
+    // one thread per INPUT pixel and output-row parity dy: it produces the two output pixels
+    // (2y+dy, 2x) and (2y+dy, 2x+1); the input pixel is read once per dy, and every weight
+    // broadcast (warp-uniform: dy is the block's) feeds both outputs' channels.
     extern __shared__ float4 smem4[];
     float* s_w = reinterpret_cast<float*>(smem4);  // [4][cin][CO]
     for (int i = threadIdx.x; i < 4 * cin * CO; i += blockDim.x) {
@@ -302,34 +412,58 @@ __global__ void __launch_bounds__(256) deconv2x2_kernel(const float* __restrict_
         s_w[i] = co < cout ? wgt[(size_t)t * cout + co] : 0.f;
     }
     __syncthreads();
-    const int ox = blockIdx.x * blockDim.x + threadIdx.x;
-    const int oy = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int oy = blockIdx.y;          // output row
     const int s = blockIdx.z;
-    if (ox >= 2 * w) return;
-    const int tap = (oy & 1) * 2 + (ox & 1);
-    const float* ip = in + (((size_t)s * h + (oy >> 1)) * w + (ox >> 1)) * ldi;
-    float acc[CO];
+    if (x >= w) return;
+    const int dy = oy & 1;
+    const float* ip = in + (((size_t)s * h + (oy >> 1)) * w + x) * ldi;
+    float acc[2][CO];
 #pragma unroll
-    for (int i = 0; i < CO; ++i) acc[i] = 0.f;
-    const float* wt = s_w + tap * cin * CO;
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int i = 0; i < CO; ++i) acc[q][i] = 0.f;
+    const float* w0 = s_w + (dy * 2 + 0) * cin * CO;
+    const float* w1 = s_w + (dy * 2 + 1) * cin * CO;
     for (int ci = 0; ci < cin; ci += 4) {
         const float4 a4 = ldg4(ip + ci);
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
             const float a = cc == 0 ? a4.x : cc == 1 ? a4.y : cc == 2 ? a4.z : a4.w;
-            const float* wp = wt + (ci + cc) * CO;
 #pragma unroll
             for (int o4 = 0; o4 < CO / 4; ++o4) {
-                const float4 wv = *reinterpret_cast<const float4*>(wp + o4 * 4);
-                acc[o4 * 4 + 0] = fmaf(a, wv.x, acc[o4 * 4 + 0]);
-                acc[o4 * 4 + 1] = fmaf(a, wv.y, acc[o4 * 4 + 1]);
-                acc[o4 * 4 + 2] = fmaf(a, wv.z, acc[o4 * 4 + 2]);
-                acc[o4 * 4 + 3] = fmaf(a, wv.w, acc[o4 * 4 + 3]);
+                const float4 u = *reinterpret_cast<const float4*>(w0 + (ci + cc) * CO + o4 * 4);
+                const float4 v = *reinterpret_cast<const float4*>(w1 + (ci + cc) * CO + o4 * 4);
+                acc[0][o4 * 4 + 0] = fmaf(a, u.x, acc[0][o4 * 4 + 0]);
+                acc[0][o4 * 4 + 1] = fmaf(a, u.y, acc[0][o4 * 4 + 1]);
+                acc[0][o4 * 4 + 2] = fmaf(a, u.z, acc[0][o4 * 4 + 2]);
+                acc[0][o4 * 4 + 3] = fmaf(a, u.w, acc[0][o4 * 4 + 3]);
+                acc[1][o4 * 4 + 0] = fmaf(a, v.x, acc[1][o4 * 4 + 0]);
+                acc[1][o4 * 4 + 1] = fmaf(a, v.y, acc[1][o4 * 4 + 1]);
+                acc[1][o4 * 4 + 2] = fmaf(a, v.z, acc[1][o4 * 4 + 2]);
+                acc[1][o4 * 4 + 3] = fmaf(a, v.w, acc[1][o4 * 4 + 3]);
             }
         }
     }
-    float* op = out + (((size_t)s * 2 * h + oy) * 2 * w + ox) * ldo;
-    for (int i = 0; i < cout; ++i) op[i] = codd_act(acc[i] + __ldg(bias + i), act, i);
+    float* op = out + (((size_t)s * 2 * h + oy) * 2 * w + 2 * x) * ldo;
+    const bool vec = (ldo & 3) == 0 && (cout & 3) == 0 && ((((uintptr_t)out) & 15u) == 0);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        if (vec) {
+#pragma unroll
+            for (int o4 = 0; o4 < CO / 4; ++o4) {
+                if (o4 * 4 >= cout) break;
+                float4 r;
+                r.x = codd_act(acc[q][o4 * 4 + 0] + __ldg(bias + o4 * 4 + 0), act, o4 * 4 + 0);
+                r.y = codd_act(acc[q][o4 * 4 + 1] + __ldg(bias + o4 * 4 + 1), act, o4 * 4 + 1);
+                r.z = codd_act(acc[q][o4 * 4 + 2] + __ldg(bias + o4 * 4 + 2), act, o4 * 4 + 2);
+                r.w = codd_act(acc[q][o4 * 4 + 3] + __ldg(bias + o4 * 4 + 3), act, o4 * 4 + 3);
+                *reinterpret_cast<float4*>(op + q * ldo + o4 * 4) = r;
+            }
+        } else {
+            for (int i = 0; i < cout; ++i) op[q * ldo + i] = codd_act(acc[q][i] + __ldg(bias + i), act, i);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -410,10 +544,23 @@ extern "C" int codd_conv2d_nhwc(const codd_conv_desc* d, const float* in0, const
     p.vec1 = p.in1 && codd_aligned16(in1) && (d->ld1 % 4 == 0) && (d->c0 % 4 == 0);
     cudaStream_t s = (cudaStream_t)stream;
     const int kh = d->kh, kw = d->kw, sh = d->sh, sw = d->sw, dil = d->dil;
+    if (kh == 1 && kw == 1 && sh == 1 && sw == 1 && d->ph == 0 && d->pw == 0 && d->ho == d->h && d->wo == d->w) {
+        const bool vec_ok = p.vec0 && (d->c0 % 4 == 0) && (p.C1 == 0 || (p.vec1 && d->c1 % 4 == 0)) &&
+                            codd_aligned16(out) && (d->ldo % 4 == 0) && (d->c0 + p.C1) * 32 * 4 <= 48 * 1024;
+        if (vec_ok && d->cout <= 16) return launch_pointwise<16, 4>(p, s);
+        if (vec_ok && d->cout <= 24) return launch_pointwise<24, 2>(p, s);
+        if (vec_ok && d->cout <= 32) return launch_pointwise<32, 2>(p, s);
+    }
     if (kh == 1 && kw == 1 && sh == 1 && sw == 1) return dispatch_cout<1, 1, 1, 1, 1, true>(p, s);
     if (kh == 3 && kw == 3 && sh == 1 && sw == 1 && dil == 1) return dispatch_cout<3, 3, 1, 1, 1, true>(p, s);
     if (kh == 3 && kw == 3 && sh == 1 && sw == 1 && dil == 3) return dispatch_cout<3, 3, 1, 1, 3, false>(p, s);
-    if (kh == 4 && kw == 4 && sh == 2 && sw == 2 && dil == 1) return dispatch_cout<4, 4, 2, 2, 1, false>(p, s);
+    if (kh == 4 && kw == 4 && sh == 2 && sw == 2 && dil == 1) {
+        // the stride-2 stage is wide (66 input columns); split the output channels over warps so that
+        // a full 256-thread CTA shares it
+        if (d->cout <= 16) return launch_conv<4, 4, 2, 2, 1, 8>(p, 4, 2, s);
+        if (d->cout <= 24) return launch_conv<4, 4, 2, 2, 1, 8>(p, 2, 3, s);
+        return dispatch_cout<4, 4, 2, 2, 1, false>(p, s);
+    }
     if (kh == 4 && kw == 4 && sh == 4 && sw == 4 && dil == 1) return dispatch_cout<4, 4, 4, 4, 1, false>(p, s);
     if (kh == 4 && kw == 4 && sh == 4 && sw == 1 && dil == 1) return dispatch_cout<4, 4, 4, 1, 1, false>(p, s);
     if (kh == 7 && kw == 7 && sh == 1 && sw == 1 && dil == 1) return dispatch_cout<7, 7, 1, 1, 1, false>(p, s);
@@ -424,8 +571,8 @@ extern "C" int codd_conv3x3_image(const float* left, const float* right, int n, 
                                   const float* bias, int cout, float* out, int ldo, void* stream) {
     if (!left || !weight || !bias || !out || n <= 0 || h <= 0 || w <= 0) return CODD_E_BADARG;
     if (cout <= 0 || cout > 16 || ldo < cout) return CODD_E_SHAPE;
-    dim3 block(128);
-    dim3 grid(codd_ceil_div(w, 128), h, right ? 2 * n : n);
+    dim3 block(64);
+    dim3 grid(codd_ceil_div(w, 64 * 4), h, right ? 2 * n : n);
     conv3x3_image_kernel<16><<<grid, block, 0, (cudaStream_t)stream>>>(left, right ? right : left, n, h, w, weight,
                                                                         bias, cout, out, ldo);
     CODD_RETURN_IF_CUDA_ERROR();
@@ -438,7 +585,7 @@ extern "C" int codd_deconv2x2_nhwc(const float* in, int ldi, int n, int h, int w
     if (cin % 4 != 0 || ldi % 4 != 0 || ldi < cin || ldo < cout || cout > 32) return CODD_E_SHAPE;
     if (!codd_aligned16(in)) return CODD_E_ALIGN;
     dim3 block(128);
-    dim3 grid(codd_ceil_div(2 * w, 128), 2 * h, n);
+    dim3 grid(codd_ceil_div(w, 128), 2 * h, n);
     cudaStream_t s = (cudaStream_t)stream;
     if (cout <= 16) {
         deconv2x2_kernel<16><<<grid, block, 4 * cin * 16 * sizeof(float), s>>>(in, ldi, n, h, w, cin, weight, bias,

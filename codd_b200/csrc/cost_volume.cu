@@ -35,12 +35,16 @@
 //   * shifts that fall off the left edge (m < 0, i.e. d >= 4j+1) need no work: their cost is
 //     |L|_1 for every d, computed once per column; it enters the arg-min as the single candidate
 //     d = 4j+1 (merged last) and the materialising variant fills it in from a per-column table.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace {
 
 constexpr int CV_C = 16;        // tile-feature channels (TileInitialization always emits 16)
 constexpr int CV_MAXW = 8;      // warps per CTA (one lane per m)
+constexpr int CV_LW = CV_MAXW * 32 + 8;   // shared row stride of the staged left features (compile-time:
+                                          // the 16 per-step channel reads become immediate offsets)
 
 struct CvP {
     const float* L;   // [N,16,h,w]
@@ -73,11 +77,12 @@ __global__ void __launch_bounds__(CV_MAXW * 32, 2) cost_volume_kernel(CvP p) {
     const int W = 4 * p.w;
     const size_t plane = (size_t)p.h * p.w;
 
-    // shared layout: S[c][RW] (right row, x - 4*mlo), l1[LW], partial cost/disp [nwarps][LW]
+    // shared layout: S[c][RW] (right row, x - 4*mlo), Lp[c][CV_LW], l1[LW], partial cost/disp [nwarps][LW]
     const int RW = 4 * nm + 4;                   // +4: keeps rows 16-byte aligned and de-phased
     const int LW = (nj + 3) & ~3;
     float* S = reinterpret_cast<float*>(smem4);
-    float* l1 = S + CV_C * RW;
+    float* Lp = S + CV_C * RW;
+    float* l1 = Lp + CV_C * CV_LW;
     float* pc = l1 + LW;
     const int nwarps = blockDim.x >> 5;
     float* pd = pc + nwarps * LW;
@@ -105,11 +110,18 @@ __global__ void __launch_bounds__(CV_MAXW * 32, 2) cost_volume_kernel(CvP p) {
                 : "memory");
         }
     }
-    // meanwhile: per-column |L|_1 (channel-sequential) and the partial tables
+    // meanwhile: stage L (planar -> planar, coalesced), per-column |L|_1 (channel-sequential)
     for (int jj = tid; jj < nj; jj += blockDim.x) {
-        float a = fabsf(__ldg(Lrow + jb + jj));
+        float lv[CV_C];
 #pragma unroll
-        for (int c = 1; c < CV_C; ++c) a = __fadd_rn(a, fabsf(__ldg(Lrow + (size_t)c * plane + jb + jj)));
+        for (int c = 0; c < CV_C; ++c) lv[c] = __ldg(Lrow + (size_t)c * plane + jb + jj);
+        float a = fabsf(lv[0]);
+        Lp[jj] = lv[0];
+#pragma unroll
+        for (int c = 1; c < CV_C; ++c) {
+            a = __fadd_rn(a, fabsf(lv[c]));
+            Lp[c * CV_LW + jj] = lv[c];
+        }
         l1[jj] = a;
     }
     if (ARGMIN)
@@ -153,54 +165,63 @@ __global__ void __launch_bounds__(CV_MAXW * 32, 2) cost_volume_kernel(CvP p) {
     float bd = 0.f;
     float* cvrow = WRITE_CV ? p.cv + (size_t)n * p.D * plane + (size_t)i * p.w : nullptr;
 
-    if (m0 < je) {  // warp-uniform
-#pragma unroll 2
-        for (int q = 0; q <= qmax; ++q) {
-            const int j = m + q;
-            const bool on = lane_on && j >= jb && j < je;
-            if (on) {
-                const float* lp = Lrow + j;
-                // lo = (r=0, r=1) <-> d = (4q, 4q-1);  hi = (r=2, r=3) <-> d = (4q-2, 4q-3)
-                float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
+    // one step of the walk; FULL: all four disparities 4q-3..4q lie in [0, D)
+    auto step = [&](const int q, auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
+        const int j = m + q;
+        const bool on = lane_on && j >= jb && j < je;
+        if (on) {
+            const float* lp = Lp + (j - jb);
+            // lo = (r=0, r=1) <-> d = (4q, 4q-1);  hi = (r=2, r=3) <-> d = (4q-2, 4q-3)
+            float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int c = 0; c < CV_C; ++c) {
-                    const float l = __ldg(lp + (size_t)c * plane);
-                    const float2 ll = make_float2(l, l);
-                    float2 d0 = __fadd2_rn(ll, make_float2(-rq[c][0].x, -rq[c][0].y));
-                    float2 d1 = __fadd2_rn(ll, make_float2(-rq[c][1].x, -rq[c][1].y));
-                    lo = __fadd2_rn(lo, make_float2(fabsf(d0.x), fabsf(d0.y)));
-                    hi = __fadd2_rn(hi, make_float2(fabsf(d1.x), fabsf(d1.y)));
-                }
-                const int d0i = 4 * q;   // disparity of r = 0; the r-th cost belongs to d0i - r
-                const float c0 = lo.x, c1 = lo.y, c2 = hi.x, c3 = hi.y;
-                const bool v0 = d0i < p.D, v1 = (d0i >= 1) && (d0i - 1 < p.D), v2 = (d0i >= 2) && (d0i - 2 < p.D),
-                           v3 = (d0i >= 3) && (d0i - 3 < p.D);
-                if (WRITE_CV) {
-                    float* o = cvrow + (ptrdiff_t)d0i * (ptrdiff_t)plane + j;
-                    if (v3) __stcs(o - 3 * plane, c3);
-                    if (v2) __stcs(o - 2 * plane, c2);
-                    if (v1) __stcs(o - plane, c1);
-                    if (v0) __stcs(o, c0);
-                }
-                if (ARGMIN) {
-                    const float dq = (float)d0i;
-                    if (v3 && c3 < bc) { bc = c3; bd = dq - 3.f; }
-                    if (v2 && c2 < bc) { bc = c2; bd = dq - 2.f; }
-                    if (v1 && c1 < bc) { bc = c1; bd = dq - 1.f; }
-                    if (v0 && c0 < bc) { bc = c0; bd = dq; }
-                }
+            for (int c = 0; c < CV_C; ++c) {
+                const float l = lp[c * CV_LW];
+                const float2 ll = make_float2(l, l);
+                float2 d0 = __fadd2_rn(ll, make_float2(-rq[c][0].x, -rq[c][0].y));
+                float2 d1 = __fadd2_rn(ll, make_float2(-rq[c][1].x, -rq[c][1].y));
+                lo = __fadd2_rn(lo, make_float2(fabsf(d0.x), fabsf(d0.y)));
+                hi = __fadd2_rn(hi, make_float2(fabsf(d1.x), fabsf(d1.y)));
+            }
+            const int d0i = 4 * q;   // disparity of r = 0; the r-th cost belongs to d0i - r
+            const float c0 = lo.x, c1 = lo.y, c2 = hi.x, c3 = hi.y;
+            const bool v0 = FULL || d0i < p.D;
+            const bool v1 = FULL || ((d0i >= 1) && (d0i - 1 < p.D));
+            const bool v2 = FULL || ((d0i >= 2) && (d0i - 2 < p.D));
+            const bool v3 = FULL || ((d0i >= 3) && (d0i - 3 < p.D));
+            if (WRITE_CV) {
+                float* o = cvrow + (ptrdiff_t)d0i * (ptrdiff_t)plane + j;
+                if (v3) __stcs(o - 3 * plane, c3);
+                if (v2) __stcs(o - 2 * plane, c2);
+                if (v1) __stcs(o - plane, c1);
+                if (v0) __stcs(o, c0);
             }
             if (ARGMIN) {
-                // column j leaves the warp through lane 0; everything else moves one lane down
-                if (lane == 0 && on) {
-                    pc[warp * LW + (j - jb)] = bc;
-                    pd[warp * LW + (j - jb)] = bd;
-                }
-                bc = __shfl_down_sync(0xffffffffu, bc, 1);
-                bd = __shfl_down_sync(0xffffffffu, bd, 1);
-                if (lane == 31) { bc = INFINITY; bd = 0.f; }
+                const float dq = (float)d0i;
+                if (v3 && c3 < bc) { bc = c3; bd = dq - 3.f; }
+                if (v2 && c2 < bc) { bc = c2; bd = dq - 2.f; }
+                if (v1 && c1 < bc) { bc = c1; bd = dq - 1.f; }
+                if (v0 && c0 < bc) { bc = c0; bd = dq; }
             }
         }
+        if (ARGMIN) {
+            // column j leaves the warp through lane 0; everything else moves one lane down
+            if (lane == 0 && on) {
+                pc[warp * LW + (j - jb)] = bc;
+                pd[warp * LW + (j - jb)] = bd;
+            }
+            bc = __shfl_down_sync(0xffffffffu, bc, 1);
+            bd = __shfl_down_sync(0xffffffffu, bd, 1);
+            if (lane == 31) { bc = INFINITY; bd = 0.f; }
+        }
+    };
+
+    if (m0 < je) {  // warp-uniform
+        const int qfull = min((p.D - 1) >> 2, qmax);     // q in [1, qfull]: all four disparities valid
+        step(0, std::false_type{});
+#pragma unroll 2
+        for (int q = 1; q <= qfull; ++q) step(q, std::true_type{});
+        for (int q = max(qfull, 0) + 1; q <= qmax; ++q) step(q, std::false_type{});
         if (ARGMIN) {
             // columns still in flight: lane now holds the state of column m + qmax + 1
             const int j = m + qmax + 1;
@@ -261,7 +282,7 @@ extern "C" int codd_cost_volume(const float* tile_l, const float* tile_r, int n,
     const int nwarps = codd_ceil_div(nm, 32);
     const int RW = 4 * nm + 4;
     const int LW = (JB + 3) & ~3;
-    const size_t smem = (size_t)(CV_C * RW + LW + 2 * nwarps * LW) * sizeof(float);
+    const size_t smem = (size_t)(CV_C * RW + CV_C * CV_LW + LW + 2 * nwarps * LW) * sizeof(float);
     if (smem > 227 * 1024) return CODD_E_SHAPE;
 
     CvP p;
