@@ -1,0 +1,414 @@
+// 3x3 / stride 1 / pad 1 convolution on the 5th-generation tensor cores (tcgen05, sm_100a).
+//
+// Replaces the dense 3x3 layers of HITUNet and of the tile-update networks
+// (model/stereo/hitnet/backbone.py:8-39; propagation.py:89-121,258-323) — 55 % of the stereo step
+// when run on the fp32 CUDA cores (conv.cu), where they are FMA-bound.
+//
+// Implicit GEMM, NHWC fp32 activations:
+//   M = 128 output pixels of one image row, N = Cout (padded to 16/32), K = Cin per filter tap.
+//   * a persistent CTA (one per SM) keeps ALL weights resident in shared memory
+//     ([pass][tap][cout][cin], K-major, 128B/64B-swizzled) and loops over output tiles of
+//     2 rows x 128 columns;
+//   * the (2+2) x (128+2) x Cin input halo tile of a step arrives by ONE 4-D TMA load
+//     (cp.async.bulk.tensor, out-of-bounds = zero fill = the convolution's zero padding;
+//     channels 24..31 of a 24-channel tensor are zero-filled the same way) into a
+//     double-buffered, hardware-swizzled stage: one pixel = one swizzle row, so the A operand
+//     of tap (ky,kx) is the same stage viewed from a start address shifted by
+//     (ky*130 + kx) pixels — no im2col, no per-tap copies;
+//   * tcgen05.mma.kind::tf32 (M128 x N x K8) issued by one thread, accumulators in TMEM
+//     (double-buffered: 2 tiles x 2 rows x N columns), completion tracked with tcgen05.commit
+//     on mbarriers; the epilogue warps read TMEM with tcgen05.ld (lane = pixel), add bias /
+//     residual, apply the activation and store NHWC.
+//
+// Precision: 3xTF32.  A single TF32 pass (10-bit mantissa) costs ~7e-4 relative error per layer
+// and flips the network's discrete tile selections; splitting both operands (x = hi + lo) and
+// accumulating hi*hi + hi*lo + lo*hi in fp32 recovers fp32-class accuracy (~2^-21).  Weights are
+// split on the host.  Activations are split IN PLACE: passes 1-2 read the raw fp32 stage (the
+// tensor core uses the top 19 bits = hi), then the epilogue warps overwrite the stage with
+// lo = x - hi(x) and pass 3 runs lo * w_hi.  One stage buffer per tile instead of two.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int TC_TW = 128;          // output columns per tile (= MMA M)
+constexpr int TC_R = 2;             // output rows per tile
+constexpr int TC_TWP = TC_TW + 2;   // staged columns
+constexpr int TC_TROWS = TC_R + 2;  // staged rows
+constexpr int TC_EPI_THREADS = 128; // warps 0-3: stage split + epilogue; warp 4: TMA; warp 5: MMA
+constexpr int TC_THREADS = 192;
+
+struct TcP {
+    const float* wpk;   // [2][9][NP][KC] fp32: pass 0 = hi, pass 1 = lo (low 13 mantissa bits zero)
+    const float* bias;
+    const float* res;
+    float* out;
+    int N, H, W, Cout, ldo, ldr, res_bcast, act;
+    int tilesX, tilesY, ntiles;
+    int split_rna;        // 1: hi(x) = round-to-nearest tf32, 0: truncation (what the MMA datapath does)
+    int use_base_offset;  // 1: set the descriptor base-offset field from the start address
+};
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+        "[%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor, K-major, swizzled (cute::UMMA::SmemDescriptor bit layout)
+template <int KC>
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int use_base_offset) {
+    constexpr uint32_t ROWB = KC * 4;
+    constexpr uint64_t LAYOUT = (KC == 32) ? 2ull : 4ull;   // SWIZZLE_128B : SWIZZLE_64B
+    constexpr uint32_t SBO = 8 * ROWB;                      // 8-row group pitch
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);               // start address
+    d |= (uint64_t)1 << 16;                                 // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(SBO >> 4) << 32;                        // stride byte offset
+    d |= (uint64_t)1 << 46;                                 // descriptor version (Blackwell)
+    if (use_base_offset) d |= (uint64_t)((saddr >> 7) & 7u) << 49;
+    d |= LAYOUT << 61;
+    return d;
+}
+
+// byte offset of 16-byte chunk j of row r inside a K-major swizzled tile whose base is 1024-aligned
+template <int KC>
+__device__ __forceinline__ uint32_t swz_off(int r, int j) {
+    constexpr uint32_t ROWB = KC * 4;
+    const uint32_t off = (uint32_t)r * ROWB + (uint32_t)j * 16u;
+    constexpr uint32_t MASK = (KC == 32) ? 7u : 3u;
+    return off ^ (((off >> 7) & MASK) << 4);
+}
+
+__device__ __forceinline__ float tf32_lo(float x, int rna) {
+    uint32_t hi;
+    if (rna) {
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    } else {
+        hi = __float_as_uint(x) & 0xFFFFE000u;
+    }
+    return __fsub_rn(x, __uint_as_float(hi));
+}
+
+template <int KC, int NP>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcP p) {
+    constexpr uint32_t ROWB = KC * 4;
+    constexpr uint32_t A_BYTES = TC_TROWS * TC_TWP * ROWB;                 // bytes delivered by one TMA box
+    constexpr uint32_t A_STRIDE = (A_BYTES + 1023u) & ~1023u;
+    constexpr uint32_t B_TAP = NP * ROWB;
+    constexpr uint32_t B_BYTES = 2 * 9 * B_TAP;
+    constexpr int KSTEPS = KC / 8;
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((128u >> 4) << 24);
+
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) unsigned long long bars[12];
+    __shared__ uint32_t tmem_base_slot;
+
+    const uint32_t sbase = (s_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gbase = smem_raw + (sbase - s_u32(smem_raw));
+    const uint32_t sA[2] = {sbase, sbase + A_STRIDE};
+    const uint32_t sB = sbase + 2 * A_STRIDE;
+    uint8_t* gA[2] = {gbase, gbase + A_STRIDE};
+    uint8_t* gB = gbase + 2 * A_STRIDE;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // barriers: full[2] empty[2] p12[2] lo[2] accf[2] acce[2]
+    const uint32_t bar0 = s_u32(&bars[0]);
+    auto BAR = [&](int kind, int b) { return bar0 + (uint32_t)(kind * 2 + b) * 8u; };
+    enum { FULL = 0, EMPTY = 1, P12 = 2, LO = 3, ACCF = 4, ACCE = 5 };
+
+    if (tid == 0) {
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(BAR(FULL, b), 1);
+            mbar_init(BAR(EMPTY, b), 1);
+            mbar_init(BAR(P12, b), 1);
+            mbar_init(BAR(LO, b), TC_EPI_THREADS);
+            mbar_init(BAR(ACCF, b), 1);
+            mbar_init(BAR(ACCE, b), TC_EPI_THREADS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&tmem_base_slot)),
+                     "r"(128u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    // weights -> swizzled shared image (once per CTA)
+    for (int idx = tid; idx < 18 * NP * (KC / 4); idx += TC_THREADS) {
+        const int j = idx % (KC / 4);
+        const int r = (idx / (KC / 4)) % NP;
+        const int pt = idx / ((KC / 4) * NP);
+        const float4 v = ldg4(p.wpk + ((size_t)pt * NP + r) * KC + j * 4);
+        *reinterpret_cast<float4*>(gB + pt * B_TAP + swz_off<KC>(r, j)) = v;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_slot;
+
+    if (warp == 4) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int it = 0;
+            for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
+                const int b = it & 1;
+                const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+                int q = t;
+                const int tx = q % p.tilesX;
+                q /= p.tilesX;
+                const int ty = q % p.tilesY;
+                const int n = q / p.tilesY;
+                mbar_wait(BAR(EMPTY, b), ph ^ 1u);
+                mbar_expect_tx(BAR(FULL, b), A_BYTES);
+                const int cx = tx * TC_TW - 1, cy = ty * TC_R - 1;
+                asm volatile(
+                    "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+                    "%6}], [%2];" ::"r"(sA[b]),
+                    "l"(&tmap), "r"(BAR(FULL, b)), "r"(0), "r"(cx), "r"(cy), "r"(n)
+                    : "memory");
+            }
+        }
+    } else if (warp == 5) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int it = 0;
+            for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
+                const int b = it & 1;
+                const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+                mbar_wait(BAR(FULL, b), ph);
+                mbar_wait(BAR(ACCE, b), ph ^ 1u);
+                tc_fence_after();
+                // passes 1, 2: raw activations (hardware reads hi) x (w_hi, w_lo)
+                for (int mt = 0; mt < TC_R; ++mt) {
+                    const uint32_t d_tmem = tmem + (uint32_t)((b * TC_R + mt) * NP);
+                    uint32_t acc = 0;
+                    for (int pass = 0; pass < 2; ++pass)
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const int ky = tap / 3, kx = tap - 3 * ky;
+                            const uint32_t a0 = sA[b] + (uint32_t)((mt + ky) * TC_TWP + kx) * ROWB;
+                            const uint32_t b0 = sB + (uint32_t)(pass * 9 + tap) * B_TAP;
+#pragma unroll
+                            for (int k = 0; k < KSTEPS; ++k) {
+                                tc_mma_tf32(d_tmem, make_desc<KC>(a0 + k * 32, p.use_base_offset),
+                                            make_desc<KC>(b0 + k * 32, 0), IDESC, acc);
+                                acc = 1;
+                            }
+                        }
+                }
+                tc_commit(BAR(P12, b));
+                // pass 3: lo(activations) x w_hi
+                mbar_wait(BAR(LO, b), ph);
+                tc_fence_after();
+                for (int mt = 0; mt < TC_R; ++mt) {
+                    const uint32_t d_tmem = tmem + (uint32_t)((b * TC_R + mt) * NP);
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int ky = tap / 3, kx = tap - 3 * ky;
+                        const uint32_t a0 = sA[b] + (uint32_t)((mt + ky) * TC_TWP + kx) * ROWB;
+                        const uint32_t b0 = sB + (uint32_t)tap * B_TAP;
+#pragma unroll
+                        for (int k = 0; k < KSTEPS; ++k)
+                            tc_mma_tf32(d_tmem, make_desc<KC>(a0 + k * 32, p.use_base_offset), make_desc<KC>(b0 + k * 32, 0),
+                                        IDESC, 1u);
+                    }
+                }
+                tc_commit(BAR(ACCF, b));   // accumulators complete -> epilogue
+                tc_commit(BAR(EMPTY, b));  // stage buffer free -> producer
+            }
+        }
+    } else {
+        // ===================== stage split + epilogue (warps 0-3) =====================
+        int it = 0;
+        for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
+            const int b = it & 1;
+            const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+            int q = t;
+            const int tx = q % p.tilesX;
+            q /= p.tilesX;
+            const int ty = q % p.tilesY;
+            const int n = q / p.tilesY;
+            // in-place x -> x - hi(x) once passes 1-2 have consumed the raw stage
+            mbar_wait(BAR(P12, b), ph);
+            tc_fence_after();
+            float4* a4 = reinterpret_cast<float4*>(gA[b]);
+            for (int idx = tid; idx < (int)(A_BYTES / 16); idx += TC_EPI_THREADS) {
+                float4 v = a4[idx];
+                v.x = tf32_lo(v.x, p.split_rna);
+                v.y = tf32_lo(v.y, p.split_rna);
+                v.z = tf32_lo(v.z, p.split_rna);
+                v.w = tf32_lo(v.w, p.split_rna);
+                a4[idx] = v;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(BAR(LO, b));
+            // epilogue
+            mbar_wait(BAR(ACCF, b), ph);
+            tc_fence_after();
+            float acc[TC_R][NP];
+#pragma unroll
+            for (int mt = 0; mt < TC_R; ++mt)
+#pragma unroll
+                for (int c = 0; c < NP; c += 16)
+                    tc_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)((b * TC_R + mt) * NP + c), &acc[mt][c]);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            mbar_arrive(BAR(ACCE, b));
+            const int x = tx * TC_TW + warp * 32 + lane;
+#pragma unroll
+            for (int mt = 0; mt < TC_R; ++mt) {
+                const int y = ty * TC_R + mt;
+                if (x >= p.W || y >= p.H) continue;
+                const size_t opix = ((size_t)n * p.H + y) * p.W + x;
+                float* op = p.out + opix * p.ldo;
+                float rb = 0.f;
+                if (p.res && p.res_bcast) rb = __ldg(p.res + opix * p.ldr);
+#pragma unroll
+                for (int c4 = 0; c4 < NP; c4 += 4) {
+                    if (c4 >= p.Cout) break;
+                    float v[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int ce = c4 + e;
+                        float tv = acc[mt][ce];
+                        if (ce < p.Cout) {
+                            if (p.bias) tv += __ldg(p.bias + ce);
+                            if (p.res) tv += p.res_bcast ? rb : __ldg(p.res + opix * p.ldr + ce);
+                            tv = codd_act(tv, p.act, ce);
+                        }
+                        v[e] = tv;
+                    }
+                    if (c4 + 3 < p.Cout && (p.ldo & 3) == 0) {
+                        *reinterpret_cast<float4*>(op + c4) = make_float4(v[0], v[1], v[2], v[3]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (c4 + e < p.Cout) op[c4 + e] = v[e];
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u));
+    }
+}
+
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_tmapEncodeTiled get_encode() {
+    static PFN_tmapEncodeTiled fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (PFN_tmapEncodeTiled)ptr;
+    }
+    return fn;
+}
+
+template <int KC, int NP>
+int launch_tc(const CUtensorMap& tmap, TcP p, cudaStream_t s) {
+    constexpr uint32_t ROWB = KC * 4;
+    constexpr uint32_t A_STRIDE = ((TC_TROWS * TC_TWP * ROWB) + 1023u) & ~1023u;
+    constexpr uint32_t B_BYTES = 2 * 9 * NP * ROWB;
+    const size_t smem = 2 * A_STRIDE + B_BYTES + 1024;
+    auto kern = conv3x3_tc_kernel<KC, NP>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = p.ntiles < sms ? p.ntiles : sms;
+    kern<<<grid, TC_THREADS, smem, s>>>(tmap, p);
+    CODD_RETURN_IF_CUDA_ERROR();
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int codd_conv3x3_tc(const float* in, int ldi, int cin, int n, int h, int w, const float* weight_split,
+                               const float* bias, const float* residual, int ldr, int res_bcast, int cout, int act,
+                               float* out, int ldo, int flags, void* stream) {
+    if (!in || !weight_split || !out || n <= 0 || h <= 0 || w <= 0 || cin <= 0 || cout <= 0) return CODD_E_BADARG;
+    if (cin > 32 || cout > 32 || cin % 4 != 0 || ldi % 4 != 0 || ldi < cin || ldo < cout) return CODD_E_SHAPE;
+    if (!codd_aligned16(in)) return CODD_E_ALIGN;
+    PFN_tmapEncodeTiled enc = get_encode();
+    if (!enc) return CODD_E_UNSUPPORTED;
+    const int KC = cin <= 16 ? 16 : 32;
+    const int NP = cout <= 16 ? 16 : 32;
+    if (KC == 16 && NP == 32) return CODD_E_UNSUPPORTED;
+    CUtensorMap tmap;
+    const cuuint64_t gdim[4] = {(cuuint64_t)cin, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+    const cuuint64_t gstr[3] = {(cuuint64_t)ldi * 4, (cuuint64_t)w * ldi * 4, (cuuint64_t)h * w * ldi * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)TC_TWP, (cuuint32_t)TC_TROWS, 1u};
+    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)in, gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, KC == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return CODD_E_SHAPE;
+    TcP p;
+    p.wpk = weight_split; p.bias = bias; p.res = residual; p.out = out;
+    p.N = n; p.H = h; p.W = w; p.Cout = cout; p.ldo = ldo; p.ldr = ldr; p.res_bcast = res_bcast; p.act = act;
+    p.tilesX = codd_ceil_div(w, TC_TW);
+    p.tilesY = codd_ceil_div(h, TC_R);
+    p.ntiles = p.tilesX * p.tilesY * n;
+    p.split_rna = (flags & 1) ? 1 : 0;
+    p.use_base_offset = (flags & 2) ? 1 : 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (KC == 32 && NP == 32) return launch_tc<32, 32>(tmap, p, s);
+    if (KC == 32 && NP == 16) return launch_tc<32, 16>(tmap, p, s);
+    return launch_tc<16, 16>(tmap, p, s);
+}

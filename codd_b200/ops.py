@@ -133,6 +133,48 @@ def pack_deconv_weight(w):
     return w.detach().permute(2, 3, 0, 1).contiguous().float()
 
 
+def _tf32_round(t):
+    """Round-to-nearest (ties away) to the 10-bit tf32 mantissa, kept in an fp32 container."""
+    i = t.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def pack_conv_weight_tc(w):
+    """torch [Cout,Cin,3,3] -> [2][9][NP][KC] hi/lo split for codd_conv3x3_tc (3xTF32)."""
+    cout, cin, kh, kw = w.shape
+    assert kh == 3 and kw == 3
+    kc = 16 if cin <= 16 else 32
+    npad = 16 if cout <= 16 else 32
+    wt = torch.zeros((9, npad, kc), dtype=torch.float32, device=w.device)
+    wt[:, :cout, :cin] = w.detach().float().permute(2, 3, 0, 1).reshape(9, cout, cin)
+    hi = _tf32_round(wt)
+    lo = _tf32_round(wt - hi)
+    return torch.stack([hi, lo]).contiguous()
+
+
+def tc_eligible(cin, cout, k, stride, pad, dil, x2):
+    kh, kw = (k, k) if isinstance(k, int) else k
+    sh, sw = (stride, stride) if isinstance(stride, int) else stride
+    ph, pw = (pad, pad) if isinstance(pad, int) else pad
+    return (x2 is None and kh == 3 and kw == 3 and sh == 1 and sw == 1 and ph == 1 and pw == 1 and dil == 1
+            and cin in (16, 24, 32) and cout <= 32 and not (cin <= 16 and cout > 16))
+
+
+def conv3x3_tc(x, wsplit, bias, cout, act=ACT_NONE, residual=None, res_bcast=False, flags=0):
+    """3x3 s1 p1 conv on the tensor cores (3xTF32).  ``wsplit`` from pack_conv_weight_tc."""
+    _require_cuda(x, wsplit, bias, residual)
+    n, cin, h, w = x.shape
+    out = empty_nhwc(n, cout, h, w, x.device)
+    nbytes = 4 * (n * h * w * (cin + cout) + wsplit.numel() // 2
+                  + (0 if residual is None else n * h * w * (1 if res_bcast else cout)))
+    rc = _run(f"conv3x3tc_cin{cin}_cout{cout}", nbytes, lambda: _lib.load().codd_conv3x3_tc(
+        x.data_ptr(), ld_of(x), cin, n, h, w, wsplit.data_ptr(), None if bias is None else bias.data_ptr(),
+        None if residual is None else residual.data_ptr(), 0 if residual is None else ld_of(residual),
+        1 if res_bcast else 0, cout, act, out.data_ptr(), ld_of(out), flags, _stream()))
+    _lib.check(rc, f"codd_conv3x3_tc(cin={cin}, cout={cout})")
+    return out
+
+
 def conv2d(x, wp, bias, cout, k, stride=(1, 1), pad=(0, 0), dil=1, act=ACT_NONE, x2=None, residual=None,
            res_bcast=False, out=None, out_hw=None, ld_out=None):
     """act(conv(cat(x, x2)) + bias + residual).  ``wp`` is a packed weight."""

@@ -5,9 +5,27 @@ Parameters live in ordinary ``nn.Conv2d`` / ``nn.ConvTranspose2d`` containers so
 read a re-laid-out copy ([tap][cin][cout]) that is rebuilt whenever the parameter changes
 (``load_state_dict``, ``.to()``, in-place updates bump ``_version``).
 """
+import os
+
 import torch
 
 from .. import ops
+
+# 3x3 convolutions run on the tensor cores (tcgen05, 3xTF32) unless CODD_TC=0
+USE_TC = os.environ.get("CODD_TC", "1") != "0"
+
+
+def run_conv(pw, conv, x, act, x2=None, residual=None, res_bcast=False, head=None):
+    """One nn.Conv2d through the C ABI: tensor-core kernel when the layer is eligible, the fp32
+    direct convolution otherwise.  ``head``: compute only the first ``head`` output channels."""
+    cout = conv.out_channels if head is None else head
+    k, st, pd, dl = conv.kernel_size, conv.stride, conv.padding, conv.dilation[0]
+    cin = x.shape[1] + (0 if x2 is None else x2.shape[1])
+    if USE_TC and ops.tc_eligible(cin, cout, k, st, pd, dl, x2):
+        ws, b = pw.conv_tc(conv, head)
+        return ops.conv3x3_tc(x, ws, b, cout, act, residual=residual, res_bcast=res_bcast)
+    wp, b = pw.conv(conv) if head is None else pw.conv_head(conv, head)
+    return ops.conv2d(x, wp, b, cout, k, st, pd, dl, act, x2=x2, residual=residual, res_bcast=res_bcast)
 
 
 class PackedWeights:
@@ -38,6 +56,20 @@ class PackedWeights:
         hit = self._cache.get(key)
         if hit is None or hit[0] != tag:
             hit = (tag, ops.pack_conv_weight(w[:n]), None if b is None else b.detach()[:n].float().contiguous())
+            self._cache[key] = hit
+        return hit[1], hit[2]
+
+    def conv_tc(self, conv, n=None):
+        """hi/lo tf32 split of a 3x3 weight for the tensor-core kernel (first ``n`` filters if given)."""
+        w = conv.weight
+        b = conv.bias
+        key = (id(conv), "tc", n)
+        tag = (w.data_ptr(), w._version, w.device, None if b is None else (b.data_ptr(), b._version))
+        hit = self._cache.get(key)
+        if hit is None or hit[0] != tag:
+            ww = w if n is None else w[:n]
+            bb = None if b is None else (b.detach() if n is None else b.detach()[:n]).float().contiguous()
+            hit = (tag, ops.pack_conv_weight_tc(ww), bb)
             self._cache[key] = hit
         return hit[1], hit[2]
 

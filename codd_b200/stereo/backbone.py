@@ -11,7 +11,7 @@ import torch.nn as nn
 from .. import ops
 from ..lib import ACT_LEAKY
 from ..registry import BACKBONES
-from ._params import PackedWeights
+from ._params import PackedWeights, run_conv
 
 
 def _conv_down(inp, oup):
@@ -55,9 +55,7 @@ class HITUNet(nn.Module):
 
     # -- building blocks -------------------------------------------------------------------
     def _c(self, conv, x, x2=None):
-        wp, b = self._pw.conv(conv)
-        return ops.conv2d(x, wp, b, conv.out_channels, conv.kernel_size, conv.stride, conv.padding,
-                          conv.dilation[0], ACT_LEAKY, x2=x2)
+        return run_conv(self._pw, conv, x, ACT_LEAKY, x2=x2)
 
     def _down(self, seq, x):
         return self._c(seq[2], self._c(seq[0], x))

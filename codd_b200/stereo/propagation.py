@@ -11,7 +11,7 @@ import torch.nn as nn
 from .. import ops
 from ..lib import ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_RELU_CH0
 from ..registry import MODELS
-from ._params import PackedWeights
+from ._params import PackedWeights, run_conv
 
 
 def _convbn(cin, cout, k, stride, pad, dilation):
@@ -37,10 +37,8 @@ def _resblock(c, d=1):
 class _Runner:
     """Kernel-launch helpers shared by the update modules."""
 
-    def _conv(self, conv, x, act, x2=None, residual=None, res_bcast=False, cout=None, wb=None):
-        wp, b = wb if wb is not None else self._pw.conv(conv)
-        return ops.conv2d(x, wp, b, conv.out_channels if cout is None else cout, conv.kernel_size, conv.stride,
-                          conv.padding, conv.dilation[0], act, x2=x2, residual=residual, res_bcast=res_bcast)
+    def _conv(self, conv, x, act, x2=None, residual=None, res_bcast=False, head=None):
+        return run_conv(self._pw, conv, x, act, x2=x2, residual=residual, res_bcast=res_bcast, head=head)
 
     def _res(self, blk, x):
         """Sequential(BasicBlock, LeakyReLU): lrelu(conv2(lrelu(conv1(x))) + x)."""
@@ -137,9 +135,8 @@ class FinalTileUpdate(nn.Module, _Runner):
             x = self._res(blk, x)
         # relu(prev[:, 0:1] + update): the single-channel residual broadcasts over the outputs.
         # Inference consumes channel 0 only (propagation.py:372), so only that filter is run.
-        nout = self.lastconv.out_channels if self.full_output else 1
-        return self._conv(self.lastconv, x, ACT_RELU, residual=prev[:, 0:1], res_bcast=True, cout=nout,
-                          wb=self._pw.conv_head(self.lastconv, nout))
+        return self._conv(self.lastconv, x, ACT_RELU, residual=prev[:, 0:1], res_bcast=True,
+                          head=None if self.full_output else 1)
 
 
 @MODELS.register_module(force=True)

@@ -76,6 +76,17 @@ CODD_API int codd_conv2d_nhwc(const codd_conv_desc* d, const float* in0, const f
                      const float* weight, const float* bias, const float* residual,
                      float* out, void* stream);
 
+/* 3x3 / stride 1 / pad 1 convolution on the tensor cores (tcgen05.mma kind::tf32, 3xTF32 split,
+ * accumulators in TMEM, input halo tiles by 4-D TMA) — same math and epilogue as codd_conv2d_nhwc
+ * for the layers it covers: cin in {16,24,32} (single source), cout <= 32 (not 16 -> 32).
+ * weight_split is [2][9][NP][KC] fp32 (NP = 16|32 >= cout, KC = 16|32 >= cin, zero padded):
+ * [0] = tf32-rounded weights, [1] = tf32-rounded remainder  (host: ops.pack_conv_weight_tc).
+ * flags: bit0 = split activations by round-to-nearest instead of truncation, bit1 = set the
+ * descriptor base-offset field (diagnostic switches; default 0). */
+CODD_API int codd_conv3x3_tc(const float* in, int ldi, int cin, int n, int h, int w,
+                             const float* weight_split, const float* bias, const float* residual, int ldr,
+                             int res_bcast, int cout, int act, float* out, int ldo, int flags, void* stream);
+
 /* First backbone layer (backbone.py:35-39,70): 3x3, pad 1, 3 -> cout (<=16) channels,
  * LeakyReLU, reading NCHW images and writing NHWC.  `left` and `right` are two [n,3,h,w]
  * images batches; the output holds 2n samples: left batch first, then right (right may be

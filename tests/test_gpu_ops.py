@@ -295,3 +295,31 @@ def test_hyp_select_bit_exact(ops):
     wide.copy_(upd.cuda())
     out = ops.hyp_select(wide, nhwc(ops, aug))
     assert torch.equal(back(ops, out), ref)
+
+
+# ------------------------------------------------------------------------------------------
+# tensor-core 3x3 conv (tcgen05, 3xTF32)
+# ------------------------------------------------------------------------------------------
+TC_CASES = [(32, 32, 8, 200), (16, 16, 7, 300), (24, 24, 9, 130), (32, 16, 6, 128), (16, 3, 5, 100), (16, 1, 4, 260),
+            (32, 24, 3, 60)]
+
+
+@pytest.mark.parametrize("cin,cout,h,w", TC_CASES)
+def test_conv3x3_tensor_core(ops, cin, cout, h, w):
+    """Same bar as the fp32 CUDA-core conv (rtol/atol 2e-5): 3xTF32 must be fp32-class."""
+    from codd_b200.lib import ACT_LEAKY
+    g = gen(cin * 100 + cout + h)
+    x = torch.randn(2, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5
+    b = torch.randn(cout, generator=g)
+    res = torch.randn(2, cout, h, w, generator=g)
+    ref = F.leaky_relu(F.conv2d(x, wt, b, padding=1) + res, 0.2)
+    ws = ops.pack_conv_weight_tc(wt.cuda())
+    errs = {}
+    for flags in (0, 1, 2, 3):
+        out = ops.conv3x3_tc(nhwc(ops, x), ws, b.cuda(), cout, ACT_LEAKY, residual=nhwc(ops, res), flags=flags)
+        torch.cuda.synchronize()
+        errs[flags] = (back(ops, out) - ref).abs().max().item()
+    print(f"conv3x3_tc cin={cin} cout={cout}: max abs err per flags {errs}")
+    out = ops.conv3x3_tc(nhwc(ops, x), ws, b.cuda(), cout, ACT_LEAKY, residual=nhwc(ops, res), flags=0)
+    torch.testing.assert_close(back(ops, out), ref, rtol=CONV_RTOL, atol=CONV_ATOL)
