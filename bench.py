@@ -194,13 +194,8 @@ def run_b200(args):
     torch.manual_seed(0)
     model = codd_b200.build_estimator(codd_b200.codd_stereo_config(MAX_DISP)).to(dev)
     model.eval()
-    if world > 1:
-        flat = torch.cat([p.data.flatten() for p in model.parameters()])
-        dist.broadcast(flat, 0)
-        off = 0
-        for p in model.parameters():
-            p.data.copy_(flat[off:off + p.numel()].view_as(p))
-            off += p.numel()
+    from codd_b200.sharding import broadcast_parameters, reduce_max_ms
+    broadcast_parameters(model, src=0)
 
     B = args.batch
     # Set U of SURVEY §8d would feed right == left (degenerate ties); use independent textured pairs
@@ -261,10 +256,7 @@ def run_b200(args):
         barrier()
         ms = e0.elapsed_time(e1)
         clocks = sampler.stop() if rank == 0 else None
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = t.item()
+        ms = reduce_max_ms(ms, dev)
 
         # ---------------- e2e: public API, pinned host buffers, H2D + D2H inside the region
         img_h = torch.stack([left_h], 1).pin_memory()       # [B, MF=1, 3, H, W]
@@ -288,10 +280,7 @@ def run_b200(args):
         e1.record()
         barrier()
         e2e_ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([e2e_ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_ms = t.item()
+        e2e_ms = reduce_max_ms(e2e_ms, dev)
         h2d = img_h.numel() * 4 + rimg_h.numel() * 4
         d2h = res_h.numel() * 4
 

@@ -36,8 +36,11 @@ constexpr int TC_TW = 128;          // output columns per tile (= MMA M)
 constexpr int TC_R = 2;             // output rows per tile
 constexpr int TC_TWP = TC_TW + 2;   // staged columns
 constexpr int TC_TROWS = TC_R + 2;  // staged rows
-constexpr int TC_EPI_THREADS = 128; // warps 0-3: stage split + epilogue; warp 4: TMA; warp 5: MMA
-constexpr int TC_THREADS = 192;
+// warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM alloc), 2-5 = epilogue (TMEM lane quarter =
+// warp % 4), 6-13 = in-place hi/lo split of the stage
+constexpr int TC_EPI_THREADS = 128;
+constexpr int TC_SPLIT_THREADS = 256;
+constexpr int TC_THREADS = 64 + TC_EPI_THREADS + TC_SPLIT_THREADS;
 
 struct TcP {
     const float* wpk;   // [2][9][NP][KC] fp32: pass 0 = hi, pass 1 = lo (low 13 mantissa bits zero)
@@ -46,8 +49,9 @@ struct TcP {
     float* out;
     int N, H, W, Cout, ldo, ldr, res_bcast, act;
     int tilesX, tilesY, ntiles;
+    long long* dbg;       // optional [grid][8] cycle counters (role wait times), NULL in production
     int split_rna;        // 1: hi(x) = round-to-nearest tf32, 0: truncation (what the MMA datapath does)
-    int use_base_offset;  // 1: set the descriptor base-offset field from the start address
+    int use_base_offset;  // 1: set the descriptor base-offset field from the start address (diagnostic)
 };
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -73,18 +77,33 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "memory");
     }
 }
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, long long& acc) {
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += clock64() - t0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc)
-        : "memory");
+template <bool ACC>
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc) {
+    if (ACC) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.eq.u32 p, 1, 1;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.eq.u32 p, 1, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc)
+            : "memory");
+    }
 }
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
     uint32_t r[16];
@@ -98,7 +117,10 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// shared-memory matrix descriptor, K-major, swizzled (cute::UMMA::SmemDescriptor bit layout)
+// shared-memory matrix descriptor, K-major, swizzled (cute::UMMA::SmemDescriptor bit layout).
+// The swizzle is a function of the shared-memory ADDRESS, so a tap's operand is simply the stage
+// seen from a shifted start address; the base-offset field stays 0 (verified on B200: setting it
+// from the address corrupts the result).
 template <int KC>
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int use_base_offset) {
     constexpr uint32_t ROWB = KC * 4;
@@ -133,47 +155,77 @@ __device__ __forceinline__ float tf32_lo(float x, int rna) {
     return __fsub_rn(x, __uint_as_float(hi));
 }
 
-template <int KC, int NP>
+// One pass (9 taps x KC/8 k-steps) of one 128-pixel row: fully unrolled, every operand descriptor is
+// the stage / weight base descriptor plus a compile-time constant (>> 4) — a single thread issues
+// an MMA every few instructions.  FIRST: the very first MMA overwrites the accumulator.
+template <int KC, int NP, bool FIRST>
+__device__ __forceinline__ void tc_issue_pass(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+    constexpr uint32_t ROWB = KC * 4;
+    constexpr uint32_t B_TAP = 2 * NP * ROWB;   // per tap: NP rows of w_hi followed by NP rows of w_lo
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+        for (int k = 0; k < KC / 8; ++k) {
+            const uint32_t aoff = (uint32_t)((tap / 3) * TC_TWP + (tap % 3)) * ROWB + k * 32;
+            const uint32_t boff = (uint32_t)tap * B_TAP + k * 32;
+            if (FIRST && tap == 0 && k == 0)
+                tc_mma_tf32<false>(d_tmem, a_desc + (aoff >> 4), b_desc + (boff >> 4), idesc);
+            else
+                tc_mma_tf32<true>(d_tmem, a_desc + (aoff >> 4), b_desc + (boff >> 4), idesc);
+        }
+    }
+}
+
+// NBUF stage buffers, NACC accumulator buffers (x TC_R rows x NP TMEM columns), LAG = how many tiles
+// pass 3 trails passes 1-2 (LAG < NBUF, NACC >= LAG + 2).
+template <int KC, int NP, int NBUF, int NACC, int LAG>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcP p) {
+    static_assert(LAG >= 1 && LAG < NBUF && NACC >= LAG + 2, "pipeline depths");
+    constexpr uint32_t TMEM_COLS = (NACC * TC_R * 2 * NP <= 128) ? 128u : (NACC * TC_R * 2 * NP <= 256) ? 256u : 512u;
     constexpr uint32_t ROWB = KC * 4;
     constexpr uint32_t A_BYTES = TC_TROWS * TC_TWP * ROWB;                 // bytes delivered by one TMA box
     constexpr uint32_t A_STRIDE = (A_BYTES + 1023u) & ~1023u;
-    constexpr uint32_t B_TAP = NP * ROWB;
-    constexpr uint32_t B_BYTES = 2 * 9 * B_TAP;
-    constexpr int KSTEPS = KC / 8;
-    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((128u >> 4) << 24);
+    constexpr uint32_t B_TAP = 2 * NP * ROWB;
+    // instruction descriptors: N = 2*NP (x * [w_hi | w_lo] in ONE MMA: the stage is read once for both
+    // weight halves — the MMA rate here is bound by the shared-memory read of A) and N = NP (x_lo * w_hi)
+    constexpr uint32_t IDESC_BASE = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 4) << 24);
+    constexpr uint32_t IDESC2 = IDESC_BASE | ((uint32_t)((2 * NP) >> 3) << 17);
+    constexpr uint32_t IDESC1 = IDESC_BASE | ((uint32_t)(NP >> 3) << 17);
+    constexpr int ACC_COLS = 2 * NP;   // per output row: [0,NP) = x*w_hi + x_lo*w_hi, [NP,2NP) = x*w_lo
 
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) unsigned long long bars[12];
+    __shared__ __align__(8) unsigned long long bars[4 * NBUF + 2 * NACC];
     __shared__ uint32_t tmem_base_slot;
 
     const uint32_t sbase = (s_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gbase = smem_raw + (sbase - s_u32(smem_raw));
-    const uint32_t sA[2] = {sbase, sbase + A_STRIDE};
-    const uint32_t sB = sbase + 2 * A_STRIDE;
-    uint8_t* gA[2] = {gbase, gbase + A_STRIDE};
-    uint8_t* gB = gbase + 2 * A_STRIDE;
+    const uint32_t sB = sbase + NBUF * A_STRIDE;
+    uint8_t* gB = gbase + NBUF * A_STRIDE;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // barriers: full[2] empty[2] p12[2] lo[2] accf[2] acce[2]
     const uint32_t bar0 = s_u32(&bars[0]);
-    auto BAR = [&](int kind, int b) { return bar0 + (uint32_t)(kind * 2 + b) * 8u; };
-    enum { FULL = 0, EMPTY = 1, P12 = 2, LO = 3, ACCF = 4, ACCE = 5 };
+    // stage barriers (per stage buffer): FULL, EMPTY, P12, LO; accumulator barriers (2): ACCF, ACCE
+    auto SBAR = [&](int kind, int b) { return bar0 + (uint32_t)(kind * NBUF + b) * 8u; };
+    auto ABAR = [&](int kind, int b) { return bar0 + (uint32_t)(4 * NBUF + kind * NACC + b) * 8u; };
+    enum { FULL = 0, EMPTY = 1, P12 = 2, LO = 3 };
+    enum { ACCF = 0, ACCE = 1 };
 
     if (tid == 0) {
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(BAR(FULL, b), 1);
-            mbar_init(BAR(EMPTY, b), 1);
-            mbar_init(BAR(P12, b), 1);
-            mbar_init(BAR(LO, b), TC_EPI_THREADS);
-            mbar_init(BAR(ACCF, b), 1);
-            mbar_init(BAR(ACCE, b), TC_EPI_THREADS);
+        for (int b = 0; b < NBUF; ++b) {
+            mbar_init(SBAR(FULL, b), 1);
+            mbar_init(SBAR(EMPTY, b), 1);
+            mbar_init(SBAR(P12, b), 1);
+            mbar_init(SBAR(LO, b), TC_SPLIT_THREADS);
+        }
+        for (int b = 0; b < NACC; ++b) {
+            mbar_init(ABAR(ACCF, b), 1);
+            mbar_init(ABAR(ACCE, b), TC_EPI_THREADS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 5) {
+    if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&tmem_base_slot)),
-                     "r"(128u));
+                     "r"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     // weights -> swizzled shared image (once per CTA)
@@ -182,7 +234,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const __grid_
         const int r = (idx / (KC / 4)) % NP;
         const int pt = idx / ((KC / 4) * NP);
         const float4 v = ldg4(p.wpk + ((size_t)pt * NP + r) * KC + j * 4);
-        *reinterpret_cast<float4*>(gB + pt * B_TAP + swz_off<KC>(r, j)) = v;
+        const int pass = pt / 9, tap = pt - 9 * pass;
+        *reinterpret_cast<float4*>(gB + tap * B_TAP + swz_off<KC>(r + pass * NP, j)) = v;
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc_fence_before();
@@ -190,115 +243,95 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const __grid_
     tc_fence_after();
     const uint32_t tmem = tmem_base_slot;
 
-    if (warp == 4) {
+    if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
+            long long w0 = 0;
+            const long long tstart = clock64();
             int it = 0;
             for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
-                const int b = it & 1;
-                const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+                const int sb = it % NBUF;
+                const uint32_t ph = (uint32_t)(it / NBUF) & 1u;
                 int q = t;
                 const int tx = q % p.tilesX;
                 q /= p.tilesX;
                 const int ty = q % p.tilesY;
                 const int n = q / p.tilesY;
-                mbar_wait(BAR(EMPTY, b), ph ^ 1u);
-                mbar_expect_tx(BAR(FULL, b), A_BYTES);
+                mbar_wait_t(SBAR(EMPTY, sb), ph ^ 1u, w0);
+                mbar_expect_tx(SBAR(FULL, sb), A_BYTES);
                 const int cx = tx * TC_TW - 1, cy = ty * TC_R - 1;
                 asm volatile(
                     "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
-                    "%6}], [%2];" ::"r"(sA[b]),
-                    "l"(&tmap), "r"(BAR(FULL, b)), "r"(0), "r"(cx), "r"(cy), "r"(n)
+                    "%6}], [%2];" ::"r"(sbase + sb * A_STRIDE),
+                    "l"(&tmap), "r"(SBAR(FULL, sb)), "r"(0), "r"(cx), "r"(cy), "r"(n)
                     : "memory");
             }
+            if (p.dbg) { p.dbg[blockIdx.x * 8 + 0] = w0; p.dbg[blockIdx.x * 8 + 7] = clock64() - tstart; }
         }
-    } else if (warp == 5) {
+    } else if (warp == 1) {
         // ===================== MMA issuer =====================
+        // Software-pipelined over tiles: passes 1-2 of tile i are issued BEFORE pass 3 of tile i-1, so
+        // the tensor pipe works on the next tile while the split warps rewrite the previous stage.
         if (lane == 0) {
+            const uint64_t b_desc = make_desc<KC>(sB, 0);
+            long long w1 = 0, w2 = 0, w3 = 0;
+            auto pass3 = [&](int it) {
+                const int sb = it % NBUF, ab = it % NACC;
+                mbar_wait_t(SBAR(LO, sb), (uint32_t)(it / NBUF) & 1u, w3);
+                tc_fence_after();
+                const uint64_t a_desc = make_desc<KC>(sbase + sb * A_STRIDE, p.use_base_offset);
+#pragma unroll
+                for (int mt = 0; mt < TC_R; ++mt)
+                    tc_issue_pass<KC, NP, false>(tmem + (uint32_t)((ab * TC_R + mt) * ACC_COLS),
+                                                 a_desc + ((uint32_t)(mt * TC_TWP) * ROWB >> 4), b_desc, IDESC1);
+                tc_commit(ABAR(ACCF, ab));     // accumulators complete -> epilogue
+                tc_commit(SBAR(EMPTY, sb));    // stage buffer free -> producer
+            };
             int it = 0;
             for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
-                const int b = it & 1;
-                const uint32_t ph = (uint32_t)(it >> 1) & 1u;
-                mbar_wait(BAR(FULL, b), ph);
-                mbar_wait(BAR(ACCE, b), ph ^ 1u);
+                const int sb = it % NBUF, ab = it % NACC;
+                mbar_wait_t(SBAR(FULL, sb), (uint32_t)(it / NBUF) & 1u, w1);
+                mbar_wait_t(ABAR(ACCE, ab), ((uint32_t)(it / NACC) & 1u) ^ 1u, w2);
                 tc_fence_after();
-                // passes 1, 2: raw activations (hardware reads hi) x (w_hi, w_lo)
-                for (int mt = 0; mt < TC_R; ++mt) {
-                    const uint32_t d_tmem = tmem + (uint32_t)((b * TC_R + mt) * NP);
-                    uint32_t acc = 0;
-                    for (int pass = 0; pass < 2; ++pass)
-                        for (int tap = 0; tap < 9; ++tap) {
-                            const int ky = tap / 3, kx = tap - 3 * ky;
-                            const uint32_t a0 = sA[b] + (uint32_t)((mt + ky) * TC_TWP + kx) * ROWB;
-                            const uint32_t b0 = sB + (uint32_t)(pass * 9 + tap) * B_TAP;
+                const uint64_t a_desc = make_desc<KC>(sbase + sb * A_STRIDE, p.use_base_offset);
 #pragma unroll
-                            for (int k = 0; k < KSTEPS; ++k) {
-                                tc_mma_tf32(d_tmem, make_desc<KC>(a0 + k * 32, p.use_base_offset),
-                                            make_desc<KC>(b0 + k * 32, 0), IDESC, acc);
-                                acc = 1;
-                            }
-                        }
-                }
-                tc_commit(BAR(P12, b));
-                // pass 3: lo(activations) x w_hi
-                mbar_wait(BAR(LO, b), ph);
-                tc_fence_after();
                 for (int mt = 0; mt < TC_R; ++mt) {
-                    const uint32_t d_tmem = tmem + (uint32_t)((b * TC_R + mt) * NP);
-                    for (int tap = 0; tap < 9; ++tap) {
-                        const int ky = tap / 3, kx = tap - 3 * ky;
-                        const uint32_t a0 = sA[b] + (uint32_t)((mt + ky) * TC_TWP + kx) * ROWB;
-                        const uint32_t b0 = sB + (uint32_t)tap * B_TAP;
-#pragma unroll
-                        for (int k = 0; k < KSTEPS; ++k)
-                            tc_mma_tf32(d_tmem, make_desc<KC>(a0 + k * 32, p.use_base_offset), make_desc<KC>(b0 + k * 32, 0),
-                                        IDESC, 1u);
-                    }
+                    const uint32_t d_tmem = tmem + (uint32_t)((ab * TC_R + mt) * ACC_COLS);
+                    const uint64_t a_mt = a_desc + ((uint32_t)(mt * TC_TWP) * ROWB >> 4);
+                    tc_issue_pass<KC, NP, true>(d_tmem, a_mt, b_desc, IDESC2);   // x_hi * [w_hi | w_lo] (raw stage: MMA reads hi)
                 }
-                tc_commit(BAR(ACCF, b));   // accumulators complete -> epilogue
-                tc_commit(BAR(EMPTY, b));  // stage buffer free -> producer
+                tc_commit(SBAR(P12, sb));
+                if (it >= LAG) pass3(it - LAG);                                // x_lo * w_hi of an earlier tile
             }
+            for (int j = (it > LAG ? it - LAG : 0); j < it; ++j) pass3(j);
+            if (p.dbg) { p.dbg[blockIdx.x * 8 + 1] = w1; p.dbg[blockIdx.x * 8 + 2] = w2; p.dbg[blockIdx.x * 8 + 3] = w3; }
         }
-    } else {
-        // ===================== stage split + epilogue (warps 0-3) =====================
+    } else if (warp < 6) {
+        // ===================== epilogue (warps 2-5) =====================
+        const int quarter = warp & 3;                 // TMEM lanes 32*quarter .. +31
+        long long w4 = 0;
         int it = 0;
         for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
-            const int b = it & 1;
-            const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+            const int ab = it % NACC;
             int q = t;
             const int tx = q % p.tilesX;
             q /= p.tilesX;
             const int ty = q % p.tilesY;
             const int n = q / p.tilesY;
-            // in-place x -> x - hi(x) once passes 1-2 have consumed the raw stage
-            mbar_wait(BAR(P12, b), ph);
+            mbar_wait_t(ABAR(ACCF, ab), (uint32_t)(it / NACC) & 1u, w4);
             tc_fence_after();
-            float4* a4 = reinterpret_cast<float4*>(gA[b]);
-            for (int idx = tid; idx < (int)(A_BYTES / 16); idx += TC_EPI_THREADS) {
-                float4 v = a4[idx];
-                v.x = tf32_lo(v.x, p.split_rna);
-                v.y = tf32_lo(v.y, p.split_rna);
-                v.z = tf32_lo(v.z, p.split_rna);
-                v.w = tf32_lo(v.w, p.split_rna);
-                a4[idx] = v;
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive(BAR(LO, b));
-            // epilogue
-            mbar_wait(BAR(ACCF, b), ph);
-            tc_fence_after();
-            float acc[TC_R][NP];
-#pragma unroll
-            for (int mt = 0; mt < TC_R; ++mt)
-#pragma unroll
-                for (int c = 0; c < NP; c += 16)
-                    tc_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)((b * TC_R + mt) * NP + c), &acc[mt][c]);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            tc_fence_before();
-            mbar_arrive(BAR(ACCE, b));
-            const int x = tx * TC_TW + warp * 32 + lane;
+            const int x = tx * TC_TW + quarter * 32 + lane;
 #pragma unroll
             for (int mt = 0; mt < TC_R; ++mt) {
+                float acc[ACC_COLS];
+#pragma unroll
+                for (int c = 0; c < ACC_COLS; c += 16)
+                    tc_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((ab * TC_R + mt) * ACC_COLS + c), &acc[c]);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (mt == TC_R - 1) {
+                    tc_fence_before();
+                    mbar_arrive(ABAR(ACCE, ab));
+                }
                 const int y = ty * TC_R + mt;
                 if (x >= p.W || y >= p.H) continue;
                 const size_t opix = ((size_t)n * p.H + y) * p.W + x;
@@ -312,7 +345,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const __grid_
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int ce = c4 + e;
-                        float tv = acc[mt][ce];
+                        float tv = acc[ce] + acc[NP + ce];
                         if (ce < p.Cout) {
                             if (p.bias) tv += __ldg(p.bias + ce);
                             if (p.res) tv += p.res_bcast ? rb : __ldg(p.res + opix * p.ldr + ce);
@@ -330,14 +363,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const __grid_
                 }
             }
         }
+        if (p.dbg && tid == 64) p.dbg[blockIdx.x * 8 + 4] = w4;
+    } else {
+        // ===================== in-place hi/lo split of the stage (warps 6-13) =====================
+        const int stid = tid - (TC_THREADS - TC_SPLIT_THREADS);
+        long long w5 = 0, w6 = 0;
+        int it = 0;
+        for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
+            const int sb = it % NBUF;
+            mbar_wait_t(SBAR(P12, sb), (uint32_t)(it / NBUF) & 1u, w5);   // passes 1-2 have consumed the raw stage
+            tc_fence_after();
+            const long long ts = clock64();
+            float4* a4 = reinterpret_cast<float4*>(gbase + sb * A_STRIDE);
+#pragma unroll 4
+            for (int idx = stid; idx < (int)(A_BYTES / 16); idx += TC_SPLIT_THREADS) {
+                float4 v = a4[idx];
+                v.x = tf32_lo(v.x, p.split_rna);
+                v.y = tf32_lo(v.y, p.split_rna);
+                v.z = tf32_lo(v.z, p.split_rna);
+                v.w = tf32_lo(v.w, p.split_rna);
+                a4[idx] = v;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(SBAR(LO, sb));
+            w6 += clock64() - ts;
+        }
+        if (p.dbg && stid == 0) { p.dbg[blockIdx.x * 8 + 5] = w5; p.dbg[blockIdx.x * 8 + 6] = w6; }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) {
+    if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
     }
 }
+
+long long* g_tc_dbg = nullptr;
 
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -355,13 +416,13 @@ PFN_tmapEncodeTiled get_encode() {
     return fn;
 }
 
-template <int KC, int NP>
+template <int KC, int NP, int NBUF, int NACC, int LAG>
 int launch_tc(const CUtensorMap& tmap, TcP p, cudaStream_t s) {
     constexpr uint32_t ROWB = KC * 4;
     constexpr uint32_t A_STRIDE = ((TC_TROWS * TC_TWP * ROWB) + 1023u) & ~1023u;
     constexpr uint32_t B_BYTES = 2 * 9 * NP * ROWB;
-    const size_t smem = 2 * A_STRIDE + B_BYTES + 1024;
-    auto kern = conv3x3_tc_kernel<KC, NP>;
+    const size_t smem = NBUF * A_STRIDE + B_BYTES + 1024;
+    auto kern = conv3x3_tc_kernel<KC, NP, NBUF, NACC, LAG>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -405,10 +466,19 @@ extern "C" int codd_conv3x3_tc(const float* in, int ldi, int cin, int n, int h, 
     p.tilesX = codd_ceil_div(w, TC_TW);
     p.tilesY = codd_ceil_div(h, TC_R);
     p.ntiles = p.tilesX * p.tilesY * n;
+    p.dbg = g_tc_dbg;
     p.split_rna = (flags & 1) ? 1 : 0;
     p.use_base_offset = (flags & 2) ? 1 : 0;
     cudaStream_t s = (cudaStream_t)stream;
-    if (KC == 32 && NP == 32) return launch_tc<32, 32>(tmap, p, s);
-    if (KC == 32 && NP == 16) return launch_tc<32, 16>(tmap, p, s);
-    return launch_tc<16, 16>(tmap, p, s);
+    if (KC == 32 && NP == 32) return launch_tc<32, 32, 2, 3, 1>(tmap, p, s);
+    if (KC == 32 && NP == 16) return launch_tc<32, 16, 2, 3, 1>(tmap, p, s);
+    return launch_tc<16, 16, 4, 4, 2>(tmap, p, s);
+}
+
+// diagnostic: device buffer of [grid][8] int64 cycle counters filled by the next codd_conv3x3_tc launches
+// (0 producer wait-empty, 1 mma wait-full, 2 mma wait-acc-empty, 3 mma wait-lo, 4 epilogue wait-acc-full,
+//  5 split wait-p12, 6 split work, 7 producer total); NULL disables.
+extern "C" CODD_API int codd_conv3x3_tc_debug(long long* dbg) {
+    g_tc_dbg = dbg;
+    return 0;
 }

@@ -87,6 +87,9 @@ CODD_API int codd_conv3x3_tc(const float* in, int ldi, int cin, int n, int h, in
                              const float* weight_split, const float* bias, const float* residual, int ldr,
                              int res_bcast, int cout, int act, float* out, int ldo, int flags, void* stream);
 
+/* Diagnostic: device buffer [grid][8] of int64 cycle counters filled by later codd_conv3x3_tc launches. */
+CODD_API int codd_conv3x3_tc_debug(long long* dbg);
+
 /* First backbone layer (backbone.py:35-39,70): 3x3, pad 1, 3 -> cout (<=16) channels,
  * LeakyReLU, reading NCHW images and writing NHWC.  `left` and `right` are two [n,3,h,w]
  * images batches; the output holds 2n samples: left batch first, then right (right may be

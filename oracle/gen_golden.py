@@ -67,7 +67,7 @@ def main():
     if not ref_loader.available():
         sys.exit("reference not mounted; fixtures can only be generated where /root/reference exists")
     hitnet_fixture("hitnet_s_128x128_d32.npz", 1, 128, 128, 32, wseed=7, dseed=11, kind="S")
-    hitnet_fixture("hitnet_g_128x192_d64.npz", 1, 128, 192, 64, wseed=3, dseed=5, kind="G", full=False)
+    hitnet_fixture("hitnet_s_128x192_d64.npz", 1, 128, 192, 64, wseed=3, dseed=5, kind="S", full=False)
 
 
 if __name__ == "__main__":

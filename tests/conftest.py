@@ -28,7 +28,7 @@ def golden_small():
 
 @pytest.fixture(scope="session")
 def golden_big():
-    return load_golden("hitnet_g_128x192_d64.npz")
+    return load_golden("hitnet_s_128x192_d64.npz")
 
 
 def golden_params(fx):
