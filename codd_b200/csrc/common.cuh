@@ -16,18 +16,17 @@
 static inline bool codd_aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
 
 __device__ __forceinline__ float codd_act(float v, int act, int ch) {
-    switch (act) {
-        case CODD_ACT_LEAKY: return v > 0.f ? v : v * CODD_LEAKY_SLOPE;
-        case CODD_ACT_RELU: return fmaxf(v, 0.f);
-        case CODD_ACT_RELU_CH0: return ch == 0 ? fmaxf(v, 0.f) : v;
-        case CODD_ACT_SIGMOID: return 1.f / (1.f + __expf(-v));
-        case CODD_ACT_MISH: {
-            // x * tanh(softplus(x)); softplus with torch's threshold 20
-            float sp = v > 20.f ? v : log1pf(expf(v));
-            return v * tanhf(sp);
-        }
-        default: return v;
+    // the activations of the stereo path (none / leaky / relu / relu on channel 0) are branch-free
+    // selects; only the rare transcendental ones (fusion heads) take a branch.  (A `switch` here
+    // compiles to an indirect jump per element and dominated the conv epilogues.)
+    if (act >= CODD_ACT_SIGMOID) {
+        if (act == CODD_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
+        const float sp = v > 20.f ? v : log1pf(expf(v));   // mish: x * tanh(softplus(x)), torch threshold 20
+        return v * tanhf(sp);
     }
+    const bool clamp = (act == CODD_ACT_RELU) || (act == CODD_ACT_RELU_CH0 && ch == 0);
+    const float neg = (act == CODD_ACT_LEAKY) ? v * CODD_LEAKY_SLOPE : (clamp ? 0.f : v);
+    return v > 0.f ? v : neg;
 }
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }

@@ -36,8 +36,10 @@ constexpr int TC_TW = 128;          // output columns per tile (= MMA M)
 constexpr int TC_R = 2;             // output rows per tile
 constexpr int TC_TWP = TC_TW + 2;   // staged columns
 constexpr int TC_TROWS = TC_R + 2;  // staged rows
-// warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM alloc), 2-5 = epilogue (TMEM lane quarter =
-// warp % 4), 6-13 = in-place hi/lo split of the stage
+// warp roles (the SM's issue arbiter favours HIGH warp ids, and waiting warps poll their mbarrier,
+// so the latency-critical single-thread roles get the highest ids and the bulk workers the lowest):
+//   0-7  in-place hi/lo split of the stage,  8-11 epilogue (TMEM lane quarter = warp % 4),
+//   12   TMA producer,  13  MMA issuer (+ TMEM alloc)
 constexpr int TC_EPI_THREADS = 128;
 constexpr int TC_SPLIT_THREADS = 256;
 constexpr int TC_THREADS = 64 + TC_EPI_THREADS + TC_SPLIT_THREADS;
@@ -52,6 +54,7 @@ struct TcP {
     long long* dbg;       // optional [grid][8] cycle counters (role wait times), NULL in production
     int split_rna;        // 1: hi(x) = round-to-nearest tf32, 0: truncation (what the MMA datapath does)
     int use_base_offset;  // 1: set the descriptor base-offset field from the start address (diagnostic)
+    int diag;             // bit0: skip epilogue stores, bit1: skip the stage split (diagnostics only)
 };
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -65,6 +68,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+template <bool BACKOFF = false>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     while (!done) {
@@ -75,11 +79,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "=r"(done)
             : "r"(bar), "r"(parity)
             : "memory");
+        if (BACKOFF && !done) __nanosleep(32);   // a polling warp must not starve the working warps of its SM sub-partition
     }
 }
+template <bool BACKOFF = false>
 __device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, long long& acc) {
     const long long t0 = clock64();
-    mbar_wait(bar, parity);
+    mbar_wait<BACKOFF>(bar, parity);
     acc += clock64() - t0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -223,7 +229,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const __grid_
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {
+    if (warp == 13) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&tmem_base_slot)),
                      "r"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -243,7 +249,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const __grid_
     tc_fence_after();
     const uint32_t tmem = tmem_base_slot;
 
-    if (warp == 0) {
+    if (warp == 12) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             long long w0 = 0;
@@ -257,7 +263,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const __grid_
                 q /= p.tilesX;
                 const int ty = q % p.tilesY;
                 const int n = q / p.tilesY;
-                mbar_wait_t(SBAR(EMPTY, sb), ph ^ 1u, w0);
+                mbar_wait_t<true>(SBAR(EMPTY, sb), ph ^ 1u, w0);
                 mbar_expect_tx(SBAR(FULL, sb), A_BYTES);
                 const int cx = tx * TC_TW - 1, cy = ty * TC_R - 1;
                 asm volatile(
@@ -266,9 +272,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const __grid_
                     "l"(&tmap), "r"(SBAR(FULL, sb)), "r"(0), "r"(cx), "r"(cy), "r"(n)
                     : "memory");
             }
-            if (p.dbg) { p.dbg[blockIdx.x * 8 + 0] = w0; p.dbg[blockIdx.x * 8 + 7] = clock64() - tstart; }
+            (void)tstart;
         }
-    } else if (warp == 1) {
+    } else if (warp == 13) {
         // ===================== MMA issuer =====================
         // Software-pipelined over tiles: passes 1-2 of tile i are issued BEFORE pass 3 of tile i-1, so
         // the tensor pipe works on the next tile while the split warps rewrite the previous stage.
@@ -277,7 +283,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const __grid_
             long long w1 = 0, w2 = 0, w3 = 0;
             auto pass3 = [&](int it) {
                 const int sb = it % NBUF, ab = it % NACC;
-                mbar_wait_t(SBAR(LO, sb), (uint32_t)(it / NBUF) & 1u, w3);
+                mbar_wait_t<true>(SBAR(LO, sb), (uint32_t)(it / NBUF) & 1u, w3);
                 tc_fence_after();
                 const uint64_t a_desc = make_desc<KC>(sbase + sb * A_STRIDE, p.use_base_offset);
 #pragma unroll
@@ -290,8 +296,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const __grid_
             int it = 0;
             for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
                 const int sb = it % NBUF, ab = it % NACC;
-                mbar_wait_t(SBAR(FULL, sb), (uint32_t)(it / NBUF) & 1u, w1);
-                mbar_wait_t(ABAR(ACCE, ab), ((uint32_t)(it / NACC) & 1u) ^ 1u, w2);
+                mbar_wait_t<true>(SBAR(FULL, sb), (uint32_t)(it / NBUF) & 1u, w1);
+                mbar_wait_t<true>(ABAR(ACCE, ab), ((uint32_t)(it / NACC) & 1u) ^ 1u, w2);
                 tc_fence_after();
                 const uint64_t a_desc = make_desc<KC>(sbase + sb * A_STRIDE, p.use_base_offset);
 #pragma unroll
@@ -306,10 +312,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const __grid_
             for (int j = (it > LAG ? it - LAG : 0); j < it; ++j) pass3(j);
             if (p.dbg) { p.dbg[blockIdx.x * 8 + 1] = w1; p.dbg[blockIdx.x * 8 + 2] = w2; p.dbg[blockIdx.x * 8 + 3] = w3; }
         }
-    } else if (warp < 6) {
-        // ===================== epilogue (warps 2-5) =====================
+    } else if (warp >= 8) {
+        // ===================== epilogue (warps 8-11) =====================
         const int quarter = warp & 3;                 // TMEM lanes 32*quarter .. +31
-        long long w4 = 0;
+        long long w4 = 0, wld = 0, warr = 0, wrest = 0;
+        // run-time epilogue switches, evaluated once
+        const float slope = p.act == CODD_ACT_LEAKY ? CODD_LEAKY_SLOPE : (p.act == CODD_ACT_RELU ? 0.f : 1.f);
+        const float slope0 = (p.act == CODD_ACT_RELU || p.act == CODD_ACT_RELU_CH0) ? 0.f : slope;
+        const bool full_vec = (p.Cout == NP) && ((p.ldo & 3) == 0) && ((((uintptr_t)p.out) & 15u) == 0);
+        const bool res_vec = p.res && !p.res_bcast && (p.Cout == NP) && ((p.ldr & 3) == 0) &&
+                             ((((uintptr_t)p.res) & 15u) == 0);
+        float biasr[NP];                              // bias lives in registers for the whole kernel
+#pragma unroll
+        for (int c = 0; c < NP; ++c) biasr[c] = (p.bias && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
         int it = 0;
         for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
             const int ab = it % NACC;
@@ -318,65 +333,90 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const __grid_
             q /= p.tilesX;
             const int ty = q % p.tilesY;
             const int n = q / p.tilesY;
-            mbar_wait_t(ABAR(ACCF, ab), (uint32_t)(it / NACC) & 1u, w4);
+            mbar_wait_t<true>(ABAR(ACCF, ab), (uint32_t)(it / NACC) & 1u, w4);
             tc_fence_after();
             const int x = tx * TC_TW + quarter * 32 + lane;
 #pragma unroll
             for (int mt = 0; mt < TC_R; ++mt) {
                 float acc[ACC_COLS];
+                const long long tl0 = clock64();
 #pragma unroll
                 for (int c = 0; c < ACC_COLS; c += 16)
                     tc_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((ab * TC_R + mt) * ACC_COLS + c), &acc[c]);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                wld += clock64() - tl0;
+                const long long ta0 = clock64();
                 if (mt == TC_R - 1) {
                     tc_fence_before();
                     mbar_arrive(ABAR(ACCE, ab));
                 }
+                warr += clock64() - ta0;
+                const long long tr0 = clock64();
                 const int y = ty * TC_R + mt;
                 if (x >= p.W || y >= p.H) continue;
                 const size_t opix = ((size_t)n * p.H + y) * p.W + x;
                 float* op = p.out + opix * p.ldo;
-                float rb = 0.f;
-                if (p.res && p.res_bcast) rb = __ldg(p.res + opix * p.ldr);
+                // straight-line epilogue: every run-time switch is hoisted out of the per-element code
+                float v[NP];
 #pragma unroll
-                for (int c4 = 0; c4 < NP; c4 += 4) {
-                    if (c4 >= p.Cout) break;
-                    float v[4];
+                for (int c = 0; c < NP; ++c) v[c] = (acc[c] + acc[NP + c]) + biasr[c];
+                if (p.res) {
+                    const float* rp = p.res + opix * p.ldr;
+                    if (p.res_bcast) {
+                        const float rb = __ldg(rp);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int ce = c4 + e;
-                        float tv = acc[ce] + acc[NP + ce];
-                        if (ce < p.Cout) {
-                            if (p.bias) tv += __ldg(p.bias + ce);
-                            if (p.res) tv += p.res_bcast ? rb : __ldg(p.res + opix * p.ldr + ce);
-                            tv = codd_act(tv, p.act, ce);
+                        for (int c = 0; c < NP; ++c) v[c] += rb;
+                    } else if (res_vec) {
+#pragma unroll
+                        for (int c4 = 0; c4 < NP; c4 += 4) {
+                            const float4 r4 = ldg4(rp + c4);
+                            v[c4] += r4.x; v[c4 + 1] += r4.y; v[c4 + 2] += r4.z; v[c4 + 3] += r4.w;
                         }
-                        v[e] = tv;
-                    }
-                    if (c4 + 3 < p.Cout && (p.ldo & 3) == 0) {
-                        *reinterpret_cast<float4*>(op + c4) = make_float4(v[0], v[1], v[2], v[3]);
                     } else {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            if (c4 + e < p.Cout) op[c4 + e] = v[e];
+                        for (int c = 0; c < NP; ++c)
+                            if (c < p.Cout) v[c] += __ldg(rp + c);
                     }
                 }
+                if (p.act <= CODD_ACT_RELU_CH0) {
+                    // none / leaky / relu / relu(ch0): max(v,0) + slope*min(v,0), slope in {1, 0.2, 0}
+#pragma unroll
+                    for (int c = 0; c < NP; ++c) {
+                        const float sl = c == 0 ? slope0 : slope;
+                        v[c] = fmaxf(v[c], 0.f) + sl * fminf(v[c], 0.f);
+                    }
+                } else {
+#pragma unroll 1
+                    for (int c = 0; c < NP; ++c) v[c] = codd_act(v[c], p.act, c);
+                }
+                if (!(p.diag & 1)) {
+                    if (full_vec) {
+#pragma unroll
+                        for (int c4 = 0; c4 < NP; c4 += 4)
+                            *reinterpret_cast<float4*>(op + c4) = make_float4(v[c4], v[c4 + 1], v[c4 + 2], v[c4 + 3]);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < NP; ++c)
+                            if (c < p.Cout) op[c] = v[c];
+                    }
+                }
+                wrest += clock64() - tr0;
             }
         }
-        if (p.dbg && tid == 64) p.dbg[blockIdx.x * 8 + 4] = w4;
+        if (p.dbg && tid == 256) { p.dbg[blockIdx.x * 8 + 4] = w4; p.dbg[blockIdx.x * 8 + 0] = wld; p.dbg[blockIdx.x * 8 + 7] = wrest; }
     } else {
-        // ===================== in-place hi/lo split of the stage (warps 6-13) =====================
-        const int stid = tid - (TC_THREADS - TC_SPLIT_THREADS);
+        // ===================== in-place hi/lo split of the stage (warps 0-7) =====================
+        const int stid = tid;
         long long w5 = 0, w6 = 0;
         int it = 0;
         for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
             const int sb = it % NBUF;
-            mbar_wait_t(SBAR(P12, sb), (uint32_t)(it / NBUF) & 1u, w5);   // passes 1-2 have consumed the raw stage
+            mbar_wait_t<true>(SBAR(P12, sb), (uint32_t)(it / NBUF) & 1u, w5);   // passes 1-2 have consumed the raw stage
             tc_fence_after();
             const long long ts = clock64();
             float4* a4 = reinterpret_cast<float4*>(gbase + sb * A_STRIDE);
 #pragma unroll 4
-            for (int idx = stid; idx < (int)(A_BYTES / 16); idx += TC_SPLIT_THREADS) {
+            for (int idx = stid; idx < ((p.diag & 2) ? 0 : (int)(A_BYTES / 16)); idx += TC_SPLIT_THREADS) {
                 float4 v = a4[idx];
                 v.x = tf32_lo(v.x, p.split_rna);
                 v.y = tf32_lo(v.y, p.split_rna);
@@ -392,7 +432,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const __grid_
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == 13) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
     }
@@ -469,6 +509,7 @@ extern "C" int codd_conv3x3_tc(const float* in, int ldi, int cin, int n, int h, 
     p.dbg = g_tc_dbg;
     p.split_rna = (flags & 1) ? 1 : 0;
     p.use_base_offset = (flags & 2) ? 1 : 0;
+    p.diag = (flags >> 2) & 3;
     cudaStream_t s = (cudaStream_t)stream;
     if (KC == 32 && NP == 32) return launch_tc<32, 32, 2, 3, 1>(tmap, p, s);
     if (KC == 32 && NP == 16) return launch_tc<32, 16, 2, 3, 1>(tmap, p, s);

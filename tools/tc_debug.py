@@ -16,11 +16,14 @@ for (cin, cout, n, h, w) in [(16, 16, 16, 576, 960), (32, 32, 8, 288, 480)]:
         ops.conv3x3_tc(x, ws, b, cout, ACT_LEAKY)
     lib.load().codd_conv3x3_tc_debug(dbg.data_ptr())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for fl in (4, 8, 12):
+        e0.record(); ops.conv3x3_tc(x, ws, b, cout, ACT_LEAKY, flags=fl); e1.record(); torch.cuda.synchronize()
+        print(f"   diag flags {fl} (4=no stores, 8=no split, 12=neither): {e0.elapsed_time(e1)*1e3:.0f} us")
     e0.record(); ops.conv3x3_tc(x, ws, b, cout, ACT_LEAKY); e1.record(); torch.cuda.synchronize()
     lib.load().codd_conv3x3_tc_debug(None)
     d = dbg.view(148, 8).double().mean(0).tolist()
-    names = ["prod wait-empty", "mma wait-full", "mma wait-acc-empty", "mma wait-lo", "epi wait-acc-full",
-             "split wait-p12", "split work", "producer total"]
+    names = ["epi tmem-ld cycles", "mma wait-full", "mma wait-acc-empty", "mma wait-lo", "epi wait-acc-full",
+             "split wait-p12", "split work", "epi math+store cycles"]
     tiles = n * ((h + 1) // 2) * ((w + 127) // 128) / 148
     print(f"cin={cin} cout={cout}: {e0.elapsed_time(e1)*1e3:.0f} us, {tiles:.0f} tiles/SM; mean cycles per tile:")
     for nm, v in zip(names, d):
