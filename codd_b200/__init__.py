@@ -8,9 +8,10 @@ from . import lib, ops  # noqa: F401
 from .builder import build_estimator  # noqa: F401
 from .codd import ConsistentOnlineDynamicDepth  # noqa: F401
 from .registry import BACKBONES, ESTIMATORS, MODELS  # noqa: F401
+from .fusion import Fusion  # noqa: F401
 from .stereo import HITNetMF, HITUNet, TileInitialization, TilePropagation  # noqa: F401
 
-__all__ = ["build_estimator", "ConsistentOnlineDynamicDepth", "HITNetMF", "HITUNet", "TileInitialization",
+__all__ = ["build_estimator", "Fusion", "ConsistentOnlineDynamicDepth", "HITNetMF", "HITUNet", "TileInitialization",
            "TilePropagation", "MODELS", "BACKBONES", "ESTIMATORS", "lib", "ops"]
 
 

@@ -29,6 +29,27 @@ __device__ __forceinline__ float codd_act(float v, int act, int ch) {
     return v > 0.f ? v : neg;
 }
 
+// Hoisted form for epilogues: evaluate the run-time activation code ONCE (ActSel), then apply it
+// per element as max(v,0) + slope*min(v,0) with slope in {1 (none), 0.2 (leaky), 0 (relu)}; only
+// the transcendental activations fall back to codd_act.
+struct ActSel {
+    float slope, slope0;
+    bool simple;
+    int act;
+};
+__device__ __forceinline__ ActSel codd_act_sel(int act) {
+    ActSel a;
+    a.act = act;
+    a.simple = act <= CODD_ACT_RELU_CH0;
+    a.slope = act == CODD_ACT_LEAKY ? CODD_LEAKY_SLOPE : (act == CODD_ACT_RELU ? 0.f : 1.f);
+    a.slope0 = (act == CODD_ACT_RELU || act == CODD_ACT_RELU_CH0) ? 0.f : a.slope;
+    return a;
+}
+__device__ __forceinline__ float codd_act_apply(const ActSel& a, float v, int ch) {
+    if (a.simple) return fmaxf(v, 0.f) + (ch == 0 ? a.slope0 : a.slope) * fminf(v, 0.f);
+    return codd_act(v, a.act, ch);
+}
+
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 static inline int codd_ceil_div(int a, int b) { return (a + b - 1) / b; }

@@ -24,7 +24,7 @@ struct ConvP {
     const float* bias;
     const float* res;
     float* out;
-    int N, H, W, C0, ld0, C1, ld1, Cout, ldo, ph, pw, Ho, Wo, act, ldr, res_bcast;
+    int N, H, W, C0, ld0, C1, ld1, Cout, ldo, ph, pw, Ho, Wo, act, ldr, res_bcast, res_after;
     int tilesX, tilesY;
     int vec0, vec1;  // 128-bit loads allowed on in0 / in1
 };
@@ -145,6 +145,7 @@ __global__ void __launch_bounds__(256, 2) conv_nhwc_kernel(ConvP p) {
     if (ox >= p.Wo) return;
     const int cbase = g * CO_T;
     const bool vec_out = ((p.ldo & 3) == 0) && ((((uintptr_t)p.out) & 15u) == 0);
+    const ActSel asel = codd_act_sel(p.act);
 #pragma unroll
     for (int i = 0; i < PX; ++i) {
         const int oy = oy0 + pwi * PX + i;
@@ -164,8 +165,8 @@ __global__ void __launch_bounds__(256, 2) conv_nhwc_kernel(ConvP p) {
                 const int ce = co + e;
                 if (ce < p.Cout) {
                     if (p.bias) t += __ldg(p.bias + ce);
-                    if (p.res) t += p.res_bcast ? rb : __ldg(p.res + opix * p.ldr + ce);
-                    t = codd_act(t, p.act, ce);
+                    const float rv = p.res ? (p.res_bcast ? rb : __ldg(p.res + opix * p.ldr + ce)) : 0.f;
+                    t = p.res_after ? codd_act_apply(asel, t, ce) + rv : codd_act_apply(asel, t + rv, ce);
                 }
                 v[e] = t;
             }
@@ -276,6 +277,7 @@ __global__ void __launch_bounds__(256) pointwise_kernel(ConvP p, size_t npix) {
             }
         }
     }
+    const ActSel asel = codd_act_sel(p.act);
 #pragma unroll
     for (int q = 0; q < PX_T; ++q) {
         const size_t px = base + (size_t)q * blockDim.x;
@@ -292,8 +294,8 @@ __global__ void __launch_bounds__(256) pointwise_kernel(ConvP p, size_t npix) {
                 float t = acc[q][ce];
                 if (ce < p.Cout) {
                     if (p.bias) t += __ldg(p.bias + ce);
-                    if (p.res) t += p.res_bcast ? rb : __ldg(p.res + px * p.ldr + ce);
-                    t = codd_act(t, p.act, ce);
+                    const float rv = p.res ? (p.res_bcast ? rb : __ldg(p.res + px * p.ldr + ce)) : 0.f;
+                    t = p.res_after ? codd_act_apply(asel, t, ce) + rv : codd_act_apply(asel, t + rv, ce);
                 }
                 v[e] = t;
             }
@@ -447,6 +449,7 @@ __global__ void __launch_bounds__(128) deconv2x2_kernel(const float* __restrict_
     }
     float* op = out + (((size_t)s * 2 * h + oy) * 2 * w + 2 * x) * ldo;
     const bool vec = (ldo & 3) == 0 && (cout & 3) == 0 && ((((uintptr_t)out) & 15u) == 0);
+    const ActSel asel = codd_act_sel(act);
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
         if (vec) {
@@ -454,14 +457,14 @@ __global__ void __launch_bounds__(128) deconv2x2_kernel(const float* __restrict_
             for (int o4 = 0; o4 < CO / 4; ++o4) {
                 if (o4 * 4 >= cout) break;
                 float4 r;
-                r.x = codd_act(acc[q][o4 * 4 + 0] + __ldg(bias + o4 * 4 + 0), act, o4 * 4 + 0);
-                r.y = codd_act(acc[q][o4 * 4 + 1] + __ldg(bias + o4 * 4 + 1), act, o4 * 4 + 1);
-                r.z = codd_act(acc[q][o4 * 4 + 2] + __ldg(bias + o4 * 4 + 2), act, o4 * 4 + 2);
-                r.w = codd_act(acc[q][o4 * 4 + 3] + __ldg(bias + o4 * 4 + 3), act, o4 * 4 + 3);
+                r.x = codd_act_apply(asel, acc[q][o4 * 4 + 0] + __ldg(bias + o4 * 4 + 0), o4 * 4 + 0);
+                r.y = codd_act_apply(asel, acc[q][o4 * 4 + 1] + __ldg(bias + o4 * 4 + 1), o4 * 4 + 1);
+                r.z = codd_act_apply(asel, acc[q][o4 * 4 + 2] + __ldg(bias + o4 * 4 + 2), o4 * 4 + 2);
+                r.w = codd_act_apply(asel, acc[q][o4 * 4 + 3] + __ldg(bias + o4 * 4 + 3), o4 * 4 + 3);
                 *reinterpret_cast<float4*>(op + q * ldo + o4 * 4) = r;
             }
         } else {
-            for (int i = 0; i < cout; ++i) op[q * ldo + i] = codd_act(acc[q][i] + __ldg(bias + i), act, i);
+            for (int i = 0; i < cout; ++i) op[q * ldo + i] = codd_act_apply(asel, acc[q][i] + __ldg(bias + i), i);
         }
     }
 }
@@ -538,7 +541,7 @@ extern "C" int codd_conv2d_nhwc(const codd_conv_desc* d, const float* in0, const
     p.C1 = d->c1 > 0 ? d->c1 : 0; p.ld1 = d->ld1;
     p.Cout = d->cout; p.ldo = d->ldo;
     p.ph = d->ph; p.pw = d->pw; p.Ho = d->ho; p.Wo = d->wo;
-    p.act = d->act; p.ldr = d->ldr; p.res_bcast = d->res_bcast;
+    p.act = d->act; p.ldr = d->ldr; p.res_bcast = d->res_bcast; p.res_after = d->res_after_act;
     p.tilesX = p.tilesY = 0;
     p.vec0 = codd_aligned16(in0) && (d->ld0 % 4 == 0);
     p.vec1 = p.in1 && codd_aligned16(in1) && (d->ld1 % 4 == 0) && (d->c0 % 4 == 0);

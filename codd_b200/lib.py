@@ -18,7 +18,7 @@ ACT_NONE, ACT_LEAKY, ACT_RELU, ACT_RELU_CH0, ACT_SIGMOID, ACT_MISH = 0, 1, 2, 3,
 class ConvDesc(Structure):
     _fields_ = [(k, c_int) for k in (
         "n", "h", "w", "c0", "ld0", "c1", "ld1", "cout", "ldo", "kh", "kw", "sh", "sw",
-        "ph", "pw", "dil", "ho", "wo", "act", "ldr", "res_bcast")]
+        "ph", "pw", "dil", "ho", "wo", "act", "ldr", "res_bcast", "res_after_act")]
 
 
 _FP = c_void_p  # device pointers travel as integers
@@ -42,6 +42,11 @@ SIGNATURES = {
     "codd_tile_warp_cost": (c_int, [_FP, c_int, _FP, c_int, _FP, c_int, _FP, c_int, _FP, _FP, c_int, c_int,
                                     c_int, _FP, c_int, _FP, c_void_p]),
     "codd_hyp_select": (c_int, [_FP, c_int, _FP, c_int, c_int, c_int, c_int, _FP, c_int, c_void_p]),
+    "codd_fusion_cues_lowres": (c_int, [_FP, c_int, _FP, c_int, _FP, c_int, _FP, c_int, _FP, _FP, c_int, c_int, c_int,
+                                        c_int, _FP, c_int, _FP, c_int, _FP, c_int, c_void_p]),
+    "codd_fusion_forget_in": (c_int, [_FP, _FP, _FP, _FP, _FP, _FP, c_int, c_int, c_int, _FP, c_int, _FP, c_void_p]),
+    "codd_fusion_blend": (c_int, [_FP, _FP, _FP, c_int, _FP, _FP, _FP, c_int, c_int, c_int, c_int, _FP, _FP, _FP,
+                                  c_void_p]),
     "codd_nhwc_to_nchw": (c_int, [_FP, c_int, c_int, c_int, c_int, c_int, _FP, c_void_p]),
     "codd_nchw_to_nhwc": (c_int, [_FP, c_int, c_int, c_int, c_int, _FP, c_int, c_void_p]),
 }

@@ -176,7 +176,7 @@ def conv3x3_tc(x, wsplit, bias, cout, act=ACT_NONE, residual=None, res_bcast=Fal
 
 
 def conv2d(x, wp, bias, cout, k, stride=(1, 1), pad=(0, 0), dil=1, act=ACT_NONE, x2=None, residual=None,
-           res_bcast=False, out=None, out_hw=None, ld_out=None):
+           res_bcast=False, out=None, out_hw=None, ld_out=None, res_after_act=False):
     """act(conv(cat(x, x2)) + bias + residual).  ``wp`` is a packed weight."""
     _require_cuda(x, x2, wp, bias, residual, out)
     n, c0, h, w = x.shape
@@ -195,7 +195,8 @@ def conv2d(x, wp, bias, cout, k, stride=(1, 1), pad=(0, 0), dil=1, act=ACT_NONE,
         out = empty_nhwc(n, cout, ho, wo, x.device, ld_out)
     d = ConvDesc(n=n, h=h, w=w, c0=c0, ld0=ld_of(x), c1=c1, ld1=0 if x2 is None else ld_of(x2), cout=cout,
                  ldo=ld_of(out), kh=kh, kw=kw, sh=sh, sw=sw, ph=ph, pw=pw, dil=dil, ho=ho, wo=wo, act=act,
-                 ldr=0 if residual is None else ld_of(residual), res_bcast=1 if res_bcast else 0)
+                 ldr=0 if residual is None else ld_of(residual), res_bcast=1 if res_bcast else 0,
+                 res_after_act=1 if res_after_act else 0)
     nbytes = 4 * (n * h * w * (c0 + c1) + n * ho * wo * cout + wp.numel()
                   + (0 if residual is None else n * ho * wo * (1 if res_bcast else cout)))
     tag = f"conv{kh}x{kw}_s{sh}{sw}_d{dil}_cin{c0 + c1}_cout{cout}"
@@ -362,3 +363,54 @@ def hyp_select(update, aug):
         update.data_ptr(), ld_of(update), aug.data_ptr(), ld_of(aug), n, h, w, out.data_ptr(), 16, _stream()))
     _lib.check(rc, "codd_hyp_select")
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# Fusion (K13)
+# ----------------------------------------------------------------------------------------------
+def fusion_cues_lowres(feat_curr, feat_warp, fea_l, fea_r, pred_curr, pred_warp, ds=4, extra=None):
+    """-> corr_feat [N,31,h,w] (NHWC, ld 32), disp2 [N,2,h,w] (NHWC)."""
+    _require_cuda(feat_curr, feat_warp, fea_l, fea_r, pred_curr, pred_warp, extra)
+    n, c, h, w = feat_curr.shape
+    fea_r = planar(fea_r)
+    pred_curr, pred_warp = pred_curr.contiguous(), pred_warp.contiguous()
+    corr = empty_nhwc(n, 31, h, w, feat_curr.device, ld=32)
+    disp2 = empty_nhwc(n, 2, h, w, feat_curr.device)
+    cs = fea_l.shape[1]
+    nbytes = 4 * n * h * w * (2 * c * 9 + 2 * cs + 2 + 34)
+    rc = _run("fusion_cues_lowres", nbytes, lambda: _lib.load().codd_fusion_cues_lowres(
+        feat_curr.data_ptr(), ld_of(feat_curr), feat_warp.data_ptr(), ld_of(feat_warp), fea_l.data_ptr(), ld_of(fea_l),
+        fea_r.data_ptr(), cs, pred_curr.data_ptr(), pred_warp.data_ptr(), n, h, w, ds, corr.data_ptr(), 32,
+        disp2.data_ptr(), 2, None if extra is None else extra.data_ptr(), 0 if extra is None else ld_of(extra),
+        _stream()))
+    _lib.check(rc, "codd_fusion_cues_lowres")
+    return corr, disp2
+
+
+def fusion_forget_in(pred_curr, pred_warp, flow_warp, conf_warp, weight, bias, want_cues=False):
+    """-> forget_head[0] output [N,16,H,W] NHWC (and the 32 planar cues when want_cues)."""
+    _require_cuda(pred_curr, pred_warp, flow_warp, conf_warp, weight, bias)
+    n, _, h, w = pred_curr.shape
+    pred_curr, pred_warp = pred_curr.contiguous(), pred_warp.contiguous()
+    flow_warp, conf_warp = planar(flow_warp), planar(conf_warp)
+    out = empty_nhwc(n, 16, h, w, pred_curr.device)
+    cues = torch.empty((n, 32, h, w), device=pred_curr.device) if want_cues else None
+    rc = _run("fusion_forget_in", 4 * n * h * w * (8 + 16), lambda: _lib.load().codd_fusion_forget_in(
+        pred_curr.data_ptr(), pred_warp.data_ptr(), flow_warp.data_ptr(), conf_warp.data_ptr(), weight.data_ptr(),
+        bias.data_ptr(), n, h, w, out.data_ptr(), 16, None if cues is None else cues.data_ptr(), _stream()))
+    _lib.check(rc, "codd_fusion_forget_in")
+    return (out, cues) if want_cues else out
+
+
+def fusion_blend(pred_curr, pred_warp, r8, weight, bias, wf_lowres, ds=4):
+    """-> (disp_fused, fusion_weights, reset_weights), each [N,1,H,W]."""
+    _require_cuda(pred_curr, pred_warp, r8, weight, bias, wf_lowres)
+    n, _, h, w = pred_curr.shape
+    pred_curr, pred_warp, wf_lowres = pred_curr.contiguous(), pred_warp.contiguous(), wf_lowres.contiguous()
+    dev = pred_curr.device
+    fused, wf, wr = (torch.empty((n, 1, h, w), device=dev) for _ in range(3))
+    rc = _run("fusion_blend", 4 * n * h * w * (2 + 8 + 3), lambda: _lib.load().codd_fusion_blend(
+        pred_curr.data_ptr(), pred_warp.data_ptr(), r8.data_ptr(), ld_of(r8), weight.data_ptr(), bias.data_ptr(),
+        wf_lowres.data_ptr(), n, h, w, ds, fused.data_ptr(), wf.data_ptr(), wr.data_ptr(), _stream()))
+    _lib.check(rc, "codd_fusion_blend")
+    return fused, wf, wr

@@ -68,6 +68,7 @@ typedef struct codd_conv_desc {
     int act;              /* CODD_ACT_* applied after bias (+ residual) */
     int ldr;              /* residual pixel stride (ignored when residual == NULL) */
     int res_bcast;        /* 1: residual has one channel, broadcast over cout */
+    int res_after_act;    /* 1: out = act(conv + bias) + residual  (fusion.py:349 long skip) instead of act(.. + residual) */
 } codd_conv_desc;
 
 /* weight is PACKED [kh*kw][c0+c1][cout] (host side: w.permute(2,3,1,0).contiguous()).
@@ -180,6 +181,31 @@ CODD_API int codd_tile_warp_cost(const float* fea_l, int ldfl, const float* fea_
  * ------------------------------------------------------------------------------------------ */
 CODD_API int codd_hyp_select(const float* update, int ldu, const float* aug, int ldaug,
                     int n, int h, int w, float* refined, int ldr, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K13  Fusion input cues and blend (reference: model/fusion/fusion.py:168-318,383-394;
+ *      disp_warp utils/warp.py:43-66).
+ * ------------------------------------------------------------------------------------------ */
+/* 1/ds-resolution cues: corr[n,y,x,0:31] = [feat cross-corr (9), self-corr curr (8), self-corr warp (8),
+ * local stereo cost of pred_curr/ds + {-1,0,1} (3), of pred_warp/ds + {-1,0,1} (3)]; disp2 = the two
+ * disparities sub-sampled at [ds/2-1::ds] (conv_disp input); extra (optional) = the same pair again.
+ * feat_* [n,h,w,32] NHWC; fea_l [n,h,w,cs] NHWC, fea_r_planar [n,cs,h,w]; pred_* [n,h*ds,w*ds]. */
+CODD_API int codd_fusion_cues_lowres(const float* feat_curr, int ldc, const float* feat_warp, int ldw,
+                                     const float* fea_l, int ldl, const float* fea_r_planar, int cs,
+                                     const float* pred_curr, const float* pred_warp, int n, int h, int w, int ds,
+                                     float* corr, int ldo, float* disp2, int ld2, float* extra, int ldx,
+                                     void* stream);
+/* Full-resolution cues [|curr - warp patch| (9), |self| (8+8), flow_warp (3), warp>0 (1), conf_warp (3)]
+ * folded into forget_head's first 1x1 conv: out[n,y,x,0:16] = W[16][32] . cues + b.
+ * flow_warp / conf_warp [n,3,h,w] planar.  cues_debug (optional) receives the 32 cues [n,32,h,w]. */
+CODD_API int codd_fusion_forget_in(const float* pred_curr, const float* pred_warp, const float* flow_warp,
+                                   const float* conf_warp, const float* weight, const float* bias, int n, int h,
+                                   int w, float* out, int ldo, float* cues_debug, void* stream);
+/* reset weight = sigmoid(w[8] . r8 + b) * (warp>0); fusion weight = wf_lowres nearest-upsampled x ds * (warp>0);
+ * fused = curr*(1 - wf*wr) + warp*wf*wr.  r8 [n,h,w,8] NHWC; outputs [n,h,w]. */
+CODD_API int codd_fusion_blend(const float* pred_curr, const float* pred_warp, const float* r8, int ldr,
+                               const float* weight, const float* bias, const float* wf_lowres, int n, int h, int w,
+                               int ds, float* fused, float* wf, float* wr, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * layout helpers at the module boundary

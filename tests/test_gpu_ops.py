@@ -323,3 +323,56 @@ def test_conv3x3_tensor_core(ops, cin, cout, h, w):
     print(f"conv3x3_tc cin={cin} cout={cout}: max abs err per flags {errs}")
     out = ops.conv3x3_tc(nhwc(ops, x), ws, b.cuda(), cout, ACT_LEAKY, residual=nhwc(ops, res), flags=0)
     torch.testing.assert_close(back(ops, out), ref, rtol=CONV_RTOL, atol=CONV_ATOL)
+
+
+# ------------------------------------------------------------------------------------------
+# Fusion (K13)
+# ------------------------------------------------------------------------------------------
+def test_fusion_cue_kernels(ops):
+    from oracle import fusion_oracle as FO
+    outputs, state = FO.synth_fusion_inputs(2, 64, 96, seed=4)
+    _, feat_warp, conf_warp, pred_warp, flow_warp = state["memory"]
+    feat_curr = torch.randn(2, 32, 16, 24, generator=gen(1))
+    corr_ref, fr_ref = FO.compute_input_cues(outputs["pred_disp"], pred_warp, feat_curr, feat_warp, flow_warp, conf_warp,
+                                             outputs["left_feat"], outputs["right_feat"], direct=True)
+    corr, disp2 = ops.fusion_cues_lowres(nhwc(ops, feat_curr), nhwc(ops, feat_warp), nhwc(ops, outputs["left_feat"]),
+                                         outputs["right_feat"].cuda(), outputs["pred_disp"].cuda(), pred_warp.cuda(), 4)
+    got = back(ops, corr)
+    assert torch.equal(got[:, 25:31], corr_ref[:, 25:31]), "local stereo costs not bit-identical"
+    torch.testing.assert_close(got[:, :25], corr_ref[:, :25], rtol=1e-5, atol=1e-5)
+    d2 = back(ops, disp2)
+    assert torch.equal(d2[:, 0:1], outputs["pred_disp"][..., 1::4, 1::4]) and torch.equal(d2[:, 1:2], pred_warp[..., 1::4, 1::4])
+    w = torch.randn(16, 32, 1, 1, generator=gen(2)) / 6
+    b = torch.randn(16, generator=gen(3))
+    r16, cues = ops.fusion_forget_in(outputs["pred_disp"].cuda(), pred_warp.cuda(), flow_warp.cuda(), conf_warp.cuda(),
+                                     w.cuda().contiguous(), b.cuda(), want_cues=True)
+    assert torch.equal(cues.cpu(), fr_ref), "full-resolution cues not bit-identical"
+    torch.testing.assert_close(back(ops, r16), F.conv2d(fr_ref, w, b), rtol=CONV_RTOL, atol=CONV_ATOL)
+
+
+def test_fusion_memory_query_vs_oracle():
+    import codd_b200
+    from oracle import fusion_oracle as FO
+    sd = FO.random_fusion_params(5)
+    fus = codd_b200.MODELS.build(dict(type="Fusion", in_channels=24, fusion_channel=32,
+                                      corr_cfg=dict(type="px2patch", patch_size=3)))
+    fus.load_state_dict(sd, strict=True)
+    fus.cuda().eval()
+    for first in (True, False):
+        outputs, state = FO.synth_fusion_inputs(2, 128, 192, seed=6)
+        if first:
+            state = {}
+        ref_o = FO.memory_query(sd, {k: v.clone() for k, v in outputs.items()}, dict(state), direct=True)
+        ref_s = dict(state)
+        FO.memory_update(ref_o, ref_s)
+        o = {k: v.cuda() for k, v in outputs.items()}
+        s = {k: [t.cuda() for t in v] for k, v in state.items()}
+        with torch.no_grad():
+            fus.memory_query(o, s)
+            fus.memory_update(o, s)
+        from codd_b200 import ops as _ops
+        torch.testing.assert_close(_ops.to_nchw(o["left_feat"]).cpu(), ref_o["left_feat"], rtol=1e-4, atol=1e-4)
+        keys = ["pred_disp"] + ([] if first else ["fusion_weights", "reset_weights"])
+        for k in keys:
+            torch.testing.assert_close(o[k].cpu(), ref_o[k], rtol=1e-4, atol=1e-4)
+        assert len(s["memory"]) == 3 and s["memory"][2].shape == ref_s["memory"][2].shape

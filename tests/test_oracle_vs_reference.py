@@ -68,3 +68,32 @@ def test_same_seed_same_weights_as_reference():
     a, b = mine.state_dict(), ref.state_dict()
     assert list(a.keys()) == list(b.keys())
     assert all(torch.equal(a[k], b[k]) for k in a)
+
+
+def test_fusion_oracle_vs_reference():
+    """Fusion.memory_query / memory_update (model/fusion/fusion.py:357-410) through the shim."""
+    from oracle import fusion_oracle as FO
+    ns = ref_loader.load()
+    assert ns.fusion is not None, getattr(ns, "fusion_error", None)
+    ref = ns.fusion.Fusion(in_channels=24, fusion_channel=32, corr_cfg=dict(type="px2patch", patch_size=3))
+    sd = FO.random_fusion_params(3)
+    ref.load_state_dict(sd, strict=True)
+    ref.eval()
+    assert set(sd) == set(ref.state_dict())
+    for first in (True, False):
+        outputs, state = FO.synth_fusion_inputs(2, 64, 96, seed=9)
+        if first:
+            state = {}
+        o_ref = {k: v.clone() for k, v in outputs.items()}
+        s_ref = {k: [t.clone() for t in v] for k, v in state.items()}
+        with torch.no_grad():
+            ref.memory_query(o_ref, s_ref)
+            ref.memory_update(o_ref, s_ref)
+            o_or = FO.memory_query(sd, {k: v.clone() for k, v in outputs.items()}, state)
+            s_or = dict(state)
+            FO.memory_update(o_or, s_or)
+        keys = ["pred_disp", "left_feat"] + ([] if first else ["fusion_weights", "reset_weights"])
+        for k in keys:
+            torch.testing.assert_close(o_or[k], o_ref[k], rtol=1e-5, atol=1e-5)
+        for a, b in zip(s_or["memory"], s_ref["memory"]):
+            torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-5)
