@@ -83,6 +83,16 @@ def load():
     except Exception as e:  # pragma: no cover - informative only
         ns.fusion = None
         ns.fusion_error = e
+    for attr, mod in (("projective_ops", "model.motion.raft3d.projective_ops"),
+                      ("sampler_ops", "model.motion.raft3d.sampler_ops"),
+                      ("se3_field", "model.motion.raft3d.se3_field"),
+                      ("corr", "model.motion.raft3d.blocks.corr"),
+                      ("gru", "model.motion.raft3d.blocks.gru")):
+        try:
+            setattr(ns, attr, importlib.import_module(mod))
+        except Exception as e:  # pragma: no cover - informative only
+            setattr(ns, attr, None)
+            setattr(ns, attr + "_error", e)
     _loaded["ns"] = ns
     return ns
 
