@@ -5,7 +5,7 @@ There is no fallback: if the shared object is missing, importing the ops raises.
 """
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcodd_b200.so")
@@ -47,6 +47,17 @@ SIGNATURES = {
     "codd_fusion_forget_in": (c_int, [_FP, _FP, _FP, _FP, _FP, _FP, c_int, c_int, c_int, _FP, c_int, _FP, c_void_p]),
     "codd_fusion_blend": (c_int, [_FP, _FP, _FP, c_int, _FP, _FP, _FP, c_int, c_int, c_int, c_int, _FP, _FP, _FP,
                                   c_void_p]),
+    "codd_raft_motion_info": (c_int, [_FP, _FP, _FP, _FP, c_int, c_int, c_int, _FP, _FP, c_int, c_void_p]),
+    "codd_avgpool2_nhwc": (c_int, [_FP, c_int, c_int, c_int, c_int, c_int, _FP, c_int, c_void_p]),
+    "codd_corr_lookup": (c_int, [_FP, c_int, POINTER(c_void_p), POINTER(c_int), c_int, _FP, c_int, c_int, c_int, c_int,
+                                 c_int, c_int, _FP, c_int, c_void_p]),
+    "codd_se3_gn_step": (c_int, [_FP, _FP, c_int, _FP, c_int, _FP, c_int, _FP, _FP, c_int, c_int, c_int, c_int, c_float,
+                                 c_float, _FP, c_void_p]),
+    "codd_cvx_upsample": (c_int, [_FP, c_int, c_int, _FP, c_int, c_int, c_int, c_int, _FP, c_int, c_void_p]),
+    "codd_se3_upsample_flow": (c_int, [_FP, _FP, c_int, _FP, _FP, c_int, c_int, c_int, _FP, _FP, _FP, c_void_p]),
+    "codd_splat_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "codd_splat_warp": (c_int, [_FP, _FP, _FP, _FP, c_int, c_int, c_int, c_int, c_int, c_float, c_float, _FP, c_int, _FP,
+                                _FP, _FP, c_size_t, c_void_p]),
     "codd_nhwc_to_nchw": (c_int, [_FP, c_int, c_int, c_int, c_int, c_int, _FP, c_void_p]),
     "codd_nchw_to_nhwc": (c_int, [_FP, c_int, c_int, c_int, c_int, _FP, c_int, c_void_p]),
 }

@@ -414,3 +414,114 @@ def fusion_blend(pred_curr, pred_warp, r8, weight, bias, wf_lowres, ds=4):
         wf_lowres.data_ptr(), n, h, w, ds, fused.data_ptr(), wf.data_ptr(), wr.data_ptr(), _stream()))
     _lib.check(rc, "codd_fusion_blend")
     return fused, wf, wr
+
+
+# ----------------------------------------------------------------------------------------------
+# Motion / RAFT3D non-convolutional ops (K9-K12)
+# ----------------------------------------------------------------------------------------------
+def raft_motion_info(Ts, depth1, depth2_inv, intr):
+    """-> (coords1_xyz [N,h,w,3], motion_info [N,9,h,w] NHWC-backed, ld 12)."""
+    _require_cuda(Ts, depth1, depth2_inv, intr)
+    n, h, w = depth1.shape
+    Ts, depth1, depth2_inv, intr = Ts.contiguous(), depth1.contiguous(), depth2_inv.contiguous(), intr.contiguous()
+    xyz = torch.empty((n, h, w, 3), device=Ts.device)
+    info = empty_nhwc(n, 9, h, w, Ts.device, ld=12)
+    rc = _run("raft_motion_info", 4 * n * h * w * (7 + 2 + 3 + 9), lambda: _lib.load().codd_raft_motion_info(
+        Ts.data_ptr(), depth1.data_ptr(), depth2_inv.data_ptr(), intr.data_ptr(), n, h, w, xyz.data_ptr(),
+        info.data_ptr(), 12, _stream()))
+    _lib.check(rc, "codd_raft_motion_info")
+    return xyz, info
+
+
+def avgpool2(x):
+    _require_cuda(x)
+    n, c, h, w = x.shape
+    out = empty_nhwc(n, c, h // 2, w // 2, x.device)
+    rc = _run("avgpool2", 5 * n * c * h * w, lambda: _lib.load().codd_avgpool2_nhwc(
+        x.data_ptr(), ld_of(x), n, h, w, c, out.data_ptr(), c, _stream()))
+    _lib.check(rc, "codd_avgpool2_nhwc")
+    return out
+
+
+def corr_pyramid(fmap2, levels=4):
+    """fmap2 NHWC-backed -> list of pooled maps (level 0 = fmap2 itself)."""
+    pyr = [to_nhwc(fmap2)]
+    for _ in range(levels - 1):
+        pyr.append(avgpool2(pyr[-1]))
+    return pyr
+
+
+def corr_lookup(fmap1, pyramid, coords_xyz, radius=3):
+    """fmap1 [N,C,h,w] NHWC-backed, pyramid from corr_pyramid, coords_xyz [N,h,w,>=2] -> [N,L*(2r+1)^2,h,w] NHWC."""
+    _require_cuda(fmap1, coords_xyz)
+    n, c, h, w = fmap1.shape
+    levels = len(pyramid)
+    nch = levels * (2 * radius + 1) ** 2
+    out = empty_nhwc(n, nch, h, w, fmap1.device)
+    ptrs = (ctypes.c_void_p * levels)(*[p.data_ptr() for p in pyramid])
+    lds = (ctypes.c_int * levels)(*[ld_of(p) for p in pyramid])
+    coords_xyz = coords_xyz.contiguous()
+    rc = _run("corr_lookup", 4 * n * h * w * (c + nch), lambda: _lib.load().codd_corr_lookup(
+        fmap1.data_ptr(), ld_of(fmap1), ptrs, lds, levels, coords_xyz.data_ptr(), coords_xyz.shape[-1], n, h, w, c,
+        radius, out.data_ptr(), nch, _stream()))
+    _lib.check(rc, "codd_corr_lookup")
+    return out
+
+
+def se3_gn_step(Ts, ae, target, weight, depth, intr, radius=32, lm=1e-4, ep=10.0):
+    """Ts [N,h,w,7]; ae [N,32,h,w], target / weight [N,3,h,w] NHWC-backed -> new Ts."""
+    _require_cuda(Ts, ae, target, weight, depth, intr)
+    n, h, w = depth.shape
+    Ts, depth, intr = Ts.contiguous(), depth.contiguous(), intr.contiguous()
+    out = torch.empty_like(Ts)
+    rc = _run("se3_gn_step", 4 * n * h * w * (7 + 32 + 3 + 3 + 1 + 7), lambda: _lib.load().codd_se3_gn_step(
+        Ts.data_ptr(), ae.data_ptr(), ld_of(ae), target.data_ptr(), ld_of(target), weight.data_ptr(), ld_of(weight),
+        depth.data_ptr(), intr.data_ptr(), n, h, w, radius, lm, ep, out.data_ptr(), _stream()))
+    _lib.check(rc, "codd_se3_gn_step")
+    return out
+
+
+def cvx_upsample(data, mask):
+    """data [N,h,w,dim] contiguous, mask [N,576,h,w] NHWC-backed -> [N,8h,8w,dim]."""
+    _require_cuda(data, mask)
+    n, h, w, dim = data.shape
+    data = data.contiguous()
+    out = torch.empty((n, 8 * h, 8 * w, dim), device=data.device)
+    rc = _run("cvx_upsample", 4 * n * h * w * (dim + 576 + 64 * dim), lambda: _lib.load().codd_cvx_upsample(
+        data.data_ptr(), dim, dim, mask.data_ptr(), ld_of(mask), n, h, w, out.data_ptr(), dim, _stream()))
+    _lib.check(rc, "codd_cvx_upsample")
+    return out
+
+
+def se3_upsample_flow(Ts, mask, depth, intr):
+    """-> (Ts_up [N,8h,8w,7], flow [N,8h,8w,3])."""
+    _require_cuda(Ts, mask, depth, intr)
+    n, h, w, _ = Ts.shape
+    Ts, depth, intr = Ts.contiguous(), depth.contiguous(), intr.contiguous()
+    ws = torch.empty((n, h, w, 6), device=Ts.device)
+    up = torch.empty((n, 8 * h, 8 * w, 7), device=Ts.device)
+    flow = torch.empty((n, 8 * h, 8 * w, 3), device=Ts.device)
+    rc = _run("se3_upsample_flow", 4 * n * h * w * (7 + 576 + 64 * 11), lambda: _lib.load().codd_se3_upsample_flow(
+        Ts.data_ptr(), mask.data_ptr(), ld_of(mask), depth.data_ptr(), intr.data_ptr(), n, h, w, ws.data_ptr(),
+        up.data_ptr(), flow.data_ptr(), _stream()))
+    _lib.check(rc, "codd_se3_upsample_flow")
+    return up, flow
+
+
+def splat_warp(Ts, depth, intr, feat, radius, bf=0.0, want_disp=False):
+    """feat [N,C,h,w] NHWC-backed -> (warped [N,C,h,w] NHWC, zbuf [N,1,h,w], disp [N,1,h,w] | None)."""
+    _require_cuda(Ts, depth, intr, feat)
+    n, c, h, w = feat.shape
+    Ts, depth, intr = Ts.contiguous(), depth.contiguous(), intr.contiguous()
+    out = empty_nhwc(n, c, h, w, feat.device)
+    zbuf = torch.empty((n, 1, h, w), device=feat.device)
+    disp = torch.empty((n, 1, h, w), device=feat.device) if want_disp else None
+    nbytes = _lib.load().codd_splat_workspace_bytes(n, h, w)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=feat.device)
+    LAUNCHES[0] += 2
+    rc = _run("splat_warp", 4 * n * h * w * (7 + 1 + 2 * c + 2), lambda: _lib.load().codd_splat_warp(
+        Ts.data_ptr(), depth.data_ptr(), intr.data_ptr(), feat.data_ptr(), ld_of(feat), c, n, h, w, float(radius),
+        float(bf), out.data_ptr(), c, zbuf.data_ptr(), None if disp is None else disp.data_ptr(), ws.data_ptr(), nbytes,
+        _stream()))
+    _lib.check(rc, "codd_splat_warp")
+    return out, zbuf, disp

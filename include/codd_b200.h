@@ -208,6 +208,42 @@ CODD_API int codd_fusion_blend(const float* pred_curr, const float* pred_warp, c
                                int ds, float* fused, float* wf, float* wr, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Motion / RAFT3D non-convolutional ops (reference: model/motion/motion.py:82-130,154-207;
+ * raft3d/projective_ops.py:11-68; sampler_ops.py:9-28; se3_field.py:150-192; blocks/corr.py:28-62).
+ * SE3 elements are 7 floats (tx,ty,tz,qx,qy,qz,qw).  The lietorch / lietorch_extras / pytorch3d
+ * semantics are restated from their published algorithms — parity unpinned.
+ * ------------------------------------------------------------------------------------------ */
+/* One iteration's geometry: xyz[n,h,w,3] = project(Ts * inv_project(depth1)); info[n,h,w,0:9] =
+ * clamp([flow(2), 10*log(Ts)(6), 10*(sample(depth2_inv, xy) - 1/Z)(1)], +-50).  intr [n,4] device. */
+CODD_API int codd_raft_motion_info(const float* Ts, const float* depth1, const float* depth2_inv, const float* intr,
+                                   int n, int h, int w, float* xyz, float* info, int ldi, void* stream);
+/* 2x2 average pooling of an NHWC map (correlation pyramid = correlation with pooled fmap2). */
+CODD_API int codd_avgpool2_nhwc(const float* in, int ldi, int n, int h, int w, int c, float* out, int ldo, void* stream);
+/* Windowed bilinear lookup into the (never materialised) all-pairs correlation pyramid:
+ * out[n,y,x, l*(2r+1)^2 + i*(2r+1) + j] = bilinear_{(coords/2^l) + (i-r, j-r)} <f1(y,x)/4, pool_l(f2)/4>. */
+CODD_API int codd_corr_lookup(const float* fmap1, int ld1, const float* const* fmap2_pyramid, const int* ld2, int levels,
+                              const float* coords, int ldc, int n, int h, int w, int c, int radius, float* out, int ldo,
+                              void* stream);
+/* Dense Gauss-Newton step: per pixel, affinity-weighted 6x6 normal equations over a (2*radius+1)^2
+ * window, damping (lm*H + ep) on the diagonal, Cholesky solve, Ts_out = exp(dx) * Ts. */
+CODD_API int codd_se3_gn_step(const float* Ts, const float* ae, int lda, const float* target, int ldt,
+                              const float* weight, int ldw, const float* depth, const float* intr, int n, int h, int w,
+                              int radius, float lm, float ep, float* Ts_out, void* stream);
+/* Convex (softmax-9) x8 up-sampling: data [n,h,w,dim<=8], mask [n,h,w,576] NHWC -> out [n,8h,8w,dim]. */
+CODD_API int codd_cvx_upsample(const float* data, int ldd, int dim, const float* mask, int ldm, int n, int h, int w,
+                               float* out, int ldo, void* stream);
+/* Ts_up [n,8h,8w,7] = exp(cvx_upsample(log Ts)); flow [n,8h,8w,3] = induced_flow(Ts_up, depth, intr).
+ * twist_ws: workspace [n,h,w,6]. */
+CODD_API int codd_se3_upsample_flow(const float* Ts, const float* mask, int ldm, const float* depth, const float* intr,
+                                    int n, int h, int w, float* twist_ws, float* Ts_up, float* flow, void* stream);
+/* K9 splat warp: out [n,h,w,c] (NHWC, ldo) = z-sorted top-8 alpha compositing of feat [n,h,w,c] (ldf) moved
+ * by Ts; zbuf / disp optional [n,h,w] (disp = bf/(z+1e-5), 0 where > w). workspace: codd_splat_workspace_bytes. */
+CODD_API size_t codd_splat_workspace_bytes(int n, int h, int w);
+CODD_API int codd_splat_warp(const float* Ts, const float* depth, const float* intr, const float* feat, int ldf, int c,
+                             int n, int h, int w, float radius, float bf, float* out, int ldo, float* zbuf, float* disp,
+                             void* workspace, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * layout helpers at the module boundary
  * ------------------------------------------------------------------------------------------ */
 /* NHWC [n,h,w,c] (pixel stride ldi) -> NCHW contiguous */
