@@ -21,6 +21,7 @@ __device__ __forceinline__ float codd_act(float v, int act, int ch) {
     // compiles to an indirect jump per element and dominated the conv epilogues.)
     if (act >= CODD_ACT_SIGMOID) {
         if (act == CODD_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
+        if (act == CODD_ACT_TANH) return tanhf(v);
         const float sp = v > 20.f ? v : log1pf(expf(v));   // mish: x * tanh(softplus(x)), torch threshold 20
         return v * tanhf(sp);
     }

@@ -25,6 +25,7 @@ struct ConvP {
     const float* res;
     float* out;
     int N, H, W, C0, ld0, C1, ld1, Cout, ldo, ph, pw, Ho, Wo, act, ldr, res_bcast, res_after;
+    int wld;         // row stride of the packed weight (= total Cout; Cout above may be one chunk of it)
     int tilesX, tilesY;
     int vec0, vec1;  // 128-bit loads allowed on in0 / in1
 };
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(256, 2) conv_nhwc_kernel(ConvP p) {
             const int t = idx / COP;
             const int ci = t % CK, tap = t / CK;
             float v = 0.f;
-            if (co < p.Cout && c0 + ci < Cin) v = __ldg(p.w + ((size_t)tap * Cin + c0 + ci) * p.Cout + co);
+            if (co < p.Cout && c0 + ci < Cin) v = __ldg(p.w + ((size_t)tap * Cin + c0 + ci) * p.wld + co);
             s_w[idx] = v;
         }
         __syncthreads();
@@ -241,7 +242,7 @@ __global__ void __launch_bounds__(256) pointwise_kernel(ConvP p, size_t npix) {
     const int Cin = p.C0 + p.C1;
     for (int i = threadIdx.x; i < Cin * CO; i += blockDim.x) {
         const int co = i % CO, ci = i / CO;
-        s_w[i] = co < p.Cout ? __ldg(p.w + (size_t)ci * p.Cout + co) : 0.f;
+        s_w[i] = co < p.Cout ? __ldg(p.w + (size_t)ci * p.wld + co) : 0.f;
     }
     __syncthreads();
     const size_t base = (size_t)blockIdx.x * (blockDim.x * PX_T) + threadIdx.x;
@@ -476,7 +477,8 @@ __global__ void __launch_bounds__(128) deconv2x2_kernel(const float* __restrict_
 // reads along the channel-contiguous side, coalesced 128-byte row writes on the planar side.
 constexpr int TR_PIX = 128;
 __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const float* __restrict__ in, int ldi, int hw, int c,
-                                                           float* __restrict__ out) {
+                                                           int ctot, int c0, float* __restrict__ out) {
+    in += c0;   // this launch moves channels [c0, c0 + c) of ctot
     extern __shared__ float4 smem4[];
     float* tile = reinterpret_cast<float*>(smem4);   // [c][TR_PIX + 1]
     const int s = blockIdx.y;
@@ -502,7 +504,7 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const float* __restri
     __syncthreads();
     for (int idx = threadIdx.x; idx < c * TR_PIX; idx += blockDim.x) {
         const int ch = idx / TR_PIX, pp = idx - ch * TR_PIX;
-        if (pp < np) out[((size_t)s * c + ch) * hw + p0 + pp] = tile[ch * (TR_PIX + 1) + pp];
+        if (pp < np) out[((size_t)s * ctot + c0 + ch) * hw + p0 + pp] = tile[ch * (TR_PIX + 1) + pp];
     }
 }
 
@@ -519,6 +521,38 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, int c, int hw,
 
 }  // namespace
 
+namespace {
+// geometry dispatch for one launch (p.Cout <= 64)
+int conv_dispatch(const ConvP& p, const codd_conv_desc* d, cudaStream_t s) {
+    const int kh = d->kh, kw = d->kw, sh = d->sh, sw = d->sw, dil = d->dil;
+    if (kh == 1 && kw == 1 && sh == 1 && sw == 1 && d->ph == 0 && d->pw == 0 && d->ho == d->h && d->wo == d->w) {
+        const bool vec_ok = p.vec0 && (d->c0 % 4 == 0) && (p.C1 == 0 || (p.vec1 && d->c1 % 4 == 0)) &&
+                            codd_aligned16(p.out) && (d->ldo % 4 == 0) && (d->c0 + p.C1) * 32 * 4 <= 48 * 1024;
+        if (vec_ok && p.Cout <= 16) return launch_pointwise<16, 4>(p, s);
+        if (vec_ok && p.Cout <= 24) return launch_pointwise<24, 2>(p, s);
+        if (vec_ok && p.Cout <= 32) return launch_pointwise<32, 2>(p, s);
+    }
+    if (kh == 1 && kw == 1 && sh == 1 && sw == 1) return dispatch_cout<1, 1, 1, 1, 1, true>(p, s);
+    if (kh == 1 && kw == 1 && sh == 2 && sw == 2) return dispatch_cout<1, 1, 2, 2, 1, false>(p, s);
+    if (kh == 3 && kw == 3 && sh == 1 && sw == 1 && dil == 1) return dispatch_cout<3, 3, 1, 1, 1, true>(p, s);
+    if (kh == 3 && kw == 3 && sh == 1 && sw == 1 && dil == 3) return dispatch_cout<3, 3, 1, 1, 3, false>(p, s);
+    if (kh == 3 && kw == 3 && sh == 1 && sw == 1 && dil == 4) return dispatch_cout<3, 3, 1, 1, 4, false>(p, s);
+    if (kh == 3 && kw == 3 && sh == 2 && sw == 2 && dil == 1) return dispatch_cout<3, 3, 2, 2, 1, false>(p, s);
+    if (kh == 4 && kw == 4 && sh == 2 && sw == 2 && dil == 1) {
+        // the stride-2 stage is wide (66 input columns); split the output channels over warps so that
+        // a full 256-thread CTA shares it
+        if (p.Cout <= 16) return launch_conv<4, 4, 2, 2, 1, 8>(p, 4, 2, s);
+        if (p.Cout <= 24) return launch_conv<4, 4, 2, 2, 1, 8>(p, 2, 3, s);
+        return dispatch_cout<4, 4, 2, 2, 1, false>(p, s);
+    }
+    if (kh == 4 && kw == 4 && sh == 4 && sw == 4 && dil == 1) return dispatch_cout<4, 4, 4, 4, 1, false>(p, s);
+    if (kh == 4 && kw == 4 && sh == 4 && sw == 1 && dil == 1) return dispatch_cout<4, 4, 4, 1, 1, false>(p, s);
+    if (kh == 7 && kw == 7 && sh == 1 && sw == 1 && dil == 1) return dispatch_cout<7, 7, 1, 1, 1, false>(p, s);
+    if (kh == 7 && kw == 7 && sh == 2 && sw == 2 && dil == 1) return dispatch_cout<7, 7, 2, 2, 1, false>(p, s);
+    return CODD_E_UNSUPPORTED;
+}
+}  // namespace
+
 extern "C" int codd_conv2d_nhwc(const codd_conv_desc* d, const float* in0, const float* in1, const float* weight,
                                 const float* bias, const float* residual, float* out, void* stream) {
     if (!d || !in0 || !weight || !out) return CODD_E_BADARG;
@@ -532,42 +566,30 @@ extern "C" int codd_conv2d_nhwc(const codd_conv_desc* d, const float* in0, const
     ConvP p;
     p.in0 = in0;
     p.in1 = d->c1 > 0 ? in1 : nullptr;
-    p.w = weight;
-    p.bias = bias;
-    p.res = residual;
-    p.out = out;
     p.N = d->n; p.H = d->h; p.W = d->w;
     p.C0 = d->c0; p.ld0 = d->ld0;
     p.C1 = d->c1 > 0 ? d->c1 : 0; p.ld1 = d->ld1;
-    p.Cout = d->cout; p.ldo = d->ldo;
+    p.ldo = d->ldo; p.wld = d->cout;
     p.ph = d->ph; p.pw = d->pw; p.Ho = d->ho; p.Wo = d->wo;
-    p.act = d->act; p.ldr = d->ldr; p.res_bcast = d->res_bcast; p.res_after = d->res_after_act;
+    p.ldr = d->ldr; p.res_bcast = d->res_bcast; p.res_after = d->res_after_act;
     p.tilesX = p.tilesY = 0;
     p.vec0 = codd_aligned16(in0) && (d->ld0 % 4 == 0);
     p.vec1 = p.in1 && codd_aligned16(in1) && (d->ld1 % 4 == 0) && (d->c0 % 4 == 0);
     cudaStream_t s = (cudaStream_t)stream;
-    const int kh = d->kh, kw = d->kw, sh = d->sh, sw = d->sw, dil = d->dil;
-    if (kh == 1 && kw == 1 && sh == 1 && sw == 1 && d->ph == 0 && d->pw == 0 && d->ho == d->h && d->wo == d->w) {
-        const bool vec_ok = p.vec0 && (d->c0 % 4 == 0) && (p.C1 == 0 || (p.vec1 && d->c1 % 4 == 0)) &&
-                            codd_aligned16(out) && (d->ldo % 4 == 0) && (d->c0 + p.C1) * 32 * 4 <= 48 * 1024;
-        if (vec_ok && d->cout <= 16) return launch_pointwise<16, 4>(p, s);
-        if (vec_ok && d->cout <= 24) return launch_pointwise<24, 2>(p, s);
-        if (vec_ok && d->cout <= 32) return launch_pointwise<32, 2>(p, s);
+    // wide layers (the RAFT3D encoders / update block, Cout up to 1024) run as 64-filter chunks:
+    // each launch sees a column slice of the packed weight (row stride wld) and of bias / residual / out
+    constexpr int CHUNK = 64;
+    for (int co0 = 0; co0 < d->cout; co0 += CHUNK) {
+        p.Cout = d->cout - co0 < CHUNK ? d->cout - co0 : CHUNK;
+        p.w = weight + co0;
+        p.bias = bias ? bias + co0 : nullptr;
+        p.res = residual ? (d->res_bcast ? residual : residual + co0) : nullptr;
+        p.out = out + co0;
+        p.act = (co0 > 0 && d->act == CODD_ACT_RELU_CH0) ? CODD_ACT_NONE : d->act;
+        const int rc = conv_dispatch(p, d, s);
+        if (rc != 0) return rc;
     }
-    if (kh == 1 && kw == 1 && sh == 1 && sw == 1) return dispatch_cout<1, 1, 1, 1, 1, true>(p, s);
-    if (kh == 3 && kw == 3 && sh == 1 && sw == 1 && dil == 1) return dispatch_cout<3, 3, 1, 1, 1, true>(p, s);
-    if (kh == 3 && kw == 3 && sh == 1 && sw == 1 && dil == 3) return dispatch_cout<3, 3, 1, 1, 3, false>(p, s);
-    if (kh == 4 && kw == 4 && sh == 2 && sw == 2 && dil == 1) {
-        // the stride-2 stage is wide (66 input columns); split the output channels over warps so that
-        // a full 256-thread CTA shares it
-        if (d->cout <= 16) return launch_conv<4, 4, 2, 2, 1, 8>(p, 4, 2, s);
-        if (d->cout <= 24) return launch_conv<4, 4, 2, 2, 1, 8>(p, 2, 3, s);
-        return dispatch_cout<4, 4, 2, 2, 1, false>(p, s);
-    }
-    if (kh == 4 && kw == 4 && sh == 4 && sw == 4 && dil == 1) return dispatch_cout<4, 4, 4, 4, 1, false>(p, s);
-    if (kh == 4 && kw == 4 && sh == 4 && sw == 1 && dil == 1) return dispatch_cout<4, 4, 4, 1, 1, false>(p, s);
-    if (kh == 7 && kw == 7 && sh == 1 && sw == 1 && dil == 1) return dispatch_cout<7, 7, 1, 1, 1, false>(p, s);
-    return CODD_E_UNSUPPORTED;
+    return 0;
 }
 
 extern "C" int codd_conv3x3_image(const float* left, const float* right, int n, int h, int w, const float* weight,
@@ -606,18 +628,21 @@ extern "C" int codd_deconv2x2_nhwc(const float* in, int ldi, int n, int h, int w
 
 extern "C" int codd_nhwc_to_nchw(const float* in, int ldi, int n, int h, int w, int c, float* out, void* stream) {
     if (!in || !out || n <= 0 || h <= 0 || w <= 0 || c <= 0 || ldi < c) return CODD_E_BADARG;
-    if (c > 384) return CODD_E_UNSUPPORTED;
     const int hw = h * w;
+    constexpr int CCH = 256;   // channels per launch (shared tile = CCH x 129 floats)
     dim3 grid((unsigned)codd_ceil_div(hw, TR_PIX), (unsigned)n);
-    const size_t smem = (size_t)c * (TR_PIX + 1) * sizeof(float);
-    static size_t configured = 48 * 1024;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(nhwc_to_nchw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        configured = smem;
+    for (int c0 = 0; c0 < c; c0 += CCH) {
+        const int cc = c - c0 < CCH ? c - c0 : CCH;
+        const size_t smem = (size_t)cc * (TR_PIX + 1) * sizeof(float);
+        static size_t configured = 48 * 1024;
+        if (smem > configured) {
+            cudaError_t e = cudaFuncSetAttribute(nhwc_to_nchw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            configured = smem;
+        }
+        nhwc_to_nchw_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(in, ldi, hw, cc, c, c0, out);
+        CODD_RETURN_IF_CUDA_ERROR();
     }
-    nhwc_to_nchw_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(in, ldi, hw, c, out);
-    CODD_RETURN_IF_CUDA_ERROR();
     return 0;
 }
 

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libcodd_b200.so")
 
 # error codes / activation codes (mirror include/codd_b200.h)
 E_BADARG, E_SHAPE, E_UNSUPPORTED, E_ALIGN = -1, -2, -3, -4
-ACT_NONE, ACT_LEAKY, ACT_RELU, ACT_RELU_CH0, ACT_SIGMOID, ACT_MISH = 0, 1, 2, 3, 4, 5
+ACT_NONE, ACT_LEAKY, ACT_RELU, ACT_RELU_CH0, ACT_SIGMOID, ACT_MISH, ACT_TANH = 0, 1, 2, 3, 4, 5, 6
 
 
 class ConvDesc(Structure):
@@ -58,6 +58,15 @@ SIGNATURES = {
     "codd_splat_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "codd_splat_warp": (c_int, [_FP, _FP, _FP, _FP, c_int, c_int, c_int, c_int, c_int, c_float, c_float, _FP, c_int, _FP,
                                 _FP, _FP, c_size_t, c_void_p]),
+    "codd_instance_norm_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "codd_instance_norm_nhwc": (c_int, [_FP, c_int, c_int, c_int, c_int, c_int, c_float, c_int, _FP, c_int, _FP, c_int,
+                                        _FP, c_size_t, c_void_p]),
+    "codd_resize_bilinear_nhwc": (c_int, [_FP, c_int, c_int, c_int, c_int, c_int, _FP, c_int, _FP, c_int, c_int, c_int,
+                                          c_int, c_int, c_void_p]),
+    "codd_eltwise_nhwc": (c_int, [c_int, c_int, _FP, c_int, _FP, c_int, _FP, c_int, _FP, c_int, c_size_t, c_int,
+                                  c_void_p]),
+    "codd_disp_to_depth": (c_int, [_FP, c_size_t, c_float, _FP, c_void_p]),
+    "codd_subsample_nhwc": (c_int, [_FP, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _FP, c_int, c_void_p]),
     "codd_nhwc_to_nchw": (c_int, [_FP, c_int, c_int, c_int, c_int, c_int, _FP, c_void_p]),
     "codd_nchw_to_nhwc": (c_int, [_FP, c_int, c_int, c_int, c_int, _FP, c_int, c_void_p]),
 }

@@ -10,7 +10,7 @@ import ctypes
 import torch
 
 from . import lib as _lib
-from .lib import ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_RELU_CH0, ConvDesc  # noqa: F401
+from .lib import ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_RELU_CH0, ACT_SIGMOID, ACT_TANH, ConvDesc  # noqa: F401
 
 LAUNCHES = [0]  # kernels launched through this module (bench.py reports it as gpu_launches)
 PROFILE = None   # when a list: (tag, algorithmic bytes, start event, end event) per launch
@@ -107,6 +107,21 @@ def to_nhwc(t):
               lambda: _lib.load().codd_nchw_to_nhwc(t.data_ptr(), n, c, h, w, out.data_ptr(), c, _stream()))
     _lib.check(rc, "codd_nchw_to_nhwc")
     return out
+
+
+def copy_to_nhwc(src, out):
+    """Copy any float32 CUDA logical-NCHW tensor into an NHWC-backed destination (e.g. a channel slice)."""
+    _require_cuda(src, out)
+    try:
+        ld_of(src)
+    except _lib.CoddError:
+        src = src.contiguous()
+        n, c, h, w = src.shape
+        rc = _run("nchw_to_nhwc", 8 * src.numel(), lambda: _lib.load().codd_nchw_to_nhwc(
+            src.data_ptr(), n, c, h, w, out.data_ptr(), ld_of(out), _stream()))
+        _lib.check(rc, "codd_nchw_to_nhwc")
+        return out
+    return eltwise(0, src, out=out)
 
 
 def to_nchw(t):
@@ -525,3 +540,81 @@ def splat_warp(Ts, depth, intr, feat, radius, bf=0.0, want_disp=False):
         _stream()))
     _lib.check(rc, "codd_splat_warp")
     return out, zbuf, disp
+
+
+# ----------------------------------------------------------------------------------------------
+# RAFT3D network glue (instance norm, bilinear resize, element-wise, depth conversion, sub-sampling)
+# ----------------------------------------------------------------------------------------------
+def instance_norm(x, relu=True, residual=None, eps=1e-5):
+    """InstanceNorm2d(affine=False) (+ReLU); with ``residual``: relu(residual + y) (ResidualBlock tail)."""
+    _require_cuda(x, residual)
+    n, c, h, w = x.shape
+    out = empty_nhwc(n, c, h, w, x.device)
+    nb = _lib.load().codd_instance_norm_workspace_bytes(n, c)
+    ws = torch.empty(nb, dtype=torch.uint8, device=x.device)
+    LAUNCHES[0] += 1
+    rc = _run("instance_norm", 4 * x.numel() * (3 + (0 if residual is None else 1)),
+              lambda: _lib.load().codd_instance_norm_nhwc(
+                  x.data_ptr(), ld_of(x), n, h, w, c, eps, 1 if relu else 0,
+                  None if residual is None else residual.data_ptr(), 0 if residual is None else ld_of(residual),
+                  out.data_ptr(), c, ws.data_ptr(), nb, _stream()))
+    _lib.check(rc, "codd_instance_norm_nhwc")
+    return out
+
+
+def resize_bilinear(x, size, align_corners, base=None, relu=False, out=None):
+    """out = relu?(base + F.interpolate(x, size, mode='bilinear', align_corners))."""
+    _require_cuda(x, base, out)
+    n, c, h, w = x.shape
+    ho, wo = size
+    if out is None:
+        out = empty_nhwc(n, c, ho, wo, x.device)
+    rc = _run("resize_bilinear", 4 * (x.numel() + n * c * ho * wo * (1 if base is None else 2)),
+              lambda: _lib.load().codd_resize_bilinear_nhwc(
+                  x.data_ptr(), ld_of(x), n, h, w, c, None if base is None else base.data_ptr(),
+                  0 if base is None else ld_of(base), out.data_ptr(), ld_of(out), ho, wo, 1 if align_corners else 0,
+                  1 if relu else 0, _stream()))
+    _lib.check(rc, "codd_resize_bilinear_nhwc")
+    return out
+
+
+EW_ACT, EW_MUL, EW_GRU, EW_ADD_ACT, EW_RECIP = 0, 1, 2, 3, 4
+
+
+def eltwise(op, a, b=None, c=None, act=ACT_NONE, out=None):
+    """Element-wise glue on NHWC-backed logical-NCHW tensors (see codd_eltwise_nhwc)."""
+    _require_cuda(a, b, c, out)
+    n, ch, h, w = a.shape
+    if out is None:
+        out = empty_nhwc(n, ch, h, w, a.device)
+    nin = 1 + (b is not None) + (c is not None)
+    rc = _run(f"eltwise_op{op}", 4 * a.numel() * (nin + 1), lambda: _lib.load().codd_eltwise_nhwc(
+        op, act, a.data_ptr(), ld_of(a), None if b is None else b.data_ptr(), 0 if b is None else ld_of(b),
+        None if c is None else c.data_ptr(), 0 if c is None else ld_of(c), out.data_ptr(), ld_of(out), n * h * w, ch,
+        _stream()))
+    _lib.check(rc, "codd_eltwise_nhwc")
+    return out
+
+
+def disp_to_depth(disp, bf):
+    """clip(bf / (disp + 1e-5), 0, bf) on a contiguous tensor of any shape."""
+    _require_cuda(disp)
+    disp = disp.contiguous()
+    out = torch.empty_like(disp)
+    rc = _run("disp_to_depth", 8 * disp.numel(), lambda: _lib.load().codd_disp_to_depth(
+        disp.data_ptr(), disp.numel(), float(bf), out.data_ptr(), _stream()))
+    _lib.check(rc, "codd_disp_to_depth")
+    return out
+
+
+def subsample(x, offset, stride, recip=False):
+    """x [N,H,W,C] contiguous (channels last) -> x[:, offset::stride, offset::stride, :] (optionally 1/x)."""
+    _require_cuda(x)
+    x = x.contiguous()
+    n, h, w, c = x.shape
+    ho, wo = (h - offset + stride - 1) // stride, (w - offset + stride - 1) // stride
+    out = torch.empty((n, ho, wo, c), device=x.device)
+    rc = _run("subsample", 8 * out.numel(), lambda: _lib.load().codd_subsample_nhwc(
+        x.data_ptr(), c, n, h, w, c, offset, stride, 1 if recip else 0, out.data_ptr(), c, _stream()))
+    _lib.check(rc, "codd_subsample_nhwc")
+    return out

@@ -47,6 +47,7 @@ extern "C" {
 #define CODD_ACT_RELU_CH0 3   /* ReLU on output channel 0 only (disparity >= 0) */
 #define CODD_ACT_SIGMOID 4
 #define CODD_ACT_MISH 5
+#define CODD_ACT_TANH 6       /* ConvGRU candidate state (raft3d/blocks/gru.py:31) */
 
 CODD_API int codd_version(void);
 CODD_API const char* codd_error_string(int code);
@@ -242,6 +243,34 @@ CODD_API size_t codd_splat_workspace_bytes(int n, int h, int w);
 CODD_API int codd_splat_warp(const float* Ts, const float* depth, const float* intr, const float* feat, int ldf, int c,
                              int n, int h, int w, float radius, float bf, float* out, int ldo, float* zbuf, float* disp,
                              void* workspace, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * RAFT3D network glue (reference: model/motion/raft3d/blocks/extractor.py:28-55,124-190 instance
+ * norm; raft3d.py:125-137 ResizeConcatConv + mmseg HRModule fuse layers; blocks/gru.py:30-34;
+ * raft3d.py:183-186,242; motion.py:154-165,196-197).  The convolutions themselves go through
+ * codd_conv2d_nhwc (any Cout: wide layers run as 64-filter chunks).
+ * ------------------------------------------------------------------------------------------ */
+/* InstanceNorm2d (affine=False, biased variance): y = (x - mean) / sqrt(var + eps) per (sample, channel);
+ * relu != 0: y = max(y, 0); residual != NULL: out = max(residual + y, 0) (ResidualBlock tail).
+ * workspace: codd_instance_norm_workspace_bytes(n, c) bytes (zeroed by the call).  c <= 256. */
+CODD_API size_t codd_instance_norm_workspace_bytes(int n, int c);
+CODD_API int codd_instance_norm_nhwc(const float* in, int ldi, int n, int h, int w, int c, float eps, int relu,
+                                     const float* residual, int ldr, float* out, int ldo, void* workspace,
+                                     size_t ws_bytes, void* stream);
+/* out[n,ho,wo,c] = relu?(base + bilinear(in[n,h,w,c]))  (torch F.interpolate semantics; base may be NULL) */
+CODD_API int codd_resize_bilinear_nhwc(const float* in, int ldi, int n, int h, int w, int c, const float* base,
+                                       int ldb, float* out, int ldo, int ho, int wo, int align_corners, int relu,
+                                       void* stream);
+/* element-wise over npix pixels x channels:  op 0: act(a)   1: a*b   2: (1-a)*b + a*c (GRU state update)
+ *                                            3: act(a+b)    4: 1/a */
+CODD_API int codd_eltwise_nhwc(int op, int act, const float* a, int lda, const float* b, int ldb, const float* c,
+                               int ldc, float* out, int ldo, size_t npix, int channels, void* stream);
+/* depth = clip(bf / (disp + 1e-5), 0, bf)   (motion.py:157-165) */
+CODD_API int codd_disp_to_depth(const float* disp, size_t count, float bf, float* depth, void* stream);
+/* out[n, i, j, :] = in[n, offset + i*stride, offset + j*stride, :]  (recip != 0: reciprocal), e.g. the 1/8 and
+ * 1/4 sampling of depth maps and SE3 fields (raft3d.py:218-219; motion.py:196-197) */
+CODD_API int codd_subsample_nhwc(const float* in, int ldi, int n, int h, int w, int c, int offset, int stride,
+                                 int recip, float* out, int ldo, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * layout helpers at the module boundary
