@@ -33,9 +33,20 @@
 namespace {
 
 constexpr int TC_TW = 128;          // output columns per tile (= MMA M)
-constexpr int TC_R = 2;             // output rows per tile
-constexpr int TC_TWP = TC_TW + 2;   // staged columns
-constexpr int TC_TROWS = TC_R + 2;  // staged rows
+// Tile geometry per dilation.  DIL = 1: 2 output rows per tile, one 4-D TMA box of (2+2) x (128+2)
+// pixels.  DIL = 3 (the dilated resblocks of tile_update4_1 / tile_update5, propagation.py:258-280):
+// 1 output row per tile, the three input rows y-3, y, y+3 arrive as three one-row TMA boxes of 128+6
+// pixels; the staged row pitch is padded to a multiple of 8 pixels so that every row starts on a
+// 1024-byte swizzle-atom boundary.
+template <int DIL>
+struct TcGeo {
+    static constexpr int R = (DIL == 1) ? 2 : 1;              // output rows per tile
+    static constexpr int TROWS = (DIL == 1) ? 4 : 3;          // staged rows
+    static constexpr int BOXW = TC_TW + 2 * DIL;              // staged columns delivered by TMA
+    static constexpr int TWP = (DIL == 1) ? BOXW : ((BOXW + 7) & ~7);   // staged row pitch (pixels)
+    static constexpr int NLOADS = (DIL == 1) ? 1 : 3;         // TMA boxes per tile
+    static constexpr int BOXROWS = (DIL == 1) ? 4 : 1;
+};
 // warp roles (the SM's issue arbiter favours HIGH warp ids, and waiting warps poll their mbarrier,
 // so the latency-critical single-thread roles get the highest ids and the bulk workers the lowest):
 //   0-7  in-place hi/lo split of the stage,  8-11 epilogue (TMEM lane quarter = warp % 4),
@@ -164,15 +175,16 @@ __device__ __forceinline__ float tf32_lo(float x, int rna) {
 // One pass (9 taps x KC/8 k-steps) of one 128-pixel row: fully unrolled, every operand descriptor is
 // the stage / weight base descriptor plus a compile-time constant (>> 4) — a single thread issues
 // an MMA every few instructions.  FIRST: the very first MMA overwrites the accumulator.
-template <int KC, int NP, bool FIRST>
+template <int KC, int NP, bool FIRST, int DIL>
 __device__ __forceinline__ void tc_issue_pass(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+    constexpr int TC_TWP = TcGeo<DIL>::TWP;
     constexpr uint32_t ROWB = KC * 4;
     constexpr uint32_t B_TAP = 2 * NP * ROWB;   // per tap: NP rows of w_hi followed by NP rows of w_lo
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
         for (int k = 0; k < KC / 8; ++k) {
-            const uint32_t aoff = (uint32_t)((tap / 3) * TC_TWP + (tap % 3)) * ROWB + k * 32;
+            const uint32_t aoff = (uint32_t)((tap / 3) * TC_TWP + (tap % 3) * DIL) * ROWB + k * 32;
             const uint32_t boff = (uint32_t)tap * B_TAP + k * 32;
             if (FIRST && tap == 0 && k == 0)
                 tc_mma_tf32<false>(d_tmem, a_desc + (aoff >> 4), b_desc + (boff >> 4), idesc);
@@ -184,12 +196,14 @@ __device__ __forceinline__ void tc_issue_pass(uint32_t d_tmem, uint64_t a_desc, 
 
 // NBUF stage buffers, NACC accumulator buffers (x TC_R rows x NP TMEM columns), LAG = how many tiles
 // pass 3 trails passes 1-2 (LAG < NBUF, NACC >= LAG + 2).
-template <int KC, int NP, int NBUF, int NACC, int LAG>
+template <int KC, int NP, int NBUF, int NACC, int LAG, int DIL>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcP p) {
     static_assert(LAG >= 1 && LAG < NBUF && NACC >= LAG + 2, "pipeline depths");
+    constexpr int TC_R = TcGeo<DIL>::R, TC_TWP = TcGeo<DIL>::TWP, TC_TROWS = TcGeo<DIL>::TROWS;
+    constexpr uint32_t BOX_BYTES = TcGeo<DIL>::BOXROWS * TcGeo<DIL>::BOXW * KC * 4;   // bytes of one TMA box
     constexpr uint32_t TMEM_COLS = (NACC * TC_R * 2 * NP <= 128) ? 128u : (NACC * TC_R * 2 * NP <= 256) ? 256u : 512u;
     constexpr uint32_t ROWB = KC * 4;
-    constexpr uint32_t A_BYTES = TC_TROWS * TC_TWP * ROWB;                 // bytes delivered by one TMA box
+    constexpr uint32_t A_BYTES = TC_TROWS * TC_TWP * ROWB;                 // bytes of one stage (incl. row padding)
     constexpr uint32_t A_STRIDE = (A_BYTES + 1023u) & ~1023u;
     constexpr uint32_t B_TAP = 2 * NP * ROWB;
     // instruction descriptors: N = 2*NP (x * [w_hi | w_lo] in ONE MMA: the stage is read once for both
@@ -264,13 +278,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const __grid_
                 const int ty = q % p.tilesY;
                 const int n = q / p.tilesY;
                 mbar_wait_t<true>(SBAR(EMPTY, sb), ph ^ 1u, w0);
-                mbar_expect_tx(SBAR(FULL, sb), A_BYTES);
-                const int cx = tx * TC_TW - 1, cy = ty * TC_R - 1;
-                asm volatile(
-                    "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
-                    "%6}], [%2];" ::"r"(sbase + sb * A_STRIDE),
-                    "l"(&tmap), "r"(SBAR(FULL, sb)), "r"(0), "r"(cx), "r"(cy), "r"(n)
-                    : "memory");
+                mbar_expect_tx(SBAR(FULL, sb), BOX_BYTES * TcGeo<DIL>::NLOADS);
+                const int cx = tx * TC_TW - DIL;
+#pragma unroll
+                for (int ld = 0; ld < TcGeo<DIL>::NLOADS; ++ld) {
+                    const int cy = (DIL == 1) ? ty * TC_R - 1 : ty + (ld - 1) * DIL;
+                    asm volatile(
+                        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+                        "%5, %6}], [%2];" ::"r"(sbase + sb * A_STRIDE + (uint32_t)ld * TC_TWP * ROWB),
+                        "l"(&tmap), "r"(SBAR(FULL, sb)), "r"(0), "r"(cx), "r"(cy), "r"(n)
+                        : "memory");
+                }
             }
             (void)tstart;
         }
@@ -288,7 +306,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const __grid_
                 const uint64_t a_desc = make_desc<KC>(sbase + sb * A_STRIDE, p.use_base_offset);
 #pragma unroll
                 for (int mt = 0; mt < TC_R; ++mt)
-                    tc_issue_pass<KC, NP, false>(tmem + (uint32_t)((ab * TC_R + mt) * ACC_COLS),
+                    tc_issue_pass<KC, NP, false, DIL>(tmem + (uint32_t)((ab * TC_R + mt) * ACC_COLS),
                                                  a_desc + ((uint32_t)(mt * TC_TWP) * ROWB >> 4), b_desc, IDESC1);
                 tc_commit(ABAR(ACCF, ab));     // accumulators complete -> epilogue
                 tc_commit(SBAR(EMPTY, sb));    // stage buffer free -> producer
@@ -304,7 +322,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const __grid_
                 for (int mt = 0; mt < TC_R; ++mt) {
                     const uint32_t d_tmem = tmem + (uint32_t)((ab * TC_R + mt) * ACC_COLS);
                     const uint64_t a_mt = a_desc + ((uint32_t)(mt * TC_TWP) * ROWB >> 4);
-                    tc_issue_pass<KC, NP, true>(d_tmem, a_mt, b_desc, IDESC2);   // x_hi * [w_hi | w_lo] (raw stage: MMA reads hi)
+                    tc_issue_pass<KC, NP, true, DIL>(d_tmem, a_mt, b_desc, IDESC2);   // x_hi * [w_hi | w_lo] (raw stage: MMA reads hi)
                 }
                 tc_commit(SBAR(P12, sb));
                 if (it >= LAG) pass3(it - LAG);                                // x_lo * w_hi of an earlier tile
@@ -456,13 +474,13 @@ PFN_tmapEncodeTiled get_encode() {
     return fn;
 }
 
-template <int KC, int NP, int NBUF, int NACC, int LAG>
+template <int KC, int NP, int NBUF, int NACC, int LAG, int DIL>
 int launch_tc(const CUtensorMap& tmap, TcP p, cudaStream_t s) {
     constexpr uint32_t ROWB = KC * 4;
-    constexpr uint32_t A_STRIDE = ((TC_TROWS * TC_TWP * ROWB) + 1023u) & ~1023u;
+    constexpr uint32_t A_STRIDE = ((TcGeo<DIL>::TROWS * TcGeo<DIL>::TWP * ROWB) + 1023u) & ~1023u;
     constexpr uint32_t B_BYTES = 2 * 9 * NP * ROWB;
     const size_t smem = NBUF * A_STRIDE + B_BYTES + 1024;
-    auto kern = conv3x3_tc_kernel<KC, NP, NBUF, NACC, LAG>;
+    auto kern = conv3x3_tc_kernel<KC, NP, NBUF, NACC, LAG, DIL>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -480,9 +498,9 @@ int launch_tc(const CUtensorMap& tmap, TcP p, cudaStream_t s) {
 
 }  // namespace
 
-extern "C" int codd_conv3x3_tc(const float* in, int ldi, int cin, int n, int h, int w, const float* weight_split,
-                               const float* bias, const float* residual, int ldr, int res_bcast, int cout, int act,
-                               float* out, int ldo, int flags, void* stream) {
+extern "C" int codd_conv3x3_tc_dil(const float* in, int ldi, int cin, int n, int h, int w, const float* weight_split,
+                                   const float* bias, const float* residual, int ldr, int res_bcast, int cout, int act,
+                                   float* out, int ldo, int dil, int flags, void* stream) {
     if (!in || !weight_split || !out || n <= 0 || h <= 0 || w <= 0 || cin <= 0 || cout <= 0) return CODD_E_BADARG;
     if (cin > 32 || cout > 32 || cin % 4 != 0 || ldi % 4 != 0 || ldi < cin || ldo < cout) return CODD_E_SHAPE;
     if (!codd_aligned16(in)) return CODD_E_ALIGN;
@@ -491,10 +509,13 @@ extern "C" int codd_conv3x3_tc(const float* in, int ldi, int cin, int n, int h, 
     const int KC = cin <= 16 ? 16 : 32;
     const int NP = cout <= 16 ? 16 : 32;
     if (KC == 16 && NP == 32) return CODD_E_UNSUPPORTED;
+    if (dil != 1 && !(dil == 3 && KC == 32 && NP == 32)) return CODD_E_UNSUPPORTED;
+    const int boxw = dil == 1 ? TcGeo<1>::BOXW : TcGeo<3>::BOXW, boxrows = dil == 1 ? TcGeo<1>::BOXROWS : TcGeo<3>::BOXROWS;
+    const int rows_per_tile = dil == 1 ? TcGeo<1>::R : TcGeo<3>::R;
     CUtensorMap tmap;
     const cuuint64_t gdim[4] = {(cuuint64_t)cin, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
     const cuuint64_t gstr[3] = {(cuuint64_t)ldi * 4, (cuuint64_t)w * ldi * 4, (cuuint64_t)h * w * ldi * 4};
-    const cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)TC_TWP, (cuuint32_t)TC_TROWS, 1u};
+    const cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)boxw, (cuuint32_t)boxrows, 1u};
     const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
     const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)in, gdim, gstr, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, KC == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
@@ -504,16 +525,24 @@ extern "C" int codd_conv3x3_tc(const float* in, int ldi, int cin, int n, int h, 
     p.wpk = weight_split; p.bias = bias; p.res = residual; p.out = out;
     p.N = n; p.H = h; p.W = w; p.Cout = cout; p.ldo = ldo; p.ldr = ldr; p.res_bcast = res_bcast; p.act = act;
     p.tilesX = codd_ceil_div(w, TC_TW);
-    p.tilesY = codd_ceil_div(h, TC_R);
+    p.tilesY = codd_ceil_div(h, rows_per_tile);
     p.ntiles = p.tilesX * p.tilesY * n;
     p.dbg = g_tc_dbg;
     p.split_rna = (flags & 1) ? 1 : 0;
     p.use_base_offset = (flags & 2) ? 1 : 0;
     p.diag = (flags >> 2) & 3;
     cudaStream_t s = (cudaStream_t)stream;
-    if (KC == 32 && NP == 32) return launch_tc<32, 32, 2, 3, 1>(tmap, p, s);
-    if (KC == 32 && NP == 16) return launch_tc<32, 16, 2, 3, 1>(tmap, p, s);
-    return launch_tc<16, 16, 4, 4, 2>(tmap, p, s);
+    if (dil == 3) return launch_tc<32, 32, 2, 3, 1, 3>(tmap, p, s);
+    if (KC == 32 && NP == 32) return launch_tc<32, 32, 2, 3, 1, 1>(tmap, p, s);
+    if (KC == 32 && NP == 16) return launch_tc<32, 16, 2, 3, 1, 1>(tmap, p, s);
+    return launch_tc<16, 16, 4, 4, 2, 1>(tmap, p, s);
+}
+
+extern "C" int codd_conv3x3_tc(const float* in, int ldi, int cin, int n, int h, int w, const float* weight_split,
+                               const float* bias, const float* residual, int ldr, int res_bcast, int cout, int act,
+                               float* out, int ldo, int flags, void* stream) {
+    return codd_conv3x3_tc_dil(in, ldi, cin, n, h, w, weight_split, bias, residual, ldr, res_bcast, cout, act, out, ldo,
+                               1, flags, stream);
 }
 
 // diagnostic: device buffer of [grid][8] int64 cycle counters filled by the next codd_conv3x3_tc launches

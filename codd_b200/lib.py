@@ -30,6 +30,8 @@ SIGNATURES = {
     "codd_conv2d_nhwc": (c_int, [POINTER(ConvDesc), _FP, _FP, _FP, _FP, _FP, _FP, c_void_p]),
     "codd_conv3x3_tc": (c_int, [_FP, c_int, c_int, c_int, c_int, c_int, _FP, _FP, _FP, c_int, c_int, c_int, c_int, _FP,
                                 c_int, c_int, c_void_p]),
+    "codd_conv3x3_tc_dil": (c_int, [_FP, c_int, c_int, c_int, c_int, c_int, _FP, _FP, _FP, c_int, c_int, c_int, c_int,
+                                    _FP, c_int, c_int, c_int, c_void_p]),
     "codd_conv3x3_tc_debug": (c_int, [_FP]),
     "codd_conv3x3_image": (c_int, [_FP, _FP, c_int, c_int, c_int, _FP, _FP, c_int, _FP, c_int, c_void_p]),
     "codd_deconv2x2_nhwc": (c_int, [_FP, c_int, c_int, c_int, c_int, c_int, _FP, _FP, c_int, _FP, c_int, c_int,

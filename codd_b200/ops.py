@@ -171,22 +171,26 @@ def tc_eligible(cin, cout, k, stride, pad, dil, x2):
     kh, kw = (k, k) if isinstance(k, int) else k
     sh, sw = (stride, stride) if isinstance(stride, int) else stride
     ph, pw = (pad, pad) if isinstance(pad, int) else pad
-    return (x2 is None and kh == 3 and kw == 3 and sh == 1 and sw == 1 and ph == 1 and pw == 1 and dil == 1
-            and cin in (16, 24, 32) and cout <= 32 and not (cin <= 16 and cout > 16))
+    if not (x2 is None and kh == 3 and kw == 3 and sh == 1 and sw == 1 and ph == dil and pw == dil):
+        return False
+    if dil == 3:
+        return cin == 32 and cout == 32
+    return dil == 1 and cin in (16, 24, 32) and cout <= 32 and not (cin <= 16 and cout > 16)
 
 
-def conv3x3_tc(x, wsplit, bias, cout, act=ACT_NONE, residual=None, res_bcast=False, flags=0):
-    """3x3 s1 p1 conv on the tensor cores (3xTF32).  ``wsplit`` from pack_conv_weight_tc."""
+def conv3x3_tc(x, wsplit, bias, cout, act=ACT_NONE, residual=None, res_bcast=False, flags=0, dil=1):
+    """3x3 s1 conv (pad = dil) on the tensor cores (3xTF32).  ``wsplit`` from pack_conv_weight_tc."""
     _require_cuda(x, wsplit, bias, residual)
     n, cin, h, w = x.shape
     out = empty_nhwc(n, cout, h, w, x.device)
     nbytes = 4 * (n * h * w * (cin + cout) + wsplit.numel() // 2
                   + (0 if residual is None else n * h * w * (1 if res_bcast else cout)))
-    rc = _run(f"conv3x3tc_cin{cin}_cout{cout}", nbytes, lambda: _lib.load().codd_conv3x3_tc(
+    tag = f"conv3x3tc_cin{cin}_cout{cout}" + ("" if dil == 1 else f"_d{dil}")
+    rc = _run(tag, nbytes, lambda: _lib.load().codd_conv3x3_tc_dil(
         x.data_ptr(), ld_of(x), cin, n, h, w, wsplit.data_ptr(), None if bias is None else bias.data_ptr(),
         None if residual is None else residual.data_ptr(), 0 if residual is None else ld_of(residual),
-        1 if res_bcast else 0, cout, act, out.data_ptr(), ld_of(out), flags, _stream()))
-    _lib.check(rc, f"codd_conv3x3_tc(cin={cin}, cout={cout})")
+        1 if res_bcast else 0, cout, act, out.data_ptr(), ld_of(out), dil, flags, _stream()))
+    _lib.check(rc, f"codd_conv3x3_tc(cin={cin}, cout={cout}, dil={dil})")
     return out
 
 

@@ -23,7 +23,7 @@ def run_conv(pw, conv, x, act, x2=None, residual=None, res_bcast=False, head=Non
     cin = x.shape[1] + (0 if x2 is None else x2.shape[1])
     if USE_TC and ops.tc_eligible(cin, cout, k, st, pd, dl, x2):
         ws, b = pw.conv_tc(conv, head)
-        return ops.conv3x3_tc(x, ws, b, cout, act, residual=residual, res_bcast=res_bcast)
+        return ops.conv3x3_tc(x, ws, b, cout, act, residual=residual, res_bcast=res_bcast, dil=dl)
     wp, b = pw.conv(conv) if head is None else pw.conv_head(conv, head)
     return ops.conv2d(x, wp, b, cout, k, st, pd, dl, act, x2=x2, residual=residual, res_bcast=res_bcast)
 

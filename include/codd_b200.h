@@ -89,6 +89,14 @@ CODD_API int codd_conv3x3_tc(const float* in, int ldi, int cin, int n, int h, in
                              const float* weight_split, const float* bias, const float* residual, int ldr,
                              int res_bcast, int cout, int act, float* out, int ldo, int flags, void* stream);
 
+/* Same kernel family with a dilation: dil = 1 (as above) or dil = 3 with pad 3, cin = cout = 32 — the dilated
+ * resblocks of tile_update4_1 / tile_update5 (propagation.py:258-280).  One output row per tile; the input rows
+ * y-3, y, y+3 arrive as three one-row TMA boxes. */
+CODD_API int codd_conv3x3_tc_dil(const float* in, int ldi, int cin, int n, int h, int w,
+                                 const float* weight_split, const float* bias, const float* residual, int ldr,
+                                 int res_bcast, int cout, int act, float* out, int ldo, int dil, int flags,
+                                 void* stream);
+
 /* Diagnostic: device buffer [grid][8] of int64 cycle counters filled by later codd_conv3x3_tc launches. */
 CODD_API int codd_conv3x3_tc_debug(long long* dbg);
 

@@ -325,6 +325,22 @@ def test_conv3x3_tensor_core(ops, cin, cout, h, w):
     torch.testing.assert_close(back(ops, out), ref, rtol=CONV_RTOL, atol=CONV_ATOL)
 
 
+@pytest.mark.parametrize("h,w", [(9, 200), (5, 128), (20, 131), (3, 7)])
+def test_conv3x3_tensor_core_dilated(ops, h, w):
+    """dilation 3 / pad 3, 32 -> 32 (the dilated resblocks of tile_update4_1 / tile_update5)."""
+    from codd_b200.lib import ACT_LEAKY
+    g = gen(1000 + h * w)
+    x = torch.randn(2, 32, h, w, generator=g)
+    wt = torch.randn(32, 32, 3, 3, generator=g) / (32 * 9) ** 0.5
+    b = torch.randn(32, generator=g)
+    res = torch.randn(2, 32, h, w, generator=g)
+    ref = F.leaky_relu(F.conv2d(x, wt, b, padding=3, dilation=3) + res, 0.2)
+    assert ops.tc_eligible(32, 32, 3, 1, 3, 3, None)
+    out = ops.conv3x3_tc(nhwc(ops, x), ops.pack_conv_weight_tc(wt.cuda()), b.cuda(), 32, ACT_LEAKY,
+                         residual=nhwc(ops, res), dil=3)
+    torch.testing.assert_close(back(ops, out), ref, rtol=CONV_RTOL, atol=CONV_ATOL)
+
+
 # ------------------------------------------------------------------------------------------
 # Fusion (K13)
 # ------------------------------------------------------------------------------------------
