@@ -15,16 +15,20 @@
 
 static inline bool codd_aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
 
+// Transcendental activations (fusion heads, GRU gates): OUT OF LINE on purpose.  Inlined into a fully unrolled
+// 64-element epilogue they blow a kernel up to several hundred KB of straight-line code that every warp
+// executes once — the direct convolutions were instruction-fetch bound on it (ncu: stall_no_inst > 50 %).
+static __device__ __noinline__ float codd_act_slow(float v, int act) {
+    if (act == CODD_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
+    if (act == CODD_ACT_TANH) return tanhf(v);
+    const float sp = v > 20.f ? v : log1pf(expf(v));   // mish: x * tanh(softplus(x)), torch threshold 20
+    return v * tanhf(sp);
+}
+
 __device__ __forceinline__ float codd_act(float v, int act, int ch) {
     // the activations of the stereo path (none / leaky / relu / relu on channel 0) are branch-free
-    // selects; only the rare transcendental ones (fusion heads) take a branch.  (A `switch` here
-    // compiles to an indirect jump per element and dominated the conv epilogues.)
-    if (act >= CODD_ACT_SIGMOID) {
-        if (act == CODD_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
-        if (act == CODD_ACT_TANH) return tanhf(v);
-        const float sp = v > 20.f ? v : log1pf(expf(v));   // mish: x * tanh(softplus(x)), torch threshold 20
-        return v * tanhf(sp);
-    }
+    // selects; only the rare transcendental ones take a (call) branch.
+    if (act >= CODD_ACT_SIGMOID) return codd_act_slow(v, act);
     const bool clamp = (act == CODD_ACT_RELU) || (act == CODD_ACT_RELU_CH0 && ch == 0);
     const float neg = (act == CODD_ACT_LEAKY) ? v * CODD_LEAKY_SLOPE : (clamp ? 0.f : v);
     return v > 0.f ? v : neg;
@@ -49,6 +53,16 @@ __device__ __forceinline__ ActSel codd_act_sel(int act) {
 __device__ __forceinline__ float codd_act_apply(const ActSel& a, float v, int ch) {
     if (a.simple) return fmaxf(v, 0.f) + (ch == 0 ? a.slope0 : a.slope) * fminf(v, 0.f);
     return codd_act(v, a.act, ch);
+}
+
+// acc[0..3] += a * w.{x,y,z,w} as two packed FFMA2 (sm_100a: one instruction = two independent fp32 FMAs, so
+// bit-identical to four FFMA at half the issue slots and half the code size — the direct convolutions are
+// instruction-fetch / issue bound, not FMA-pipe bound).
+__device__ __forceinline__ void fma4(float* acc, float a, const float4& w) {
+    const float2 aa = make_float2(a, a);
+    float2* a2 = reinterpret_cast<float2*>(acc);
+    a2[0] = __ffma2_rn(aa, make_float2(w.x, w.y), a2[0]);
+    a2[1] = __ffma2_rn(aa, make_float2(w.z, w.w), a2[1]);
 }
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }

@@ -50,6 +50,51 @@ __device__ __forceinline__ float4 conv_load4(const ConvP& p, size_t pix, int c) 
                        conv_load1(p, pix, c + 3));
 }
 
+// Fast epilogue for one pixel's group of NC accumulators (the common case: full channel group, 16-byte aligned
+// output / residual rows, branch-free activation).  ~5 instructions per element; the general path below
+// (ragged Cout, unaligned rows, transcendental activations, residual after the activation) costs ~45 and, fully
+// unrolled over 64 accumulators, made these kernels instruction-fetch bound.
+struct EpiFast {
+    bool ok, res_vec, res_b;
+    float slope, slope0;
+};
+__device__ __forceinline__ EpiFast epi_fast_setup(const ConvP& p, int cbase, int nc) {
+    EpiFast e;
+    e.res_b = p.res && p.res_bcast;
+    e.res_vec = p.res && !p.res_bcast;
+    e.ok = (cbase + nc <= p.Cout) && ((p.ldo & 3) == 0) && ((((uintptr_t)p.out) & 15u) == 0) &&
+           (p.act <= CODD_ACT_RELU_CH0) && !p.res_after && (!p.bias || (((uintptr_t)p.bias) & 15u) == 0) &&
+           (!e.res_vec || (((p.ldr & 3) == 0) && ((((uintptr_t)p.res) & 15u) == 0)));
+    e.slope = p.act == CODD_ACT_LEAKY ? CODD_LEAKY_SLOPE : (p.act == CODD_ACT_RELU ? 0.f : 1.f);
+    e.slope0 = (p.act == CODD_ACT_RELU || p.act == CODD_ACT_RELU_CH0) ? 0.f : e.slope;
+    return e;
+}
+template <int NC>
+__device__ __forceinline__ void epi_fast_store(const ConvP& p, const EpiFast& e, const float* acc, size_t opix, int cbase) {
+    float* op = p.out + opix * p.ldo + cbase;
+    const float rb = e.res_b ? __ldg(p.res + opix * p.ldr) : 0.f;
+#pragma unroll
+    for (int o4 = 0; o4 < NC / 4; ++o4) {
+        float4 v = make_float4(acc[o4 * 4], acc[o4 * 4 + 1], acc[o4 * 4 + 2], acc[o4 * 4 + 3]);
+        if (p.bias) {
+            const float4 b = ldg4(p.bias + cbase + o4 * 4);
+            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        }
+        if (e.res_vec) {
+            const float4 r = ldg4(p.res + opix * p.ldr + cbase + o4 * 4);
+            v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+        } else {
+            v.x += rb; v.y += rb; v.z += rb; v.w += rb;
+        }
+        const float s0 = (cbase + o4 == 0) ? e.slope0 : e.slope;
+        v.x = fmaxf(v.x, 0.f) + s0 * fminf(v.x, 0.f);
+        v.y = fmaxf(v.y, 0.f) + e.slope * fminf(v.y, 0.f);
+        v.z = fmaxf(v.z, 0.f) + e.slope * fminf(v.z, 0.f);
+        v.w = fmaxf(v.w, 0.f) + e.slope * fminf(v.w, 0.f);
+        *reinterpret_cast<float4*>(op + o4 * 4) = v;
+    }
+}
+
 template <int KH, int KW, int SH, int SW, int DIL, int CO_T>
 __global__ void __launch_bounds__(256, 2) conv_nhwc_kernel(ConvP p) {
     constexpr int IW = (TW - 1) * SW + (KW - 1) * DIL + 1;
@@ -74,7 +119,7 @@ __global__ void __launch_bounds__(256, 2) conv_nhwc_kernel(ConvP p) {
     const int iy0 = oy0 * SH - p.ph, ix0 = ox0 * SW - p.pw;
     const int Cin = p.C0 + p.C1;
 
-    float acc[PX][CO_T];
+    __align__(8) float acc[PX][CO_T];
 #pragma unroll
     for (int i = 0; i < PX; ++i)
 #pragma unroll
@@ -129,10 +174,7 @@ __global__ void __launch_bounds__(256, 2) conv_nhwc_kernel(ConvP p) {
 #pragma unroll
                             for (int i = 0; i < PX; ++i) {
                                 const float av = cc == 0 ? a[i].x : cc == 1 ? a[i].y : cc == 2 ? a[i].z : a[i].w;
-                                acc[i][o4 * 4 + 0] = fmaf(av, wv.x, acc[i][o4 * 4 + 0]);
-                                acc[i][o4 * 4 + 1] = fmaf(av, wv.y, acc[i][o4 * 4 + 1]);
-                                acc[i][o4 * 4 + 2] = fmaf(av, wv.z, acc[i][o4 * 4 + 2]);
-                                acc[i][o4 * 4 + 3] = fmaf(av, wv.w, acc[i][o4 * 4 + 3]);
+                                fma4(&acc[i][o4 * 4], av, wv);
                             }
                         }
                     }
@@ -147,11 +189,16 @@ __global__ void __launch_bounds__(256, 2) conv_nhwc_kernel(ConvP p) {
     const int cbase = g * CO_T;
     const bool vec_out = ((p.ldo & 3) == 0) && ((((uintptr_t)p.out) & 15u) == 0);
     const ActSel asel = codd_act_sel(p.act);
+    const EpiFast fast = epi_fast_setup(p, cbase, CO_T);
 #pragma unroll
     for (int i = 0; i < PX; ++i) {
         const int oy = oy0 + pwi * PX + i;
         if (oy >= p.Ho) continue;
         const size_t opix = ((size_t)n * p.Ho + oy) * p.Wo + ox;
+        if (fast.ok) {
+            epi_fast_store<CO_T>(p, fast, acc[i], opix, cbase);
+            continue;
+        }
         float* op = p.out + opix * p.ldo;
         float rb = 0.f;
         if (p.res && p.res_bcast) rb = __ldg(p.res + opix * p.ldr);
@@ -236,7 +283,7 @@ int dispatch_cout(const ConvP& p, cudaStream_t s) {
 // broadcasts.  HBM-bound (AI = 2*Cin*Cout / (4*(Cin+Cout)) < 12 flop/B for every layer here).
 // ---------------------------------------------------------------------------------------------
 template <int CO, int PX_T>
-__global__ void __launch_bounds__(256) pointwise_kernel(ConvP p, size_t npix) {
+__global__ void __launch_bounds__(256, 2) pointwise_kernel(ConvP p, size_t npix) {
     extern __shared__ float4 smem4[];
     float* s_w = reinterpret_cast<float*>(smem4);  // [Cin][CO]
     const int Cin = p.C0 + p.C1;
@@ -246,7 +293,7 @@ __global__ void __launch_bounds__(256) pointwise_kernel(ConvP p, size_t npix) {
     }
     __syncthreads();
     const size_t base = (size_t)blockIdx.x * (blockDim.x * PX_T) + threadIdx.x;
-    float acc[PX_T][CO];
+    __align__(8) float acc[PX_T][CO];
 #pragma unroll
     for (int q = 0; q < PX_T; ++q)
 #pragma unroll
@@ -270,19 +317,21 @@ __global__ void __launch_bounds__(256) pointwise_kernel(ConvP p, size_t npix) {
 #pragma unroll
                 for (int q = 0; q < PX_T; ++q) {
                     const float av = cc == 0 ? a[q].x : cc == 1 ? a[q].y : cc == 2 ? a[q].z : a[q].w;
-                    acc[q][o4 * 4 + 0] = fmaf(av, wv.x, acc[q][o4 * 4 + 0]);
-                    acc[q][o4 * 4 + 1] = fmaf(av, wv.y, acc[q][o4 * 4 + 1]);
-                    acc[q][o4 * 4 + 2] = fmaf(av, wv.z, acc[q][o4 * 4 + 2]);
-                    acc[q][o4 * 4 + 3] = fmaf(av, wv.w, acc[q][o4 * 4 + 3]);
+                    fma4(&acc[q][o4 * 4], av, wv);
                 }
             }
         }
     }
     const ActSel asel = codd_act_sel(p.act);
+    const EpiFast fast = epi_fast_setup(p, 0, CO);
 #pragma unroll
     for (int q = 0; q < PX_T; ++q) {
         const size_t px = base + (size_t)q * blockDim.x;
         if (px >= npix) continue;
+        if (fast.ok) {
+            epi_fast_store<CO>(p, fast, acc[q], px, 0);
+            continue;
+        }
         float* op = p.out + px * p.ldo;
         float rb = 0.f;
         if (p.res && p.res_bcast) rb = __ldg(p.res + px * p.ldr);
@@ -345,7 +394,7 @@ __global__ void __launch_bounds__(128) conv3x3_image_kernel(const float* __restr
     const int s = blockIdx.z;  // sample in [0, 2n)
     if (x0 >= w) return;
     const float* img = (s < n ? left + (size_t)s * 3 * h * w : right + (size_t)(s - n) * 3 * h * w);
-    float acc[PXI][CO];
+    __align__(8) float acc[PXI][CO];
 #pragma unroll
     for (int q = 0; q < PXI; ++q)
 #pragma unroll
@@ -371,10 +420,7 @@ __global__ void __launch_bounds__(128) conv3x3_image_kernel(const float* __restr
                     const float4 wv = *reinterpret_cast<const float4*>(wp + o4 * 4);
 #pragma unroll
                     for (int q = 0; q < PXI; ++q) {
-                        acc[q][o4 * 4 + 0] = fmaf(a[q + kx], wv.x, acc[q][o4 * 4 + 0]);
-                        acc[q][o4 * 4 + 1] = fmaf(a[q + kx], wv.y, acc[q][o4 * 4 + 1]);
-                        acc[q][o4 * 4 + 2] = fmaf(a[q + kx], wv.z, acc[q][o4 * 4 + 2]);
-                        acc[q][o4 * 4 + 3] = fmaf(a[q + kx], wv.w, acc[q][o4 * 4 + 3]);
+                        fma4(&acc[q][o4 * 4], a[q + kx], wv);
                     }
                 }
             }
