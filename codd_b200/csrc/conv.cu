@@ -373,16 +373,18 @@ int launch_pointwise(const ConvP& p, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------
 // first layer: NCHW image (3 ch) -> NHWC, 3x3 pad 1, LeakyReLU
 // ---------------------------------------------------------------------------------------------
+constexpr int IMG_ROWS = 8;   // output rows per thread (the row loop re-uses the ~6 KB tap body from the I-cache)
 template <int CO>
 __global__ void __launch_bounds__(128) conv3x3_image_kernel(const float* __restrict__ left,
                                                             const float* __restrict__ right, int n, int h,
                                                             int w, const float* __restrict__ wgt,
                                                             const float* __restrict__ bias, int cout,
                                                             float* __restrict__ out, int ldo) {
-    // each thread computes 4 horizontally adjacent pixels: one weight broadcast feeds 4 FMAs
+    // each thread computes 4 horizontally adjacent pixels of IMG_ROWS consecutive rows: one weight broadcast
+    // feeds 4 packed FMAs; the ky / row loops stay ROLLED so that the instruction footprint is one tap row
     constexpr int PXI = 4;
     __shared__ __align__(16) float s_w[27 * CO];
-    __shared__ float s_b[CO];
+    __shared__ __align__(16) float s_b[CO];
     for (int i = threadIdx.x; i < 27 * CO; i += blockDim.x) {
         const int co = i % CO, t = i / CO;
         s_w[i] = co < cout ? wgt[t * cout + co] : 0.f;
@@ -390,55 +392,60 @@ __global__ void __launch_bounds__(128) conv3x3_image_kernel(const float* __restr
     for (int i = threadIdx.x; i < CO; i += blockDim.x) s_b[i] = i < cout ? bias[i] : 0.f;
     __syncthreads();
     const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * PXI;
-    const int y = blockIdx.y;
     const int s = blockIdx.z;  // sample in [0, 2n)
     if (x0 >= w) return;
     const float* img = (s < n ? left + (size_t)s * 3 * h * w : right + (size_t)(s - n) * 3 * h * w);
-    __align__(8) float acc[PXI][CO];
+    const bool vec = (ldo & 3) == 0 && cout == CO && ((((uintptr_t)out) & 15u) == 0);
+    const int y_end = min(h, (int)(blockIdx.y + 1) * IMG_ROWS);
+#pragma unroll 1
+    for (int y = blockIdx.y * IMG_ROWS; y < y_end; ++y) {
+        __align__(8) float acc[PXI][CO];
 #pragma unroll
-    for (int q = 0; q < PXI; ++q)
+        for (int q = 0; q < PXI; ++q)
 #pragma unroll
-        for (int i = 0; i < CO; ++i) acc[q][i] = s_b[i];
+            for (int i = 0; i < CO; ++i) acc[q][i] = s_b[i];
+#pragma unroll 1
+        for (int ky = 0; ky < 3; ++ky) {
+            const int yy = y + ky - 1;
+            if (yy < 0 || yy >= h) continue;
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-        const int yy = y + ky - 1;
-        if (yy < 0 || yy >= h) continue;
+            for (int ci = 0; ci < 3; ++ci) {
+                const float* rp = img + ((size_t)ci * h + yy) * w;
+                float a[PXI + 2];
 #pragma unroll
-        for (int ci = 0; ci < 3; ++ci) {
-            const float* rp = img + ((size_t)ci * h + yy) * w;
-            float a[PXI + 2];
+                for (int e = 0; e < PXI + 2; ++e) {
+                    const int xx = x0 + e - 1;
+                    a[e] = (xx >= 0 && xx < w) ? __ldg(rp + xx) : 0.f;
+                }
 #pragma unroll
-            for (int e = 0; e < PXI + 2; ++e) {
-                const int xx = x0 + e - 1;
-                a[e] = (xx >= 0 && xx < w) ? __ldg(rp + xx) : 0.f;
-            }
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float* wp = s_w + ((ky * 3 + kx) * 3 + ci) * CO;
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const float* wp = s_w + ((ky * 3 + kx) * 3 + ci) * CO;
+                    for (int o4 = 0; o4 < CO / 4; ++o4) {
+                        const float4 wv = *reinterpret_cast<const float4*>(wp + o4 * 4);
 #pragma unroll
-                for (int o4 = 0; o4 < CO / 4; ++o4) {
-                    const float4 wv = *reinterpret_cast<const float4*>(wp + o4 * 4);
-#pragma unroll
-                    for (int q = 0; q < PXI; ++q) {
-                        fma4(&acc[q][o4 * 4], a[q + kx], wv);
+                        for (int q = 0; q < PXI; ++q) fma4(&acc[q][o4 * 4], a[q + kx], wv);
                     }
                 }
             }
         }
-    }
-    const bool vec = (ldo & 3) == 0 && cout == CO && ((((uintptr_t)out) & 15u) == 0);
 #pragma unroll
-    for (int q = 0; q < PXI; ++q) {
-        if (x0 + q >= w) break;
-        float* op = out + (((size_t)s * h + y) * w + x0 + q) * ldo;
-        if (vec) {
+        for (int q = 0; q < PXI; ++q) {
+            if (x0 + q >= w) break;
+            float* op = out + (((size_t)s * h + y) * w + x0 + q) * ldo;
+            if (vec) {
 #pragma unroll
-            for (int o4 = 0; o4 < CO / 4; ++o4)
-                *reinterpret_cast<float4*>(op + o4 * 4) = make_float4(
-                    codd_act(acc[q][o4 * 4], CODD_ACT_LEAKY, 0), codd_act(acc[q][o4 * 4 + 1], CODD_ACT_LEAKY, 0),
-                    codd_act(acc[q][o4 * 4 + 2], CODD_ACT_LEAKY, 0), codd_act(acc[q][o4 * 4 + 3], CODD_ACT_LEAKY, 0));
-        } else {
-            for (int i = 0; i < cout; ++i) op[i] = codd_act(acc[q][i], CODD_ACT_LEAKY, 0);
+                for (int o4 = 0; o4 < CO / 4; ++o4) {
+                    float4 v = make_float4(acc[q][o4 * 4], acc[q][o4 * 4 + 1], acc[q][o4 * 4 + 2], acc[q][o4 * 4 + 3]);
+                    v.x = fmaxf(v.x, 0.f) + CODD_LEAKY_SLOPE * fminf(v.x, 0.f);
+                    v.y = fmaxf(v.y, 0.f) + CODD_LEAKY_SLOPE * fminf(v.y, 0.f);
+                    v.z = fmaxf(v.z, 0.f) + CODD_LEAKY_SLOPE * fminf(v.z, 0.f);
+                    v.w = fmaxf(v.w, 0.f) + CODD_LEAKY_SLOPE * fminf(v.w, 0.f);
+                    *reinterpret_cast<float4*>(op + o4 * 4) = v;
+                }
+            } else {
+                for (int i = 0; i < cout; ++i) op[i] = codd_act(acc[q][i], CODD_ACT_LEAKY, 0);
+            }
         }
     }
 }
@@ -467,7 +474,7 @@ __global__ void __launch_bounds__(128) deconv2x2_kernel(const float* __restrict_
     if (x >= w) return;
     const int dy = oy & 1;
     const float* ip = in + (((size_t)s * h + (oy >> 1)) * w + x) * ldi;
-    float acc[2][CO];
+    __align__(8) float acc[2][CO];
 #pragma unroll
     for (int q = 0; q < 2; ++q)
 #pragma unroll
@@ -483,14 +490,8 @@ __global__ void __launch_bounds__(128) deconv2x2_kernel(const float* __restrict_
             for (int o4 = 0; o4 < CO / 4; ++o4) {
                 const float4 u = *reinterpret_cast<const float4*>(w0 + (ci + cc) * CO + o4 * 4);
                 const float4 v = *reinterpret_cast<const float4*>(w1 + (ci + cc) * CO + o4 * 4);
-                acc[0][o4 * 4 + 0] = fmaf(a, u.x, acc[0][o4 * 4 + 0]);
-                acc[0][o4 * 4 + 1] = fmaf(a, u.y, acc[0][o4 * 4 + 1]);
-                acc[0][o4 * 4 + 2] = fmaf(a, u.z, acc[0][o4 * 4 + 2]);
-                acc[0][o4 * 4 + 3] = fmaf(a, u.w, acc[0][o4 * 4 + 3]);
-                acc[1][o4 * 4 + 0] = fmaf(a, v.x, acc[1][o4 * 4 + 0]);
-                acc[1][o4 * 4 + 1] = fmaf(a, v.y, acc[1][o4 * 4 + 1]);
-                acc[1][o4 * 4 + 2] = fmaf(a, v.z, acc[1][o4 * 4 + 2]);
-                acc[1][o4 * 4 + 3] = fmaf(a, v.w, acc[1][o4 * 4 + 3]);
+                fma4(&acc[0][o4 * 4], a, u);
+                fma4(&acc[1][o4 * 4], a, v);
             }
         }
     }
@@ -643,7 +644,7 @@ extern "C" int codd_conv3x3_image(const float* left, const float* right, int n, 
     if (!left || !weight || !bias || !out || n <= 0 || h <= 0 || w <= 0) return CODD_E_BADARG;
     if (cout <= 0 || cout > 16 || ldo < cout) return CODD_E_SHAPE;
     dim3 block(64);
-    dim3 grid(codd_ceil_div(w, 64 * 4), h, right ? 2 * n : n);
+    dim3 grid(codd_ceil_div(w, 64 * 4), codd_ceil_div(h, IMG_ROWS), right ? 2 * n : n);
     conv3x3_image_kernel<16><<<grid, block, 0, (cudaStream_t)stream>>>(left, right ? right : left, n, h, w, weight,
                                                                         bias, cout, out, ldo);
     CODD_RETURN_IF_CUDA_ERROR();

@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(TF_THREADS) tile_features_kernel(TfP p) {
         s_b1[t] = __ldg(p.b1 + t);
     }
 
-    float acc[NOUT][16];
+    __align__(8) float acc[NOUT][16];
 #pragma unroll
     for (int o = 0; o < NOUT; ++o)
 #pragma unroll
@@ -102,10 +102,7 @@ __global__ void __launch_bounds__(TF_THREADS) tile_features_kernel(TfP p) {
 #pragma unroll
                             for (int o = 0; o < NOUT; ++o) {
                                 const float av = cc == 0 ? a[o].x : cc == 1 ? a[o].y : cc == 2 ? a[o].z : a[o].w;
-                                acc[o][o4 * 4 + 0] = fmaf(av, wv.x, acc[o][o4 * 4 + 0]);
-                                acc[o][o4 * 4 + 1] = fmaf(av, wv.y, acc[o][o4 * 4 + 1]);
-                                acc[o][o4 * 4 + 2] = fmaf(av, wv.z, acc[o][o4 * 4 + 2]);
-                                acc[o][o4 * 4 + 3] = fmaf(av, wv.w, acc[o][o4 * 4 + 3]);
+                                fma4(&acc[o][o4 * 4], av, wv);
                             }
                         }
                     }
@@ -122,7 +119,7 @@ __global__ void __launch_bounds__(TF_THREADS) tile_features_kernel(TfP p) {
         float hid[16];
 #pragma unroll
         for (int c = 0; c < 16; ++c) hid[c] = codd_act(acc[o][c] + s_b0[c], CODD_ACT_LEAKY, 0);
-        float outv[16];
+        __align__(8) float outv[16];
 #pragma unroll
         for (int c = 0; c < 16; ++c) outv[c] = s_b1[c];
 #pragma unroll
@@ -130,10 +127,7 @@ __global__ void __launch_bounds__(TF_THREADS) tile_features_kernel(TfP p) {
 #pragma unroll
             for (int o4 = 0; o4 < 4; ++o4) {
                 const float4 wv = *reinterpret_cast<const float4*>(&s_w1[hh][o4 * 4]);
-                outv[o4 * 4 + 0] = fmaf(hid[hh], wv.x, outv[o4 * 4 + 0]);
-                outv[o4 * 4 + 1] = fmaf(hid[hh], wv.y, outv[o4 * 4 + 1]);
-                outv[o4 * 4 + 2] = fmaf(hid[hh], wv.z, outv[o4 * 4 + 2]);
-                outv[o4 * 4 + 3] = fmaf(hid[hh], wv.w, outv[o4 * 4 + 3]);
+                fma4(&outv[o4 * 4], hid[hh], wv);
             }
         }
         if (xo < p.Wo) {
