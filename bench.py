@@ -303,11 +303,21 @@ def run_b200(args):
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
 
     total_ms = sum(k["ms"] for k in kernels)
+    # dram__bytes_read + dram__bytes_write per launch from the committed ncu capture of one step
+    # (tools/traffic_table.py -> profiles/traffic_r01.json); None for a kernel the capture does not hold
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))["kernels"]
+    except Exception:  # noqa: BLE001
+        traffic = {}
 
     def roof(k):
         gbs = k["bytes"] / (k["ms"] * 1e-3) / 1e9
+        tr = traffic.get(k["kernel"])
         return {"kernel": k["kernel"], "bound": "hbm", "achieved": round(gbs, 1), "peak": peak_gbs, "unit": "GB/s",
-                "frac": round(gbs / peak_gbs, 4), "traffic": None, "launches_per_step": k["launches"],
+                "frac": round(gbs / peak_gbs, 4),
+                "traffic": None if tr is None else round(tr["traffic_per_launch"]),
+                "algorithmic_bytes_per_launch": round(k["bytes"] / k["launches"]),
+                "launches_per_step": k["launches"],
                 "ms_per_step": round(k["ms"], 4), "share_of_step": round(k["ms"] / total_ms, 4),
                 "algorithmic_bytes_per_step": k["bytes"], "peak_source": peak_src,
                 "how": "per-launch CUDA events on the launching stream, instrumented eager pass after the timed region"}

@@ -98,3 +98,34 @@ def test_training_paths_fail_loudly():
     m = codd_b200.build_estimator(codd_b200.codd_stereo_config(64))
     with pytest.raises(NotImplementedError):
         m(img=[torch.zeros(1, 1, 3, 64, 64)], img_metas=[[{}]], return_loss=True)
+
+
+def test_full_codd_config_builds_reference_parameter_tree():
+    """stereo + motion + fusion through the registry: names / shapes of SURVEY.md Appendix B."""
+    m = codd_b200.build_estimator(codd_b200.codd_full_config(192, iters=16))
+    assert type(m.motion).__name__ == "Motion" and type(m.motion.raft3d).__name__ == "RAFT3D"
+    assert type(m.motion.raft3d.cnet[0]).__name__ == "HRNet" and type(m.fusion).__name__ == "Fusion"
+    sd = m.state_dict()
+    want = {
+        "motion.raft3d.fnet.conv1.weight": (64, 3, 7, 7),
+        "motion.raft3d.fnet.layer2.0.downsample.0.weight": (96, 64, 1, 1),
+        "motion.raft3d.cnet.0.conv1.weight": (64, 3, 3, 3),
+        "motion.raft3d.cnet.0.layer1.0.downsample.0.weight": (256, 64, 1, 1),
+        "motion.raft3d.cnet.0.transition1.1.0.0.weight": (36, 256, 3, 3),
+        "motion.raft3d.cnet.0.stage4.1.fuse_layers.3.0.2.0.weight": (144, 18, 3, 3),
+        "motion.raft3d.cnet.0.stage3.2.fuse_layers.0.2.0.weight": (18, 72, 1, 1),
+        "motion.raft3d.cnet.1.convs.0.weight": (512, 270, 1, 1),
+        "motion.raft3d.update_block.gru.convq2.weight": (128, 128, 3, 3),
+        "motion.raft3d.update_block.corr_enc.0.weight": (256, 196, 3, 3),
+        "motion.raft3d.update_block.flow_enc.0.weight": (128, 9, 7, 7),
+        "motion.raft3d.update_block.mask.2.weight": (576, 256, 1, 1),
+        "fusion.motion_conv.0.weight": (30, 64, 7, 7),
+        "stereo.tile_update.tile_update4_1.resblocks.1.0.conv1.0.0.weight": (32, 32, 3, 3),
+    }
+    for k, shape in want.items():
+        assert k in sd and tuple(sd[k].shape) == shape, k
+    assert "motion.raft3d.cnet.1.convs.0.bias" not in sd
+    n_update = sum(v.numel() for k, v in sd.items() if k.startswith("motion.raft3d.update_block."))
+    n_fnet = sum(v.numel() for k, v in sd.items() if k.startswith("motion.raft3d.fnet."))
+    assert abs(n_update / 1e6 - 3.47) < 0.01 and abs(n_fnet / 1e6 - 1.05) < 0.01      # SURVEY.md §6
+    assert m.eval() is None and not m.motion.training
