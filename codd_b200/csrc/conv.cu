@@ -125,7 +125,12 @@ __global__ void __launch_bounds__(256, 2) conv_nhwc_kernel(ConvP p) {
 #pragma unroll
         for (int j = 0; j < CO_T; ++j) acc[i][j] = 0.f;
 
-    const float* sa_base = s_in + ((pwi * PX * SH) * IW + lane * SW) * CP;
+    // Stride-2 layers store even and odd input columns in separate halves of a staged row: the lanes of a warp
+    // (consecutive output columns) then read consecutive slots for every tap instead of every second one, which
+    // with 48-byte pixel slots was an 8-way bank conflict on the 128-bit activation loads.
+    constexpr int IWH = (IW + 1) / 2;
+    auto col_slot = [&](int cc) { return SW == 2 ? (cc & 1) * IWH + (cc >> 1) : cc; };
+    const float* sa_base = s_in + ((pwi * PX * SH) * IW) * CP;
 
     for (int c0 = 0; c0 < Cin; c0 += CK) {
         __syncthreads();
@@ -139,7 +144,7 @@ __global__ void __launch_bounds__(256, 2) conv_nhwc_kernel(ConvP p) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W && c < Cin)
                 v = conv_load4(p, ((size_t)n * p.H + gy) * p.W + gx, c);
-            *reinterpret_cast<float4*>(s_in + pix * CP + c4 * 4) = v;
+            *reinterpret_cast<float4*>(s_in + (r * IW + col_slot(cc)) * CP + c4 * 4) = v;
         }
         // ---- stage weights: [tap][ci][COP]
         for (int idx = tid; idx < KH * KW * CK * COP; idx += nthreads) {
@@ -158,7 +163,7 @@ __global__ void __launch_bounds__(256, 2) conv_nhwc_kernel(ConvP p) {
         for (int ky = 0; ky < KH; ++ky) {
 #pragma unroll 1
             for (int kx = 0; kx < KW; ++kx) {
-                const float* sa = sa_base + ((ky * DIL) * IW + kx * DIL) * CP;
+                const float* sa = sa_base + ((ky * DIL) * IW + col_slot(lane * SW + kx * DIL)) * CP;
                 const float* sw = s_w + ((ky * KW + kx) * CK) * COP + g * CO_T;
 #pragma unroll
                 for (int c4 = 0; c4 < 2; ++c4) {
@@ -444,7 +449,9 @@ __global__ void __launch_bounds__(128) conv3x3_image_kernel(const float* __restr
                     *reinterpret_cast<float4*>(op + o4 * 4) = v;
                 }
             } else {
-                for (int i = 0; i < cout; ++i) op[i] = codd_act(acc[q][i], CODD_ACT_LEAKY, 0);
+#pragma unroll
+                for (int i = 0; i < CO; ++i)
+                    if (i < cout) op[i] = codd_act(acc[q][i], CODD_ACT_LEAKY, 0);
             }
         }
     }
@@ -453,14 +460,15 @@ __global__ void __launch_bounds__(128) conv3x3_image_kernel(const float* __restr
 // ---------------------------------------------------------------------------------------------
 // ConvTranspose2d k=2 s=2: every output pixel sees exactly one input pixel and one of 4 taps
 // ---------------------------------------------------------------------------------------------
+constexpr int DC_PX = 2;   // input pixels per thread: every weight broadcast (2 x LDS.128) feeds 2 x 2 x 2 packed FMAs
 template <int CO>
 __global__ void __launch_bounds__(128) deconv2x2_kernel(const float* __restrict__ in, int ldi, int n, int h,
                                                         int w, int cin, const float* __restrict__ wgt,
                                                         const float* __restrict__ bias, int cout,
                                                         float* __restrict__ out, int ldo, int act) {
-    // one thread per INPUT pixel and output-row parity dy: it produces the two output pixels
-    // (2y+dy, 2x) and (2y+dy, 2x+1); the input pixel is read once per dy, and every weight
-    // broadcast (warp-uniform: dy is the block's) feeds both outputs' channels.
+    // one thread per DC_PX horizontally adjacent INPUT pixels (x, x + 128) and output-row parity dy: per input pixel
+    // it produces the two output pixels (2y+dy, 2x) and (2y+dy, 2x+1); every weight broadcast (warp-uniform:
+    // dy is the block's) feeds both pixels' output channels.
     extern __shared__ float4 smem4[];
     float* s_w = reinterpret_cast<float*>(smem4);  // [4][cin][CO]
     for (int i = threadIdx.x; i < 4 * cin * CO; i += blockDim.x) {
@@ -468,51 +476,70 @@ __global__ void __launch_bounds__(128) deconv2x2_kernel(const float* __restrict_
         s_w[i] = co < cout ? wgt[(size_t)t * cout + co] : 0.f;
     }
     __syncthreads();
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int x0 = blockIdx.x * (blockDim.x * DC_PX) + threadIdx.x;
     const int oy = blockIdx.y;          // output row
     const int s = blockIdx.z;
-    if (x >= w) return;
+    if (x0 >= w) return;
     const int dy = oy & 1;
-    const float* ip = in + (((size_t)s * h + (oy >> 1)) * w + x) * ldi;
-    __align__(8) float acc[2][CO];
+    const float* ip[DC_PX];
 #pragma unroll
-    for (int q = 0; q < 2; ++q)
+    for (int q = 0; q < DC_PX; ++q)
+        ip[q] = in + (((size_t)s * h + (oy >> 1)) * w + min(x0 + q * (int)blockDim.x, w - 1)) * ldi;
+    __align__(8) float acc[DC_PX][2][CO];
 #pragma unroll
-        for (int i = 0; i < CO; ++i) acc[q][i] = 0.f;
+    for (int q = 0; q < DC_PX; ++q)
+#pragma unroll
+        for (int d = 0; d < 2; ++d)
+#pragma unroll
+            for (int i = 0; i < CO; ++i) acc[q][d][i] = 0.f;
     const float* w0 = s_w + (dy * 2 + 0) * cin * CO;
     const float* w1 = s_w + (dy * 2 + 1) * cin * CO;
     for (int ci = 0; ci < cin; ci += 4) {
-        const float4 a4 = ldg4(ip + ci);
+        float4 a4[DC_PX];
+#pragma unroll
+        for (int q = 0; q < DC_PX; ++q) a4[q] = ldg4(ip[q] + ci);
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
-            const float a = cc == 0 ? a4.x : cc == 1 ? a4.y : cc == 2 ? a4.z : a4.w;
 #pragma unroll
             for (int o4 = 0; o4 < CO / 4; ++o4) {
                 const float4 u = *reinterpret_cast<const float4*>(w0 + (ci + cc) * CO + o4 * 4);
                 const float4 v = *reinterpret_cast<const float4*>(w1 + (ci + cc) * CO + o4 * 4);
-                fma4(&acc[0][o4 * 4], a, u);
-                fma4(&acc[1][o4 * 4], a, v);
+#pragma unroll
+                for (int q = 0; q < DC_PX; ++q) {
+                    const float a = cc == 0 ? a4[q].x : cc == 1 ? a4[q].y : cc == 2 ? a4[q].z : a4[q].w;
+                    fma4(&acc[q][0][o4 * 4], a, u);
+                    fma4(&acc[q][1][o4 * 4], a, v);
+                }
             }
         }
     }
-    float* op = out + (((size_t)s * 2 * h + oy) * 2 * w + 2 * x) * ldo;
-    const bool vec = (ldo & 3) == 0 && (cout & 3) == 0 && ((((uintptr_t)out) & 15u) == 0);
+    const bool vec = (ldo & 3) == 0 && (cout & 3) == 0 && ((((uintptr_t)out) & 15u) == 0) && ((((uintptr_t)bias) & 15u) == 0);
     const ActSel asel = codd_act_sel(act);
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        if (vec) {
+    for (int q = 0; q < DC_PX; ++q) {
+        const int x = x0 + q * (int)blockDim.x;
+        if (x >= w) break;
+        float* op = out + (((size_t)s * 2 * h + oy) * 2 * w + 2 * x) * ldo;
 #pragma unroll
-            for (int o4 = 0; o4 < CO / 4; ++o4) {
-                if (o4 * 4 >= cout) break;
-                float4 r;
-                r.x = codd_act_apply(asel, acc[q][o4 * 4 + 0] + __ldg(bias + o4 * 4 + 0), o4 * 4 + 0);
-                r.y = codd_act_apply(asel, acc[q][o4 * 4 + 1] + __ldg(bias + o4 * 4 + 1), o4 * 4 + 1);
-                r.z = codd_act_apply(asel, acc[q][o4 * 4 + 2] + __ldg(bias + o4 * 4 + 2), o4 * 4 + 2);
-                r.w = codd_act_apply(asel, acc[q][o4 * 4 + 3] + __ldg(bias + o4 * 4 + 3), o4 * 4 + 3);
-                *reinterpret_cast<float4*>(op + q * ldo + o4 * 4) = r;
+        for (int d = 0; d < 2; ++d) {
+            if (vec && asel.simple) {
+#pragma unroll
+                for (int o4 = 0; o4 < CO / 4; ++o4) {
+                    if (o4 * 4 >= cout) break;
+                    const float4 b4 = ldg4(bias + o4 * 4);
+                    float4 r = make_float4(acc[q][d][o4 * 4] + b4.x, acc[q][d][o4 * 4 + 1] + b4.y,
+                                           acc[q][d][o4 * 4 + 2] + b4.z, acc[q][d][o4 * 4 + 3] + b4.w);
+                    r.x = fmaxf(r.x, 0.f) + (o4 == 0 ? asel.slope0 : asel.slope) * fminf(r.x, 0.f);
+                    r.y = fmaxf(r.y, 0.f) + asel.slope * fminf(r.y, 0.f);
+                    r.z = fmaxf(r.z, 0.f) + asel.slope * fminf(r.z, 0.f);
+                    r.w = fmaxf(r.w, 0.f) + asel.slope * fminf(r.w, 0.f);
+                    *reinterpret_cast<float4*>(op + d * ldo + o4 * 4) = r;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < CO; ++i)
+                    if (i < cout) op[d * ldo + i] = codd_act_apply(asel, acc[q][d][i] + __ldg(bias + i), i);
             }
-        } else {
-            for (int i = 0; i < cout; ++i) op[q * ldo + i] = codd_act_apply(asel, acc[q][i] + __ldg(bias + i), i);
         }
     }
 }
@@ -657,7 +684,7 @@ extern "C" int codd_deconv2x2_nhwc(const float* in, int ldi, int n, int h, int w
     if (cin % 4 != 0 || ldi % 4 != 0 || ldi < cin || ldo < cout || cout > 32) return CODD_E_SHAPE;
     if (!codd_aligned16(in)) return CODD_E_ALIGN;
     dim3 block(128);
-    dim3 grid(codd_ceil_div(w, 128), 2 * h, n);
+    dim3 grid(codd_ceil_div(w, 128 * DC_PX), 2 * h, n);
     cudaStream_t s = (cudaStream_t)stream;
     if (cout <= 16) {
         deconv2x2_kernel<16><<<grid, block, 4 * cin * 16 * sizeof(float), s>>>(in, ldi, n, h, w, cin, weight, bias,
