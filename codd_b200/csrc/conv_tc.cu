@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const __grid_
                         v[c] = fmaxf(v[c], 0.f) + sl * fminf(v[c], 0.f);
                     }
                 } else {
-#pragma unroll 1
+#pragma unroll
                     for (int c = 0; c < NP; ++c) v[c] = codd_act(v[c], p.act, c);
                 }
                 if (!(p.diag & 1)) {

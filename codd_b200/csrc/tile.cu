@@ -10,6 +10,8 @@
 // (see oracle/hitnet_oracle.py: warp_coords / warp_right_direct, which is bit-identical to
 // F.grid_sample on CPU): explicit __f*_rn intrinsics, no FMA contraction except where torch's own
 // kernel uses fused multiply-adds (the 4-tap blend).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "warp_sample.cuh"
 
@@ -112,6 +114,7 @@ struct WarpP {
     float* aug;
     int ldaug;
     float* raw;
+    int max_win;   // widest right-feature window (columns) worth staging in shared memory
 };
 
 constexpr int K4_TILES = 16;              // tile columns per CTA
@@ -122,14 +125,64 @@ constexpr int K4_THREADS = K4_PXW * 4;    // one thread per pixel of the 4-row s
 // pixels, so every per-channel tap load is a (nearly) contiguous 128-byte request — one L1
 // wavefront — where the NHWC layout costs 16 (lanes 64 B apart).  The left features stay NHWC:
 // each lane reads its own pixel's channels once.
+constexpr int K4_STAGE_BYTES = 92 * 1024;   // shared-memory budget of the staged right-feature window (2 CTAs / SM)
+
+// Channel loop of K4 on a STAGED window: the CTA's right-feature window (all taps of its 64 x 4 pixels) sits in shared
+// memory as [row][x][C + 4] (channel innermost, pitch C+4 floats => the 128-bit reads of 8 horizontally adjacent
+// lanes fall on 32 distinct banks), so one LDS.128 fetches 4 channels of a tap and the address is one 32-bit add —
+// versus one LDG + 64-bit address arithmetic per channel and tap on the gather path (k4_channels).  Same arithmetic,
+// same order: bit-identical results.
+template <int NSETS, bool TWO_ROWS>
+__device__ __forceinline__ void k4_channels_staged(const float* __restrict__ flp, const float* s_R, int C, int rowstep,
+                                                   const int (&offA)[NSETS][3], const int (&offB)[NSETS][3],
+                                                   const float (&wA)[NSETS][3], const float (&wB)[NSETS][3],
+                                                   const float (&wC)[NSETS][3], const float (&wD)[NSETS][3],
+                                                   float (&cost)[NSETS][3], float& lnorm) {
+    for (int c = 0; c < C; c += 4) {
+        const float4 l4 = ldg4(flp + c);
+        const float lv[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) lnorm = __fadd_rn(lnorm, fabsf(lv[cc]));
+#pragma unroll
+        for (int s = 0; s < NSETS; ++s)
+#pragma unroll
+            for (int ki = 0; ki < 3; ++ki) {
+                const float4 a4 = *reinterpret_cast<const float4*>(s_R + offA[s][ki] + c);
+                const float4 b4 = *reinterpret_cast<const float4*>(s_R + offB[s][ki] + c);
+                const float ta[4] = {a4.x, a4.y, a4.z, a4.w}, tb[4] = {b4.x, b4.y, b4.z, b4.w};
+                float ua[4], ub[4];
+                if (TWO_ROWS) {
+                    const float4 c4 = *reinterpret_cast<const float4*>(s_R + offA[s][ki] + rowstep + c);
+                    const float4 d4 = *reinterpret_cast<const float4*>(s_R + offB[s][ki] + rowstep + c);
+                    ua[0] = c4.x; ua[1] = c4.y; ua[2] = c4.z; ua[3] = c4.w;
+                    ub[0] = d4.x; ub[1] = d4.y; ub[2] = d4.z; ub[3] = d4.w;
+                }
+                float acc = cost[s][ki];
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    float v = __fmaf_rn(tb[cc], wB[s][ki], __fmul_rn(ta[cc], wA[s][ki]));
+                    if (TWO_ROWS) v = __fmaf_rn(ub[cc], wD[s][ki], __fmaf_rn(ua[cc], wC[s][ki], v));
+                    acc = __fadd_rn(acc, fabsf(__fsub_rn(lv[cc], v)));
+                }
+                cost[s][ki] = acc;
+            }
+    }
+}
+
 template <int NSETS>
 __global__ void __launch_bounds__(K4_THREADS, 2) tile_warp_cost_kernel(WarpP p) {
     __shared__ __align__(16) float s_raw[NSETS][K4_TILES][64];
     __shared__ __align__(16) float s_dec[NSETS][K4_TILES][16];
     __shared__ __align__(16) float s_wt[64][16];
     __shared__ float s_b[16];
+    __shared__ int s_rng[4];   // window of right-feature columns / rows touched by this CTA: xlo, xhi, rlo, rhi
+    extern __shared__ float4 k4_dyn[];
+    float* s_R = reinterpret_cast<float*>(k4_dyn);
 
     const int tid = threadIdx.x;
+    if (tid == 0) {
+        s_rng[0] = 0x7fffffff; s_rng[1] = -1; s_rng[2] = 0x7fffffff; s_rng[3] = -1;
+    }
     for (int i = tid; i < 64 * 16; i += K4_THREADS) {
         const int co = i & 15, ci = i >> 4;
         s_wt[ci][co] = __ldg(p.dec_w + co * 64 + ci);
@@ -152,6 +205,13 @@ __global__ void __launch_bounds__(K4_THREADS, 2) tile_warp_cost_kernel(WarpP p) 
     const int y = 4 * i + yo, x = 4 * j + xo;
     const bool on = j < p.w;
 
+    __syncthreads();   // s_rng initialised
+    // per-pixel sampling state (registers; computed before the CTA-wide window reduction)
+    float cost[NSETS][3];
+    float wA[NSETS][3], wB[NSETS][3], wC[NSETS][3], wD[NSETS][3];
+    int colA[NSETS][3], colB[NSETS][3];
+    bool paired = true, two_rows = false, row1_ok = false;
+    int y0 = 0;
     if (on) {
         const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
         const float wdiv = (float)max(W - 1, 1), hdiv = (float)max(H - 1, 1);
@@ -162,10 +222,9 @@ __global__ void __launch_bounds__(K4_THREADS, 2) tile_warp_cost_kernel(WarpP p) 
         const float fy = floorf(iy);
         const float fn = __fsub_rn(iy, fy);
         const float fs = __fsub_rn(1.f, fn);
-        const int y0 = min(max((int)fy, 0), H - 1);
-        const bool two_rows = fn != 0.f;                 // uniform per image row => per warp
-        const bool row1_ok = (y0 + 1 < H);
-        const int rowstep = row1_ok ? W : 0;             // invalid second row: any address, zero weight
+        y0 = min(max((int)fy, 0), H - 1);
+        two_rows = fn != 0.f;                 // uniform per image row => per warp
+        row1_ok = (y0 + 1 < H);
 
         const float a = (float)xo - 1.5f, bb = (float)yo - 1.5f;
         Taps tp[NSETS];
@@ -180,16 +239,7 @@ __global__ void __launch_bounds__(K4_THREADS, 2) tile_warp_cost_kernel(WarpP p) 
             const float du = __fmul_rn(__fadd_rn(__fadd_rn(q4.x, __fmul_rn(cx, q4.y)), __fmul_rn(cy, q4.z)), 2.f);
             sample_setup(du, q4.y, q4.z, a, bb, x, wm1, wdiv, wrcp, tp[NSETS - 1]);
         }
-
-        const float* flp = p.fl + (((size_t)n * H + y) * W + x) * p.ldfl;
-        const size_t cstride = (size_t)H * W;
-        const float* frn = p.fr + (size_t)n * p.C * cstride;
-        const int rowoff = y0 * W;
-
-        float cost[NSETS][3];
-        float wA[NSETS][3], wB[NSETS][3], wC[NSETS][3], wD[NSETS][3];
-        int offA[NSETS][3], offB[NSETS][3];
-        bool paired = true;
+        int xlo = 0x7fffffff, xhi = -1;
 #pragma unroll
         for (int s = 0; s < NSETS; ++s) {
 #pragma unroll
@@ -198,21 +248,80 @@ __global__ void __launch_bounds__(K4_THREADS, 2) tile_warp_cost_kernel(WarpP p) 
                 const int xa = tp[s].x0[ki];
                 const bool va = (xa >= 0 && xa < W), vb = (xa + 1 >= 0 && xa + 1 < W);
                 paired = paired && va && vb;
-                offA[s][ki] = rowoff + min(max(xa, 0), W - 1);
-                offB[s][ki] = rowoff + min(max(xa + 1, 0), W - 1);
+                colA[s][ki] = min(max(xa, 0), W - 1);
+                colB[s][ki] = min(max(xa + 1, 0), W - 1);
+                xlo = min(xlo, colA[s][ki]);
+                xhi = max(xhi, colB[s][ki]);
                 wA[s][ki] = va ? __fmul_rn(fs, tp[s].fe[ki]) : 0.f;
                 wB[s][ki] = vb ? __fmul_rn(fs, tp[s].fw[ki]) : 0.f;
                 wC[s][ki] = (va && row1_ok) ? __fmul_rn(fn, tp[s].fe[ki]) : 0.f;
                 wD[s][ki] = (vb && row1_ok) ? __fmul_rn(fn, tp[s].fw[ki]) : 0.f;
             }
         }
+        atomicMin(&s_rng[0], xlo);
+        atomicMax(&s_rng[1], xhi);
+        atomicMin(&s_rng[2], y0);
+        atomicMax(&s_rng[3], (two_rows && row1_ok) ? y0 + 1 : y0);
+    }
+    __syncthreads();
+    const int xlo = s_rng[0], rlo = s_rng[2];
+    const int wwin = s_rng[1] - xlo + 1, rwin = s_rng[3] - rlo + 1;
+    const int pitch = p.C + 4;
+    const bool staged = (s_rng[1] >= 0) && wwin <= p.max_win &&
+                        ((size_t)wwin * rwin * pitch * sizeof(float) <= (size_t)K4_STAGE_BYTES);
+    const size_t cstride = (size_t)H * W;
+    const float* frn = p.fr + (size_t)n * p.C * cstride;
+    if (staged) {
+        // planar global rows (coalesced along x) -> [row][x][C+4]: a warp takes one (4-channel group, row) segment at
+        // a time; every lane loads 4 channel planes at its column and writes them as one 128-bit store
+        const int nseg = (p.C >> 2) * rwin;
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int seg = warp; seg < nseg; seg += K4_THREADS / 32) {
+            const int c4 = seg / rwin, r = seg - c4 * rwin;
+            const float* src = frn + (size_t)(c4 * 4) * cstride + (size_t)(rlo + r) * W + xlo;
+            float* dst = s_R + (size_t)(r * wwin) * pitch + c4 * 4;
+            for (int xi = lane; xi < wwin; xi += 32) {
+                const float4 v = make_float4(__ldg(src + xi), __ldg(src + cstride + xi), __ldg(src + 2 * cstride + xi),
+                                             __ldg(src + 3 * cstride + xi));
+                *reinterpret_cast<float4*>(dst + (size_t)xi * pitch) = v;
+            }
+        }
+        __syncthreads();
+    }
+
+    if (on) {
+        const float* flp = p.fl + (((size_t)n * H + y) * W + x) * p.ldfl;
+        int offA[NSETS][3], offB[NSETS][3];
         float lnorm = 0.f;
-        if (paired) {
-            if (two_rows) k4_channels<NSETS, true, true>(flp, frn, cstride, p.C, rowstep, offA, offB, wA, wB, wC, wD, cost, lnorm);
-            else k4_channels<NSETS, false, true>(flp, frn, cstride, p.C, rowstep, offA, offB, wA, wB, wC, wD, cost, lnorm);
+        if (staged) {
+            const int rbase = (y0 - rlo) * wwin - xlo;
+#pragma unroll
+            for (int s = 0; s < NSETS; ++s)
+#pragma unroll
+                for (int ki = 0; ki < 3; ++ki) {
+                    offA[s][ki] = (rbase + colA[s][ki]) * pitch;
+                    offB[s][ki] = (rbase + colB[s][ki]) * pitch;
+                }
+            const int rowstep = row1_ok ? wwin * pitch : 0;
+            if (two_rows) k4_channels_staged<NSETS, true>(flp, s_R, p.C, rowstep, offA, offB, wA, wB, wC, wD, cost, lnorm);
+            else k4_channels_staged<NSETS, false>(flp, s_R, p.C, rowstep, offA, offB, wA, wB, wC, wD, cost, lnorm);
         } else {
-            if (two_rows) k4_channels<NSETS, true, false>(flp, frn, cstride, p.C, rowstep, offA, offB, wA, wB, wC, wD, cost, lnorm);
-            else k4_channels<NSETS, false, false>(flp, frn, cstride, p.C, rowstep, offA, offB, wA, wB, wC, wD, cost, lnorm);
+            const int rowoff = y0 * W;
+            const int rowstep = row1_ok ? W : 0;             // invalid second row: any address, zero weight
+#pragma unroll
+            for (int s = 0; s < NSETS; ++s)
+#pragma unroll
+                for (int ki = 0; ki < 3; ++ki) {
+                    offA[s][ki] = rowoff + colA[s][ki];
+                    offB[s][ki] = rowoff + colB[s][ki];
+                }
+            if (paired) {
+                if (two_rows) k4_channels<NSETS, true, true>(flp, frn, cstride, p.C, rowstep, offA, offB, wA, wB, wC, wD, cost, lnorm);
+                else k4_channels<NSETS, false, true>(flp, frn, cstride, p.C, rowstep, offA, offB, wA, wB, wC, wD, cost, lnorm);
+            } else {
+                if (two_rows) k4_channels<NSETS, true, false>(flp, frn, cstride, p.C, rowstep, offA, offB, wA, wB, wC, wD, cost, lnorm);
+                else k4_channels<NSETS, false, false>(flp, frn, cstride, p.C, rowstep, offA, offB, wA, wB, wC, wD, cost, lnorm);
+            }
         }
         const int po = yo * 4 + xo;
 #pragma unroll
@@ -347,10 +456,20 @@ extern "C" int codd_tile_warp_cost(const float* fea_l, int ldfl, const float* fe
     p.cur = cur; p.ldc = ldc; p.prev = prev; p.ldp = ldp;
     p.dec_w = dec_w; p.dec_b = dec_b; p.N = n; p.h = h; p.w = w;
     p.aug = aug; p.ldaug = ldaug; p.raw = raw_cv;
+    static const int max_win = getenv("CODD_K4_MAXWIN") ? atoi(getenv("CODD_K4_MAXWIN")) : 4096;
+    p.max_win = max_win;
     const int nblk = codd_ceil_div(w, K4_TILES);
     dim3 grid((unsigned)(n * h * nblk)), block(K4_THREADS);
-    if (prev) tile_warp_cost_kernel<2><<<grid, block, 0, (cudaStream_t)stream>>>(p);
-    else tile_warp_cost_kernel<1><<<grid, block, 0, (cudaStream_t)stream>>>(p);
+    static bool configured = false;   // set once so graph capture sees no API calls
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tile_warp_cost_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, K4_STAGE_BYTES);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(tile_warp_cost_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, K4_STAGE_BYTES);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    if (prev) tile_warp_cost_kernel<2><<<grid, block, K4_STAGE_BYTES, (cudaStream_t)stream>>>(p);
+    else tile_warp_cost_kernel<1><<<grid, block, K4_STAGE_BYTES, (cudaStream_t)stream>>>(p);
     CODD_RETURN_IF_CUDA_ERROR();
     return 0;
 }

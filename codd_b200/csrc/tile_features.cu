@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(TF_THREADS) tile_features_kernel(TfP p) {
         const float* rowp = p.in + ((size_t)n * p.H + gy) * p.W * p.ldi;
         for (int c0 = 0; c0 < p.Cin; c0 += TF_CK) {
             __syncthreads();
+#pragma unroll 2
             for (int idx = t; idx < ICOLS * 2; idx += TF_THREADS) {
                 const int c4 = idx & 1, col = idx >> 1;
                 const int gx = ix0 + col;
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(TF_THREADS) tile_features_kernel(TfP p) {
                 if (gx < p.W && c0 + c4 * 4 < p.Cin) v = ldg4(rowp + (size_t)gx * p.ldi + c0 + c4 * 4);
                 *reinterpret_cast<float4*>(s_in + col * TF_CP + c4 * 4) = v;
             }
+#pragma unroll 2
             for (int idx = t; idx < 4 * TF_CK * 16; idx += TF_THREADS) {
                 const int co = idx & 15, ci = (idx >> 4) % TF_CK, kx = idx / (16 * TF_CK);
                 float v = 0.f;
@@ -111,29 +113,35 @@ __global__ void __launch_bounds__(TF_THREADS) tile_features_kernel(TfP p) {
         }
     }
 
-    // ---- LeakyReLU, 1x1 conv, LeakyReLU, planar store
+    // ---- LeakyReLU, 1x1 conv, LeakyReLU, planar store.  The weight loop is OUTERMOST: one broadcast of a w1 row
+    // feeds all NOUT columns (with the column loop outside, the compiler kept all 256 weights live in registers
+    // to share them between columns: 255 registers + spills).
     const size_t plane = (size_t)p.h * p.Wo;
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o)
+#pragma unroll
+        for (int c = 0; c < 16; ++c) acc[o][c] = codd_act(acc[o][c] + s_b0[c], CODD_ACT_LEAKY, 0);   // hidden
+    __align__(8) float outv[NOUT][16];
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o)
+#pragma unroll
+        for (int c = 0; c < 16; ++c) outv[o][c] = s_b1[c];
+#pragma unroll
+    for (int hh = 0; hh < 16; ++hh) {
+#pragma unroll
+        for (int o4 = 0; o4 < 4; ++o4) {
+            const float4 wv = *reinterpret_cast<const float4*>(&s_w1[hh][o4 * 4]);
+#pragma unroll
+            for (int o = 0; o < NOUT; ++o) fma4(&outv[o][o4 * 4], acc[o][hh], wv);
+        }
+    }
 #pragma unroll
     for (int o = 0; o < NOUT; ++o) {
         const int xo = xblk + t + TF_THREADS * o;
-        float hid[16];
-#pragma unroll
-        for (int c = 0; c < 16; ++c) hid[c] = codd_act(acc[o][c] + s_b0[c], CODD_ACT_LEAKY, 0);
-        __align__(8) float outv[16];
-#pragma unroll
-        for (int c = 0; c < 16; ++c) outv[c] = s_b1[c];
-#pragma unroll
-        for (int hh = 0; hh < 16; ++hh) {
-#pragma unroll
-            for (int o4 = 0; o4 < 4; ++o4) {
-                const float4 wv = *reinterpret_cast<const float4*>(&s_w1[hh][o4 * 4]);
-                fma4(&outv[o4 * 4], hid[hh], wv);
-            }
-        }
         if (xo < p.Wo) {
             float* op = p.out + ((size_t)n * 16 * p.h + i) * p.Wo + xo;
 #pragma unroll
-            for (int c = 0; c < 16; ++c) op[(size_t)c * plane] = codd_act(outv[c], CODD_ACT_LEAKY, 0);
+            for (int c = 0; c < 16; ++c) op[(size_t)c * plane] = codd_act(outv[o][c], CODD_ACT_LEAKY, 0);
         }
     }
 }
