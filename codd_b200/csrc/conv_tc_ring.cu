@@ -1,0 +1,489 @@
+// 3x3 / stride 1 / pad 1 convolution on tcgen05 — "rolling ring" formulation.
+//
+// Same math, precision (3xTF32) and epilogue as conv_tc.cu, different dataflow.  conv_tc.cu is bound by the
+// shared-memory reads of the A operand: every (tap, k-step, pass) MMA re-reads a 4 KB activation slice for only
+// N = 2*Cout <= 64 output columns (ncu: sm__pipe_tc_cycles_active 82 %, tensor math 20 %).  Here the three ky taps
+// are folded into N:
+//
+//   * a CTA walks a vertical strip (128 output columns x SEG rows) top to bottom, ONE staged input row at a time
+//     (one-row TMA boxes of 130 pixels, OOB = zero fill = padding): every input row is loaded, split and read by
+//     the tensor core exactly once per strip — no 2x halo re-load;
+//   * staged row yi contributes tap ky to output row yi+1-ky, so ONE MMA per (kx, k-step) multiplies the row by
+//     B = [W(ky=0,kx) | W(ky=1,kx) | W(ky=2,kx)]  (N = 3 * 2*Cout) and accumulates into THREE output rows at once;
+//   * the output-row accumulators form a ring of TMEM slots (slot index descends with the row, so the three target
+//     slots are adjacent columns); a row is complete two staged rows later and is drained by the epilogue warps
+//     while the MMAs continue on the following slots.
+// Per output row and 128 pixels the tensor core now reads 12 A slices (Cin=16) instead of 36, B grows from 0.5-1 KB
+// to 3 KB per MMA: 84 KB instead of 162 KB of operand traffic, and the stage is written / split once instead of twice.
+//
+// 3xTF32: pass A multiplies the raw fp32 row (the MMA reads the top 19 bits = x_hi) by [w_hi | w_lo] per tap, the
+// split warps then overwrite the row with x_lo = x - x_hi in place and pass B multiplies it by [w_hi | 0].
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int RG_TW = 128;              // output columns per strip (= MMA M)
+constexpr int RG_BOXW = RG_TW + 2;      // staged pixels per row
+constexpr int RG_EPI_THREADS = 128;
+constexpr int RG_SPLIT_THREADS = 256;
+constexpr int RG_THREADS = 64 + RG_EPI_THREADS + RG_SPLIT_THREADS;   // warps 0-7 split, 8-11 epilogue, 12 TMA, 13 MMA
+
+struct RgP {
+    const float* wpk;   // [2 pass][3 kx][6*NP rows][KC]: pass 0 rows per ky = [w_hi | w_lo], pass 1 = [w_hi | 0]
+    const float* bias;
+    const float* res;
+    float* out;
+    int N, H, W, Cout, ldo, ldr, res_bcast, act;
+    int tilesX, nseg, seg, nitems;
+};
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!done) __nanosleep(32);
+    }
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.u32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+        "[%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major swizzled shared-memory matrix descriptor (same encoding as conv_tc.cu: base-offset field 0, the swizzle is
+// a function of the shared-memory address, so shifted start addresses address shifted windows of the same tile)
+template <int KC>
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    constexpr uint32_t ROWB = KC * 4;
+    constexpr uint64_t LAYOUT = (KC == 32) ? 2ull : 4ull;   // SWIZZLE_128B : SWIZZLE_64B
+    constexpr uint32_t SBO = 8 * ROWB;
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(SBO >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= LAYOUT << 61;
+    return d;
+}
+template <int KC>
+__device__ __forceinline__ uint32_t swz_off(int r, int j) {
+    constexpr uint32_t ROWB = KC * 4;
+    const uint32_t off = (uint32_t)r * ROWB + (uint32_t)j * 16u;
+    constexpr uint32_t MASK = (KC == 32) ? 7u : 3u;
+    return off ^ (((off >> 7) & MASK) << 4);
+}
+__device__ __forceinline__ float tf32_lo(float x) {
+    return __fsub_rn(x, __uint_as_float(__float_as_uint(x) & 0xFFFFE000u));
+}
+
+// Cursor over the staged rows a CTA processes: items (sample, column strip, row segment) in grid-stride order, and
+// inside an item the rows t = 0 .. rows+1 (image rows y0-1 .. y0+rows).  Every warp role runs its own copy.
+struct Cursor {
+    int item, t, rows, y0, x0, n;
+    int orow0;   // running output-row counter of this CTA at the item's first output row (ring slot = f(orow))
+    int g;       // running staged-row counter of this CTA (stage buffer = g % NBUF)
+    __device__ __forceinline__ void load(const RgP& p) {
+        if (item >= p.nitems) return;
+        int q = item;
+        const int sg = q % p.nseg;
+        q /= p.nseg;
+        const int tx = q % p.tilesX;
+        n = q / p.tilesX;
+        x0 = tx * RG_TW;
+        y0 = sg * p.seg;
+        rows = min(p.seg, p.H - y0);
+    }
+    __device__ __forceinline__ void init(const RgP& p) {
+        item = blockIdx.x; t = 0; orow0 = 0; g = 0;
+        load(p);
+    }
+    __device__ __forceinline__ bool valid(const RgP& p) const { return item < p.nitems; }
+    __device__ __forceinline__ void next(const RgP& p) {
+        ++g;
+        if (++t == rows + 2) {
+            t = 0;
+            orow0 += rows;
+            item += gridDim.x;
+            load(p);
+        }
+    }
+};
+
+template <int KC, int NP, int NBUF, int LAG>
+__global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __grid_constant__ CUtensorMap tmap, RgP p) {
+    constexpr int SLOT = 2 * NP;                 // TMEM columns of one output row: [hi NP | lo NP]
+    constexpr int RING = 512 / SLOT;             // 16 (NP = 16) or 8 (NP = 32) output rows in flight
+    constexpr uint32_t ROWB = KC * 4;
+    constexpr uint32_t A_BYTES = RG_BOXW * ROWB;
+    constexpr uint32_t A_STRIDE = (A_BYTES + 1023u) & ~1023u;
+    constexpr uint32_t WBLK = 6 * NP * ROWB;     // one (pass, kx) weight block: 3 ky x [2*NP rows]
+    constexpr int KS = KC / 8;
+    constexpr uint32_t IDESC_BASE = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 4) << 24);
+    static_assert(NBUF >= LAG + 2, "stage depth");
+
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) unsigned long long bars[4 * NBUF + 2 * RING];
+    __shared__ uint32_t tmem_base_slot;
+
+    const uint32_t sbase = (s_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gbase = smem_raw + (sbase - s_u32(smem_raw));
+    const uint32_t sB = sbase + NBUF * A_STRIDE;
+    uint8_t* gB = gbase + NBUF * A_STRIDE;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t bar0 = s_u32(&bars[0]);
+    auto SBAR = [&](int kind, int b) { return bar0 + (uint32_t)(kind * NBUF + b) * 8u; };
+    auto ABAR = [&](int kind, int b) { return bar0 + (uint32_t)(4 * NBUF + kind * RING + b) * 8u; };
+    enum { FULL = 0, EMPTY = 1, P12 = 2, LO = 3 };
+    enum { ACCF = 0, ACCE = 1 };
+
+    if (tid == 0) {
+        for (int b = 0; b < NBUF; ++b) {
+            mbar_init(SBAR(FULL, b), 1);
+            mbar_init(SBAR(EMPTY, b), 1);
+            mbar_init(SBAR(P12, b), 1);
+            mbar_init(SBAR(LO, b), RG_SPLIT_THREADS);
+        }
+        for (int b = 0; b < RING; ++b) {
+            mbar_init(ABAR(ACCF, b), 1);
+            mbar_init(ABAR(ACCE, b), RG_EPI_THREADS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 13) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&tmem_base_slot)),
+                     "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    // weights -> swizzled shared image: 6 blocks (pass, kx) of 6*NP rows
+    for (int idx = tid; idx < 6 * 6 * NP * (KC / 4); idx += RG_THREADS) {
+        const int j = idx % (KC / 4);
+        const int r = (idx / (KC / 4)) % (6 * NP);
+        const int blk = idx / ((KC / 4) * 6 * NP);
+        const float4 v = ldg4(p.wpk + ((size_t)blk * 6 * NP + r) * KC + j * 4);
+        *reinterpret_cast<float4*>(gB + blk * WBLK + swz_off<KC>(r, j)) = v;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_slot;
+
+    if (warp == 12) {
+        // ===================== TMA producer: one staged row per step =====================
+        if (lane == 0) {
+            Cursor c;
+            for (c.init(p); c.valid(p); c.next(p)) {
+                const int sb = c.g % NBUF;
+                mbar_wait(SBAR(EMPTY, sb), (((uint32_t)(c.g / NBUF)) & 1u) ^ 1u);
+                mbar_expect_tx(SBAR(FULL, sb), A_BYTES);
+                const int cx = c.x0 - 1, cy = c.y0 - 1 + c.t;
+                asm volatile(
+                    "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+                    "%6}], [%2];" ::"r"(sbase + sb * A_STRIDE),
+                    "l"(&tmap), "r"(SBAR(FULL, sb)), "r"(0), "r"(cx), "r"(cy), "r"(c.n)
+                    : "memory");
+            }
+        }
+    } else if (warp == 13) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            // one pass over one staged row: for every (kx, k-step) the row is multiplied by the weight blocks of the
+            // valid ky taps; consecutive ring slots are covered by one MMA (N = 2NP, 4NP or 6NP)
+            auto issue = [&](const Cursor& c, int pass) {
+                const int sb = c.g % NBUF;
+                const uint64_t a_desc = make_desc<KC>(sbase + sb * A_STRIDE);
+                const int kylo = max(0, c.t - c.rows + 1), kyhi = min(2, c.t);   // output row = y0 + t - ky inside the item
+                // runs of adjacent slots: slot(orow) = RING-1 - (orow % RING); ky ascending <=> orow descending <=> slot ascending
+                int run_ky[3], run_n[3], run_slot[3], nrun = 0;
+                for (int ky = kylo; ky <= kyhi; ++ky) {
+                    const int orow = c.orow0 + c.t - ky;
+                    const int slot = RING - 1 - (orow % RING);
+                    if (nrun > 0 && run_slot[nrun - 1] + run_n[nrun - 1] == slot) {
+                        ++run_n[nrun - 1];
+                    } else {
+                        run_ky[nrun] = ky; run_n[nrun] = 1; run_slot[nrun] = slot;
+                        ++nrun;
+                    }
+                }
+                const bool has_fresh = (pass == 0 && kylo == 0);   // ky = 0 is the FIRST contribution to its output row
+                if (has_fresh) {
+                    // the fresh slot is about to be overwritten: its previous row must have been drained
+                    const int orow = c.orow0 + c.t;
+                    const int slot = RING - 1 - (orow % RING);
+                    mbar_wait(ABAR(ACCE, slot), (((uint32_t)(orow / RING)) & 1u) ^ 1u);
+                    tc_fence_after();
+                }
+                const uint32_t wbase = sB + (uint32_t)(pass * 3) * WBLK;
+#pragma unroll 1
+                for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll 1
+                    for (int k = 0; k < KS; ++k) {
+                        const uint64_t a_k = a_desc + (((uint32_t)kx * ROWB + (uint32_t)k * 32u) >> 4);
+                        for (int r = 0; r < nrun; ++r) {
+                            int ky0 = run_ky[r], nk = run_n[r], slot = run_slot[r];
+                            if (has_fresh && kx == 0 && k == 0 && ky0 == 0) {
+                                // the very first MMA of a fresh output row overwrites its slot (N = one slot) ...
+                                const uint64_t b_f = make_desc<KC>(wbase + (uint32_t)k * 32u);
+                                tc_mma_tf32(tmem + (uint32_t)(slot * SLOT), a_k, b_f, IDESC_BASE | ((uint32_t)(SLOT >> 3) << 17), 0u);
+                                ++ky0; --nk; ++slot;          // ... the rest of the run accumulates as usual
+                                if (nk == 0) continue;
+                            }
+                            const uint32_t boff = (uint32_t)kx * WBLK + (uint32_t)ky0 * (SLOT * ROWB) + (uint32_t)k * 32u;
+                            const uint64_t b_k = make_desc<KC>(wbase + boff);
+                            const uint32_t idesc = IDESC_BASE | ((uint32_t)((nk * SLOT) >> 3) << 17);
+                            tc_mma_tf32(tmem + (uint32_t)(slot * SLOT), a_k, b_k, idesc, 1u);
+                        }
+                    }
+                }
+            };
+            Cursor ca, cb;     // pass A cursor, pass B cursor (LAG rows behind)
+            ca.init(p);
+            cb.init(p);
+            auto pass_b = [&]() {
+                const int sb = cb.g % NBUF;
+                mbar_wait(SBAR(LO, sb), ((uint32_t)(cb.g / NBUF)) & 1u);
+                tc_fence_after();
+                issue(cb, 1);
+                tc_commit(SBAR(EMPTY, sb));                       // stage buffer free -> producer
+                if (cb.t >= 2) {                                  // output row y0 + t - 2 is complete
+                    const int orow = cb.orow0 + cb.t - 2;
+                    tc_commit(ABAR(ACCF, RING - 1 - (orow % RING)));
+                }
+                cb.next(p);
+            };
+            for (; ca.valid(p); ca.next(p)) {
+                const int sb = ca.g % NBUF;
+                mbar_wait(SBAR(FULL, sb), ((uint32_t)(ca.g / NBUF)) & 1u);
+                tc_fence_after();
+                issue(ca, 0);
+                tc_commit(SBAR(P12, sb));                         // raw row consumed -> split warps
+                if (ca.g >= LAG) pass_b();
+            }
+            while (cb.valid(p)) pass_b();
+        }
+    } else if (warp >= 8) {
+        // ===================== epilogue (warps 8-11): one output row per step =====================
+        const int quarter = warp & 3;
+        const float slope = p.act == CODD_ACT_LEAKY ? CODD_LEAKY_SLOPE : (p.act == CODD_ACT_RELU ? 0.f : 1.f);
+        const float slope0 = (p.act == CODD_ACT_RELU || p.act == CODD_ACT_RELU_CH0) ? 0.f : slope;
+        const bool full_vec = (p.Cout == NP) && ((p.ldo & 3) == 0) && ((((uintptr_t)p.out) & 15u) == 0);
+        const bool res_vec = p.res && !p.res_bcast && (p.Cout == NP) && ((p.ldr & 3) == 0) &&
+                             ((((uintptr_t)p.res) & 15u) == 0);
+        float biasr[NP];
+#pragma unroll
+        for (int c = 0; c < NP; ++c) biasr[c] = (p.bias && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
+        int orow = 0;
+        for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+            int q = item;
+            const int sg = q % p.nseg;
+            q /= p.nseg;
+            const int tx = q % p.tilesX;
+            const int n = q / p.tilesX;
+            const int y0 = sg * p.seg;
+            const int rows = min(p.seg, p.H - y0);
+            const int x = tx * RG_TW + quarter * 32 + lane;
+            for (int r = 0; r < rows; ++r, ++orow) {
+                const int slot = RING - 1 - (orow % RING);
+                mbar_wait(ABAR(ACCF, slot), ((uint32_t)(orow / RING)) & 1u);
+                tc_fence_after();
+                float acc[SLOT];
+#pragma unroll
+                for (int c = 0; c < SLOT; c += 16)
+                    tc_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * SLOT + c), &acc[c]);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                mbar_arrive(ABAR(ACCE, slot));
+                const int y = y0 + r;
+                if (x >= p.W) continue;
+                const size_t opix = ((size_t)n * p.H + y) * p.W + x;
+                float* op = p.out + opix * p.ldo;
+                float v[NP];
+#pragma unroll
+                for (int c = 0; c < NP; ++c) v[c] = (acc[c] + acc[NP + c]) + biasr[c];
+                if (p.res) {
+                    const float* rp = p.res + opix * p.ldr;
+                    if (p.res_bcast) {
+                        const float rb = __ldg(rp);
+#pragma unroll
+                        for (int c = 0; c < NP; ++c) v[c] += rb;
+                    } else if (res_vec) {
+#pragma unroll
+                        for (int c4 = 0; c4 < NP; c4 += 4) {
+                            const float4 r4 = ldg4(rp + c4);
+                            v[c4] += r4.x; v[c4 + 1] += r4.y; v[c4 + 2] += r4.z; v[c4 + 3] += r4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < NP; ++c)
+                            if (c < p.Cout) v[c] += __ldg(rp + c);
+                    }
+                }
+                if (p.act <= CODD_ACT_RELU_CH0) {
+#pragma unroll
+                    for (int c = 0; c < NP; ++c) {
+                        const float sl = c == 0 ? slope0 : slope;
+                        v[c] = fmaxf(v[c], 0.f) + sl * fminf(v[c], 0.f);
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < NP; ++c) v[c] = codd_act(v[c], p.act, c);
+                }
+                if (full_vec) {
+#pragma unroll
+                    for (int c4 = 0; c4 < NP; c4 += 4)
+                        *reinterpret_cast<float4*>(op + c4) = make_float4(v[c4], v[c4 + 1], v[c4 + 2], v[c4 + 3]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < NP; ++c)
+                        if (c < p.Cout) op[c] = v[c];
+                }
+            }
+        }
+    } else {
+        // ===================== in-place hi/lo split of a staged row (warps 0-7) =====================
+        Cursor c;
+        for (c.init(p); c.valid(p); c.next(p)) {
+            const int sb = c.g % NBUF;
+            mbar_wait(SBAR(P12, sb), ((uint32_t)(c.g / NBUF)) & 1u);   // pass A has consumed the raw row
+            tc_fence_after();
+            float4* a4 = reinterpret_cast<float4*>(gbase + sb * A_STRIDE);
+            for (int idx = tid; idx < (int)(A_BYTES / 16); idx += RG_SPLIT_THREADS) {
+                float4 v = a4[idx];
+                v.x = tf32_lo(v.x); v.y = tf32_lo(v.y); v.z = tf32_lo(v.z); v.w = tf32_lo(v.w);
+                a4[idx] = v;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(SBAR(LO, sb));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 13) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+    }
+}
+
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_tmapEncodeTiled rg_get_encode() {
+    static PFN_tmapEncodeTiled fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (PFN_tmapEncodeTiled)ptr;
+    }
+    return fn;
+}
+
+template <int KC, int NP, int NBUF, int LAG>
+int launch_ring(const CUtensorMap& tmap, RgP p, cudaStream_t s) {
+    constexpr uint32_t ROWB = KC * 4;
+    constexpr uint32_t A_STRIDE = ((RG_BOXW * ROWB) + 1023u) & ~1023u;
+    constexpr uint32_t B_BYTES = 6 * 6 * NP * ROWB;
+    const size_t smem = NBUF * A_STRIDE + B_BYTES + 1024;
+    auto kern = conv3x3_tc_ring_kernel<KC, NP, NBUF, LAG>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // row segments: as long as possible (the 2 halo rows of a segment are its only overhead) while giving every SM
+    // several items; pick the segment length with the best (work / (rounds * segment cost)) balance
+    const int strips = p.N * p.tilesX;
+    int best_seg = p.H;
+    double best = -1.0;
+    for (int nseg = 1; nseg <= p.H && nseg <= 64; ++nseg) {
+        const int seg = codd_ceil_div(p.H, nseg);
+        if (seg < 8 && nseg > 1) break;
+        const int items = strips * codd_ceil_div(p.H, seg);
+        const int rounds = codd_ceil_div(items, sms);
+        const double eff = ((double)strips * p.H) / ((double)rounds * sms * (seg + 2));
+        if (eff > best + 1e-9) { best = eff; best_seg = seg; }
+    }
+    p.seg = best_seg;
+    p.nseg = codd_ceil_div(p.H, p.seg);
+    p.nitems = strips * p.nseg;
+    const int grid = p.nitems < sms ? p.nitems : sms;
+    kern<<<grid, RG_THREADS, smem, s>>>(tmap, p);
+    CODD_RETURN_IF_CUDA_ERROR();
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int codd_conv3x3_tc_ring(const float* in, int ldi, int cin, int n, int h, int w, const float* weight_ring,
+                                    const float* bias, const float* residual, int ldr, int res_bcast, int cout, int act,
+                                    float* out, int ldo, void* stream) {
+    if (!in || !weight_ring || !out || n <= 0 || h <= 0 || w <= 0 || cin <= 0 || cout <= 0) return CODD_E_BADARG;
+    if (cin > 32 || cout > 32 || cin % 4 != 0 || ldi % 4 != 0 || ldi < cin || ldo < cout) return CODD_E_SHAPE;
+    if (!codd_aligned16(in)) return CODD_E_ALIGN;
+    PFN_tmapEncodeTiled enc = rg_get_encode();
+    if (!enc) return CODD_E_UNSUPPORTED;
+    const int KC = cin <= 16 ? 16 : 32;
+    const int NP = cout <= 16 ? 16 : 32;
+    if (KC == 16 && NP == 32) return CODD_E_UNSUPPORTED;
+    CUtensorMap tmap;
+    const cuuint64_t gdim[4] = {(cuuint64_t)cin, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+    const cuuint64_t gstr[3] = {(cuuint64_t)ldi * 4, (cuuint64_t)w * ldi * 4, (cuuint64_t)h * w * ldi * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)RG_BOXW, 1u, 1u};
+    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)in, gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, KC == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return CODD_E_SHAPE;
+    RgP p;
+    p.wpk = weight_ring; p.bias = bias; p.res = residual; p.out = out;
+    p.N = n; p.H = h; p.W = w; p.Cout = cout; p.ldo = ldo; p.ldr = ldr; p.res_bcast = res_bcast; p.act = act;
+    p.tilesX = codd_ceil_div(w, RG_TW);
+    p.nseg = p.seg = p.nitems = 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (KC == 32 && NP == 32) return launch_ring<32, 32, 4, 2>(tmap, p, s);
+    if (KC == 32 && NP == 16) return launch_ring<32, 16, 4, 2>(tmap, p, s);
+    return launch_ring<16, 16, 6, 2>(tmap, p, s);
+}

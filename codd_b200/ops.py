@@ -167,6 +167,39 @@ def pack_conv_weight_tc(w):
     return torch.stack([hi, lo]).contiguous()
 
 
+def pack_conv_weight_ring(w):
+    """torch [Cout,Cin,3,3] -> [2 pass][3 kx][6*NP][KC] for codd_conv3x3_tc_ring: per (pass, kx) block the rows are,
+    for ky = 0,1,2, [w_hi (NP) | w_lo (NP)] (pass 0) or [w_hi (NP) | 0 (NP)] (pass 1)."""
+    cout, cin, kh, kw = w.shape
+    assert kh == 3 and kw == 3
+    kc = 16 if cin <= 16 else 32
+    npad = 16 if cout <= 16 else 32
+    wt = torch.zeros((3, 3, npad, kc), dtype=torch.float32, device=w.device)            # [ky][kx][cout][cin]
+    wt[:, :, :cout, :cin] = w.detach().float().permute(2, 3, 0, 1)
+    hi = _tf32_round(wt)
+    lo = _tf32_round(wt - hi)
+    out = torch.zeros((2, 3, 3, 2, npad, kc), dtype=torch.float32, device=w.device)     # [pass][kx][ky][hi|lo][cout][cin]
+    out[0, :, :, 0] = hi.permute(1, 0, 2, 3)
+    out[0, :, :, 1] = lo.permute(1, 0, 2, 3)
+    out[1, :, :, 0] = hi.permute(1, 0, 2, 3)
+    return out.reshape(2, 3, 6 * npad, kc).contiguous()
+
+
+def conv3x3_tc_ring(x, wring, bias, cout, act=ACT_NONE, residual=None, res_bcast=False):
+    """3x3 s1 p1 conv on the tensor cores, rolling-ring kernel (3xTF32).  ``wring`` from pack_conv_weight_ring."""
+    _require_cuda(x, wring, bias, residual)
+    n, cin, h, w = x.shape
+    out = empty_nhwc(n, cout, h, w, x.device)
+    nbytes = 4 * (n * h * w * (cin + cout) + wring.numel() // 4
+                  + (0 if residual is None else n * h * w * (1 if res_bcast else cout)))
+    rc = _run(f"conv3x3ring_cin{cin}_cout{cout}", nbytes, lambda: _lib.load().codd_conv3x3_tc_ring(
+        x.data_ptr(), ld_of(x), cin, n, h, w, wring.data_ptr(), None if bias is None else bias.data_ptr(),
+        None if residual is None else residual.data_ptr(), 0 if residual is None else ld_of(residual),
+        1 if res_bcast else 0, cout, act, out.data_ptr(), ld_of(out), _stream()))
+    _lib.check(rc, f"codd_conv3x3_tc_ring(cin={cin}, cout={cout})")
+    return out
+
+
 def tc_eligible(cin, cout, k, stride, pad, dil, x2):
     kh, kw = (k, k) if isinstance(k, int) else k
     sh, sw = (stride, stride) if isinstance(stride, int) else stride

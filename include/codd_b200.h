@@ -97,6 +97,15 @@ CODD_API int codd_conv3x3_tc_dil(const float* in, int ldi, int cin, int n, int h
                                  int res_bcast, int cout, int act, float* out, int ldo, int dil, int flags,
                                  void* stream);
 
+/* Rolling-ring formulation of the same 3x3 / stride 1 / pad 1 tensor-core convolution (csrc/conv_tc_ring.cu): a CTA
+ * walks a 128-column strip one staged input row at a time and ONE MMA per (kx, k-step) accumulates into the three
+ * output rows a staged row contributes to (N = 3 * 2*Cout; accumulators = a ring of TMEM slots).  Same shapes as
+ * codd_conv3x3_tc (dilation 1).  weight_ring is [2 pass][3 kx][6*NP rows][KC] fp32 (host: ops.pack_conv_weight_ring):
+ * rows of a (pass, kx) block are, per ky = 0,1,2:  pass 0 -> [w_hi (NP) | w_lo (NP)],  pass 1 -> [w_hi (NP) | 0]. */
+CODD_API int codd_conv3x3_tc_ring(const float* in, int ldi, int cin, int n, int h, int w, const float* weight_ring,
+                                  const float* bias, const float* residual, int ldr, int res_bcast, int cout, int act,
+                                  float* out, int ldo, void* stream);
+
 /* Diagnostic: device buffer [grid][8] of int64 cycle counters filled by later codd_conv3x3_tc launches. */
 CODD_API int codd_conv3x3_tc_debug(long long* dbg);
 

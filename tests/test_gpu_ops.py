@@ -325,6 +325,28 @@ def test_conv3x3_tensor_core(ops, cin, cout, h, w):
     torch.testing.assert_close(back(ops, out), ref, rtol=CONV_RTOL, atol=CONV_ATOL)
 
 
+RING_CASES = [(16, 16, 1, 100), (16, 16, 2, 128), (16, 16, 3, 129), (16, 16, 40, 300), (32, 32, 5, 200), (32, 32, 23, 260),
+              (24, 24, 9, 130), (32, 16, 6, 128), (16, 3, 17, 100), (16, 1, 4, 260), (32, 24, 3, 60), (16, 16, 70, 64)]
+
+
+@pytest.mark.parametrize("cin,cout,h,w", RING_CASES)
+def test_conv3x3_tensor_core_ring(ops, cin, cout, h, w):
+    """Rolling-ring tcgen05 kernel: same bar as the other convolutions (3xTF32 must be fp32-class)."""
+    from codd_b200.lib import ACT_LEAKY
+    g = gen(cin * 1000 + cout * 10 + h)
+    x = torch.randn(3, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5
+    b = torch.randn(cout, generator=g)
+    res = torch.randn(3, cout, h, w, generator=g)
+    ref = F.leaky_relu(F.conv2d(x, wt, b, padding=1) + res, 0.2)
+    out = ops.conv3x3_tc_ring(nhwc(ops, x), ops.pack_conv_weight_ring(wt.cuda()), b.cuda(), cout, ACT_LEAKY,
+                              residual=nhwc(ops, res))
+    torch.cuda.synchronize()
+    got = back(ops, out)
+    print(f"ring cin={cin} cout={cout} {h}x{w}: max abs err {(got - ref).abs().max().item():.3e}")
+    torch.testing.assert_close(got, ref, rtol=CONV_RTOL, atol=CONV_ATOL)
+
+
 @pytest.mark.parametrize("h,w", [(9, 200), (5, 128), (20, 131), (3, 7)])
 def test_conv3x3_tensor_core_dilated(ops, h, w):
     """dilation 3 / pad 3, 32 -> 32 (the dilated resblocks of tile_update4_1 / tile_update5)."""
