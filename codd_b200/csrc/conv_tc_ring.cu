@@ -20,6 +20,8 @@
 // split warps then overwrite the row with x_lo = x - x_hi in place and pass B multiplies it by [w_hi | 0].
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace {
@@ -37,6 +39,7 @@ struct RgP {
     float* out;
     int N, H, W, Cout, ldo, ldr, res_bcast, act;
     int tilesX, nseg, seg, nitems;
+    long long* dbg;   // optional [grid][8] cycle counters (role wait times), NULL in production
 };
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -61,6 +64,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "memory");
         if (!done) __nanosleep(32);
     }
+}
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, long long& acc) {
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += clock64() - t0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -210,9 +218,10 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
         // ===================== TMA producer: one staged row per step =====================
         if (lane == 0) {
             Cursor c;
+            long long w0 = 0;
             for (c.init(p); c.valid(p); c.next(p)) {
                 const int sb = c.g % NBUF;
-                mbar_wait(SBAR(EMPTY, sb), (((uint32_t)(c.g / NBUF)) & 1u) ^ 1u);
+                mbar_wait_t(SBAR(EMPTY, sb), (((uint32_t)(c.g / NBUF)) & 1u) ^ 1u, w0);
                 mbar_expect_tx(SBAR(FULL, sb), A_BYTES);
                 const int cx = c.x0 - 1, cy = c.y0 - 1 + c.t;
                 asm volatile(
@@ -221,55 +230,113 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
                     "l"(&tmap), "r"(SBAR(FULL, sb)), "r"(0), "r"(cx), "r"(cy), "r"(c.n)
                     : "memory");
             }
+            if (p.dbg) p.dbg[blockIdx.x * 8 + 0] = w0;
         }
     } else if (warp == 13) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
+            constexpr bool leader = true;
             // one pass over one staged row: for every (kx, k-step) the row is multiplied by the weight blocks of the
             // valid ky taps; consecutive ring slots are covered by one MMA (N = 2NP, 4NP or 6NP)
+            long long w_full = 0, w_lo = 0, w_acce = 0;
+            const long long t_start = clock64();
+            // Everything below is indexed by compile-time constants only (fully unrolled): a run table in local memory
+            // made the single issuing thread spend ~450 cycles per MMA on dependent local loads.
+            const uint64_t b_desc0 = make_desc<KC>(sB);
             auto issue = [&](const Cursor& c, int pass) {
                 const int sb = c.g % NBUF;
                 const uint64_t a_desc = make_desc<KC>(sbase + sb * A_STRIDE);
                 const int kylo = max(0, c.t - c.rows + 1), kyhi = min(2, c.t);   // output row = y0 + t - ky inside the item
-                // runs of adjacent slots: slot(orow) = RING-1 - (orow % RING); ky ascending <=> orow descending <=> slot ascending
-                int run_ky[3], run_n[3], run_slot[3], nrun = 0;
-                for (int ky = kylo; ky <= kyhi; ++ky) {
-                    const int orow = c.orow0 + c.t - ky;
-                    const int slot = RING - 1 - (orow % RING);
-                    if (nrun > 0 && run_slot[nrun - 1] + run_n[nrun - 1] == slot) {
-                        ++run_n[nrun - 1];
-                    } else {
-                        run_ky[nrun] = ky; run_n[nrun] = 1; run_slot[nrun] = slot;
-                        ++nrun;
-                    }
-                }
-                const bool has_fresh = (pass == 0 && kylo == 0);   // ky = 0 is the FIRST contribution to its output row
+                // slot(orow) = RING-1 - (orow % RING); ky ascending <=> orow descending <=> slot ascending (mod RING)
+                int slot[3], runn[3];   // runn[ky] > 0: a run of runn adjacent slots starts at ky
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) slot[ky] = RING - 1 - ((c.orow0 + c.t - ky + 3 * RING) % RING);
+                const bool v0 = kylo <= 0 && 0 <= kyhi, v1 = kylo <= 1 && 1 <= kyhi, v2 = kylo <= 2 && 2 <= kyhi;
+                const bool j01 = v0 && v1 && slot[1] == slot[0] + 1;    // ky 0 and 1 adjacent
+                const bool j12 = v1 && v2 && slot[2] == slot[1] + 1;
+                runn[0] = v0 ? 1 + (j01 ? 1 + (j12 ? 1 : 0) : 0) : 0;
+                runn[1] = (v1 && !j01) ? 1 + (j12 ? 1 : 0) : 0;
+                runn[2] = (v2 && !j12) ? 1 : 0;
+                const bool has_fresh = (pass == 0 && v0);   // ky = 0 is the FIRST contribution to its output row
                 if (has_fresh) {
                     // the fresh slot is about to be overwritten: its previous row must have been drained
                     const int orow = c.orow0 + c.t;
-                    const int slot = RING - 1 - (orow % RING);
-                    mbar_wait(ABAR(ACCE, slot), (((uint32_t)(orow / RING)) & 1u) ^ 1u);
+                    mbar_wait_t(ABAR(ACCE, slot[0]), (((uint32_t)(orow / RING)) & 1u) ^ 1u, w_acce);
                     tc_fence_after();
                 }
-                const uint32_t wbase = sB + (uint32_t)(pass * 3) * WBLK;
-#pragma unroll 1
+                const uint64_t b_pass = b_desc0 + (((uint32_t)(pass * 3) * WBLK) >> 4);
+                constexpr uint32_t IDESC3 = IDESC_BASE | ((uint32_t)((3 * SLOT) >> 3) << 17);
+                constexpr uint32_t IDESC2 = IDESC_BASE | ((uint32_t)((2 * SLOT) >> 3) << 17);
+                constexpr uint32_t IDESC1 = IDESC_BASE | ((uint32_t)(SLOT >> 3) << 17);
+                constexpr uint32_t KYB = (SLOT * ROWB) >> 4;     // descriptor offset of one ky weight block
+                // Interior rows (all three taps valid) take one of three fully unrolled code paths whose MMA operands
+                // are base + compile-time constants and whose instruction descriptors are immediates — the single
+                // issuing thread pays ~6 instructions per MMA instead of ~40 dependent ones on the generic path:
+                //   SPLIT = 0: slots adjacent              -> 1 MMA (N = 3 slots) per (kx, k-step)
+                //   SPLIT = 1: ring wraps after ky = 0     -> N = 1 slot + N = 2 slots
+                //   SPLIT = 2: ring wraps after ky = 1     -> N = 2 slots + N = 1 slot
+                auto interior = [&](auto split_tag) {
+                    constexpr int SPLIT = decltype(split_tag)::value;
+                    const uint32_t d0 = tmem + (uint32_t)(slot[0] * SLOT);
+                    const uint32_t d1 = tmem + (uint32_t)(slot[1] * SLOT);
+                    const uint32_t d2 = tmem + (uint32_t)(slot[2] * SLOT);
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+                        for (int k = 0; k < KS; ++k) {
+                            const uint64_t a_k = a_desc + (((uint32_t)kx * ROWB + (uint32_t)k * 32u) >> 4);
+                            const uint64_t b_k = b_pass + (((uint32_t)kx * WBLK + (uint32_t)k * 32u) >> 4);
+                            const bool first = (kx == 0 && k == 0);
+                            if (first && pass == 0) {
+                                tc_mma_tf32(d0, a_k, b_k, IDESC1, 0u);                    // fresh row: overwrite its slot
+                                if (SPLIT == 1 || SPLIT == 0) {
+                                    tc_mma_tf32(d1, a_k, b_k + KYB, IDESC2, 1u);          // ky 1,2 adjacent
+                                } else {
+                                    tc_mma_tf32(d1, a_k, b_k + KYB, IDESC1, 1u);
+                                    tc_mma_tf32(d2, a_k, b_k + 2 * KYB, IDESC1, 1u);
+                                }
+                            } else if (SPLIT == 0) {
+                                tc_mma_tf32(d0, a_k, b_k, IDESC3, 1u);
+                            } else if (SPLIT == 1) {
+                                tc_mma_tf32(d0, a_k, b_k, IDESC1, 1u);
+                                tc_mma_tf32(d1, a_k, b_k + KYB, IDESC2, 1u);
+                            } else {
+                                tc_mma_tf32(d0, a_k, b_k, IDESC2, 1u);
+                                tc_mma_tf32(d2, a_k, b_k + 2 * KYB, IDESC1, 1u);
+                            }
+                        }
+                    }
+                };
+                if (v0 && v2) {
+                    if (j01 && j12) interior(std::integral_constant<int, 0>{});
+                    else if (j12) interior(std::integral_constant<int, 1>{});
+                    else interior(std::integral_constant<int, 2>{});
+                    return;
+                }
+                // generic path (first / last two staged rows of a segment): per-run operands computed once per row
+                uint32_t d_run[3], i_run[3];
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+                    d_run[ky] = tmem + (uint32_t)(slot[ky] * SLOT);
+                    i_run[ky] = IDESC_BASE | ((uint32_t)((runn[ky] * SLOT) >> 3) << 17);
+                }
+                if (has_fresh) {
+                    tc_mma_tf32(d_run[0], a_desc, b_pass, IDESC1, 0u);
+                    if (runn[0] > 1)
+                        tc_mma_tf32(d_run[0] + SLOT, a_desc, b_pass + KYB,
+                                    IDESC_BASE | ((uint32_t)(((runn[0] - 1) * SLOT) >> 3) << 17), 1u);
+                }
+#pragma unroll
                 for (int kx = 0; kx < 3; ++kx) {
-#pragma unroll 1
+#pragma unroll
                     for (int k = 0; k < KS; ++k) {
                         const uint64_t a_k = a_desc + (((uint32_t)kx * ROWB + (uint32_t)k * 32u) >> 4);
-                        for (int r = 0; r < nrun; ++r) {
-                            int ky0 = run_ky[r], nk = run_n[r], slot = run_slot[r];
-                            if (has_fresh && kx == 0 && k == 0 && ky0 == 0) {
-                                // the very first MMA of a fresh output row overwrites its slot (N = one slot) ...
-                                const uint64_t b_f = make_desc<KC>(wbase + (uint32_t)k * 32u);
-                                tc_mma_tf32(tmem + (uint32_t)(slot * SLOT), a_k, b_f, IDESC_BASE | ((uint32_t)(SLOT >> 3) << 17), 0u);
-                                ++ky0; --nk; ++slot;          // ... the rest of the run accumulates as usual
-                                if (nk == 0) continue;
-                            }
-                            const uint32_t boff = (uint32_t)kx * WBLK + (uint32_t)ky0 * (SLOT * ROWB) + (uint32_t)k * 32u;
-                            const uint64_t b_k = make_desc<KC>(wbase + boff);
-                            const uint32_t idesc = IDESC_BASE | ((uint32_t)((nk * SLOT) >> 3) << 17);
-                            tc_mma_tf32(tmem + (uint32_t)(slot * SLOT), a_k, b_k, idesc, 1u);
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky) {
+                            if (runn[ky] == 0) continue;
+                            if (ky == 0 && kx == 0 && k == 0 && has_fresh) continue;     // issued above
+                            const uint32_t boff = (uint32_t)kx * WBLK + (uint32_t)ky * (SLOT * ROWB) + (uint32_t)k * 32u;
+                            tc_mma_tf32(d_run[ky], a_k, b_pass + (boff >> 4), i_run[ky], 1u);
                         }
                     }
                 }
@@ -279,25 +346,29 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
             cb.init(p);
             auto pass_b = [&]() {
                 const int sb = cb.g % NBUF;
-                mbar_wait(SBAR(LO, sb), ((uint32_t)(cb.g / NBUF)) & 1u);
+                mbar_wait_t(SBAR(LO, sb), ((uint32_t)(cb.g / NBUF)) & 1u, w_lo);
                 tc_fence_after();
                 issue(cb, 1);
-                tc_commit(SBAR(EMPTY, sb));                       // stage buffer free -> producer
+                if (leader) tc_commit(SBAR(EMPTY, sb));           // stage buffer free -> producer
                 if (cb.t >= 2) {                                  // output row y0 + t - 2 is complete
                     const int orow = cb.orow0 + cb.t - 2;
-                    tc_commit(ABAR(ACCF, RING - 1 - (orow % RING)));
+                    if (leader) tc_commit(ABAR(ACCF, RING - 1 - (orow % RING)));
                 }
                 cb.next(p);
             };
             for (; ca.valid(p); ca.next(p)) {
                 const int sb = ca.g % NBUF;
-                mbar_wait(SBAR(FULL, sb), ((uint32_t)(ca.g / NBUF)) & 1u);
+                mbar_wait_t(SBAR(FULL, sb), ((uint32_t)(ca.g / NBUF)) & 1u, w_full);
                 tc_fence_after();
                 issue(ca, 0);
-                tc_commit(SBAR(P12, sb));                         // raw row consumed -> split warps
+                if (leader) tc_commit(SBAR(P12, sb));             // raw row consumed -> split warps
                 if (ca.g >= LAG) pass_b();
             }
             while (cb.valid(p)) pass_b();
+            if (p.dbg && leader) {
+                p.dbg[blockIdx.x * 8 + 1] = w_full; p.dbg[blockIdx.x * 8 + 2] = w_lo; p.dbg[blockIdx.x * 8 + 3] = w_acce;
+                p.dbg[blockIdx.x * 8 + 4] = clock64() - t_start; p.dbg[blockIdx.x * 8 + 5] = cb.g;
+            }
         }
     } else if (warp >= 8) {
         // ===================== epilogue (warps 8-11): one output row per step =====================
@@ -311,6 +382,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
 #pragma unroll
         for (int c = 0; c < NP; ++c) biasr[c] = (p.bias && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
         int orow = 0;
+        long long w_accf = 0;
         for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
             int q = item;
             const int sg = q % p.nseg;
@@ -322,7 +394,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
             const int x = tx * RG_TW + quarter * 32 + lane;
             for (int r = 0; r < rows; ++r, ++orow) {
                 const int slot = RING - 1 - (orow % RING);
-                mbar_wait(ABAR(ACCF, slot), ((uint32_t)(orow / RING)) & 1u);
+                mbar_wait_t(ABAR(ACCF, slot), ((uint32_t)(orow / RING)) & 1u, w_accf);
                 tc_fence_after();
                 float acc[SLOT];
 #pragma unroll
@@ -377,12 +449,14 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
                 }
             }
         }
+        if (p.dbg && tid == 256) p.dbg[blockIdx.x * 8 + 6] = w_accf;
     } else {
         // ===================== in-place hi/lo split of a staged row (warps 0-7) =====================
         Cursor c;
+        long long w_p12 = 0;
         for (c.init(p); c.valid(p); c.next(p)) {
             const int sb = c.g % NBUF;
-            mbar_wait(SBAR(P12, sb), ((uint32_t)(c.g / NBUF)) & 1u);   // pass A has consumed the raw row
+            mbar_wait_t(SBAR(P12, sb), ((uint32_t)(c.g / NBUF)) & 1u, w_p12);   // pass A has consumed the raw row
             tc_fence_after();
             float4* a4 = reinterpret_cast<float4*>(gbase + sb * A_STRIDE);
             for (int idx = tid; idx < (int)(A_BYTES / 16); idx += RG_SPLIT_THREADS) {
@@ -393,6 +467,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(SBAR(LO, sb));
         }
+        if (p.dbg && tid == 0) p.dbg[blockIdx.x * 8 + 7] = w_p12;
     }
     tc_fence_before();
     __syncthreads();
@@ -401,6 +476,8 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
     }
 }
+
+long long* g_rg_dbg = nullptr;
 
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -482,8 +559,17 @@ extern "C" int codd_conv3x3_tc_ring(const float* in, int ldi, int cin, int n, in
     p.N = n; p.H = h; p.W = w; p.Cout = cout; p.ldo = ldo; p.ldr = ldr; p.res_bcast = res_bcast; p.act = act;
     p.tilesX = codd_ceil_div(w, RG_TW);
     p.nseg = p.seg = p.nitems = 0;
+    p.dbg = g_rg_dbg;
     cudaStream_t s = (cudaStream_t)stream;
     if (KC == 32 && NP == 32) return launch_ring<32, 32, 4, 2>(tmap, p, s);
     if (KC == 32 && NP == 16) return launch_ring<32, 16, 4, 2>(tmap, p, s);
-    return launch_ring<16, 16, 6, 2>(tmap, p, s);
+    return launch_ring<16, 16, 12, 8>(tmap, p, s);
+}
+
+// diagnostic: device buffer of [grid][8] int64 cycle counters filled by the next codd_conv3x3_tc_ring launches
+// (0 producer wait-empty, 1 mma wait-full, 2 mma wait-lo, 3 mma wait-slot-drained, 4 mma total, 5 staged rows,
+//  6 epilogue wait-acc-full, 7 split wait-p12); NULL disables.
+extern "C" CODD_API int codd_conv3x3_tc_ring_debug(long long* dbg) {
+    g_rg_dbg = dbg;
+    return 0;
 }

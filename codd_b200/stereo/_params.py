@@ -13,6 +13,8 @@ from .. import ops
 
 # 3x3 convolutions run on the tensor cores (tcgen05, 3xTF32) unless CODD_TC=0
 USE_TC = os.environ.get("CODD_TC", "1") != "0"
+# dilation-1 layers use the rolling-ring tcgen05 kernel (csrc/conv_tc_ring.cu) unless CODD_TC_RING=0
+USE_RING = os.environ.get("CODD_TC_RING", "1") != "0"
 
 
 def run_conv(pw, conv, x, act, x2=None, residual=None, res_bcast=False, head=None):
@@ -21,6 +23,12 @@ def run_conv(pw, conv, x, act, x2=None, residual=None, res_bcast=False, head=Non
     cout = conv.out_channels if head is None else head
     k, st, pd, dl = conv.kernel_size, conv.stride, conv.padding, conv.dilation[0]
     cin = x.shape[1] + (0 if x2 is None else x2.shape[1])
+    # rolling-ring kernel for everything but the tiny coarse-level layers (a strip segment needs >= ~16 rows per SM to
+    # amortise its pipeline fill; measured cross-over ~50k pixels, tools/conv_probe.py)
+    big = x.shape[0] * x.shape[2] * x.shape[3] >= 50000
+    if USE_TC and USE_RING and big and dl == 1 and ops.tc_eligible(cin, cout, k, st, pd, dl, x2):
+        ws, b = pw.conv_ring(conv, head)
+        return ops.conv3x3_tc_ring(x, ws, b, cout, act, residual=residual, res_bcast=res_bcast)
     if USE_TC and ops.tc_eligible(cin, cout, k, st, pd, dl, x2):
         ws, b = pw.conv_tc(conv, head)
         return ops.conv3x3_tc(x, ws, b, cout, act, residual=residual, res_bcast=res_bcast, dil=dl)
@@ -70,6 +78,20 @@ class PackedWeights:
             ww = w if n is None else w[:n]
             bb = None if b is None else (b.detach() if n is None else b.detach()[:n]).float().contiguous()
             hit = (tag, ops.pack_conv_weight_tc(ww), bb)
+            self._cache[key] = hit
+        return hit[1], hit[2]
+
+    def conv_ring(self, conv, n=None):
+        """[pass][kx][6*NP][KC] layout of a 3x3 weight for the rolling-ring tensor-core kernel."""
+        w = conv.weight
+        b = conv.bias
+        key = (id(conv), "ring", n)
+        tag = (w.data_ptr(), w._version, w.device, None if b is None else (b.data_ptr(), b._version))
+        hit = self._cache.get(key)
+        if hit is None or hit[0] != tag:
+            ww = w if n is None else w[:n]
+            bb = None if b is None else (b.detach() if n is None else b.detach()[:n]).float().contiguous()
+            hit = (tag, ops.pack_conv_weight_ring(ww), bb)
             self._cache[key] = hit
         return hit[1], hit[2]
 

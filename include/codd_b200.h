@@ -106,6 +106,9 @@ CODD_API int codd_conv3x3_tc_ring(const float* in, int ldi, int cin, int n, int 
                                   const float* bias, const float* residual, int ldr, int res_bcast, int cout, int act,
                                   float* out, int ldo, void* stream);
 
+/* Diagnostic: device buffer [grid][8] of int64 cycle counters filled by later codd_conv3x3_tc_ring launches. */
+CODD_API int codd_conv3x3_tc_ring_debug(long long* dbg);
+
 /* Diagnostic: device buffer [grid][8] of int64 cycle counters filled by later codd_conv3x3_tc launches. */
 CODD_API int codd_conv3x3_tc_debug(long long* dbg);
 
