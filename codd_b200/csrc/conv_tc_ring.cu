@@ -30,7 +30,7 @@ constexpr int RG_TW = 128;              // output columns per strip (= MMA M)
 constexpr int RG_BOXW = RG_TW + 2;      // staged pixels per row
 constexpr int RG_EPI_THREADS = 128;
 constexpr int RG_SPLIT_THREADS = 256;
-constexpr int RG_THREADS = 64 + RG_EPI_THREADS + RG_SPLIT_THREADS;   // warps 0-7 split, 8-11 epilogue, 12 TMA, 13 MMA
+constexpr int RG_THREADS = 96 + RG_EPI_THREADS + RG_SPLIT_THREADS;   // warps 0-7 split, 8-11 epilogue, 12 TMA, 13 MMA pass A, 14 MMA pass B
 
 struct RgP {
     const float* wpk;   // [2 pass][3 kx][6*NP rows][KC]: pass 0 rows per ky = [w_hi | w_lo], pass 1 = [w_hi | 0]
@@ -65,7 +65,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (!done) __nanosleep(32);
     }
 }
-__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, long long& acc) {
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, long long& acc, bool timing) {
+    if (!timing) {
+        mbar_wait(bar, parity);
+        return;
+    }
     const long long t0 = clock64();
     mbar_wait(bar, parity);
     acc += clock64() - t0;
@@ -167,7 +171,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
     static_assert(NBUF >= LAG + 2, "stage depth");
 
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) unsigned long long bars[4 * NBUF + 2 * RING];
+    __shared__ __align__(8) unsigned long long bars[5 * NBUF + 2 * RING];
     __shared__ uint32_t tmem_base_slot;
 
     const uint32_t sbase = (s_u32(smem_raw) + 1023u) & ~1023u;
@@ -176,10 +180,11 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
     uint8_t* gB = gbase + NBUF * A_STRIDE;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool timing = p.dbg != nullptr;
     const uint32_t bar0 = s_u32(&bars[0]);
     auto SBAR = [&](int kind, int b) { return bar0 + (uint32_t)(kind * NBUF + b) * 8u; };
-    auto ABAR = [&](int kind, int b) { return bar0 + (uint32_t)(4 * NBUF + kind * RING + b) * 8u; };
-    enum { FULL = 0, EMPTY = 1, P12 = 2, LO = 3 };
+    auto ABAR = [&](int kind, int b) { return bar0 + (uint32_t)(5 * NBUF + kind * RING + b) * 8u; };
+    enum { FULL = 0, EMPTY = 1, P12 = 2, LO = 3, ISS = 4 };
     enum { ACCF = 0, ACCE = 1 };
 
     if (tid == 0) {
@@ -188,6 +193,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
             mbar_init(SBAR(EMPTY, b), 1);
             mbar_init(SBAR(P12, b), 1);
             mbar_init(SBAR(LO, b), RG_SPLIT_THREADS);
+            mbar_init(SBAR(ISS, b), 1);
         }
         for (int b = 0; b < RING; ++b) {
             mbar_init(ABAR(ACCF, b), 1);
@@ -221,7 +227,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
             long long w0 = 0;
             for (c.init(p); c.valid(p); c.next(p)) {
                 const int sb = c.g % NBUF;
-                mbar_wait_t(SBAR(EMPTY, sb), (((uint32_t)(c.g / NBUF)) & 1u) ^ 1u, w0);
+                mbar_wait_t(SBAR(EMPTY, sb), (((uint32_t)(c.g / NBUF)) & 1u) ^ 1u, w0, timing);
                 mbar_expect_tx(SBAR(FULL, sb), A_BYTES);
                 const int cx = c.x0 - 1, cy = c.y0 - 1 + c.t;
                 asm volatile(
@@ -232,8 +238,11 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
             }
             if (p.dbg) p.dbg[blockIdx.x * 8 + 0] = w0;
         }
-    } else if (warp == 13) {
-        // ===================== MMA issuer =====================
+    } else if (warp == 13 || warp == 14) {
+        // ===================== MMA issuers: warp 13 = pass A (raw rows), warp 14 = pass B (x_lo rows) =====================
+        // Two issuing threads: a single thread pays ~55 cycles per MMA (operand moves to uniform registers + the issue
+        // itself), which at 13 MMAs + 5 barrier operations per row was the kernel's critical path.  Ordering between
+        // the two is carried by the barriers: pass B of a row waits for the split, which waits for pass A's commit.
         if (lane == 0) {
             constexpr bool leader = true;
             // one pass over one staged row: for every (kx, k-step) the row is multiplied by the weight blocks of the
@@ -261,7 +270,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
                 if (has_fresh) {
                     // the fresh slot is about to be overwritten: its previous row must have been drained
                     const int orow = c.orow0 + c.t;
-                    mbar_wait_t(ABAR(ACCE, slot[0]), (((uint32_t)(orow / RING)) & 1u) ^ 1u, w_acce);
+                    mbar_wait_t(ABAR(ACCE, slot[0]), (((uint32_t)(orow / RING)) & 1u) ^ 1u, w_acce, timing);
                     tc_fence_after();
                 }
                 const uint64_t b_pass = b_desc0 + (((uint32_t)(pass * 3) * WBLK) >> 4);
@@ -341,33 +350,41 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
                     }
                 }
             };
-            Cursor ca, cb;     // pass A cursor, pass B cursor (LAG rows behind)
-            ca.init(p);
-            cb.init(p);
-            auto pass_b = [&]() {
-                const int sb = cb.g % NBUF;
-                mbar_wait_t(SBAR(LO, sb), ((uint32_t)(cb.g / NBUF)) & 1u, w_lo);
-                tc_fence_after();
-                issue(cb, 1);
-                if (leader) tc_commit(SBAR(EMPTY, sb));           // stage buffer free -> producer
-                if (cb.t >= 2) {                                  // output row y0 + t - 2 is complete
-                    const int orow = cb.orow0 + cb.t - 2;
-                    if (leader) tc_commit(ABAR(ACCF, RING - 1 - (orow % RING)));
+            if (warp == 13) {
+                Cursor ca;
+                for (ca.init(p); ca.valid(p); ca.next(p)) {
+                    const int sb = ca.g % NBUF;
+                    mbar_wait_t(SBAR(FULL, sb), ((uint32_t)(ca.g / NBUF)) & 1u, w_full, timing);
+                    tc_fence_after();
+                    issue(ca, 0);
+                    tc_commit(SBAR(P12, sb));                     // raw row consumed -> split warps
+                    mbar_arrive(SBAR(ISS, sb));                   // pass A of this row is in the tensor queue
                 }
-                cb.next(p);
-            };
-            for (; ca.valid(p); ca.next(p)) {
-                const int sb = ca.g % NBUF;
-                mbar_wait_t(SBAR(FULL, sb), ((uint32_t)(ca.g / NBUF)) & 1u, w_full);
-                tc_fence_after();
-                issue(ca, 0);
-                if (leader) tc_commit(SBAR(P12, sb));             // raw row consumed -> split warps
-                if (ca.g >= LAG) pass_b();
-            }
-            while (cb.valid(p)) pass_b();
-            if (p.dbg && leader) {
-                p.dbg[blockIdx.x * 8 + 1] = w_full; p.dbg[blockIdx.x * 8 + 2] = w_lo; p.dbg[blockIdx.x * 8 + 3] = w_acce;
-                p.dbg[blockIdx.x * 8 + 4] = clock64() - t_start; p.dbg[blockIdx.x * 8 + 5] = cb.g;
+                if (p.dbg) {
+                    p.dbg[blockIdx.x * 8 + 1] = w_full; p.dbg[blockIdx.x * 8 + 3] = w_acce;
+                    p.dbg[blockIdx.x * 8 + 4] = clock64() - t_start; p.dbg[blockIdx.x * 8 + 5] = ca.g;
+                }
+            } else {
+                // Deterministic accumulation order: pass B of row g touches output rows g-2..g, pass A of row h touches
+                // h-2..h, so B(g) is only ambiguous against A(g+1), A(g+2) — it is issued after both are in the queue.
+                int gtotal = 0;
+                for (int item = blockIdx.x; item < p.nitems; item += gridDim.x)
+                    gtotal += min(p.seg, p.H - (item % p.nseg) * p.seg) + 2;
+                Cursor cb;
+                for (cb.init(p); cb.valid(p); cb.next(p)) {
+                    const int sb = cb.g % NBUF;
+                    const int ga = min(cb.g + 2, gtotal - 1);
+                    mbar_wait(SBAR(ISS, ga % NBUF), ((uint32_t)(ga / NBUF)) & 1u);
+                    mbar_wait_t(SBAR(LO, sb), ((uint32_t)(cb.g / NBUF)) & 1u, w_lo, timing);
+                    tc_fence_after();
+                    issue(cb, 1);
+                    tc_commit(SBAR(EMPTY, sb));                   // stage buffer free -> producer
+                    if (cb.t >= 2) {                              // output row y0 + t - 2 is complete
+                        const int orow = cb.orow0 + cb.t - 2;
+                        tc_commit(ABAR(ACCF, RING - 1 - (orow % RING)));
+                    }
+                }
+                if (p.dbg) p.dbg[blockIdx.x * 8 + 2] = w_lo;
             }
         }
     } else if (warp >= 8) {
@@ -394,7 +411,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
             const int x = tx * RG_TW + quarter * 32 + lane;
             for (int r = 0; r < rows; ++r, ++orow) {
                 const int slot = RING - 1 - (orow % RING);
-                mbar_wait_t(ABAR(ACCF, slot), ((uint32_t)(orow / RING)) & 1u, w_accf);
+                mbar_wait_t(ABAR(ACCF, slot), ((uint32_t)(orow / RING)) & 1u, w_accf, timing);
                 tc_fence_after();
                 float acc[SLOT];
 #pragma unroll
@@ -456,7 +473,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
         long long w_p12 = 0;
         for (c.init(p); c.valid(p); c.next(p)) {
             const int sb = c.g % NBUF;
-            mbar_wait_t(SBAR(P12, sb), ((uint32_t)(c.g / NBUF)) & 1u, w_p12);   // pass A has consumed the raw row
+            mbar_wait_t(SBAR(P12, sb), ((uint32_t)(c.g / NBUF)) & 1u, w_p12, timing);   // pass A has consumed the raw row
             tc_fence_after();
             float4* a4 = reinterpret_cast<float4*>(gbase + sb * A_STRIDE);
             for (int idx = tid; idx < (int)(A_BYTES / 16); idx += RG_SPLIT_THREADS) {
