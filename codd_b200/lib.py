@@ -63,6 +63,10 @@ SIGNATURES = {
     "codd_splat_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "codd_splat_warp": (c_int, [_FP, _FP, _FP, _FP, c_int, c_int, c_int, c_int, c_int, c_float, c_float, _FP, c_int, _FP,
                                 _FP, _FP, c_size_t, c_void_p]),
+    "codd_im2col_split": (c_int, [_FP, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _FP, _FP, c_int,
+                                  c_void_p]),
+    "codd_gemm_tc": (c_int, [_FP, _FP, c_int, _FP, _FP, c_int, c_int, c_int, c_int, _FP, _FP, c_int, c_int, _FP, c_int,
+                             c_void_p]),
     "codd_instance_norm_workspace_bytes": (c_size_t, [c_int, c_int]),
     "codd_instance_norm_nhwc": (c_int, [_FP, c_int, c_int, c_int, c_int, c_int, c_float, c_int, _FP, c_int, _FP, c_int,
                                         _FP, c_size_t, c_void_p]),

@@ -200,6 +200,54 @@ def conv3x3_tc_ring(x, wring, bias, cout, act=ACT_NONE, residual=None, res_bcast
     return out
 
 
+def pack_conv_weight_gemm(w):
+    """torch [Cout,Cin,KH,KW] -> (B_hi, B_lo), each [Cout][KH*KW*Cin] (k = tap*Cin + ch), tf32 halves for codd_gemm_tc."""
+    cout = w.shape[0]
+    b = w.detach().float().permute(0, 2, 3, 1).reshape(cout, -1).contiguous()
+    hi = _tf32_round(b)
+    return hi.contiguous(), _tf32_round(b - hi).contiguous()
+
+
+GEMM_3XTF32 = True    # False: single-pass TF32 (what cuDNN does by default for the reference on GPUs)
+
+
+def gemm_eligible(n, h, w, cin, cout, k, stride, x2):
+    kh, kw = (k, k) if isinstance(k, int) else k
+    sh, sw = (stride, stride) if isinstance(stride, int) else stride
+    m, kk = n * h * w, kh * kw * cin
+    return (x2 is None and sh == 1 and sw == 1 and cin % 4 == 0 and kk >= 128 and cout >= 16 and m >= 1024
+            and m * kk * 8 <= (3 << 29))
+
+
+def conv2d_gemm(x, wg, bias, cout, k, pad=(0, 0), dil=1, act=ACT_NONE, residual=None, out=None):
+    """Stride-1 convolution as im2col + tcgen05 GEMM (3xTF32 unless ops.GEMM_3XTF32 is False).  ``wg`` from
+    pack_conv_weight_gemm; out = act(conv(x) + bias + residual)."""
+    _require_cuda(x, wg[0], wg[1], bias, residual, out)
+    n, cin, h, w = x.shape
+    kh, kw = (k, k) if isinstance(k, int) else k
+    ph, pw = (pad, pad) if isinstance(pad, int) else pad
+    if 2 * ph != dil * (kh - 1) or 2 * pw != dil * (kw - 1):
+        raise _lib.CoddError("conv2d_gemm: 'same' padding only")
+    m, kk = n * h * w, kh * kw * cin
+    if out is None:
+        out = empty_nhwc(n, cout, h, w, x.device)
+    a = torch.empty((m, kk), device=x.device, dtype=torch.float32)
+    a_lo = torch.empty_like(a) if GEMM_3XTF32 else None
+    rc = _run(f"im2col_k{kh}x{kw}_cin{cin}", 4 * (x.numel() + (2 if GEMM_3XTF32 else 1) * m * kk), lambda: _lib.load().codd_im2col_split(
+        x.data_ptr(), ld_of(x), n, h, w, cin, kh, kw, ph, pw, dil, a.data_ptr(), None if a_lo is None else a_lo.data_ptr(), kk,
+        _stream()))
+    _lib.check(rc, "codd_im2col_split")
+    nseg = 3 if GEMM_3XTF32 else 1
+    nbytes = 4 * (nseg * m * kk + cout * kk + m * cout * (1 if residual is None else 2))
+    rc = _run(f"gemm_tc_k{kk}_n{cout}", nbytes, lambda: _lib.load().codd_gemm_tc(
+        a.data_ptr(), None if a_lo is None else a_lo.data_ptr(), kk, wg[0].data_ptr(),
+        wg[1].data_ptr() if GEMM_3XTF32 else None, kk, m, cout, kk, None if bias is None else bias.data_ptr(),
+        None if residual is None else residual.data_ptr(), 0 if residual is None else ld_of(residual), act, out.data_ptr(),
+        ld_of(out), _stream()))
+    _lib.check(rc, f"codd_gemm_tc(m={m}, n={cout}, k={kk})")
+    return out
+
+
 def tc_eligible(cin, cout, k, stride, pad, dil, x2):
     kh, kw = (k, k) if isinstance(k, int) else k
     sh, sw = (stride, stride) if isinstance(stride, int) else stride

@@ -265,6 +265,21 @@ CODD_API int codd_splat_warp(const float* Ts, const float* depth, const float* i
                              void* workspace, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Wide convolutions of the RAFT3D update block as a tcgen05 GEMM (reference: BasicUpdateBlock / ConvGRU,
+ * model/motion/raft3d/raft3d.py:43-106, blocks/gru.py:10-35; 128..384-channel layers at 1/8 resolution).
+ * ------------------------------------------------------------------------------------------ */
+/* Patch matrix of a stride-1 convolution: A[m][tap*c + ch] = in[pixel m shifted by tap] (zero outside), m in NHWC pixel
+ * order, row pitch lda >= kh*kw*c; A_lo (optional) = A - tf32(A), the remainder the 3xTF32 GEMM consumes. */
+CODD_API int codd_im2col_split(const float* in, int ldi, int n, int h, int w, int c, int kh, int kw, int ph, int pw,
+                               int dil, float* A, float* A_lo, int lda, void* stream);
+/* out[m][n] = act(sum_k A[m][k] * B[n][k] + bias[n] + residual[m][n]) on tcgen05 (kind::tf32, TMA-fed, TMEM
+ * accumulators).  B_hi / B_lo: tf32-rounded weights and remainder, [n][k] row-major (pitch ldb).  A_lo and B_lo both
+ * given: 3xTF32 (fp32-class accuracy); both NULL: single-pass TF32. */
+CODD_API int codd_gemm_tc(const float* A, const float* A_lo, int lda, const float* B_hi, const float* B_lo, int ldb, int m,
+                          int n, int k, const float* bias, const float* residual, int ldr, int act, float* out, int ldo,
+                          void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * RAFT3D network glue (reference: model/motion/raft3d/blocks/extractor.py:28-55,124-190 instance
  * norm; raft3d.py:125-137 ResizeConcatConv + mmseg HRModule fuse layers; blocks/gru.py:30-34;
  * raft3d.py:183-186,242; motion.py:154-165,196-197).  The convolutions themselves go through

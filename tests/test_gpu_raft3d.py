@@ -160,3 +160,20 @@ def test_motion_forward_two_frames(ops, raft):
         assert a.shape == b.shape, name
         bad = ((a - b).abs() > 1e-2 * b.abs().clamp(min=1.0)).float().mean().item()
         assert bad < 0.01, f"{name}: {bad * 100:.2f}% of elements differ"
+
+
+@pytest.mark.parametrize("cin,cout,k,p,d,n,h,w", [
+    (128, 256, 3, 1, 1, 2, 24, 40), (196, 256, 3, 1, 1, 1, 33, 47), (128, 128, 3, 4, 4, 2, 24, 40),
+    (256, 384, 1, 0, 1, 2, 24, 40), (128, 1024, 3, 1, 1, 1, 20, 60), (12, 128, 7, 3, 1, 2, 24, 40),
+    (256, 576, 1, 0, 1, 1, 30, 36), (256, 32, 1, 0, 1, 2, 24, 40)])
+def test_conv_as_tcgen05_gemm(ops, cin, cout, k, p, d, n, h, w):
+    """im2col + tcgen05 GEMM (3xTF32) against fp32 F.conv2d: same bar as every other convolution."""
+    x = torch.randn(n, cin, h, w, generator=g(21))
+    wt = torch.randn(cout, cin, k, k, generator=g(22)) / (cin * k * k) ** 0.5
+    b = torch.randn(cout, generator=g(23))
+    res = torch.randn(n, cout, h, w, generator=g(24))
+    want = F.relu(F.conv2d(x, wt, b, padding=p, dilation=d) + res)
+    assert ops.gemm_eligible(n, h, w, cin, cout, k, 1, None)
+    got = ops.conv2d_gemm(ops.to_nhwc(x.cuda()), ops.pack_conv_weight_gemm(wt.cuda()), b.cuda(), cout, k, p, d, ops.ACT_RELU,
+                          residual=ops.to_nhwc(res.cuda()))
+    close(ops.to_nchw(got).cpu(), want, 2e-5)
