@@ -15,7 +15,7 @@ import torch.nn as nn
 
 from .. import ops
 from ..registry import MODELS, build_backbone
-from ._net import NetWeights, conv
+from ._net import NetWeights, conv, conv_cat
 from .extractor import BasicEncoder
 
 
@@ -41,11 +41,8 @@ class ConvGRU(nn.Module):
         hd = self.hidden_dim
         n, _, hh, ww = h.shape
         # z | r: two 128->256 convolutions (dilation 1, then dilation 4 accumulating) + sigmoid
-        w1, b1 = pw.conv_cat([self.convz1, self.convr1])
-        w2, b2 = pw.conv_cat([self.convz2, self.convr2])
-        d = self.convz2.dilation[0]
-        zr = ops.conv2d(h, w1, b1, 2 * hd, 3, 1, 1, 1, ops.ACT_NONE, residual=inp_sum[:, :2 * hd])
-        zr = ops.conv2d(h, w2, b2, 2 * hd, 3, 1, d, d, ops.ACT_SIGMOID, residual=zr)
+        zr = conv_cat(pw, [self.convz1, self.convr1], h, ops.ACT_NONE, residual=inp_sum[:, :2 * hd])
+        zr = conv_cat(pw, [self.convz2, self.convr2], h, ops.ACT_SIGMOID, residual=zr)
         rh = ops.eltwise(ops.EW_MUL, zr[:, hd:], h)
         q = conv(pw, self.convq1, rh, ops.ACT_NONE, residual=inp_sum[:, 2 * hd:])
         q = conv(pw, self.convq2, rh, ops.ACT_TANH, residual=q)
@@ -83,8 +80,7 @@ class BasicUpdateBlock(nn.Module):
         s = conv(pw, self.flow_enc[2], m, ops.ACT_NONE, residual=s)
         net = self.gru.run(pw, net, s)
         heads = [self.ae, self.delta, self.weight] + ([self.mask] if want_mask else [])
-        w, b = pw.conv_cat([hd[0] for hd in heads])
-        stem = ops.conv2d(net, w, b, 256 * len(heads), 3, 1, 1, 1, ops.ACT_RELU)
+        stem = conv_cat(pw, [hd[0] for hd in heads], net, ops.ACT_RELU)
         ae = conv(pw, self.ae[2], stem[:, 0:256])
         delta = conv(pw, self.delta[2], stem[:, 256:512])
         weight = conv(pw, self.weight[2], stem[:, 512:768], ops.ACT_SIGMOID)
