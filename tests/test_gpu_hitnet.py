@@ -136,3 +136,21 @@ def test_full_size_properties():
     with torch.no_grad():
         solo = m.stereo_matching(left[1:], right[1:])["pred_disp"]
     assert torch.equal(solo, pred[1:])
+
+
+def test_kitti_shape_properties():
+    """384x1280 (KITTI 1242x375 padded: BASELINE.json configs[3] geometry), D=192, batch 2: finite, non-negative,
+    deterministic, batch-independent, and cropped correctly by the top-level API."""
+    import codd_b200
+    torch.manual_seed(1)
+    model = codd_b200.build_estimator(codd_b200.codd_stereo_config(192)).cuda()
+    model.eval()
+    left, right = O.synth_pair(2, 384, 1280, 192, seed=7, kind="S")
+    img, r_img = left.unsqueeze(1).cuda(), right.unsqueeze(1).cuda()
+    metas = [[dict(min_disp=1, max_disp=192, ori_shape=(375, 1242), img_shape=(375, 1242))]]
+    res = model(return_loss=False, rescale=True, evaluate=False, img=[img], img_metas=metas, r_img=[r_img])[0]
+    assert res.shape == (2, 1, 375, 1242) and torch.isfinite(res).all() and (res >= 0).all()
+    res2 = model(return_loss=False, rescale=True, evaluate=False, img=[img], img_metas=metas, r_img=[r_img])[0]
+    assert torch.equal(res, res2)
+    solo = model(return_loss=False, rescale=True, evaluate=False, img=[img[1:]], img_metas=metas, r_img=[r_img[1:]])[0]
+    assert torch.equal(solo, res[1:])
