@@ -216,11 +216,64 @@ __global__ void __launch_bounds__(CV_MAXW * 32, 2) cost_volume_kernel(CvP p) {
         }
     };
 
+    // Two consecutive FULL steps of a warp whose 32 lanes are all inside the row for both: the eight cost chains
+    // (four 16-term FADD2 chains instead of two) are computed in ONE straight-line block — twice the independent
+    // work per warp for the FP32 pipe, no per-step branches — and then consumed in step order exactly as `step`
+    // does (stores, strict-< arg-min updates, hand-off shuffle), so results are bit-identical.
+    auto step2 = [&](const int q) {
+        const int j = m + q;
+        const float* lp = Lp + (j - jb);
+        float2 lo0 = make_float2(0.f, 0.f), hi0 = lo0, lo1 = lo0, hi1 = lo0;
+#pragma unroll
+        for (int c = 0; c < CV_C; ++c) {
+            const float la = lp[c * CV_LW], lb = lp[c * CV_LW + 1];
+            const float2 n0 = make_float2(-rq[c][0].x, -rq[c][0].y), n1 = make_float2(-rq[c][1].x, -rq[c][1].y);
+            const float2 a0 = __fadd2_rn(make_float2(la, la), n0), a1 = __fadd2_rn(make_float2(la, la), n1);
+            const float2 b0 = __fadd2_rn(make_float2(lb, lb), n0), b1 = __fadd2_rn(make_float2(lb, lb), n1);
+            lo0 = __fadd2_rn(lo0, make_float2(fabsf(a0.x), fabsf(a0.y)));
+            hi0 = __fadd2_rn(hi0, make_float2(fabsf(a1.x), fabsf(a1.y)));
+            lo1 = __fadd2_rn(lo1, make_float2(fabsf(b0.x), fabsf(b0.y)));
+            hi1 = __fadd2_rn(hi1, make_float2(fabsf(b1.x), fabsf(b1.y)));
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float2 lo = h ? lo1 : lo0, hi = h ? hi1 : hi0;
+            const int jj = j + h, d0i = 4 * (q + h);
+            if (WRITE_CV) {
+                float* o = cvrow + (ptrdiff_t)d0i * (ptrdiff_t)plane + jj;
+                __stcs(o - 3 * plane, hi.y);
+                __stcs(o - 2 * plane, hi.x);
+                __stcs(o - plane, lo.y);
+                __stcs(o, lo.x);
+            }
+            if (ARGMIN) {
+                const float dq = (float)d0i;
+                if (hi.y < bc) { bc = hi.y; bd = dq - 3.f; }
+                if (hi.x < bc) { bc = hi.x; bd = dq - 2.f; }
+                if (lo.y < bc) { bc = lo.y; bd = dq - 1.f; }
+                if (lo.x < bc) { bc = lo.x; bd = dq; }
+                if (lane == 0) {
+                    pc[warp * LW + (jj - jb)] = bc;
+                    pd[warp * LW + (jj - jb)] = bd;
+                }
+                bc = __shfl_down_sync(0xffffffffu, bc, 1);
+                bd = __shfl_down_sync(0xffffffffu, bd, 1);
+                if (lane == 31) { bc = INFINITY; bd = 0.f; }
+            }
+        }
+    };
+
     if (m0 < je) {  // warp-uniform
         const int qfull = min((p.D - 1) >> 2, qmax);     // q in [1, qfull]: all four disparities valid
         step(0, std::false_type{});
+        int q = 1;
+        // all 32 lanes on for steps q and q+1  <=>  m0 + q >= jb  and  m0 + 31 + q + 1 < je  (and every lane has an m)
+        if (m0 + 31 < je) {
+            for (; q + 1 <= qfull && m0 + q < jb; ++q) step(q, std::true_type{});
+            for (; q + 1 <= qfull && m0 + 32 + q < je; q += 2) step2(q);
+        }
 #pragma unroll 2
-        for (int q = 1; q <= qfull; ++q) step(q, std::true_type{});
+        for (; q <= qfull; ++q) step(q, std::true_type{});
         for (int q = max(qfull, 0) + 1; q <= qmax; ++q) step(q, std::false_type{});
         if (ARGMIN) {
             // columns still in flight: lane now holds the state of column m + qmax + 1
