@@ -19,6 +19,7 @@
 // 3xTF32: pass A multiplies the raw fp32 row (the MMA reads the top 19 bits = x_hi) by [w_hi | w_lo] per tap, the
 // split warps then overwrite the row with x_lo = x - x_hi in place and pass B multiplies it by [w_hi | 0].
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <type_traits>
 
@@ -124,6 +125,34 @@ __device__ __forceinline__ uint32_t swz_off(int r, int j) {
 __device__ __forceinline__ float tf32_lo(float x) {
     return __fsub_rn(x, __uint_as_float(__float_as_uint(x) & 0xFFFFE000u));
 }
+// K-major swizzled descriptor for rows of RB bytes (32 / 64 / 128: SWIZZLE_32B / 64B / 128B, 8-row group pitch 8*RB)
+template <int RB>
+__device__ __forceinline__ uint64_t make_desc_rb(uint32_t saddr) {
+    constexpr uint64_t LAYOUT = (RB == 128) ? 2ull : (RB == 64) ? 4ull : 6ull;
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((8u * RB) >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= LAYOUT << 61;
+    return d;
+}
+// byte offset of 16-byte chunk j of row r in a tile of RB-byte rows whose base is 1024-aligned
+template <int RB>
+__device__ __forceinline__ uint32_t swz_rb(int r, int j) {
+    const uint32_t off = (uint32_t)r * RB + (uint32_t)j * 16u;
+    constexpr uint32_t MASK = RB / 16 - 1;     // 1, 3, 7
+    return off ^ (((off >> 7) & MASK) << 4);
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.u32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+constexpr float RG_LO_SCALE = 1024.f;   // x_lo and w_lo travel scaled by 2^10 (fp16 range); the epilogue undoes it
 
 // Cursor over the staged rows a CTA processes: items (sample, column strip, row segment) in grid-stride order, and
 // inside an item the rows t = 0 .. rows+1 (image rows y0-1 .. y0+rows).  Every warp role runs its own copy.
@@ -165,7 +194,11 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
     constexpr uint32_t ROWB = KC * 4;
     constexpr uint32_t A_BYTES = RG_BOXW * ROWB;
     constexpr uint32_t A_STRIDE = (A_BYTES + 1023u) & ~1023u;
-    constexpr uint32_t WBLK = 6 * NP * ROWB;     // one (pass, kx) weight block: 3 ky x [2*NP rows]
+    constexpr uint32_t WBLK = 6 * NP * ROWB;     // one pass-A kx weight block: 3 ky x [2*NP rows], fp32
+    constexpr uint32_t ROWH = KC * 2;            // fp16 operand rows of pass B
+    constexpr uint32_t H_BYTES = RG_BOXW * ROWH;
+    constexpr uint32_t H_STRIDE = (H_BYTES + 1023u) & ~1023u;
+    constexpr uint32_t WBLKH = 6 * NP * ROWH;    // one pass-B kx weight block, fp16
     constexpr int KS = KC / 8;
     constexpr uint32_t IDESC_BASE = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 4) << 24);
     static_assert(NBUF >= LAG + 2, "stage depth");
@@ -176,8 +209,12 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
 
     const uint32_t sbase = (s_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gbase = smem_raw + (sbase - s_u32(smem_raw));
-    const uint32_t sB = sbase + NBUF * A_STRIDE;
-    uint8_t* gB = gbase + NBUF * A_STRIDE;
+    const uint32_t sH = sbase + NBUF * A_STRIDE;             // fp16 x_lo stages
+    uint8_t* gH = gbase + NBUF * A_STRIDE;
+    const uint32_t sB = sH + NBUF * H_STRIDE;                // pass-A weights (fp32), then pass-B weights (fp16)
+    uint8_t* gB = gH + NBUF * H_STRIDE;
+    const uint32_t sBH = sB + 3 * WBLK;
+    uint8_t* gBH = gB + 3 * WBLK;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool timing = p.dbg != nullptr;
@@ -206,13 +243,23 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
                      "r"(512u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
-    // weights -> swizzled shared image: 6 blocks (pass, kx) of 6*NP rows
-    for (int idx = tid; idx < 6 * 6 * NP * (KC / 4); idx += RG_THREADS) {
+    // weights -> swizzled shared images: 3 fp32 blocks (pass A, per kx, 6*NP rows of KC floats) and 3 fp16 blocks (pass B)
+    for (int idx = tid; idx < 3 * 6 * NP * (KC / 4); idx += RG_THREADS) {
         const int j = idx % (KC / 4);
         const int r = (idx / (KC / 4)) % (6 * NP);
         const int blk = idx / ((KC / 4) * 6 * NP);
         const float4 v = ldg4(p.wpk + ((size_t)blk * 6 * NP + r) * KC + j * 4);
         *reinterpret_cast<float4*>(gB + blk * WBLK + swz_off<KC>(r, j)) = v;
+    }
+    {
+        const float* wh = p.wpk + (size_t)3 * 6 * NP * KC;      // fp16 data, KC/2 floats per row
+        for (int idx = tid; idx < 3 * 6 * NP * (KC / 8); idx += RG_THREADS) {
+            const int j = idx % (KC / 8);
+            const int r = (idx / (KC / 8)) % (6 * NP);
+            const int blk = idx / ((KC / 8) * 6 * NP);
+            const float4 v = ldg4(wh + ((size_t)blk * 6 * NP + r) * (KC / 2) + j * 4);
+            *reinterpret_cast<float4*>(gBH + blk * WBLKH + swz_rb<ROWH>(r, j)) = v;
+        }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc_fence_before();
@@ -252,9 +299,21 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
             // Everything below is indexed by compile-time constants only (fully unrolled): a run table in local memory
             // made the single issuing thread spend ~450 cycles per MMA on dependent local loads.
             const uint64_t b_desc0 = make_desc<KC>(sB);
-            auto issue = [&](const Cursor& c, int pass) {
+            const uint64_t bh_desc0 = make_desc_rb<ROWH>(sBH);
+            auto issue = [&](const Cursor& c, auto pass_tag) {
+                // PASS 0: raw fp32 row x [w_hi | 2^10 w_lo] (kind::tf32, K = 8 floats per MMA);
+                // PASS 1: fp16(2^10 x_lo) row x [0 | fp16(w_hi)] (kind::f16, K = 16 halves per MMA, half the operand bytes)
+                constexpr int PASS = decltype(pass_tag)::value;
+                constexpr uint32_t RB = PASS ? ROWH : ROWB;
+                constexpr uint32_t WB = PASS ? WBLKH : WBLK;
+                constexpr int KSP = PASS ? KC / 16 : KC / 8;
+                constexpr uint32_t IDB = PASS ? ((1u << 4) | ((128u >> 4) << 24)) : IDESC_BASE;    // f16: a/b format 0 = F16
+                auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+                    if (PASS) tc_mma_f16(d, da, db, idesc, acc);
+                    else tc_mma_tf32(d, da, db, idesc, acc);
+                };
                 const int sb = c.g % NBUF;
-                const uint64_t a_desc = make_desc<KC>(sbase + sb * A_STRIDE);
+                const uint64_t a_desc = PASS ? make_desc_rb<ROWH>(sH + sb * H_STRIDE) : make_desc<KC>(sbase + sb * A_STRIDE);
                 const int kylo = max(0, c.t - c.rows + 1), kyhi = min(2, c.t);   // output row = y0 + t - ky inside the item
                 // slot(orow) = RING-1 - (orow % RING); ky ascending <=> orow descending <=> slot ascending (mod RING)
                 int slot[3], runn[3];   // runn[ky] > 0: a run of runn adjacent slots starts at ky
@@ -266,18 +325,18 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
                 runn[0] = v0 ? 1 + (j01 ? 1 + (j12 ? 1 : 0) : 0) : 0;
                 runn[1] = (v1 && !j01) ? 1 + (j12 ? 1 : 0) : 0;
                 runn[2] = (v2 && !j12) ? 1 : 0;
-                const bool has_fresh = (pass == 0 && v0);   // ky = 0 is the FIRST contribution to its output row
+                const bool has_fresh = (PASS == 0 && v0);   // ky = 0 is the FIRST contribution to its output row
                 if (has_fresh) {
                     // the fresh slot is about to be overwritten: its previous row must have been drained
                     const int orow = c.orow0 + c.t;
                     mbar_wait_t(ABAR(ACCE, slot[0]), (((uint32_t)(orow / RING)) & 1u) ^ 1u, w_acce, timing);
                     tc_fence_after();
                 }
-                const uint64_t b_pass = b_desc0 + (((uint32_t)(pass * 3) * WBLK) >> 4);
-                constexpr uint32_t IDESC3 = IDESC_BASE | ((uint32_t)((3 * SLOT) >> 3) << 17);
-                constexpr uint32_t IDESC2 = IDESC_BASE | ((uint32_t)((2 * SLOT) >> 3) << 17);
-                constexpr uint32_t IDESC1 = IDESC_BASE | ((uint32_t)(SLOT >> 3) << 17);
-                constexpr uint32_t KYB = (SLOT * ROWB) >> 4;     // descriptor offset of one ky weight block
+                const uint64_t b_pass = PASS ? bh_desc0 : b_desc0;
+                constexpr uint32_t IDESC3 = IDB | ((uint32_t)((3 * SLOT) >> 3) << 17);
+                constexpr uint32_t IDESC2 = IDB | ((uint32_t)((2 * SLOT) >> 3) << 17);
+                constexpr uint32_t IDESC1 = IDB | ((uint32_t)(SLOT >> 3) << 17);
+                constexpr uint32_t KYB = (SLOT * RB) >> 4;     // descriptor offset of one ky weight block
                 // Interior rows (all three taps valid) take one of three fully unrolled code paths whose MMA operands
                 // are base + compile-time constants and whose instruction descriptors are immediates — the single
                 // issuing thread pays ~6 instructions per MMA instead of ~40 dependent ones on the generic path:
@@ -292,26 +351,26 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
 #pragma unroll
                     for (int kx = 0; kx < 3; ++kx) {
 #pragma unroll
-                        for (int k = 0; k < KS; ++k) {
-                            const uint64_t a_k = a_desc + (((uint32_t)kx * ROWB + (uint32_t)k * 32u) >> 4);
-                            const uint64_t b_k = b_pass + (((uint32_t)kx * WBLK + (uint32_t)k * 32u) >> 4);
+                        for (int k = 0; k < KSP; ++k) {
+                            const uint64_t a_k = a_desc + (((uint32_t)kx * RB + (uint32_t)k * 32u) >> 4);
+                            const uint64_t b_k = b_pass + (((uint32_t)kx * WB + (uint32_t)k * 32u) >> 4);
                             const bool first = (kx == 0 && k == 0);
-                            if (first && pass == 0) {
-                                tc_mma_tf32(d0, a_k, b_k, IDESC1, 0u);                    // fresh row: overwrite its slot
+                            if (first && PASS == 0) {
+                                mma(d0, a_k, b_k, IDESC1, 0u);                    // fresh row: overwrite its slot
                                 if (SPLIT == 1 || SPLIT == 0) {
-                                    tc_mma_tf32(d1, a_k, b_k + KYB, IDESC2, 1u);          // ky 1,2 adjacent
+                                    mma(d1, a_k, b_k + KYB, IDESC2, 1u);          // ky 1,2 adjacent
                                 } else {
-                                    tc_mma_tf32(d1, a_k, b_k + KYB, IDESC1, 1u);
-                                    tc_mma_tf32(d2, a_k, b_k + 2 * KYB, IDESC1, 1u);
+                                    mma(d1, a_k, b_k + KYB, IDESC1, 1u);
+                                    mma(d2, a_k, b_k + 2 * KYB, IDESC1, 1u);
                                 }
                             } else if (SPLIT == 0) {
-                                tc_mma_tf32(d0, a_k, b_k, IDESC3, 1u);
+                                mma(d0, a_k, b_k, IDESC3, 1u);
                             } else if (SPLIT == 1) {
-                                tc_mma_tf32(d0, a_k, b_k, IDESC1, 1u);
-                                tc_mma_tf32(d1, a_k, b_k + KYB, IDESC2, 1u);
+                                mma(d0, a_k, b_k, IDESC1, 1u);
+                                mma(d1, a_k, b_k + KYB, IDESC2, 1u);
                             } else {
-                                tc_mma_tf32(d0, a_k, b_k, IDESC2, 1u);
-                                tc_mma_tf32(d2, a_k, b_k + 2 * KYB, IDESC1, 1u);
+                                mma(d0, a_k, b_k, IDESC2, 1u);
+                                mma(d2, a_k, b_k + 2 * KYB, IDESC1, 1u);
                             }
                         }
                     }
@@ -327,25 +386,25 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky) {
                     d_run[ky] = tmem + (uint32_t)(slot[ky] * SLOT);
-                    i_run[ky] = IDESC_BASE | ((uint32_t)((runn[ky] * SLOT) >> 3) << 17);
+                    i_run[ky] = IDB | ((uint32_t)((runn[ky] * SLOT) >> 3) << 17);
                 }
                 if (has_fresh) {
-                    tc_mma_tf32(d_run[0], a_desc, b_pass, IDESC1, 0u);
+                    mma(d_run[0], a_desc, b_pass, IDESC1, 0u);
                     if (runn[0] > 1)
-                        tc_mma_tf32(d_run[0] + SLOT, a_desc, b_pass + KYB,
-                                    IDESC_BASE | ((uint32_t)(((runn[0] - 1) * SLOT) >> 3) << 17), 1u);
+                        mma(d_run[0] + SLOT, a_desc, b_pass + KYB,
+                                    IDB | ((uint32_t)(((runn[0] - 1) * SLOT) >> 3) << 17), 1u);
                 }
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx) {
 #pragma unroll
-                    for (int k = 0; k < KS; ++k) {
-                        const uint64_t a_k = a_desc + (((uint32_t)kx * ROWB + (uint32_t)k * 32u) >> 4);
+                    for (int k = 0; k < KSP; ++k) {
+                        const uint64_t a_k = a_desc + (((uint32_t)kx * RB + (uint32_t)k * 32u) >> 4);
 #pragma unroll
                         for (int ky = 0; ky < 3; ++ky) {
                             if (runn[ky] == 0) continue;
                             if (ky == 0 && kx == 0 && k == 0 && has_fresh) continue;     // issued above
-                            const uint32_t boff = (uint32_t)kx * WBLK + (uint32_t)ky * (SLOT * ROWB) + (uint32_t)k * 32u;
-                            tc_mma_tf32(d_run[ky], a_k, b_pass + (boff >> 4), i_run[ky], 1u);
+                            const uint32_t boff = (uint32_t)kx * WB + (uint32_t)ky * (SLOT * RB) + (uint32_t)k * 32u;
+                            mma(d_run[ky], a_k, b_pass + (boff >> 4), i_run[ky], 1u);
                         }
                     }
                 }
@@ -356,7 +415,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
                     const int sb = ca.g % NBUF;
                     mbar_wait_t(SBAR(FULL, sb), ((uint32_t)(ca.g / NBUF)) & 1u, w_full, timing);
                     tc_fence_after();
-                    issue(ca, 0);
+                    issue(ca, std::integral_constant<int, 0>{});
                     tc_commit(SBAR(P12, sb));                     // raw row consumed -> split warps
                     mbar_arrive(SBAR(ISS, sb));                   // pass A of this row is in the tensor queue
                 }
@@ -377,7 +436,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
                     mbar_wait(SBAR(ISS, ga % NBUF), ((uint32_t)(ga / NBUF)) & 1u);
                     mbar_wait_t(SBAR(LO, sb), ((uint32_t)(cb.g / NBUF)) & 1u, w_lo, timing);
                     tc_fence_after();
-                    issue(cb, 1);
+                    issue(cb, std::integral_constant<int, 1>{});
                     tc_commit(SBAR(EMPTY, sb));                   // stage buffer free -> producer
                     if (cb.t >= 2) {                              // output row y0 + t - 2 is complete
                         const int orow = cb.orow0 + cb.t - 2;
@@ -426,7 +485,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
                 float* op = p.out + opix * p.ldo;
                 float v[NP];
 #pragma unroll
-                for (int c = 0; c < NP; ++c) v[c] = (acc[c] + acc[NP + c]) + biasr[c];
+                for (int c = 0; c < NP; ++c) v[c] = fmaf(acc[NP + c], 1.f / RG_LO_SCALE, acc[c]) + biasr[c];
                 if (p.res) {
                     const float* rp = p.res + opix * p.ldr;
                     if (p.res_bcast) {
@@ -475,11 +534,22 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
             const int sb = c.g % NBUF;
             mbar_wait_t(SBAR(P12, sb), ((uint32_t)(c.g / NBUF)) & 1u, w_p12, timing);   // pass A has consumed the raw row
             tc_fence_after();
-            float4* a4 = reinterpret_cast<float4*>(gbase + sb * A_STRIDE);
-            for (int idx = tid; idx < (int)(A_BYTES / 16); idx += RG_SPLIT_THREADS) {
-                float4 v = a4[idx];
-                v.x = tf32_lo(v.x); v.y = tf32_lo(v.y); v.z = tf32_lo(v.z); v.w = tf32_lo(v.w);
-                a4[idx] = v;
+            const uint8_t* a8 = gbase + sb * A_STRIDE;
+            uint8_t* h8 = gH + sb * H_STRIDE;
+            // one unit = 8 channels of one pixel: two 16-byte fp32 chunks in, one 16-byte fp16 chunk out
+            for (int idx = tid; idx < RG_BOXW * (KC / 8); idx += RG_SPLIT_THREADS) {
+                const int px = idx / (KC / 8), u = idx - px * (KC / 8);
+                const float4 v0 = *reinterpret_cast<const float4*>(a8 + swz_off<KC>(px, 2 * u));
+                const float4 v1 = *reinterpret_cast<const float4*>(a8 + swz_off<KC>(px, 2 * u + 1));
+                auto lo16 = [](float a, float b) {
+                    const float la = fminf(fmaxf(tf32_lo(a) * RG_LO_SCALE, -65504.f), 65504.f);
+                    const float lb = fminf(fmaxf(tf32_lo(b) * RG_LO_SCALE, -65504.f), 65504.f);
+                    const __half2 h = __floats2half2_rn(la, lb);
+                    return *reinterpret_cast<const uint32_t*>(&h);
+                };
+                uint4 o;
+                o.x = lo16(v0.x, v0.y); o.y = lo16(v0.z, v0.w); o.z = lo16(v1.x, v1.y); o.w = lo16(v1.z, v1.w);
+                *reinterpret_cast<uint4*>(h8 + swz_rb<ROWH>(px, u)) = o;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(SBAR(LO, sb));
@@ -515,8 +585,9 @@ template <int KC, int NP, int NBUF, int LAG>
 int launch_ring(const CUtensorMap& tmap, RgP p, cudaStream_t s) {
     constexpr uint32_t ROWB = KC * 4;
     constexpr uint32_t A_STRIDE = ((RG_BOXW * ROWB) + 1023u) & ~1023u;
-    constexpr uint32_t B_BYTES = 6 * 6 * NP * ROWB;
-    const size_t smem = NBUF * A_STRIDE + B_BYTES + 1024;
+    constexpr uint32_t H_STRIDE = ((RG_BOXW * KC * 2) + 1023u) & ~1023u;
+    constexpr uint32_t B_BYTES = 3 * 6 * NP * ROWB + 3 * 6 * NP * KC * 2;
+    const size_t smem = NBUF * (A_STRIDE + H_STRIDE) + B_BYTES + 1024;
     auto kern = conv3x3_tc_ring_kernel<KC, NP, NBUF, LAG>;
     static bool configured = false;
     if (!configured) {

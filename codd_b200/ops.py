@@ -168,8 +168,10 @@ def pack_conv_weight_tc(w):
 
 
 def pack_conv_weight_ring(w):
-    """torch [Cout,Cin,3,3] -> [2 pass][3 kx][6*NP][KC] for codd_conv3x3_tc_ring: per (pass, kx) block the rows are,
-    for ky = 0,1,2, [w_hi (NP) | w_lo (NP)] (pass 0) or [w_hi (NP) | 0 (NP)] (pass 1)."""
+    """torch [Cout,Cin,3,3] -> flat fp32 buffer for codd_conv3x3_tc_ring:
+    pass A  [3 kx][6*NP rows][KC] fp32 — rows per ky = [w_hi (NP) | 2^10 * w_lo (NP)]   (tf32 halves of the weight),
+    pass B  [3 kx][6*NP rows][KC] fp16 — rows per ky = [0 (NP) | fp16(w_hi) (NP)], stored as KC/2 floats per row.
+    The lo half of a TMEM slot therefore accumulates 2^10 * (x_hi*w_lo + x_lo*w_hi); the epilogue scales it back."""
     cout, cin, kh, kw = w.shape
     assert kh == 3 and kw == 3
     kc = 16 if cin <= 16 else 32
@@ -178,11 +180,12 @@ def pack_conv_weight_ring(w):
     wt[:, :, :cout, :cin] = w.detach().float().permute(2, 3, 0, 1)
     hi = _tf32_round(wt)
     lo = _tf32_round(wt - hi)
-    out = torch.zeros((2, 3, 3, 2, npad, kc), dtype=torch.float32, device=w.device)     # [pass][kx][ky][hi|lo][cout][cin]
-    out[0, :, :, 0] = hi.permute(1, 0, 2, 3)
-    out[0, :, :, 1] = lo.permute(1, 0, 2, 3)
-    out[1, :, :, 0] = hi.permute(1, 0, 2, 3)
-    return out.reshape(2, 3, 6 * npad, kc).contiguous()
+    pa = torch.zeros((3, 3, 2, npad, kc), dtype=torch.float32, device=w.device)         # [kx][ky][hi|lo][cout][cin]
+    pa[:, :, 0] = hi.permute(1, 0, 2, 3)
+    pa[:, :, 1] = lo.permute(1, 0, 2, 3) * 1024.0
+    pb = torch.zeros((3, 3, 2, npad, kc), dtype=torch.float16, device=w.device)
+    pb[:, :, 1] = hi.permute(1, 0, 2, 3).half()
+    return torch.cat([pa.reshape(-1), pb.reshape(-1).view(torch.float32)]).contiguous()
 
 
 def conv3x3_tc_ring(x, wring, bias, cout, act=ACT_NONE, residual=None, res_bcast=False):
@@ -190,7 +193,7 @@ def conv3x3_tc_ring(x, wring, bias, cout, act=ACT_NONE, residual=None, res_bcast
     _require_cuda(x, wring, bias, residual)
     n, cin, h, w = x.shape
     out = empty_nhwc(n, cout, h, w, x.device)
-    nbytes = 4 * (n * h * w * (cin + cout) + wring.numel() // 4
+    nbytes = 4 * (n * h * w * (cin + cout) + wring.numel() // 3
                   + (0 if residual is None else n * h * w * (1 if res_bcast else cout)))
     rc = _run(f"conv3x3ring_cin{cin}_cout{cout}", nbytes, lambda: _lib.load().codd_conv3x3_tc_ring(
         x.data_ptr(), ld_of(x), cin, n, h, w, wring.data_ptr(), None if bias is None else bias.data_ptr(),

@@ -23,9 +23,11 @@ def run_conv(pw, conv, x, act, x2=None, residual=None, res_bcast=False, head=Non
     cout = conv.out_channels if head is None else head
     k, st, pd, dl = conv.kernel_size, conv.stride, conv.padding, conv.dilation[0]
     cin = x.shape[1] + (0 if x2 is None else x2.shape[1])
-    # rolling-ring kernel for everything but the tiny coarse-level layers (a strip segment needs >= ~16 rows per SM to
-    # amortise its pipeline fill; measured cross-over ~50k pixels, tools/conv_probe.py)
-    big = x.shape[0] * x.shape[2] * x.shape[3] >= 50000
+    # rolling-ring kernel for everything but the tiny coarse-level layers (a strip segment needs ~16 rows per SM to
+    # amortise its pipeline fill; measured cross-over at batch 8 between the 36x60 and 72x120 levels,
+    # tools/conv_probe.py).  The choice depends on the per-sample size only: the two kernels round differently, and a
+    # sample's result must not depend on the batch it is in.
+    big = x.shape[2] * x.shape[3] >= 4096
     if USE_TC and USE_RING and big and dl == 1 and ops.tc_eligible(cin, cout, k, st, pd, dl, x2):
         ws, b = pw.conv_ring(conv, head)
         return ops.conv3x3_tc_ring(x, ws, b, cout, act, residual=residual, res_bcast=res_bcast)

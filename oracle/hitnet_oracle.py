@@ -421,6 +421,41 @@ def stereo_matching(sd, left, right, max_disp, direct=False, return_all=False, r
     return out
 
 
+def stereo_matching_given_argmin(sd, left, right, max_disp, other_disp, rel_tol=1e-4, direct=True):
+    """End-to-end parity MODULO CERTIFIED NEAR-TIES of the arg-min initialisation.
+
+    The reference's cost volumes contain near-ties at fp32 resolution (e.g. 2.6e-9 absolute / 1.5e-5 relative between
+    the two best disparities of a tile in tests/golden/hitnet_s_128x192_d64): an implementation whose feature maps
+    differ from the reference's by one ulp may legitimately pick the other disparity, and that one discrete choice
+    changes the propagated disparity of a whole image region.  ``other_disp`` is the other implementation's arg-min
+    pyramid (5 tensors [N,1,h,w] or [N,h,w], coarse->fine).  Every tile where it differs from this oracle's arg-min is
+    checked against THIS oracle's cost volume: the cost at the other disparity must lie within ``rel_tol`` of the minimum
+    (otherwise the difference is a real error and is reported in ``uncertified``).  The certified choices are adopted and
+    the propagation is re-run, so the returned ``pred_disp`` is what the reference computes for those choices.
+    Returns dict(pred_disp, flips, uncertified)."""
+    with torch.no_grad():
+        bsd = _sub(sd, "backbone.")
+        fl, fr = backbone(bsd, left), backbone(bsd, right)
+        isd = _sub(sd, "tile_init.")
+        tiles = tile_features(isd, fl, fr)
+        hyps, cvs = tile_hypotheses(isd, tiles, fl, max_disp, return_cv=True)
+        flips = uncertified = 0
+        for k in range(5):
+            od = other_disp[k].reshape(hyps[k][:, 0].shape).to(hyps[k].dtype)
+            diff = od != hyps[k][:, 0]
+            if diff.any():
+                cmin = cvs[k].min(1)[0]
+                cother = cvs[k].gather(1, od.long().clamp(0, cvs[k].shape[1] - 1).unsqueeze(1)).squeeze(1)
+                near = (cother - cmin) <= rel_tol * cmin.abs().clamp(min=1e-6)
+                flips += int(diff.sum())
+                uncertified += int((diff & ~near).sum())
+                take = diff & near
+                hyps[k] = hyps[k].clone()
+                hyps[k][:, 0] = torch.where(take, od, hyps[k][:, 0])
+        disp = tile_propagation(_sub(sd, "tile_update."), fl, fr, hyps, direct)
+    return dict(pred_disp=disp, left_feat=fl[2], right_feat=fr[2], left_img=left, flips=flips, uncertified=uncertified)
+
+
 # --------------------------------------------------------------------------------------
 # parameters and synthetic inputs (SURVEY.md §8d: Sets U / S / G)
 # --------------------------------------------------------------------------------------

@@ -12,11 +12,24 @@ from oracle import raft3d_oracle as R
 pytestmark = pytest.mark.gpu
 
 
-def oracle_sequence(sds, lefts, rights, max_disp, intr, iters):
+def gpu_argmin(stereo, left, right):
+    """The CUDA path's arg-min initialisation pyramid (coarse->fine), as CPU tensors [N,h,w]."""
+    from codd_b200 import ops
+    with torch.no_grad():
+        fl, fr = stereo.backbone.forward_pair(left.cuda(), right.cuda())
+        _, hyps = stereo.tile_init(fl, fr)
+    return [ops.to_nchw(h).cpu()[:, 0] for h in hyps]
+
+
+def oracle_sequence(sds, lefts, rights, max_disp, intr, iters, stereo=None):
+    """``stereo``: the CUDA HITNetMF module — its arg-min initialisation is handed to the oracle, which adopts the
+    choices it can certify as near-ties of its own cost volume (oracle.stereo_matching_given_argmin) and fails on any
+    other disagreement; one such flip would otherwise change a whole image region of every later frame."""
     hsd, msd, fsd = sds
     state, preds = {}, []
     for left, right in zip(lefts, rights):
-        out = O.stereo_matching(hsd, left, right, max_disp, direct=True)
+        out = O.stereo_matching_given_argmin(hsd, left, right, max_disp, gpu_argmin(stereo, left, right))
+        assert out["uncertified"] == 0, "arg-min initialisation differs beyond a near-tie"
         out = dict(pred_disp=out["pred_disp"], left_feat=out["left_feat"], right_feat=out["right_feat"], left_img=left)
         R.motion_forward(msd, "", state, out, intr, iters)
         FO.memory_query(fsd, out, state, direct=True)
@@ -55,7 +68,7 @@ def test_full_codd_sequence_vs_oracle():
     assert isinstance(res, list) and res[0].shape == (n, frames, h - 8, w - 2)
 
     msd = {"raft3d." + k: v for k, v in rsd.items()}
-    ref, ref_out = oracle_sequence((hsd, msd, fsd), lefts, rights, max_disp, intr, iters)
+    ref, ref_out = oracle_sequence((hsd, msd, fsd), lefts, rights, max_disp, intr, iters, stereo=model.stereo)
     ref = ref[:, :, :h - 8, :w - 2]
     got = res[0].cpu()
     for t in range(frames):
