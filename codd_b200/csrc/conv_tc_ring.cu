@@ -152,6 +152,36 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t da, uint64_
         ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// MMA with descriptors given as LOW 32-bit words (start address | LBO) plus compile-time HIGH words (SBO | version |
+// swizzle mode): per-MMA operand arithmetic is one 32-bit add per descriptor and the issuing thread moves three
+// instead of five values to uniform registers.
+template <uint32_t HI_A, uint32_t HI_B, bool F16>
+__device__ __forceinline__ void tc_mma_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    if (F16) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "setp.ne.u32 p, %4, 0;\n\t"
+            "mov.b64 da, {%1, %5};\n\t"
+            "mov.b64 db, {%2, %6};\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+            ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "n"(HI_A), "n"(HI_B)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "setp.ne.u32 p, %4, 0;\n\t"
+            "mov.b64 da, {%1, %5};\n\t"
+            "mov.b64 db, {%2, %6};\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t}"
+            ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "n"(HI_A), "n"(HI_B)
+            : "memory");
+    }
+}
+template <int RB>
+__host__ __device__ constexpr uint32_t desc_hi() {   // high word of make_desc_rb<RB>
+    return ((8u * RB) >> 4) | (1u << 14) | (((RB == 128) ? 2u : (RB == 64) ? 4u : 6u) << 29);
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
 constexpr float RG_LO_SCALE = 1024.f;   // x_lo and w_lo travel scaled by 2^10 (fp16 range); the epilogue undoes it
 
 // Cursor over the staged rows a CTA processes: items (sample, column strip, row segment) in grid-stride order, and
@@ -298,8 +328,8 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
             const long long t_start = clock64();
             // Everything below is indexed by compile-time constants only (fully unrolled): a run table in local memory
             // made the single issuing thread spend ~450 cycles per MMA on dependent local loads.
-            const uint64_t b_desc0 = make_desc<KC>(sB);
-            const uint64_t bh_desc0 = make_desc_rb<ROWH>(sBH);
+            const uint32_t b_desc0 = desc_lo(sB);
+            const uint32_t bh_desc0 = desc_lo(sBH);
             auto issue = [&](const Cursor& c, auto pass_tag) {
                 // PASS 0: raw fp32 row x [w_hi | 2^10 w_lo] (kind::tf32, K = 8 floats per MMA);
                 // PASS 1: fp16(2^10 x_lo) row x [0 | fp16(w_hi)] (kind::f16, K = 16 halves per MMA, half the operand bytes)
@@ -308,12 +338,11 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
                 constexpr uint32_t WB = PASS ? WBLKH : WBLK;
                 constexpr int KSP = PASS ? KC / 16 : KC / 8;
                 constexpr uint32_t IDB = PASS ? ((1u << 4) | ((128u >> 4) << 24)) : IDESC_BASE;    // f16: a/b format 0 = F16
-                auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
-                    if (PASS) tc_mma_f16(d, da, db, idesc, acc);
-                    else tc_mma_tf32(d, da, db, idesc, acc);
+                auto mma = [&](uint32_t d, uint32_t da, uint32_t db, uint32_t idesc, uint32_t acc) {
+                    tc_mma_lo<desc_hi<(int)RB>(), desc_hi<(int)RB>(), PASS != 0>(d, da, db, idesc, acc);
                 };
                 const int sb = c.g % NBUF;
-                const uint64_t a_desc = PASS ? make_desc_rb<ROWH>(sH + sb * H_STRIDE) : make_desc<KC>(sbase + sb * A_STRIDE);
+                const uint32_t a_desc = desc_lo(PASS ? sH + sb * H_STRIDE : sbase + sb * A_STRIDE);
                 const int kylo = max(0, c.t - c.rows + 1), kyhi = min(2, c.t);   // output row = y0 + t - ky inside the item
                 // slot(orow) = RING-1 - (orow % RING); ky ascending <=> orow descending <=> slot ascending (mod RING)
                 int slot[3], runn[3];   // runn[ky] > 0: a run of runn adjacent slots starts at ky
@@ -332,7 +361,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
                     mbar_wait_t(ABAR(ACCE, slot[0]), (((uint32_t)(orow / RING)) & 1u) ^ 1u, w_acce, timing);
                     tc_fence_after();
                 }
-                const uint64_t b_pass = PASS ? bh_desc0 : b_desc0;
+                const uint32_t b_pass = PASS ? bh_desc0 : b_desc0;
                 constexpr uint32_t IDESC3 = IDB | ((uint32_t)((3 * SLOT) >> 3) << 17);
                 constexpr uint32_t IDESC2 = IDB | ((uint32_t)((2 * SLOT) >> 3) << 17);
                 constexpr uint32_t IDESC1 = IDB | ((uint32_t)(SLOT >> 3) << 17);
@@ -352,8 +381,8 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
                     for (int kx = 0; kx < 3; ++kx) {
 #pragma unroll
                         for (int k = 0; k < KSP; ++k) {
-                            const uint64_t a_k = a_desc + (((uint32_t)kx * RB + (uint32_t)k * 32u) >> 4);
-                            const uint64_t b_k = b_pass + (((uint32_t)kx * WB + (uint32_t)k * 32u) >> 4);
+                            const uint32_t a_k = a_desc + (((uint32_t)kx * RB + (uint32_t)k * 32u) >> 4);
+                            const uint32_t b_k = b_pass + (((uint32_t)kx * WB + (uint32_t)k * 32u) >> 4);
                             const bool first = (kx == 0 && k == 0);
                             if (first && PASS == 0) {
                                 mma(d0, a_k, b_k, IDESC1, 0u);                    // fresh row: overwrite its slot
@@ -398,7 +427,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
                 for (int kx = 0; kx < 3; ++kx) {
 #pragma unroll
                     for (int k = 0; k < KSP; ++k) {
-                        const uint64_t a_k = a_desc + (((uint32_t)kx * RB + (uint32_t)k * 32u) >> 4);
+                        const uint32_t a_k = a_desc + (((uint32_t)kx * RB + (uint32_t)k * 32u) >> 4);
 #pragma unroll
                         for (int ky = 0; ky < 3; ++ky) {
                             if (runn[ky] == 0) continue;
