@@ -125,7 +125,7 @@ constexpr int K4_THREADS = K4_PXW * 4;    // one thread per pixel of the 4-row s
 // pixels, so every per-channel tap load is a (nearly) contiguous 128-byte request — one L1
 // wavefront — where the NHWC layout costs 16 (lanes 64 B apart).  The left features stay NHWC:
 // each lane reads its own pixel's channels once.
-constexpr int K4_STAGE_BYTES = 92 * 1024;   // shared-memory budget of the staged right-feature window (2 CTAs / SM)
+constexpr int K4_STAGE_BYTES = 58 * 1024;   // shared-memory budget of the staged right-feature window (2 CTAs / SM)
 
 // Channel loop of K4 on a STAGED window: the CTA's right-feature window (all taps of its 64 x 4 pixels) sits in shared
 // memory as [row][x][C + 4] (channel innermost, pitch C+4 floats => the 128-bit reads of 8 horizontally adjacent
@@ -170,7 +170,7 @@ __device__ __forceinline__ void k4_channels_staged(const float* __restrict__ flp
 }
 
 template <int NSETS>
-__global__ void __launch_bounds__(K4_THREADS, 2) tile_warp_cost_kernel(WarpP p) {
+__global__ void __launch_bounds__(K4_THREADS, 3) tile_warp_cost_kernel(WarpP p) {
     __shared__ __align__(16) float s_raw[NSETS][K4_TILES][64];
     __shared__ __align__(16) float s_dec[NSETS][K4_TILES][16];
     __shared__ __align__(16) float s_wt[64][16];
@@ -212,6 +212,7 @@ __global__ void __launch_bounds__(K4_THREADS, 2) tile_warp_cost_kernel(WarpP p) 
     int colA[NSETS][3], colB[NSETS][3];
     bool paired = true, two_rows = false, row1_ok = false;
     int y0 = 0;
+    int lxlo = 0x7fffffff, lxhi = -1, lrlo = 0x7fffffff, lrhi = -1;   // this pixel's window (empty when the pixel is off)
     if (on) {
         const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
         const float wdiv = (float)max(W - 1, 1), hdiv = (float)max(H - 1, 1);
@@ -258,10 +259,18 @@ __global__ void __launch_bounds__(K4_THREADS, 2) tile_warp_cost_kernel(WarpP p) 
                 wD[s][ki] = (vb && row1_ok) ? __fmul_rn(fn, tp[s].fw[ki]) : 0.f;
             }
         }
-        atomicMin(&s_rng[0], xlo);
-        atomicMax(&s_rng[1], xhi);
-        atomicMin(&s_rng[2], y0);
-        atomicMax(&s_rng[3], (two_rows && row1_ok) ? y0 + 1 : y0);
+        lxlo = xlo; lxhi = xhi; lrlo = y0; lrhi = (two_rows && row1_ok) ? y0 + 1 : y0;
+    }
+    // CTA-wide window: warp reductions first (256 same-address shared atomics serialise), one atomic per warp
+    lxlo = __reduce_min_sync(0xffffffffu, lxlo);
+    lxhi = __reduce_max_sync(0xffffffffu, lxhi);
+    lrlo = __reduce_min_sync(0xffffffffu, lrlo);
+    lrhi = __reduce_max_sync(0xffffffffu, lrhi);
+    if ((tid & 31) == 0 && lxhi >= 0) {
+        atomicMin(&s_rng[0], lxlo);
+        atomicMax(&s_rng[1], lxhi);
+        atomicMin(&s_rng[2], lrlo);
+        atomicMax(&s_rng[3], lrhi);
     }
     __syncthreads();
     const int xlo = s_rng[0], rlo = s_rng[2];
