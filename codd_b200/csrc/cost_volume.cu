@@ -60,11 +60,10 @@ struct CvP {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 template <bool WRITE_CV, bool ARGMIN>
-__global__ void __launch_bounds__(CV_MAXW * 32, 2) cost_volume_kernel(CvP p) {
+__device__ __forceinline__ void cost_volume_body(const CvP& p, int b) {
     extern __shared__ float4 smem4[];
     __shared__ __align__(8) unsigned long long mbar;
     const int qmax = (p.D + 2) >> 2;             // q in [0, qmax];  d = 4q - r
-    int b = blockIdx.x;
     const int jblk = b % p.nblk;
     b /= p.nblk;
     const int i = b % p.h;
@@ -314,6 +313,51 @@ __global__ void __launch_bounds__(CV_MAXW * 32, 2) cost_volume_kernel(CvP p) {
     }
 }
 
+template <bool WRITE_CV, bool ARGMIN>
+__global__ void __launch_bounds__(CV_MAXW * 32, 2) cost_volume_kernel(CvP p) {
+    cost_volume_body<WRITE_CV, ARGMIN>(p, (int)blockIdx.x);
+}
+
+// All levels of the tile-initialisation pyramid in ONE launch: the four coarse levels (6-30 us each, latency bound when
+// launched alone) fill the tail of the finest level's last wave.  Blocks are ordered finest level first.
+constexpr int CV_MAXLEV = 8;
+struct CvPyr {
+    CvP lv[CV_MAXLEV];
+    int first[CV_MAXLEV + 1];   // first[l] = first block of level l (in launch order)
+    int nlev;
+};
+template <bool WRITE_CV, bool ARGMIN>
+__global__ void __launch_bounds__(CV_MAXW * 32, 2) cost_volume_pyramid_kernel(const __grid_constant__ CvPyr P) {
+    int l = 0;
+    while (l + 1 < P.nlev && (int)blockIdx.x >= P.first[l + 1]) ++l;
+    cost_volume_body<WRITE_CV, ARGMIN>(P.lv[l], (int)blockIdx.x - P.first[l]);
+}
+
+}  // namespace
+
+namespace {
+// column blocking of one level; returns the dynamic shared-memory bytes for `nwarps_launch` warps, or 0 if unsupported
+size_t cv_setup(CvP& p, const float* tile_l, const float* tile_r, int n, int h, int w, int max_disp, float* cv,
+                float* min_cost, float* min_disp, int* nwarps_needed, int nwarps_launch) {
+    const int qmax = (max_disp + 2) / 4;
+    const int max_m = CV_MAXW * 32;
+    if (qmax + 1 > max_m) return 0;
+    int nblk = 1;
+    while (nblk < w && codd_ceil_div(w, nblk) + (nblk > 1 ? qmax : 0) > max_m) ++nblk;
+    const int JB = codd_ceil_div(w, nblk);
+    nblk = codd_ceil_div(w, JB);
+    const int nm = (nblk > 1) ? JB + qmax : w;   // single block: m in [0, w)
+    if (nm > max_m) return 0;
+    const int nwarps = codd_ceil_div(nm, 32);
+    *nwarps_needed = nwarps;
+    const int nw = nwarps_launch > 0 ? nwarps_launch : nwarps;
+    const int RW = 4 * nm + 4;
+    const int LW = (JB + 3) & ~3;
+    p.L = tile_l; p.R = tile_r;
+    p.N = n; p.h = h; p.w = w; p.D = max_disp; p.JB = JB; p.nblk = nblk;
+    p.cv = cv; p.min_cost = min_cost; p.min_disp = min_disp;
+    return (size_t)(CV_C * RW + CV_C * CV_LW + LW + 2 * nw * LW) * sizeof(float);
+}
 }  // namespace
 
 extern "C" int codd_cost_volume(const float* tile_l, const float* tile_r, int n, int h, int w, int max_disp,
@@ -322,27 +366,11 @@ extern "C" int codd_cost_volume(const float* tile_l, const float* tile_r, int n,
     if (!codd_aligned16(tile_r)) return CODD_E_ALIGN;   // bulk-TMA source rows (4w floats) must be 16-byte aligned
     const bool argmin = (min_cost != nullptr) || (min_disp != nullptr);
     if (!cv && !argmin) return CODD_E_BADARG;
-    const int qmax = (max_disp + 2) / 4;
-    // columns per CTA: the m-range (JB + qmax values, one lane each) must fit CV_MAXW warps
-    const int max_m = CV_MAXW * 32;
-    if (qmax + 1 > max_m) return CODD_E_SHAPE;
-    int nblk = 1;
-    while (nblk < w && codd_ceil_div(w, nblk) + (nblk > 1 ? qmax : 0) > max_m) ++nblk;
-    const int JB = codd_ceil_div(w, nblk);
-    nblk = codd_ceil_div(w, JB);
-    const int nm = (nblk > 1) ? JB + qmax : w;   // single block: m in [0, w)
-    if (nm > max_m) return CODD_E_SHAPE;
-    const int nwarps = codd_ceil_div(nm, 32);
-    const int RW = 4 * nm + 4;
-    const int LW = (JB + 3) & ~3;
-    const size_t smem = (size_t)(CV_C * RW + CV_C * CV_LW + LW + 2 * nwarps * LW) * sizeof(float);
-    if (smem > 227 * 1024) return CODD_E_SHAPE;
-
     CvP p;
-    p.L = tile_l; p.R = tile_r;
-    p.N = n; p.h = h; p.w = w; p.D = max_disp; p.JB = JB; p.nblk = nblk;
-    p.cv = cv; p.min_cost = min_cost; p.min_disp = min_disp;
-    dim3 grid((unsigned)(n * h * nblk)), block(32 * nwarps);
+    int nwarps = 0;
+    const size_t smem = cv_setup(p, tile_l, tile_r, n, h, w, max_disp, cv, min_cost, min_disp, &nwarps, 0);
+    if (smem == 0 || smem > 227 * 1024) return CODD_E_SHAPE;
+    dim3 grid((unsigned)(n * h * p.nblk)), block(32 * nwarps);
     cudaStream_t s = (cudaStream_t)stream;
     void (*kern)(CvP) = nullptr;
     static size_t configured[3] = {48 * 1024, 48 * 1024, 48 * 1024};
@@ -356,6 +384,57 @@ extern "C" int codd_cost_volume(const float* tile_l, const float* tile_r, int n,
         configured[slot] = smem;
     }
     kern<<<grid, block, smem, s>>>(p);
+    CODD_RETURN_IF_CUDA_ERROR();
+    return 0;
+}
+
+extern "C" int codd_cost_volume_pyramid(int levels, const float* const* tile_l, const float* const* tile_r, int n,
+                                        const int* h, const int* w, const int* max_disp, float* const* cv,
+                                        float* const* min_cost, float* const* min_disp, void* stream) {
+    if (levels <= 0 || levels > CV_MAXLEV || !tile_l || !tile_r || !h || !w || !max_disp || n <= 0) return CODD_E_BADARG;
+    const bool want_cv = cv && cv[0];
+    const bool argmin = (min_cost && min_cost[0]) || (min_disp && min_disp[0]);
+    if (!want_cv && !argmin) return CODD_E_BADARG;
+    CvPyr P;
+    P.nlev = levels;
+    // launch order: largest level first
+    int order[CV_MAXLEV];
+    for (int i = 0; i < levels; ++i) order[i] = i;
+    for (int i = 0; i < levels; ++i)
+        for (int j = i + 1; j < levels; ++j)
+            if ((long long)h[order[j]] * w[order[j]] * max_disp[order[j]] > (long long)h[order[i]] * w[order[i]] * max_disp[order[i]]) {
+                const int t = order[i]; order[i] = order[j]; order[j] = t;
+            }
+    size_t smem = 0;
+    int nblocks = 0;
+    for (int i = 0; i < levels; ++i) {
+        const int l = order[i];
+        if (!tile_l[l] || !tile_r[l] || h[l] <= 0 || w[l] <= 0 || max_disp[l] <= 0) return CODD_E_BADARG;
+        if (!codd_aligned16(tile_r[l])) return CODD_E_ALIGN;
+        if ((want_cv && !cv[l]) || (min_cost && min_cost[0] && !min_cost[l]) || (min_disp && min_disp[0] && !min_disp[l]))
+            return CODD_E_BADARG;
+        int nwarps = 0;
+        const size_t sm = cv_setup(P.lv[i], tile_l[l], tile_r[l], n, h[l], w[l], max_disp[l], want_cv ? cv[l] : nullptr,
+                                   (min_cost && min_cost[0]) ? min_cost[l] : nullptr,
+                                   (min_disp && min_disp[0]) ? min_disp[l] : nullptr, &nwarps, CV_MAXW);
+        if (sm == 0 || sm > 227 * 1024) return CODD_E_SHAPE;
+        smem = sm > smem ? sm : smem;
+        P.first[i] = nblocks;
+        nblocks += n * h[l] * P.lv[i].nblk;
+    }
+    P.first[levels] = nblocks;
+    void (*kern)(const CvPyr) = nullptr;
+    static size_t configured[3] = {48 * 1024, 48 * 1024, 48 * 1024};
+    int slot;
+    if (want_cv && argmin) { kern = cost_volume_pyramid_kernel<true, true>; slot = 0; }
+    else if (want_cv) { kern = cost_volume_pyramid_kernel<true, false>; slot = 1; }
+    else { kern = cost_volume_pyramid_kernel<false, true>; slot = 2; }
+    if (smem > configured[slot]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        configured[slot] = smem;
+    }
+    kern<<<(unsigned)nblocks, CV_MAXW * 32, smem, (cudaStream_t)stream>>>(P);
     CODD_RETURN_IF_CUDA_ERROR();
     return 0;
 }

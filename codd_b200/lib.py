@@ -41,6 +41,8 @@ SIGNATURES = {
                                     c_void_p]),
     "codd_tile_features": (c_int, [_FP, c_int, c_int, c_int, c_int, c_int, _FP, _FP, _FP, _FP, c_int, _FP, c_void_p]),
     "codd_cost_volume": (c_int, [_FP, _FP, c_int, c_int, c_int, c_int, _FP, _FP, _FP, c_void_p]),
+    "codd_cost_volume_pyramid": (c_int, [c_int, POINTER(c_void_p), POINTER(c_void_p), c_int, POINTER(c_int), POINTER(c_int),
+                                         POINTER(c_int), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), c_void_p]),
     "codd_tile_hyp_init": (c_int, [_FP, _FP, _FP, c_int, c_int, _FP, _FP, c_int, c_int, c_int, _FP, c_int,
                                    c_void_p]),
     "codd_plane_upsample": (c_int, [_FP, c_int, c_int, c_int, c_int, c_int, c_float, _FP, c_int, c_void_p]),

@@ -382,6 +382,36 @@ def cost_volume(tile_l, tile_r, max_disp, want_cv=False, want_argmin=True):
     return cv, mc, md
 
 
+def cost_volume_pyramid(tiles, max_disps, want_cv=False, want_argmin=True):
+    """K1 for all levels in one launch.  tiles: list of (tile_l [N,16,h,w], tile_r [N,16,h,4w]); max_disps: per level.
+    Returns a list of (cv | None, min_cost | None, min_disp | None) per level, bit-identical to ops.cost_volume."""
+    nl = len(tiles)
+    tls = [planar(t[0]) for t in tiles]
+    trs = [planar(t[1]) for t in tiles]
+    _require_cuda(*tls, *trs)
+    n = tls[0].shape[0]
+    dev = tls[0].device
+    outs, nbytes = [], 0
+    for tl, tr, d in zip(tls, trs, max_disps):
+        _, c, h, w = tl.shape
+        if c != 16 or tr.shape != (n, 16, h, 4 * w):
+            raise _lib.CoddError("cost_volume_pyramid expects [N,16,h,w] / [N,16,h,4w] pairs")
+        cv = torch.empty((n, d, h, w), device=dev, dtype=torch.float32) if want_cv else None
+        mc = torch.empty((n, 1, h, w), device=dev, dtype=torch.float32) if want_argmin else None
+        md = torch.empty((n, 1, h, w), device=dev, dtype=torch.float32) if want_argmin else None
+        outs.append((cv, mc, md))
+        nbytes += cost_volume_bytes(n, h, w, d, want_cv, want_argmin)
+    arr = lambda vals: (ctypes.c_void_p * nl)(*[None if v is None else v.data_ptr() for v in vals])
+    iarr = lambda vals: (ctypes.c_int * nl)(*vals)
+    tag = "cost_volume_pyramid_" + ("build" if want_cv else "") + ("argmin" if want_argmin else "")
+    rc = _run(tag, nbytes, lambda: _lib.load().codd_cost_volume_pyramid(
+        nl, arr(tls), arr(trs), n, iarr([t.shape[2] for t in tls]), iarr([t.shape[3] for t in tls]), iarr(list(max_disps)),
+        arr([o[0] for o in outs]) if want_cv else None, arr([o[1] for o in outs]) if want_argmin else None,
+        arr([o[2] for o in outs]) if want_argmin else None, _stream()))
+    _lib.check(rc, "codd_cost_volume_pyramid")
+    return outs
+
+
 def cost_volume_bytes(n, h, w, max_disp, want_cv, want_argmin):
     """Algorithmic HBM bytes of K1: fp32 tile features in (16 ch x (w + 4w)
     columns), the volume out when materialised (4*D per tile), min cost + arg-min out (8 per tile)."""

@@ -67,9 +67,12 @@ class TileInitialization(nn.Module):
     def tile_hypothesis_pyramid(self, tile_feature_pyramid, fea_l_pyramid):
         want_cv = self.training if self.materialize_cv is None else self.materialize_cv
         cvs, hyps = [], []
-        for k, (_, dsc, div) in enumerate(self._levels()):
+        levels = self._levels()
+        # K1 for the five levels in one launch (the coarse levels fill the tail of the finest one)
+        k1 = ops.cost_volume_pyramid(tile_feature_pyramid, [self.maxdisp // div for _, _, div in levels], want_cv=want_cv)
+        for k, (_, dsc, div) in enumerate(levels):
             tl, tr = tile_feature_pyramid[k]
-            cv, cost, disp = ops.cost_volume(tl, tr, self.maxdisp // div, want_cv=want_cv)
+            cv, cost, disp = k1[k]
             # descriptor input: tile features at 16x / 8x, backbone pyramid [0..2] below (Eq. 4)
             feat = tl if k < 2 else ops.to_nhwc(fea_l_pyramid[k - 2])
             w, b = self._pw.raw(dsc[0])

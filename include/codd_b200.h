@@ -157,6 +157,15 @@ CODD_API int codd_cost_volume(const float* tile_l, const float* tile_r,
                      int n, int h, int w, int max_disp,
                      float* cv, float* min_cost, float* min_disp, void* stream);
 
+/* The whole tile-initialisation pyramid (initialization.py:158-183, one calc_init_disp + torch.min per level) in ONE
+ * launch: `levels` entries (<= 8) of host arrays — device pointers and sizes per level, same meaning as the arguments
+ * of codd_cost_volume; cv / min_cost / min_disp must be given for all levels or for none (array or its first entry
+ * NULL).  Results are bit-identical to per-level codd_cost_volume calls; the coarse levels, latency-bound when launched
+ * alone, fill the tail of the finest level's last wave. */
+CODD_API int codd_cost_volume_pyramid(int levels, const float* const* tile_l, const float* const* tile_r, int n,
+                                      const int* h, const int* w, const int* max_disp, float* const* cv,
+                                      float* const* min_cost, float* const* min_disp, void* stream);
+
 /* Tile descriptor + hypothesis assembly (initialization.py:186-208):
  *   hyp[n,i,j,0:16] = [ min_disp, 0, 0, LeakyReLU(W . cat[min_cost, feat] + b) (13 ch) ]
  * feat [n,h,w,cf] NHWC (ldf > 0) or PLANAR [n,cf,h,w] (ldf == 0, the K2 tile features);

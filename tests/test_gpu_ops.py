@@ -181,6 +181,24 @@ def test_cost_volume_bit_exact(ops, n, h, w, d):
             assert torch.equal(md.cpu()[:, 0], ri.float()), "arg-min indices differ"
 
 
+def test_cost_volume_pyramid_matches_per_level(ops):
+    """The fused 5-level launch is bit-identical to per-level launches (materialising and fused arg-min variants)."""
+    n, D = 2, 64
+    g = gen(77)
+    tiles, disps = [], []
+    for k in range(5):
+        h, w = 3 << k, 5 << k
+        tiles.append((torch.randn(n, 16, h, w, generator=g).cuda(), torch.randn(n, 16, h, 4 * w, generator=g).cuda()))
+        disps.append(D // (16 >> k))
+    for want_cv in (True, False):
+        fused = ops.cost_volume_pyramid(tiles, disps, want_cv=want_cv)
+        for (tl, tr), d, (cv, mc, md) in zip(tiles, disps, fused):
+            cv1, mc1, md1 = ops.cost_volume(tl, tr, d, want_cv=want_cv)
+            assert torch.equal(mc, mc1) and torch.equal(md, md1)
+            if want_cv:
+                assert torch.equal(cv, cv1)
+
+
 def test_cost_volume_all_ties(ops):
     """right == 0: every disparity costs |L|_1 -> arg-min must be 0 everywhere (first index)."""
     tl = torch.randn(1, 16, 4, 37, generator=gen(3))

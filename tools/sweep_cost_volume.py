@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """BASELINE.json configs[4]: K1 sweep {540p, 720p, 1080p} x D in {64,128,192,256}, 8 samples per
 GPU; achieved algorithmic GB/s (SURVEY.md §8d byte counts) of the materialising and the fused
-arg-min variant, whole 5-level pyramid per measurement, CUDA events, L2 flushed between reps.
+arg-min variant, whole 5-level pyramid per measurement (ONE fused launch, codd_cost_volume_pyramid), CUDA events, L2 flushed between reps.
 
     python tools/sweep_cost_volume.py [--out profiles/cost_volume_sweep_rNN.json]
 """
@@ -47,8 +47,8 @@ def main():
                     flush.zero_()
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()
-                    for tl, tr, d, _, _ in levels:
-                        ops.cost_volume(tl, tr, d, want_cv=want_cv, want_argmin=True)
+                    ops.cost_volume_pyramid([(tl, tr) for tl, tr, _, _, _ in levels], [d for _, _, d, _, _ in levels],
+                                            want_cv=want_cv, want_argmin=True)
                     e1.record()
                     torch.cuda.synchronize()
                     if r >= 2:
