@@ -298,6 +298,38 @@ def run_b200(args):
         e2e_ms = e0.elapsed_time(e1)
         e2e_ms = reduce_max_ms(e2e_ms, dev)
         h2d = img_h.numel() * 4 + rimg_h.numel() * 4
+
+        # ---------------- e2e with the input-staging step on the GPU: uint8 frames cross PCIe, the
+        # Normalize + reflect Pad(64) + HWC->CHW of the reference's CPU pipeline runs as one kernel per view
+        g8 = torch.Generator().manual_seed(99 + rank)
+        l8_h = torch.randint(0, 256, (B, H_IMG, W_IMG, 3), dtype=torch.uint8, generator=g8).pin_memory()
+        r8_h = torch.randint(0, 256, (B, H_IMG, W_IMG, 3), dtype=torch.uint8, generator=g8).pin_memory()
+
+        def e2e_u8_step(i):
+            with torch.cuda.stream(streams[i % 2]):
+                l8 = l8_h.to(dev, non_blocking=True)
+                r8 = r8_h.to(dev, non_blocking=True)
+                img = ops.stage_images_u8(l8).unsqueeze(1)
+                rimg = ops.stage_images_u8(r8).unsqueeze(1)
+                res = model(return_loss=False, rescale=True, evaluate=False, img=[img], img_metas=metas, r_img=[rimg])
+                res_hs[i % 2].copy_(res[0], non_blocking=True)
+
+        for st in streams:
+            st.wait_stream(torch.cuda.current_stream())
+        for i in range(2):
+            e2e_u8_step(i)
+        e2e_join()
+        barrier()
+        e0.record()
+        for st in streams:
+            st.wait_stream(torch.cuda.current_stream())
+        for i in range(e2e_steps):
+            e2e_u8_step(i)
+        e2e_join()
+        e1.record()
+        barrier()
+        e2e_u8_ms = reduce_max_ms(e0.elapsed_time(e1), dev)
+        h2d_u8 = l8_h.numel() + r8_h.numel()
         d2h = res_h.numel() * 4
 
         # ---------------- instrumented pass: per-launch events -> dominant kernel + K1/K4 numbers
@@ -357,6 +389,10 @@ def run_b200(args):
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "api": "ConsistentOnlineDynamicDepth.__call__(return_loss=False, evaluate=False, img=[..], r_img=[..])",
                 "pipelining": "2 CUDA streams used alternately (copies of one step overlap kernels of the other)"},
+        "e2e_u8": {"value": round(e2e_steps * B * world / (e2e_u8_ms * 1e-3), 3), "unit": UNIT,
+                   "h2d_bytes_per_step": h2d_u8, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                   "what": "same as e2e, but uint8 HWC frames cross PCIe and codd_stage_images_u8 does the reference's "
+                           "Normalize + reflect Pad(64) + HWC->CHW (datasets/transforms.py) on the GPU"},
         "gpu_launches": launches_per_step * args.steps,
         "gpu_launches_per_step": launches_per_step,
         "roofline": dominant,

@@ -237,3 +237,42 @@ extern "C" int codd_subsample_nhwc(const float* in, int ldi, int n, int h, int w
     CODD_RETURN_IF_CUDA_ERROR();
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// N1 — input staging: the reference normalises and pads every frame on the CPU
+// (datasets/transforms.py:391-421 Normalize -> mmcv.imnormalize; :147-176 Pad(size_divisor=64) -> mmcv.impad
+// 'reflect'; datasets/formating.py:77-85 HWC -> CHW float tensor).  One pass on the GPU instead: uint8 HWC in,
+// normalised fp32 NCHW out, reflect-padded (no edge repeat) on the bottom / right to (hp, wp).
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) stage_images_u8_kernel(const uint8_t* __restrict__ img, int n, int h, int w,
+                                                              float m0, float m1, float m2, float s0, float s1, float s2,
+                                                              int to_rgb, int hp, int wp, float* __restrict__ out,
+                                                              size_t total) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // over n * hp * wp
+    if (i >= total) return;
+    const int x = (int)(i % wp);
+    const int y = (int)((i / wp) % hp);
+    const size_t s = i / ((size_t)wp * hp);
+    const int ys = y < h ? y : 2 * (h - 1) - y;       // numpy / cv2 BORDER_REFLECT_101
+    const int xs = x < w ? x : 2 * (w - 1) - x;
+    const uint8_t* px = img + ((s * h + ys) * (size_t)w + xs) * 3;
+    const float c0 = (float)px[to_rgb ? 2 : 0], c1 = (float)px[1], c2 = (float)px[to_rgb ? 0 : 2];
+    const size_t plane = (size_t)hp * wp;
+    float* o = out + s * 3 * plane + (size_t)y * wp + x;
+    o[0] = __fmul_rn(__fsub_rn(c0, m0), s0);          // (v - mean) * (1 / std), as mmcv.imnormalize
+    o[plane] = __fmul_rn(__fsub_rn(c1, m1), s1);
+    o[2 * plane] = __fmul_rn(__fsub_rn(c2, m2), s2);
+}
+}  // namespace
+
+extern "C" int codd_stage_images_u8(const uint8_t* img_hwc, int n, int h, int w, const float* mean, const float* std_,
+                                    int to_rgb, int hp, int wp, float* out, void* stream) {
+    if (!img_hwc || !mean || !std_ || !out || n <= 0 || h <= 0 || w <= 0) return CODD_E_BADARG;
+    if (hp < h || wp < w || hp - h >= h || wp - w >= w) return CODD_E_SHAPE;   // reflect needs pad < size
+    const size_t total = (size_t)n * hp * wp;
+    stage_images_u8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        img_hwc, n, h, w, mean[0], mean[1], mean[2], 1.f / std_[0], 1.f / std_[1], 1.f / std_[2], to_rgb, hp, wp, out, total);
+    CODD_RETURN_IF_CUDA_ERROR();
+    return 0;
+}

@@ -78,6 +78,8 @@ SIGNATURES = {
                                   c_void_p]),
     "codd_disp_to_depth": (c_int, [_FP, c_size_t, c_float, _FP, c_void_p]),
     "codd_subsample_nhwc": (c_int, [_FP, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _FP, c_int, c_void_p]),
+    "codd_stage_images_u8": (c_int, [_FP, c_int, c_int, c_int, POINTER(c_float), POINTER(c_float), c_int, c_int, c_int, _FP,
+                                     c_void_p]),
     "codd_nhwc_to_nchw": (c_int, [_FP, c_int, c_int, c_int, c_int, c_int, _FP, c_void_p]),
     "codd_nchw_to_nhwc": (c_int, [_FP, c_int, c_int, c_int, c_int, _FP, c_int, c_void_p]),
 }

@@ -736,3 +736,27 @@ def subsample(x, offset, stride, recip=False):
         x.data_ptr(), c, n, h, w, c, offset, stride, 1 if recip else 0, out.data_ptr(), c, _stream()))
     _lib.check(rc, "codd_subsample_nhwc")
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# N1 input staging: Normalize + Pad(size_divisor) + HWC->CHW of the reference's test pipeline on the GPU
+# ----------------------------------------------------------------------------------------------
+IMG_NORM = dict(mean=(123.675, 116.28, 103.53), std=(58.395, 57.12, 57.375), to_rgb=True)   # configs/datasets/*.py
+
+
+def stage_images_u8(img, mean=IMG_NORM["mean"], std=IMG_NORM["std"], to_rgb=True, size_divisor=64):
+    """img: uint8 CUDA tensor [N,H,W,3] (as cv2 / mmcv load frames) -> normalised fp32 [N,3,Hp,Wp], Hp/Wp = H/W rounded up
+    to ``size_divisor``, reflect-padded on the bottom / right (datasets/transforms.py:147-176, 391-421)."""
+    if not img.is_cuda or img.dtype != torch.uint8 or img.dim() != 4 or img.shape[-1] != 3:
+        raise _lib.CoddError("stage_images_u8 expects a uint8 CUDA tensor [N,H,W,3]")
+    img = img.contiguous()
+    n, h, w, _ = img.shape
+    hp = -(-h // size_divisor) * size_divisor
+    wp = -(-w // size_divisor) * size_divisor
+    out = torch.empty((n, 3, hp, wp), device=img.device, dtype=torch.float32)
+    m = (ctypes.c_float * 3)(*mean)
+    s = (ctypes.c_float * 3)(*std)
+    rc = _run("stage_images_u8", img.numel() + 4 * out.numel(), lambda: _lib.load().codd_stage_images_u8(
+        img.data_ptr(), n, h, w, m, s, 1 if to_rgb else 0, hp, wp, out.data_ptr(), _stream()))
+    _lib.check(rc, "codd_stage_images_u8")
+    return out

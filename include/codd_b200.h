@@ -319,6 +319,15 @@ CODD_API int codd_subsample_nhwc(const float* in, int ldi, int n, int h, int w, 
                                  int recip, float* out, int ldo, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * N1  input staging (reference: datasets/transforms.py:391-421 Normalize, :147-176 Pad(size_divisor=64,
+ * 'reflect'), datasets/formating.py:77-85): uint8 HWC frames [n,h,w,3] (device) -> normalised fp32 NCHW [n,3,hp,wp],
+ * out = (v - mean[c]) * (1/std[c]) with the channel order reversed first when to_rgb != 0, reflect-padded (no edge
+ * repeat) on the bottom / right.  mean / std are HOST arrays of 3 floats (the config's img_norm_cfg).
+ * ------------------------------------------------------------------------------------------ */
+CODD_API int codd_stage_images_u8(const uint8_t* img_hwc, int n, int h, int w, const float* mean, const float* std_,
+                                  int to_rgb, int hp, int wp, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * layout helpers at the module boundary
  * ------------------------------------------------------------------------------------------ */
 /* NHWC [n,h,w,c] (pixel stride ldi) -> NCHW contiguous */

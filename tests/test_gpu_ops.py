@@ -432,3 +432,18 @@ def test_fusion_memory_query_vs_oracle():
         for k in keys:
             torch.testing.assert_close(o[k].cpu(), ref_o[k], rtol=1e-4, atol=1e-4)
         assert len(s["memory"]) == 3 and s["memory"][2].shape == ref_s["memory"][2].shape
+
+
+# ------------------------------------------------------------------------------------------
+# N1 input staging
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("h,w,to_rgb", [(540, 960, True), (375, 1242, True), (64, 64, False), (65, 130, True)])
+def test_stage_images_u8(ops, h, w, to_rgb):
+    import numpy as np
+    from oracle import staging_oracle as SO
+    rng = np.random.default_rng(h * 7 + w)
+    img = rng.integers(0, 256, size=(2, h, w, 3), dtype=np.uint8)
+    ref = SO.stage_images_u8(img, to_rgb=to_rgb)
+    out = ops.stage_images_u8(torch.from_numpy(img).cuda(), to_rgb=to_rgb)
+    assert tuple(out.shape) == ref.shape and out.shape[2] % 64 == 0 and out.shape[3] % 64 == 0
+    assert torch.equal(out.cpu(), torch.from_numpy(ref)), "staging differs from the oracle"
