@@ -16,8 +16,13 @@
 // Per output row and 128 pixels the tensor core now reads 12 A slices (Cin=16) instead of 36, B grows from 0.5-1 KB
 // to 3 KB per MMA: 84 KB instead of 162 KB of operand traffic, and the stage is written / split once instead of twice.
 //
-// 3xTF32: pass A multiplies the raw fp32 row (the MMA reads the top 19 bits = x_hi) by [w_hi | w_lo] per tap, the
-// split warps then overwrite the row with x_lo = x - x_hi in place and pass B multiplies it by [w_hi | 0].
+// Precision (3xTF32-class): pass A (kind::tf32) multiplies the raw fp32 row (the MMA reads the top 19 bits = x_hi) by
+// [w_hi | 2^10 w_lo] per tap; the split warps write fp16(2^10 * x_lo), x_lo = x - x_hi, into a second half-size stage
+// and pass B (kind::f16, K = 16 per MMA) multiplies it by [0 | fp16(w_hi)]: the lo half of a TMEM slot accumulates
+// 2^10 (x_hi w_lo + x_lo w_hi), the epilogue adds hi + 2^-10 lo.  x_lo carries <= 13 significant bits and is 2^-10 of
+// the result, so the 11-bit fp16 mantissa costs nothing measurable (max abs err 4.8e-6 on O(1) outputs).
+// Issue: pass A and pass B are issued by two threads in two warps; a per-stage mbarrier orders pass B of row g after
+// pass A of rows g+1, g+2 (the only MMAs that share accumulators with it), which makes the result bit-deterministic.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -80,14 +85,6 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.u32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
     uint32_t r[16];
     asm volatile(
@@ -100,21 +97,6 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// K-major swizzled shared-memory matrix descriptor (same encoding as conv_tc.cu: base-offset field 0, the swizzle is
-// a function of the shared-memory address, so shifted start addresses address shifted windows of the same tile)
-template <int KC>
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-    constexpr uint32_t ROWB = KC * 4;
-    constexpr uint64_t LAYOUT = (KC == 32) ? 2ull : 4ull;   // SWIZZLE_128B : SWIZZLE_64B
-    constexpr uint32_t SBO = 8 * ROWB;
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(SBO >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= LAYOUT << 61;
-    return d;
-}
 template <int KC>
 __device__ __forceinline__ uint32_t swz_off(int r, int j) {
     constexpr uint32_t ROWB = KC * 4;
@@ -125,32 +107,12 @@ __device__ __forceinline__ uint32_t swz_off(int r, int j) {
 __device__ __forceinline__ float tf32_lo(float x) {
     return __fsub_rn(x, __uint_as_float(__float_as_uint(x) & 0xFFFFE000u));
 }
-// K-major swizzled descriptor for rows of RB bytes (32 / 64 / 128: SWIZZLE_32B / 64B / 128B, 8-row group pitch 8*RB)
-template <int RB>
-__device__ __forceinline__ uint64_t make_desc_rb(uint32_t saddr) {
-    constexpr uint64_t LAYOUT = (RB == 128) ? 2ull : (RB == 64) ? 4ull : 6ull;
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)((8u * RB) >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= LAYOUT << 61;
-    return d;
-}
 // byte offset of 16-byte chunk j of row r in a tile of RB-byte rows whose base is 1024-aligned
 template <int RB>
 __device__ __forceinline__ uint32_t swz_rb(int r, int j) {
     const uint32_t off = (uint32_t)r * RB + (uint32_t)j * 16u;
     constexpr uint32_t MASK = RB / 16 - 1;     // 1, 3, 7
     return off ^ (((off >> 7) & MASK) << 4);
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.u32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-        : "memory");
 }
 // MMA with descriptors given as LOW 32-bit words (start address | LBO) plus compile-time HIGH words (SBO | version |
 // swizzle mode): per-MMA operand arithmetic is one 32-bit add per descriptor and the issuing thread moves three
@@ -178,7 +140,8 @@ __device__ __forceinline__ void tc_mma_lo(uint32_t tmem_d, uint32_t a_lo, uint32
     }
 }
 template <int RB>
-__host__ __device__ constexpr uint32_t desc_hi() {   // high word of make_desc_rb<RB>
+__host__ __device__ constexpr uint32_t desc_hi() {   // high word of a K-major swizzled descriptor for RB-byte rows:
+                                                     // 8-row group pitch (SBO) | descriptor version | SWIZZLE_32B/64B/128B
     return ((8u * RB) >> 4) | (1u << 14) | (((RB == 128) ? 2u : (RB == 64) ? 4u : 6u) << 29);
 }
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
@@ -217,7 +180,7 @@ struct Cursor {
     }
 };
 
-template <int KC, int NP, int NBUF, int LAG>
+template <int KC, int NP, int NBUF>
 __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __grid_constant__ CUtensorMap tmap, RgP p) {
     constexpr int SLOT = 2 * NP;                 // TMEM columns of one output row: [hi NP | lo NP]
     constexpr int RING = 512 / SLOT;             // 16 (NP = 16) or 8 (NP = 32) output rows in flight
@@ -229,9 +192,8 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
     constexpr uint32_t H_BYTES = RG_BOXW * ROWH;
     constexpr uint32_t H_STRIDE = (H_BYTES + 1023u) & ~1023u;
     constexpr uint32_t WBLKH = 6 * NP * ROWH;    // one pass-B kx weight block, fp16
-    constexpr int KS = KC / 8;
     constexpr uint32_t IDESC_BASE = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 4) << 24);
-    static_assert(NBUF >= LAG + 2, "stage depth");
+    static_assert(NBUF >= 4, "stage depth: pass B trails pass A by >= 2 rows");
 
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) unsigned long long bars[5 * NBUF + 2 * RING];
@@ -321,7 +283,6 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
         // itself), which at 13 MMAs + 5 barrier operations per row was the kernel's critical path.  Ordering between
         // the two is carried by the barriers: pass B of a row waits for the split, which waits for pass A's commit.
         if (lane == 0) {
-            constexpr bool leader = true;
             // one pass over one staged row: for every (kx, k-step) the row is multiplied by the weight blocks of the
             // valid ky taps; consecutive ring slots are covered by one MMA (N = 2NP, 4NP or 6NP)
             long long w_full = 0, w_lo = 0, w_acce = 0;
@@ -610,14 +571,14 @@ PFN_tmapEncodeTiled rg_get_encode() {
     return fn;
 }
 
-template <int KC, int NP, int NBUF, int LAG>
+template <int KC, int NP, int NBUF>
 int launch_ring(const CUtensorMap& tmap, RgP p, cudaStream_t s) {
     constexpr uint32_t ROWB = KC * 4;
     constexpr uint32_t A_STRIDE = ((RG_BOXW * ROWB) + 1023u) & ~1023u;
     constexpr uint32_t H_STRIDE = ((RG_BOXW * KC * 2) + 1023u) & ~1023u;
     constexpr uint32_t B_BYTES = 3 * 6 * NP * ROWB + 3 * 6 * NP * KC * 2;
     const size_t smem = NBUF * (A_STRIDE + H_STRIDE) + B_BYTES + 1024;
-    auto kern = conv3x3_tc_ring_kernel<KC, NP, NBUF, LAG>;
+    auto kern = conv3x3_tc_ring_kernel<KC, NP, NBUF>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -678,9 +639,9 @@ extern "C" int codd_conv3x3_tc_ring(const float* in, int ldi, int cin, int n, in
     p.nseg = p.seg = p.nitems = 0;
     p.dbg = g_rg_dbg;
     cudaStream_t s = (cudaStream_t)stream;
-    if (KC == 32 && NP == 32) return launch_ring<32, 32, 4, 2>(tmap, p, s);
-    if (KC == 32 && NP == 16) return launch_ring<32, 16, 4, 2>(tmap, p, s);
-    return launch_ring<16, 16, 12, 8>(tmap, p, s);
+    if (KC == 32 && NP == 32) return launch_ring<32, 32, 4>(tmap, p, s);
+    if (KC == 32 && NP == 16) return launch_ring<32, 16, 4>(tmap, p, s);
+    return launch_ring<16, 16, 12>(tmap, p, s);
 }
 
 // diagnostic: device buffer of [grid][8] int64 cycle counters filled by the next codd_conv3x3_tc_ring launches

@@ -81,3 +81,26 @@ def test_full_codd_sequence_vs_oracle():
     st = model.inference_state
     assert len(st["memory"]) == 3 and st["memory"][1].shape == (n, 32, h // 4, w // 4)
     assert ops.LAUNCHES[0] > 0
+
+
+def test_full_codd_full_size_properties():
+    """BASELINE.json configs[2] geometry (960x540 padded to 576x960, D=192) at batch 1, 2 frames, 4 RAFT3D iterations:
+    properties that need no CPU oracle at this size — output shape / crop, finiteness, non-negativity, run-to-run
+    determinism, the 3-tuple memory left by Fusion.memory_update and the fusion weights' range."""
+    import codd_b200
+    from codd_b200.synth import synth_pair
+    torch.manual_seed(3)
+    model = codd_b200.build_estimator(codd_b200.codd_full_config(192, iters=4)).cuda()
+    model.eval()
+    left, right = synth_pair(1, 576, 960, 192, seed=5, kind="S")
+    img = torch.stack([left, torch.roll(left, shifts=(1, 2), dims=(2, 3))], 1).cuda()
+    r_img = torch.stack([right, torch.roll(right, shifts=(1, 2), dims=(2, 3))], 1).cuda()
+    metas = [[dict(min_disp=1, max_disp=192, ori_shape=(540, 960), img_shape=(540, 960),
+                   intrinsics=[1050.0, 1050.0, 480.0, 270.0])]]
+    run = lambda: model(return_loss=False, rescale=True, evaluate=False, img=[img], img_metas=metas, r_img=[r_img])[0]
+    a = run()
+    assert a.shape == (1, 2, 540, 960) and torch.isfinite(a).all() and (a >= 0).all()
+    mem = model.inference_state["memory"]
+    assert len(mem) == 3 and mem[1].shape == (1, 32, 144, 240) and mem[2].shape == (1, 576, 960)
+    b = run()
+    assert torch.equal(a, b), "full CODD forward is not deterministic"
