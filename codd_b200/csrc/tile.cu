@@ -102,7 +102,9 @@ __global__ void __launch_bounds__(256) plane_upsample_kernel(const float* __rest
 // ------------------------------------------------------------------------------------------
 struct WarpP {
     const float* fl;
-    const float* fr;      // PLANAR [n][C][H][W]
+    const float* fr;      // PLANAR [n][C][H][W] (staged / per-channel gather paths), or NULL
+    const float* fr_nhwc; // NHWC [n][H][W][ldfr] (direct 128-bit gather path), or NULL
+    int ldfr;
     int ldfl, C;
     const float* cur;
     int ldc;
@@ -276,10 +278,11 @@ __global__ void __launch_bounds__(K4_THREADS, 3) tile_warp_cost_kernel(WarpP p) 
     const int xlo = s_rng[0], rlo = s_rng[2];
     const int wwin = s_rng[1] - xlo + 1, rwin = s_rng[3] - rlo + 1;
     const int pitch = p.C + 4;
-    const bool staged = (s_rng[1] >= 0) && wwin <= p.max_win &&
+    const bool direct = p.fr_nhwc != nullptr;
+    const bool staged = !direct && (s_rng[1] >= 0) && wwin <= p.max_win &&
                         ((size_t)wwin * rwin * pitch * sizeof(float) <= (size_t)K4_STAGE_BYTES);
     const size_t cstride = (size_t)H * W;
-    const float* frn = p.fr + (size_t)n * p.C * cstride;
+    const float* frn = direct ? p.fr_nhwc + (size_t)n * cstride * p.ldfr : p.fr + (size_t)n * p.C * cstride;
     if (staged) {
         // planar global rows (coalesced along x) -> [row][x][C+4]: a warp takes one (4-channel group, row) segment at
         // a time; every lane loads 4 channel planes at its column and writes them as one 128-bit store
@@ -302,7 +305,21 @@ __global__ void __launch_bounds__(K4_THREADS, 3) tile_warp_cost_kernel(WarpP p) 
         const float* flp = p.fl + (((size_t)n * H + y) * W + x) * p.ldfl;
         int offA[NSETS][3], offB[NSETS][3];
         float lnorm = 0.f;
-        if (staged) {
+        if (direct) {
+            // right features read in place, NHWC: one 128-bit load fetches 4 channels of a tap (horizontally adjacent
+            // lanes read adjacent pixels: contiguous 64..128-byte runs, L1-resident across the planes of a pixel)
+            const int rbase = y0 * W;
+#pragma unroll
+            for (int s = 0; s < NSETS; ++s)
+#pragma unroll
+                for (int ki = 0; ki < 3; ++ki) {
+                    offA[s][ki] = (rbase + colA[s][ki]) * p.ldfr;
+                    offB[s][ki] = (rbase + colB[s][ki]) * p.ldfr;
+                }
+            const int rowstep = row1_ok ? W * p.ldfr : 0;
+            if (two_rows) k4_channels_staged<NSETS, true>(flp, frn, p.C, rowstep, offA, offB, wA, wB, wC, wD, cost, lnorm);
+            else k4_channels_staged<NSETS, false>(flp, frn, p.C, rowstep, offA, offB, wA, wB, wC, wD, cost, lnorm);
+        } else if (staged) {
             const int rbase = (y0 - rlo) * wwin - xlo;
 #pragma unroll
             for (int s = 0; s < NSETS; ++s)
@@ -448,11 +465,10 @@ extern "C" int codd_plane_upsample(const float* in, int ldi, int n, int h, int w
     return 0;
 }
 
-extern "C" int codd_tile_warp_cost(const float* fea_l, int ldfl, const float* fea_r_planar, int c,
-                                   const float* cur, int ldc, const float* prev, int ldp, const float* dec_w,
-                                   const float* dec_b, int n, int h, int w, float* aug, int ldaug, float* raw_cv,
-                                   void* stream) {
-    const float* fea_r = fea_r_planar;
+namespace {
+int tile_warp_cost_impl(const float* fea_l, int ldfl, const float* fea_r, int ldfr, int c, const float* cur, int ldc,
+                        const float* prev, int ldp, const float* dec_w, const float* dec_b, int n, int h, int w, float* aug,
+                        int ldaug, float* raw_cv, void* stream) {
     if (!fea_l || !fea_r || !cur || !dec_w || !dec_b || !aug || n <= 0 || h <= 0 || w <= 0) return CODD_E_BADARG;
     if (c <= 0 || c % 4 != 0 || ldfl < c || ldfl % 4 || ldc < 16 || ldc % 4) return CODD_E_SHAPE;
     if (prev && (ldp < 16 || ldp % 4 || (h & 1) || (w & 1))) return CODD_E_SHAPE;
@@ -461,7 +477,11 @@ extern "C" int codd_tile_warp_cost(const float* fea_l, int ldfl, const float* fe
         (prev && !codd_aligned16(prev)) || (raw_cv && !codd_aligned16(raw_cv)))
         return CODD_E_ALIGN;
     WarpP p;
-    p.fl = fea_l; p.fr = fea_r; p.ldfl = ldfl; p.C = c;
+    if (ldfr != 0 && (ldfr < c || ldfr % 4 || !codd_aligned16(fea_r))) return CODD_E_SHAPE;
+    p.fl = fea_l; p.ldfl = ldfl; p.C = c;
+    p.fr = ldfr == 0 ? fea_r : nullptr;
+    p.fr_nhwc = ldfr != 0 ? fea_r : nullptr;
+    p.ldfr = ldfr;
     p.cur = cur; p.ldc = ldc; p.prev = prev; p.ldp = ldp;
     p.dec_w = dec_w; p.dec_b = dec_b; p.N = n; p.h = h; p.w = w;
     p.aug = aug; p.ldaug = ldaug; p.raw = raw_cv;
@@ -481,6 +501,24 @@ extern "C" int codd_tile_warp_cost(const float* fea_l, int ldfl, const float* fe
     else tile_warp_cost_kernel<1><<<grid, block, K4_STAGE_BYTES, (cudaStream_t)stream>>>(p);
     CODD_RETURN_IF_CUDA_ERROR();
     return 0;
+}
+}  // namespace
+
+extern "C" int codd_tile_warp_cost(const float* fea_l, int ldfl, const float* fea_r_planar, int c,
+                                   const float* cur, int ldc, const float* prev, int ldp, const float* dec_w,
+                                   const float* dec_b, int n, int h, int w, float* aug, int ldaug, float* raw_cv,
+                                   void* stream) {
+    return tile_warp_cost_impl(fea_l, ldfl, fea_r_planar, 0, c, cur, ldc, prev, ldp, dec_w, dec_b, n, h, w, aug, ldaug, raw_cv,
+                               stream);
+}
+
+extern "C" int codd_tile_warp_cost_nhwc(const float* fea_l, int ldfl, const float* fea_r, int ldfr, int c,
+                                        const float* cur, int ldc, const float* prev, int ldp, const float* dec_w,
+                                        const float* dec_b, int n, int h, int w, float* aug, int ldaug, float* raw_cv,
+                                        void* stream) {
+    if (ldfr <= 0) return CODD_E_BADARG;
+    return tile_warp_cost_impl(fea_l, ldfl, fea_r, ldfr, c, cur, ldc, prev, ldp, dec_w, dec_b, n, h, w, aug, ldaug, raw_cv,
+                               stream);
 }
 
 extern "C" int codd_hyp_select(const float* update, int ldu, const float* aug, int ldaug, int n, int h, int w,

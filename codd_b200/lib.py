@@ -48,6 +48,8 @@ SIGNATURES = {
     "codd_plane_upsample": (c_int, [_FP, c_int, c_int, c_int, c_int, c_int, c_float, _FP, c_int, c_void_p]),
     "codd_tile_warp_cost": (c_int, [_FP, c_int, _FP, c_int, _FP, c_int, _FP, c_int, _FP, _FP, c_int, c_int,
                                     c_int, _FP, c_int, _FP, c_void_p]),
+    "codd_tile_warp_cost_nhwc": (c_int, [_FP, c_int, _FP, c_int, c_int, _FP, c_int, _FP, c_int, _FP, _FP, c_int, c_int,
+                                         c_int, _FP, c_int, _FP, c_void_p]),
     "codd_hyp_select": (c_int, [_FP, c_int, _FP, c_int, c_int, c_int, c_int, _FP, c_int, c_void_p]),
     "codd_fusion_cues_lowres": (c_int, [_FP, c_int, _FP, c_int, _FP, c_int, _FP, c_int, _FP, _FP, c_int, c_int, c_int,
                                         c_int, _FP, c_int, _FP, c_int, _FP, c_int, c_void_p]),

@@ -6,6 +6,7 @@ buffer).  Torch is used for allocation, streams and nothing else: all arithmetic
 ``libcodd_b200.so``.  Non-CUDA inputs raise — there is no CPU path.
 """
 import ctypes
+import os
 
 import torch
 
@@ -455,11 +456,19 @@ def planar(t):
     return to_nchw(t)
 
 
-def tile_warp_cost(fea_l, fea_r, cur, prev, dec_w, dec_b, want_raw=False):
+# Right features of K4: planar copy + shared-memory staged window (default) or gathered in place from NHWC
+# (CODD_K4_NHWC=1).  Measured at level 0, batch 8 (tools/k4_probe.py): in-place 0.82 / 0.92 ms (smooth / noisy hypotheses)
+# vs 0.51 / 0.69 ms staged — the 128-bit global gathers are L1-latency bound, so the planar path stays the default.
+K4_NHWC = os.environ.get("CODD_K4_NHWC", "0") == "1"
+
+
+def tile_warp_cost(fea_l, fea_r, cur, prev, dec_w, dec_b, want_raw=False, force_nhwc=False):
     """K4.  Returns aug [N,32|64,h,w] (and the raw 64-ch/set decrease input when want_raw).
-    ``fea_r`` may be NHWC-backed (transposed here) or already planar NCHW (``ops.planar``)."""
+    ``fea_r``: NHWC-backed (gathered in place) or plain contiguous NCHW (planar path)."""
     _require_cuda(fea_l, fea_r, cur, prev, dec_w, dec_b)
-    fea_r = planar(fea_r)
+    nhwc_r = (K4_NHWC or force_nhwc) and not _is_planar(fea_r)
+    if not nhwc_r:
+        fea_r = planar(fea_r)
     n, c, H, W = fea_l.shape
     _, _, h, w = cur.shape
     if (H, W) != (4 * h, 4 * w) or fea_r.shape != fea_l.shape or cur.shape[1] != 16:
@@ -470,10 +479,15 @@ def tile_warp_cost(fea_l, fea_r, cur, prev, dec_w, dec_b, want_raw=False):
     aug = empty_nhwc(n, ca, h, w, cur.device)
     raw = empty_nhwc(n, 2 * ca, h, w, cur.device) if want_raw else None
     nbytes = tile_warp_bytes(n, c, h, w, prev is not None)
-    rc = _run(f"tile_warp_cost_c{c}_sets{2 if prev is not None else 1}", nbytes, lambda: _lib.load().codd_tile_warp_cost(
-        fea_l.data_ptr(), ld_of(fea_l), fea_r.data_ptr(), c, cur.data_ptr(), ld_of(cur),
-        None if prev is None else prev.data_ptr(), 0 if prev is None else ld_of(prev), dec_w.data_ptr(),
-        dec_b.data_ptr(), n, h, w, aug.data_ptr(), ca, None if raw is None else raw.data_ptr(), _stream()))
+    tail = (cur.data_ptr(), ld_of(cur), None if prev is None else prev.data_ptr(), 0 if prev is None else ld_of(prev),
+            dec_w.data_ptr(), dec_b.data_ptr(), n, h, w, aug.data_ptr(), ca, None if raw is None else raw.data_ptr(), _stream())
+    tag = f"tile_warp_cost_c{c}_sets{2 if prev is not None else 1}"
+    if nhwc_r:
+        rc = _run(tag, nbytes, lambda: _lib.load().codd_tile_warp_cost_nhwc(
+            fea_l.data_ptr(), ld_of(fea_l), fea_r.data_ptr(), ld_of(fea_r), c, *tail))
+    else:
+        rc = _run(tag, nbytes, lambda: _lib.load().codd_tile_warp_cost(
+            fea_l.data_ptr(), ld_of(fea_l), fea_r.data_ptr(), c, *tail))
     _lib.check(rc, "codd_tile_warp_cost")
     return (aug, raw) if want_raw else aug
 

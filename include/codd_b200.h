@@ -206,6 +206,14 @@ CODD_API int codd_tile_warp_cost(const float* fea_l, int ldfl, const float* fea_
                         int n, int h, int w, float* aug, int ldaug, float* raw_cv,
                         void* stream);
 
+/* Same operation with the right features given in NHWC ([n,H,W,c], pixel stride ldfr) — the backbone's own layout, no
+ * planar copy: every tap is gathered in place with 128-bit loads (4 channels each). */
+CODD_API int codd_tile_warp_cost_nhwc(const float* fea_l, int ldfl, const float* fea_r, int ldfr, int c,
+                                      const float* cur, int ldc, const float* prev, int ldp,
+                                      const float* dec_w, const float* dec_b,
+                                      int n, int h, int w, float* aug, int ldaug, float* raw_cv,
+                                      void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * K5  hypothesis selection (reference: TileUpdate.forward, propagation.py:225-248).
  * update [n,h,w,34] = [conf_prev, conf_cur, dprev(16), dcur(16)];  aug as written by K4.

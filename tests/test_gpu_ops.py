@@ -261,9 +261,12 @@ def _warp_inputs(n, c, h, w, seed, dmax):
     return fl, fr, cur, prev, dw, db
 
 
+@pytest.mark.parametrize("right_layout", ["nhwc", "planar"])
 @pytest.mark.parametrize("n,c,h,w,dmax", [(1, 16, 4, 6, 10.0), (2, 24, 6, 18, 40.0), (1, 32, 2, 34, 90.0),
                                           (1, 16, 10, 16, 30.0), (1, 16, 36, 8, 20.0)])
-def test_tile_warp_cost(ops, n, c, h, w, dmax):
+def test_tile_warp_cost(ops, n, c, h, w, dmax, right_layout):
+    """right_layout: NHWC right features are gathered in place (codd_tile_warp_cost_nhwc); a plain contiguous NCHW
+    tensor takes the planar entry point (shared-memory staged window / per-channel gathers)."""
     fl, fr, cur, prev, dw, db = _warp_inputs(n, c, h, w, c + h + w, dmax)
     fnorm = F.pixel_unshuffle(O.l1_over_channels(fl), 4)
     up_prev = O.plane_upsample(prev, 2, 2)
@@ -272,7 +275,8 @@ def test_tile_warp_cost(ops, n, c, h, w, dmax):
     dec = lambda r: F.leaky_relu(F.conv2d(r, dw, db), 0.2)
     args = (nhwc(ops, fl), nhwc(ops, fr), nhwc(ops, cur))
     # two hypothesis sets (TileUpdate)
-    aug, raw = ops.tile_warp_cost(*args, nhwc(ops, prev), dw.cuda().contiguous(), db.cuda(), want_raw=True)
+    kw = dict(want_raw=True, force_nhwc=right_layout == "nhwc")
+    aug, raw = ops.tile_warp_cost(*args, nhwc(ops, prev), dw.cuda().contiguous(), db.cuda(), **kw)
     raw = back(ops, raw)
     assert torch.equal(raw[:, :64], raw_cur), "local cost volume (current set) not bit-identical"
     assert torch.equal(raw[:, 64:], raw_prev), "local cost volume (up-sampled previous set) not bit-identical"
@@ -281,7 +285,7 @@ def test_tile_warp_cost(ops, n, c, h, w, dmax):
     torch.testing.assert_close(aug[:, 16:32], dec(raw_cur), rtol=CONV_RTOL, atol=CONV_ATOL)
     torch.testing.assert_close(aug[:, 48:], dec(raw_prev), rtol=CONV_RTOL, atol=CONV_ATOL)
     # one set (TileUpdate0)
-    aug0, raw0 = ops.tile_warp_cost(*args, None, dw.cuda().contiguous(), db.cuda(), want_raw=True)
+    aug0, raw0 = ops.tile_warp_cost(*args, None, dw.cuda().contiguous(), db.cuda(), **kw)
     assert torch.equal(back(ops, raw0), raw_cur)
     aug0 = back(ops, aug0)
     assert aug0.shape[1] == 32 and torch.equal(aug0[:, :16], cur)

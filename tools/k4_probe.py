@@ -16,6 +16,8 @@ def main():
     g = torch.Generator(device="cuda").manual_seed(0)
     fl = ops.to_nhwc(torch.randn(n, c, 4 * h, 4 * w, device=dev, generator=g))
     fr = torch.randn(n, c, 4 * h, 4 * w, device=dev, generator=g)
+    if os.environ.get("CODD_K4_NHWC", "0") == "1":
+        fr = ops.to_nhwc(fr)      # gathered in place (codd_tile_warp_cost_nhwc)
     dec_w = torch.randn(16, 64, device=dev, generator=g) / 8
     dec_b = torch.zeros(16, device=dev)
     yy, xx = torch.meshgrid(torch.arange(h, device=dev).float(), torch.arange(w, device=dev).float(), indexing="ij")
@@ -40,7 +42,7 @@ def main():
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
         gb = ops.tile_warp_bytes(n, c, h, w, True) / 1e9
-        print(f"maxwin={os.environ.get('CODD_K4_MAXWIN', 'default')} {kind}: {ms:.3f} ms  {gb / (ms * 1e-3):.0f} GB/s")
+        print(f"right={'nhwc' if not fr.is_contiguous() else 'planar'} maxwin={os.environ.get('CODD_K4_MAXWIN', 'default')} {kind}: {ms:.3f} ms  {gb / (ms * 1e-3):.0f} GB/s")
 
 
 if __name__ == "__main__":
