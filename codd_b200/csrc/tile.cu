@@ -279,11 +279,23 @@ __global__ void __launch_bounds__(K4_THREADS, 3) tile_warp_cost_kernel(WarpP p) 
     const int wwin = s_rng[1] - xlo + 1, rwin = s_rng[3] - rlo + 1;
     const int pitch = p.C + 4;
     const bool direct = p.fr_nhwc != nullptr;
-    const bool staged = !direct && (s_rng[1] >= 0) && wwin <= p.max_win &&
+    const bool staged = (s_rng[1] >= 0) && wwin <= p.max_win &&
                         ((size_t)wwin * rwin * pitch * sizeof(float) <= (size_t)K4_STAGE_BYTES);
     const size_t cstride = (size_t)H * W;
     const float* frn = direct ? p.fr_nhwc + (size_t)n * cstride * p.ldfr : p.fr + (size_t)n * p.C * cstride;
-    if (staged) {
+    if (staged && direct) {
+        // NHWC source: the window is already channel-innermost in global memory — one 128-bit load + one 128-bit store
+        // per (pixel, 4 channels), consecutive threads on consecutive 16-byte pieces of a pixel
+        const int c4n = p.C >> 2;
+        const int per_row = wwin * c4n;
+        for (int idx = tid; idx < rwin * per_row; idx += K4_THREADS) {
+            const int r = idx / per_row, rem = idx - r * per_row;
+            const int xi = rem / c4n, c4 = rem - xi * c4n;
+            const float4 v = ldg4(frn + ((size_t)(rlo + r) * W + xlo + xi) * p.ldfr + c4 * 4);
+            *reinterpret_cast<float4*>(s_R + (size_t)(r * wwin + xi) * pitch + c4 * 4) = v;
+        }
+        __syncthreads();
+    } else if (staged) {
         // planar global rows (coalesced along x) -> [row][x][C+4]: a warp takes one (4-channel group, row) segment at
         // a time; every lane loads 4 channel planes at its column and writes them as one 128-bit store
         const int nseg = (p.C >> 2) * rwin;
@@ -305,8 +317,8 @@ __global__ void __launch_bounds__(K4_THREADS, 3) tile_warp_cost_kernel(WarpP p) 
         const float* flp = p.fl + (((size_t)n * H + y) * W + x) * p.ldfl;
         int offA[NSETS][3], offB[NSETS][3];
         float lnorm = 0.f;
-        if (direct) {
-            // right features read in place, NHWC: one 128-bit load fetches 4 channels of a tap (horizontally adjacent
+        if (direct && !staged) {
+            // window too large for shared memory: right features read in place, NHWC: one 128-bit load fetches 4 channels of a tap (horizontally adjacent
             // lanes read adjacent pixels: contiguous 64..128-byte runs, L1-resident across the planes of a pixel)
             const int rbase = y0 * W;
 #pragma unroll

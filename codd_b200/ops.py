@@ -456,10 +456,11 @@ def planar(t):
     return to_nchw(t)
 
 
-# Right features of K4: planar copy + shared-memory staged window (default) or gathered in place from NHWC
-# (CODD_K4_NHWC=1).  Measured at level 0, batch 8 (tools/k4_probe.py): in-place 0.82 / 0.92 ms (smooth / noisy hypotheses)
-# vs 0.51 / 0.69 ms staged — the 128-bit global gathers are L1-latency bound, so the planar path stays the default.
-K4_NHWC = os.environ.get("CODD_K4_NHWC", "0") == "1"
+# Right features of K4: read in place from the backbone's NHWC map (default; the CTA's window is staged into shared memory
+# with 128-bit copies, no planar transpose) or from a planar copy (CODD_K4_NHWC=0, the earlier path).  tools/k4_probe.py at
+# level 0, batch 8: smooth hypotheses 0.50 ms (NHWC) vs 0.51 ms (planar); hypotheses too scattered to stage 0.86 vs 0.69 ms
+# (in-place 128-bit gathers are L1-latency bound); in the bench step both give 0.74 ms and NHWC saves the 5 transposes.
+K4_NHWC = os.environ.get("CODD_K4_NHWC", "1") != "0"
 
 
 def tile_warp_cost(fea_l, fea_r, cur, prev, dec_w, dec_b, want_raw=False, force_nhwc=False):

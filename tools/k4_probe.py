@@ -16,7 +16,7 @@ def main():
     g = torch.Generator(device="cuda").manual_seed(0)
     fl = ops.to_nhwc(torch.randn(n, c, 4 * h, 4 * w, device=dev, generator=g))
     fr = torch.randn(n, c, 4 * h, 4 * w, device=dev, generator=g)
-    if os.environ.get("CODD_K4_NHWC", "0") == "1":
+    if os.environ.get("CODD_K4_NHWC", "1") != "0":
         fr = ops.to_nhwc(fr)      # gathered in place (codd_tile_warp_cost_nhwc)
     dec_w = torch.randn(16, 64, device=dev, generator=g) / 8
     dec_b = torch.zeros(16, device=dev)
