@@ -458,6 +458,55 @@ __global__ void __launch_bounds__(128) conv3x3_image_kernel(const float* __restr
 }
 
 // ---------------------------------------------------------------------------------------------
+// single-output 3x3 head: FinalTileUpdate's last layer in eval mode needs the disparity channel only
+// (propagation.py:325-333, 16 -> 3 channels of which channel 0 is returned).  16 -> 1 is a memory-bound reduction
+// (144 MACs per 64 bytes read), not a GEMM: a (32+2) x (8+2) NHWC tile is staged in shared memory with 128-bit copies
+// (pixel pitch CIN+4 floats: conflict-free 128-bit reads for adjacent lanes), one thread per output pixel.
+// ---------------------------------------------------------------------------------------------
+constexpr int H1_TW = 32, H1_TH = 8;
+template <int CIN>
+__global__ void __launch_bounds__(H1_TW * H1_TH) conv3x3_head1_kernel(const float* __restrict__ in, int ldi, int n, int h,
+                                                                      int w, const float* __restrict__ wgt,
+                                                                      const float* __restrict__ bias,
+                                                                      const float* __restrict__ res, int ldr, int act,
+                                                                      float* __restrict__ out, int ldo) {
+    constexpr int PITCH = CIN + 4;
+    __shared__ __align__(16) float s_t[(H1_TH + 2) * (H1_TW + 2) * PITCH];
+    __shared__ __align__(16) float s_w[9 * CIN];
+    const int tid = threadIdx.y * H1_TW + threadIdx.x;
+    const int x0 = blockIdx.x * H1_TW, y0 = blockIdx.y * H1_TH, s = blockIdx.z;
+    for (int i = tid; i < 9 * CIN; i += H1_TW * H1_TH) s_w[i] = __ldg(wgt + i);       // packed [tap][cin][1]
+    for (int i = tid; i < (H1_TH + 2) * (H1_TW + 2) * (CIN / 4); i += H1_TW * H1_TH) {
+        const int c4 = i % (CIN / 4), pix = i / (CIN / 4);
+        const int px = pix % (H1_TW + 2), py = pix / (H1_TW + 2);
+        const int gx = x0 + px - 1, gy = y0 + py - 1;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gx >= 0 && gx < w && gy >= 0 && gy < h) v = ldg4(in + (((size_t)s * h + gy) * w + gx) * ldi + c4 * 4);
+        *reinterpret_cast<float4*>(s_t + pix * PITCH + c4 * 4) = v;
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x >= w || y >= h) return;
+    float acc = bias ? __ldg(bias) : 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const float* tp = s_t + ((threadIdx.y + ky) * (H1_TW + 2) + threadIdx.x + kx) * PITCH;
+            const float* wp = s_w + (ky * 3 + kx) * CIN;
+#pragma unroll
+            for (int c4 = 0; c4 < CIN / 4; ++c4) {
+                const float4 a = *reinterpret_cast<const float4*>(tp + c4 * 4);
+                const float4 b = *reinterpret_cast<const float4*>(wp + c4 * 4);
+                acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+            }
+        }
+    const size_t opix = ((size_t)s * h + y) * w + x;
+    if (res) acc += __ldg(res + opix * ldr);
+    out[opix * ldo] = codd_act(acc, act, 0);
+}
+
+// ---------------------------------------------------------------------------------------------
 // ConvTranspose2d k=2 s=2: every output pixel sees exactly one input pixel and one of 4 taps
 // ---------------------------------------------------------------------------------------------
 constexpr int DC_PX = 2;   // input pixels per thread: every weight broadcast (2 x LDS.128) feeds 2 x 2 x 2 packed FMAs
@@ -608,6 +657,14 @@ int conv_dispatch(const ConvP& p, const codd_conv_desc* d, cudaStream_t s) {
     }
     if (kh == 1 && kw == 1 && sh == 1 && sw == 1) return dispatch_cout<1, 1, 1, 1, 1, true>(p, s);
     if (kh == 1 && kw == 1 && sh == 2 && sw == 2) return dispatch_cout<1, 1, 2, 2, 1, false>(p, s);
+    if (kh == 3 && kw == 3 && sh == 1 && sw == 1 && dil == 1 && p.Cout == 1 && p.C0 == 16 && p.C1 == 0 && p.vec0 &&
+        d->ph == 1 && d->pw == 1 && d->ho == d->h && d->wo == d->w && !p.res_after) {
+        dim3 grid(codd_ceil_div(p.W, H1_TW), codd_ceil_div(p.H, H1_TH), p.N), block(H1_TW, H1_TH);
+        conv3x3_head1_kernel<16><<<grid, block, 0, s>>>(p.in0, p.ld0, p.N, p.H, p.W, p.w, p.bias, p.res, p.ldr, p.act,
+                                                        p.out, p.ldo);
+        CODD_RETURN_IF_CUDA_ERROR();
+        return 0;
+    }
     if (kh == 3 && kw == 3 && sh == 1 && sw == 1 && dil == 1) return dispatch_cout<3, 3, 1, 1, 1, true>(p, s);
     if (kh == 3 && kw == 3 && sh == 1 && sw == 1 && dil == 3) return dispatch_cout<3, 3, 1, 1, 3, false>(p, s);
     if (kh == 3 && kw == 3 && sh == 1 && sw == 1 && dil == 4) return dispatch_cout<3, 3, 1, 1, 4, false>(p, s);

@@ -27,6 +27,10 @@ def run_conv(pw, conv, x, act, x2=None, residual=None, res_bcast=False, head=Non
     # amortise its pipeline fill; measured cross-over at batch 8 between the 36x60 and 72x120 levels,
     # tools/conv_probe.py).  The choice depends on the per-sample size only: the two kernels round differently, and a
     # sample's result must not depend on the batch it is in.
+    if cout == 1 and cin == 16 and x2 is None and k == (3, 3) and st == (1, 1) and pd == (1, 1) and dl == 1:
+        # single-channel head (FinalTileUpdate disparity): memory-bound, its own shared-memory tile kernel
+        wp, b = pw.conv_head(conv, 1)
+        return ops.conv2d(x, wp, b, 1, k, st, pd, dl, act, residual=residual, res_bcast=res_bcast)
     big = x.shape[2] * x.shape[3] >= 4096
     if USE_TC and USE_RING and big and dl == 1 and ops.tc_eligible(cin, cout, k, st, pd, dl, x2):
         ws, b = pw.conv_ring(conv, head)

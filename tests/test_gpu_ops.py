@@ -103,6 +103,23 @@ def test_conv2d_dual_input_residual_slices(ops):
     torch.testing.assert_close(back(ops, out), r, rtol=CONV_RTOL, atol=CONV_ATOL)
 
 
+def test_conv3x3_head1_residual_relu(ops):
+    """Single-channel head kernel (propagation.py:325-333 in eval mode): ragged tile edges, 1-channel residual,
+    relu, input as a channel slice of a wider buffer."""
+    from codd_b200.lib import ACT_RELU
+    g = gen(11)
+    x = torch.randn(3, 16, 37, 71, generator=g)
+    wt = torch.randn(1, 16, 3, 3, generator=g) / 12
+    b = torch.randn(1, generator=g)
+    res = torch.randn(3, 1, 37, 71, generator=g)
+    ref = F.relu(F.conv2d(x, wt, b, padding=1) + res)
+    wide = ops.empty_nhwc(3, 32, 37, 71, "cuda")
+    wide[:, 16:32].copy_(x.cuda())
+    out = ops.conv2d(wide[:, 16:32], ops.pack_conv_weight(wt).cuda(), b.cuda(), 1, 3, 1, 1, 1, ACT_RELU,
+                     residual=nhwc(ops, res), res_bcast=True)
+    torch.testing.assert_close(back(ops, out), ref, rtol=CONV_RTOL, atol=CONV_ATOL)
+
+
 def test_tile_conv_right_stride41(ops):
     """initialization.py:121-124: stride (4,1) over the input zero-padded 3 columns on the right."""
     from codd_b200.lib import ACT_LEAKY
