@@ -55,6 +55,13 @@ __device__ __forceinline__ float codd_act_apply(const ActSel& a, float v, int ch
     return codd_act(v, a.act, ch);
 }
 
+// one thread of a converged warp; unlike `lane == 0` ptxas knows the branch body runs in exactly one thread, so
+// tcgen05 operands move to uniform registers without a per-instruction "elect / issue / loop" waterfall
+__device__ __forceinline__ bool codd_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 // acc[0..3] += a * w.{x,y,z,w} as two packed FFMA2 (sm_100a: one instruction = two independent fp32 FMAs, so
 // bit-identical to four FFMA at half the issue slots and half the code size — the direct convolutions are
 // instruction-fetch / issue bound, not FMA-pipe bound).

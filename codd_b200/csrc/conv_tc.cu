@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const __grid_
         // ===================== MMA issuer =====================
         // Software-pipelined over tiles: passes 1-2 of tile i are issued BEFORE pass 3 of tile i-1, so
         // the tensor pipe works on the next tile while the split warps rewrite the previous stage.
-        if (lane == 0) {
+        if (codd_elect_one()) {
             const uint64_t b_desc = make_desc<KC>(sB, 0);
             long long w1 = 0, w2 = 0, w3 = 0;
             auto pass3 = [&](int it) {

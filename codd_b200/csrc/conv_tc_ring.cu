@@ -21,11 +21,17 @@
 // and pass B (kind::f16, K = 16 per MMA) multiplies it by [0 | fp16(w_hi)]: the lo half of a TMEM slot accumulates
 // 2^10 (x_hi w_lo + x_lo w_hi), the epilogue adds hi + 2^-10 lo.  x_lo carries <= 13 significant bits and is 2^-10 of
 // the result, so the 11-bit fp16 mantissa costs nothing measurable (max abs err 4.8e-6 on O(1) outputs).
-// Issue: pass A and pass B are issued by two threads in two warps; a per-stage mbarrier orders pass B of row g after
-// pass A of rows g+1, g+2 (the only MMAs that share accumulators with it), which makes the result bit-deterministic.
+// Issue: pass A and pass B are issued by two elected threads in two warps (elect.sync, so that ptxas keeps the MMA
+// operands in uniform registers: 2-3 instructions per MMA instead of a 10-instruction elect/issue/loop waterfall); a
+// shared "rows issued" counter orders pass B of row g after pass A of rows g+1, g+2 (the only MMAs that share
+// accumulators with it), which makes the result bit-deterministic.
+// Stages: the fp32 rows (TMA -> pass A + split warps) and the fp16 x_lo rows (split warps -> pass B) live in two
+// separate rings with their own full/empty barriers, so a raw row is recycled as soon as pass A and the split have
+// read it and the TMA producer runs ahead of pass B.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -180,7 +186,19 @@ struct Cursor {
     }
 };
 
-template <int KC, int NP, int NBUF>
+__device__ __forceinline__ void st_release_s32(uint32_t addr, int v) {
+    asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_s32(uint32_t addr) {
+    int v;
+    asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+// NBUF fp32 row stages (TMA -> pass A + split warps) and NH fp16 x_lo stages (split warps -> pass B) are separate rings:
+// a raw row is released as soon as pass A and the split have read it, so the TMA producer runs ahead of pass B
+// (which trails pass A by two rows for the deterministic accumulation order).
+template <int KC, int NP, int NBUF, int NH>
 __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __grid_constant__ CUtensorMap tmap, RgP p) {
     constexpr int SLOT = 2 * NP;                 // TMEM columns of one output row: [hi NP | lo NP]
     constexpr int RING = 512 / SLOT;             // 16 (NP = 16) or 8 (NP = 32) output rows in flight
@@ -193,18 +211,19 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
     constexpr uint32_t H_STRIDE = (H_BYTES + 1023u) & ~1023u;
     constexpr uint32_t WBLKH = 6 * NP * ROWH;    // one pass-B kx weight block, fp16
     constexpr uint32_t IDESC_BASE = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 4) << 24);
-    static_assert(NBUF >= 4, "stage depth: pass B trails pass A by >= 2 rows");
+    static_assert(NBUF >= 3 && NH >= 3, "stage depth: pass B trails pass A by 2 rows");
 
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) unsigned long long bars[5 * NBUF + 2 * RING];
+    __shared__ __align__(8) unsigned long long bars[2 * NBUF + 2 * NH + 2 * RING];
     __shared__ uint32_t tmem_base_slot;
+    __shared__ int a_issued_s;      // staged rows whose pass A is in the tensor queue (written by the pass-A thread)
 
     const uint32_t sbase = (s_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gbase = smem_raw + (sbase - s_u32(smem_raw));
     const uint32_t sH = sbase + NBUF * A_STRIDE;             // fp16 x_lo stages
     uint8_t* gH = gbase + NBUF * A_STRIDE;
-    const uint32_t sB = sH + NBUF * H_STRIDE;                // pass-A weights (fp32), then pass-B weights (fp16)
-    uint8_t* gB = gH + NBUF * H_STRIDE;
+    const uint32_t sB = sH + NH * H_STRIDE;                  // pass-A weights (fp32), then pass-B weights (fp16)
+    uint8_t* gB = gH + NH * H_STRIDE;
     const uint32_t sBH = sB + 3 * WBLK;
     uint8_t* gBH = gB + 3 * WBLK;
 
@@ -212,18 +231,23 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
     const bool timing = p.dbg != nullptr;
     const uint32_t bar0 = s_u32(&bars[0]);
     auto SBAR = [&](int kind, int b) { return bar0 + (uint32_t)(kind * NBUF + b) * 8u; };
-    auto ABAR = [&](int kind, int b) { return bar0 + (uint32_t)(5 * NBUF + kind * RING + b) * 8u; };
-    enum { FULL = 0, EMPTY = 1, P12 = 2, LO = 3, ISS = 4 };
+    auto HBAR = [&](int kind, int b) { return bar0 + (uint32_t)(2 * NBUF + kind * NH + b) * 8u; };
+    auto ABAR = [&](int kind, int b) { return bar0 + (uint32_t)(2 * NBUF + 2 * NH + kind * RING + b) * 8u; };
+    enum { FULL = 0, EMPTY = 1 };       // fp32 row stage: TMA landed / pass A done + split done
+    enum { LO = 0, HEMPTY = 1 };        // fp16 x_lo stage: split done / pass B done
     enum { ACCF = 0, ACCE = 1 };
+    const uint32_t a_issued = s_u32(&a_issued_s);
 
     if (tid == 0) {
         for (int b = 0; b < NBUF; ++b) {
             mbar_init(SBAR(FULL, b), 1);
-            mbar_init(SBAR(EMPTY, b), 1);
-            mbar_init(SBAR(P12, b), 1);
-            mbar_init(SBAR(LO, b), RG_SPLIT_THREADS);
-            mbar_init(SBAR(ISS, b), 1);
+            mbar_init(SBAR(EMPTY, b), 1 + RG_SPLIT_THREADS);
         }
+        for (int b = 0; b < NH; ++b) {
+            mbar_init(HBAR(LO, b), RG_SPLIT_THREADS);
+            mbar_init(HBAR(HEMPTY, b), 1);
+        }
+        a_issued_s = 0;
         for (int b = 0; b < RING; ++b) {
             mbar_init(ABAR(ACCF, b), 1);
             mbar_init(ABAR(ACCE, b), RG_EPI_THREADS);
@@ -261,7 +285,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
 
     if (warp == 12) {
         // ===================== TMA producer: one staged row per step =====================
-        if (lane == 0) {
+        if (codd_elect_one()) {
             Cursor c;
             long long w0 = 0;
             for (c.init(p); c.valid(p); c.next(p)) {
@@ -279,10 +303,9 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
         }
     } else if (warp == 13 || warp == 14) {
         // ===================== MMA issuers: warp 13 = pass A (raw rows), warp 14 = pass B (x_lo rows) =====================
-        // Two issuing threads: a single thread pays ~55 cycles per MMA (operand moves to uniform registers + the issue
-        // itself), which at 13 MMAs + 5 barrier operations per row was the kernel's critical path.  Ordering between
-        // the two is carried by the barriers: pass B of a row waits for the split, which waits for pass A's commit.
-        if (lane == 0) {
+        // Two issuing threads (the single-thread issue rate was the first kernel's critical path).  Pass B of a row
+        // waits for its x_lo stage (split warps) and for pass A of the two following rows to be queued.
+        if (codd_elect_one()) {
             // one pass over one staged row: for every (kx, k-step) the row is multiplied by the weight blocks of the
             // valid ky taps; consecutive ring slots are covered by one MMA (N = 2NP, 4NP or 6NP)
             long long w_full = 0, w_lo = 0, w_acce = 0;
@@ -302,8 +325,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
                 auto mma = [&](uint32_t d, uint32_t da, uint32_t db, uint32_t idesc, uint32_t acc) {
                     tc_mma_lo<desc_hi<(int)RB>(), desc_hi<(int)RB>(), PASS != 0>(d, da, db, idesc, acc);
                 };
-                const int sb = c.g % NBUF;
-                const uint32_t a_desc = desc_lo(PASS ? sH + sb * H_STRIDE : sbase + sb * A_STRIDE);
+                const uint32_t a_desc = desc_lo(PASS ? sH + (c.g % NH) * H_STRIDE : sbase + (c.g % NBUF) * A_STRIDE);
                 const int kylo = max(0, c.t - c.rows + 1), kyhi = min(2, c.t);   // output row = y0 + t - ky inside the item
                 // slot(orow) = RING-1 - (orow % RING); ky ascending <=> orow descending <=> slot ascending (mod RING)
                 int slot[3], runn[3];   // runn[ky] > 0: a run of runn adjacent slots starts at ky
@@ -406,8 +428,8 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
                     mbar_wait_t(SBAR(FULL, sb), ((uint32_t)(ca.g / NBUF)) & 1u, w_full, timing);
                     tc_fence_after();
                     issue(ca, std::integral_constant<int, 0>{});
-                    tc_commit(SBAR(P12, sb));                     // raw row consumed -> split warps
-                    mbar_arrive(SBAR(ISS, sb));                   // pass A of this row is in the tensor queue
+                    tc_commit(SBAR(EMPTY, sb));                   // raw row consumed by the tensor core (1 of 1 + split)
+                    st_release_s32(a_issued, ca.g + 1);           // pass A of this row is in the tensor queue
                 }
                 if (p.dbg) {
                     p.dbg[blockIdx.x * 8 + 1] = w_full; p.dbg[blockIdx.x * 8 + 3] = w_acce;
@@ -421,13 +443,13 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
                     gtotal += min(p.seg, p.H - (item % p.nseg) * p.seg) + 2;
                 Cursor cb;
                 for (cb.init(p); cb.valid(p); cb.next(p)) {
-                    const int sb = cb.g % NBUF;
+                    const int hb = cb.g % NH;
                     const int ga = min(cb.g + 2, gtotal - 1);
-                    mbar_wait(SBAR(ISS, ga % NBUF), ((uint32_t)(ga / NBUF)) & 1u);
-                    mbar_wait_t(SBAR(LO, sb), ((uint32_t)(cb.g / NBUF)) & 1u, w_lo, timing);
+                    while (ld_acquire_s32(a_issued) <= ga) {}
+                    mbar_wait_t(HBAR(LO, hb), ((uint32_t)(cb.g / NH)) & 1u, w_lo, timing);
                     tc_fence_after();
                     issue(cb, std::integral_constant<int, 1>{});
-                    tc_commit(SBAR(EMPTY, sb));                   // stage buffer free -> producer
+                    tc_commit(HBAR(HEMPTY, hb));                  // x_lo stage free -> split warps
                     if (cb.t >= 2) {                              // output row y0 + t - 2 is complete
                         const int orow = cb.orow0 + cb.t - 2;
                         tc_commit(ABAR(ACCF, RING - 1 - (orow % RING)));
@@ -521,11 +543,12 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
         Cursor c;
         long long w_p12 = 0;
         for (c.init(p); c.valid(p); c.next(p)) {
-            const int sb = c.g % NBUF;
-            mbar_wait_t(SBAR(P12, sb), ((uint32_t)(c.g / NBUF)) & 1u, w_p12, timing);   // pass A has consumed the raw row
+            const int sb = c.g % NBUF, hb = c.g % NH;
+            mbar_wait_t(HBAR(HEMPTY, hb), (((uint32_t)(c.g / NH)) & 1u) ^ 1u, w_p12, timing);   // pass B of row g - NH done
+            mbar_wait_t(SBAR(FULL, sb), ((uint32_t)(c.g / NBUF)) & 1u, w_p12, timing);          // raw row landed
             tc_fence_after();
             const uint8_t* a8 = gbase + sb * A_STRIDE;
-            uint8_t* h8 = gH + sb * H_STRIDE;
+            uint8_t* h8 = gH + hb * H_STRIDE;
             // one unit = 8 channels of one pixel: two 16-byte fp32 chunks in, one 16-byte fp16 chunk out
             for (int idx = tid; idx < RG_BOXW * (KC / 8); idx += RG_SPLIT_THREADS) {
                 const int px = idx / (KC / 8), u = idx - px * (KC / 8);
@@ -542,7 +565,8 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
                 *reinterpret_cast<uint4*>(h8 + swz_rb<ROWH>(px, u)) = o;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive(SBAR(LO, sb));
+            mbar_arrive(HBAR(LO, hb));
+            mbar_arrive(SBAR(EMPTY, sb));
         }
         if (p.dbg && tid == 0) p.dbg[blockIdx.x * 8 + 7] = w_p12;
     }
@@ -571,14 +595,14 @@ PFN_tmapEncodeTiled rg_get_encode() {
     return fn;
 }
 
-template <int KC, int NP, int NBUF>
+template <int KC, int NP, int NBUF, int NH>
 int launch_ring(const CUtensorMap& tmap, RgP p, cudaStream_t s) {
     constexpr uint32_t ROWB = KC * 4;
     constexpr uint32_t A_STRIDE = ((RG_BOXW * ROWB) + 1023u) & ~1023u;
     constexpr uint32_t H_STRIDE = ((RG_BOXW * KC * 2) + 1023u) & ~1023u;
     constexpr uint32_t B_BYTES = 3 * 6 * NP * ROWB + 3 * 6 * NP * KC * 2;
-    const size_t smem = NBUF * (A_STRIDE + H_STRIDE) + B_BYTES + 1024;
-    auto kern = conv3x3_tc_ring_kernel<KC, NP, NBUF>;
+    const size_t smem = NBUF * A_STRIDE + NH * H_STRIDE + B_BYTES + 1024;
+    auto kern = conv3x3_tc_ring_kernel<KC, NP, NBUF, NH>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -639,9 +663,10 @@ extern "C" int codd_conv3x3_tc_ring(const float* in, int ldi, int cin, int n, in
     p.nseg = p.seg = p.nitems = 0;
     p.dbg = g_rg_dbg;
     cudaStream_t s = (cudaStream_t)stream;
-    if (KC == 32 && NP == 32) return launch_ring<32, 32, 4>(tmap, p, s);
-    if (KC == 32 && NP == 16) return launch_ring<32, 16, 4>(tmap, p, s);
-    return launch_ring<16, 16, 12>(tmap, p, s);
+    static const int cfg = getenv("CODD_RING_CFG") ? atoi(getenv("CODD_RING_CFG")) : 0;   // probe switch (stage depths)
+    if (KC == 32 && NP == 32) return cfg == 1 ? launch_ring<32, 32, 4, 4>(tmap, p, s) : launch_ring<32, 32, 5, 3>(tmap, p, s);
+    if (KC == 32 && NP == 16) return launch_ring<32, 16, 6, 4>(tmap, p, s);
+    return launch_ring<16, 16, 12, 8>(tmap, p, s);
 }
 
 // diagnostic: device buffer of [grid][8] int64 cycle counters filled by the next codd_conv3x3_tc_ring launches

@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (codd_elect_one()) {
             int it = 0, tl = 0;
             for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tl) {
                 const int ab = tl & 1;
