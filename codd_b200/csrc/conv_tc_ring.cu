@@ -42,7 +42,9 @@ constexpr int RG_TW = 128;              // output columns per strip (= MMA M)
 constexpr int RG_BOXW = RG_TW + 2;      // staged pixels per row
 constexpr int RG_EPI_THREADS = 128;
 constexpr int RG_SPLIT_THREADS = 256;
-constexpr int RG_THREADS = 96 + RG_EPI_THREADS + RG_SPLIT_THREADS;   // warps 0-7 split, 8-11 epilogue, 12 TMA, 13 MMA pass A, 14 MMA pass B
+constexpr int RG_SPLIT_GROUP = 128;     // split warps 0-3 take the even staged rows, warps 4-7 the odd ones
+// warps 0-7 split, 8-11 epilogue, 12 TMA, 13 MMA pass A (even rows), 14 MMA pass B, 15 MMA pass A (odd rows)
+constexpr int RG_THREADS = 128 + RG_EPI_THREADS + RG_SPLIT_THREADS;
 
 struct RgP {
     const float* wpk;   // [2 pass][3 kx][6*NP rows][KC]: pass 0 rows per ky = [w_hi | w_lo], pass 1 = [w_hi | 0]
@@ -52,6 +54,8 @@ struct RgP {
     int N, H, W, Cout, ldo, ldr, res_bcast, act;
     int tilesX, nseg, seg, nitems;
     long long* dbg;   // optional [grid][8] cycle counters (role wait times), NULL in production
+    int diag;         // CODD_RING_DIAG probe bits (results are WRONG when set): 1 no pass-B MMAs, 2 no split work,
+                      // 4 no epilogue global traffic, 8 pass A issues kx = 0 only, 16 no TMA loads
 };
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -241,10 +245,10 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
     if (tid == 0) {
         for (int b = 0; b < NBUF; ++b) {
             mbar_init(SBAR(FULL, b), 1);
-            mbar_init(SBAR(EMPTY, b), 1 + RG_SPLIT_THREADS);
+            mbar_init(SBAR(EMPTY, b), 1 + RG_SPLIT_GROUP);
         }
         for (int b = 0; b < NH; ++b) {
-            mbar_init(HBAR(LO, b), RG_SPLIT_THREADS);
+            mbar_init(HBAR(LO, b), RG_SPLIT_GROUP);
             mbar_init(HBAR(HEMPTY, b), 1);
         }
         a_issued_s = 0;
@@ -291,6 +295,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
             for (c.init(p); c.valid(p); c.next(p)) {
                 const int sb = c.g % NBUF;
                 mbar_wait_t(SBAR(EMPTY, sb), (((uint32_t)(c.g / NBUF)) & 1u) ^ 1u, w0, timing);
+                if (p.diag & 16) { mbar_arrive(SBAR(FULL, sb)); continue; }
                 mbar_expect_tx(SBAR(FULL, sb), A_BYTES);
                 const int cx = c.x0 - 1, cy = c.y0 - 1 + c.t;
                 asm volatile(
@@ -301,14 +306,14 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
             }
             if (p.dbg) p.dbg[blockIdx.x * 8 + 0] = w0;
         }
-    } else if (warp == 13 || warp == 14) {
+    } else if (warp >= 13) {
         // ===================== MMA issuers: warp 13 = pass A (raw rows), warp 14 = pass B (x_lo rows) =====================
         // Two issuing threads (the single-thread issue rate was the first kernel's critical path).  Pass B of a row
         // waits for its x_lo stage (split warps) and for pass A of the two following rows to be queued.
         if (codd_elect_one()) {
             // one pass over one staged row: for every (kx, k-step) the row is multiplied by the weight blocks of the
             // valid ky taps; consecutive ring slots are covered by one MMA (N = 2NP, 4NP or 6NP)
-            long long w_full = 0, w_lo = 0, w_acce = 0;
+            long long w_full = 0, w_lo = 0, w_acce = 0, w_iss = 0;
             const long long t_start = clock64();
             // Everything below is indexed by compile-time constants only (fully unrolled): a run table in local memory
             // made the single issuing thread spend ~450 cycles per MMA on dependent local loads.
@@ -344,6 +349,11 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
                     mbar_wait_t(ABAR(ACCE, slot[0]), (((uint32_t)(orow / RING)) & 1u) ^ 1u, w_acce, timing);
                     tc_fence_after();
                 }
+                if (PASS == 0) {
+                    // the two pass-A threads alternate rows; everything above (row landed, slot drained, operand set-up)
+                    // overlaps with the other thread's issue, only the MMAs themselves are handed over in row order
+                    while (ld_acquire_s32(a_issued) < c.g) {}
+                }
                 const uint32_t b_pass = PASS ? bh_desc0 : b_desc0;
                 constexpr uint32_t IDESC3 = IDB | ((uint32_t)((3 * SLOT) >> 3) << 17);
                 constexpr uint32_t IDESC2 = IDB | ((uint32_t)((2 * SLOT) >> 3) << 17);
@@ -362,6 +372,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
                     const uint32_t d2 = tmem + (uint32_t)(slot[2] * SLOT);
 #pragma unroll
                     for (int kx = 0; kx < 3; ++kx) {
+                        if (kx > 0 && (p.diag & 8)) break;
 #pragma unroll
                         for (int k = 0; k < KSP; ++k) {
                             const uint32_t a_k = a_desc + (((uint32_t)kx * RB + (uint32_t)k * 32u) >> 4);
@@ -421,19 +432,23 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
                     }
                 }
             };
-            if (warp == 13) {
+            if (warp != 14) {
                 Cursor ca;
-                for (ca.init(p); ca.valid(p); ca.next(p)) {
+                ca.init(p);
+                if (warp == 15 && ca.valid(p)) ca.next(p);
+                while (ca.valid(p)) {
                     const int sb = ca.g % NBUF;
                     mbar_wait_t(SBAR(FULL, sb), ((uint32_t)(ca.g / NBUF)) & 1u, w_full, timing);
                     tc_fence_after();
                     issue(ca, std::integral_constant<int, 0>{});
-                    tc_commit(SBAR(EMPTY, sb));                   // raw row consumed by the tensor core (1 of 1 + split)
                     st_release_s32(a_issued, ca.g + 1);           // pass A of this row is in the tensor queue
+                    tc_commit(SBAR(EMPTY, sb));                   // raw row consumed by the tensor core (1 of 1 + split)
+                    ca.next(p);
+                    if (ca.valid(p)) ca.next(p);
                 }
-                if (p.dbg) {
+                if (p.dbg && warp == 13) {
                     p.dbg[blockIdx.x * 8 + 1] = w_full; p.dbg[blockIdx.x * 8 + 3] = w_acce;
-                    p.dbg[blockIdx.x * 8 + 4] = clock64() - t_start; p.dbg[blockIdx.x * 8 + 5] = ca.g;
+                    p.dbg[blockIdx.x * 8 + 4] = clock64() - t_start;
                 }
             } else {
                 // Deterministic accumulation order: pass B of row g touches output rows g-2..g, pass A of row h touches
@@ -445,17 +460,21 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
                 for (cb.init(p); cb.valid(p); cb.next(p)) {
                     const int hb = cb.g % NH;
                     const int ga = min(cb.g + 2, gtotal - 1);
-                    while (ld_acquire_s32(a_issued) <= ga) {}
+                    {
+                        const long long t0 = timing ? clock64() : 0;
+                        while (ld_acquire_s32(a_issued) <= ga) {}
+                        if (timing) w_iss += clock64() - t0;
+                    }
                     mbar_wait_t(HBAR(LO, hb), ((uint32_t)(cb.g / NH)) & 1u, w_lo, timing);
                     tc_fence_after();
-                    issue(cb, std::integral_constant<int, 1>{});
+                    if (!(p.diag & 1)) issue(cb, std::integral_constant<int, 1>{});
                     tc_commit(HBAR(HEMPTY, hb));                  // x_lo stage free -> split warps
                     if (cb.t >= 2) {                              // output row y0 + t - 2 is complete
                         const int orow = cb.orow0 + cb.t - 2;
                         tc_commit(ABAR(ACCF, RING - 1 - (orow % RING)));
                     }
                 }
-                if (p.dbg) p.dbg[blockIdx.x * 8 + 2] = w_lo;
+                if (p.dbg) { p.dbg[blockIdx.x * 8 + 2] = w_lo; p.dbg[blockIdx.x * 8 + 5] = w_iss; }
             }
         }
     } else if (warp >= 8) {
@@ -492,7 +511,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
                 tc_fence_before();
                 mbar_arrive(ABAR(ACCE, slot));
                 const int y = y0 + r;
-                if (x >= p.W) continue;
+                if (x >= p.W || (p.diag & 4)) continue;
                 const size_t opix = ((size_t)n * p.H + y) * p.W + x;
                 float* op = p.out + opix * p.ldo;
                 float v[NP];
@@ -539,34 +558,56 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
         }
         if (p.dbg && tid == 256) p.dbg[blockIdx.x * 8 + 6] = w_accf;
     } else {
-        // ===================== in-place hi/lo split of a staged row (warps 0-7) =====================
+        // ===================== x_lo stage of a staged row (warps 0-3: even rows, warps 4-7: odd rows) =====================
+        constexpr int UNITS = RG_BOXW * (KC / 8);                  // one unit = 8 channels of one pixel
+        constexpr int UMAX = (UNITS + RG_SPLIT_GROUP - 1) / RG_SPLIT_GROUP;
+        const int gt = tid & (RG_SPLIT_GROUP - 1);
         Cursor c;
         long long w_p12 = 0;
-        for (c.init(p); c.valid(p); c.next(p)) {
+        c.init(p);
+        if (warp >= 4 && c.valid(p)) c.next(p);
+        while (c.valid(p)) {
             const int sb = c.g % NBUF, hb = c.g % NH;
             mbar_wait_t(HBAR(HEMPTY, hb), (((uint32_t)(c.g / NH)) & 1u) ^ 1u, w_p12, timing);   // pass B of row g - NH done
             mbar_wait_t(SBAR(FULL, sb), ((uint32_t)(c.g / NBUF)) & 1u, w_p12, timing);          // raw row landed
             tc_fence_after();
             const uint8_t* a8 = gbase + sb * A_STRIDE;
             uint8_t* h8 = gH + hb * H_STRIDE;
-            // one unit = 8 channels of one pixel: two 16-byte fp32 chunks in, one 16-byte fp16 chunk out
-            for (int idx = tid; idx < RG_BOXW * (KC / 8); idx += RG_SPLIT_THREADS) {
-                const int px = idx / (KC / 8), u = idx - px * (KC / 8);
-                const float4 v0 = *reinterpret_cast<const float4*>(a8 + swz_off<KC>(px, 2 * u));
-                const float4 v1 = *reinterpret_cast<const float4*>(a8 + swz_off<KC>(px, 2 * u + 1));
-                auto lo16 = [](float a, float b) {
-                    const float la = fminf(fmaxf(tf32_lo(a) * RG_LO_SCALE, -65504.f), 65504.f);
-                    const float lb = fminf(fmaxf(tf32_lo(b) * RG_LO_SCALE, -65504.f), 65504.f);
-                    const __half2 h = __floats2half2_rn(la, lb);
-                    return *reinterpret_cast<const uint32_t*>(&h);
-                };
-                uint4 o;
-                o.x = lo16(v0.x, v0.y); o.y = lo16(v0.z, v0.w); o.z = lo16(v1.x, v1.y); o.w = lo16(v1.z, v1.w);
-                *reinterpret_cast<uint4*>(h8 + swz_rb<ROWH>(px, u)) = o;
+            if (!(p.diag & 2)) {
+                // all loads first (two 16-byte fp32 chunks per unit), then the conversions, then one 16-byte fp16 chunk out
+                float4 v0[UMAX], v1[UMAX];
+#pragma unroll
+                for (int k = 0; k < UMAX; ++k) {
+                    const int idx = gt + k * RG_SPLIT_GROUP;
+                    if (idx < UNITS) {
+                        const int px = idx / (KC / 8), u = idx - px * (KC / 8);
+                        v0[k] = *reinterpret_cast<const float4*>(a8 + swz_off<KC>(px, 2 * u));
+                        v1[k] = *reinterpret_cast<const float4*>(a8 + swz_off<KC>(px, 2 * u + 1));
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < UMAX; ++k) {
+                    const int idx = gt + k * RG_SPLIT_GROUP;
+                    if (idx < UNITS) {
+                        const int px = idx / (KC / 8), u = idx - px * (KC / 8);
+                        auto lo16 = [](float a, float b) {
+                            const float la = fminf(fmaxf(tf32_lo(a) * RG_LO_SCALE, -65504.f), 65504.f);
+                            const float lb = fminf(fmaxf(tf32_lo(b) * RG_LO_SCALE, -65504.f), 65504.f);
+                            const __half2 h = __floats2half2_rn(la, lb);
+                            return *reinterpret_cast<const uint32_t*>(&h);
+                        };
+                        uint4 o;
+                        o.x = lo16(v0[k].x, v0[k].y); o.y = lo16(v0[k].z, v0[k].w);
+                        o.z = lo16(v1[k].x, v1[k].y); o.w = lo16(v1[k].z, v1[k].w);
+                        *reinterpret_cast<uint4*>(h8 + swz_rb<ROWH>(px, u)) = o;
+                    }
+                }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(HBAR(LO, hb));
             mbar_arrive(SBAR(EMPTY, sb));
+            c.next(p);
+            if (c.valid(p)) c.next(p);
         }
         if (p.dbg && tid == 0) p.dbg[blockIdx.x * 8 + 7] = w_p12;
     }
@@ -662,6 +703,8 @@ extern "C" int codd_conv3x3_tc_ring(const float* in, int ldi, int cin, int n, in
     p.tilesX = codd_ceil_div(w, RG_TW);
     p.nseg = p.seg = p.nitems = 0;
     p.dbg = g_rg_dbg;
+    static const int diag = getenv("CODD_RING_DIAG") ? atoi(getenv("CODD_RING_DIAG")) : 0;
+    p.diag = diag;
     cudaStream_t s = (cudaStream_t)stream;
     static const int cfg = getenv("CODD_RING_CFG") ? atoi(getenv("CODD_RING_CFG")) : 0;   // probe switch (stage depths)
     if (KC == 32 && NP == 32) return cfg == 1 ? launch_ring<32, 32, 4, 4>(tmap, p, s) : launch_ring<32, 32, 5, 3>(tmap, p, s);
@@ -670,8 +713,8 @@ extern "C" int codd_conv3x3_tc_ring(const float* in, int ldi, int cin, int n, in
 }
 
 // diagnostic: device buffer of [grid][8] int64 cycle counters filled by the next codd_conv3x3_tc_ring launches
-// (0 producer wait-empty, 1 mma wait-full, 2 mma wait-lo, 3 mma wait-slot-drained, 4 mma total, 5 staged rows,
-//  6 epilogue wait-acc-full, 7 split wait-p12); NULL disables.
+// (0 producer wait-empty, 1 mma wait-full, 2 mma wait-lo, 3 mma wait-slot-drained, 4 pass-A thread total, 5 pass-B wait for pass A of row g+2,
+//  6 epilogue wait-acc-full, 7 split wait (x_lo stage free + row landed)); NULL disables.
 extern "C" CODD_API int codd_conv3x3_tc_ring_debug(long long* dbg) {
     g_rg_dbg = dbg;
     return 0;

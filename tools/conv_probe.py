@@ -38,7 +38,7 @@ def main():
         torch.cuda.synchronize()
         lib.load().codd_conv3x3_tc_ring_debug(None)
         d = dbg.view(148, 8).float().mean(0).tolist()
-        print("   ring role waits (mean clk/CTA): producer-empty %.0f | mma: full %.0f lo %.0f slot %.0f total %.0f rows %.0f | "
+        print("   ring role waits (mean clk/CTA): producer-empty %.0f | A: full %.0f | B: lo %.0f | A: slot %.0f total %.0f | B: iss %.0f | "
               "epi accf %.0f | split p12 %.0f" % tuple(d))
         print(f"N={n} C={c} {h}x{w}: halo-tile {t_old * 1e3:.1f} us ({gb / t_old * 1e3:.0f} GB/s)   ring {t_new * 1e3:.1f} us "
               f"({gb / t_new * 1e3:.0f} GB/s)")
