@@ -1,6 +1,6 @@
 // 3x3 / stride 1 / pad 1 convolution on tcgen05 — "rolling ring" formulation.
 //
-// Same math, precision (3xTF32) and epilogue as conv_tc.cu, different dataflow.  conv_tc.cu is bound by the
+// Same math and epilogue as conv_tc.cu, different dataflow and operand format.  conv_tc.cu is bound by the
 // shared-memory reads of the A operand: every (tap, k-step, pass) MMA re-reads a 4 KB activation slice for only
 // N = 2*Cout <= 64 output columns (ncu: sm__pipe_tc_cycles_active 82 %, tensor math 20 %).  Here the three ky taps
 // are folded into N:
@@ -16,11 +16,15 @@
 // Per output row and 128 pixels the tensor core now reads 12 A slices (Cin=16) instead of 36, B grows from 0.5-1 KB
 // to 3 KB per MMA: 84 KB instead of 162 KB of operand traffic, and the stage is written / split once instead of twice.
 //
-// Precision (3xTF32-class): pass A (kind::tf32) multiplies the raw fp32 row (the MMA reads the top 19 bits = x_hi) by
-// [w_hi | 2^10 w_lo] per tap; the split warps write fp16(2^10 * x_lo), x_lo = x - x_hi, into a second half-size stage
-// and pass B (kind::f16, K = 16 per MMA) multiplies it by [0 | fp16(w_hi)]: the lo half of a TMEM slot accumulates
-// 2^10 (x_hi w_lo + x_lo w_hi), the epilogue adds hi + 2^-10 lo.  x_lo carries <= 13 significant bits and is 2^-10 of
-// the result, so the 11-bit fp16 mantissa costs nothing measurable (max abs err 4.8e-6 on O(1) outputs).
+// Precision (3xTF32-class, all operands fp16): the split warps write x_hi = fp16(x) and fp16(2^10 x_lo), x_lo = x - x_hi
+// (exact in fp32), as two fp16 tiles; the weights are split the same way on the host.  Pass A multiplies the x_hi tile
+// by [w_hi | 2^10 w_lo] per tap, pass B the x_lo tile by [0 | w_hi]: the hi half of a TMEM slot accumulates x_hi w_hi
+// (exact products, fp32 accumulation), the lo half 2^10 (x_hi w_lo + x_lo w_hi), the epilogue adds hi + 2^-10 lo.  fp16
+// and tf32 both carry 11 significant bits, so the error is that of 3xTF32 (dropped term x_lo w_lo ~ 2^-22), but
+// kind::f16 consumes K = 16 per MMA where kind::tf32 consumes 8: half the MMAs and half the shared-memory operand
+// reads per row — the kernel is bound by the L1/shared data pipe (ncu: tensor-core operand wavefronts 46 % + LSU 34 %).
+// Range: |x| and |w| are clamped to the fp16 maximum 65504 (HITNet activations are O(1..1e3)); values below 6e-5 keep
+// an absolute error <= 6e-11.
 // Issue: pass A and pass B are issued by two elected threads in two warps (elect.sync, so that ptxas keeps the MMA
 // operands in uniform registers: 2-3 instructions per MMA instead of a 10-instruction elect/issue/loop waterfall); a
 // shared "rows issued" counter orders pass B of row g after pass A of rows g+1, g+2 (the only MMAs that share
@@ -114,9 +118,6 @@ __device__ __forceinline__ uint32_t swz_off(int r, int j) {
     constexpr uint32_t MASK = (KC == 32) ? 7u : 3u;
     return off ^ (((off >> 7) & MASK) << 4);
 }
-__device__ __forceinline__ float tf32_lo(float x) {
-    return __fsub_rn(x, __uint_as_float(__float_as_uint(x) & 0xFFFFE000u));
-}
 // byte offset of 16-byte chunk j of row r in a tile of RB-byte rows whose base is 1024-aligned
 template <int RB>
 __device__ __forceinline__ uint32_t swz_rb(int r, int j) {
@@ -209,13 +210,16 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
     constexpr uint32_t ROWB = KC * 4;
     constexpr uint32_t A_BYTES = RG_BOXW * ROWB;
     constexpr uint32_t A_STRIDE = (A_BYTES + 1023u) & ~1023u;
-    constexpr uint32_t WBLK = 6 * NP * ROWB;     // one pass-A kx weight block: 3 ky x [2*NP rows], fp32
-    constexpr uint32_t ROWH = KC * 2;            // fp16 operand rows of pass B
+    constexpr uint32_t ROWH = KC * 2;            // fp16 operand rows (both passes)
     constexpr uint32_t H_BYTES = RG_BOXW * ROWH;
-    constexpr uint32_t H_STRIDE = (H_BYTES + 1023u) & ~1023u;
-    constexpr uint32_t WBLKH = 6 * NP * ROWH;    // one pass-B kx weight block, fp16
-    constexpr uint32_t IDESC_BASE = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 4) << 24);
-    static_assert(NBUF >= 3 && NH >= 3, "stage depth: pass B trails pass A by 2 rows");
+    constexpr uint32_t H_STRIDE = (H_BYTES + 1023u) & ~1023u;   // one fp16 tile (x_hi or x_lo) of a staged row
+    constexpr uint32_t HL_STRIDE = 2 * H_STRIDE;                // operand stage = [x_hi tile | x_lo tile]
+    constexpr uint32_t WBLKH = 6 * NP * ROWH;    // one kx weight block: 3 ky x [2*NP rows], fp16
+    static_assert(NBUF >= 4 && NH >= 4, "stage depth: pass B trails pass A by 2 rows");
+    // rows alternate between two warp sets (split groups, pass-A threads): with an even ring depth a given stage barrier
+    // is always waited on by the SAME set, which therefore sees every phase of it — with an odd depth a set would see
+    // every other phase and the one-bit parity wait could pass two phases early
+    static_assert(NBUF % 2 == 0 && NH % 2 == 0, "ring depths must be even");
 
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) unsigned long long bars[2 * NBUF + 2 * NH + 2 * RING];
@@ -224,12 +228,11 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
 
     const uint32_t sbase = (s_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gbase = smem_raw + (sbase - s_u32(smem_raw));
-    const uint32_t sH = sbase + NBUF * A_STRIDE;             // fp16 x_lo stages
+    const uint32_t sH = sbase + NBUF * A_STRIDE;             // fp16 operand stages [x_hi | x_lo]
     uint8_t* gH = gbase + NBUF * A_STRIDE;
-    const uint32_t sB = sH + NH * H_STRIDE;                  // pass-A weights (fp32), then pass-B weights (fp16)
-    uint8_t* gB = gH + NH * H_STRIDE;
-    const uint32_t sBH = sB + 3 * WBLK;
-    uint8_t* gBH = gB + 3 * WBLK;
+    const uint32_t sB = sH + NH * HL_STRIDE;                 // pass-A weights, then pass-B weights (both fp16)
+    uint8_t* gB = gH + NH * HL_STRIDE;
+    const uint32_t sBH = sB + 3 * WBLKH;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool timing = p.dbg != nullptr;
@@ -237,19 +240,19 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
     auto SBAR = [&](int kind, int b) { return bar0 + (uint32_t)(kind * NBUF + b) * 8u; };
     auto HBAR = [&](int kind, int b) { return bar0 + (uint32_t)(2 * NBUF + kind * NH + b) * 8u; };
     auto ABAR = [&](int kind, int b) { return bar0 + (uint32_t)(2 * NBUF + 2 * NH + kind * RING + b) * 8u; };
-    enum { FULL = 0, EMPTY = 1 };       // fp32 row stage: TMA landed / pass A done + split done
-    enum { LO = 0, HEMPTY = 1 };        // fp16 x_lo stage: split done / pass B done
+    enum { FULL = 0, EMPTY = 1 };       // fp32 row stage: TMA landed / split done
+    enum { LO = 0, HEMPTY = 1 };        // fp16 operand stage: split done / pass A and pass B done
     enum { ACCF = 0, ACCE = 1 };
     const uint32_t a_issued = s_u32(&a_issued_s);
 
     if (tid == 0) {
         for (int b = 0; b < NBUF; ++b) {
             mbar_init(SBAR(FULL, b), 1);
-            mbar_init(SBAR(EMPTY, b), 1 + RG_SPLIT_GROUP);
+            mbar_init(SBAR(EMPTY, b), RG_SPLIT_GROUP);
         }
         for (int b = 0; b < NH; ++b) {
             mbar_init(HBAR(LO, b), RG_SPLIT_GROUP);
-            mbar_init(HBAR(HEMPTY, b), 1);
+            mbar_init(HBAR(HEMPTY, b), 2);
         }
         a_issued_s = 0;
         for (int b = 0; b < RING; ++b) {
@@ -263,23 +266,13 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
                      "r"(512u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
-    // weights -> swizzled shared images: 3 fp32 blocks (pass A, per kx, 6*NP rows of KC floats) and 3 fp16 blocks (pass B)
-    for (int idx = tid; idx < 3 * 6 * NP * (KC / 4); idx += RG_THREADS) {
-        const int j = idx % (KC / 4);
-        const int r = (idx / (KC / 4)) % (6 * NP);
-        const int blk = idx / ((KC / 4) * 6 * NP);
-        const float4 v = ldg4(p.wpk + ((size_t)blk * 6 * NP + r) * KC + j * 4);
-        *reinterpret_cast<float4*>(gB + blk * WBLK + swz_off<KC>(r, j)) = v;
-    }
-    {
-        const float* wh = p.wpk + (size_t)3 * 6 * NP * KC;      // fp16 data, KC/2 floats per row
-        for (int idx = tid; idx < 3 * 6 * NP * (KC / 8); idx += RG_THREADS) {
-            const int j = idx % (KC / 8);
-            const int r = (idx / (KC / 8)) % (6 * NP);
-            const int blk = idx / ((KC / 8) * 6 * NP);
-            const float4 v = ldg4(wh + ((size_t)blk * 6 * NP + r) * (KC / 2) + j * 4);
-            *reinterpret_cast<float4*>(gBH + blk * WBLKH + swz_rb<ROWH>(r, j)) = v;
-        }
+    // weights -> swizzled shared images: 2 passes x 3 kx blocks of 6*NP rows x KC halves (KC/2 floats per row)
+    for (int idx = tid; idx < 2 * 3 * 6 * NP * (KC / 8); idx += RG_THREADS) {
+        const int j = idx % (KC / 8);
+        const int r = (idx / (KC / 8)) % (6 * NP);
+        const int blk = idx / ((KC / 8) * 6 * NP);         // pass * 3 + kx
+        const float4 v = ldg4(p.wpk + ((size_t)blk * 6 * NP + r) * (KC / 2) + j * 4);
+        *reinterpret_cast<float4*>(gB + blk * WBLKH + swz_rb<ROWH>(r, j)) = v;
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc_fence_before();
@@ -320,17 +313,17 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
             const uint32_t b_desc0 = desc_lo(sB);
             const uint32_t bh_desc0 = desc_lo(sBH);
             auto issue = [&](const Cursor& c, auto pass_tag) {
-                // PASS 0: raw fp32 row x [w_hi | 2^10 w_lo] (kind::tf32, K = 8 floats per MMA);
-                // PASS 1: fp16(2^10 x_lo) row x [0 | fp16(w_hi)] (kind::f16, K = 16 halves per MMA, half the operand bytes)
+                // PASS 0: x_hi row x [w_hi | 2^10 w_lo];  PASS 1: 2^10 x_lo row x [0 | w_hi]   (all fp16 operands, fp32
+                // accumulation; kind::f16, K = 16 halves = 32 operand bytes per row and MMA)
                 constexpr int PASS = decltype(pass_tag)::value;
-                constexpr uint32_t RB = PASS ? ROWH : ROWB;
-                constexpr uint32_t WB = PASS ? WBLKH : WBLK;
-                constexpr int KSP = PASS ? KC / 16 : KC / 8;
-                constexpr uint32_t IDB = PASS ? ((1u << 4) | ((128u >> 4) << 24)) : IDESC_BASE;    // f16: a/b format 0 = F16
+                constexpr uint32_t RB = ROWH;
+                constexpr uint32_t WB = WBLKH;
+                constexpr int KSP = KC / 16;
+                constexpr uint32_t IDB = (1u << 4) | ((128u >> 4) << 24);    // D = f32, A = B = f16, M = 128
                 auto mma = [&](uint32_t d, uint32_t da, uint32_t db, uint32_t idesc, uint32_t acc) {
-                    tc_mma_lo<desc_hi<(int)RB>(), desc_hi<(int)RB>(), PASS != 0>(d, da, db, idesc, acc);
+                    tc_mma_lo<desc_hi<(int)RB>(), desc_hi<(int)RB>(), true>(d, da, db, idesc, acc);
                 };
-                const uint32_t a_desc = desc_lo(PASS ? sH + (c.g % NH) * H_STRIDE : sbase + (c.g % NBUF) * A_STRIDE);
+                const uint32_t a_desc = desc_lo(sH + (c.g % NH) * HL_STRIDE + (PASS ? H_STRIDE : 0u));
                 const int kylo = max(0, c.t - c.rows + 1), kyhi = min(2, c.t);   // output row = y0 + t - ky inside the item
                 // slot(orow) = RING-1 - (orow % RING); ky ascending <=> orow descending <=> slot ascending (mod RING)
                 int slot[3], runn[3];   // runn[ky] > 0: a run of runn adjacent slots starts at ky
@@ -437,12 +430,12 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
                 ca.init(p);
                 if (warp == 15 && ca.valid(p)) ca.next(p);
                 while (ca.valid(p)) {
-                    const int sb = ca.g % NBUF;
-                    mbar_wait_t(SBAR(FULL, sb), ((uint32_t)(ca.g / NBUF)) & 1u, w_full, timing);
+                    const int hb = ca.g % NH;
+                    mbar_wait_t(HBAR(LO, hb), ((uint32_t)(ca.g / NH)) & 1u, w_full, timing);    // operand stage written
                     tc_fence_after();
                     issue(ca, std::integral_constant<int, 0>{});
                     st_release_s32(a_issued, ca.g + 1);           // pass A of this row is in the tensor queue
-                    tc_commit(SBAR(EMPTY, sb));                   // raw row consumed by the tensor core (1 of 1 + split)
+                    tc_commit(HBAR(HEMPTY, hb));                  // 1 of 2: pass A has read the operand stage
                     ca.next(p);
                     if (ca.valid(p)) ca.next(p);
                 }
@@ -468,7 +461,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
                     mbar_wait_t(HBAR(LO, hb), ((uint32_t)(cb.g / NH)) & 1u, w_lo, timing);
                     tc_fence_after();
                     if (!(p.diag & 1)) issue(cb, std::integral_constant<int, 1>{});
-                    tc_commit(HBAR(HEMPTY, hb));                  // x_lo stage free -> split warps
+                    tc_commit(HBAR(HEMPTY, hb));                  // 2 of 2: pass B has read the operand stage
                     if (cb.t >= 2) {                              // output row y0 + t - 2 is complete
                         const int orow = cb.orow0 + cb.t - 2;
                         tc_commit(ABAR(ACCF, RING - 1 - (orow % RING)));
@@ -572,7 +565,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
             mbar_wait_t(SBAR(FULL, sb), ((uint32_t)(c.g / NBUF)) & 1u, w_p12, timing);          // raw row landed
             tc_fence_after();
             const uint8_t* a8 = gbase + sb * A_STRIDE;
-            uint8_t* h8 = gH + hb * H_STRIDE;
+            uint8_t* h8 = gH + hb * HL_STRIDE;
             if (!(p.diag & 2)) {
                 // all loads first (two 16-byte fp32 chunks per unit), then the conversions, then one 16-byte fp16 chunk out
                 float4 v0[UMAX], v1[UMAX];
@@ -590,16 +583,22 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
                     const int idx = gt + k * RG_SPLIT_GROUP;
                     if (idx < UNITS) {
                         const int px = idx / (KC / 8), u = idx - px * (KC / 8);
-                        auto lo16 = [](float a, float b) {
-                            const float la = fminf(fmaxf(tf32_lo(a) * RG_LO_SCALE, -65504.f), 65504.f);
-                            const float lb = fminf(fmaxf(tf32_lo(b) * RG_LO_SCALE, -65504.f), 65504.f);
-                            const __half2 h = __floats2half2_rn(la, lb);
-                            return *reinterpret_cast<const uint32_t*>(&h);
-                        };
-                        uint4 o;
-                        o.x = lo16(v0[k].x, v0[k].y); o.y = lo16(v0[k].z, v0[k].w);
-                        o.z = lo16(v1[k].x, v1[k].y); o.w = lo16(v1[k].z, v1[k].w);
-                        *reinterpret_cast<uint4*>(h8 + swz_rb<ROWH>(px, u)) = o;
+                        // x = x_hi + x_lo with x_hi = fp16(x) (11 significant bits, like tf32) and the exact fp32 remainder
+                        // x_lo travelling as fp16(2^10 x_lo); |x| is clamped to the fp16 range (see header)
+                        uint32_t hi2[4], lo2[4];
+                        const float xs[8] = {v0[k].x, v0[k].y, v0[k].z, v0[k].w, v1[k].x, v1[k].y, v1[k].z, v1[k].w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float a = fminf(fmaxf(xs[2 * e], -65504.f), 65504.f);
+                            const float b = fminf(fmaxf(xs[2 * e + 1], -65504.f), 65504.f);
+                            const __half2 h = __floats2half2_rn(a, b);
+                            const float2 hf = __half22float2(h);
+                            const __half2 l = __floats2half2_rn((a - hf.x) * RG_LO_SCALE, (b - hf.y) * RG_LO_SCALE);
+                            hi2[e] = *reinterpret_cast<const uint32_t*>(&h);
+                            lo2[e] = *reinterpret_cast<const uint32_t*>(&l);
+                        }
+                        *reinterpret_cast<uint4*>(h8 + swz_rb<ROWH>(px, u)) = make_uint4(hi2[0], hi2[1], hi2[2], hi2[3]);
+                        *reinterpret_cast<uint4*>(h8 + H_STRIDE + swz_rb<ROWH>(px, u)) = make_uint4(lo2[0], lo2[1], lo2[2], lo2[3]);
                     }
                 }
             }
@@ -641,8 +640,9 @@ int launch_ring(const CUtensorMap& tmap, RgP p, cudaStream_t s) {
     constexpr uint32_t ROWB = KC * 4;
     constexpr uint32_t A_STRIDE = ((RG_BOXW * ROWB) + 1023u) & ~1023u;
     constexpr uint32_t H_STRIDE = ((RG_BOXW * KC * 2) + 1023u) & ~1023u;
-    constexpr uint32_t B_BYTES = 3 * 6 * NP * ROWB + 3 * 6 * NP * KC * 2;
-    const size_t smem = NBUF * A_STRIDE + NH * H_STRIDE + B_BYTES + 1024;
+    constexpr uint32_t B_BYTES = 2 * 3 * 6 * NP * KC * 2;
+    const size_t smem = NBUF * A_STRIDE + NH * 2 * H_STRIDE + B_BYTES + 1024;
+    static_assert(NBUF * A_STRIDE + NH * 2 * H_STRIDE + B_BYTES + 1024 + 2048 <= 232448, "shared memory budget");
     auto kern = conv3x3_tc_ring_kernel<KC, NP, NBUF, NH>;
     static bool configured = false;
     if (!configured) {
@@ -706,10 +706,9 @@ extern "C" int codd_conv3x3_tc_ring(const float* in, int ldi, int cin, int n, in
     static const int diag = getenv("CODD_RING_DIAG") ? atoi(getenv("CODD_RING_DIAG")) : 0;
     p.diag = diag;
     cudaStream_t s = (cudaStream_t)stream;
-    static const int cfg = getenv("CODD_RING_CFG") ? atoi(getenv("CODD_RING_CFG")) : 0;   // probe switch (stage depths)
-    if (KC == 32 && NP == 32) return cfg == 1 ? launch_ring<32, 32, 4, 4>(tmap, p, s) : launch_ring<32, 32, 5, 3>(tmap, p, s);
-    if (KC == 32 && NP == 16) return launch_ring<32, 16, 6, 4>(tmap, p, s);
-    return launch_ring<16, 16, 12, 8>(tmap, p, s);
+    if (KC == 32 && NP == 32) return launch_ring<32, 32, 4, 4>(tmap, p, s);
+    if (KC == 32 && NP == 16) return launch_ring<32, 16, 4, 6>(tmap, p, s);
+    return launch_ring<16, 16, 6, 10>(tmap, p, s);
 }
 
 // diagnostic: device buffer of [grid][8] int64 cycle counters filled by the next codd_conv3x3_tc_ring launches

@@ -169,32 +169,34 @@ def pack_conv_weight_tc(w):
 
 
 def pack_conv_weight_ring(w):
-    """torch [Cout,Cin,3,3] -> flat fp32 buffer for codd_conv3x3_tc_ring:
-    pass A  [3 kx][6*NP rows][KC] fp32 — rows per ky = [w_hi (NP) | 2^10 * w_lo (NP)]   (tf32 halves of the weight),
-    pass B  [3 kx][6*NP rows][KC] fp16 — rows per ky = [0 (NP) | fp16(w_hi) (NP)], stored as KC/2 floats per row.
-    The lo half of a TMEM slot therefore accumulates 2^10 * (x_hi*w_lo + x_lo*w_hi); the epilogue scales it back."""
+    """torch [Cout,Cin,3,3] -> flat buffer for codd_conv3x3_tc_ring (fp16 data, returned viewed as float32):
+    pass A  [3 kx][6*NP rows][KC] — rows per ky = [w_hi (NP) | 2^10 * w_lo (NP)],  w_hi = fp16(w), w_lo = w - w_hi,
+    pass B  [3 kx][6*NP rows][KC] — rows per ky = [0 (NP) | w_hi (NP)].
+    With x split the same way by the kernel, the lo half of a TMEM slot accumulates 2^10 * (x_hi*w_lo + x_lo*w_hi) and
+    the epilogue scales it back: three fp16 products with fp32 accumulation = fp32-class accuracy (cf. 3xTF32)."""
     cout, cin, kh, kw = w.shape
     assert kh == 3 and kw == 3
     kc = 16 if cin <= 16 else 32
     npad = 16 if cout <= 16 else 32
     wt = torch.zeros((3, 3, npad, kc), dtype=torch.float32, device=w.device)            # [ky][kx][cout][cin]
     wt[:, :, :cout, :cin] = w.detach().float().permute(2, 3, 0, 1)
-    hi = _tf32_round(wt)
-    lo = _tf32_round(wt - hi)
-    pa = torch.zeros((3, 3, 2, npad, kc), dtype=torch.float32, device=w.device)         # [kx][ky][hi|lo][cout][cin]
+    wt = wt.clamp(-65504.0, 65504.0)
+    hi = wt.half()
+    lo = ((wt - hi.float()) * 1024.0).half()
+    pa = torch.zeros((3, 3, 2, npad, kc), dtype=torch.float16, device=w.device)         # [kx][ky][hi|lo][cout][cin]
     pa[:, :, 0] = hi.permute(1, 0, 2, 3)
-    pa[:, :, 1] = lo.permute(1, 0, 2, 3) * 1024.0
+    pa[:, :, 1] = lo.permute(1, 0, 2, 3)
     pb = torch.zeros((3, 3, 2, npad, kc), dtype=torch.float16, device=w.device)
-    pb[:, :, 1] = hi.permute(1, 0, 2, 3).half()
-    return torch.cat([pa.reshape(-1), pb.reshape(-1).view(torch.float32)]).contiguous()
+    pb[:, :, 1] = hi.permute(1, 0, 2, 3)
+    return torch.cat([pa.reshape(-1), pb.reshape(-1)]).contiguous().view(torch.float32)
 
 
 def conv3x3_tc_ring(x, wring, bias, cout, act=ACT_NONE, residual=None, res_bcast=False):
-    """3x3 s1 p1 conv on the tensor cores, rolling-ring kernel (3xTF32).  ``wring`` from pack_conv_weight_ring."""
+    """3x3 s1 p1 conv on the tensor cores, rolling-ring kernel (3 fp16 products, fp32 accumulation).  ``wring`` from pack_conv_weight_ring."""
     _require_cuda(x, wring, bias, residual)
     n, cin, h, w = x.shape
     out = empty_nhwc(n, cout, h, w, x.device)
-    nbytes = 4 * (n * h * w * (cin + cout) + wring.numel() // 3
+    nbytes = 4 * (n * h * w * (cin + cout) + wring.numel()
                   + (0 if residual is None else n * h * w * (1 if res_bcast else cout)))
     rc = _run(f"conv3x3ring_cin{cin}_cout{cout}", nbytes, lambda: _lib.load().codd_conv3x3_tc_ring(
         x.data_ptr(), ld_of(x), cin, n, h, w, wring.data_ptr(), None if bias is None else bias.data_ptr(),

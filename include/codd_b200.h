@@ -100,10 +100,12 @@ CODD_API int codd_conv3x3_tc_dil(const float* in, int ldi, int cin, int n, int h
 /* Rolling-ring formulation of the same 3x3 / stride 1 / pad 1 tensor-core convolution (csrc/conv_tc_ring.cu): a CTA
  * walks a 128-column strip one staged input row at a time and ONE MMA per (kx, k-step) accumulates into the three
  * output rows a staged row contributes to (N = 3 * 2*Cout; accumulators = a ring of TMEM slots).  Same shapes as
- * codd_conv3x3_tc (dilation 1).  weight_ring (host: ops.pack_conv_weight_ring) holds the pass-A block [3 kx][6*NP rows][KC]
- * fp32 — rows per ky = [w_hi (NP) | 2^10 * w_lo (NP)] — followed by the pass-B block [3 kx][6*NP rows][KC] fp16 — rows per
- * ky = [0 | fp16(w_hi)]: the x_lo pass runs as kind::f16 on fp16(2^10 * x_lo) into the lo half of each TMEM slot, the
- * epilogue adds hi + 2^-10 * lo (fp32-class accuracy at half the operand traffic of a tf32 pass). */
+ * codd_conv3x3_tc (dilation 1).  weight_ring (host: ops.pack_conv_weight_ring) holds fp16 data: the pass-A block
+ * [3 kx][6*NP rows][KC] — rows per ky = [w_hi (NP) | 2^10 * w_lo (NP)], w_hi = fp16(w), w_lo = w - w_hi — followed by the
+ * pass-B block [3 kx][6*NP rows][KC] — rows per ky = [0 | w_hi].  The kernel splits the activations the same way
+ * (x_hi = fp16(x), fp16(2^10 * x_lo)); both passes run as kind::f16 with fp32 accumulation, the lo half of each TMEM slot
+ * collects 2^10 (x_hi w_lo + x_lo w_hi) and the epilogue adds hi + 2^-10 * lo: 3xTF32-class accuracy (11-bit halves) at
+ * half the MMAs and operand traffic of a tf32 pass.  |x|, |w| are clamped to the fp16 range (65504). */
 CODD_API int codd_conv3x3_tc_ring(const float* in, int ldi, int cin, int n, int h, int w, const float* weight_ring,
                                   const float* bias, const float* residual, int ldr, int res_bcast, int cout, int act,
                                   float* out, int ldo, void* stream);
