@@ -25,13 +25,12 @@
 // reads per row — the kernel is bound by the L1/shared data pipe (ncu: tensor-core operand wavefronts 46 % + LSU 34 %).
 // Range: |x| and |w| are clamped to the fp16 maximum 65504 (HITNet activations are O(1..1e3)); values below 6e-5 keep
 // an absolute error <= 6e-11.
-// Issue: pass A and pass B are issued by two elected threads in two warps (elect.sync, so that ptxas keeps the MMA
-// operands in uniform registers: 2-3 instructions per MMA instead of a 10-instruction elect/issue/loop waterfall); a
-// shared "rows issued" counter orders pass B of row g after pass A of rows g+1, g+2 (the only MMAs that share
-// accumulators with it), which makes the result bit-deterministic.
-// Stages: the fp32 rows (TMA -> pass A + split warps) and the fp16 x_lo rows (split warps -> pass B) live in two
-// separate rings with their own full/empty barriers, so a raw row is recycled as soon as pass A and the split have
-// read it and the TMA producer runs ahead of pass B.
+// Issue: two elected threads in two warps alternate staged rows (elect.sync, so that ptxas keeps the MMA operands in
+// uniform registers: 2-3 instructions per MMA instead of a 10-instruction elect/issue/loop waterfall); each issues pass
+// A then pass B of its row, and a shared "rows issued" counter hands the rows over in order, which fixes the
+// accumulation order (bit-deterministic results).
+// Stages: the fp32 rows (TMA -> split warps) and the fp16 operand rows (split warps -> tensor core) live in two rings
+// with their own full/empty barriers.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -252,7 +251,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
         }
         for (int b = 0; b < NH; ++b) {
             mbar_init(HBAR(LO, b), RG_SPLIT_GROUP);
-            mbar_init(HBAR(HEMPTY, b), 2);
+            mbar_init(HBAR(HEMPTY, b), 1);
         }
         a_issued_s = 0;
         for (int b = 0; b < RING; ++b) {
@@ -300,10 +299,11 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
             if (p.dbg) p.dbg[blockIdx.x * 8 + 0] = w0;
         }
     } else if (warp >= 13) {
-        // ===================== MMA issuers: warp 13 = pass A (raw rows), warp 14 = pass B (x_lo rows) =====================
-        // Two issuing threads (the single-thread issue rate was the first kernel's critical path).  Pass B of a row
-        // waits for its x_lo stage (split warps) and for pass A of the two following rows to be queued.
-        if (codd_elect_one()) {
+        // ===================== MMA issuers: warp 13 = even staged rows, warp 15 = odd ones (warp 14 idle) =====================
+        // Each thread issues pass A then pass B of its row; the rows are handed over in order through a shared counter, so
+        // the tensor queue sees A(g) B(g) A(g+1) B(g+1) ...: a fixed accumulation order (bit-deterministic results) and an
+        // operand stage that is released one row after it was written.
+        if (warp != 14 && codd_elect_one()) {
             // one pass over one staged row: for every (kx, k-step) the row is multiplied by the weight blocks of the
             // valid ky taps; consecutive ring slots are covered by one MMA (N = 2NP, 4NP or 6NP)
             long long w_full = 0, w_lo = 0, w_acce = 0, w_iss = 0;
@@ -425,49 +425,28 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
                     }
                 }
             };
-            if (warp != 14) {
-                Cursor ca;
-                ca.init(p);
-                if (warp == 15 && ca.valid(p)) ca.next(p);
-                while (ca.valid(p)) {
-                    const int hb = ca.g % NH;
-                    mbar_wait_t(HBAR(LO, hb), ((uint32_t)(ca.g / NH)) & 1u, w_full, timing);    // operand stage written
-                    tc_fence_after();
-                    issue(ca, std::integral_constant<int, 0>{});
-                    st_release_s32(a_issued, ca.g + 1);           // pass A of this row is in the tensor queue
-                    tc_commit(HBAR(HEMPTY, hb));                  // 1 of 2: pass A has read the operand stage
-                    ca.next(p);
-                    if (ca.valid(p)) ca.next(p);
+            Cursor ca;
+            ca.init(p);
+            if (warp == 15 && ca.valid(p)) ca.next(p);
+            while (ca.valid(p)) {
+                const int hb = ca.g % NH;
+                mbar_wait_t(HBAR(LO, hb), ((uint32_t)(ca.g / NH)) & 1u, w_full, timing);    // operand stage written
+                tc_fence_after();
+                issue(ca, std::integral_constant<int, 0>{});
+                if (!(p.diag & 1)) issue(ca, std::integral_constant<int, 1>{});
+                st_release_s32(a_issued, ca.g + 1);           // both passes of this row are in the tensor queue
+                tc_commit(HBAR(HEMPTY, hb));                  // operand stage free once they have executed
+                if (ca.t >= 2) {                              // output row y0 + t - 2 is complete
+                    const int orow = ca.orow0 + ca.t - 2;
+                    tc_commit(ABAR(ACCF, RING - 1 - (orow % RING)));
                 }
-                if (p.dbg && warp == 13) {
-                    p.dbg[blockIdx.x * 8 + 1] = w_full; p.dbg[blockIdx.x * 8 + 3] = w_acce;
-                    p.dbg[blockIdx.x * 8 + 4] = clock64() - t_start;
-                }
-            } else {
-                // Deterministic accumulation order: pass B of row g touches output rows g-2..g, pass A of row h touches
-                // h-2..h, so B(g) is only ambiguous against A(g+1), A(g+2) — it is issued after both are in the queue.
-                int gtotal = 0;
-                for (int item = blockIdx.x; item < p.nitems; item += gridDim.x)
-                    gtotal += min(p.seg, p.H - (item % p.nseg) * p.seg) + 2;
-                Cursor cb;
-                for (cb.init(p); cb.valid(p); cb.next(p)) {
-                    const int hb = cb.g % NH;
-                    const int ga = min(cb.g + 2, gtotal - 1);
-                    {
-                        const long long t0 = timing ? clock64() : 0;
-                        while (ld_acquire_s32(a_issued) <= ga) {}
-                        if (timing) w_iss += clock64() - t0;
-                    }
-                    mbar_wait_t(HBAR(LO, hb), ((uint32_t)(cb.g / NH)) & 1u, w_lo, timing);
-                    tc_fence_after();
-                    if (!(p.diag & 1)) issue(cb, std::integral_constant<int, 1>{});
-                    tc_commit(HBAR(HEMPTY, hb));                  // 2 of 2: pass B has read the operand stage
-                    if (cb.t >= 2) {                              // output row y0 + t - 2 is complete
-                        const int orow = cb.orow0 + cb.t - 2;
-                        tc_commit(ABAR(ACCF, RING - 1 - (orow % RING)));
-                    }
-                }
-                if (p.dbg) { p.dbg[blockIdx.x * 8 + 2] = w_lo; p.dbg[blockIdx.x * 8 + 5] = w_iss; }
+                ca.next(p);
+                if (ca.valid(p)) ca.next(p);
+            }
+            if (p.dbg && warp == 13) {
+                p.dbg[blockIdx.x * 8 + 1] = w_full; p.dbg[blockIdx.x * 8 + 3] = w_acce;
+                p.dbg[blockIdx.x * 8 + 4] = clock64() - t_start;
+                p.dbg[blockIdx.x * 8 + 2] = w_lo; p.dbg[blockIdx.x * 8 + 5] = w_iss;
             }
         }
     } else if (warp >= 8) {
