@@ -1,6 +1,3 @@
-timeout 100 python -m pytest tests/test_gpu_ops.py -m gpu -x -q -k "ring" 2>&1 | tail -3
-timeout 100 python tools/ring_check.py 2>&1 | tail -5
-timeout 60 python tools/conv_probe.py 2>&1 | grep "N="| sed 's/halo-tile.*ring/ring/'
-timeout 100 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_dec.json 2> gpurun_out/bench_dec.err; python -c "
-import json;d=json.loads(open('gpurun_out/bench_dec.json').read().strip().splitlines()[-1]);print(d['value'],d['ms_per_step'],d['e2e']['value']);print([(k['kernel'],k['ms']) for k in d['top_kernels']])"
-timeout 100 python -m pytest tests/test_gpu_hitnet.py -m gpu -x -q 2>&1 | tail -5
+timeout 400 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; tail -c 600 gpurun_out/bench_final.json
+timeout 200 python bench.py --no-cpu-baseline --dump-kernels gpurun_out/kernels_final.json --steps 10 --warmup 3 > /dev/null 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_bench_cmd.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/b.log 2>&1; tail -2 gpurun_out/b.log | cut -c1-200
