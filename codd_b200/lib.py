@@ -82,6 +82,10 @@ SIGNATURES = {
     "codd_subsample_nhwc": (c_int, [_FP, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _FP, c_int, c_void_p]),
     "codd_stage_images_u8": (c_int, [_FP, c_int, c_int, c_int, POINTER(c_float), POINTER(c_float), c_int, c_int, c_int, _FP,
                                      c_void_p]),
+    "codd_disp_metrics": (c_int, [_FP, ctypes.c_longlong, c_int, _FP, _FP, c_int, c_int, c_int, c_float, c_float, _FP, _FP,
+                                  c_void_p]),
+    "codd_temporal_metrics": (c_int, [_FP, _FP, _FP, ctypes.c_longlong, c_int, _FP, _FP, _FP, ctypes.c_longlong, c_int, _FP,
+                                      _FP, _FP, c_int, c_int, c_int, c_float, c_float, _FP, c_void_p]),
     "codd_nhwc_to_nchw": (c_int, [_FP, c_int, c_int, c_int, c_int, c_int, _FP, c_void_p]),
     "codd_nchw_to_nhwc": (c_int, [_FP, c_int, c_int, c_int, c_int, _FP, c_int, c_void_p]),
 }

@@ -1,0 +1,66 @@
+"""On-GPU evaluation state for sequence inference.
+
+Mirrors what ``ConsistentOnlineDynamicDepth.calc_metric`` / ``reset_inference_state`` keep in
+``inference_state`` (model/codd.py:400-517): per frame the EPE / 3-px meters, from the second frame on the temporal
+EPE meters and the flow-magnitude meter.  The reference calls ``.item()`` several times per frame (a host
+synchronisation each); here every frame adds one row of float64 sums on the device (two kernel launches) and
+``collect()`` reads them back once and applies the reference's AverageMeter semantics (mean over the frames that
+updated a meter, utils/running_stats.py).  The scene-flow meters (codd.py:519-575) are not ported yet.
+"""
+import numpy as np
+import torch
+
+from . import ops
+
+ROW = 16   # doubles per frame: [0:4] codd_disp_metrics, [4:13] codd_temporal_metrics
+
+
+class SequenceMetrics:
+    def __init__(self, disp_range, max_frames=4096, device="cuda"):
+        self.disp_range = (float(disp_range[0]), float(disp_range[1]))
+        self.acc = torch.zeros((max_frames, ROW), dtype=torch.float64, device=device)
+        self.frames = 0
+        self._prev = None   # (gt, pred, mask, flow) of the previous frame
+
+    def reset(self):
+        self.acc.zero_()
+        self.frames = 0
+        self._prev = None
+
+    def update(self, pred_disp, gt_disp, gt_flow=None, seg=None, gt_disp2=None):
+        """One frame (codd.py:435-517).  pred_disp: the network output [N,1,Hp,Wp] (padded is fine, it is cropped to
+        gt's size); gt_disp [N,1,H,W]; gt_flow [N,2,H,W] = this frame's ground-truth flow to the NEXT frame (kept for
+        the next call, as inference_state["gt_flow"][-2]); seg: optional semantic / occlusion mask (> 0 = keep)."""
+        if self.frames >= self.acc.shape[0]:
+            raise RuntimeError("SequenceMetrics: max_frames exceeded")
+        n, _, h, w = gt_disp.shape
+        row = self.acc[self.frames]
+        mask = torch.empty((n, 1, h, w), dtype=torch.uint8, device=gt_disp.device)
+        ops.disp_metrics(pred_disp, gt_disp, self.disp_range, row[0:4], seg=seg, mask_out=mask)
+        if self._prev is not None and self._prev[3] is not None:
+            p_gt, p_pred, p_mask, p_flow, p_gt2 = self._prev
+            ops.temporal_metrics(p_flow, gt_disp, pred_disp, p_gt, p_pred, p_mask, self.disp_range, row[4:13], seg=seg,
+                                 gt_disp2_prev=p_gt2, gt_pos_count=row[3:4])
+        self._prev = (gt_disp, pred_disp, mask, gt_flow, gt_disp2)
+        self.frames += 1
+
+    def collect(self):
+        """One device->host copy; returns the meters of utils/misc.py:62-86 that N3 covers."""
+        a = self.acc[: self.frames].cpu().numpy()
+        out = {}
+
+        def meter(name, num, den, gate):
+            vals = [num[i] / den[i] if den[i] else float("nan") for i in range(len(num)) if gate[i]]
+            out[name] = float(np.mean(vals)) if vals else 0.0
+
+        has = a[:, 0] > 0
+        meter("epe", a[:, 1], a[:, 0], has)
+        meter("th3", a[:, 2], a[:, 0], has)
+        t = a[:, 4:13]
+        upd = (t[:, 5] > 0) & (t[:, 6] > 0)          # mask_prev.any() and mask_curr.any() (codd.py:506)
+        meter("tepe", t[:, 1], t[:, 0], upd)
+        meter("tepe_rel", t[:, 2], t[:, 0], upd)
+        meter("th1_tepe_rel", t[:, 3], t[:, 0], upd)
+        meter("th3_tepe", t[:, 4], t[:, 0], upd)
+        meter("flow_mag", t[:, 7], t[:, 8], t[:, 8] > 0)
+        return out

@@ -777,3 +777,47 @@ def stage_images_u8(img, mean=IMG_NORM["mean"], std=IMG_NORM["std"], to_rgb=True
         img.data_ptr(), n, h, w, m, s, 1 if to_rgb else 0, hp, wp, out.data_ptr(), _stream()))
     _lib.check(rc, "codd_stage_images_u8")
     return out
+
+
+# ------------------------------------------------------------------------------------------
+# N3: on-GPU evaluation (codd.py:435-517).  Accumulator rows live on the device; nothing here synchronises.
+# ------------------------------------------------------------------------------------------
+def _plane_view(t, name):
+    """[N,1,H,W] fp32 CUDA tensor whose rows are contiguous (e.g. the [:h,:w] crop of a padded map)
+    -> (data_ptr, sample stride, row stride)."""
+    if t.dim() != 4 or t.shape[1] != 1 or (t.shape[3] > 1 and t.stride(3) != 1):
+        raise _lib.CoddError(f"{name}: expected an [N,1,H,W] tensor with contiguous rows, got {tuple(t.shape)} / {t.stride()}")
+    return t.data_ptr(), (t.stride(0) if t.shape[0] > 1 else t.shape[2] * t.stride(2)), t.stride(2)
+
+
+def disp_metrics(pred, gt, disp_range, acc, seg=None, mask_out=None):
+    """acc[0..3] += (#valid, sum |pred-gt|, #(|pred-gt| > 3), #(gt > 0)); mask_out (uint8 [N,1,H,W]) = validity."""
+    _require_cuda(pred, gt, seg)
+    n, _, h, w = gt.shape
+    gt = gt.contiguous()
+    seg = None if seg is None else seg.contiguous()
+    pp, pss, prs = _plane_view(pred[:, :, :h, :w], "pred")
+    rc = _run("disp_metrics", 4 * n * h * w * (2 + (seg is not None)) + n * h * w, lambda: _lib.load().codd_disp_metrics(
+        pp, pss, prs, gt.data_ptr(), None if seg is None else seg.data_ptr(), n, h, w, float(disp_range[0]),
+        float(disp_range[1]), None if mask_out is None else mask_out.data_ptr(), acc.data_ptr(), _stream()))
+    _lib.check(rc, "codd_disp_metrics")
+    return acc
+
+
+def temporal_metrics(flow_prev, gt, pred, gt_prev, pred_prev, mask_prev, disp_range, acc, seg=None, gt_disp2_prev=None,
+                     gt_pos_count=None):
+    """acc[0..8] += the temporal-EPE sums of one frame pair (see include/codd_b200.h)."""
+    _require_cuda(flow_prev, gt, pred, gt_prev, pred_prev, seg, gt_disp2_prev)
+    n, _, h, w = gt.shape
+    flow_prev, gt, gt_prev = flow_prev.contiguous(), gt.contiguous(), gt_prev.contiguous()
+    seg = None if seg is None else seg.contiguous()
+    g2 = None if gt_disp2_prev is None else gt_disp2_prev.contiguous()
+    pp, pss, prs = _plane_view(pred[:, :, :h, :w], "pred")
+    qp, qss, qrs = _plane_view(pred_prev[:, :, :h, :w], "pred_prev")
+    rc = _run("temporal_metrics", 4 * n * h * w * 8, lambda: _lib.load().codd_temporal_metrics(
+        flow_prev.data_ptr(), gt.data_ptr(), pp, pss, prs, None if seg is None else seg.data_ptr(), gt_prev.data_ptr(),
+        qp, qss, qrs, mask_prev.data_ptr(), None if g2 is None else g2.data_ptr(),
+        None if gt_pos_count is None else gt_pos_count.data_ptr(), n, h, w, float(disp_range[0]), float(disp_range[1]),
+        acc.data_ptr(), _stream()))
+    _lib.check(rc, "codd_temporal_metrics")
+    return acc

@@ -347,6 +347,32 @@ CODD_API int codd_nhwc_to_nchw(const float* in, int ldi, int n, int h, int w, in
 CODD_API int codd_nchw_to_nhwc(const float* in, int n, int c, int h, int w, float* out, int ldo,
                       void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * N3  on-GPU evaluation (reference: model/codd.py:435-517 calc_metric, utils/misc.py:12-36
+ * compute_valid_mask, utils/warp.py:69-92 flow_warp(mode="nearest", padding_mode="zeros"), utils/metric.py:9-54).
+ * Each call makes one pass over a frame and ADDS into a row of float64 accumulators on the device; the host takes the
+ * means once per sequence (no .item() per frame).  All tensors are dense [n,1,h,w] / [n,2,h,w] fp32 except pred /
+ * pred_prev, which may be views of the padded network output (sample / row strides in elements).  seg, mask_out,
+ * gt_disp2_prev may be NULL.
+ *   codd_disp_metrics:     acc[0] += #valid, [1] += sum |pred-gt|, [2] += #(|pred-gt| > 3), [3] += #(gt > 0);
+ *                          mask_out[n,h,w] (uint8) = (disp_lo < gt < disp_hi) & (seg > 0)            (codd.py:462-474)
+ *   codd_temporal_metrics: flow_prev = ground-truth flow of the previous frame; the current gt / pred / mask are
+ *                          sampled at p + flow(p) (nearest) and compared with the previous frame:
+ *                          acc[0] += #(mask_prev & mask_curr), [1] += sum abs_err, [2] += sum rel_err, [3] += #(rel > 1),
+ *                          [4] += #(abs > 3), [5] += #mask_prev, [6] += #mask_curr, [7] += sum |flow|, [8] += #pixels.
+ *                          gt_pos_count: device pointer to acc[3] of codd_disp_metrics for the same frame (0 -> the
+ *                          KITTI dummy-disparity mask of codd.py:486-490), or NULL.                  (codd.py:476-517)
+ * ------------------------------------------------------------------------------------------ */
+CODD_API int codd_disp_metrics(const float* pred, long long pred_sample_stride, int pred_row_stride, const float* gt,
+                               const float* seg, int n, int h, int w, float disp_lo, float disp_hi,
+                               unsigned char* mask_out, double* acc, void* stream);
+CODD_API int codd_temporal_metrics(const float* flow_prev, const float* gt, const float* pred,
+                                   long long pred_sample_stride, int pred_row_stride, const float* seg,
+                                   const float* gt_prev, const float* pred_prev, long long pprev_sample_stride,
+                                   int pprev_row_stride, const unsigned char* mask_prev, const float* gt_disp2_prev,
+                                   const double* gt_pos_count, int n, int h, int w, float disp_lo, float disp_hi, double* acc,
+                                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

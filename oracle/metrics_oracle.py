@@ -1,0 +1,109 @@
+"""CPU restatement of the reference's per-frame evaluation arithmetic.
+
+TEST INFRASTRUCTURE ONLY: imported by tests/ (and nothing on the product path).  numpy, float32
+arithmetic step by step where the reference computes in float32, float64 only for the final sums.
+
+Follows
+  utils/misc.py:12-36      compute_valid_mask
+  utils/warp.py:7-40,69-92 normalize_coords / meshgrid / flow_warp (mode="nearest", padding_mode="zeros";
+                           F.grid_sample with align_corners=True restated: unnormalise ((c+1)/2)*(size-1),
+                           nearbyint, zero outside the image)
+  utils/metric.py:9-54     epe_metric, t_epe_metric, thres_metric
+  model/codd.py:435-517    calc_metric: disparity block (:462-474) and temporal block (:476-515)
+Pinned against those functions imported from /root/reference in tests/test_metrics_oracle.py.
+The scene-flow block (codd.py:519-575) is not restated yet.
+"""
+import numpy as np
+
+BF_DEFAULT = np.float32(1050 * 0.2)   # utils/misc.py:7
+F32 = np.float32
+
+
+def valid_mask(gt_disp, disp_range, seg=None, flow_prev=None, disp_change=None):
+    """utils/misc.py:26-33.  gt_disp [N,1,H,W]; seg [N,1,H,W]; flow_prev [N,2,H,W] -> bool [N,1,H,W]."""
+    gt = np.asarray(gt_disp, F32)
+    m = (gt > F32(disp_range[0])) & (gt < F32(disp_range[1]))
+    if seg is not None:
+        m &= np.asarray(seg) > 0
+    if flow_prev is not None:
+        f = np.asarray(flow_prev, F32)
+        mag = np.sqrt((f[:, 0:1] * f[:, 0:1] + f[:, 1:2] * f[:, 1:2]).astype(F32)).astype(F32)
+        m &= mag < BF_DEFAULT
+    if disp_change is not None:
+        m &= np.abs(np.asarray(disp_change, F32)) < BF_DEFAULT
+    return m
+
+
+def _sample_index(base, flow, size):
+    """grid + flow -> normalize_coords -> grid_sample unnormalise -> nearbyint, all in float32."""
+    s = (base + flow).astype(F32)
+    n = (F32(2) * (s / F32(size - 1)).astype(F32)).astype(F32) - F32(1)          # warp.py:14-15
+    u = (((n + F32(1)).astype(F32) / F32(2)).astype(F32) * F32(size - 1)).astype(F32)
+    return np.rint(u)                                                           # round half to even
+
+
+def flow_warp_nearest(img, flow):
+    """utils/warp.py:69-92 with mode='nearest', padding_mode='zeros'.  img [N,C,H,W], flow [N,2,H,W]
+    -> warped [N,C,H,W] float32, valid [N,C,H,W] bool."""
+    img = np.asarray(img, F32)
+    flow = np.asarray(flow, F32)
+    n, c, h, w = img.shape
+    xs = np.arange(w, dtype=F32)[None, None, :]
+    ys = np.arange(h, dtype=F32)[None, :, None]
+    ix = _sample_index(np.broadcast_to(xs, (n, h, w)), flow[:, 0], w)
+    iy = _sample_index(np.broadcast_to(ys, (n, h, w)), flow[:, 1], h)
+    inb = (ix >= 0) & (ix <= w - 1) & (iy >= 0) & (iy <= h - 1)
+    xi = np.clip(ix, 0, w - 1).astype(np.int64)
+    yi = np.clip(iy, 0, h - 1).astype(np.int64)
+    out = np.zeros_like(img)
+    for b in range(n):
+        g = img[b][:, yi[b], xi[b]]
+        out[b] = np.where(inb[b][None], g, F32(0))
+    valid = np.broadcast_to(inb[:, None], img.shape).copy()
+    return out, valid
+
+
+def disp_metrics(pred, gt, mask):
+    """codd.py:462-474.  Returns dict(n, epe, th3); epe / th3 are None when no pixel is valid."""
+    pred, gt = np.asarray(pred, F32), np.asarray(gt, F32)
+    n = int(mask.sum())
+    if n == 0:
+        return dict(n=0, epe=None, th3=None)
+    e = np.abs((pred[mask] - gt[mask]).astype(F32))
+    return dict(n=n, epe=float(e.astype(np.float64).sum() / n), th3=float((e > F32(3.0)).sum() / n))
+
+
+def temporal_metrics(flow, gt, pred, seg, gt_prev, pred_prev, mask_prev, disp_range, gt_disp2_prev=None):
+    """codd.py:476-515 for one frame pair.  flow = ground-truth flow of the PREVIOUS frame [N,2,H,W]; gt / pred the
+    current frame [N,1,H,W]; *_prev the previous one; mask_prev the previous frame's disparity mask.
+    Returns dict(updated, tepe, tepe_rel, th1_tepe_rel, th3_tepe, n, flow_mag)."""
+    gt, pred = np.asarray(gt, F32), np.asarray(pred, F32)
+    flow = np.asarray(flow, F32)
+    if (gt > 0).any():
+        mask = valid_mask(gt, disp_range, seg=seg, flow_prev=flow)
+    else:   # KITTI: only one frame has disparity, dummy gt of BF/2 (codd.py:486-490)
+        mask = valid_mask(np.full_like(gt, BF_DEFAULT / F32(2.0)), disp_range, seg=seg, flow_prev=flow)
+    to_warp = np.concatenate([gt, pred, mask.astype(F32)], axis=1)
+    warped, valid = flow_warp_nearest(to_warp, flow)
+    w_gt, w_pred, w_mask = warped[:, 0:1], warped[:, 1:2], warped[:, 2:3]
+    # codd.py:499 takes valid.squeeze()[0]: with the batch of 1 the reference evaluates at, channel 0's mask
+    mask_curr = valid[:, 0:1] & (w_mask != 0) & mask
+    if gt_disp2_prev is not None:
+        w_gt = np.asarray(gt_disp2_prev, F32)
+        mask_curr = mask_curr & (w_gt > 0)
+    mag = np.sqrt((flow[:, 0] * flow[:, 0] + flow[:, 1] * flow[:, 1]).astype(F32)).astype(F32)
+    out = dict(updated=False, flow_mag=float(mag.astype(np.float64).mean()))
+    if mask_prev.any() and mask_curr.any():
+        d_est = (w_pred - np.asarray(pred_prev, F32)).astype(F32)
+        d_gt = (w_gt - np.asarray(gt_prev, F32)).astype(F32)
+        m = mask_prev & mask_curr
+        abs_err = np.abs((d_est - d_gt).astype(F32))[m]
+        rel = (abs_err / (np.abs(d_gt[m]) + F32(1e-3)).astype(F32)).astype(F32)
+        n = int(m.sum())
+        with np.errstate(invalid="ignore", divide="ignore"):
+            out.update(updated=True, n=n,
+                       tepe=float(abs_err.astype(np.float64).sum() / n) if n else float("nan"),
+                       tepe_rel=float(rel.astype(np.float64).sum() / n) if n else float("nan"),
+                       th1_tepe_rel=float((rel > F32(1.0)).sum() / n) if n else float("nan"),
+                       th3_tepe=float((abs_err > F32(3.0)).sum() / n) if n else float("nan"))
+    return out

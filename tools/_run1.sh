@@ -1,3 +1,3 @@
-timeout 400 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; tail -c 600 gpurun_out/bench_final.json
-timeout 200 python bench.py --no-cpu-baseline --dump-kernels gpurun_out/kernels_final.json --steps 10 --warmup 3 > /dev/null 2>&1
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_bench_cmd.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/b.log 2>&1; tail -2 gpurun_out/b.log | cut -c1-200
+timeout 120 python -m pytest tests/test_gpu_metrics.py -m gpu -x -q 2>&1 | tail -8
+RC=16 timeout 200 ncu --set full --import-source on --clock-control none -k regex:conv3x3_tc_ring -s 2 -c 1 -f -o gpurun_out/ring16_v12 python tools/_ring_one.py 2>&1 | tail -1
+RC=32 timeout 200 ncu --set full --import-source on --clock-control none -k regex:conv3x3_tc_ring -s 2 -c 1 -f -o gpurun_out/ring32_v12 python tools/_ring_one.py 2>&1 | tail -1
