@@ -1,3 +1,5 @@
-timeout 120 python -m pytest tests/test_gpu_metrics.py -m gpu -x -q 2>&1 | tail -8
-RC=16 timeout 200 ncu --set full --import-source on --clock-control none -k regex:conv3x3_tc_ring -s 2 -c 1 -f -o gpurun_out/ring16_v12 python tools/_ring_one.py 2>&1 | tail -1
-RC=32 timeout 200 ncu --set full --import-source on --clock-control none -k regex:conv3x3_tc_ring -s 2 -c 1 -f -o gpurun_out/ring32_v12 python tools/_ring_one.py 2>&1 | tail -1
+timeout 100 python -m pytest tests/test_gpu_ops.py -m gpu -x -q -k "ring" 2>&1 | tail -3
+timeout 100 python tools/ring_check.py 2>&1 | tail -5
+timeout 60 python tools/conv_probe.py 2>&1 | grep "N="| sed 's/halo-tile.*ring/ring/'
+timeout 100 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_dec.json 2> gpurun_out/bench_dec.err; python -c "
+import json;d=json.loads(open('gpurun_out/bench_dec.json').read().strip().splitlines()[-1]);print(d['value'],d['ms_per_step'],d['e2e']['value']);print([(k['kernel'],k['ms']) for k in d['top_kernels']])"
