@@ -1,3 +1,5 @@
+"""One rolling-ring conv launch for ncu captures: RC=16 -> 8x16x576x960, RC=32 -> 8x32x288x480.
+   ncu --set full --import-source on --clock-control none -k regex:conv3x3_tc_ring -s 2 -c 1 -o gpurun_out/ring16 python tools/ring_one.py"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
