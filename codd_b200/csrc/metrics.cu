@@ -135,6 +135,55 @@ __global__ void __launch_bounds__(MT_THREADS) temporal_metrics_kernel(
     block_accumulate<9>(v, acc);
 }
 
+// codd.py:519-575.  acc[0] += #valid, [1] += sum scene-flow EPE, [2] += sum optical-flow EPE, [3] += #(sf < 1), [4] += #(of < 1)
+// Ts: dense SE3 field (tx, ty, tz, qx, qy, qz, qw) with pixel strides (a [:h,:w] crop of the padded field is fine);
+// induced_flow of model/motion/raft3d/projective_ops.py:11-68 at depth = clip(BF / pred_prev, 0, BF).
+__global__ void __launch_bounds__(MT_THREADS) sceneflow_metrics_kernel(
+    const float* __restrict__ Ts, size_t ts_ss, size_t ts_rs, const float* __restrict__ pred_prev, size_t pp_ss, int pp_rs,
+    const float* __restrict__ intr, const float* __restrict__ flow, const float* __restrict__ disp_change,
+    const float* __restrict__ gt_prev, const float* __restrict__ seg, const unsigned char* __restrict__ flow_occ, int h,
+    int w, size_t total, float lo, float hi, double* __restrict__ acc) {
+    double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    const size_t hw = (size_t)h * w;
+    for (size_t i = (size_t)blockIdx.x * MT_THREADS + threadIdx.x; i < total; i += (size_t)gridDim.x * MT_THREADS) {
+        const size_t s = i / hw, q = i - s * hw;
+        const int y = (int)(q / w), x = (int)(q - (size_t)y * w);
+        const float fxg = __ldg(flow + (s * 2) * hw + q), fyg = __ldg(flow + (s * 2 + 1) * hw + q);
+        const float dc = __ldg(disp_change + i);
+        bool m = in_range(__ldg(gt_prev + i), lo, hi);
+        if (seg) m = m && (__ldg(seg + i) > 0.f);
+        m = m && (__fsqrt_rn(__fadd_rn(__fmul_rn(fxg, fxg), __fmul_rn(fyg, fyg))) < MT_BF) && (fabsf(dc) < MT_BF);
+        if (flow_occ) m = m && (flow_occ[i] == 0);
+        if (!m) continue;
+        const float fx = __ldg(intr + s * 4), fy = __ldg(intr + s * 4 + 1), cx = __ldg(intr + s * 4 + 2), cy = __ldg(intr + s * 4 + 3);
+        const float d = fminf(fmaxf(__fdiv_rn(MT_BF, __ldg(pred_prev + s * pp_ss + (size_t)y * pp_rs + x)), 0.f), MT_BF);
+        const float X0x = __fmul_rn(d, __fdiv_rn(__fsub_rn((float)x, cx), fx));
+        const float X0y = __fmul_rn(d, __fdiv_rn(__fsub_rn((float)y, cy), fy));
+        const float X0z = d;
+        const float* tp = Ts + s * ts_ss + (size_t)y * ts_rs + (size_t)x * 7;
+        const float tx = __ldg(tp), ty = __ldg(tp + 1), tz = __ldg(tp + 2);
+        const float qx = __ldg(tp + 3), qy = __ldg(tp + 4), qz = __ldg(tp + 5), qw = __ldg(tp + 6);
+        // X1 = X0 + qw * uv + qv x uv + t,  uv = 2 (qv x X0)
+        const float ux = 2.f * (qy * X0z - qz * X0y), uy = 2.f * (qz * X0x - qx * X0z), uz = 2.f * (qx * X0y - qy * X0x);
+        const float X1x = X0x + qw * ux + (qy * uz - qz * uy) + tx;
+        const float X1y = X0y + qw * uy + (qz * ux - qx * uz) + ty;
+        const float X1z = X0z + qw * uz + (qx * uy - qy * ux) + tz;
+        const float Z0 = X0z + 1e-5f, Z1 = X1z + 1e-5f;
+        const float ex = (fx * (X1x / Z1) + cx) - (fx * (X0x / Z0) + cx);
+        const float ey = (fy * (X1y / Z1) + cy) - (fy * (X0y / Z0) + cy);
+        const float ez = (1.f / Z1 - 1.f / Z0) * MT_BF;
+        const float dx = ex - fxg, dy = ey - fyg, dz = ez - dc;
+        const float of2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        const float sf = __fsqrt_rn(__fadd_rn(of2, __fmul_rn(dz, dz))), of = __fsqrt_rn(of2);
+        v[0] += 1.0;
+        v[1] += (double)sf;
+        v[2] += (double)of;
+        v[3] += sf < 1.0f ? 1.0 : 0.0;
+        v[4] += of < 1.0f ? 1.0 : 0.0;
+    }
+    block_accumulate<5>(v, acc);
+}
+
 int metrics_grid(size_t total) {
     const size_t blocks = (total + MT_THREADS - 1) / MT_THREADS;
     return (int)(blocks < 148 * 8 ? (blocks ? blocks : 1) : 148 * 8);
@@ -170,6 +219,24 @@ extern "C" int codd_temporal_metrics(const float* flow_prev, const float* gt, co
         flow_prev, gt, pred, (size_t)pred_sample_stride, pred_row_stride, seg, gt_prev, pred_prev,
         (size_t)pprev_sample_stride, pprev_row_stride, mask_prev, gt_disp2_prev, gt_pos_count, h, w, total, disp_lo, disp_hi,
         acc);
+    CODD_RETURN_IF_CUDA_ERROR();
+    return 0;
+}
+
+extern "C" int codd_sceneflow_metrics(const float* Ts, long long ts_sample_stride, long long ts_row_stride,
+                                      const float* pred_prev, long long pprev_sample_stride, int pprev_row_stride,
+                                      const float* intrinsics, const float* flow_prev, const float* gt_disp_change,
+                                      const float* gt_prev, const float* seg, const unsigned char* flow_occ, int n, int h,
+                                      int w, float disp_lo, float disp_hi, double* acc, void* stream) {
+    if (!Ts || !pred_prev || !intrinsics || !flow_prev || !gt_disp_change || !gt_prev || !acc || n <= 0 || h <= 0 || w <= 0)
+        return CODD_E_BADARG;
+    if (ts_row_stride < (long long)w * 7 || ts_sample_stride < (long long)h * ts_row_stride || pprev_row_stride < w ||
+        pprev_sample_stride < (long long)h * pprev_row_stride)
+        return CODD_E_SHAPE;
+    const size_t total = (size_t)n * h * w;
+    sceneflow_metrics_kernel<<<metrics_grid(total), MT_THREADS, 0, (cudaStream_t)stream>>>(
+        Ts, (size_t)ts_sample_stride, (size_t)ts_row_stride, pred_prev, (size_t)pprev_sample_stride, pprev_row_stride,
+        intrinsics, flow_prev, gt_disp_change, gt_prev, seg, flow_occ, h, w, total, disp_lo, disp_hi, acc);
     CODD_RETURN_IF_CUDA_ERROR();
     return 0;
 }

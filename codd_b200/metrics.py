@@ -5,14 +5,14 @@ Mirrors what ``ConsistentOnlineDynamicDepth.calc_metric`` / ``reset_inference_st
 EPE meters and the flow-magnitude meter.  The reference calls ``.item()`` several times per frame (a host
 synchronisation each); here every frame adds one row of float64 sums on the device (two kernel launches) and
 ``collect()`` reads them back once and applies the reference's AverageMeter semantics (mean over the frames that
-updated a meter, utils/running_stats.py).  The scene-flow meters (codd.py:519-575) are not ported yet.
+updated a meter, utils/running_stats.py) and the running sums of the scene-flow block (codd.py:519-575).
 """
 import numpy as np
 import torch
 
 from . import ops
 
-ROW = 16   # doubles per frame: [0:4] codd_disp_metrics, [4:13] codd_temporal_metrics
+ROW = 20   # doubles per frame: [0:4] codd_disp_metrics, [4:13] codd_temporal_metrics, [13:18] codd_sceneflow_metrics
 
 
 class SequenceMetrics:
@@ -27,10 +27,15 @@ class SequenceMetrics:
         self.frames = 0
         self._prev = None
 
-    def update(self, pred_disp, gt_disp, gt_flow=None, seg=None, gt_disp2=None):
+    def update(self, pred_disp, gt_disp, gt_flow=None, seg=None, gt_disp2=None, Ts=None, intrinsics=None,
+               gt_disp_change=None, gt_flow_occ_prev=None):
         """One frame (codd.py:435-517).  pred_disp: the network output [N,1,Hp,Wp] (padded is fine, it is cropped to
         gt's size); gt_disp [N,1,H,W]; gt_flow [N,2,H,W] = this frame's ground-truth flow to the NEXT frame (kept for
-        the next call, as inference_state["gt_flow"][-2]); seg: optional semantic / occlusion mask (> 0 = keep)."""
+        the next call, as inference_state["gt_flow"][-2]); seg: optional semantic / occlusion mask (> 0 = keep).
+        Motion meters (codd.py:519-575), from the second frame on: Ts = the SE3 field [N,H',W',7] estimated between the
+        previous and this frame, intrinsics [N,4], gt_disp_change [N,1,H,W] = the disparity change of the previous
+        frame's pixels (the reference's gt_disp_change[-2], or [-1] when it was derived from flow, in which case
+        gt_flow_occ_prev = gt_flow_occ[-2] removes the occluded pixels)."""
         if self.frames >= self.acc.shape[0]:
             raise RuntimeError("SequenceMetrics: max_frames exceeded")
         n, _, h, w = gt_disp.shape
@@ -41,6 +46,9 @@ class SequenceMetrics:
             p_gt, p_pred, p_mask, p_flow, p_gt2 = self._prev
             ops.temporal_metrics(p_flow, gt_disp, pred_disp, p_gt, p_pred, p_mask, self.disp_range, row[4:13], seg=seg,
                                  gt_disp2_prev=p_gt2, gt_pos_count=row[3:4])
+            if Ts is not None and gt_disp_change is not None:
+                ops.sceneflow_metrics(Ts, p_pred, intrinsics, p_flow, gt_disp_change, p_gt, self.disp_range, row[13:18],
+                                      seg=seg, flow_occ=gt_flow_occ_prev)
         self._prev = (gt_disp, pred_disp, mask, gt_flow, gt_disp2)
         self.frames += 1
 
@@ -63,4 +71,7 @@ class SequenceMetrics:
         meter("th1_tepe_rel", t[:, 3], t[:, 0], upd)
         meter("th3_tepe", t[:, 4], t[:, 0], upd)
         meter("flow_mag", t[:, 7], t[:, 8], t[:, 8] > 0)
+        sf = a[:, 13:18].sum(0)                       # running sums over the sequence (codd.py:567-575, misc.py:76-77)
+        out.update(count=float(sf[0]), epe2d_scene_flow=float(sf[1]), epe2d_optical_flow=float(sf[2]),
+                   **{"1px_scene_flow": float(sf[3]), "1px_optical_flow": float(sf[4])})
         return out

@@ -821,3 +821,26 @@ def temporal_metrics(flow_prev, gt, pred, gt_prev, pred_prev, mask_prev, disp_ra
         acc.data_ptr(), _stream()))
     _lib.check(rc, "codd_temporal_metrics")
     return acc
+
+
+def sceneflow_metrics(Ts, pred_prev, intrinsics, flow_prev, gt_disp_change, gt_prev, disp_range, acc, seg=None,
+                      flow_occ=None):
+    """acc[0..4] += (#valid, sum scene-flow EPE, sum optical-flow EPE, #(sf < 1), #(of < 1)) of one frame pair
+    (codd.py:519-575).  Ts: [N,H',W',7] dense SE3 field (cropped to gt's size here); intrinsics [N,4] CUDA."""
+    _require_cuda(Ts, pred_prev, intrinsics, flow_prev, gt_disp_change, gt_prev, seg)
+    n, _, h, w = gt_prev.shape
+    if Ts.dim() != 4 or Ts.shape[-1] != 7 or Ts.stride(3) != 1 or Ts.stride(2) != 7:
+        raise _lib.CoddError("sceneflow_metrics: Ts must be [N,H,W,7] with contiguous pixels")
+    flow_prev, gt_disp_change, gt_prev = flow_prev.contiguous(), gt_disp_change.contiguous(), gt_prev.contiguous()
+    intrinsics = intrinsics.contiguous()
+    seg = None if seg is None else seg.contiguous()
+    occ = None if flow_occ is None else flow_occ.to(torch.uint8).contiguous()
+    qp, qss, qrs = _plane_view(pred_prev[:, :, :h, :w], "pred_prev")
+    tss = Ts.stride(0) if Ts.shape[0] > 1 else Ts.shape[1] * Ts.stride(1)
+    rc = _run("sceneflow_metrics", 4 * n * h * w * 14, lambda: _lib.load().codd_sceneflow_metrics(
+        Ts.data_ptr(), tss, Ts.stride(1), qp, qss, qrs, intrinsics.data_ptr(), flow_prev.data_ptr(),
+        gt_disp_change.data_ptr(), gt_prev.data_ptr(), None if seg is None else seg.data_ptr(),
+        None if occ is None else occ.data_ptr(), n, h, w, float(disp_range[0]), float(disp_range[1]), acc.data_ptr(),
+        _stream()))
+    _lib.check(rc, "codd_sceneflow_metrics")
+    return acc

@@ -362,6 +362,11 @@ CODD_API int codd_nchw_to_nhwc(const float* in, int n, int c, int h, int w, floa
  *                          [4] += #(abs > 3), [5] += #mask_prev, [6] += #mask_curr, [7] += sum |flow|, [8] += #pixels.
  *                          gt_pos_count: device pointer to acc[3] of codd_disp_metrics for the same frame (0 -> the
  *                          KITTI dummy-disparity mask of codd.py:486-490), or NULL.                  (codd.py:476-517)
+ *   codd_sceneflow_metrics: the motion block (codd.py:519-575): 2-D / 3-D flow induced by the dense SE3 field Ts
+ *                          [n,h,w,7] = (t, q) at depth clip(BF / pred_prev, 0, BF) (projective_ops.py:11-68) against
+ *                          (gt flow, gt disparity change), under compute_valid_mask(gt_prev, flow, disp_change, seg) minus
+ *                          flow_occ: acc[0] += #valid, [1] += sum scene-flow EPE, [2] += sum optical-flow EPE,
+ *                          [3] += #(sf < 1 px), [4] += #(of < 1 px).  Ts strides in floats (a [:h,:w] crop is fine).
  * ------------------------------------------------------------------------------------------ */
 CODD_API int codd_disp_metrics(const float* pred, long long pred_sample_stride, int pred_row_stride, const float* gt,
                                const float* seg, int n, int h, int w, float disp_lo, float disp_hi,
@@ -372,6 +377,11 @@ CODD_API int codd_temporal_metrics(const float* flow_prev, const float* gt, cons
                                    int pprev_row_stride, const unsigned char* mask_prev, const float* gt_disp2_prev,
                                    const double* gt_pos_count, int n, int h, int w, float disp_lo, float disp_hi, double* acc,
                                    void* stream);
+CODD_API int codd_sceneflow_metrics(const float* Ts, long long ts_sample_stride, long long ts_row_stride,
+                                    const float* pred_prev, long long pprev_sample_stride, int pprev_row_stride,
+                                    const float* intrinsics, const float* flow_prev, const float* gt_disp_change,
+                                    const float* gt_prev, const float* seg, const unsigned char* flow_occ, int n, int h,
+                                    int w, float disp_lo, float disp_hi, double* acc, void* stream);
 
 #ifdef __cplusplus
 }

@@ -10,8 +10,9 @@ Follows
                            nearbyint, zero outside the image)
   utils/metric.py:9-54     epe_metric, t_epe_metric, thres_metric
   model/codd.py:435-517    calc_metric: disparity block (:462-474) and temporal block (:476-515)
-Pinned against those functions imported from /root/reference in tests/test_metrics_oracle.py.
-The scene-flow block (codd.py:519-575) is not restated yet.
+  model/codd.py:519-575    the scene-flow block (induced_flow of projective_ops.py:11-68; see the note further down)
+Pinned against those functions imported from /root/reference in tests/test_metrics_oracle.py (disparity and
+temporal blocks); the scene-flow block's `Ts * X0` is lietorch's and therefore unpinned.
 """
 import numpy as np
 
@@ -107,3 +108,50 @@ def temporal_metrics(flow, gt, pred, seg, gt_prev, pred_prev, mask_prev, disp_ra
                        th1_tepe_rel=float((rel > F32(1.0)).sum() / n) if n else float("nan"),
                        th3_tepe=float((abs_err > F32(3.0)).sum() / n) if n else float("nan"))
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# scene-flow block (codd.py:519-575): induced_flow (model/motion/raft3d/projective_ops.py:11-68) restated for a dense
+# SE3 field given as (tx, ty, tz, qx, qy, qz, qw).  The lietorch action `Ts * X0` is restated as the quaternion
+# rotation + translation (lietorch is absent from this container: that one line is unpinned; the projective ops are
+# the ones pinned in oracle/motion_oracle.py).
+# ----------------------------------------------------------------------------------------------
+P_EPS = F32(1e-5)   # projective_ops.py:8
+
+
+def induced_flow(Ts, depth, intr):
+    """Ts [N,H,W,7], depth [N,H,W], intr [N,4] -> flow2d [N,H,W,3] = project(T*X0) - project(X0) (float32)."""
+    Ts, depth, intr = np.asarray(Ts, F32), np.asarray(depth, F32), np.asarray(intr, F32)
+    n, h, w = depth.shape
+    fx, fy, cx, cy = [intr[:, i][:, None, None] for i in range(4)]
+    x = np.arange(w, dtype=F32)[None, None, :]
+    y = np.arange(h, dtype=F32)[None, :, None]
+    X0 = np.stack([depth * ((x - cx) / fx), depth * ((y - cy) / fy), depth], -1).astype(F32)
+    qv, qw, t = Ts[..., 3:6], Ts[..., 6:7], Ts[..., 0:3]
+    uv = (F32(2) * np.cross(qv, X0)).astype(F32)
+    X1 = (X0 + qw * uv + np.cross(qv, uv) + t).astype(F32)
+
+    def project(X):
+        Z = X[..., 2] + P_EPS
+        return np.stack([fx * (X[..., 0] / Z) + cx, fy * (X[..., 1] / Z) + cy, F32(1) / Z], -1).astype(F32)
+
+    return (project(X1) - project(X0)).astype(F32)
+
+
+def sceneflow_metrics(Ts, pred_prev, intr, flow, gt_disp_change, gt_disp_prev, disp_range, seg=None, flow_occ=None):
+    """codd.py:519-575 for one frame pair.  Returns dict(n, sum_sf, sum_of, n1_sf, n1_of)."""
+    flow = np.asarray(flow, F32)
+    mask = valid_mask(gt_disp_prev, disp_range, seg=seg, flow_prev=flow, disp_change=gt_disp_change)
+    if flow_occ is not None:
+        mask = mask & ~np.asarray(flow_occ, bool)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        depth1 = np.clip((BF_DEFAULT / np.asarray(pred_prev, F32)).astype(F32), F32(0), BF_DEFAULT)[:, 0]
+    est = induced_flow(Ts, depth1, intr)
+    est[..., 2] = est[..., 2] * BF_DEFAULT
+    gt3 = np.concatenate([flow.transpose(0, 2, 3, 1), np.asarray(gt_disp_change, F32).transpose(0, 2, 3, 1)], -1)
+    d2 = ((est - gt3).astype(F32) ** 2).astype(F32)
+    sf = np.sqrt(d2.sum(-1, dtype=F32))
+    of = np.sqrt(d2[..., :2].sum(-1, dtype=F32))
+    m = mask[:, 0]
+    return dict(n=int(m.sum()), sum_sf=float(sf[m].astype(np.float64).sum()), sum_of=float(of[m].astype(np.float64).sum()),
+                n1_sf=int((sf[m] < F32(1.0)).sum()), n1_of=int((of[m] < F32(1.0)).sum()))

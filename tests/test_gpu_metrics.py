@@ -86,3 +86,63 @@ def test_sequence_metrics_matches_per_frame_oracle(ops):
     got = sm.collect()
     for k, v in exp.items():
         assert got[k] == pytest.approx(float(np.mean(v)), rel=1e-10), k
+
+
+def make_motion_case(seed, n, h, w):
+    g = np.random.default_rng(seed)
+    q = g.normal(0, 0.03, (n, h + 5, w + 11, 4)).astype(np.float32)
+    q[..., 3] += 1.0
+    q /= np.linalg.norm(q, axis=-1, keepdims=True)
+    Ts = np.concatenate([g.normal(0, 0.05, (n, h + 5, w + 11, 3)).astype(np.float32), q], -1)
+    pred_prev = g.uniform(-2, 120, (n, 1, h, w)).astype(np.float32)
+    pred_prev[g.random(pred_prev.shape) < 0.05] = 0.0
+    intr = np.tile(np.array([[450.0, 460.0, w / 2.0, h / 2.0]], np.float32), (n, 1))
+    flow = g.normal(0, 2, (n, 2, h, w)).astype(np.float32)
+    flow[g.random(flow.shape) < 0.02] = 300.0
+    dc = g.normal(0, 1.0, (n, 1, h, w)).astype(np.float32)
+    dc[g.random(dc.shape) < 0.05] = 210.0                      # BF_DEFAULT marks invalid disparity change
+    gt_prev = g.uniform(-3, 220, (n, 1, h, w)).astype(np.float32)
+    seg = (g.random((n, 1, h, w)) > 0.1).astype(np.float32)
+    occ = g.random((n, 1, h, w)) < 0.1
+    return dict(Ts=Ts, pred_prev=pred_prev, intr=intr, flow=flow, dc=dc, gt_prev=gt_prev, seg=seg, occ=occ)
+
+
+@pytest.mark.parametrize("seed,n,h,w,use_occ", [(0, 1, 24, 40, True), (1, 2, 33, 57, False)])
+def test_sceneflow_metrics_vs_oracle(ops, seed, n, h, w, use_occ):
+    c = make_motion_case(seed, n, h, w)
+    d = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in c.items()}
+    acc = torch.zeros(5, dtype=torch.float64, device="cuda")
+    ops.sceneflow_metrics(d["Ts"][:, :h, :w], d["pred_prev"], d["intr"], d["flow"], d["dc"], d["gt_prev"], RANGE, acc,
+                          seg=d["seg"], flow_occ=d["occ"] if use_occ else None)
+    a = acc.cpu().numpy()
+    o = M.sceneflow_metrics(c["Ts"][:, :h, :w], c["pred_prev"], c["intr"], c["flow"], c["dc"], c["gt_prev"], RANGE,
+                            seg=c["seg"], flow_occ=c["occ"] if use_occ else None)
+    assert a[0] == o["n"] and o["n"] > 0                                      # the mask is exact
+    assert a[1] == pytest.approx(o["sum_sf"], rel=1e-4) and a[2] == pytest.approx(o["sum_of"], rel=1e-4)
+    assert abs(a[3] - o["n1_sf"]) <= 2 and abs(a[4] - o["n1_of"]) <= 2        # fp32 contraction at the 1-px boundary
+
+
+def test_sequence_metrics_motion_block(ops):
+    """SequenceMetrics.update(..., Ts=, intrinsics=, gt_disp_change=) accumulates the running sums of codd.py:567-575."""
+    from codd_b200.metrics import SequenceMetrics
+    h, w = 31, 45
+    frames = [_cases.make_case(40 + i, n=1, h=h, w=w) for i in range(3)]
+    motions = [make_motion_case(50 + i, 1, h, w) for i in range(3)]
+    sm = SequenceMetrics(RANGE, max_frames=8)
+    exp = np.zeros(5)
+    prev = None
+    for f, mo in zip(frames, motions):
+        d = dev(f)
+        md = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in mo.items()}
+        sm.update(d["pred"], d["gt"], gt_flow=d["flow"], seg=d["seg"], Ts=md["Ts"][:, :h, :w], intrinsics=md["intr"],
+                  gt_disp_change=md["dc"], gt_flow_occ_prev=md["occ"])
+        if prev is not None:
+            o = M.sceneflow_metrics(mo["Ts"][:, :h, :w], prev["pred"], mo["intr"], prev["flow"], mo["dc"], prev["gt"], RANGE,
+                                    seg=f["seg"], flow_occ=mo["occ"])
+            exp += np.array([o["n"], o["sum_sf"], o["sum_of"], o["n1_sf"], o["n1_of"]], np.float64)
+        prev = dict(pred=f["pred"], gt=f["gt"], flow=f["flow"])
+    got = sm.collect()
+    assert got["count"] == exp[0] and exp[0] > 0
+    assert got["epe2d_scene_flow"] == pytest.approx(exp[1], rel=1e-4)
+    assert got["epe2d_optical_flow"] == pytest.approx(exp[2], rel=1e-4)
+    assert abs(got["1px_scene_flow"] - exp[3]) <= 3 and abs(got["1px_optical_flow"] - exp[4]) <= 3
