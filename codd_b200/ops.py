@@ -191,11 +191,13 @@ def pack_conv_weight_ring(w):
     return torch.cat([pa.reshape(-1), pb.reshape(-1)]).contiguous().view(torch.float32)
 
 
-def conv3x3_tc_ring(x, wring, bias, cout, act=ACT_NONE, residual=None, res_bcast=False):
-    """3x3 s1 p1 conv on the tensor cores, rolling-ring kernel (3 fp16 products, fp32 accumulation).  ``wring`` from pack_conv_weight_ring."""
-    _require_cuda(x, wring, bias, residual)
+def conv3x3_tc_ring(x, wring, bias, cout, act=ACT_NONE, residual=None, res_bcast=False, out=None):
+    """3x3 s1 p1 conv on the tensor cores, rolling-ring kernel (3 fp16 products, fp32 accumulation).  ``wring`` from
+    pack_conv_weight_ring; ``out``: optional NHWC-backed destination (e.g. a channel slice of a wider buffer)."""
+    _require_cuda(x, wring, bias, residual, out)
     n, cin, h, w = x.shape
-    out = empty_nhwc(n, cout, h, w, x.device)
+    if out is None:
+        out = empty_nhwc(n, cout, h, w, x.device)
     nbytes = 4 * (n * h * w * (cin + cout) + wring.numel()
                   + (0 if residual is None else n * h * w * (1 if res_bcast else cout)))
     rc = _run(f"conv3x3ring_cin{cin}_cout{cout}", nbytes, lambda: _lib.load().codd_conv3x3_tc_ring(

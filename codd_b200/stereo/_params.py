@@ -32,6 +32,16 @@ def run_conv(pw, conv, x, act, x2=None, residual=None, res_bcast=False, head=Non
         wp, b = pw.conv_head(conv, 1)
         return ops.conv2d(x, wp, b, 1, k, st, pd, dl, act, residual=residual, res_bcast=res_bcast)
     big = x.shape[2] * x.shape[3] >= 4096
+    if (USE_TC and USE_RING and big and cout == 34 and cin == 32 and x2 is None and residual is None and dl == 1
+            and act != ops.ACT_RELU_CH0 and ops.tc_eligible(cin, 32, k, st, pd, dl, x2)):
+        # TileUpdate.lastconv (32 -> 34, propagation.py:190-199): the first 32 filters run on the tensor cores, the
+        # last two as a direct convolution, both into one buffer with a 16-byte aligned pixel stride of 36 floats
+        out = ops.empty_nhwc(x.shape[0], 34, x.shape[2], x.shape[3], x.device, 36)
+        ws, b = pw.conv_ring(conv, 32)
+        ops.conv3x3_tc_ring(x, ws, b, 32, act, out=out[:, :32])
+        wp, b2 = pw.conv_range(conv, 32, 34)
+        ops.conv2d(x, wp, b2, 2, k, st, pd, dl, act, out=out[:, 32:34])
+        return out
     if USE_TC and USE_RING and big and dl == 1 and ops.tc_eligible(cin, cout, k, st, pd, dl, x2):
         ws, b = pw.conv_ring(conv, head)
         return ops.conv3x3_tc_ring(x, ws, b, cout, act, residual=residual, res_bcast=res_bcast)
@@ -70,6 +80,18 @@ class PackedWeights:
         hit = self._cache.get(key)
         if hit is None or hit[0] != tag:
             hit = (tag, ops.pack_conv_weight(w[:n]), None if b is None else b.detach()[:n].float().contiguous())
+            self._cache[key] = hit
+        return hit[1], hit[2]
+
+    def conv_range(self, conv, c0, c1):
+        """Packed direct-conv weight / bias of output channels [c0, c1)."""
+        w = conv.weight
+        b = conv.bias
+        key = (id(conv), "range", c0, c1)
+        tag = (w.data_ptr(), w._version, w.device, None if b is None else (b.data_ptr(), b._version))
+        hit = self._cache.get(key)
+        if hit is None or hit[0] != tag:
+            hit = (tag, ops.pack_conv_weight(w[c0:c1]), None if b is None else b.detach()[c0:c1].float().contiguous())
             self._cache[key] = hit
         return hit[1], hit[2]
 
