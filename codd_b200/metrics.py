@@ -52,26 +52,58 @@ class SequenceMetrics:
         self._prev = (gt_disp, pred_disp, mask, gt_flow, gt_disp2)
         self.frames += 1
 
-    def collect(self):
-        """One device->host copy; returns the meters of utils/misc.py:62-86 that N3 covers."""
-        a = self.acc[: self.frames].cpu().numpy()
-        out = {}
+    def rows(self):
+        """The per-frame accumulator rows of this rank as a CPU float64 tensor [frames, ROW] (one D2H copy)."""
+        return self.acc[: self.frames].cpu()
 
-        def meter(name, num, den, gate):
-            vals = [num[i] / den[i] if den[i] else float("nan") for i in range(len(num)) if gate[i]]
-            out[name] = float(np.mean(vals)) if vals else 0.0
+    def collect(self, all_ranks=False):
+        """One device->host copy; returns the meters of utils/misc.py:62-86.  all_ranks=True: the rows of every rank
+        are gathered first (the role of apis/inference.py's collect_results after multi_gpu_inference), so every rank
+        returns the statistics of the whole dataset."""
+        rows = self.rows()
+        if all_ranks:
+            rows = gather_rows(rows)
+        return summarise(rows.numpy())
 
-        has = a[:, 0] > 0
-        meter("epe", a[:, 1], a[:, 0], has)
-        meter("th3", a[:, 2], a[:, 0], has)
-        t = a[:, 4:13]
-        upd = (t[:, 5] > 0) & (t[:, 6] > 0)          # mask_prev.any() and mask_curr.any() (codd.py:506)
-        meter("tepe", t[:, 1], t[:, 0], upd)
-        meter("tepe_rel", t[:, 2], t[:, 0], upd)
-        meter("th1_tepe_rel", t[:, 3], t[:, 0], upd)
-        meter("th3_tepe", t[:, 4], t[:, 0], upd)
-        meter("flow_mag", t[:, 7], t[:, 8], t[:, 8] > 0)
-        sf = a[:, 13:18].sum(0)                       # running sums over the sequence (codd.py:567-575, misc.py:76-77)
-        out.update(count=float(sf[0]), epe2d_scene_flow=float(sf[1]), epe2d_optical_flow=float(sf[2]),
-                   **{"1px_scene_flow": float(sf[3]), "1px_optical_flow": float(sf[4])})
-        return out
+
+def gather_rows(rows):
+    """All-gather of per-frame accumulator rows [frames_r, ROW] over the default process group (ranks may hold
+    different numbers of frames).  Works on NCCL (rows are moved to the current CUDA device) and gloo."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return rows
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    world = dist.get_world_size()
+    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(counts, torch.tensor([rows.shape[0]], dtype=torch.int64, device=dev))
+    cap = max(int(c.item()) for c in counts)
+    pad = torch.zeros((cap, rows.shape[1]), dtype=torch.float64, device=dev)
+    pad[: rows.shape[0]] = rows.to(dev)
+    out = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad)
+    return torch.cat([o[: int(c.item())].cpu() for o, c in zip(out, counts)], 0)
+
+
+def summarise(a):
+    """Accumulator rows [frames, ROW] (numpy float64) -> the reference's meters (AverageMeter = mean over the frames
+    that updated it, utils/running_stats.py; scene-flow entries are running sums, codd.py:567-575)."""
+    out = {}
+
+    def meter(name, num, den, gate):
+        vals = [num[i] / den[i] if den[i] else float("nan") for i in range(len(num)) if gate[i]]
+        out[name] = float(np.mean(vals)) if vals else 0.0
+
+    has = a[:, 0] > 0
+    meter("epe", a[:, 1], a[:, 0], has)
+    meter("th3", a[:, 2], a[:, 0], has)
+    t = a[:, 4:13]
+    upd = (t[:, 5] > 0) & (t[:, 6] > 0)              # mask_prev.any() and mask_curr.any() (codd.py:506)
+    meter("tepe", t[:, 1], t[:, 0], upd)
+    meter("tepe_rel", t[:, 2], t[:, 0], upd)
+    meter("th1_tepe_rel", t[:, 3], t[:, 0], upd)
+    meter("th3_tepe", t[:, 4], t[:, 0], upd)
+    meter("flow_mag", t[:, 7], t[:, 8], t[:, 8] > 0)
+    sf = a[:, 13:18].sum(0)                           # running sums over the sequence (codd.py:567-575, misc.py:76-77)
+    out.update(count=float(sf[0]), epe2d_scene_flow=float(sf[1]), epe2d_optical_flow=float(sf[2]),
+               **{"1px_scene_flow": float(sf[3]), "1px_optical_flow": float(sf[4])})
+    return out

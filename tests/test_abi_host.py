@@ -129,3 +129,23 @@ def test_full_codd_config_builds_reference_parameter_tree():
     n_fnet = sum(v.numel() for k, v in sd.items() if k.startswith("motion.raft3d.fnet."))
     assert abs(n_update / 1e6 - 3.47) < 0.01 and abs(n_fnet / 1e6 - 1.05) < 0.01
     assert m.eval() is None and not m.motion.training
+
+
+def test_ring_weight_packing_reconstructs_weights():
+    """ops.pack_conv_weight_ring (host side of codd_conv3x3_tc_ring): pass A rows per ky = [fp16(w) | fp16(2^10 (w - fp16(w)))],
+    pass B = [0 | fp16(w)]; hi + lo / 1024 reproduces w to 2^-22 relative, padding rows / columns are zero."""
+    import torch
+    from codd_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    for cout, cin in [(16, 16), (24, 24), (32, 32), (1, 16), (16, 32)]:
+        w = torch.randn(cout, cin, 3, 3, generator=g) * 0.3
+        buf = ops.pack_conv_weight_ring(w)
+        kc = 16 if cin <= 16 else 32
+        npad = 16 if cout <= 16 else 32
+        h = buf.view(torch.float16).view(2, 3, 3, 2, npad, kc).float()      # [pass][kx][ky][hi|lo][cout][cin]
+        pa, pb = h[0], h[1]
+        rec = (pa[:, :, 0] + pa[:, :, 1] / 1024.0)[:, :, :cout, :cin]       # [kx][ky][cout][cin]
+        ref = w.permute(3, 2, 0, 1)
+        assert torch.allclose(rec, ref, rtol=0, atol=float(ref.abs().max()) * 2.0 ** -21)
+        assert torch.equal(pb[:, :, 1], pa[:, :, 0]) and not pb[:, :, 0].any()
+        assert not pa[:, :, :, cout:].any() and not pa[:, :, :, :, cin:].any()

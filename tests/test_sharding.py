@@ -49,3 +49,34 @@ def test_world_size_two_gloo():
     assert all(r[1] for r in res), "weights differ after broadcast"
     assert res[0][2] == [0, 2, 4, 6, 8] and res[1][2] == [1, 3, 5, 7, 9]
     assert res[0][3] == res[1][3] == 6.0
+
+
+def _metrics_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import numpy as np
+    from codd_b200.metrics import ROW, gather_rows, summarise
+    g = np.random.default_rng(7)
+    rows_all = g.uniform(1, 50, (7, ROW))
+    rows_all[3, 0] = 0.0                                  # a frame without valid pixels does not update the EPE meter
+    mine = torch.from_numpy(rows_all[rank::world].copy())  # ranks hold different numbers of frames (4 and 3)
+    got = summarise(gather_rows(mine).numpy())
+    ref = summarise(np.concatenate([rows_all[r::world] for r in range(world)], 0))
+    q.put((rank, got == ref, got["epe"]))
+    dist.destroy_process_group()
+
+
+def test_metric_rows_gathered_over_ranks():
+    """N2/N3 on several GPUs: every rank evaluates its own sequences, the accumulator rows are all-gathered once and
+    every rank reports the statistics of the whole dataset (apis/inference.py collect_results)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_metrics_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] for r in res) and res[0][2] == res[1][2] > 0
