@@ -335,15 +335,23 @@ def run_b200(args):
         # ---------------- the same through the sequence driver: staging + stereo forward + crop replayed
         # from one CUDA graph per serving slot, uint8 frames in pinned host memory, results in pinned host memory
         from codd_b200.runner import StereoSequenceRunner
-        runner = StereoSequenceRunner(model, device=dev, use_graph=not args.no_graph, n_streams=2)
-        for _ in runner.infer_batches([(l8_h, r8_h)] * 2):
-            pass
+        e2e_graph_err = None
+        try:
+            runner = StereoSequenceRunner(model, device=dev, use_graph=not args.no_graph, n_streams=2)
+            for _ in runner.infer_batches([(l8_h, r8_h)] * 2):
+                pass
+        except Exception as exc:      # an auxiliary leg must not take the headline numbers down with it
+            e2e_graph_err = f"{type(exc).__name__}: {exc}"
         barrier()
         e0.record()
-        n_out = sum(o.shape[0] for o in runner.infer_batches([(l8_h, r8_h)] * e2e_steps))
+        if e2e_graph_err is None:
+            try:
+                n_out = sum(o.shape[0] for o in runner.infer_batches([(l8_h, r8_h)] * e2e_steps))
+                assert n_out == B * e2e_steps
+            except Exception as exc:
+                e2e_graph_err = f"{type(exc).__name__}: {exc}"
         e1.record()
         barrier()
-        assert n_out == B * e2e_steps
         e2e_graph_ms = reduce_max_ms(e0.elapsed_time(e1), dev)
 
         # ---------------- instrumented pass: per-launch events -> dominant kernel + K1/K4 numbers
@@ -407,7 +415,8 @@ def run_b200(args):
                    "h2d_bytes_per_step": h2d_u8, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                    "what": "same as e2e, but uint8 HWC frames cross PCIe and codd_stage_images_u8 does the reference's "
                            "Normalize + reflect Pad(64) + HWC->CHW (datasets/transforms.py) on the GPU"},
-        "e2e_graph": {"value": round(e2e_steps * B * world / (e2e_graph_ms * 1e-3), 3), "unit": UNIT,
+        "e2e_graph": {"error": e2e_graph_err} if e2e_graph_err else {
+                      "value": round(e2e_steps * B * world / (e2e_graph_ms * 1e-3), 3), "unit": UNIT,
                       "h2d_bytes_per_step": h2d_u8, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                       "what": "same as e2e_u8 through codd_b200.runner.StereoSequenceRunner (SURVEY 8f N2): staging + "
                               "stereo forward + crop replayed from one CUDA graph per serving slot, 2 slots"},
