@@ -3,6 +3,8 @@ inputs.  Integer / index / discrete outputs and the whole cost-volume + warp ari
 compared BIT-EXACT; the dense convolutions (fp32 FMA, different summation order than torch's
 CPU kernels) within rtol 2e-5 / atol 2e-5, tolerance stated per test."""
 import numpy as np
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -117,6 +119,27 @@ def test_conv3x3_head1_residual_relu(ops):
     wide[:, 16:32].copy_(x.cuda())
     out = ops.conv2d(wide[:, 16:32], ops.pack_conv_weight(wt).cuda(), b.cuda(), 1, 3, 1, 1, 1, ACT_RELU,
                      residual=nhwc(ops, res), res_bcast=True)
+    torch.testing.assert_close(back(ops, out), ref, rtol=CONV_RTOL, atol=CONV_ATOL)
+
+
+@pytest.mark.skipif(os.environ.get("CODD_PW_STAGED") != "1",
+                    reason="experimental shared-memory-staged 1x1 kernel: run the suite with CODD_PW_STAGED=1")
+@pytest.mark.parametrize("c0,c1,cout,n,h,w", [(16, 16, 16, 2, 37, 71), (32, 0, 16, 1, 64, 130), (32, 32, 32, 2, 19, 33),
+                                               (24, 16, 32, 1, 7, 9), (16, 0, 16, 3, 50, 50)])
+def test_pointwise_staged(ops, c0, c1, cout, n, h, w):
+    """With CODD_PW_STAGED=1 every eligible 1x1 conv of the process runs the staged kernel; this covers ragged tiles,
+    two concatenated sources, a broadcast residual and the leaky epilogue against F.conv2d."""
+    from codd_b200.lib import ACT_LEAKY
+    g = gen(c0 * 7 + c1 + cout)
+    a = torch.randn(n, c0, h, w, generator=g)
+    b2 = torch.randn(n, c1, h, w, generator=g) if c1 else None
+    wt = torch.randn(cout, c0 + c1, 1, 1, generator=g) / (c0 + c1) ** 0.5
+    bias = torch.randn(cout, generator=g)
+    res = torch.randn(n, 1, h, w, generator=g)
+    x = a if b2 is None else torch.cat([a, b2], 1)
+    ref = F.leaky_relu(F.conv2d(x, wt, bias) + res, 0.2)
+    out = ops.conv2d(nhwc(ops, a), ops.pack_conv_weight(wt).cuda(), bias.cuda(), cout, 1, act=ACT_LEAKY,
+                     x2=None if b2 is None else nhwc(ops, b2), residual=nhwc(ops, res), res_bcast=True)
     torch.testing.assert_close(back(ops, out), ref, rtol=CONV_RTOL, atol=CONV_ATOL)
 
 
