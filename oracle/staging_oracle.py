@@ -4,7 +4,9 @@ reference's test pipeline (datasets/transforms.py:391-421, :147-176; datasets/fo
 TEST INFRASTRUCTURE ONLY.  **Parity unpinned**: the arithmetic lives in mmcv (`mmcv.imnormalize`, `mmcv.impad`,
 mmcv-full==1.7.0 per README.md:41), which is absent from /root/reference and from this container; restated from its
 published algorithm: float32 image, optional BGR->RGB, subtract mean, multiply by 1/std (reciprocal rounded to fp32
-here), cv2.copyMakeBorder(BORDER_REFLECT_101) == numpy 'reflect' on the bottom / right."""
+here), cv2.copyMakeBorder(BORDER_REFLECT_101) == numpy 'reflect' on the bottom / right.  tests/test_staging_oracle.py
+checks it against the OpenCV calls mmcv 1.7.0 makes (cvtColor / subtract / multiply / copyMakeBorder): identical
+geometry, values within one float32 ulp (mmcv multiplies by a float64 reciprocal)."""
 import math
 
 import numpy as np
