@@ -119,9 +119,11 @@ class ConsistentOnlineDynamicDepth(nn.Module):
             st["gt_disp_change"].append(crop("gt_disp_change"))
         if gts["gt_flow_occ"] is not None:
             st["gt_flow_occ"].append((gts["gt_flow_occ"][idx] > 0)[:, :, :img_h, :img_w])     # True = occluded
-            if gts["gt_disp_change"] is None and idx > 0:
-                raise NotImplementedError("deriving gt_disp_change from flow (utils/misc.py:39-59) is not ported: "
-                                          "pass gt_disp_change (or gt_disp2) with the ground truth")
+            if gts["gt_disp_change"] is None and idx > 0:                                     # codd.py:331-340
+                from . import ops
+                change, _ = ops.gt_disp_change(gts["gt_flow"][idx - 1][:, :, :img_h, :img_w], gt_disp,
+                                               st["gt_disp"][idx - 1], st["gt_flow_occ"][idx - 1])
+                st["gt_disp_change"].append(change)
         if gt_disp2 is not None and gts["gt_disp_change"] is None:                           # codd.py:343-349
             change = gt_disp2 - gt_disp
             change[gt_disp2 <= 0.0] = 1050 * 0.2

@@ -184,6 +184,28 @@ __global__ void __launch_bounds__(MT_THREADS) sceneflow_metrics_kernel(
     block_accumulate<5>(v, acc);
 }
 
+// utils/misc.py:39-59 compute_gt_disp_change: change = flow_warp(gt_curr, flow, nearest, zeros) - gt_prev, BF where the
+// sample falls outside the image or the previous frame's pixel is flow-occluded; warped_out (optional) = the warped map.
+__global__ void __launch_bounds__(MT_THREADS) disp_change_kernel(const float* __restrict__ flow, const float* __restrict__ gt_curr,
+                                                                 const float* __restrict__ gt_prev,
+                                                                 const unsigned char* __restrict__ occ_prev, int h, int w,
+                                                                 size_t total, float* __restrict__ change,
+                                                                 float* __restrict__ warped_out) {
+    const size_t hw = (size_t)h * w;
+    for (size_t i = (size_t)blockIdx.x * MT_THREADS + threadIdx.x; i < total; i += (size_t)gridDim.x * MT_THREADS) {
+        const size_t s = i / hw, q = i - s * hw;
+        const int y = (int)(q / w), x = (int)(q - (size_t)y * w);
+        const float ix = sample_index((float)x, __ldg(flow + (s * 2) * hw + q), w);
+        const float iy = sample_index((float)y, __ldg(flow + (s * 2 + 1) * hw + q), h);
+        const bool inb = ix >= 0.f && ix <= (float)(w - 1) && iy >= 0.f && iy <= (float)(h - 1);
+        const float wv = inb ? __ldg(gt_curr + s * hw + (size_t)((int)iy) * w + (int)ix) : 0.f;
+        float c = __fsub_rn(wv, __ldg(gt_prev + i));
+        if (!inb || (occ_prev && occ_prev[i] != 0)) c = MT_BF;
+        change[i] = c;
+        if (warped_out) warped_out[i] = wv;
+    }
+}
+
 int metrics_grid(size_t total) {
     const size_t blocks = (total + MT_THREADS - 1) / MT_THREADS;
     return (int)(blocks < 148 * 8 ? (blocks ? blocks : 1) : 148 * 8);
@@ -237,6 +259,17 @@ extern "C" int codd_sceneflow_metrics(const float* Ts, long long ts_sample_strid
     sceneflow_metrics_kernel<<<metrics_grid(total), MT_THREADS, 0, (cudaStream_t)stream>>>(
         Ts, (size_t)ts_sample_stride, (size_t)ts_row_stride, pred_prev, (size_t)pprev_sample_stride, pprev_row_stride,
         intrinsics, flow_prev, gt_disp_change, gt_prev, seg, flow_occ, h, w, total, disp_lo, disp_hi, acc);
+    CODD_RETURN_IF_CUDA_ERROR();
+    return 0;
+}
+
+extern "C" int codd_gt_disp_change(const float* flow_prev, const float* gt_curr, const float* gt_prev,
+                                   const unsigned char* flow_occ_prev, int n, int h, int w, float* change, float* warped,
+                                   void* stream) {
+    if (!flow_prev || !gt_curr || !gt_prev || !change || n <= 0 || h <= 1 || w <= 1) return CODD_E_BADARG;
+    const size_t total = (size_t)n * h * w;
+    disp_change_kernel<<<metrics_grid(total), MT_THREADS, 0, (cudaStream_t)stream>>>(flow_prev, gt_curr, gt_prev, flow_occ_prev,
+                                                                                    h, w, total, change, warped);
     CODD_RETURN_IF_CUDA_ERROR();
     return 0;
 }

@@ -86,6 +86,7 @@ SIGNATURES = {
                                   c_void_p]),
     "codd_temporal_metrics": (c_int, [_FP, _FP, _FP, ctypes.c_longlong, c_int, _FP, _FP, _FP, ctypes.c_longlong, c_int, _FP,
                                       _FP, _FP, c_int, c_int, c_int, c_float, c_float, _FP, c_void_p]),
+    "codd_gt_disp_change": (c_int, [_FP, _FP, _FP, _FP, c_int, c_int, c_int, _FP, _FP, c_void_p]),
     "codd_sceneflow_metrics": (c_int, [_FP, ctypes.c_longlong, ctypes.c_longlong, _FP, ctypes.c_longlong, c_int, _FP, _FP, _FP,
                                        _FP, _FP, _FP, c_int, c_int, c_int, c_float, c_float, _FP, c_void_p]),
     "codd_nhwc_to_nchw": (c_int, [_FP, c_int, c_int, c_int, c_int, c_int, _FP, c_void_p]),

@@ -846,3 +846,18 @@ def sceneflow_metrics(Ts, pred_prev, intrinsics, flow_prev, gt_disp_change, gt_p
         _stream()))
     _lib.check(rc, "codd_sceneflow_metrics")
     return acc
+
+
+def gt_disp_change(flow_prev, gt_curr, gt_prev, flow_occ_prev=None):
+    """utils/misc.py:39-59: (change [N,1,H,W], warped gt [N,1,H,W]) for one frame pair."""
+    _require_cuda(flow_prev, gt_curr, gt_prev)
+    n, _, h, w = gt_prev.shape
+    flow_prev, gt_curr, gt_prev = flow_prev.contiguous(), gt_curr.contiguous(), gt_prev.contiguous()
+    occ = None if flow_occ_prev is None else flow_occ_prev.to(torch.uint8).contiguous()
+    change = torch.empty_like(gt_prev)
+    warped = torch.empty_like(gt_prev)
+    rc = _run("gt_disp_change", 4 * n * h * w * 6, lambda: _lib.load().codd_gt_disp_change(
+        flow_prev.data_ptr(), gt_curr.data_ptr(), gt_prev.data_ptr(), None if occ is None else occ.data_ptr(), n, h, w,
+        change.data_ptr(), warped.data_ptr(), _stream()))
+    _lib.check(rc, "codd_gt_disp_change")
+    return change, warped

@@ -377,6 +377,12 @@ CODD_API int codd_temporal_metrics(const float* flow_prev, const float* gt, cons
                                    int pprev_row_stride, const unsigned char* mask_prev, const float* gt_disp2_prev,
                                    const double* gt_pos_count, int n, int h, int w, float disp_lo, float disp_hi, double* acc,
                                    void* stream);
+/* utils/misc.py:39-59 compute_gt_disp_change (ground-truth preparation of the motion meters, codd.py:331-340):
+ * change[n,1,h,w] = flow_warp(gt_curr, flow_prev, nearest, zeros) - gt_prev, BF_DEFAULT (210) where the sample leaves the
+ * image or flow_occ_prev (uint8, may be NULL) marks the pixel occluded; warped (may be NULL) receives the warped map. */
+CODD_API int codd_gt_disp_change(const float* flow_prev, const float* gt_curr, const float* gt_prev,
+                                 const unsigned char* flow_occ_prev, int n, int h, int w, float* change, float* warped,
+                                 void* stream);
 CODD_API int codd_sceneflow_metrics(const float* Ts, long long ts_sample_stride, long long ts_row_stride,
                                     const float* pred_prev, long long pprev_sample_stride, int pprev_row_stride,
                                     const float* intrinsics, const float* flow_prev, const float* gt_disp_change,

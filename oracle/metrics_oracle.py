@@ -155,3 +155,13 @@ def sceneflow_metrics(Ts, pred_prev, intr, flow, gt_disp_change, gt_disp_prev, d
     m = mask[:, 0]
     return dict(n=int(m.sum()), sum_sf=float(sf[m].astype(np.float64).sum()), sum_of=float(of[m].astype(np.float64).sum()),
                 n1_sf=int((sf[m] < F32(1.0)).sum()), n1_of=int((of[m] < F32(1.0)).sum()))
+
+
+def gt_disp_change(flow_occ_prev, gt_prev, gt_curr, flow):
+    """utils/misc.py:39-59 compute_gt_disp_change -> (change, warped gt), float32 [N,1,H,W]."""
+    warped, valid = flow_warp_nearest(gt_curr, flow)
+    change = (warped - np.asarray(gt_prev, F32)).astype(F32)
+    change[~valid] = BF_DEFAULT
+    if flow_occ_prev is not None:
+        change[np.asarray(flow_occ_prev, bool)] = BF_DEFAULT
+    return change, warped

@@ -94,3 +94,37 @@ def test_evaluate_true_with_disp2_or_flow_occ(monkeypatch):
           gt_disp_change=[dc], gt_flow_occ=[focc])
     c = _Recorder.calls[2]
     assert torch.equal(c["gt_disp_change"], dc[:, 2]) and torch.equal(c["gt_flow_occ_prev"], focc[:, 1] > 0)
+
+
+def test_evaluate_true_derives_disp_change_from_flow(monkeypatch):
+    """gt_flow_occ without gt_disp_change: the change of frame pair (idx-1, idx) comes from compute_gt_disp_change
+    (codd.py:331-340) with the PREVIOUS frame's flow / disparity / occlusion, and the motion block uses entry [-1]."""
+    from codd_b200 import ops
+    monkeypatch.setattr(metrics_mod, "SequenceMetrics", _Recorder)
+    seen = []
+
+    def fake_change(flow_prev, gt_curr, gt_prev, occ_prev):
+        seen.append((flow_prev, gt_curr, gt_prev, occ_prev))
+        return torch.full_like(gt_prev, float(len(seen))), None
+
+    monkeypatch.setattr(ops, "gt_disp_change", fake_change)
+    model = codd_b200.build_estimator(codd_b200.codd_stereo_config(64))
+    model.eval()
+    B, MF, H, W = 1, 3, 64, 64
+    g = torch.Generator().manual_seed(2)
+    monkeypatch.setattr(model, "consistent_online_depth_estimation",
+                        lambda l, r, m, s: {"pred_disp": torch.ones(B, 1, H, W), "Ts": torch.zeros(B, H, W, 7)})
+    img = torch.zeros(B, MF, 3, H, W)
+    gt = torch.rand(B, MF, 1, H, W, generator=g) * 60
+    flow = torch.randn(B, MF, 2, H, W, generator=g)
+    focc = (torch.rand(B, MF, 1, H, W, generator=g) > 0.7).float()
+    metas = [[dict(img_shape=(H, W, 3), disp_range=(0.0, 64.0), intrinsics=[100.0, 100.0, 32.0, 32.0])]]
+    model(return_loss=False, evaluate=True, img=[img], img_metas=metas, r_img=[img], gt_disp=[gt], gt_flow=[flow],
+          gt_flow_occ=[focc])
+    assert len(seen) == MF - 1
+    for i, (f, gc, gp, oc) in enumerate(seen, start=1):
+        assert torch.equal(f, flow[:, i - 1]) and torch.equal(gc, gt[:, i]) and torch.equal(gp, gt[:, i - 1])
+        assert torch.equal(oc, focc[:, i - 1] > 0)
+        c = _Recorder.calls[i]
+        assert torch.equal(c["gt_disp_change"], torch.full((B, 1, H, W), float(i)))
+        assert torch.equal(c["gt_flow_occ_prev"], focc[:, i - 1] > 0)

@@ -119,3 +119,14 @@ def test_oracle_matches_golden_fixture():
             assert t["n"] == r["n"]
             for k_o, k_r in [("tepe", "tepe"), ("tepe_rel", "tepe_rel"), ("th1_tepe_rel", "th1"), ("th3_tepe", "th3_tepe")]:
                 assert t[k_o] == pytest.approx(r[k_r], rel=1e-5)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="needs /root/reference")
+def test_gt_disp_change_matches_reference():
+    U = ref_loader.load().utils
+    c = make_case(5, n=2)
+    occ = np.random.default_rng(9).random(c["gt"].shape) < 0.2
+    ref_change, ref_warp = U.compute_gt_disp_change(torch.from_numpy(occ), torch.from_numpy(c["gt_prev"]),
+                                                    torch.from_numpy(c["gt"]), torch.from_numpy(c["flow"]))
+    change, warped = M.gt_disp_change(occ, c["gt_prev"], c["gt"], c["flow"])
+    assert np.array_equal(change, ref_change.numpy()) and np.array_equal(warped, ref_warp.numpy())
