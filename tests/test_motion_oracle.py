@@ -119,3 +119,21 @@ def test_cvx_upsample_and_correlation_vs_reference():
     mine = M.all_pairs_correlation(f1, f2, 3)
     for a, b in zip(mine, blk.corr_pyramid):
         assert torch.equal(a, b)
+
+
+def test_se3_exp_matches_matrix_exponential():
+    """Independent statement of lietorch's SE3.exp (absent here): exp of the 4x4 twist matrix [[phi^, tau], [0, 0]]
+    (scipy.linalg.expm) gives the rotation R = exp(phi^) and the translation t = V(phi) tau of the oracle."""
+    from scipy.linalg import expm
+    xi = (torch.randn(40, 6, generator=g(7)) * torch.tensor([1.5, 1.5, 1.5, .9, .9, .9])).double()
+    xi[:5, 3:] *= 1e-5                                     # small-angle series branch
+    T = M.se3_exp(xi)
+    for i in range(xi.shape[0]):
+        tau, phi = xi[i, :3].numpy(), xi[i, 3:].numpy()
+        tw = np.zeros((4, 4))
+        tw[:3, :3] = np.array([[0, -phi[2], phi[1]], [phi[2], 0, -phi[0]], [-phi[1], phi[0], 0]])
+        tw[:3, 3] = tau
+        E = expm(tw)
+        R = Rotation.from_quat(T[i, 3:].numpy()).as_matrix()
+        np.testing.assert_allclose(R, E[:3, :3], atol=1e-9)
+        np.testing.assert_allclose(T[i, :3].numpy(), E[:3, 3], atol=1e-9)
