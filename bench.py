@@ -369,6 +369,16 @@ def run_b200(args):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:  # noqa: BLE001
         pass
+    def _flatten(obj, prefix=""):
+        out = {}
+        if isinstance(obj, dict):
+            for k, v in obj.items():
+                out.update(_flatten(v, f"{prefix}{k}_" if isinstance(v, dict) else f"{prefix}{k}"))
+        elif isinstance(obj, (int, float)) and not isinstance(obj, bool):
+            out[prefix] = obj
+        return out
+
+    peaks = _flatten(peaks)      # tolerate nesting ({"hbm": {"gbs": ..}} -> "hbm_gbs") and non-dict files
     # the kernels are timed inside a long step: prefer a sustained figure when the driver's file has one
     peak_key = next((k for k in ("hbm_gbs_sustained", "hbm_sustained_gbs", "hbm_gbs", "hbm_gbs_burst")
                      if isinstance(peaks.get(k), (int, float))), None)
