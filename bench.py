@@ -383,7 +383,8 @@ def run_b200(args):
     peak_key = next((k for k in ("hbm_gbs_sustained", "hbm_sustained_gbs", "hbm_gbs", "hbm_gbs_burst")
                      if isinstance(peaks.get(k), (int, float))), None)
     if peak_key is None:
-        peak_key = next((k for k, v in peaks.items() if "hbm" in k.lower() and isinstance(v, (int, float))), None)
+        peak_key = next((k for k, v in peaks.items()           # any HBM figure that can be a bandwidth in GB/s
+                         if "hbm" in k.lower() and isinstance(v, (int, float)) and 1000.0 <= v <= 20000.0), None)
     peak_gbs = float(peaks[peak_key]) if peak_key else 6650.0
     peak_src = f"MEASURED_PEAKS.json {peak_key} (measured)" if peak_key else "fallback 6650 GB/s"
 
