@@ -1,0 +1,60 @@
+"""Static checks on the compiled sm_100a objects (cuobjdump, no GPU): the properties that cost the most time to get
+right and that a harmless-looking edit can silently undo.  Skipped when the build directory or cuobjdump is missing."""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+BUILD = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "codd_b200", "csrc", "build")
+needs_build = pytest.mark.skipif(shutil.which("cuobjdump") is None or not os.path.exists(os.path.join(BUILD, "conv_tc_ring.o")),
+                                 reason="needs cuobjdump and the built objects (python -c 'import __graft_entry__ as g; g.build()')")
+
+
+def _sass(obj):
+    return subprocess.run(["cuobjdump", "-sass", os.path.join(BUILD, obj)], capture_output=True, text=True, check=True).stdout
+
+
+def _functions(sass):
+    out, name = {}, None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            out[name] = []
+        elif name:
+            out[name].append(line)
+    return out
+
+
+@needs_build
+def test_ring_conv_uses_tcgen05_tma_and_uniform_issue():
+    fns = {k: v for k, v in _functions(_sass("conv_tc_ring.o")).items() if "conv3x3_tc_ring_kernel" in k}
+    assert len(fns) == 3                                          # <16,16>, <32,16>, <32,32>
+    for name, lines in fns.items():
+        text = "\n".join(lines)
+        assert "UTCHMMA" in text, name                            # tcgen05.mma kind::f16
+        assert "UTMALDG" in text, name                            # TMA tensor loads
+        assert "UTCBAR" in text or "UTCCOMMIT" in text or "ARRIVE" in text, name
+        # issuers elected with elect.sync: operands stay in uniform registers.  With `if (lane == 0)` ptxas wrapped every
+        # MMA in an elect / R2UR / issue / BRA.U.ANY waterfall loop (79 of them in this kernel, 10 instructions per MMA)
+        assert text.count("BRA.U.ANY") <= 4, (name, text.count("BRA.U.ANY"))
+        assert text.count("UTCHMMA") >= 40, name                  # the interior paths are fully unrolled
+
+
+@needs_build
+def test_no_stack_frame_in_the_call_free_kernels():
+    """Kernels without out-of-line calls must not need a stack frame: accumulators indexed by a run-time loop bound, or
+    weights CSE'd across unrolled columns, once put their register arrays in local memory ("What made the
+    direct convolutions slow").  (Kernels that call the out-of-line transcendental activations legitimately have one.)"""
+    res = ""
+    for o in ("conv_tc_ring.o", "gemm_tc.o", "cost_volume.o", "tile_features.o", "metrics.o"):
+        res += subprocess.run(["cuobjdump", "-res-usage", os.path.join(BUILD, o)], capture_output=True, text=True,
+                              check=True).stdout
+    entries = re.findall(r"Function (\S+):\s*\n\s*(.*)", res)
+    assert len(entries) >= 15
+    for name, usage in entries:
+        stack = int(re.search(r"STACK:(\d+)", usage).group(1))
+        local = int(re.search(r"LOCAL:(\d+)", usage).group(1))
+        assert local == 0 and stack == 0, (name, usage)
