@@ -15,6 +15,32 @@
 
 static inline bool codd_aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
 
+// One-time, PER-DEVICE function-attribute set-up (cudaFuncSetAttribute applies to the current device only), safe
+// under concurrent first calls from several host threads.  Each call site owns one CoddDeviceOnce; `done` holds one bit
+// per device ordinal, published with release/acquire so a thread that sees the bit also sees the attribute set.  The
+// fast path is one relaxed-cost atomic load, no API call except cudaGetDevice — legal during stream capture.
+#include <atomic>
+#include <mutex>
+struct CoddDeviceOnce {
+    std::atomic<unsigned long long> done[4];   // 256 device ordinals
+    std::mutex mu;
+};
+template <typename F>
+static inline int codd_once_per_device(CoddDeviceOnce& o, F&& setup) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    std::atomic<unsigned long long>& word = o.done[(dev >> 6) & 3];
+    if (word.load(std::memory_order_acquire) & bit) return 0;
+    std::lock_guard<std::mutex> lock(o.mu);
+    if (word.load(std::memory_order_relaxed) & bit) return 0;
+    e = setup();
+    if (e != cudaSuccess) return (int)e;
+    word.fetch_or(bit, std::memory_order_release);
+    return 0;
+}
+
 // Transcendental activations (fusion heads, GRU gates): OUT OF LINE on purpose.  Inlined into a fully unrolled
 // 64-element epilogue they blow a kernel up to several hundred KB of straight-line code that every warp
 // executes once — the direct convolutions were instruction-fetch bound on it (ncu: stall_no_inst > 50 %).

@@ -250,12 +250,11 @@ int launch_conv(ConvP p, int PWn, int G, cudaStream_t stream) {
     const size_t smem = smem_for(PWn);
     if (smem > 227 * 1024) return CODD_E_UNSUPPORTED;
     auto kern = conv_nhwc_kernel<KH, KW, SH, SW, DIL, CO_T>;
-    static size_t configured = 48 * 1024;  // per instantiation; set once so graph capture sees no API calls
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        configured = smem;
-    }
+    static CoddDeviceOnce once;   // per instantiation and device: graph capture sees no attribute calls afterwards
+    if (int rc = codd_once_per_device(once, [&] {
+            return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        }))
+        return rc;
     p.tilesX = codd_ceil_div(p.Wo, TW);
     p.tilesY = codd_ceil_div(p.Ho, PWn * PX);
     dim3 block(32, PWn, G);
@@ -459,12 +458,11 @@ int launch_pointwise_staged(const ConvP& p, cudaStream_t s) {
     const int Cin = p.C0 + p.C1;
     const int tile_floats = 128 * PX_T * ((Cin + 4) > (CO + 4) ? (Cin + 4) : (CO + 4));
     const size_t smem = ((size_t)Cin * CO + tile_floats) * sizeof(float);
-    static size_t configured = 48 * 1024;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(pointwise_staged_kernel<CO, PX_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        configured = smem;
-    }
+    static CoddDeviceOnce once;
+    if (int rc = codd_once_per_device(once, [&] {
+            return cudaFuncSetAttribute(pointwise_staged_kernel<CO, PX_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        }))
+        return rc;
     const unsigned grid = (unsigned)((npix + 128 * PX_T - 1) / (128 * PX_T));
     pointwise_staged_kernel<CO, PX_T><<<grid, 128, smem, s>>>(p, npix);
     CODD_RETURN_IF_CUDA_ERROR();
@@ -757,7 +755,11 @@ int conv_dispatch(const ConvP& p, const codd_conv_desc* d, cudaStream_t s) {
     if (kh == 1 && kw == 1 && sh == 1 && sw == 1 && d->ph == 0 && d->pw == 0 && d->ho == d->h && d->wo == d->w) {
         const bool vec_ok = p.vec0 && (d->c0 % 4 == 0) && (p.C1 == 0 || (p.vec1 && d->c1 % 4 == 0)) &&
                             codd_aligned16(p.out) && (d->ldo % 4 == 0) && (d->c0 + p.C1) * 32 * 4 <= 48 * 1024;
+#ifdef CODD_DIAG
         static const bool pw_staged = getenv("CODD_PW_STAGED") && atoi(getenv("CODD_PW_STAGED")) != 0;   // experimental
+#else
+        constexpr bool pw_staged = false;
+#endif
         if (pw_staged && vec_ok && (p.Cout == 16 || p.Cout == 32) && (d->c0 + p.C1) <= 64 && (d->ldr % 4 == 0 || !p.res || p.res_bcast)) {
             if (p.Cout == 16) return launch_pointwise_staged<16, 4>(p, s);
             return launch_pointwise_staged<32, 2>(p, s);
@@ -876,12 +878,11 @@ extern "C" int codd_nhwc_to_nchw(const float* in, int ldi, int n, int h, int w, 
     for (int c0 = 0; c0 < c; c0 += CCH) {
         const int cc = c - c0 < CCH ? c - c0 : CCH;
         const size_t smem = (size_t)cc * (TR_PIX + 1) * sizeof(float);
-        static size_t configured = 48 * 1024;
-        if (smem > configured) {
-            cudaError_t e = cudaFuncSetAttribute(nhwc_to_nchw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return (int)e;
-            configured = smem;
-        }
+        static CoddDeviceOnce once;
+        if (int rc = codd_once_per_device(once, [&] {
+                return cudaFuncSetAttribute(nhwc_to_nchw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            }))
+            return rc;
         nhwc_to_nchw_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(in, ldi, hw, cc, c, c0, out);
         CODD_RETURN_IF_CUDA_ERROR();
     }

@@ -456,7 +456,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const __grid_
     }
 }
 
-long long* g_tc_dbg = nullptr;
+#ifdef CODD_DIAG
+long long* g_tc_dbg = nullptr;   // diagnostic builds only (make DIAG=1): cycle-counter buffer
+#endif
 
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -481,12 +483,11 @@ int launch_tc(const CUtensorMap& tmap, TcP p, cudaStream_t s) {
     constexpr uint32_t B_BYTES = 2 * 9 * NP * ROWB;
     const size_t smem = NBUF * A_STRIDE + B_BYTES + 1024;
     auto kern = conv3x3_tc_kernel<KC, NP, NBUF, NACC, LAG, DIL>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        configured = true;
-    }
+    static CoddDeviceOnce once;   // one per template instantiation
+    if (int rc = codd_once_per_device(once, [&] {
+            return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        }))
+        return rc;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -527,7 +528,11 @@ extern "C" int codd_conv3x3_tc_dil(const float* in, int ldi, int cin, int n, int
     p.tilesX = codd_ceil_div(w, TC_TW);
     p.tilesY = codd_ceil_div(h, rows_per_tile);
     p.ntiles = p.tilesX * p.tilesY * n;
+#ifdef CODD_DIAG
     p.dbg = g_tc_dbg;
+#else
+    p.dbg = nullptr;
+#endif
     p.split_rna = (flags & 1) ? 1 : 0;
     p.use_base_offset = (flags & 2) ? 1 : 0;
     p.diag = (flags >> 2) & 3;
@@ -548,7 +553,9 @@ extern "C" int codd_conv3x3_tc(const float* in, int ldi, int cin, int n, int h, 
 // diagnostic: device buffer of [grid][8] int64 cycle counters filled by the next codd_conv3x3_tc launches
 // (0 producer wait-empty, 1 mma wait-full, 2 mma wait-acc-empty, 3 mma wait-lo, 4 epilogue wait-acc-full,
 //  5 split wait-p12, 6 split work, 7 producer total); NULL disables.
+#ifdef CODD_DIAG
 extern "C" CODD_API int codd_conv3x3_tc_debug(long long* dbg) {
     g_tc_dbg = dbg;
     return 0;
 }
+#endif

@@ -597,7 +597,9 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
     }
 }
 
-long long* g_rg_dbg = nullptr;
+#ifdef CODD_DIAG
+long long* g_rg_dbg = nullptr;   // diagnostic builds only (make DIAG=1): cycle-counter buffer
+#endif
 
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -623,12 +625,11 @@ int launch_ring(const CUtensorMap& tmap, RgP p, cudaStream_t s) {
     const size_t smem = NBUF * A_STRIDE + NH * 2 * H_STRIDE + B_BYTES + 1024;
     static_assert(NBUF * A_STRIDE + NH * 2 * H_STRIDE + B_BYTES + 1024 + 2048 <= 232448, "shared memory budget");
     auto kern = conv3x3_tc_ring_kernel<KC, NP, NBUF, NH>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        configured = true;
-    }
+    static CoddDeviceOnce once;   // one per template instantiation
+    if (int rc = codd_once_per_device(once, [&] {
+            return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        }))
+        return rc;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -681,9 +682,14 @@ extern "C" int codd_conv3x3_tc_ring(const float* in, int ldi, int cin, int n, in
     p.N = n; p.H = h; p.W = w; p.Cout = cout; p.ldo = ldo; p.ldr = ldr; p.res_bcast = res_bcast; p.act = act;
     p.tilesX = codd_ceil_div(w, RG_TW);
     p.nseg = p.seg = p.nitems = 0;
+#ifdef CODD_DIAG
     p.dbg = g_rg_dbg;
     static const int diag = getenv("CODD_RING_DIAG") ? atoi(getenv("CODD_RING_DIAG")) : 0;
     p.diag = diag;
+#else
+    p.dbg = nullptr;   // release builds: no environment switches, no mutable globals behind the ABI
+    p.diag = 0;
+#endif
     cudaStream_t s = (cudaStream_t)stream;
     if (KC == 32 && NP == 32) return launch_ring<32, 32, 4, 4>(tmap, p, s);
     if (KC == 32 && NP == 16) return launch_ring<32, 16, 4, 6>(tmap, p, s);
@@ -693,7 +699,9 @@ extern "C" int codd_conv3x3_tc_ring(const float* in, int ldi, int cin, int n, in
 // diagnostic: device buffer of [grid][8] int64 cycle counters filled by the next codd_conv3x3_tc_ring launches
 // (0 producer wait-empty, 1 mma wait-full, 2 mma wait-lo, 3 mma wait-slot-drained, 4 pass-A thread total, 5 pass-B wait for pass A of row g+2,
 //  6 epilogue wait-acc-full, 7 split wait (x_lo stage free + row landed)); NULL disables.
+#ifdef CODD_DIAG
 extern "C" CODD_API int codd_conv3x3_tc_ring_debug(long long* dbg) {
     g_rg_dbg = dbg;
     return 0;
 }
+#endif

@@ -373,16 +373,16 @@ extern "C" int codd_cost_volume(const float* tile_l, const float* tile_r, int n,
     dim3 grid((unsigned)(n * h * p.nblk)), block(32 * nwarps);
     cudaStream_t s = (cudaStream_t)stream;
     void (*kern)(CvP) = nullptr;
-    static size_t configured[3] = {48 * 1024, 48 * 1024, 48 * 1024};
+    static CoddDeviceOnce once[3];
     int slot;
     if (cv && argmin) { kern = cost_volume_kernel<true, true>; slot = 0; }
     else if (cv) { kern = cost_volume_kernel<true, false>; slot = 1; }
     else { kern = cost_volume_kernel<false, true>; slot = 2; }
-    if (smem > configured[slot]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        configured[slot] = smem;
-    }
+    // opt in to the full 227 KB once per device (the per-launch request stays `smem`)
+    if (int rc = codd_once_per_device(once[slot], [&] {
+            return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        }))
+        return rc;
     kern<<<grid, block, smem, s>>>(p);
     CODD_RETURN_IF_CUDA_ERROR();
     return 0;
@@ -424,16 +424,15 @@ extern "C" int codd_cost_volume_pyramid(int levels, const float* const* tile_l, 
     }
     P.first[levels] = nblocks;
     void (*kern)(const CvPyr) = nullptr;
-    static size_t configured[3] = {48 * 1024, 48 * 1024, 48 * 1024};
+    static CoddDeviceOnce once[3];
     int slot;
     if (want_cv && argmin) { kern = cost_volume_pyramid_kernel<true, true>; slot = 0; }
     else if (want_cv) { kern = cost_volume_pyramid_kernel<true, false>; slot = 1; }
     else { kern = cost_volume_pyramid_kernel<false, true>; slot = 2; }
-    if (smem > configured[slot]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        configured[slot] = smem;
-    }
+    if (int rc = codd_once_per_device(once[slot], [&] {
+            return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        }))
+        return rc;
     kern<<<(unsigned)nblocks, CV_MAXW * 32, smem, (cudaStream_t)stream>>>(P);
     CODD_RETURN_IF_CUDA_ERROR();
     return 0;

@@ -265,12 +265,11 @@ int launch_gemm(const CUtensorMap& a, const CUtensorMap& alo, const CUtensorMap&
                 cudaStream_t s) {
     const size_t smem = (size_t)STAGES * (GM_BM * GM_BK * 4 + BN * GM_BK * 4) + 1024;
     auto kern = gemm_tc_kernel<BN, STAGES>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        configured = true;
-    }
+    static CoddDeviceOnce once;   // one per template instantiation
+    if (int rc = codd_once_per_device(once, [&] {
+            return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        }))
+        return rc;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

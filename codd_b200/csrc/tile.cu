@@ -497,18 +497,22 @@ int tile_warp_cost_impl(const float* fea_l, int ldfl, const float* fea_r, int ld
     p.cur = cur; p.ldc = ldc; p.prev = prev; p.ldp = ldp;
     p.dec_w = dec_w; p.dec_b = dec_b; p.N = n; p.h = h; p.w = w;
     p.aug = aug; p.ldaug = ldaug; p.raw = raw_cv;
+#ifdef CODD_DIAG
     static const int max_win = getenv("CODD_K4_MAXWIN") ? atoi(getenv("CODD_K4_MAXWIN")) : 4096;
     p.max_win = max_win;
+#else
+    p.max_win = 4096;
+#endif
     const int nblk = codd_ceil_div(w, K4_TILES);
     dim3 grid((unsigned)(n * h * nblk)), block(K4_THREADS);
-    static bool configured = false;   // set once so graph capture sees no API calls
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tile_warp_cost_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, K4_STAGE_BYTES);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(tile_warp_cost_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, K4_STAGE_BYTES);
-        if (e != cudaSuccess) return (int)e;
-        configured = true;
-    }
+    static CoddDeviceOnce once;   // once per device, so graph capture sees no attribute calls
+    if (int rc = codd_once_per_device(once, [&] {
+            cudaError_t e = cudaFuncSetAttribute(tile_warp_cost_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, K4_STAGE_BYTES);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(tile_warp_cost_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, K4_STAGE_BYTES);
+            return e;
+        }))
+        return rc;
     if (prev) tile_warp_cost_kernel<2><<<grid, block, K4_STAGE_BYTES, (cudaStream_t)stream>>>(p);
     else tile_warp_cost_kernel<1><<<grid, block, K4_STAGE_BYTES, (cudaStream_t)stream>>>(p);
     CODD_RETURN_IF_CUDA_ERROR();

@@ -34,8 +34,6 @@ SIGNATURES = {
                                     _FP, c_int, c_int, c_int, c_void_p]),
     "codd_conv3x3_tc_ring": (c_int, [_FP, c_int, c_int, c_int, c_int, c_int, _FP, _FP, _FP, c_int, c_int, c_int, c_int,
                                      _FP, c_int, c_void_p]),
-    "codd_conv3x3_tc_debug": (c_int, [_FP]),
-    "codd_conv3x3_tc_ring_debug": (c_int, [_FP]),
     "codd_conv3x3_image": (c_int, [_FP, _FP, c_int, c_int, c_int, _FP, _FP, c_int, _FP, c_int, c_void_p]),
     "codd_deconv2x2_nhwc": (c_int, [_FP, c_int, c_int, c_int, c_int, c_int, _FP, _FP, c_int, _FP, c_int, c_int,
                                     c_void_p]),

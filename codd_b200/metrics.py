@@ -66,6 +66,63 @@ class SequenceMetrics:
         return summarise(rows.numpy())
 
 
+class SequenceStats:
+    """Mean / standard deviation over SEQUENCES of the per-sequence metric rows: the role of the reference's
+    RunningStatsWithBuffer (utils/running_stats.py, apis/inference.py:47,72-76,140-153): one `collect_metric` row per
+    sequence, `mean` / `std` over the rows, ranks merged by gathering the rows."""
+
+    def __init__(self):
+        self.names, self.rows = [], []
+
+    def push(self, name, metrics):
+        self.names.append(name)
+        self.rows.append(dict(metrics))
+
+    @property
+    def n(self):
+        return len(self.rows)
+
+    def _table(self):
+        keys = sorted(self.rows[0]) if self.rows else []
+        return keys, np.array([[r[k] for k in keys] for r in self.rows], dtype=np.float64).reshape(len(self.rows), len(keys))
+
+    @property
+    def mean(self):
+        keys, t = self._table()
+        return dict(zip(keys, t.mean(0))) if len(t) else {}
+
+    @property
+    def std(self):
+        """Population standard deviation over sequences (sqrt(s / n)), as the reference's RunningStats.std."""
+        keys, t = self._table()
+        return dict(zip(keys, t.std(0))) if len(t) else {}
+
+    def gather(self):
+        """All ranks' rows (dist.all_gather_object, as apis/inference.py:147); returns a merged SequenceStats."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return self
+        parts = [None] * dist.get_world_size()
+        dist.all_gather_object(parts, (self.names, self.rows))
+        merged = SequenceStats()
+        for names, rows in parts:
+            merged.names += names
+            merged.rows += rows
+        return merged
+
+    def dump(self, path):
+        """stats.csv: one line per sequence, then mean and std (RunningStatsWithBuffer.dump)."""
+        import csv
+        keys, t = self._table()
+        with open(path, "w", newline="") as f:
+            wr = csv.writer(f)
+            wr.writerow(["name"] + keys)
+            for name, row in zip(self.names, t):
+                wr.writerow([name] + [f"{v:.6g}" for v in row])
+            wr.writerow(["mean"] + [f"{self.mean[k]:.6g}" for k in keys])
+            wr.writerow(["std"] + [f"{self.std[k]:.6g}" for k in keys])
+
+
 def gather_rows(rows):
     """All-gather of per-frame accumulator rows [frames_r, ROW] over the default process group (ranks may hold
     different numbers of frames).  Works on NCCL (rows are moved to the current CUDA device) and gloo."""

@@ -133,12 +133,20 @@ class StereoSequenceRunner:
         for s in pending:
             yield s.wait().numpy().copy()
 
-    def run_sequences(self, sequences, out_dir=None, rank=0, world_size=1, metrics=None, batch=1):
+    def run_sequences(self, sequences, out_dir=None, rank=0, world_size=1, metrics=None, batch=1, stats=None):
         """sequences: list of dicts {"name": str, "left": [T,H,W,3] uint8, "right": [T,H,W,3] uint8, optional
         "gt_disp": [T,1,H,W] float32, "gt_flow": [T,2,H,W]}.  This rank processes sequences rank::world_size, `batch`
-        frames per launch (stereo frames are independent).  Returns {name: [T,1,H,W] disparity}; writes
-        `<out_dir>/<name>/<frame>.disp.pred.npz`; feeds `metrics` (a SequenceMetrics) frame by frame when ground
-        truth is present."""
+        frames per launch (stereo frames are independent).  Returns {name: [T,1,H,W] disparity}.
+
+        Output layout follows the reference's show_result (codd.py:596-599, apis/inference.py:50-67): ONE file per
+        sequence, `<out_dir>/<name>.disp.pred.npz`, key "disp", shape [1,T,H,W] (batch of one sequence, MF frames).
+
+        Evaluation follows the reference per SEQUENCE (reset_inference_state codd.py:400-433 + RunningStats of
+        apis/inference.py:47,72-76): the meters are reset at every sequence start, each sequence yields one row of
+        metrics, and `stats` (a SequenceStats, created on demand and returned as results["__stats__"]) holds the
+        mean / std over sequences.  `metrics` may be passed to reuse a SequenceMetrics buffer; it is re-sized to the
+        sequence length, so long datasets never hit a frame cap."""
+        from .metrics import SequenceMetrics, SequenceStats
         results = {}
         for si in shard_indices(len(sequences), rank, world_size):
             seq = sequences[si]
@@ -148,16 +156,22 @@ class StereoSequenceRunner:
             disp = np.concatenate(outs, 0)
             results[seq["name"]] = disp
             if out_dir is not None:
-                for t in range(t_total):
-                    write_disp_npz(os.path.join(out_dir, seq["name"], f"{t:06d}.png"), disp[t:t + 1])
-            if metrics is not None and "gt_disp" in seq:
-                if metrics._prev is not None:
-                    metrics._prev = None               # temporal meters do not cross sequence boundaries
+                write_disp_npz(os.path.join(out_dir, seq["name"] + ".png"), disp[None, :, 0])
+            if "gt_disp" in seq and (metrics is not None or stats is not None):
+                if stats is None:
+                    stats = SequenceStats()
+                if metrics is None or metrics.acc.shape[0] < t_total:
+                    rng = metrics.disp_range if metrics is not None else seq.get("disp_range", (1.0, 192.0))
+                    metrics = SequenceMetrics(rng, max_frames=t_total, device=self.device)
+                metrics.reset()                        # every meter restarts with the sequence (codd.py:400-433)
                 for t in range(t_total):
                     pred = torch.from_numpy(disp[t:t + 1]).to(self.device)
                     gt = torch.as_tensor(seq["gt_disp"][t:t + 1]).to(self.device)
                     flow = None if "gt_flow" not in seq else torch.as_tensor(seq["gt_flow"][t:t + 1]).to(self.device)
                     metrics.update(pred, gt, gt_flow=flow)
+                stats.push(seq["name"], metrics.collect())
+        if stats is not None:
+            results["__stats__"] = stats
         return results
 
 

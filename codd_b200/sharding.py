@@ -15,16 +15,24 @@ def shard_batch(n_items, rank, world):
 
 
 def broadcast_parameters(model, src=0):
-    """One flat broadcast of every parameter (NCCL on GPUs, gloo in the CPU tests)."""
+    """Module state of rank `src` to every rank: parameters AND buffers (the reference's DDP wrap syncs both,
+    inference.py:130-134 — HRNet's BatchNorm running statistics are buffers, and they are folded into the packed
+    convolution weights), one flat broadcast per (dtype, device) group (NCCL on GPUs, gloo in the CPU tests)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return
-    params = [p for p in model.parameters()]
-    flat = torch.cat([p.data.flatten() for p in params])
-    dist.broadcast(flat, src)
-    off = 0
-    for p in params:
-        p.data.copy_(flat[off:off + p.numel()].view_as(p))
-        off += p.numel()
+    groups = {}
+    for t in list(model.parameters()) + list(model.buffers()):
+        groups.setdefault((t.dtype, t.device), []).append(t)
+    for (dtype, _), tensors in groups.items():
+        if dtype == torch.bool:        # no broadcast kernel for bool on every backend
+            flat = torch.cat([t.data.flatten().to(torch.uint8) for t in tensors])
+        else:
+            flat = torch.cat([t.data.flatten() for t in tensors])
+        dist.broadcast(flat, src)
+        off = 0
+        for t in tensors:
+            t.data.copy_(flat[off:off + t.numel()].view_as(t).to(t.dtype))
+            off += t.numel()
 
 
 def reduce_max_ms(ms, device=None):

@@ -86,6 +86,8 @@ class TileUpdate(nn.Module, _Runner):
         u = self._res(self.resblock0, u)
         u = self._res(self.resblock1, u)
         u = self._conv(self.lastconv, u, ACT_NONE)
+        if getattr(self, "keep_aux", False):     # parity tests read the confidences behind the arg-max select
+            self.aux = dict(update=u, aug=aug)
         # eval path needs only the selected hypothesis; the two auxiliary tensors of the
         # reference's return list feed the training losses only (propagation.py:241-248)
         return [ops.hyp_select(u, aug)]

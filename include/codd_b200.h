@@ -16,7 +16,10 @@
  *     Images enter as NCHW (the reference's layout); cost volumes are [N,D,h,w] planar.
  *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises.
  *   - return value: 0 success; < 0 argument error (CODD_E_*); > 0 a cudaError_t.
- *   - no global mutable state; thread-safe for concurrent calls on distinct streams.
+ *   - no mutable state behind the ABI except the one-time, per-device kernel attribute set-up (an atomic bit per
+ *     device ordinal under a mutex, csrc/common.cuh: CoddDeviceOnce), and no environment switches: concurrent calls
+ *     from several host threads / on several devices of one process are safe (tests/test_gpu_boundary.py).
+ *     Diagnostic hooks (cycle counters, CODD_* environment variables) exist only in `make DIAG=1` builds.
  *   - there is no CPU fallback: on a machine without an sm_100 device every call fails.
  */
 #ifndef CODD_B200_H
@@ -109,12 +112,6 @@ CODD_API int codd_conv3x3_tc_dil(const float* in, int ldi, int cin, int n, int h
 CODD_API int codd_conv3x3_tc_ring(const float* in, int ldi, int cin, int n, int h, int w, const float* weight_ring,
                                   const float* bias, const float* residual, int ldr, int res_bcast, int cout, int act,
                                   float* out, int ldo, void* stream);
-
-/* Diagnostic: device buffer [grid][8] of int64 cycle counters filled by later codd_conv3x3_tc_ring launches. */
-CODD_API int codd_conv3x3_tc_ring_debug(long long* dbg);
-
-/* Diagnostic: device buffer [grid][8] of int64 cycle counters filled by later codd_conv3x3_tc launches. */
-CODD_API int codd_conv3x3_tc_debug(long long* dbg);
 
 /* First backbone layer (backbone.py:35-39,70): 3x3, pad 1, 3 -> cout (<=16) channels,
  * LeakyReLU, reading NCHW images and writing NHWC.  `left` and `right` are two [n,3,h,w]

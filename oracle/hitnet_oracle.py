@@ -116,8 +116,8 @@ def cost_volume(tile_l, tile_r, max_disp):
     """
     n, c, h, w = tile_l.shape
     wr = tile_r.shape[3]
-    j4 = torch.arange(w) * 4
-    out = torch.empty(n, max_disp, h, w, dtype=torch.float32)
+    j4 = torch.arange(w, device=tile_l.device) * 4
+    out = torch.empty(n, max_disp, h, w, dtype=torch.float32, device=tile_l.device)
     for d in range(max_disp):
         x = j4 - d
         ok = (x >= 0) & (x <= wr - 1)
@@ -138,12 +138,13 @@ def cost_volume_reference_form(tile_l, tile_r, max_disp):
     CPU baseline / ``--impl reference`` arm of bench.py times this form, not the cheap gather."""
     n, c, h, w = tile_l.shape
     wr, hr = tile_r.shape[3], tile_r.shape[2]
-    xs = torch.arange(0, wr, 4, dtype=torch.float32)[:w] / (wr - 1) * 2 - 1          # columns 4j
-    ys = torch.arange(h, dtype=torch.float32) / (hr - 1) * 2 - 1
-    shift = torch.arange(max_disp, dtype=torch.float32) / (wr - 1) * 2
+    dev = tile_l.device
+    xs = torch.arange(0, wr, 4, dtype=torch.float32, device=dev)[:w] / (wr - 1) * 2 - 1          # columns 4j
+    ys = torch.arange(h, dtype=torch.float32, device=dev) / (hr - 1) * 2 - 1
+    shift = torch.arange(max_disp, dtype=torch.float32, device=dev) / (wr - 1) * 2
     gx = xs.view(1, 1, 1, w) - shift.view(1, max_disp, 1, 1)
     grid = torch.stack((gx.expand(n, max_disp, h, w), ys.view(1, 1, h, 1).expand(n, max_disp, h, w),
-                        torch.zeros(n, max_disp, h, w)), -1)
+                        torch.zeros(n, max_disp, h, w, device=dev)), -1)
     shifted = F.grid_sample(tile_r.unsqueeze(2), grid, mode="nearest", align_corners=True, padding_mode="zeros")
     return torch.norm(tile_l.unsqueeze(2) - shifted, p=1, dim=1)
 
@@ -200,14 +201,14 @@ def tile_hypotheses(sd, tile_pyr, fea_l, max_disp, return_cv=False, reference_fo
 # --------------------------------------------------------------------------------------
 # a5  to_plane / upsample                    (model/stereo/hitnet/propagation.py:10-32)
 # --------------------------------------------------------------------------------------
-def plane_offsets(size):
+def plane_offsets(size, device=None):
     """linspace(-(s-1)/2, (s-1)/2, s): exactly representable half-integers."""
-    return torch.arange(size, dtype=torch.float32) - (size - 1) / 2.0
+    return torch.arange(size, dtype=torch.float32, device=device) - (size - 1) / 2.0
 
 
 def plane_expand(d, dx, dy, size):
     """[N,1,h,w] -> [N,1,h*size,w*size]:  (d + c[x%size]*dx) + c[y%size]*dy."""
-    c = plane_offsets(size)
+    c = plane_offsets(size, d.device)
     n, _, h, w = d.shape
     a = c.view(1, 1, 1, size).repeat(1, 1, h * size, w)           # varies with x
     b = c.view(1, 1, size, 1).repeat(1, 1, h, w * size)           # varies with y
@@ -229,8 +230,8 @@ def warp_coords(disp):
     torch compute them: normalise ``2*(x-d)/(W-1) - 1`` (true division), then
     grid_sample's align_corners=True un-normalisation ``((g+1)/2)*(W-1)``."""
     n, _, h, w = disp.shape
-    xs = torch.arange(w, dtype=torch.float32).view(1, 1, w)
-    ys = torch.arange(h, dtype=torch.float32)
+    xs = torch.arange(w, dtype=torch.float32, device=disp.device).view(1, 1, w)
+    ys = torch.arange(h, dtype=torch.float32, device=disp.device)
     gx = 2.0 * (xs - disp[:, 0]) / max(w - 1, 1) - 1.0
     gy = 2.0 * ys / max(h - 1, 1) - 1.0
     ix = ((gx + 1.0) / 2.0) * (w - 1)
@@ -241,8 +242,8 @@ def warp_coords(disp):
 def warp_right(fea_r, disp):
     """Bilinear, zeros padding, sampled at (x - disp, y).  Reference form (grid_sample)."""
     n, c, h, w = fea_r.shape
-    xs = torch.arange(w, dtype=torch.float32).view(1, 1, w).expand(n, h, w)
-    ys = torch.arange(h, dtype=torch.float32).view(1, h, 1).expand(n, h, w)
+    xs = torch.arange(w, dtype=torch.float32, device=disp.device).view(1, 1, w).expand(n, h, w)
+    ys = torch.arange(h, dtype=torch.float32, device=disp.device).view(1, h, 1).expand(n, h, w)
     gx = 2.0 * (xs - disp[:, 0]) / max(w - 1, 1) - 1.0
     gy = 2.0 * ys / max(h - 1, 1) - 1.0
     return F.grid_sample(fea_r, torch.stack((gx, gy), -1), mode="bilinear",

@@ -1,9 +1,11 @@
 """Import the UNMODIFIED CODD reference files in this container.
 
-TEST INFRASTRUCTURE ONLY.  Used by ``oracle/gen_golden.py`` (fixture generation) and
-by the ``-m "not gpu"`` tests that pin the oracle restatement against the reference
-when ``/root/reference`` is present.  Nothing on the product path, in ``-m gpu`` tests,
-``smoke()`` or ``bench.py`` imports this module: the reference does not exist on the GPU box.
+TEST / BASELINE INFRASTRUCTURE ONLY.  Used by ``oracle/gen_golden.py`` (fixture generation), by
+the ``-m "not gpu"`` tests that pin the oracle restatement against the reference, and by the
+baseline legs of ``bench.py`` (``--impl reference``, ``cpu_baseline``, ``gpu_eager_baseline``), which time
+the UNMODIFIED reference modules from the git-ignored copy under ``baseline/_ref`` that
+``__graft_entry__.build()`` makes (the snapshot `gpurun` ships carries it to the GPU box).  Nothing on the
+product path imports this module.
 
 The reference needs mmcv / mmseg (registry, BaseModule, init helpers) and imports
 pytorch3d / lietorch at module scope.  None is installable here, so ``oracle/_shim``
@@ -22,8 +24,13 @@ _SHIM = os.path.join(_HERE, "_shim")
 
 
 def reference_root():
-    root = os.environ.get("CODD_REF", "/root/reference")
-    return root if os.path.isdir(os.path.join(root, "model", "stereo")) else None
+    """$CODD_REF -> baseline/_ref (the git-ignored copy __graft_entry__.build() makes so that the unmodified reference
+    travels to the GPU box with the snapshot) -> /root/reference (build container)."""
+    cands = [os.environ.get("CODD_REF"), os.path.join(os.path.dirname(_HERE), "baseline", "_ref"), "/root/reference"]
+    for root in cands:
+        if root and os.path.isdir(os.path.join(root, "model", "stereo")):
+            return root
+    return None
 
 
 def available():

@@ -16,6 +16,17 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """`gpu` tests are SKIPPED (not failed) on a machine without a CUDA device or without the built library, so a
+    plain `pytest tests` goes green on host-only CI.  On a GPU box nothing is skipped here: a missing .so fails loudly."""
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device (B200): run with `pytest -m gpu` on the GPU box")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 def load_golden(name):
     with np.load(os.path.join(GOLDEN, name)) as z:
         return {k: z[k] for k in z.files}

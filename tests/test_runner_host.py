@@ -62,3 +62,32 @@ def test_infer_batches_order_and_slot_reuse(monkeypatch):
     assert [o.shape[0] for o in outs] == [s[0] for s in shapes]
     waits = [e[2] for e in _FakeSlot.log if e[0] == "wait"]
     assert waits == sorted(waits)                       # results are taken in submission order
+
+
+def test_sequence_stats_mean_std_and_dump(tmp_path):
+    """Per-sequence rows aggregated like the reference's RunningStats (utils/running_stats.py): mean and (population) std
+    over sequences; checked against the reference class itself when /root/reference (or its mirror) is importable."""
+    import numpy as np
+    from codd_b200.metrics import SequenceStats
+    st = SequenceStats()
+    rows = [dict(epe=1.0, th3=0.5), dict(epe=2.0, th3=0.25), dict(epe=4.5, th3=0.0)]
+    for i, r in enumerate(rows):
+        st.push(f"s{i}", r)
+    assert st.n == 3
+    assert abs(st.mean["epe"] - 2.5) < 1e-12 and abs(st.std["epe"] - np.std([1.0, 2.0, 4.5])) < 1e-12
+    st.dump(str(tmp_path / "stats.csv"))
+    lines = open(tmp_path / "stats.csv").read().strip().splitlines()
+    assert lines[0] == "name,epe,th3" and lines[-2].startswith("mean,2.5") and len(lines) == 6
+    try:
+        from oracle import ref_loader
+        if not ref_loader.available():
+            return
+        ref_loader.load()
+        from utils.running_stats import RunningStats
+    except Exception:
+        return
+    rs = RunningStats()
+    for r in rows:
+        rs.push(np.array([r["epe"], r["th3"]]))
+    assert np.allclose(rs.mean, [st.mean["epe"], st.mean["th3"]], atol=1e-6)
+    assert np.allclose(rs.std, [st.std["epe"], st.std["th3"]], atol=1e-6)

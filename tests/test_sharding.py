@@ -29,6 +29,12 @@ def _worker(rank, world, port, q):
     gathered = [torch.empty_like(flat) for _ in range(world)]
     dist.all_gather(gathered, flat)
     same = all(torch.equal(gathered[0], g) for g in gathered)
+    # buffers travel too (BatchNorm running statistics of the motion network's HRNet; int64 num_batches_tracked)
+    bn = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 1), torch.nn.BatchNorm2d(4))
+    bn[1].running_mean.fill_(float(rank + 1))
+    bn[1].num_batches_tracked.fill_(10 * (rank + 1))
+    broadcast_parameters(bn, src=0)
+    same = same and bool((bn[1].running_mean == 1.0).all()) and int(bn[1].num_batches_tracked) == 10
     idx = shard_batch(10, rank, world)                 # rank r takes items r::world (DistributedSampler order)
     ms = reduce_max_ms(float(rank + 1) * 3.0)          # timing is the max over ranks
     q.put((rank, same, idx, ms))

@@ -31,15 +31,18 @@ def main():
         t_old = timeit(lambda: ops.conv3x3_tc(x, ws, b, c, ops.ACT_LEAKY))
         t_new = timeit(lambda: ops.conv3x3_tc_ring(x, wr, b, c, ops.ACT_LEAKY))
         gb = 4 * n * h * w * 2 * c / 1e9
+        import ctypes
         from codd_b200 import lib
-        dbg = torch.zeros(148 * 8, dtype=torch.int64, device=dev)
-        lib.load().codd_conv3x3_tc_ring_debug(dbg.data_ptr())
-        ops.conv3x3_tc_ring(x, wr, b, c, ops.ACT_LEAKY)
-        torch.cuda.synchronize()
-        lib.load().codd_conv3x3_tc_ring_debug(None)
-        d = dbg.view(148, 8).float().mean(0).tolist()
-        print("   ring role waits (mean clk/CTA): producer-empty %.0f | A: full %.0f | B: lo %.0f | A: slot %.0f total %.0f | B: iss %.0f | "
-              "epi accf %.0f | split p12 %.0f" % tuple(d))
+        hook = getattr(ctypes.CDLL(lib.LIB_PATH), "codd_conv3x3_tc_ring_debug", None)   # only in `make DIAG=1` builds
+        if hook is not None:
+            dbg = torch.zeros(148 * 8, dtype=torch.int64, device=dev)
+            hook(ctypes.c_void_p(dbg.data_ptr()))
+            ops.conv3x3_tc_ring(x, wr, b, c, ops.ACT_LEAKY)
+            torch.cuda.synchronize()
+            hook(None)
+            d = dbg.view(148, 8).float().mean(0).tolist()
+            print("   ring role waits (mean clk/CTA): producer-empty %.0f | A: full %.0f | B: lo %.0f | A: slot %.0f total %.0f | B: iss %.0f | "
+                  "epi accf %.0f | split p12 %.0f" % tuple(d))
         print(f"N={n} C={c} {h}x{w}: halo-tile {t_old * 1e3:.1f} us ({gb / t_old * 1e3:.0f} GB/s)   ring {t_new * 1e3:.1f} us "
               f"({gb / t_new * 1e3:.0f} GB/s)")
 

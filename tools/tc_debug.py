@@ -14,13 +14,13 @@ for (cin, cout, n, h, w) in [(16, 16, 16, 576, 960), (32, 32, 8, 288, 480)]:
     dbg = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
     for _ in range(3):
         ops.conv3x3_tc(x, ws, b, cout, ACT_LEAKY)
-    lib.load().codd_conv3x3_tc_debug(dbg.data_ptr())
+    __import__('ctypes').CDLL(lib.LIB_PATH).codd_conv3x3_tc_debug(__import__('ctypes').c_void_p(dbg.data_ptr()))   # needs a `make DIAG=1` build
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for fl in (4, 8, 12):
         e0.record(); ops.conv3x3_tc(x, ws, b, cout, ACT_LEAKY, flags=fl); e1.record(); torch.cuda.synchronize()
         print(f"   diag flags {fl} (4=no stores, 8=no split, 12=neither): {e0.elapsed_time(e1)*1e3:.0f} us")
     e0.record(); ops.conv3x3_tc(x, ws, b, cout, ACT_LEAKY); e1.record(); torch.cuda.synchronize()
-    lib.load().codd_conv3x3_tc_debug(None)
+    __import__('ctypes').CDLL(lib.LIB_PATH).codd_conv3x3_tc_debug(None)
     d = dbg.view(148, 8).double().mean(0).tolist()
     names = ["epi tmem-ld cycles", "mma wait-full", "mma wait-acc-empty", "mma wait-lo", "epi wait-acc-full",
              "split wait-p12", "split work", "epi math+store cycles"]
