@@ -25,6 +25,19 @@ struct CoddDeviceOnce {
     std::atomic<unsigned long long> done[4];   // 256 device ordinals
     std::mutex mu;
 };
+// Opt a kernel in to the largest dynamic shared-memory size its static allocation leaves room for (the opt-in limit
+// counts static + dynamic bytes; asking for the full 227 KB fails for a kernel with any __shared__ variable).
+template <typename K>
+static inline cudaError_t codd_max_dynamic_smem(K kern) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+    if (e != cudaSuccess) return e;
+    int dev = 0, optin = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+}
+
 template <typename F>
 static inline int codd_once_per_device(CoddDeviceOnce& o, F&& setup) {
     int dev = 0;

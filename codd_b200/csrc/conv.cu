@@ -252,7 +252,7 @@ int launch_conv(ConvP p, int PWn, int G, cudaStream_t stream) {
     auto kern = conv_nhwc_kernel<KH, KW, SH, SW, DIL, CO_T>;
     static CoddDeviceOnce once;   // per instantiation and device: graph capture sees no attribute calls afterwards
     if (int rc = codd_once_per_device(once, [&] {
-            return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            return codd_max_dynamic_smem(kern);
         }))
         return rc;
     p.tilesX = codd_ceil_div(p.Wo, TW);
@@ -366,108 +366,9 @@ __global__ void __launch_bounds__(256, 2) pointwise_kernel(ConvP p, size_t npix)
     }
 }
 
-// Staged variant (EXPERIMENTAL, off unless CODD_PW_STAGED=1; not yet measured on a GPU): the per-pixel access of
-// pointwise_kernel makes every LDG.128 / STG.128 of a warp touch 16-32 cache lines (one L1 tag cycle each).  Here a CTA
-// moves a tile of 128*PX_T pixels with cooperative, fully coalesced 16-byte copies through shared memory (pixel pitch
-// Cin+4 floats: conflict-free 128-bit reads for adjacent pixels), computes one GEMV per thread and pixel out of the
-// tile, and stores the results back through the same tile.
-template <int CO, int PX_T>
-__global__ void __launch_bounds__(128) pointwise_staged_kernel(ConvP p, size_t npix) {
-    extern __shared__ float4 smem4[];
-    const int Cin = p.C0 + p.C1;
-    const int pitch = Cin + 4;
-    constexpr int TILE = 128 * PX_T;
-    float* s_w = reinterpret_cast<float*>(smem4);      // [Cin][CO]
-    float* s_t = s_w + Cin * CO;                        // [TILE][pitch], later [TILE][CO + 4]
-    const int tid = threadIdx.x;
-    const size_t pix0 = (size_t)blockIdx.x * TILE;
-    for (int i = tid; i < Cin * CO; i += 128) {
-        const int co = i % CO, ci = i / CO;
-        s_w[i] = co < p.Cout ? __ldg(p.w + (size_t)ci * p.wld + co) : 0.f;
-    }
-    {
-        const int n0 = p.C0 >> 2;
-        for (int q = tid; q < TILE * n0; q += 128) {
-            const int px = q / n0, c4 = q - px * n0;
-            const size_t gp = min(pix0 + px, npix - 1);
-            *reinterpret_cast<float4*>(s_t + px * pitch + c4 * 4) = ldg4(p.in0 + gp * p.ld0 + c4 * 4);
-        }
-        const int n1 = p.C1 >> 2;
-        for (int q = tid; q < TILE * n1; q += 128) {
-            const int px = q / n1, c4 = q - px * n1;
-            const size_t gp = min(pix0 + px, npix - 1);
-            *reinterpret_cast<float4*>(s_t + px * pitch + p.C0 + c4 * 4) = ldg4(p.in1 + gp * p.ld1 + c4 * 4);
-        }
-    }
-    __syncthreads();
-    __align__(8) float acc[PX_T][CO];
-#pragma unroll
-    for (int q = 0; q < PX_T; ++q)
-#pragma unroll
-        for (int c = 0; c < CO; ++c) acc[q][c] = 0.f;
-    for (int c = 0; c < Cin; c += 4) {
-        float4 a[PX_T];
-#pragma unroll
-        for (int q = 0; q < PX_T; ++q) a[q] = *reinterpret_cast<const float4*>(s_t + (tid + q * 128) * pitch + c);
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-            const float* wp = s_w + (c + cc) * CO;
-#pragma unroll
-            for (int o4 = 0; o4 < CO / 4; ++o4) {
-                const float4 wv = *reinterpret_cast<const float4*>(wp + o4 * 4);
-#pragma unroll
-                for (int q = 0; q < PX_T; ++q) {
-                    const float av = cc == 0 ? a[q].x : cc == 1 ? a[q].y : cc == 2 ? a[q].z : a[q].w;
-                    fma4(&acc[q][o4 * 4], av, wv);
-                }
-            }
-        }
-    }
-    __syncthreads();                                    // every thread is done reading the input tile
-    const ActSel asel = codd_act_sel(p.act);
-    constexpr int OP = CO + 4;
-#pragma unroll
-    for (int q = 0; q < PX_T; ++q) {
-        const int px = tid + q * 128;
-        const size_t gp = min(pix0 + px, npix - 1);
-        const float rb = (p.res && p.res_bcast) ? __ldg(p.res + gp * p.ldr) : 0.f;
-#pragma unroll
-        for (int o4 = 0; o4 < CO / 4; ++o4) {
-            float v[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int ce = o4 * 4 + e;
-                float t = acc[q][ce] + (p.bias ? __ldg(p.bias + ce) : 0.f);
-                const float rv = p.res ? (p.res_bcast ? rb : __ldg(p.res + gp * p.ldr + ce)) : 0.f;
-                v[e] = p.res_after ? codd_act_apply(asel, t, ce) + rv : codd_act_apply(asel, t + rv, ce);
-            }
-            *reinterpret_cast<float4*>(s_t + px * OP + o4 * 4) = make_float4(v[0], v[1], v[2], v[3]);
-        }
-    }
-    __syncthreads();
-    for (int q = tid; q < TILE * (CO / 4); q += 128) {
-        const int px = q / (CO / 4), c4 = q - px * (CO / 4);
-        if (pix0 + px < npix)
-            *reinterpret_cast<float4*>(p.out + (pix0 + px) * p.ldo + c4 * 4) = *reinterpret_cast<const float4*>(s_t + px * OP + c4 * 4);
-    }
-}
-
-template <int CO, int PX_T>
-int launch_pointwise_staged(const ConvP& p, cudaStream_t s) {
-    const size_t npix = (size_t)p.N * p.H * p.W;
-    const int Cin = p.C0 + p.C1;
-    const int tile_floats = 128 * PX_T * ((Cin + 4) > (CO + 4) ? (Cin + 4) : (CO + 4));
-    const size_t smem = ((size_t)Cin * CO + tile_floats) * sizeof(float);
-    static CoddDeviceOnce once;
-    if (int rc = codd_once_per_device(once, [&] {
-            return cudaFuncSetAttribute(pointwise_staged_kernel<CO, PX_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        }))
-        return rc;
-    const unsigned grid = (unsigned)((npix + 128 * PX_T - 1) / (128 * PX_T));
-    pointwise_staged_kernel<CO, PX_T><<<grid, 128, smem, s>>>(p, npix);
-    CODD_RETURN_IF_CUDA_ERROR();
-    return 0;
-}
+// (A shared-memory-staged 1x1 variant was tried in round 2 and measured SLOWER on the GPU: 1.29 ms vs 0.81 ms per step
+// for the 32->16 full-resolution layers — the extra shared-memory round trip costs more than the uncoalesced
+// 64-byte-stride loads it removes.  Removed; see DESIGN.md.)
 
 template <int CO, int PX_T>
 int launch_pointwise(const ConvP& p, cudaStream_t s) {
@@ -755,15 +656,6 @@ int conv_dispatch(const ConvP& p, const codd_conv_desc* d, cudaStream_t s) {
     if (kh == 1 && kw == 1 && sh == 1 && sw == 1 && d->ph == 0 && d->pw == 0 && d->ho == d->h && d->wo == d->w) {
         const bool vec_ok = p.vec0 && (d->c0 % 4 == 0) && (p.C1 == 0 || (p.vec1 && d->c1 % 4 == 0)) &&
                             codd_aligned16(p.out) && (d->ldo % 4 == 0) && (d->c0 + p.C1) * 32 * 4 <= 48 * 1024;
-#ifdef CODD_DIAG
-        static const bool pw_staged = getenv("CODD_PW_STAGED") && atoi(getenv("CODD_PW_STAGED")) != 0;   // experimental
-#else
-        constexpr bool pw_staged = false;
-#endif
-        if (pw_staged && vec_ok && (p.Cout == 16 || p.Cout == 32) && (d->c0 + p.C1) <= 64 && (d->ldr % 4 == 0 || !p.res || p.res_bcast)) {
-            if (p.Cout == 16) return launch_pointwise_staged<16, 4>(p, s);
-            return launch_pointwise_staged<32, 2>(p, s);
-        }
         if (vec_ok && p.Cout <= 16) return launch_pointwise<16, 4>(p, s);
         if (vec_ok && p.Cout <= 24) return launch_pointwise<24, 2>(p, s);
         if (vec_ok && p.Cout <= 32) return launch_pointwise<32, 2>(p, s);
@@ -880,7 +772,7 @@ extern "C" int codd_nhwc_to_nchw(const float* in, int ldi, int n, int h, int w, 
         const size_t smem = (size_t)cc * (TR_PIX + 1) * sizeof(float);
         static CoddDeviceOnce once;
         if (int rc = codd_once_per_device(once, [&] {
-                return cudaFuncSetAttribute(nhwc_to_nchw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+                return codd_max_dynamic_smem(nhwc_to_nchw_kernel);
             }))
             return rc;
         nhwc_to_nchw_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(in, ldi, hw, cc, c, c0, out);

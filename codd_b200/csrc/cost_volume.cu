@@ -380,7 +380,7 @@ extern "C" int codd_cost_volume(const float* tile_l, const float* tile_r, int n,
     else { kern = cost_volume_kernel<false, true>; slot = 2; }
     // opt in to the full 227 KB once per device (the per-launch request stays `smem`)
     if (int rc = codd_once_per_device(once[slot], [&] {
-            return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            return codd_max_dynamic_smem(kern);
         }))
         return rc;
     kern<<<grid, block, smem, s>>>(p);
@@ -430,7 +430,7 @@ extern "C" int codd_cost_volume_pyramid(int levels, const float* const* tile_l, 
     else if (want_cv) { kern = cost_volume_pyramid_kernel<true, false>; slot = 1; }
     else { kern = cost_volume_pyramid_kernel<false, true>; slot = 2; }
     if (int rc = codd_once_per_device(once[slot], [&] {
-            return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            return codd_max_dynamic_smem(kern);
         }))
         return rc;
     kern<<<(unsigned)nblocks, CV_MAXW * 32, smem, (cudaStream_t)stream>>>(P);

@@ -528,11 +528,34 @@ extern "C" int codd_tile_warp_cost(const float* fea_l, int ldfl, const float* fe
                                stream);
 }
 
+// second decomposition (tile_warp.cu): TMA-staged window, planes sharing a register window, tensor-core `decrease`
+int codd_tile_warp_cost2(const float* fea_l, int ldfl, const float* fea_r, int ldfr, int c, const float* cur, int ldc,
+                         const float* prev, int ldp, const float* dec_w, const float* dec_b, int n, int h, int w,
+                         float* aug, int ldaug, float* raw_cv, void* stream);
+
 extern "C" int codd_tile_warp_cost_nhwc(const float* fea_l, int ldfl, const float* fea_r, int ldfr, int c,
                                         const float* cur, int ldc, const float* prev, int ldp, const float* dec_w,
                                         const float* dec_b, int n, int h, int w, float* aug, int ldaug, float* raw_cv,
                                         void* stream) {
     if (ldfr <= 0) return CODD_E_BADARG;
+    bool v2 = true;
+#ifdef CODD_DIAG
+    static const bool force_v1 = getenv("CODD_K4_V1") && atoi(getenv("CODD_K4_V1")) != 0;   // A/B against the first kernel
+    v2 = !force_v1;
+#endif
+    if (v2) {
+        // same argument checks as the first kernel, then the TMA / tensor-core kernel for C in {16, 24, 32}
+        if (!fea_l || !fea_r || !cur || !dec_w || !dec_b || !aug || n <= 0 || h <= 0 || w <= 0) return CODD_E_BADARG;
+        if (c <= 0 || c % 4 != 0 || ldfl < c || ldfl % 4 || ldc < 16 || ldc % 4 || ldfr < c || ldfr % 4) return CODD_E_SHAPE;
+        if (prev && (ldp < 16 || ldp % 4 || (h & 1) || (w & 1))) return CODD_E_SHAPE;
+        if (ldaug < (prev ? 64 : 32) || ldaug % 4) return CODD_E_SHAPE;
+        if (!codd_aligned16(fea_l) || !codd_aligned16(fea_r) || !codd_aligned16(cur) || !codd_aligned16(aug) ||
+            !codd_aligned16(dec_b) || !codd_aligned16(dec_w) || (prev && !codd_aligned16(prev)))
+            return CODD_E_ALIGN;
+        const int rc = codd_tile_warp_cost2(fea_l, ldfl, fea_r, ldfr, c, cur, ldc, prev, ldp, dec_w, dec_b, n, h, w, aug,
+                                            ldaug, raw_cv, stream);
+        if (rc != CODD_E_UNSUPPORTED) return rc;
+    }
     return tile_warp_cost_impl(fea_l, ldfl, fea_r, ldfr, c, cur, ldc, prev, ldp, dec_w, dec_b, n, h, w, aug, ldaug, raw_cv,
                                stream);
 }

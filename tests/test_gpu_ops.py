@@ -122,27 +122,6 @@ def test_conv3x3_head1_residual_relu(ops):
     torch.testing.assert_close(back(ops, out), ref, rtol=CONV_RTOL, atol=CONV_ATOL)
 
 
-@pytest.mark.skipif(os.environ.get("CODD_PW_STAGED") != "1",
-                    reason="experimental shared-memory-staged 1x1 kernel: run the suite with CODD_PW_STAGED=1")
-@pytest.mark.parametrize("c0,c1,cout,n,h,w", [(16, 16, 16, 2, 37, 71), (32, 0, 16, 1, 64, 130), (32, 32, 32, 2, 19, 33),
-                                               (24, 16, 32, 1, 7, 9), (16, 0, 16, 3, 50, 50)])
-def test_pointwise_staged(ops, c0, c1, cout, n, h, w):
-    """With CODD_PW_STAGED=1 every eligible 1x1 conv of the process runs the staged kernel; this covers ragged tiles,
-    two concatenated sources, a broadcast residual and the leaky epilogue against F.conv2d."""
-    from codd_b200.lib import ACT_LEAKY
-    g = gen(c0 * 7 + c1 + cout)
-    a = torch.randn(n, c0, h, w, generator=g)
-    b2 = torch.randn(n, c1, h, w, generator=g) if c1 else None
-    wt = torch.randn(cout, c0 + c1, 1, 1, generator=g) / (c0 + c1) ** 0.5
-    bias = torch.randn(cout, generator=g)
-    res = torch.randn(n, 1, h, w, generator=g)
-    x = a if b2 is None else torch.cat([a, b2], 1)
-    ref = F.leaky_relu(F.conv2d(x, wt, bias) + res, 0.2)
-    out = ops.conv2d(nhwc(ops, a), ops.pack_conv_weight(wt).cuda(), bias.cuda(), cout, 1, act=ACT_LEAKY,
-                     x2=None if b2 is None else nhwc(ops, b2), residual=nhwc(ops, res), res_bcast=True)
-    torch.testing.assert_close(back(ops, out), ref, rtol=CONV_RTOL, atol=CONV_ATOL)
-
-
 def test_tile_conv_right_stride41(ops):
     """initialization.py:121-124: stride (4,1) over the input zero-padded 3 columns on the right."""
     from codd_b200.lib import ACT_LEAKY
@@ -303,7 +282,9 @@ def _warp_inputs(n, c, h, w, seed, dmax):
 
 @pytest.mark.parametrize("right_layout", ["nhwc", "planar"])
 @pytest.mark.parametrize("n,c,h,w,dmax", [(1, 16, 4, 6, 10.0), (2, 24, 6, 18, 40.0), (1, 32, 2, 34, 90.0),
-                                          (1, 16, 10, 16, 30.0), (1, 16, 36, 8, 20.0)])
+                                          (1, 16, 10, 16, 30.0), (1, 16, 36, 8, 20.0),
+                                          # hypotheses of one CTA too far apart to stage: read in place from global memory
+                                          (1, 16, 6, 80, 310.0), (1, 32, 4, 48, 180.0), (2, 24, 2, 64, 250.0)])
 def test_tile_warp_cost(ops, n, c, h, w, dmax, right_layout):
     """right_layout: NHWC right features are gathered in place (codd_tile_warp_cost_nhwc); a plain contiguous NCHW
     tensor takes the planar entry point (shared-memory staged window / per-channel gathers)."""
@@ -330,6 +311,34 @@ def test_tile_warp_cost(ops, n, c, h, w, dmax, right_layout):
     aug0 = back(ops, aug0)
     assert aug0.shape[1] == 32 and torch.equal(aug0[:, :16], cur)
     torch.testing.assert_close(aug0[:, 16:], dec(raw_cur), rtol=CONV_RTOL, atol=CONV_ATOL)
+
+
+@pytest.mark.parametrize("n,c,h,w,dmax", [(2, 16, 8, 40, 24), (1, 24, 6, 18, 12), (1, 32, 4, 20, 9), (1, 16, 34, 16, 60)])
+def test_tile_warp_cost_integer_hypotheses(ops, n, c, h, w, dmax):
+    """What the network feeds K4 as the CURRENT set: arg-min initialisations (integer disparity, zero slants,
+    initialization.py:179-183).  Then ix sits within an ulp of an integer and floor() jitters by one independently per
+    plane, so the planes do NOT share one 4-column window: the kernel must detect that and still be bit-exact."""
+    g = gen(c * 100 + h + w)
+    fl, fr, cur, prev, dw, db = _warp_inputs(n, c, h, w, c + h + w + 1, float(dmax))
+    cur[:, 0] = torch.randint(0, dmax + 1, (n, h, w), generator=g).float()
+    cur[:, 1:3] = 0.0
+    prev[0, 0, : h // 4] = torch.randint(0, dmax // 2 + 1, (h // 4, w // 2), generator=g).float()   # some integer tiles here too
+    prev[0, 1:3, : h // 4] = 0.0
+    fnorm = F.pixel_unshuffle(O.l1_over_channels(fl), 4)
+    up_prev = O.plane_upsample(prev, 2, 2)
+    raw_cur = torch.cat([fnorm, O.tile_warp_cost(cur[:, :3], fl, fr, direct=True)], 1)
+    raw_prev = torch.cat([fnorm, O.tile_warp_cost(up_prev[:, :3], fl, fr, direct=True)], 1)
+    # the oracle's explicit-arithmetic form is itself bit-identical to F.grid_sample (tests/test_oracle_vs_reference.py)
+    assert torch.equal(raw_cur[:, 16:], O.tile_warp_cost(cur[:, :3], fl, fr, direct=False))
+    for layout in ("nhwc", "planar"):
+        aug, raw = ops.tile_warp_cost(nhwc(ops, fl), nhwc(ops, fr), nhwc(ops, cur), nhwc(ops, prev), dw.cuda().contiguous(),
+                                      db.cuda(), want_raw=True, force_nhwc=layout == "nhwc")
+        raw = back(ops, raw)
+        assert torch.equal(raw[:, :64], raw_cur), f"{layout}: integer current set not bit-identical"
+        assert torch.equal(raw[:, 64:], raw_prev), f"{layout}: previous set not bit-identical"
+        dec = lambda r: F.leaky_relu(F.conv2d(r, dw, db), 0.2)
+        torch.testing.assert_close(back(ops, aug)[:, 16:32], dec(raw_cur), rtol=CONV_RTOL, atol=CONV_ATOL)
+        torch.testing.assert_close(back(ops, aug)[:, 48:], dec(raw_prev), rtol=CONV_RTOL, atol=CONV_ATOL)
 
 
 def test_tile_warp_cost_golden(ops, golden_small):

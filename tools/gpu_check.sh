@@ -4,7 +4,6 @@
 #   gpurun --timeout 150 -- 'bash tools/gpu_check.sh quick'     ring / conv unit tests + conv probe            (~15 s run)
 #   gpurun --timeout 400 -- 'bash tools/gpu_check.sh full'      full -m gpu suite, smoke(), default bench      (~60 s run)
 #   gpurun --timeout 600 -- 'bash tools/gpu_check.sh profile'   step traffic table + launch list + ring ncu    (~150 s run)
-#   gpurun --timeout 300 -- 'bash tools/gpu_check.sh staged'    the experimental staged 1x1 kernel: suite + bench with it on
 set -u
 mkdir -p gpurun_out
 case "${1:-quick}" in
@@ -32,11 +31,5 @@ PY
           -o gpurun_out/ring$c python tools/ring_one.py 2>&1 | tail -1
     done
     echo "then here: python tools/traffic_table.py gpurun_out/step.csv gpurun_out/tags.json profiles/traffic_rNN.json" ;;
-  staged)
-    CODD_PW_STAGED=1 timeout 200 python -m pytest tests/test_gpu_ops.py tests/test_gpu_hitnet.py -m gpu -x -q 2>&1 | tail -4
-    for v in 0 1; do
-      CODD_PW_STAGED=$v timeout 100 python bench.py --steps 20 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('staged=$v', d['value'], d['ms_per_step'])"
-    done ;;
-  *) echo "usage: $0 quick|full|profile|staged"; exit 2 ;;
+  *) echo "usage: $0 quick|full|profile"; exit 2 ;;
 esac

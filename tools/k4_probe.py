@@ -21,16 +21,21 @@ def main():
     dec_w = torch.randn(16, 64, device=dev, generator=g) / 8
     dec_b = torch.zeros(16, device=dev)
     yy, xx = torch.meshgrid(torch.arange(h, device=dev).float(), torch.arange(w, device=dev).float(), indexing="ij")
-    for kind in ("smooth", "noisy"):
+    kinds = os.environ.get("K4_KINDS", "init,smooth,noisy").split(",")
+    for kind in kinds:
         cur = torch.zeros(n, 16, h, w, device=dev)
         prev = torch.zeros(n, 16, h // 2, w // 2, device=dev)
-        if kind == "smooth":
+        if kind in ("smooth", "init"):
             cur[:, 0] = 60 + 40 * torch.sin(xx / 37) * torch.cos(yy / 23)
             prev[:, 0] = (cur[:, 0, ::2, ::2] + 0.7) / 2
+            prev[:, 1:3] = torch.randn(n, 2, h // 2, w // 2, device=dev, generator=g) * 0.05
         else:
             cur[:, 0] = torch.rand(n, h, w, device=dev, generator=g) * 190
             prev[:, 0] = torch.rand(n, h // 2, w // 2, device=dev, generator=g) * 95
         cur[:, 1:3] = torch.randn(n, 2, h, w, device=dev, generator=g) * 0.2
+        if kind == "init":       # what the network feeds: arg-min initialisations (integer disparity, zero slants)
+            cur[:, 0] = cur[:, 0].round()
+            cur[:, 1:3] = 0.0
         cur_n, prev_n = ops.to_nhwc(cur), ops.to_nhwc(prev)
         for _ in range(3):
             ops.tile_warp_cost(fl, fr, cur_n, prev_n, dec_w, dec_b)
