@@ -185,23 +185,37 @@ struct W2Meta {
     int staged;
 };
 
+// Window producer, step 1: ISSUE the load of one plane hypothesis per lane (lane < 16: current hypothesis of tile
+// j0 + lane; lane >= 16: previous-level hypothesis under tile j0 + lane - 16).  Nothing here consumes the loaded value,
+// so the warp does not wait on memory before the CTA's early barrier.
 template <int NSETS>
-__device__ __forceinline__ void w2_item_hyps(const W2P& p, int n, int i, int j0, int lane, float& d, float& sl) {
-    // lane < 16: current hypothesis of tile j0 + lane; lane >= 16: up-sampled previous hypothesis of tile j0 + lane - 16
+__device__ __forceinline__ float4 w2_item_hyps_load(const W2P& p, int n, int i, int j0, int lane) {
+    const int j = j0 + (lane & 15);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < p.w) {
+        if (lane < 16) {
+            v = ldg4(p.cur + (((size_t)n * p.h + i) * p.w + j) * p.ldc);
+        } else if (NSETS == 2) {
+            const int hp = p.h >> 1, wp = p.w >> 1;
+            v = ldg4(p.prev + (((size_t)n * hp + (i >> 1)) * wp + (j >> 1)) * p.ldp);
+        }
+    }
+    return v;
+}
+// step 2: disparity at the tile centre and |dx| + |dy| of that plane (sl < 0: no plane on this lane)
+template <int NSETS>
+__device__ __forceinline__ void w2_item_hyps(const W2P& p, const float4& v, int i, int j0, int lane, float& d, float& sl) {
     const int j = j0 + (lane & 15);
     d = 0.f;
-    sl = -1.f;                 // "no plane here"
+    sl = -1.f;
     if (j >= p.w) return;
     if (lane < 16) {
-        const float4 c4 = ldg4(p.cur + (((size_t)n * p.h + i) * p.w + j) * p.ldc);
-        d = c4.x;
-        sl = fabsf(c4.y) + fabsf(c4.z);
+        d = v.x;
+        sl = fabsf(v.y) + fabsf(v.z);
     } else if (NSETS == 2) {
-        const int hp = p.h >> 1, wp = p.w >> 1;
-        const float4 q4 = ldg4(p.prev + (((size_t)n * hp + (i >> 1)) * wp + (j >> 1)) * p.ldp);
         const float cx = (float)(j & 1) - 0.5f, cy = (float)(i & 1) - 0.5f;
-        d = __fmul_rn(__fadd_rn(__fadd_rn(q4.x, __fmul_rn(cx, q4.y)), __fmul_rn(cy, q4.z)), 2.f);
-        sl = fabsf(q4.y) + fabsf(q4.z);
+        d = __fmul_rn(__fadd_rn(__fadd_rn(v.x, __fmul_rn(cx, v.y)), __fmul_rn(cy, v.z)), 2.f);
+        sl = fabsf(v.y) + fabsf(v.z);
     }
 }
 
@@ -270,12 +284,12 @@ __global__ void __launch_bounds__(W2_THREADS, 2) tile_warp_cost2_kernel(const __
     __shared__ __align__(16) float s_part[4][NSETS][W2_TILES][20];   // per pixel-row partial sums of `decrease` (padded)
     __shared__ __align__(16) uint32_t s_wh[16][68], s_wl[16][68];   // `decrease` weights [co][ci] as tf32 hi / lo parts
     __shared__ W2Meta s_meta;
-    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ __align__(8) unsigned long long s_bar, s_bar_w;     // window landed / `decrease` weights staged
     extern __shared__ __align__(128) float4 w2_dyn[];
     float* s_win = reinterpret_cast<float*>(w2_dyn);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t bar = w2_s32(&s_bar);
+    const uint32_t bar = w2_s32(&s_bar), bar_w = w2_s32(&s_bar_w);
     const int j0 = blockIdx.x * W2_TILES, i = blockIdx.y, n = blockIdx.z;
     // warp = (pixel row yo, half of the strip): lane = 4 * (tile within the half) + xo
     const int yo = warp >> 1;
@@ -306,15 +320,22 @@ __global__ void __launch_bounds__(W2_THREADS, 2) tile_warp_cost2_kernel(const __
 #pragma unroll
         for (int c = 0; c < C / 2; ++c) lp[c] = make_float2(0.f, 0.f);
     }
+    float4 ph = make_float4(0.f, 0.f, 0.f, 0.f);
     if (warp == 0) {
         if (lane == 0) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_w), "n"(W2_THREADS));
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        __syncwarp();
-        float d, sl;
-        w2_item_hyps<NSETS>(p, n, i, j0, lane, d, sl);
-        w2_produce<C>(&tmap, p, n, i, j0, d, sl, &s_meta, s_win, bar, lane);
+        ph = w2_item_hyps_load<NSETS>(p, n, i, j0, lane);
+    }
+    // The only CTA-wide barrier before the output phase, placed where nobody waits on memory yet: it publishes the
+    // mbarrier.  From here on every warp runs on its own (set-up, window wait, channel loops).
+    __syncthreads();
+    if (warp == 0) {
+        float pd, psl;
+        w2_item_hyps<NSETS>(p, ph, i, j0, lane, pd, psl);
+        w2_produce<C>(&tmap, p, n, i, j0, pd, psl, &s_meta, s_win, bar, lane);
     }
 
     // ---- per-pixel sampling state of every set (compact: floor column and fraction per plane)
@@ -366,8 +387,10 @@ __global__ void __launch_bounds__(W2_THREADS, 2) tile_warp_cost2_kernel(const __
         const int co = tid >> 4, ci = (tid & 15) * 4;
         *reinterpret_cast<uint4*>(&s_wh[co][ci]) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<uint4*>(&s_wl[co][ci]) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        // split barrier (an mbarrier counting all threads): arrive now, wait right before the fragments are read, after
+        // the channel loops — by then every thread has arrived long ago and nobody waits
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_w) : "memory");
     }
-    __syncthreads();      // mbarrier initialised, window description and weights visible
 
     // ---- wait for the window
     {
@@ -382,6 +405,7 @@ __global__ void __launch_bounds__(W2_THREADS, 2) tile_warp_cost2_kernel(const __
                 : "memory");
         }
     }
+    // (the window description was written by the thread that armed the mbarrier, before it did: visible after the wait)
     const int xlo = s_meta.xlo, rlo = s_meta.rlo, wc = s_meta.wc;
     const bool win_staged = s_meta.staged != 0;
     const bool rows_in = y0 >= rlo && y0 + (two_rows ? 1 : 0) < rlo + s_meta.rwin;
@@ -438,10 +462,42 @@ __global__ void __launch_bounds__(W2_THREADS, 2) tile_warp_cost2_kernel(const __
         }
     }
 
+    // ---- output phase, part 1 (its global loads travel behind the tensor-core tail): one float4 granule per thread of the
+    // augmented hypothesis tensor [cur | cur_cv | up_prev | prev_cv] of the strip's 16 tiles
+    constexpr int nf4 = NSETS * 8;            // float4 granules per tile
+    static_assert(W2_TILES * nf4 <= W2_THREADS, "one output granule per thread");
+    const int ot = tid / nf4, of = tid - ot * nf4;
+    const int ojj = j0 + ot;
+    const bool oon = tid < W2_TILES * nf4 && ojj < p.w;
+    const size_t otpix = ((size_t)n * p.h + i) * p.w + ojj;
+    float4 ov = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (oon) {
+        if (of < 4) {
+            ov = ldg4(p.cur + otpix * p.ldc + of * 4);
+        } else if (of < 8 || of >= 12) {
+            ov = ldg4(p.dec_b + (of & 3) * 4);
+        } else {
+            const int hp = p.h >> 1, wp = p.w >> 1;
+            ov = ldg4(p.prev + (((size_t)n * hp + (i >> 1)) * wp + (ojj >> 1)) * p.ldp + (of - 8) * 4);
+        }
+    }
+
     // ---- `decrease` on the tensor cores.  A rows 0..7: set 0 of the warp's 8 tiles, rows 8..15: the last set;
     // this warp contributes the 16 features of its pixel row yo (two k-steps of 8).  B fragments: k-step s covers
     // feature blocks q = 2s (k index t) and 2s+1 (t + 4), feature index ci = 16 q + 4 yo + xo; n-tile nt covers
     // output channels 8 nt + g.
+    {
+        uint32_t done = 0;      // `decrease` weights of every thread are in shared memory
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(bar_w), "r"(0)
+                : "memory");
+        }
+    }
     {
         const int g = lane >> 2, t = lane & 3;
         float acc[2][4];
@@ -482,36 +538,23 @@ __global__ void __launch_bounds__(W2_THREADS, 2) tile_warp_cost2_kernel(const __
     }
     __syncthreads();
 
-    // ---- write the augmented hypothesis tensor: [cur | cur_cv | up_prev | prev_cv]
-    constexpr int nf4 = NSETS * 8;  // float4 granules per tile
-    for (int o = tid; o < W2_TILES * nf4; o += W2_THREADS) {
-        const int t = o / nf4, f = o - t * nf4;
-        const int jj = j0 + t;
-        if (jj >= p.w) continue;
-        const size_t tpix = ((size_t)n * p.h + i) * p.w + jj;
-        float4 v;
-        if (f < 4) {
-            v = ldg4(p.cur + tpix * p.ldc + f * 4);
-        } else if (f < 8 || f >= 12) {
-            const int s = f < 8 ? 0 : NSETS - 1, co = (f & 3) * 4;
-            const float4 bias = ldg4(p.dec_b + co);
-            float r[4] = {bias.x, bias.y, bias.z, bias.w};
+    // ---- output phase, part 2
+    if (oon) {
+        if (of >= 4 && (of < 8 || of >= 12)) {
+            const int s = of < 8 ? 0 : NSETS - 1, co = (of & 3) * 4;
+            float r[4] = {ov.x, ov.y, ov.z, ov.w};       // bias
 #pragma unroll
             for (int yy = 0; yy < 4; ++yy) {          // fixed order: deterministic
-                const float4 q = *reinterpret_cast<const float4*>(&s_part[yy][s][t][co]);
+                const float4 q = *reinterpret_cast<const float4*>(&s_part[yy][s][ot][co]);
                 r[0] += q.x; r[1] += q.y; r[2] += q.z; r[3] += q.w;
             }
-            v = make_float4(codd_act(r[0], CODD_ACT_LEAKY, 0), codd_act(r[1], CODD_ACT_LEAKY, 0),
-                            codd_act(r[2], CODD_ACT_LEAKY, 0), codd_act(r[3], CODD_ACT_LEAKY, 0));
-        } else {
-            const int hp = p.h >> 1, wp = p.w >> 1;
-            v = ldg4(p.prev + (((size_t)n * hp + (i >> 1)) * wp + (jj >> 1)) * p.ldp + (f - 8) * 4);
-            if (f == 8) {
-                const float cx = (float)(jj & 1) - 0.5f, cy = (float)(i & 1) - 0.5f;
-                v.x = __fmul_rn(__fadd_rn(__fadd_rn(v.x, __fmul_rn(cx, v.y)), __fmul_rn(cy, v.z)), 2.f);
-            }
+            ov = make_float4(codd_act(r[0], CODD_ACT_LEAKY, 0), codd_act(r[1], CODD_ACT_LEAKY, 0),
+                             codd_act(r[2], CODD_ACT_LEAKY, 0), codd_act(r[3], CODD_ACT_LEAKY, 0));
+        } else if (of == 8) {
+            const float cx = (float)(ojj & 1) - 0.5f, cy = (float)(i & 1) - 0.5f;
+            ov.x = __fmul_rn(__fadd_rn(__fadd_rn(ov.x, __fmul_rn(cx, ov.y)), __fmul_rn(cy, ov.z)), 2.f);
         }
-        *reinterpret_cast<float4*>(p.aug + tpix * p.ldaug + f * 4) = v;
+        *reinterpret_cast<float4*>(p.aug + otpix * p.ldaug + of * 4) = ov;
     }
 }
 
