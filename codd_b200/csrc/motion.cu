@@ -231,13 +231,72 @@ struct GnP {
     float* out;            // [N,h,w,7]
 };
 
-__global__ void __launch_bounds__(128) se3_gn_step_kernel(GnP p) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int pix = blockIdx.x * 4 + warp;
-    if (pix >= p.N * p.h * p.w) return;
-    const int n = pix / (p.h * p.w);
-    const int rem = pix - n * p.h * p.w;
-    const int y = rem / p.w, x = rem - y * p.w;
+// Second version (round 2).  The first one gave every centre its own warp that read its 65 x 65 neighbours straight
+// from global memory: lane k fetched neighbour k's 128-byte embedding with eight 128-bit loads, every one of which touched
+// 32 different cache lines — ~256 L1 tag wavefronts per 32 (centre, neighbour) pairs, 1.2 G wavefronts per call, which
+// IS the 3.3 ms it took (the arithmetic is ~0.8 ms).  Now a CTA owns GN_CX = 8 horizontally adjacent centres (one warp
+// each), whose windows overlap by 57 of 65 columns; the union window is streamed through shared memory GN_ROWS rows at a
+// time (cp.async, double buffered): embeddings with a pitch of 36 floats (so the 128-bit reads of 8 neighbouring lanes hit
+// 8 different bank groups), the 7 per-neighbour scalars as separate rows.  Each neighbour record is fetched from L2 once
+// per CTA (8 centres) instead of once per centre, and the L1 data pipe sees 4 wavefronts per 128-bit load instead of 32.
+constexpr int GN_CX = 8;            // centres (= warps) per CTA
+constexpr int GN_ROWS = 4;          // window rows per stage
+constexpr int GN_MAXR = 32;         // largest radius the staged kernel handles (reference: 32)
+constexpr int GN_WMAX = 2 * GN_MAXR + GN_CX;      // 72 window columns per CTA
+constexpr int GN_AEP = 36;          // embedding pitch (floats)
+constexpr int GN_REC = GN_ROWS * GN_WMAX;         // records per stage
+constexpr int GN_STAGE_FLOATS = GN_REC * (GN_AEP + 8);      // embeddings + 7 scalar rows (+1 spare)
+
+__device__ __forceinline__ void gn_cp16(float* dst, const float* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void gn_cp4(float* dst, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+
+__global__ void __launch_bounds__(GN_CX * 32, 2) se3_gn_step_kernel(GnP p) {
+    extern __shared__ __align__(16) float gn_smem[];      // 2 stages
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n = blockIdx.z, y = blockIdx.y, xc0 = blockIdx.x * GN_CX;
+    const int x = xc0 + warp;
+    const bool on = x < p.w;
+    const int R = p.radius;
+    const int y0 = max(0, y - R), y1 = min(p.h - 1, y + R);
+    const int cx0 = max(0, xc0 - R), cx1 = min(p.w - 1, xc0 + GN_CX - 1 + R);     // CTA window columns
+    const int cw = cx1 - cx0 + 1;
+    const int nchunks = (y1 - y0 + GN_ROWS) / GN_ROWS;
+
+    auto stage_load = [&](int chunk, int buf) {
+        float* sb = gn_smem + buf * GN_STAGE_FLOATS;
+        float* s_ae = sb;
+        float* s_sc = sb + GN_REC * GN_AEP;
+        const int r0 = y0 + chunk * GN_ROWS;
+        const int rows = min(GN_ROWS, y1 - r0 + 1);
+        // embeddings: 8 x 16 bytes per record, consecutive threads on consecutive pieces (coalesced 128-byte rows)
+        for (int e = tid; e < rows * cw * 8; e += GN_CX * 32) {
+            const int rec = e >> 3, piece = e & 7;
+            const int rr = rec / cw, cc = rec - rr * cw;
+            const size_t q = ((size_t)n * p.h + r0 + rr) * p.w + cx0 + cc;
+            gn_cp16(s_ae + (rr * GN_WMAX + cc) * GN_AEP + piece * 4, p.ae + q * p.lda + piece * 4);
+        }
+        for (int e = tid; e < rows * cw; e += GN_CX * 32) {
+            const int rr = e / cw, cc = e - rr * cw;
+            const size_t q = ((size_t)n * p.h + r0 + rr) * p.w + cx0 + cc;
+            float* d = s_sc + rr * GN_WMAX + cc;
+            gn_cp4(d, p.depth + q);
+            gn_cp4(d + GN_REC, p.target + q * p.ldt);
+            gn_cp4(d + 2 * GN_REC, p.target + q * p.ldt + 1);
+            gn_cp4(d + 3 * GN_REC, p.target + q * p.ldt + 2);
+            gn_cp4(d + 4 * GN_REC, p.weight + q * p.ldw);
+            gn_cp4(d + 5 * GN_REC, p.weight + q * p.ldw + 1);
+            gn_cp4(d + 6 * GN_REC, p.weight + q * p.ldw + 2);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    stage_load(0, 0);
+
+    const int pix = (n * p.h + y) * p.w + min(x, p.w - 1);
     const float fx = __ldg(p.intr + n * 4), fy = __ldg(p.intr + n * 4 + 1), cx = __ldg(p.intr + n * 4 + 2), cy = __ldg(p.intr + n * 4 + 3);
     const SE3 T = se3_load(p.Ts + (size_t)pix * 7);
     float aei[32];
@@ -251,43 +310,61 @@ __global__ void __launch_bounds__(128) se3_gn_step_kernel(GnP p) {
     for (int i = 0; i < 21; ++i) Hm[i] = 0.f;
 #pragma unroll
     for (int i = 0; i < 6; ++i) g[i] = 0.f;
-    const int y0 = max(0, y - p.radius), y1 = min(p.h - 1, y + p.radius);
-    const int x0 = max(0, x - p.radius), x1 = min(p.w - 1, x + p.radius);
-    const int ww = x1 - x0 + 1, cnt = ww * (y1 - y0 + 1);
-    for (int k = lane; k < cnt; k += 32) {
-        const int yy = y0 + k / ww, xx = x0 + k % ww;
-        const size_t q = ((size_t)n * p.h + yy) * p.w + xx;
-        float d2 = 0.f;
-#pragma unroll
-        for (int c = 0; c < 32; c += 4) {
-            const float4 v = ldg4(p.ae + q * p.lda + c);
-            const float e0 = v.x * 0.125f - aei[c], e1 = v.y * 0.125f - aei[c + 1], e2 = v.z * 0.125f - aei[c + 2],
-                        e3 = v.w * 0.125f - aei[c + 3];
-            d2 += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
+    const int x0 = max(0, x - R), x1 = min(p.w - 1, x + R);      // this centre's columns
+    const int ww = x1 - x0 + 1, lc0 = x0 - cx0;
+
+    for (int chunk = 0; chunk < nchunks; ++chunk) {
+        const int buf = chunk & 1;
+        if (chunk + 1 < nchunks) {
+            stage_load(chunk + 1, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
-        const float aff = 1.f / (1.f + expf(d2));                      // sigmoid(-d2)
-        const float dj = __ldg(p.depth + q);
-        const V3 Xj = v3(dj * (((float)xx - cx) / fx), dj * (((float)yy - cy) / fy), dj);
-        const V3 Y = se3_act(T, Xj);
-        const float iz = 1.f / Y.z;
-        const float r0 = __ldg(p.target + q * p.ldt) - (fx * Y.x * iz + cx);
-        const float r1 = __ldg(p.target + q * p.ldt + 1) - (fy * Y.y * iz + cy);
-        const float r2 = __ldg(p.target + q * p.ldt + 2) - iz;
-        const float w0 = aff * __ldg(p.weight + q * p.ldw), w1 = aff * __ldg(p.weight + q * p.ldw + 1),
-                    w2 = aff * __ldg(p.weight + q * p.ldw + 2);
-        // rows of J = J_pi * [I | -[Y]x]
-        const float a = fx * iz, b = -fx * Y.x * iz * iz, c = fy * iz, e = -fy * Y.y * iz * iz, f = -iz * iz;
-        float J0[6] = {a, 0.f, b, b * Y.y, a * Y.z - b * Y.x, -a * Y.y};
-        float J1[6] = {0.f, c, e, -c * Y.z + e * Y.y, -e * Y.x, c * Y.x};
-        float J2[6] = {0.f, 0.f, f, f * Y.y, -f * Y.x, 0.f};
-        int idx = 0;
+        __syncthreads();
+        const float* s_ae = gn_smem + buf * GN_STAGE_FLOATS;
+        const float* s_sc = s_ae + GN_REC * GN_AEP;
+        const int r0 = y0 + chunk * GN_ROWS;
+        const int rows = min(GN_ROWS, y1 - r0 + 1);
+        const int cnt = on ? rows * ww : 0;
+        for (int k = lane; k < cnt; k += 32) {
+            const int rr = k / ww, cc = k - rr * ww;
+            const int yy = r0 + rr, xx = x0 + cc;
+            const int rec = rr * GN_WMAX + lc0 + cc;
+            const float* ap = s_ae + rec * GN_AEP;
+            float d2 = 0.f;
 #pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            g[i] += w0 * J0[i] * r0 + w1 * J1[i] * r1 + w2 * J2[i] * r2;
+            for (int c = 0; c < 32; c += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(ap + c);
+                const float e0 = v.x * 0.125f - aei[c], e1 = v.y * 0.125f - aei[c + 1], e2 = v.z * 0.125f - aei[c + 2],
+                            e3 = v.w * 0.125f - aei[c + 3];
+                d2 += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
+            }
+            const float aff = 1.f / (1.f + expf(d2));                      // sigmoid(-d2)
+            const float dj = s_sc[rec];
+            const V3 Xj = v3(dj * (((float)xx - cx) / fx), dj * (((float)yy - cy) / fy), dj);
+            const V3 Y = se3_act(T, Xj);
+            const float iz = 1.f / Y.z;
+            const float r0_ = s_sc[rec + GN_REC] - (fx * Y.x * iz + cx);
+            const float r1_ = s_sc[rec + 2 * GN_REC] - (fy * Y.y * iz + cy);
+            const float r2_ = s_sc[rec + 3 * GN_REC] - iz;
+            const float w0 = aff * s_sc[rec + 4 * GN_REC], w1 = aff * s_sc[rec + 5 * GN_REC], w2 = aff * s_sc[rec + 6 * GN_REC];
+            // rows of J = J_pi * [I | -[Y]x]
+            const float a = fx * iz, b = -fx * Y.x * iz * iz, c = fy * iz, e = -fy * Y.y * iz * iz, f = -iz * iz;
+            float J0[6] = {a, 0.f, b, b * Y.y, a * Y.z - b * Y.x, -a * Y.y};
+            float J1[6] = {0.f, c, e, -c * Y.z + e * Y.y, -e * Y.x, c * Y.x};
+            float J2[6] = {0.f, 0.f, f, f * Y.y, -f * Y.x, 0.f};
+            int idx = 0;
 #pragma unroll
-            for (int j = i; j < 6; ++j) Hm[idx++] += w0 * J0[i] * J0[j] + w1 * J1[i] * J1[j] + w2 * J2[i] * J2[j];
+            for (int i = 0; i < 6; ++i) {
+                g[i] += w0 * J0[i] * r0_ + w1 * J1[i] * r1_ + w2 * J2[i] * r2_;
+#pragma unroll
+                for (int j = i; j < 6; ++j) Hm[idx++] += w0 * J0[i] * J0[j] + w1 * J1[i] * J1[j] + w2 * J2[i] * J2[j];
+            }
         }
+        __syncthreads();       // the buffer is refilled two iterations later
     }
+    if (!on) return;
 #pragma unroll
     for (int i = 0; i < 21; ++i)
 #pragma unroll
@@ -431,11 +508,19 @@ extern "C" int codd_se3_gn_step(const float* Ts, const float* ae, int lda, const
                                 int radius, float lm, float ep, float* Ts_out, void* stream) {
     if (!Ts || !ae || !target || !weight || !depth || !intr || !Ts_out || n <= 0 || h <= 0 || w <= 0) return CODD_E_BADARG;
     if (lda < 32 || lda % 4 || ldt < 3 || ldw < 3 || radius < 0) return CODD_E_SHAPE;
+    if (radius > GN_MAXR || h > 65535 || n > 65535) return CODD_E_UNSUPPORTED;
     if (!codd_aligned16(ae)) return CODD_E_ALIGN;
     GnP p;
     p.Ts = Ts; p.ae = ae; p.lda = lda; p.target = target; p.ldt = ldt; p.weight = weight; p.ldw = ldw; p.depth = depth;
     p.intr = intr; p.N = n; p.h = h; p.w = w; p.radius = radius; p.lm = lm; p.ep = ep; p.out = Ts_out;
-    se3_gn_step_kernel<<<(unsigned)codd_ceil_div(n * h * w, 4), 128, 0, (cudaStream_t)stream>>>(p);
+    const size_t smem = 2 * (size_t)GN_STAGE_FLOATS * sizeof(float);
+    static CoddDeviceOnce once;
+    if (int rc = codd_once_per_device(once, [&] {
+            return cudaFuncSetAttribute(se3_gn_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        }))
+        return rc;
+    se3_gn_step_kernel<<<dim3((unsigned)codd_ceil_div(w, GN_CX), (unsigned)h, (unsigned)n), GN_CX * 32, smem,
+                         (cudaStream_t)stream>>>(p);
     CODD_RETURN_IF_CUDA_ERROR();
     return 0;
 }

@@ -104,3 +104,74 @@ def test_full_codd_full_size_properties():
     assert len(mem) == 3 and mem[1].shape == (1, 32, 144, 240) and mem[2].shape == (1, 576, 960)
     b = run()
     assert torch.equal(a, b), "full CODD forward is not deterministic"
+
+
+def test_evaluate_true_through_model_vs_metrics_oracle():
+    """model(..., evaluate=True, gt_*=...) on the GPU for a 3-frame full-CODD sequence (codd.py:313-355, 435-575): the
+    returned meters against oracle/metrics_oracle.py (pinned against the reference's utils) evaluated on the model's own
+    per-frame outputs (recorded from consistent_online_depth_estimation while the call runs)."""
+    import numpy as np
+    import codd_b200
+    from oracle import metrics_oracle as M
+    torch.manual_seed(3)
+    D, h, w, H, W, T = 64, 120, 180, 128, 192, 3
+    model = codd_b200.build_estimator(codd_b200.codd_full_config(D, 1)).cuda()
+    model.eval()
+    left, right = O.synth_pair(1, H, W, D, seed=11, kind="S")
+    lefts = [torch.roll(left, shifts=(t, 2 * t), dims=(2, 3)) for t in range(T)]
+    rights = [torch.roll(right, shifts=(t, 2 * t), dims=(2, 3)) for t in range(T)]
+    g = torch.Generator().manual_seed(5)
+    gt = torch.rand(1, T, 1, H, W, generator=g) * 70 - 3          # some invalid (<= 0) pixels
+    flow = torch.randn(1, T, 2, H, W, generator=g) * 1.5
+    dc = torch.randn(1, T, 1, H, W, generator=g)
+    occ = (torch.rand(1, T, 1, H, W, generator=g) > 0.85).float()  # gt_disp_occ: > 0 = occluded
+    intr = [float(W), float(W), W / 2.0, H / 2.0]
+    rng = (0.0, float(D))
+    metas = [[dict(min_disp=1, max_disp=D, ori_shape=(h, w), img_shape=(h, w), intrinsics=intr, disp_range=rng)]]
+    rec = []
+    inner = model.consistent_online_depth_estimation
+
+    def recording(l, r, m, state):
+        out = inner(l, r, m, state)
+        rec.append(dict(pred=out["pred_disp"].detach().clone(), Ts=None if out.get("Ts") is None else out["Ts"].detach().clone()))
+        return out
+
+    model.consistent_online_depth_estimation = recording
+    res = model(return_loss=False, rescale=True, evaluate=True, img=[torch.stack(lefts, 1).cuda()], img_metas=metas,
+                r_img=[torch.stack(rights, 1).cuda()], gt_disp=[gt.cuda()], gt_flow=[flow.cuda()],
+                gt_disp_change=[dc.cuda()], gt_disp_occ=[occ.cuda()])[0]
+    assert len(rec) == T and all(r["Ts"] is not None for r in rec[1:])
+    got = {k: float(v) for k, v in res.items()}
+
+    # ---- the reference's bookkeeping on the CPU, frame by frame
+    exp = {k: [] for k in ("epe", "th3", "tepe", "tepe_rel", "th1_tepe_rel", "th3_tepe", "flow_mag")}
+    sf = np.zeros(5)
+    prev = None
+    intr_np = np.array([intr], np.float32)
+    for t in range(T):
+        pred = rec[t]["pred"][:, :, :h, :w].cpu().numpy()
+        gtt = gt[:, t, :, :h, :w].numpy()
+        seg = (occ[:, t] <= 0)[:, :, :h, :w].float().numpy()
+        mask = M.valid_mask(gtt, rng, seg=seg)
+        do = M.disp_metrics(pred, gtt, mask)
+        if do["n"]:
+            exp["epe"].append(do["epe"]); exp["th3"].append(do["th3"])
+        if prev is not None:
+            to = M.temporal_metrics(prev["flow"], gtt, pred, seg, prev["gt"], prev["pred"], prev["mask"], rng)
+            exp["flow_mag"].append(to["flow_mag"])
+            if to["updated"]:
+                for k in ("tepe", "tepe_rel", "th1_tepe_rel", "th3_tepe"):
+                    exp[k].append(to[k])
+            # provided gt_disp_change: the reference uses entry [-2], i.e. the previous frame's (codd.py:519-540)
+            Ts = rec[t]["Ts"][:, :h, :w].cpu().numpy()
+            o = M.sceneflow_metrics(Ts, prev["pred"], intr_np, prev["flow"], dc[:, t - 1, :, :h, :w].numpy(), prev["gt"], rng,
+                                    seg=seg)
+            sf += np.array([o["n"], o["sum_sf"], o["sum_of"], o["n1_sf"], o["n1_of"]], np.float64)
+        prev = dict(flow=flow[:, t, :, :h, :w].numpy(), gt=gtt, pred=pred, mask=mask)
+    for k, v in exp.items():
+        assert v, k
+        assert got[k] == pytest.approx(float(np.mean(v)), rel=1e-6), k      # the meters come back as float32 tensors
+    assert got["count"] == sf[0] and sf[0] > 0
+    assert got["epe2d_scene_flow"] == pytest.approx(sf[1], rel=1e-4)
+    assert got["epe2d_optical_flow"] == pytest.approx(sf[2], rel=1e-4)
+    assert abs(got["1px_scene_flow"] - sf[3]) <= 3 and abs(got["1px_optical_flow"] - sf[4]) <= 3

@@ -81,9 +81,10 @@ def test_stereo_matching_vs_golden(which, golden_small, golden_big):
         agree = (got == ref).float().mean().item()
         differ = int((got != ref).sum())
         print(f"[{which}] level {k}: arg-min agreement {agree:.5f} ({differ} of {ref.numel()} differ)")
-        # end to end, the inputs of K1 differ from the reference's by conv rounding (~1e-6), which can
-        # flip near-ties; bit-exactness on identical inputs is asserted in test_gpu_ops.py
-        assert differ <= max(2, 0.05 * ref.numel())
+        # end to end, the inputs of K1 differ from the reference's by conv rounding (~1e-7), which can flip near-ties
+        # (measured: at most ONE tile per level on these fixtures, two in total at 576x960, profiles/parity_r02.json);
+        # bit-exactness on identical inputs is asserted in test_gpu_ops.py, the flips themselves are certified below
+        assert differ <= 2
     frac = parity_modulo_near_ties(m, sd, left, right, d, pred, torch.from_numpy(fx["pred_disp"]), f"[{which}]")
     assert frac >= 0.995
 

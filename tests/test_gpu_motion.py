@@ -93,3 +93,32 @@ def test_splat_warp(ops):
         dref = 210.0 / (zref + 1e-5)
         dref[dref > w] = 0.0
         torch.testing.assert_close(disp.cpu(), dref, rtol=1e-4, atol=1e-4)
+
+
+def test_splat_warp_crowded_pixels_exact_and_deterministic(ops):
+    """More than 32 points on one pixel (low-res feature warp at radius 4 after a converging motion): the
+    renderer must keep exactly the 8 nearest in z — like pytorch3d's points_per_pixel — whatever order the atomics land
+    in, and two runs must agree bit for bit."""
+    n, c, h, w = 1, 4, 16, 16
+    intr = torch.tensor([[30., 30., 8., 8.]])
+    depth = 2.0 + torch.rand(n, h, w, generator=g(31)) * 3
+    feat = torch.randn(n, c, h, w, generator=g(32))
+    Ts = rand_Ts(n, h, w, 33, 0.01)
+    # converge: pull every point toward the optical axis so that the central pixels collect most of the image
+    Ts[..., 0:2] = -0.7 * (torch.stack(torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")[::-1], -1).float()
+                           - 8.0).unsqueeze(0) * depth.unsqueeze(-1) / 30.0
+    radius = 6.0
+    ref, zref = M.splat_warp(Ts, depth, feat, intr, radius)
+    # crowding check on the oracle's own candidate count
+    X = M.se3_act(Ts, M.inv_project(depth, intr)).reshape(-1, 3)
+    u, v = 30 * X[:, 0] / X[:, 2] + 8, 30 * X[:, 1] / X[:, 2] + 8
+    s, r = 2.0 / 16, radius / h
+    most = max(int(((((u - (px + .5)) * s) ** 2 + ((v - (py + .5)) * s) ** 2) < r * r).sum()) for py in range(6, 10) for px in range(6, 10))
+    assert most > 32, most
+    outs = []
+    for _ in range(3):
+        out, zbuf, _ = ops.splat_warp(Ts.cuda(), depth.cuda(), intr.cuda(), ops.to_nhwc(feat.cuda()), radius)
+        outs.append((ops.to_nchw(out).cpu(), zbuf.cpu()))
+    assert all(torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1]) for o in outs[1:]), "not deterministic"
+    torch.testing.assert_close(outs[0][1], zref, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(outs[0][0], ref, rtol=1e-4, atol=1e-4)
