@@ -4,6 +4,11 @@ GPU; achieved algorithmic GB/s (SURVEY.md §8d byte counts) of the materialising
 arg-min variant, whole 5-level pyramid per measurement (ONE fused launch, codd_cost_volume_pyramid), CUDA events, L2 flushed between reps.
 
     python tools/sweep_cost_volume.py [--out profiles/cost_volume_sweep_rNN.json]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 tools/sweep_cost_volume.py ...
+
+Under torchrun the batch of 64 of BASELINE.json configs[4] is sharded 8 samples per rank (no collective on the data path);
+a row then reports the aggregate over ranks: bytes of all ranks / max-over-ranks time.  The fused variant is also given
+against its own roof, the fp32 add pipe (2 * 16 * D lane-adds per (tile, disparity) pair with 4j - d >= 0).
 """
 import argparse
 import json
@@ -24,7 +29,14 @@ def main():
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
-    dev = torch.device("cuda")
+    import torch.distributed as dist
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    sm_mhz = 1965.0
     peak = 6650.0
     try:
         peak = float(json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"])
@@ -54,14 +66,28 @@ def main():
                     if r >= 2:
                         ms.append(e0.elapsed_time(e1))
                 t = sorted(ms)[len(ms) // 2]
-                gbs = nbytes / (t * 1e-3) / 1e9
-                rows.append(dict(size=name, padded=[H, W], D=D, batch=a.batch,
-                                 variant="materialise+argmin" if want_cv else "fused argmin",
-                                 algorithmic_mb=round(nbytes / 1e6, 2), ms=round(t, 4), gbs=round(gbs, 1),
-                                 frac_of_measured_peak=round(gbs / peak, 4)))
-                print(rows[-1])
-    if a.out:
-        json.dump(dict(peak_gbs=peak, rows=rows), open(a.out, "w"), indent=1)
+                if world > 1:
+                    tt = torch.tensor([t], dtype=torch.float64, device=dev)
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                    t = tt.item()
+                gbs = world * nbytes / (t * 1e-3) / 1e9
+                row = dict(size=name, padded=[H, W], D=D, batch=a.batch * world, n_gpus=world,
+                           variant="materialise+argmin" if want_cv else "fused argmin",
+                           algorithmic_mb=round(world * nbytes / 1e6, 2), ms=round(t, 4), gbs=round(gbs, 1),
+                           gbs_per_gpu=round(gbs / world, 1), frac_of_measured_peak=round(gbs / world / peak, 4))
+                if not want_cv:
+                    lane_adds = 0
+                    for _, _, d, h, w in levels:
+                        lane_adds += 2 * 16 * a.batch * h * sum(min(d, 4 * j + 1) for j in range(w))
+                    row["fp32_roof_frac"] = round(lane_adds / (t * 1e-3) / (148 * 128 * sm_mhz * 1e6), 4)
+                rows.append(row)
+                if rank == 0:
+                    print(row)
+    if a.out and rank == 0:
+        json.dump(dict(peak_gbs=peak, n_gpus=world, batch_per_gpu=a.batch, fp32_peak="148 SMs x 128 lanes x 1965 MHz",
+                       rows=rows), open(a.out, "w"), indent=1)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
