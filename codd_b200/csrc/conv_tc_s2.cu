@@ -1,0 +1,405 @@
+// 4x4 / stride 2 / pad 1 convolution on the 5th-generation tensor cores (tcgen05, sm_100a), Cin = 16.
+//
+// Replaces the first layer of HITUNet's conv_down blocks at the two finest levels
+// (model/stereo/hitnet/backbone.py:8-14: Conv2d(inp, oup, 4, stride=2, padding=1) + LeakyReLU; down1 16->16 at
+// 576x960 -> 288x480, down2 16->24 at 288x480 -> 144x240).  On the fp32 CUDA cores (conv.cu, packed FFMA2) these two
+// launches took 1.03 ms of a 9.4 ms step at 10-15 % of the HBM roofline: 256 MACs per output and channel are
+// FMA-issue bound there, while the tensor pipe does them in a few hundred cycles per 128-pixel tile.
+//
+// Implicit GEMM, NHWC fp32 activations, M = 128 output pixels of one output row, N = Cout (padded to 16 / 32),
+// K = 16 input channels per filter tap, 16 taps:
+//   * input column of output xo and tap kx is xi = 2 xo + kx - 1: taps kx = 1, 3 read EVEN columns 2(xo + {0,1}),
+//     taps kx = 0, 2 read ODD columns 2(xo + {-1,0}) + 1.  The feature map is presented to TMA as a 5-D tensor
+//     {C, 2 (column parity), W/2, H, N}, so one box {16, 1, 136, 1, 1} delivers 136 same-parity pixels of one input row
+//     K-major into a 64-byte-swizzled slot; the two taps that share a parity are the SAME slot seen from a start address
+//     shifted by one pixel (the swizzle is a function of the address) — every input element is loaded once per
+//     output row, no im2col, and out-of-range coordinates (left / right / top / bottom padding) arrive as zeros;
+//   * a stage = the two parity slots of ONE input row (one ky); a tile consumes 4 stages; NBUF stages in flight;
+//   * precision 3xTF32 exactly as conv_tc.cu: pass A multiplies the raw fp32 stage (the MMA datapath reads the top 19
+//     bits = x_hi) by [w_hi | w_lo] (N = 2 NP), the split warps then rewrite the stage as x_lo = x - x_hi in place and
+//     pass B multiplies it by w_hi (N = NP), LAG stages behind pass A so the tensor pipe never waits for the split;
+//   * accumulators in TMEM (NACC tiles x 2 NP columns), epilogue warps read them with tcgen05.ld (lane = pixel), add
+//     the bias, apply the activation and store NHWC.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int S2_TW = 128;                 // output columns per tile (= MMA M)
+constexpr int S2_KC = 16;                  // input channels (K per tap)
+constexpr int S2_BOXP = 136;               // same-parity pixels per slot (129 needed, multiple of 8)
+constexpr uint32_t S2_ROWB = S2_KC * 4;    // bytes per pixel row of the K-major tile
+constexpr uint32_t S2_SLOT = 9 * 1024;     // slot pitch (136 * 64 = 8704 bytes used), 1024-aligned for the swizzle atom
+constexpr uint32_t S2_STAGE = 2 * S2_SLOT;
+constexpr int S2_EPI_THREADS = 128;
+constexpr int S2_SPLIT_THREADS = 256;
+constexpr int S2_THREADS = 64 + S2_EPI_THREADS + S2_SPLIT_THREADS;   // warps 0-7 split, 8-11 epilogue, 12 TMA, 13 MMA
+
+struct S2P {
+    const float* wpk;   // [2][16 taps][NP][16] fp32: pass 0 = tf32 hi, pass 1 = lo
+    const float* bias;
+    float* out;
+    int N, Ho, Wo, Cout, ldo, act;
+    int tilesX, ntiles;
+};
+
+__device__ __forceinline__ uint32_t s2_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void s2_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void s2_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void s2_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void s2_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!done) __nanosleep(32);   // a polling warp must not starve the working warps of its SM sub-partition
+    }
+}
+__device__ __forceinline__ void s2_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void s2_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void s2_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+template <bool ACC>
+__device__ __forceinline__ void s2_mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc) {
+    if (ACC) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.eq.u32 p, 1, 1;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.eq.u32 p, 1, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void s2_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+        "[%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor, K-major, SWIZZLE_64B (64-byte rows), as conv_tc.cu make_desc<16>
+__device__ __forceinline__ uint64_t s2_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);               // start address
+    d |= (uint64_t)1 << 16;                                 // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)((8 * S2_ROWB) >> 4) << 32;              // stride byte offset: 8-row group pitch
+    d |= (uint64_t)1 << 46;                                 // descriptor version (Blackwell)
+    d |= 4ull << 61;                                        // SWIZZLE_64B
+    return d;
+}
+// byte offset of 16-byte chunk j of row r inside a K-major SWIZZLE_64B tile whose base is 1024-aligned
+__device__ __forceinline__ uint32_t s2_swz(int r, int j) {
+    const uint32_t off = (uint32_t)r * S2_ROWB + (uint32_t)j * 16u;
+    return off ^ (((off >> 7) & 3u) << 4);
+}
+
+// NBUF stage buffers, NACC accumulator buffers, pass B trails pass A by LAG stages (LAG < NBUF).
+template <int NP, int NBUF, int NACC, int LAG>
+__global__ void __launch_bounds__(S2_THREADS, 1) conv4x4s2_tc_kernel(const __grid_constant__ CUtensorMap tmap, S2P p) {
+    static_assert(LAG >= 1 && LAG < NBUF && NACC >= 2, "pipeline depths");
+    constexpr uint32_t ACC_COLS = 2 * NP;          // per tile: [0,NP) = x_hi*w_hi + x_lo*w_hi, [NP,2NP) = x_hi*w_lo
+    constexpr uint32_t TMEM_COLS = (NACC * ACC_COLS <= 128) ? 128u : (NACC * ACC_COLS <= 256) ? 256u : 512u;
+    constexpr uint32_t B_TAP = 2 * NP * S2_ROWB;   // per tap: NP rows of w_hi followed by NP rows of w_lo
+    constexpr uint32_t IDESC_BASE = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 4) << 24);   // f32 acc, tf32 x tf32, M = 128
+    constexpr uint32_t IDESC2 = IDESC_BASE | ((uint32_t)((2 * NP) >> 3) << 17);
+    constexpr uint32_t IDESC1 = IDESC_BASE | ((uint32_t)(NP >> 3) << 17);
+    constexpr uint32_t BOX_BYTES = S2_BOXP * S2_ROWB;
+
+    extern __shared__ uint8_t s2_smem_raw[];
+    __shared__ __align__(8) unsigned long long bars[4 * NBUF + 2 * NACC];
+    __shared__ uint32_t tmem_base_slot;
+
+    const uint32_t sbase = (s2_u32(s2_smem_raw) + 1023u) & ~1023u;
+    uint8_t* gbase = s2_smem_raw + (sbase - s2_u32(s2_smem_raw));
+    const uint32_t sB = sbase + NBUF * S2_STAGE;
+    uint8_t* gB = gbase + NBUF * S2_STAGE;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t bar0 = s2_u32(&bars[0]);
+    auto SBAR = [&](int kind, int b) { return bar0 + (uint32_t)(kind * NBUF + b) * 8u; };
+    auto ABAR = [&](int kind, int b) { return bar0 + (uint32_t)(4 * NBUF + kind * NACC + b) * 8u; };
+    enum { FULL = 0, EMPTY = 1, P12 = 2, LO = 3 };
+    enum { ACCF = 0, ACCE = 1 };
+
+    if (tid == 0) {
+        for (int b = 0; b < NBUF; ++b) {
+            s2_mbar_init(SBAR(FULL, b), 1);
+            s2_mbar_init(SBAR(EMPTY, b), 1);
+            s2_mbar_init(SBAR(P12, b), 1);
+            s2_mbar_init(SBAR(LO, b), S2_SPLIT_THREADS);
+        }
+        for (int b = 0; b < NACC; ++b) {
+            s2_mbar_init(ABAR(ACCF, b), 1);
+            s2_mbar_init(ABAR(ACCE, b), S2_EPI_THREADS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 13) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2_u32(&tmem_base_slot)),
+                     "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    // weights -> swizzled shared image (once per CTA): [tap][w_hi rows | w_lo rows][16]
+    for (int idx = tid; idx < 2 * 16 * NP * (S2_KC / 4); idx += S2_THREADS) {
+        const int j = idx % (S2_KC / 4);
+        const int r = (idx / (S2_KC / 4)) % NP;
+        const int pt = idx / ((S2_KC / 4) * NP);          // pass * 16 + tap
+        const float4 v = ldg4(p.wpk + ((size_t)pt * NP + r) * S2_KC + j * 4);
+        const int pass = pt >> 4, tap = pt & 15;
+        *reinterpret_cast<float4*>(gB + tap * B_TAP + s2_swz(r + pass * NP, j)) = v;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    s2_fence_before();
+    __syncthreads();
+    s2_fence_after();
+    const uint32_t tmem = tmem_base_slot;
+
+    // stage counter `it` = 4 * (tile index of this CTA) + ky
+    if (warp == 12) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int it = 0;
+            for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+                int q = t;
+                const int tx = q % p.tilesX;
+                q /= p.tilesX;
+                const int yo = q % p.Ho;
+                const int n = q / p.Ho;
+                const int xo0 = tx * S2_TW;
+                for (int ky = 0; ky < 4; ++ky, ++it) {
+                    const int sb = it % NBUF;
+                    s2_mbar_wait(SBAR(EMPTY, sb), (((uint32_t)(it / NBUF)) & 1u) ^ 1u);
+                    s2_mbar_expect_tx(SBAR(FULL, sb), 2 * BOX_BYTES);
+                    const int y = 2 * yo + ky - 1;
+                    // slot 0: even columns 2p, p from xo0 (taps kx = 1, 3); slot 1: odd columns 2p + 1, p from xo0 - 1 (kx = 0, 2)
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        asm volatile(
+                            "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+                            "%5, %6, %7}], [%2];" ::"r"(sbase + sb * S2_STAGE + (uint32_t)r * S2_SLOT),
+                            "l"(&tmap), "r"(SBAR(FULL, sb)), "r"(0), "r"(r), "r"(xo0 - r), "r"(y), "r"(n)
+                            : "memory");
+                    }
+                }
+            }
+        }
+    } else if (warp == 13) {
+        // ===================== MMA issuer =====================
+        if (codd_elect_one()) {
+            const uint64_t b_desc = s2_desc(sB);
+            // pass B of stage j: x_lo * w_hi into columns [0, NP) of its tile's accumulator
+            auto pass_b = [&](int j) {
+                const int sb = j % NBUF, ky = j & 3, ab = (j >> 2) % NACC;
+                s2_mbar_wait(SBAR(LO, sb), ((uint32_t)(j / NBUF)) & 1u);
+                s2_fence_after();
+                const uint64_t a_desc = s2_desc(sbase + sb * S2_STAGE);
+                const uint32_t d_tmem = tmem + (uint32_t)ab * ACC_COLS;
+#pragma unroll
+                for (int kx = 0; kx < 4; ++kx)
+#pragma unroll
+                    for (int k = 0; k < S2_KC / 8; ++k) {
+                        const uint32_t aoff = (uint32_t)((kx + 1) & 1) * S2_SLOT + (uint32_t)(kx >> 1) * S2_ROWB + k * 32;
+                        const uint32_t boff = (uint32_t)(ky * 4 + kx) * B_TAP + k * 32;
+                        s2_mma_tf32<true>(d_tmem, a_desc + (aoff >> 4), b_desc + (boff >> 4), IDESC1);
+                    }
+                s2_commit(SBAR(EMPTY, sb));                  // stage buffer free -> producer
+                if (ky == 3) s2_commit(ABAR(ACCF, ab));      // the tile's accumulators are complete -> epilogue
+            };
+            int it = 0;
+            for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+                for (int ky = 0; ky < 4; ++ky, ++it) {
+                    const int sb = it % NBUF, ti = it >> 2, ab = ti % NACC;
+                    s2_mbar_wait(SBAR(FULL, sb), ((uint32_t)(it / NBUF)) & 1u);
+                    if (ky == 0) s2_mbar_wait(ABAR(ACCE, ab), (((uint32_t)(ti / NACC)) & 1u) ^ 1u);
+                    s2_fence_after();
+                    const uint64_t a_desc = s2_desc(sbase + sb * S2_STAGE);
+                    const uint32_t d_tmem = tmem + (uint32_t)ab * ACC_COLS;
+                    // pass A: x_hi * [w_hi | w_lo] (raw fp32 stage: the MMA reads the top 19 bits)
+#pragma unroll
+                    for (int kx = 0; kx < 4; ++kx)
+#pragma unroll
+                        for (int k = 0; k < S2_KC / 8; ++k) {
+                            const uint32_t aoff = (uint32_t)((kx + 1) & 1) * S2_SLOT + (uint32_t)(kx >> 1) * S2_ROWB + k * 32;
+                            const uint32_t boff = (uint32_t)(ky * 4 + kx) * B_TAP + k * 32;
+                            if (ky == 0 && kx == 0 && k == 0)
+                                s2_mma_tf32<false>(d_tmem, a_desc + (aoff >> 4), b_desc + (boff >> 4), IDESC2);
+                            else
+                                s2_mma_tf32<true>(d_tmem, a_desc + (aoff >> 4), b_desc + (boff >> 4), IDESC2);
+                        }
+                    s2_commit(SBAR(P12, sb));
+                    if (it >= LAG) pass_b(it - LAG);
+                }
+            }
+            for (int j = (it > LAG ? it - LAG : 0); j < it; ++j) pass_b(j);
+        }
+    } else if (warp >= 8) {
+        // ===================== epilogue (warps 8-11) =====================
+        const int quarter = warp & 3;                 // TMEM lanes 32*quarter .. +31
+        const float slope = p.act == CODD_ACT_LEAKY ? CODD_LEAKY_SLOPE : (p.act == CODD_ACT_RELU ? 0.f : 1.f);
+        const float slope0 = (p.act == CODD_ACT_RELU || p.act == CODD_ACT_RELU_CH0) ? 0.f : slope;
+        const bool full_vec = ((p.ldo & 3) == 0) && ((((uintptr_t)p.out) & 15u) == 0) && (p.Cout % 4 == 0);
+        float biasr[NP];
+#pragma unroll
+        for (int c = 0; c < NP; ++c) biasr[c] = (p.bias && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
+        int ti = 0;
+        for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++ti) {
+            const int ab = ti % NACC;
+            int q = t;
+            const int tx = q % p.tilesX;
+            q /= p.tilesX;
+            const int yo = q % p.Ho;
+            const int n = q / p.Ho;
+            s2_mbar_wait(ABAR(ACCF, ab), ((uint32_t)(ti / NACC)) & 1u);
+            s2_fence_after();
+            float acc[ACC_COLS];
+#pragma unroll
+            for (int c = 0; c < (int)ACC_COLS; c += 16)
+                s2_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)ab * ACC_COLS + c, &acc[c]);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            s2_fence_before();
+            s2_mbar_arrive(ABAR(ACCE, ab));
+            const int xo = tx * S2_TW + quarter * 32 + lane;
+            if (xo >= p.Wo) continue;
+            float* op = p.out + (((size_t)n * p.Ho + yo) * p.Wo + xo) * p.ldo;
+            float v[NP];
+#pragma unroll
+            for (int c = 0; c < NP; ++c) v[c] = (acc[c] + acc[NP + c]) + biasr[c];
+            if (p.act <= CODD_ACT_RELU_CH0) {
+#pragma unroll
+                for (int c = 0; c < NP; ++c) {
+                    const float sl = c == 0 ? slope0 : slope;
+                    v[c] = fmaxf(v[c], 0.f) + sl * fminf(v[c], 0.f);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < NP; ++c) v[c] = codd_act(v[c], p.act, c);
+            }
+            if (full_vec) {
+#pragma unroll
+                for (int c4 = 0; c4 < NP; c4 += 4)
+                    if (c4 < p.Cout) *reinterpret_cast<float4*>(op + c4) = make_float4(v[c4], v[c4 + 1], v[c4 + 2], v[c4 + 3]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < NP; ++c)
+                    if (c < p.Cout) op[c] = v[c];
+            }
+        }
+    } else {
+        // ===================== in-place hi/lo split of the stage (warps 0-7) =====================
+        int it = 0;
+        for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+            for (int ky = 0; ky < 4; ++ky, ++it) {
+                const int sb = it % NBUF;
+                s2_mbar_wait(SBAR(P12, sb), ((uint32_t)(it / NBUF)) & 1u);   // pass A has consumed the raw stage
+                s2_fence_after();
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    float4* a4 = reinterpret_cast<float4*>(gbase + sb * S2_STAGE + r * S2_SLOT);
+#pragma unroll 2
+                    for (int idx = tid; idx < (int)(BOX_BYTES / 16); idx += S2_SPLIT_THREADS) {
+                        float4 v = a4[idx];
+                        v.x = __fsub_rn(v.x, __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u));
+                        v.y = __fsub_rn(v.y, __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u));
+                        v.z = __fsub_rn(v.z, __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u));
+                        v.w = __fsub_rn(v.w, __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
+                        a4[idx] = v;
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                s2_mbar_arrive(SBAR(LO, sb));
+            }
+        }
+    }
+    s2_fence_before();
+    __syncthreads();
+    if (warp == 13) {
+        s2_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
+    }
+}
+
+typedef CUresult (*PFN_s2EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_s2EncodeTiled s2_get_encode() {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+        return (PFN_s2EncodeTiled)ptr;
+    return nullptr;
+}
+
+template <int NP, int NBUF, int NACC, int LAG>
+int s2_launch(const CUtensorMap& tmap, S2P p, cudaStream_t s) {
+    const size_t smem = (size_t)NBUF * S2_STAGE + 16 * 2 * NP * S2_ROWB + 1024;
+    auto kern = conv4x4s2_tc_kernel<NP, NBUF, NACC, LAG>;
+    static CoddDeviceOnce once;
+    if (int rc = codd_once_per_device(once, [&] {
+            return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        }))
+        return rc;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = p.ntiles < sms ? p.ntiles : sms;
+    kern<<<grid, S2_THREADS, smem, s>>>(tmap, p);
+    CODD_RETURN_IF_CUDA_ERROR();
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int codd_conv4x4s2_tc(const float* in, int ldi, int cin, int n, int h, int w, const float* weight_split,
+                                 const float* bias, int cout, int act, float* out, int ldo, void* stream) {
+    if (!in || !weight_split || !out || n <= 0 || h <= 0 || w <= 0 || cout <= 0) return CODD_E_BADARG;
+    if (cin != S2_KC || cout > 32 || (w & 1) || (h & 1) || ldi % 4 != 0 || ldi < cin || ldo < cout) return CODD_E_UNSUPPORTED;
+    if (!codd_aligned16(in)) return CODD_E_ALIGN;
+    static PFN_s2EncodeTiled enc = s2_get_encode();
+    if (!enc) return CODD_E_UNSUPPORTED;
+    CUtensorMap tmap;
+    // {channel, column parity, column / 2, row, sample}
+    const cuuint64_t gdim[5] = {(cuuint64_t)cin, 2u, (cuuint64_t)(w / 2), (cuuint64_t)h, (cuuint64_t)n};
+    const cuuint64_t gstr[4] = {(cuuint64_t)ldi * 4, (cuuint64_t)ldi * 8, (cuuint64_t)w * ldi * 4, (cuuint64_t)h * w * ldi * 4};
+    const cuuint32_t box[5] = {(cuuint32_t)S2_KC, 1u, (cuuint32_t)S2_BOXP, 1u, 1u};
+    const cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
+    const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)in, gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return CODD_E_UNSUPPORTED;
+    S2P p;
+    p.wpk = weight_split; p.bias = bias; p.out = out;
+    p.N = n; p.Ho = h / 2; p.Wo = w / 2; p.Cout = cout; p.ldo = ldo; p.act = act;
+    p.tilesX = codd_ceil_div(p.Wo, S2_TW);
+    const long long nt = (long long)p.tilesX * p.Ho * n;
+    if (nt > 0x7fffffffLL) return CODD_E_SHAPE;
+    p.ntiles = (int)nt;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (cout <= 16) return s2_launch<16, 6, 4, 2>(tmap, p, s);
+    return s2_launch<32, 6, 4, 2>(tmap, p, s);
+}

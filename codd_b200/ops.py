@@ -168,6 +168,38 @@ def pack_conv_weight_tc(w):
     return torch.stack([hi, lo]).contiguous()
 
 
+def pack_conv_weight_tc4(w):
+    """torch [Cout,16,4,4] -> [2][16][NP][16] hi/lo split for codd_conv4x4s2_tc (3xTF32), tap = ky*4 + kx."""
+    cout, cin, kh, kw = w.shape
+    assert kh == 4 and kw == 4 and cin == 16 and cout <= 32
+    npad = 16 if cout <= 16 else 32
+    wt = torch.zeros((16, npad, 16), dtype=torch.float32, device=w.device)
+    wt[:, :cout, :] = w.detach().float().permute(2, 3, 0, 1).reshape(16, cout, cin)
+    hi = _tf32_round(wt)
+    lo = _tf32_round(wt - hi)
+    return torch.stack([hi, lo]).contiguous()
+
+
+def tc4_eligible(x, cout, k, stride, pad, dil, x2, residual):
+    """4x4 / stride 2 / pad 1, Cin = 16, Cout <= 32, even sizes, large enough to fill the persistent grid."""
+    n, cin, h, w = x.shape
+    return (x2 is None and residual is None and tuple(k) == (4, 4) and tuple(stride) == (2, 2) and tuple(pad) == (1, 1)
+            and dil == 1 and cin == 16 and cout <= 32 and h % 2 == 0 and w % 2 == 0 and h * w >= 16384)
+
+
+def conv4x4s2_tc(x, wsplit, bias, cout, act=ACT_NONE):
+    """4x4 s2 p1 conv on the tensor cores (3xTF32).  ``wsplit`` from pack_conv_weight_tc4."""
+    _require_cuda(x, wsplit, bias)
+    n, cin, h, w = x.shape
+    out = empty_nhwc(n, cout, h // 2, w // 2, x.device)
+    nbytes = 4 * (n * h * w * cin + n * (h // 2) * (w // 2) * cout + wsplit.numel() // 2)
+    rc = _run(f"conv4x4s2tc_cin{cin}_cout{cout}", nbytes, lambda: _lib.load().codd_conv4x4s2_tc(
+        x.data_ptr(), ld_of(x), cin, n, h, w, wsplit.data_ptr(), None if bias is None else bias.data_ptr(), cout, act,
+        out.data_ptr(), ld_of(out), _stream()))
+    _lib.check(rc, f"codd_conv4x4s2_tc(cin={cin}, cout={cout})")
+    return out
+
+
 def pack_conv_weight_ring(w):
     """torch [Cout,Cin,3,3] -> flat buffer for codd_conv3x3_tc_ring (fp16 data, returned viewed as float32):
     pass A  [3 kx][6*NP rows][KC] — rows per ky = [w_hi (NP) | 2^10 * w_lo (NP)],  w_hi = fp16(w), w_lo = w - w_hi,

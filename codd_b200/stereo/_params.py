@@ -31,6 +31,10 @@ def run_conv(pw, conv, x, act, x2=None, residual=None, res_bcast=False, head=Non
         # single-channel head (FinalTileUpdate disparity): memory-bound, its own shared-memory tile kernel
         wp, b = pw.conv_head(conv, 1)
         return ops.conv2d(x, wp, b, 1, k, st, pd, dl, act, residual=residual, res_bcast=res_bcast)
+    if USE_TC and head is None and ops.tc4_eligible(x, cout, k, st, pd, dl, x2, residual):
+        # conv_down first layer at the two finest levels (backbone.py:8-14): tcgen05 implicit GEMM over parity boxes
+        ws, b = pw.conv_tc4(conv)
+        return ops.conv4x4s2_tc(x, ws, b, cout, act)
     big = x.shape[2] * x.shape[3] >= 4096
     if (USE_TC and USE_RING and big and cout == 34 and cin == 32 and x2 is None and residual is None and dl == 1
             and act != ops.ACT_RELU_CH0 and ops.tc_eligible(cin, 32, k, st, pd, dl, x2)):
@@ -106,6 +110,18 @@ class PackedWeights:
             ww = w if n is None else w[:n]
             bb = None if b is None else (b.detach() if n is None else b.detach()[:n]).float().contiguous()
             hit = (tag, ops.pack_conv_weight_tc(ww), bb)
+            self._cache[key] = hit
+        return hit[1], hit[2]
+
+    def conv_tc4(self, conv):
+        """hi/lo tf32 split of a 4x4 stride-2 weight for codd_conv4x4s2_tc."""
+        w = conv.weight
+        b = conv.bias
+        key = (id(conv), "tc4")
+        tag = (w.data_ptr(), w._version, w.device, None if b is None else (b.data_ptr(), b._version))
+        hit = self._cache.get(key)
+        if hit is None or hit[0] != tag:
+            hit = (tag, ops.pack_conv_weight_tc4(w), None if b is None else b.detach().float().contiguous())
             self._cache[key] = hit
         return hit[1], hit[2]
 

@@ -113,6 +113,13 @@ CODD_API int codd_conv3x3_tc_ring(const float* in, int ldi, int cin, int n, int 
                                   const float* bias, const float* residual, int ldr, int res_bcast, int cout, int act,
                                   float* out, int ldo, void* stream);
 
+/* 4x4 / stride 2 / pad 1 convolution (HITUNet conv_down first layer, backbone.py:8-14) on the tensor cores, Cin = 16,
+ * Cout <= 32, even H and W: implicit GEMM over TMA boxes of same-parity columns (csrc/conv_tc_s2.cu), 3xTF32.
+ * weight_split (host: ops.pack_conv_weight_tc4) = [2][16 taps][NP][16], pass 0 = tf32 hi, pass 1 = lo, NP = 16 | 32.
+ * out [n, h/2, w/2, cout] NHWC (ldo).  CODD_E_UNSUPPORTED for other geometries (callers fall back to codd_conv2d_nhwc). */
+CODD_API int codd_conv4x4s2_tc(const float* in, int ldi, int cin, int n, int h, int w, const float* weight_split,
+                               const float* bias, int cout, int act, float* out, int ldo, void* stream);
+
 /* First backbone layer (backbone.py:35-39,70): 3x3, pad 1, 3 -> cout (<=16) channels,
  * LeakyReLU, reading NCHW images and writing NHWC.  `left` and `right` are two [n,3,h,w]
  * images batches; the output holds 2n samples: left batch first, then right (right may be

@@ -418,6 +418,30 @@ def test_conv3x3_tensor_core_ring(ops, cin, cout, h, w):
     torch.testing.assert_close(got, ref, rtol=CONV_RTOL, atol=CONV_ATOL)
 
 
+@pytest.mark.parametrize("cout,n,h,w", [(16, 2, 64, 256), (24, 1, 130, 330), (16, 1, 2, 2), (32, 2, 36, 600), (3, 1, 70, 258),
+                                         (16, 3, 128, 128)])
+def test_conv4x4_stride2_tensor_core(ops, cout, n, h, w):
+    """conv_down first layer (backbone.py:8-14) on tcgen05: 4x4 / stride 2 / pad 1, Cin = 16, TMA boxes of same-parity
+    columns, 3xTF32 — same bar as the fp32 CUDA-core convolution; ragged tile widths, single-tile and padded-filter
+    (Cout = 24, 3) cases."""
+    from codd_b200.lib import ACT_LEAKY
+    g = gen(cout * 1000 + h + w)
+    x = torch.randn(n, 16, h, w, generator=g)
+    wt = torch.randn(cout, 16, 4, 4, generator=g) / 16.0
+    b = torch.randn(cout, generator=g)
+    ref = F.leaky_relu(F.conv2d(x, wt, b, stride=2, padding=1), 0.2)
+    out = ops.conv4x4s2_tc(nhwc(ops, x), ops.pack_conv_weight_tc4(wt.cuda()), b.cuda(), cout, ACT_LEAKY)
+    torch.cuda.synchronize()
+    got = back(ops, out)
+    print(f"conv4x4s2tc cout={cout} {n}x{h}x{w}: max abs err {(got - ref).abs().max().item():.3e}")
+    torch.testing.assert_close(got, ref, rtol=CONV_RTOL, atol=CONV_ATOL)
+    # a channel slice of a wider buffer as input (ld > C)
+    wide = ops.empty_nhwc(n, 32, h, w, "cuda")
+    wide[:, 8:24].copy_(x.cuda())
+    out2 = ops.conv4x4s2_tc(wide[:, 8:24], ops.pack_conv_weight_tc4(wt.cuda()), b.cuda(), cout, ACT_LEAKY)
+    assert torch.equal(back(ops, out2), got)
+
+
 @pytest.mark.parametrize("h,w", [(9, 200), (5, 128), (20, 131), (3, 7)])
 def test_conv3x3_tensor_core_dilated(ops, h, w):
     """dilation 3 / pad 3, 32 -> 32 (the dilated resblocks of tile_update4_1 / tile_update5)."""
