@@ -20,6 +20,13 @@
 //     pass B multiplies it by w_hi (N = NP), LAG stages behind pass A so the tensor pipe never waits for the split;
 //   * accumulators in TMEM (NACC tiles x 2 NP columns), epilogue warps read them with tcgen05.ld (lane = pixel), add
 //     the bias, apply the activation and store NHWC.
+//
+// The same kernel, re-parametrised, computes TileInitialization.tile_features (initialization.py:119-156) at the two
+// finest levels (Cin = 16): the 4x4 conv with stride (4,4) on the left features (columns split into FOUR residue classes
+// mod 4, one tap each, no shift) and with stride (4,1) over the right features zero-padded by 3 columns (ONE class, taps
+// shifted by kx pixels; the padding is TMA's out-of-bounds fill), followed in the epilogue by LeakyReLU, the 16x16 1x1
+// conv, LeakyReLU and a PLANAR store (what the cost-volume kernel reads).  General rule: input column
+// xi = SW*xo + kx - PW = SW*(xo + s) + r with r = (kx - PW) mod SW, s = floor((kx - PW) / SW): slot r, pixel shift s.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -28,20 +35,46 @@ namespace {
 
 constexpr int S2_TW = 128;                 // output columns per tile (= MMA M)
 constexpr int S2_KC = 16;                  // input channels (K per tap)
-constexpr int S2_BOXP = 136;               // same-parity pixels per slot (129 needed, multiple of 8)
 constexpr uint32_t S2_ROWB = S2_KC * 4;    // bytes per pixel row of the K-major tile
-constexpr uint32_t S2_SLOT = 9 * 1024;     // slot pitch (136 * 64 = 8704 bytes used), 1024-aligned for the swizzle atom
-constexpr uint32_t S2_STAGE = 2 * S2_SLOT;
 constexpr int S2_EPI_THREADS = 128;
 constexpr int S2_SPLIT_THREADS = 256;
 constexpr int S2_THREADS = 64 + S2_EPI_THREADS + S2_SPLIT_THREADS;   // warps 0-7 split, 8-11 epilogue, 12 TMA, 13 MMA
 
+// geometry of a 4-wide kernel row at horizontal stride SW with left padding PW
+template <int SW, int PW>
+struct K4Geo {
+    static constexpr int NSLOT = SW;
+    __host__ __device__ static constexpr int cls(int kx) { return (((kx - PW) % SW) + SW) % SW; }
+    __host__ __device__ static constexpr int fdiv(int kx) { return (kx - PW - cls(kx)) / SW; }            // floor((kx - PW) / SW)
+    __host__ __device__ static constexpr int smin(int r) {
+        int m = 1 << 20;
+        for (int kx = 0; kx < 4; ++kx)
+            if (cls(kx) == r && fdiv(kx) < m) m = fdiv(kx);
+        return m == (1 << 20) ? 0 : m;
+    }
+    __host__ __device__ static constexpr int shift(int kx) { return fdiv(kx) - smin(cls(kx)); }             // pixel offset of tap kx inside its slot
+    __host__ __device__ static constexpr int maxshift() {
+        int m = 0;
+        for (int kx = 0; kx < 4; ++kx)
+            if (shift(kx) > m) m = shift(kx);
+        return m;
+    }
+    static constexpr int BOXP = (S2_TW + maxshift() + 7) & ~7;                          // pixels per slot
+    static constexpr uint32_t SLOT = ((uint32_t)BOXP * S2_ROWB + 1023u) & ~1023u;       // 1024-aligned for the swizzle atom
+    static constexpr uint32_t STAGE = (uint32_t)NSLOT * SLOT;
+};
+static_assert(K4Geo<2, 1>::cls(0) == 1 && K4Geo<2, 1>::shift(0) == 0 && K4Geo<2, 1>::shift(2) == 1 && K4Geo<2, 1>::cls(3) == 0 &&
+              K4Geo<2, 1>::shift(3) == 1 && K4Geo<2, 1>::smin(1) == -1 && K4Geo<2, 1>::BOXP == 136, "stride-2 geometry");
+static_assert(K4Geo<4, 0>::cls(3) == 3 && K4Geo<4, 0>::shift(3) == 0 && K4Geo<4, 0>::BOXP == 128, "stride-4 geometry");
+static_assert(K4Geo<1, 0>::cls(3) == 0 && K4Geo<1, 0>::shift(3) == 3 && K4Geo<1, 0>::BOXP == 136, "stride-1 geometry");
 struct S2P {
     const float* wpk;   // [2][16 taps][NP][16] fp32: pass 0 = tf32 hi, pass 1 = lo
     const float* bias;
     float* out;
     int N, Ho, Wo, Cout, ldo, act;
     int tilesX, ntiles;
+    const float* w1;    // tile-feature epilogue: 1x1 conv [16][16] (torch layout) and its bias; out is PLANAR then
+    const float* b1;
 };
 
 __device__ __forceinline__ uint32_t s2_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -119,9 +152,13 @@ __device__ __forceinline__ uint32_t s2_swz(int r, int j) {
 }
 
 // NBUF stage buffers, NACC accumulator buffers, pass B trails pass A by LAG stages (LAG < NBUF).
-template <int NP, int NBUF, int NACC, int LAG>
+// SW / SH: strides, PW / PH: left / top padding, TILEF: tile-feature epilogue (LeakyReLU, 1x1, LeakyReLU, planar store)
+template <int SW, int SH, int PW, int PH, int NP, int NBUF, int NACC, int LAG, bool TILEF>
 __global__ void __launch_bounds__(S2_THREADS, 1) conv4x4s2_tc_kernel(const __grid_constant__ CUtensorMap tmap, S2P p) {
     static_assert(LAG >= 1 && LAG < NBUF && NACC >= 2, "pipeline depths");
+    using G = K4Geo<SW, PW>;
+    constexpr int S2_BOXP = G::BOXP;
+    constexpr uint32_t S2_SLOT = G::SLOT, S2_STAGE = G::STAGE;
     constexpr uint32_t ACC_COLS = 2 * NP;          // per tile: [0,NP) = x_hi*w_hi + x_lo*w_hi, [NP,2NP) = x_hi*w_lo
     constexpr uint32_t TMEM_COLS = (NACC * ACC_COLS <= 128) ? 128u : (NACC * ACC_COLS <= 256) ? 256u : 512u;
     constexpr uint32_t B_TAP = 2 * NP * S2_ROWB;   // per tap: NP rows of w_hi followed by NP rows of w_lo
@@ -133,6 +170,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) conv4x4s2_tc_kernel(const __gri
     extern __shared__ uint8_t s2_smem_raw[];
     __shared__ __align__(8) unsigned long long bars[4 * NBUF + 2 * NACC];
     __shared__ uint32_t tmem_base_slot;
+    __shared__ __align__(16) float s_w1[TILEF ? 16 * 16 : 4];     // 1x1 weights, TRANSPOSED [ci][co]
 
     const uint32_t sbase = (s2_u32(s2_smem_raw) + 1023u) & ~1023u;
     uint8_t* gbase = s2_smem_raw + (sbase - s2_u32(s2_smem_raw));
@@ -173,6 +211,8 @@ __global__ void __launch_bounds__(S2_THREADS, 1) conv4x4s2_tc_kernel(const __gri
         const int pass = pt >> 4, tap = pt & 15;
         *reinterpret_cast<float4*>(gB + tap * B_TAP + s2_swz(r + pass * NP, j)) = v;
     }
+    if (TILEF)
+        for (int idx = tid; idx < 256; idx += S2_THREADS) s_w1[(idx & 15) * 16 + (idx >> 4)] = __ldg(p.w1 + idx);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     s2_fence_before();
     __syncthreads();
@@ -194,15 +234,16 @@ __global__ void __launch_bounds__(S2_THREADS, 1) conv4x4s2_tc_kernel(const __gri
                 for (int ky = 0; ky < 4; ++ky, ++it) {
                     const int sb = it % NBUF;
                     s2_mbar_wait(SBAR(EMPTY, sb), (((uint32_t)(it / NBUF)) & 1u) ^ 1u);
-                    s2_mbar_expect_tx(SBAR(FULL, sb), 2 * BOX_BYTES);
-                    const int y = 2 * yo + ky - 1;
-                    // slot 0: even columns 2p, p from xo0 (taps kx = 1, 3); slot 1: odd columns 2p + 1, p from xo0 - 1 (kx = 0, 2)
+                    s2_mbar_expect_tx(SBAR(FULL, sb), G::NSLOT * BOX_BYTES);
+                    const int y = SH * yo + ky - PH;
+                    // slot r: columns SW*p + r, p from xo0 + smin(r) (stride 2, pad 1: slot 0 = even columns from xo0 for
+                    // taps kx = 1, 3; slot 1 = odd columns from xo0 - 1 for kx = 0, 2)
 #pragma unroll
-                    for (int r = 0; r < 2; ++r) {
+                    for (int r = 0; r < G::NSLOT; ++r) {
                         asm volatile(
                             "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
                             "%5, %6, %7}], [%2];" ::"r"(sbase + sb * S2_STAGE + (uint32_t)r * S2_SLOT),
-                            "l"(&tmap), "r"(SBAR(FULL, sb)), "r"(0), "r"(r), "r"(xo0 - r), "r"(y), "r"(n)
+                            "l"(&tmap), "r"(SBAR(FULL, sb)), "r"(0), "r"(r), "r"(xo0 + G::smin(r)), "r"(y), "r"(n)
                             : "memory");
                     }
                 }
@@ -223,7 +264,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) conv4x4s2_tc_kernel(const __gri
                 for (int kx = 0; kx < 4; ++kx)
 #pragma unroll
                     for (int k = 0; k < S2_KC / 8; ++k) {
-                        const uint32_t aoff = (uint32_t)((kx + 1) & 1) * S2_SLOT + (uint32_t)(kx >> 1) * S2_ROWB + k * 32;
+                        const uint32_t aoff = (uint32_t)G::cls(kx) * S2_SLOT + (uint32_t)G::shift(kx) * S2_ROWB + k * 32;
                         const uint32_t boff = (uint32_t)(ky * 4 + kx) * B_TAP + k * 32;
                         s2_mma_tf32<true>(d_tmem, a_desc + (aoff >> 4), b_desc + (boff >> 4), IDESC1);
                     }
@@ -244,7 +285,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) conv4x4s2_tc_kernel(const __gri
                     for (int kx = 0; kx < 4; ++kx)
 #pragma unroll
                         for (int k = 0; k < S2_KC / 8; ++k) {
-                            const uint32_t aoff = (uint32_t)((kx + 1) & 1) * S2_SLOT + (uint32_t)(kx >> 1) * S2_ROWB + k * 32;
+                            const uint32_t aoff = (uint32_t)G::cls(kx) * S2_SLOT + (uint32_t)G::shift(kx) * S2_ROWB + k * 32;
                             const uint32_t boff = (uint32_t)(ky * 4 + kx) * B_TAP + k * 32;
                             if (ky == 0 && kx == 0 && k == 0)
                                 s2_mma_tf32<false>(d_tmem, a_desc + (aoff >> 4), b_desc + (boff >> 4), IDESC2);
@@ -285,10 +326,31 @@ __global__ void __launch_bounds__(S2_THREADS, 1) conv4x4s2_tc_kernel(const __gri
             s2_mbar_arrive(ABAR(ACCE, ab));
             const int xo = tx * S2_TW + quarter * 32 + lane;
             if (xo >= p.Wo) continue;
-            float* op = p.out + (((size_t)n * p.Ho + yo) * p.Wo + xo) * p.ldo;
             float v[NP];
 #pragma unroll
             for (int c = 0; c < NP; ++c) v[c] = (acc[c] + acc[NP + c]) + biasr[c];
+            if (TILEF) {
+                // initialization.py:119-124: LeakyReLU -> 1x1 conv (16 -> 16) -> LeakyReLU, planar [n,16,Ho,Wo]
+#pragma unroll
+                for (int c = 0; c < 16; ++c) v[c] = v[c] > 0.f ? v[c] : v[c] * CODD_LEAKY_SLOPE;
+                float o[16];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) o[c] = __ldg(p.b1 + c);
+#pragma unroll
+                for (int ci = 0; ci < 16; ++ci) {
+#pragma unroll
+                    for (int c4 = 0; c4 < 16; c4 += 4) {
+                        const float4 w4 = *reinterpret_cast<const float4*>(&s_w1[ci * 16 + c4]);
+                        fma4(&o[c4], v[ci], w4);
+                    }
+                }
+                float* pp = p.out + (((size_t)n * 16) * p.Ho + yo) * p.Wo + xo;
+                const size_t plane = (size_t)p.Ho * p.Wo;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) pp[c * plane] = o[c] > 0.f ? o[c] : o[c] * CODD_LEAKY_SLOPE;
+                continue;
+            }
+            float* op = p.out + (((size_t)n * p.Ho + yo) * p.Wo + xo) * p.ldo;
             if (p.act <= CODD_ACT_RELU_CH0) {
 #pragma unroll
                 for (int c = 0; c < NP; ++c) {
@@ -318,7 +380,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) conv4x4s2_tc_kernel(const __gri
                 s2_mbar_wait(SBAR(P12, sb), ((uint32_t)(it / NBUF)) & 1u);   // pass A has consumed the raw stage
                 s2_fence_after();
 #pragma unroll
-                for (int r = 0; r < 2; ++r) {
+                for (int r = 0; r < G::NSLOT; ++r) {
                     float4* a4 = reinterpret_cast<float4*>(gbase + sb * S2_STAGE + r * S2_SLOT);
 #pragma unroll 2
                     for (int idx = tid; idx < (int)(BOX_BYTES / 16); idx += S2_SPLIT_THREADS) {
@@ -355,10 +417,11 @@ PFN_s2EncodeTiled s2_get_encode() {
     return nullptr;
 }
 
-template <int NP, int NBUF, int NACC, int LAG>
+template <int SW, int SH, int PW, int PH, int NP, int NBUF, int NACC, int LAG, bool TILEF>
 int s2_launch(const CUtensorMap& tmap, S2P p, cudaStream_t s) {
-    const size_t smem = (size_t)NBUF * S2_STAGE + 16 * 2 * NP * S2_ROWB + 1024;
-    auto kern = conv4x4s2_tc_kernel<NP, NBUF, NACC, LAG>;
+    const size_t smem = (size_t)NBUF * K4Geo<SW, PW>::STAGE + 16 * 2 * NP * S2_ROWB + 1024;
+    static_assert((size_t)NBUF * K4Geo<SW, PW>::STAGE + 16 * 2 * NP * S2_ROWB + 1024 + 2048 <= 232448, "shared memory budget");
+    auto kern = conv4x4s2_tc_kernel<SW, SH, PW, PH, NP, NBUF, NACC, LAG, TILEF>;
     static CoddDeviceOnce once;
     if (int rc = codd_once_per_device(once, [&] {
             return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -375,31 +438,60 @@ int s2_launch(const CUtensorMap& tmap, S2P p, cudaStream_t s) {
 
 }  // namespace
 
+namespace {
+// 5-D view {channel, column class (x mod SW), x / SW, row, sample} of an NHWC map whose width is a multiple of SW
+int s2_make_tmap(CUtensorMap* tmap, const float* in, int ldi, int cin, int n, int h, int w, int sw, int boxp) {
+    static PFN_s2EncodeTiled enc = s2_get_encode();      // C++11 magic static
+    if (!enc) return CODD_E_UNSUPPORTED;
+    const cuuint64_t gdim[5] = {(cuuint64_t)cin, (cuuint64_t)sw, (cuuint64_t)(w / sw), (cuuint64_t)h, (cuuint64_t)n};
+    const cuuint64_t gstr[4] = {(cuuint64_t)ldi * 4, (cuuint64_t)ldi * 4 * sw, (cuuint64_t)w * ldi * 4,
+                                (cuuint64_t)h * w * ldi * 4};
+    const cuuint32_t box[5] = {(cuuint32_t)S2_KC, 1u, (cuuint32_t)boxp, 1u, 1u};
+    const cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
+    const CUresult r = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)in, gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : CODD_E_UNSUPPORTED;
+}
+}  // namespace
+
 extern "C" int codd_conv4x4s2_tc(const float* in, int ldi, int cin, int n, int h, int w, const float* weight_split,
                                  const float* bias, int cout, int act, float* out, int ldo, void* stream) {
     if (!in || !weight_split || !out || n <= 0 || h <= 0 || w <= 0 || cout <= 0) return CODD_E_BADARG;
     if (cin != S2_KC || cout > 32 || (w & 1) || (h & 1) || ldi % 4 != 0 || ldi < cin || ldo < cout) return CODD_E_UNSUPPORTED;
     if (!codd_aligned16(in)) return CODD_E_ALIGN;
-    static PFN_s2EncodeTiled enc = s2_get_encode();
-    if (!enc) return CODD_E_UNSUPPORTED;
     CUtensorMap tmap;
-    // {channel, column parity, column / 2, row, sample}
-    const cuuint64_t gdim[5] = {(cuuint64_t)cin, 2u, (cuuint64_t)(w / 2), (cuuint64_t)h, (cuuint64_t)n};
-    const cuuint64_t gstr[4] = {(cuuint64_t)ldi * 4, (cuuint64_t)ldi * 8, (cuuint64_t)w * ldi * 4, (cuuint64_t)h * w * ldi * 4};
-    const cuuint32_t box[5] = {(cuuint32_t)S2_KC, 1u, (cuuint32_t)S2_BOXP, 1u, 1u};
-    const cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
-    const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)in, gdim, gstr, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return CODD_E_UNSUPPORTED;
+    if (int rc = s2_make_tmap(&tmap, in, ldi, cin, n, h, w, 2, K4Geo<2, 1>::BOXP)) return rc;
     S2P p;
-    p.wpk = weight_split; p.bias = bias; p.out = out;
+    p.wpk = weight_split; p.bias = bias; p.out = out; p.w1 = nullptr; p.b1 = nullptr;
     p.N = n; p.Ho = h / 2; p.Wo = w / 2; p.Cout = cout; p.ldo = ldo; p.act = act;
     p.tilesX = codd_ceil_div(p.Wo, S2_TW);
     const long long nt = (long long)p.tilesX * p.Ho * n;
     if (nt > 0x7fffffffLL) return CODD_E_SHAPE;
     p.ntiles = (int)nt;
     cudaStream_t s = (cudaStream_t)stream;
-    if (cout <= 16) return s2_launch<16, 6, 4, 2>(tmap, p, s);
-    return s2_launch<32, 6, 4, 2>(tmap, p, s);
+    if (cout <= 16) return s2_launch<2, 2, 1, 1, 16, 6, 4, 2, false>(tmap, p, s);
+    return s2_launch<2, 2, 1, 1, 32, 6, 4, 2, false>(tmap, p, s);
+}
+
+// Tile features on the tensor cores (Cin = 16): see the header comment.  w0_split as for codd_conv4x4s2_tc with NP = 16.
+extern "C" int codd_tile_features_tc(const float* in, int ldi, int cin, int n, int h_in, int w_in, const float* w0_split,
+                                     const float* b0, const float* w1, const float* b1, int right, float* out,
+                                     void* stream) {
+    if (!in || !w0_split || !b0 || !w1 || !b1 || !out || n <= 0 || h_in <= 0 || w_in <= 0) return CODD_E_BADARG;
+    if (cin != S2_KC || ldi < cin || ldi % 4 != 0 || h_in % 4 != 0 || w_in % 4 != 0) return CODD_E_UNSUPPORTED;
+    if (!codd_aligned16(in)) return CODD_E_ALIGN;
+    CUtensorMap tmap;
+    const int sw = right ? 1 : 4;
+    if (int rc = s2_make_tmap(&tmap, in, ldi, cin, n, h_in, w_in, sw, right ? K4Geo<1, 0>::BOXP : K4Geo<4, 0>::BOXP)) return rc;
+    S2P p;
+    p.wpk = w0_split; p.bias = b0; p.out = out; p.w1 = w1; p.b1 = b1;
+    p.N = n; p.Ho = h_in / 4; p.Wo = right ? w_in : w_in / 4; p.Cout = 16; p.ldo = 16; p.act = CODD_ACT_LEAKY;
+    p.tilesX = codd_ceil_div(p.Wo, S2_TW);
+    const long long nt = (long long)p.tilesX * p.Ho * n;
+    if (nt > 0x7fffffffLL) return CODD_E_SHAPE;
+    p.ntiles = (int)nt;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (right) return s2_launch<1, 4, 0, 0, 16, 6, 4, 2, true>(tmap, p, s);
+    return s2_launch<4, 4, 0, 0, 16, 4, 4, 2, true>(tmap, p, s);
 }

@@ -395,6 +395,25 @@ def tile_features(fea, w0p, b0, w1, b1, right):
     return out
 
 
+def tile_features_tc_eligible(fea):
+    n, c, h, w = fea.shape
+    return c == 16 and h % 4 == 0 and w % 4 == 0 and h * w >= 16384
+
+
+def tile_features_tc(fea, w0split, b0, w1, b1, right):
+    """K2 on the tensor cores (Cin = 16): same contract as tile_features, ``w0split`` from pack_conv_weight_tc4."""
+    _require_cuda(fea, w0split, b0, w1, b1)
+    n, c, h, w = fea.shape
+    wo = w if right else w // 4
+    out = torch.empty((n, 16, h // 4, wo), device=fea.device, dtype=torch.float32)
+    rc = _run("tile_features_tc_" + ("right" if right else "left") + f"_c{c}", 4 * (n * h * w * c + out.numel()),
+              lambda: _lib.load().codd_tile_features_tc(fea.data_ptr(), ld_of(fea), c, n, h, w, w0split.data_ptr(),
+                                                        b0.data_ptr(), w1.data_ptr(), b1.data_ptr(), 1 if right else 0,
+                                                        out.data_ptr(), _stream()))
+    _lib.check(rc, "codd_tile_features_tc")
+    return out
+
+
 def cost_volume(tile_l, tile_r, max_disp, want_cv=False, want_argmin=True):
     """K1.  tile_l [N,16,h,w], tile_r [N,16,h,4w] (planar NCHW as K2 writes them; NHWC-backed
     inputs are transposed first).  Returns (cv or None, min_cost or None, min_disp or None);

@@ -55,8 +55,13 @@ class TileInitialization(nn.Module):
     def _tile_pair(self, seq, fl, fr):
         """initialization.py:119-124: left 4x4/s4; right the same weights at stride (4,1) over the
         input zero-padded by 3 columns on the right.  One fused kernel per side (K2), planar out."""
-        w0, b0 = self._pw.conv(seq[0])
         w1, b1 = self._pw.raw(seq[2])
+        if ops.tile_features_tc_eligible(fl):
+            # 16-channel levels: the 4x4 conv as a tcgen05 implicit GEMM (csrc/conv_tc_s2.cu)
+            ws, b0 = self._pw.conv_tc4(seq[0])
+            return (ops.tile_features_tc(fl, ws, b0, w1, b1, right=False),
+                    ops.tile_features_tc(fr, ws, b0, w1, b1, right=True))
+        w0, b0 = self._pw.conv(seq[0])
         return ops.tile_features(fl, w0, b0, w1, b1, right=False), ops.tile_features(fr, w0, b0, w1, b1, right=True)
 
     def tile_features(self, fea_l, fea_r):

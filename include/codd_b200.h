@@ -146,6 +146,13 @@ CODD_API int codd_tile_features(const float* in, int ldi, int cin, int n, int h_
                                 const float* w0, const float* b0, const float* w1, const float* b1,
                                 int right, float* out, void* stream);
 
+/* The same on the tensor cores for cin = 16 (csrc/conv_tc_s2.cu: the 4x4 conv as a tcgen05 implicit GEMM over TMA boxes of
+ * column residue classes, 3xTF32; LeakyReLU, the 1x1 conv, LeakyReLU and the planar store in the epilogue).
+ * w0_split (host: ops.pack_conv_weight_tc4) = [2][16 taps][16][16] tf32 hi / lo.  CODD_E_UNSUPPORTED for cin != 16. */
+CODD_API int codd_tile_features_tc(const float* in, int ldi, int cin, int n, int h_in, int w_in,
+                                   const float* w0_split, const float* b0, const float* w1, const float* b1,
+                                   int right, float* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * K1  L1 cost volume + arg-min tile initialisation
  * (reference: calc_init_disp, initialization.py:18-45; torch.min, :167-171).

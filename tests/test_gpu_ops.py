@@ -122,6 +122,28 @@ def test_conv3x3_head1_residual_relu(ops):
     torch.testing.assert_close(back(ops, out), ref, rtol=CONV_RTOL, atol=CONV_ATOL)
 
 
+@pytest.mark.parametrize("n,h,w", [(2, 64, 256), (1, 128, 132), (1, 4, 4), (2, 36, 520)])
+def test_tile_features_tensor_core(ops, n, h, w):
+    """K2 on tcgen05 (Cin = 16): left = 4x4 stride 4, right = stride (4,1) over the input zero-padded by 3 columns
+    (initialization.py:119-124), LeakyReLU + 1x1 + LeakyReLU, planar output — against the oracle, conv tolerance."""
+    g = gen(h * 7 + w)
+    sd = {"t.0.weight": torch.randn(16, 16, 4, 4, generator=g) / 16.0, "t.0.bias": torch.randn(16, generator=g),
+          "t.2.weight": torch.randn(16, 16, 1, 1, generator=g) / 4.0, "t.2.bias": torch.randn(16, generator=g)}
+    fl, fr = torch.randn(n, 16, h, w, generator=g), torch.randn(n, 16, h, w, generator=g)
+    tl, tr = O.tile_features_level(sd, "t", fl, fr)
+    ws = ops.pack_conv_weight_tc4(sd["t.0.weight"].cuda())
+    w1 = sd["t.2.weight"].reshape(16, 16).cuda().contiguous()
+    args = (ws, sd["t.0.bias"].cuda(), w1, sd["t.2.bias"].cuda())
+    got_l = ops.tile_features_tc(nhwc(ops, fl), *args, right=False)
+    got_r = ops.tile_features_tc(nhwc(ops, fr), *args, right=True)
+    torch.cuda.synchronize()
+    assert got_l.is_contiguous() and got_l.shape == tl.shape and got_r.shape == tr.shape
+    print(f"tile features tc {n}x{h}x{w}: max abs err left {(got_l.cpu() - tl).abs().max().item():.3e} "
+          f"right {(got_r.cpu() - tr).abs().max().item():.3e}")
+    torch.testing.assert_close(got_l.cpu(), tl, rtol=CONV_RTOL, atol=CONV_ATOL)
+    torch.testing.assert_close(got_r.cpu(), tr, rtol=CONV_RTOL, atol=CONV_ATOL)
+
+
 def test_tile_conv_right_stride41(ops):
     """initialization.py:121-124: stride (4,1) over the input zero-padded 3 columns on the right."""
     from codd_b200.lib import ACT_LEAKY
