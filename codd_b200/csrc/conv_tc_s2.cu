@@ -34,15 +34,16 @@
 namespace {
 
 constexpr int S2_TW = 128;                 // output columns per tile (= MMA M)
-constexpr int S2_KC = 16;                  // input channels (K per tap)
-constexpr uint32_t S2_ROWB = S2_KC * 4;    // bytes per pixel row of the K-major tile
+// KC = input channels per tap as staged (16, or 32 for Cin = 24 / 32: channels beyond Cin are zero-filled by TMA);
+// a pixel row of the K-major tile is KC * 4 bytes = the swizzle span (SWIZZLE_64B / SWIZZLE_128B)
 constexpr int S2_EPI_THREADS = 128;
 constexpr int S2_SPLIT_THREADS = 256;
 constexpr int S2_THREADS = 64 + S2_EPI_THREADS + S2_SPLIT_THREADS;   // warps 0-7 split, 8-11 epilogue, 12 TMA, 13 MMA
 
 // geometry of a 4-wide kernel row at horizontal stride SW with left padding PW
-template <int SW, int PW>
+template <int SW, int PW, int KC>
 struct K4Geo {
+    static constexpr uint32_t S2_ROWB = KC * 4;
     static constexpr int NSLOT = SW;
     __host__ __device__ static constexpr int cls(int kx) { return (((kx - PW) % SW) + SW) % SW; }
     __host__ __device__ static constexpr int fdiv(int kx) { return (kx - PW - cls(kx)) / SW; }            // floor((kx - PW) / SW)
@@ -63,10 +64,10 @@ struct K4Geo {
     static constexpr uint32_t SLOT = ((uint32_t)BOXP * S2_ROWB + 1023u) & ~1023u;       // 1024-aligned for the swizzle atom
     static constexpr uint32_t STAGE = (uint32_t)NSLOT * SLOT;
 };
-static_assert(K4Geo<2, 1>::cls(0) == 1 && K4Geo<2, 1>::shift(0) == 0 && K4Geo<2, 1>::shift(2) == 1 && K4Geo<2, 1>::cls(3) == 0 &&
-              K4Geo<2, 1>::shift(3) == 1 && K4Geo<2, 1>::smin(1) == -1 && K4Geo<2, 1>::BOXP == 136, "stride-2 geometry");
-static_assert(K4Geo<4, 0>::cls(3) == 3 && K4Geo<4, 0>::shift(3) == 0 && K4Geo<4, 0>::BOXP == 128, "stride-4 geometry");
-static_assert(K4Geo<1, 0>::cls(3) == 0 && K4Geo<1, 0>::shift(3) == 3 && K4Geo<1, 0>::BOXP == 136, "stride-1 geometry");
+static_assert(K4Geo<2, 1, 16>::cls(0) == 1 && K4Geo<2, 1, 16>::shift(0) == 0 && K4Geo<2, 1, 16>::shift(2) == 1 && K4Geo<2, 1, 16>::cls(3) == 0 &&
+              K4Geo<2, 1, 16>::shift(3) == 1 && K4Geo<2, 1, 16>::smin(1) == -1 && K4Geo<2, 1, 16>::BOXP == 136, "stride-2 geometry");
+static_assert(K4Geo<4, 0, 16>::cls(3) == 3 && K4Geo<4, 0, 16>::shift(3) == 0 && K4Geo<4, 0, 16>::BOXP == 128, "stride-4 geometry");
+static_assert(K4Geo<1, 0, 16>::cls(3) == 0 && K4Geo<1, 0, 16>::shift(3) == 3 && K4Geo<1, 0, 16>::BOXP == 136, "stride-1 geometry");
 struct S2P {
     const float* wpk;   // [2][16 taps][NP][16] fp32: pass 0 = tf32 hi, pass 1 = lo
     const float* bias;
@@ -135,28 +136,34 @@ __device__ __forceinline__ void s2_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// shared-memory matrix descriptor, K-major, SWIZZLE_64B (64-byte rows), as conv_tc.cu make_desc<16>
+// shared-memory matrix descriptor, K-major, swizzled (64-byte rows: SWIZZLE_64B, 128-byte rows: SWIZZLE_128B), as
+// conv_tc.cu make_desc
+template <int KC>
 __device__ __forceinline__ uint64_t s2_desc(uint32_t saddr) {
+    constexpr uint32_t ROWB = KC * 4;
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);               // start address
     d |= (uint64_t)1 << 16;                                 // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)((8 * S2_ROWB) >> 4) << 32;              // stride byte offset: 8-row group pitch
+    d |= (uint64_t)((8 * ROWB) >> 4) << 32;                 // stride byte offset: 8-row group pitch
     d |= (uint64_t)1 << 46;                                 // descriptor version (Blackwell)
-    d |= 4ull << 61;                                        // SWIZZLE_64B
+    d |= ((KC == 32) ? 2ull : 4ull) << 61;                  // SWIZZLE_128B : SWIZZLE_64B
     return d;
 }
-// byte offset of 16-byte chunk j of row r inside a K-major SWIZZLE_64B tile whose base is 1024-aligned
+// byte offset of 16-byte chunk j of row r inside a K-major swizzled tile whose base is 1024-aligned
+template <int KC>
 __device__ __forceinline__ uint32_t s2_swz(int r, int j) {
-    const uint32_t off = (uint32_t)r * S2_ROWB + (uint32_t)j * 16u;
-    return off ^ (((off >> 7) & 3u) << 4);
+    const uint32_t off = (uint32_t)r * (KC * 4) + (uint32_t)j * 16u;
+    return off ^ (((off >> 7) & ((KC == 32) ? 7u : 3u)) << 4);
 }
 
 // NBUF stage buffers, NACC accumulator buffers, pass B trails pass A by LAG stages (LAG < NBUF).
 // SW / SH: strides, PW / PH: left / top padding, TILEF: tile-feature epilogue (LeakyReLU, 1x1, LeakyReLU, planar store)
-template <int SW, int SH, int PW, int PH, int NP, int NBUF, int NACC, int LAG, bool TILEF>
+template <int SW, int SH, int PW, int PH, int KC, int NP, int NBUF, int NACC, int LAG, bool TILEF>
 __global__ void __launch_bounds__(S2_THREADS, 1) conv4x4s2_tc_kernel(const __grid_constant__ CUtensorMap tmap, S2P p) {
     static_assert(LAG >= 1 && LAG < NBUF && NACC >= 2, "pipeline depths");
-    using G = K4Geo<SW, PW>;
+    using G = K4Geo<SW, PW, KC>;
+    constexpr int S2_KC = KC;
+    constexpr uint32_t S2_ROWB = KC * 4;
     constexpr int S2_BOXP = G::BOXP;
     constexpr uint32_t S2_SLOT = G::SLOT, S2_STAGE = G::STAGE;
     constexpr uint32_t ACC_COLS = 2 * NP;          // per tile: [0,NP) = x_hi*w_hi + x_lo*w_hi, [NP,2NP) = x_hi*w_lo
@@ -209,7 +216,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) conv4x4s2_tc_kernel(const __gri
         const int pt = idx / ((S2_KC / 4) * NP);          // pass * 16 + tap
         const float4 v = ldg4(p.wpk + ((size_t)pt * NP + r) * S2_KC + j * 4);
         const int pass = pt >> 4, tap = pt & 15;
-        *reinterpret_cast<float4*>(gB + tap * B_TAP + s2_swz(r + pass * NP, j)) = v;
+        *reinterpret_cast<float4*>(gB + tap * B_TAP + s2_swz<KC>(r + pass * NP, j)) = v;
     }
     if (TILEF)
         for (int idx = tid; idx < 256; idx += S2_THREADS) s_w1[(idx & 15) * 16 + (idx >> 4)] = __ldg(p.w1 + idx);
@@ -252,13 +259,13 @@ __global__ void __launch_bounds__(S2_THREADS, 1) conv4x4s2_tc_kernel(const __gri
     } else if (warp == 13) {
         // ===================== MMA issuer =====================
         if (codd_elect_one()) {
-            const uint64_t b_desc = s2_desc(sB);
+            const uint64_t b_desc = s2_desc<KC>(sB);
             // pass B of stage j: x_lo * w_hi into columns [0, NP) of its tile's accumulator
             auto pass_b = [&](int j) {
                 const int sb = j % NBUF, ky = j & 3, ab = (j >> 2) % NACC;
                 s2_mbar_wait(SBAR(LO, sb), ((uint32_t)(j / NBUF)) & 1u);
                 s2_fence_after();
-                const uint64_t a_desc = s2_desc(sbase + sb * S2_STAGE);
+                const uint64_t a_desc = s2_desc<KC>(sbase + sb * S2_STAGE);
                 const uint32_t d_tmem = tmem + (uint32_t)ab * ACC_COLS;
 #pragma unroll
                 for (int kx = 0; kx < 4; ++kx)
@@ -278,7 +285,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) conv4x4s2_tc_kernel(const __gri
                     s2_mbar_wait(SBAR(FULL, sb), ((uint32_t)(it / NBUF)) & 1u);
                     if (ky == 0) s2_mbar_wait(ABAR(ACCE, ab), (((uint32_t)(ti / NACC)) & 1u) ^ 1u);
                     s2_fence_after();
-                    const uint64_t a_desc = s2_desc(sbase + sb * S2_STAGE);
+                    const uint64_t a_desc = s2_desc<KC>(sbase + sb * S2_STAGE);
                     const uint32_t d_tmem = tmem + (uint32_t)ab * ACC_COLS;
                     // pass A: x_hi * [w_hi | w_lo] (raw fp32 stage: the MMA reads the top 19 bits)
 #pragma unroll
@@ -417,11 +424,13 @@ PFN_s2EncodeTiled s2_get_encode() {
     return nullptr;
 }
 
-template <int SW, int SH, int PW, int PH, int NP, int NBUF, int NACC, int LAG, bool TILEF>
+template <int SW, int SH, int PW, int PH, int KC, int NP, int NBUF, int NACC, int LAG, bool TILEF>
 int s2_launch(const CUtensorMap& tmap, S2P p, cudaStream_t s) {
-    const size_t smem = (size_t)NBUF * K4Geo<SW, PW>::STAGE + 16 * 2 * NP * S2_ROWB + 1024;
-    static_assert((size_t)NBUF * K4Geo<SW, PW>::STAGE + 16 * 2 * NP * S2_ROWB + 1024 + 2048 <= 232448, "shared memory budget");
-    auto kern = conv4x4s2_tc_kernel<SW, SH, PW, PH, NP, NBUF, NACC, LAG, TILEF>;
+    constexpr size_t SMEM = (size_t)NBUF * K4Geo<SW, PW, KC>::STAGE + 16 * 2 * NP * (KC * 4) + 1024;
+    static_assert(SMEM + 2048 <= 232448, "shared memory budget");
+    static_assert(NACC * 2 * NP <= 512, "TMEM columns");
+    const size_t smem = SMEM;
+    auto kern = conv4x4s2_tc_kernel<SW, SH, PW, PH, KC, NP, NBUF, NACC, LAG, TILEF>;
     static CoddDeviceOnce once;
     if (int rc = codd_once_per_device(once, [&] {
             return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -440,17 +449,17 @@ int s2_launch(const CUtensorMap& tmap, S2P p, cudaStream_t s) {
 
 namespace {
 // 5-D view {channel, column class (x mod SW), x / SW, row, sample} of an NHWC map whose width is a multiple of SW
-int s2_make_tmap(CUtensorMap* tmap, const float* in, int ldi, int cin, int n, int h, int w, int sw, int boxp) {
+int s2_make_tmap(CUtensorMap* tmap, const float* in, int ldi, int cin, int kc, int n, int h, int w, int sw, int boxp) {
     static PFN_s2EncodeTiled enc = s2_get_encode();      // C++11 magic static
     if (!enc) return CODD_E_UNSUPPORTED;
     const cuuint64_t gdim[5] = {(cuuint64_t)cin, (cuuint64_t)sw, (cuuint64_t)(w / sw), (cuuint64_t)h, (cuuint64_t)n};
     const cuuint64_t gstr[4] = {(cuuint64_t)ldi * 4, (cuuint64_t)ldi * 4 * sw, (cuuint64_t)w * ldi * 4,
                                 (cuuint64_t)h * w * ldi * 4};
-    const cuuint32_t box[5] = {(cuuint32_t)S2_KC, 1u, (cuuint32_t)boxp, 1u, 1u};
+    const cuuint32_t box[5] = {(cuuint32_t)kc, 1u, (cuuint32_t)boxp, 1u, 1u};
     const cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
     const CUresult r = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)in, gdim, gstr, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, kc == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : CODD_E_UNSUPPORTED;
 }
 }  // namespace
@@ -458,10 +467,12 @@ int s2_make_tmap(CUtensorMap* tmap, const float* in, int ldi, int cin, int n, in
 extern "C" int codd_conv4x4s2_tc(const float* in, int ldi, int cin, int n, int h, int w, const float* weight_split,
                                  const float* bias, int cout, int act, float* out, int ldo, void* stream) {
     if (!in || !weight_split || !out || n <= 0 || h <= 0 || w <= 0 || cout <= 0) return CODD_E_BADARG;
-    if (cin != S2_KC || cout > 32 || (w & 1) || (h & 1) || ldi % 4 != 0 || ldi < cin || ldo < cout) return CODD_E_UNSUPPORTED;
+    if ((cin != 16 && cin != 24 && cin != 32) || cout > 32 || (w & 1) || (h & 1) || ldi % 4 != 0 || ldi < cin || ldo < cout)
+        return CODD_E_UNSUPPORTED;
     if (!codd_aligned16(in)) return CODD_E_ALIGN;
+    const int kc = cin <= 16 ? 16 : 32;
     CUtensorMap tmap;
-    if (int rc = s2_make_tmap(&tmap, in, ldi, cin, n, h, w, 2, K4Geo<2, 1>::BOXP)) return rc;
+    if (int rc = s2_make_tmap(&tmap, in, ldi, cin, kc, n, h, w, 2, K4Geo<2, 1, 16>::BOXP)) return rc;
     S2P p;
     p.wpk = weight_split; p.bias = bias; p.out = out; p.w1 = nullptr; p.b1 = nullptr;
     p.N = n; p.Ho = h / 2; p.Wo = w / 2; p.Cout = cout; p.ldo = ldo; p.act = act;
@@ -470,20 +481,29 @@ extern "C" int codd_conv4x4s2_tc(const float* in, int ldi, int cin, int n, int h
     if (nt > 0x7fffffffLL) return CODD_E_SHAPE;
     p.ntiles = (int)nt;
     cudaStream_t s = (cudaStream_t)stream;
-    if (cout <= 16) return s2_launch<2, 2, 1, 1, 16, 6, 4, 2, false>(tmap, p, s);
-    return s2_launch<2, 2, 1, 1, 32, 6, 4, 2, false>(tmap, p, s);
+    if (kc == 16) {
+        if (cout <= 16) return s2_launch<2, 2, 1, 1, 16, 16, 6, 4, 2, false>(tmap, p, s);
+        return s2_launch<2, 2, 1, 1, 16, 32, 6, 4, 2, false>(tmap, p, s);
+    }
+    // Cin = 24 / 32 (down3, down4): 128 KB of weights leave room for two stages
+    if (cout <= 16) return s2_launch<2, 2, 1, 1, 32, 16, 3, 4, 1, false>(tmap, p, s);
+    return s2_launch<2, 2, 1, 1, 32, 32, 2, 4, 1, false>(tmap, p, s);
 }
 
-// Tile features on the tensor cores (Cin = 16): see the header comment.  w0_split as for codd_conv4x4s2_tc with NP = 16.
+// Tile features on the tensor cores: see the header comment.  w0_split as for codd_conv4x4s2_tc with NP = 16.
 extern "C" int codd_tile_features_tc(const float* in, int ldi, int cin, int n, int h_in, int w_in, const float* w0_split,
                                      const float* b0, const float* w1, const float* b1, int right, float* out,
                                      void* stream) {
     if (!in || !w0_split || !b0 || !w1 || !b1 || !out || n <= 0 || h_in <= 0 || w_in <= 0) return CODD_E_BADARG;
-    if (cin != S2_KC || ldi < cin || ldi % 4 != 0 || h_in % 4 != 0 || w_in % 4 != 0) return CODD_E_UNSUPPORTED;
+    if ((cin != 16 && cin != 24 && cin != 32) || ldi < cin || ldi % 4 != 0 || h_in % 4 != 0 || w_in % 4 != 0)
+        return CODD_E_UNSUPPORTED;
     if (!codd_aligned16(in)) return CODD_E_ALIGN;
+    const int kc = cin <= 16 ? 16 : 32;
     CUtensorMap tmap;
     const int sw = right ? 1 : 4;
-    if (int rc = s2_make_tmap(&tmap, in, ldi, cin, n, h_in, w_in, sw, right ? K4Geo<1, 0>::BOXP : K4Geo<4, 0>::BOXP)) return rc;
+    if (int rc = s2_make_tmap(&tmap, in, ldi, cin, kc, n, h_in, w_in, sw,
+                              right ? K4Geo<1, 0, 16>::BOXP : K4Geo<4, 0, 16>::BOXP))
+        return rc;
     S2P p;
     p.wpk = w0_split; p.bias = b0; p.out = out; p.w1 = w1; p.b1 = b1;
     p.N = n; p.Ho = h_in / 4; p.Wo = right ? w_in : w_in / 4; p.Cout = 16; p.ldo = 16; p.act = CODD_ACT_LEAKY;
@@ -492,6 +512,10 @@ extern "C" int codd_tile_features_tc(const float* in, int ldi, int cin, int n, i
     if (nt > 0x7fffffffLL) return CODD_E_SHAPE;
     p.ntiles = (int)nt;
     cudaStream_t s = (cudaStream_t)stream;
-    if (right) return s2_launch<1, 4, 0, 0, 16, 6, 4, 2, true>(tmap, p, s);
-    return s2_launch<4, 4, 0, 0, 16, 4, 4, 2, true>(tmap, p, s);
+    if (kc == 16) {
+        if (right) return s2_launch<1, 4, 0, 0, 16, 16, 6, 4, 2, true>(tmap, p, s);
+        return s2_launch<4, 4, 0, 0, 16, 16, 4, 4, 2, true>(tmap, p, s);
+    }
+    if (right) return s2_launch<1, 4, 0, 0, 32, 16, 4, 4, 2, true>(tmap, p, s);
+    return s2_launch<4, 4, 0, 0, 32, 16, 2, 4, 1, true>(tmap, p, s);
 }

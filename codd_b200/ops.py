@@ -169,22 +169,25 @@ def pack_conv_weight_tc(w):
 
 
 def pack_conv_weight_tc4(w):
-    """torch [Cout,16,4,4] -> [2][16][NP][16] hi/lo split for codd_conv4x4s2_tc (3xTF32), tap = ky*4 + kx."""
+    """torch [Cout,Cin,4,4] -> [2][16][NP][KC] hi/lo split for codd_conv4x4s2_tc / codd_tile_features_tc (3xTF32),
+    tap = ky*4 + kx, KC = 16 (Cin = 16) or 32 (Cin = 24, 32: zero-padded), NP = 16 | 32."""
     cout, cin, kh, kw = w.shape
-    assert kh == 4 and kw == 4 and cin == 16 and cout <= 32
+    assert kh == 4 and kw == 4 and cin in (16, 24, 32) and cout <= 32
     npad = 16 if cout <= 16 else 32
-    wt = torch.zeros((16, npad, 16), dtype=torch.float32, device=w.device)
-    wt[:, :cout, :] = w.detach().float().permute(2, 3, 0, 1).reshape(16, cout, cin)
+    kc = 16 if cin <= 16 else 32
+    wt = torch.zeros((16, npad, kc), dtype=torch.float32, device=w.device)
+    wt[:, :cout, :cin] = w.detach().float().permute(2, 3, 0, 1).reshape(16, cout, cin)
     hi = _tf32_round(wt)
     lo = _tf32_round(wt - hi)
     return torch.stack([hi, lo]).contiguous()
 
 
 def tc4_eligible(x, cout, k, stride, pad, dil, x2, residual):
-    """4x4 / stride 2 / pad 1, Cin = 16, Cout <= 32, even sizes, large enough to fill the persistent grid."""
+    """4x4 / stride 2 / pad 1, Cin in {16, 24, 32}, Cout <= 32, even sizes, large enough to fill the persistent grid
+    (a per-sample criterion: a sample's result must not depend on the batch it is in)."""
     n, cin, h, w = x.shape
     return (x2 is None and residual is None and tuple(k) == (4, 4) and tuple(stride) == (2, 2) and tuple(pad) == (1, 1)
-            and dil == 1 and cin == 16 and cout <= 32 and h % 2 == 0 and w % 2 == 0 and h * w >= 16384)
+            and dil == 1 and cin in (16, 24, 32) and cout <= 32 and h % 2 == 0 and w % 2 == 0 and h * w >= 4096)
 
 
 def conv4x4s2_tc(x, wsplit, bias, cout, act=ACT_NONE):
@@ -397,7 +400,7 @@ def tile_features(fea, w0p, b0, w1, b1, right):
 
 def tile_features_tc_eligible(fea):
     n, c, h, w = fea.shape
-    return c == 16 and h % 4 == 0 and w % 4 == 0 and h * w >= 16384
+    return c in (16, 24, 32) and h % 4 == 0 and w % 4 == 0 and h * w >= 2048
 
 
 def tile_features_tc(fea, w0split, b0, w1, b1, right):

@@ -57,7 +57,7 @@ class TileInitialization(nn.Module):
         input zero-padded by 3 columns on the right.  One fused kernel per side (K2), planar out."""
         w1, b1 = self._pw.raw(seq[2])
         if ops.tile_features_tc_eligible(fl):
-            # 16-channel levels: the 4x4 conv as a tcgen05 implicit GEMM (csrc/conv_tc_s2.cu)
+            # the 4x4 conv as a tcgen05 implicit GEMM (csrc/conv_tc_s2.cu)
             ws, b0 = self._pw.conv_tc4(seq[0])
             return (ops.tile_features_tc(fl, ws, b0, w1, b1, right=False),
                     ops.tile_features_tc(fr, ws, b0, w1, b1, right=True))

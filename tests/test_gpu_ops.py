@@ -122,14 +122,15 @@ def test_conv3x3_head1_residual_relu(ops):
     torch.testing.assert_close(back(ops, out), ref, rtol=CONV_RTOL, atol=CONV_ATOL)
 
 
-@pytest.mark.parametrize("n,h,w", [(2, 64, 256), (1, 128, 132), (1, 4, 4), (2, 36, 520)])
-def test_tile_features_tensor_core(ops, n, h, w):
+@pytest.mark.parametrize("c,n,h,w", [(16, 2, 64, 256), (16, 1, 128, 132), (16, 1, 4, 4), (16, 2, 36, 520), (24, 2, 72, 120),
+                                      (24, 1, 36, 264), (32, 2, 36, 60), (32, 1, 8, 520)])
+def test_tile_features_tensor_core(ops, c, n, h, w):
     """K2 on tcgen05 (Cin = 16): left = 4x4 stride 4, right = stride (4,1) over the input zero-padded by 3 columns
     (initialization.py:119-124), LeakyReLU + 1x1 + LeakyReLU, planar output — against the oracle, conv tolerance."""
-    g = gen(h * 7 + w)
-    sd = {"t.0.weight": torch.randn(16, 16, 4, 4, generator=g) / 16.0, "t.0.bias": torch.randn(16, generator=g),
+    g = gen(h * 7 + w + c)
+    sd = {"t.0.weight": torch.randn(16, c, 4, 4, generator=g) / (16 * c) ** 0.5, "t.0.bias": torch.randn(16, generator=g),
           "t.2.weight": torch.randn(16, 16, 1, 1, generator=g) / 4.0, "t.2.bias": torch.randn(16, generator=g)}
-    fl, fr = torch.randn(n, 16, h, w, generator=g), torch.randn(n, 16, h, w, generator=g)
+    fl, fr = torch.randn(n, c, h, w, generator=g), torch.randn(n, c, h, w, generator=g)
     tl, tr = O.tile_features_level(sd, "t", fl, fr)
     ws = ops.pack_conv_weight_tc4(sd["t.0.weight"].cuda())
     w1 = sd["t.2.weight"].reshape(16, 16).cuda().contiguous()
@@ -138,7 +139,7 @@ def test_tile_features_tensor_core(ops, n, h, w):
     got_r = ops.tile_features_tc(nhwc(ops, fr), *args, right=True)
     torch.cuda.synchronize()
     assert got_l.is_contiguous() and got_l.shape == tl.shape and got_r.shape == tr.shape
-    print(f"tile features tc {n}x{h}x{w}: max abs err left {(got_l.cpu() - tl).abs().max().item():.3e} "
+    print(f"tile features tc c={c} {n}x{h}x{w}: max abs err left {(got_l.cpu() - tl).abs().max().item():.3e} "
           f"right {(got_r.cpu() - tr).abs().max().item():.3e}")
     torch.testing.assert_close(got_l.cpu(), tl, rtol=CONV_RTOL, atol=CONV_ATOL)
     torch.testing.assert_close(got_r.cpu(), tr, rtol=CONV_RTOL, atol=CONV_ATOL)
@@ -440,27 +441,28 @@ def test_conv3x3_tensor_core_ring(ops, cin, cout, h, w):
     torch.testing.assert_close(got, ref, rtol=CONV_RTOL, atol=CONV_ATOL)
 
 
-@pytest.mark.parametrize("cout,n,h,w", [(16, 2, 64, 256), (24, 1, 130, 330), (16, 1, 2, 2), (32, 2, 36, 600), (3, 1, 70, 258),
-                                         (16, 3, 128, 128)])
-def test_conv4x4_stride2_tensor_core(ops, cout, n, h, w):
+@pytest.mark.parametrize("cin,cout,n,h,w", [(16, 16, 2, 64, 256), (16, 24, 1, 130, 330), (16, 16, 1, 2, 2), (16, 32, 2, 36, 600),
+                                             (16, 3, 1, 70, 258), (16, 16, 3, 128, 128), (24, 24, 2, 72, 120),
+                                             (24, 32, 1, 36, 300), (32, 16, 1, 20, 260), (32, 32, 2, 18, 30)])
+def test_conv4x4_stride2_tensor_core(ops, cin, cout, n, h, w):
     """conv_down first layer (backbone.py:8-14) on tcgen05: 4x4 / stride 2 / pad 1, Cin = 16, TMA boxes of same-parity
     columns, 3xTF32 — same bar as the fp32 CUDA-core convolution; ragged tile widths, single-tile and padded-filter
     (Cout = 24, 3) cases."""
     from codd_b200.lib import ACT_LEAKY
-    g = gen(cout * 1000 + h + w)
-    x = torch.randn(n, 16, h, w, generator=g)
-    wt = torch.randn(cout, 16, 4, 4, generator=g) / 16.0
+    g = gen(cout * 1000 + h + w + cin)
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, 4, 4, generator=g) / (16 * cin) ** 0.5
     b = torch.randn(cout, generator=g)
     ref = F.leaky_relu(F.conv2d(x, wt, b, stride=2, padding=1), 0.2)
     out = ops.conv4x4s2_tc(nhwc(ops, x), ops.pack_conv_weight_tc4(wt.cuda()), b.cuda(), cout, ACT_LEAKY)
     torch.cuda.synchronize()
     got = back(ops, out)
-    print(f"conv4x4s2tc cout={cout} {n}x{h}x{w}: max abs err {(got - ref).abs().max().item():.3e}")
+    print(f"conv4x4s2tc cin={cin} cout={cout} {n}x{h}x{w}: max abs err {(got - ref).abs().max().item():.3e}")
     torch.testing.assert_close(got, ref, rtol=CONV_RTOL, atol=CONV_ATOL)
     # a channel slice of a wider buffer as input (ld > C)
-    wide = ops.empty_nhwc(n, 32, h, w, "cuda")
-    wide[:, 8:24].copy_(x.cuda())
-    out2 = ops.conv4x4s2_tc(wide[:, 8:24], ops.pack_conv_weight_tc4(wt.cuda()), b.cuda(), cout, ACT_LEAKY)
+    wide = ops.empty_nhwc(n, 48, h, w, "cuda")
+    wide[:, 8:8 + cin].copy_(x.cuda())
+    out2 = ops.conv4x4s2_tc(wide[:, 8:8 + cin], ops.pack_conv_weight_tc4(wt.cuda()), b.cuda(), cout, ACT_LEAKY)
     assert torch.equal(back(ops, out2), got)
 
 
