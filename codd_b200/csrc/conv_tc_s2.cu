@@ -27,9 +27,7 @@
 // shifted by kx pixels; the padding is TMA's out-of-bounds fill), followed in the epilogue by LeakyReLU, the 16x16 1x1
 // conv, LeakyReLU and a PLANAR store (what the cost-volume kernel reads).  General rule: input column
 // xi = SW*xo + kx - PW = SW*(xo + s) + r with r = (kx - PW) mod SW, s = floor((kx - PW) / SW): slot r, pixel shift s.
-#include <cuda.h>
-
-#include "common.cuh"
+#include "tc_util.cuh"
 
 namespace {
 
@@ -77,84 +75,6 @@ struct S2P {
     const float* w1;    // tile-feature epilogue: 1x1 conv [16][16] (torch layout) and its bias; out is PLANAR then
     const float* b1;
 };
-
-__device__ __forceinline__ uint32_t s2_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void s2_mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void s2_mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void s2_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void s2_mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    while (!done) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (!done) __nanosleep(32);   // a polling warp must not starve the working warps of its SM sub-partition
-    }
-}
-__device__ __forceinline__ void s2_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void s2_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void s2_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-template <bool ACC>
-__device__ __forceinline__ void s2_mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc) {
-    if (ACC) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "setp.eq.u32 p, 1, 1;\n\t"
-            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-            ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc)
-            : "memory");
-    } else {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "setp.eq.u32 p, 1, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-            ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc)
-            : "memory");
-    }
-}
-__device__ __forceinline__ void s2_ld16(uint32_t taddr, float* v) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
-        "[%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// shared-memory matrix descriptor, K-major, swizzled (64-byte rows: SWIZZLE_64B, 128-byte rows: SWIZZLE_128B), as
-// conv_tc.cu make_desc
-template <int KC>
-__device__ __forceinline__ uint64_t s2_desc(uint32_t saddr) {
-    constexpr uint32_t ROWB = KC * 4;
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);               // start address
-    d |= (uint64_t)1 << 16;                                 // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)((8 * ROWB) >> 4) << 32;                 // stride byte offset: 8-row group pitch
-    d |= (uint64_t)1 << 46;                                 // descriptor version (Blackwell)
-    d |= ((KC == 32) ? 2ull : 4ull) << 61;                  // SWIZZLE_128B : SWIZZLE_64B
-    return d;
-}
-// byte offset of 16-byte chunk j of row r inside a K-major swizzled tile whose base is 1024-aligned
-template <int KC>
-__device__ __forceinline__ uint32_t s2_swz(int r, int j) {
-    const uint32_t off = (uint32_t)r * (KC * 4) + (uint32_t)j * 16u;
-    return off ^ (((off >> 7) & ((KC == 32) ? 7u : 3u)) << 4);
-}
 
 // NBUF stage buffers, NACC accumulator buffers, pass B trails pass A by LAG stages (LAG < NBUF).
 // SW / SH: strides, PW / PH: left / top padding, TILEF: tile-feature epilogue (LeakyReLU, 1x1, LeakyReLU, planar store)
@@ -240,7 +160,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) conv4x4s2_tc_kernel(const __gri
                 const int xo0 = tx * S2_TW;
                 for (int ky = 0; ky < 4; ++ky, ++it) {
                     const int sb = it % NBUF;
-                    s2_mbar_wait(SBAR(EMPTY, sb), (((uint32_t)(it / NBUF)) & 1u) ^ 1u);
+                    s2_mbar_wait<false>(SBAR(EMPTY, sb), (((uint32_t)(it / NBUF)) & 1u) ^ 1u);
                     s2_mbar_expect_tx(SBAR(FULL, sb), G::NSLOT * BOX_BYTES);
                     const int y = SH * yo + ky - PH;
                     // slot r: columns SW*p + r, p from xo0 + smin(r) (stride 2, pad 1: slot 0 = even columns from xo0 for
@@ -263,7 +183,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) conv4x4s2_tc_kernel(const __gri
             // pass B of stage j: x_lo * w_hi into columns [0, NP) of its tile's accumulator
             auto pass_b = [&](int j) {
                 const int sb = j % NBUF, ky = j & 3, ab = (j >> 2) % NACC;
-                s2_mbar_wait(SBAR(LO, sb), ((uint32_t)(j / NBUF)) & 1u);
+                s2_mbar_wait<false>(SBAR(LO, sb), ((uint32_t)(j / NBUF)) & 1u);
                 s2_fence_after();
                 const uint64_t a_desc = s2_desc<KC>(sbase + sb * S2_STAGE);
                 const uint32_t d_tmem = tmem + (uint32_t)ab * ACC_COLS;
@@ -282,8 +202,8 @@ __global__ void __launch_bounds__(S2_THREADS, 1) conv4x4s2_tc_kernel(const __gri
             for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
                 for (int ky = 0; ky < 4; ++ky, ++it) {
                     const int sb = it % NBUF, ti = it >> 2, ab = ti % NACC;
-                    s2_mbar_wait(SBAR(FULL, sb), ((uint32_t)(it / NBUF)) & 1u);
-                    if (ky == 0) s2_mbar_wait(ABAR(ACCE, ab), (((uint32_t)(ti / NACC)) & 1u) ^ 1u);
+                    s2_mbar_wait<false>(SBAR(FULL, sb), ((uint32_t)(it / NBUF)) & 1u);
+                    if (ky == 0) s2_mbar_wait<false>(ABAR(ACCE, ab), (((uint32_t)(ti / NACC)) & 1u) ^ 1u);
                     s2_fence_after();
                     const uint64_t a_desc = s2_desc<KC>(sbase + sb * S2_STAGE);
                     const uint32_t d_tmem = tmem + (uint32_t)ab * ACC_COLS;
@@ -322,7 +242,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) conv4x4s2_tc_kernel(const __gri
             q /= p.tilesX;
             const int yo = q % p.Ho;
             const int n = q / p.Ho;
-            s2_mbar_wait(ABAR(ACCF, ab), ((uint32_t)(ti / NACC)) & 1u);
+            s2_mbar_wait<true, 128>(ABAR(ACCF, ab), ((uint32_t)(ti / NACC)) & 1u);
             s2_fence_after();
             float acc[ACC_COLS];
 #pragma unroll
@@ -384,19 +304,36 @@ __global__ void __launch_bounds__(S2_THREADS, 1) conv4x4s2_tc_kernel(const __gri
         for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
             for (int ky = 0; ky < 4; ++ky, ++it) {
                 const int sb = it % NBUF;
-                s2_mbar_wait(SBAR(P12, sb), ((uint32_t)(it / NBUF)) & 1u);   // pass A has consumed the raw stage
+                s2_mbar_wait<true, 128>(SBAR(P12, sb), ((uint32_t)(it / NBUF)) & 1u);   // pass A has consumed the raw stage
                 s2_fence_after();
+                // all loads of a stage first (up to NSLOT * 3 independent 128-bit reads in flight per thread), then the
+                // conversions and the stores: the split warps are the pacing role of this kernel (ncu: 36 % of the samples)
+                constexpr int PER_SLOT = (int)(BOX_BYTES / 16);
+                constexpr int ITERS = (PER_SLOT + S2_SPLIT_THREADS - 1) / S2_SPLIT_THREADS;
+                float4 v[G::NSLOT][ITERS];
+#pragma unroll
+                for (int r = 0; r < G::NSLOT; ++r) {
+                    const float4* a4 = reinterpret_cast<const float4*>(gbase + sb * S2_STAGE + r * S2_SLOT);
+#pragma unroll
+                    for (int i = 0; i < ITERS; ++i) {
+                        const int idx = tid + i * S2_SPLIT_THREADS;
+                        if (idx < PER_SLOT) v[r][i] = a4[idx];
+                    }
+                }
 #pragma unroll
                 for (int r = 0; r < G::NSLOT; ++r) {
                     float4* a4 = reinterpret_cast<float4*>(gbase + sb * S2_STAGE + r * S2_SLOT);
-#pragma unroll 2
-                    for (int idx = tid; idx < (int)(BOX_BYTES / 16); idx += S2_SPLIT_THREADS) {
-                        float4 v = a4[idx];
-                        v.x = __fsub_rn(v.x, __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u));
-                        v.y = __fsub_rn(v.y, __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u));
-                        v.z = __fsub_rn(v.z, __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u));
-                        v.w = __fsub_rn(v.w, __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
-                        a4[idx] = v;
+#pragma unroll
+                    for (int i = 0; i < ITERS; ++i) {
+                        const int idx = tid + i * S2_SPLIT_THREADS;
+                        if (idx < PER_SLOT) {
+                            float4 q = v[r][i];
+                            q.x = __fsub_rn(q.x, __uint_as_float(__float_as_uint(q.x) & 0xFFFFE000u));
+                            q.y = __fsub_rn(q.y, __uint_as_float(__float_as_uint(q.y) & 0xFFFFE000u));
+                            q.z = __fsub_rn(q.z, __uint_as_float(__float_as_uint(q.z) & 0xFFFFE000u));
+                            q.w = __fsub_rn(q.w, __uint_as_float(__float_as_uint(q.w) & 0xFFFFE000u));
+                            a4[idx] = q;
+                        }
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -410,18 +347,6 @@ __global__ void __launch_bounds__(S2_THREADS, 1) conv4x4s2_tc_kernel(const __gri
         s2_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
     }
-}
-
-typedef CUresult (*PFN_s2EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-PFN_s2EncodeTiled s2_get_encode() {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-        return (PFN_s2EncodeTiled)ptr;
-    return nullptr;
 }
 
 template <int SW, int SH, int PW, int PH, int KC, int NP, int NBUF, int NACC, int LAG, bool TILEF>
