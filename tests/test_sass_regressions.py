@@ -58,3 +58,27 @@ def test_no_stack_frame_in_the_call_free_kernels():
         stack = int(re.search(r"STACK:(\d+)", usage).group(1))
         local = int(re.search(r"LOCAL:(\d+)", usage).group(1))
         assert local == 0 and stack == 0, (name, usage)
+
+
+@needs_build
+def test_round2_kernels_use_the_blackwell_paths():
+    """K4 (tile_warp.cu): TMA tensor loads for the window, packed fp32x2 arithmetic in the channel loop, the `decrease`
+    tail on tensor-core MMAs.  Strided convolutions / tile features (conv_tc_s2.cu): tcgen05.mma + TMEM loads + 5-D TMA boxes,
+    no stack frame."""
+    k4 = {k: "\n".join(v) for k, v in _functions(_sass("tile_warp.o")).items() if "tile_warp_cost2_kernel" in k}
+    assert len(k4) == 6                                           # NSETS in {1,2} x C in {16,24,32}
+    for name, text in k4.items():
+        assert "UTMALDG" in text, name                            # cp.async.bulk.tensor window boxes
+        assert text.count("FFMA2") >= 24 and "FMUL2" in text and "FADD2" in text, name
+        assert text.count("HMMA.1688.F32.TF32") == 12, name       # 2 k-steps x 2 n-tiles x 3 (3xTF32)
+        assert "LDS.128" in text, name                            # the window reads stay 128-bit shared loads
+    s2 = {k: "\n".join(v) for k, v in _functions(_sass("conv_tc_s2.o")).items() if "conv4x4s2_tc_kernel" in k}
+    assert len(s2) == 8
+    for name, text in s2.items():
+        assert "UTCHMMA" in text or "UTCMMA" in text or re.search(r"UTC\w*MMA", text), name
+        assert "UTMALDG.5D" in text or "UTMALDG" in text, name
+        assert "LDTM" in text, name
+    res = subprocess.run(["cuobjdump", "-res-usage", os.path.join(BUILD, "conv_tc_s2.o")], capture_output=True, text=True,
+                         check=True).stdout
+    for name, usage in re.findall(r"Function (\S+):\s*\n\s*(.*)", res):
+        assert int(re.search(r"STACK:(\d+)", usage).group(1)) == 0, (name, usage)
