@@ -1,0 +1,176 @@
+// Fused conv_up + first layer of conv_merge of HITUNet (model/stereo/hitnet/backbone.py:17-32,75-88):
+//
+//   up  = LeakyReLU(ConvTranspose2d(k=2, s=2)(coarse) + b_up)                 (conv_up,  backbone.py:17-21)
+//   out = LeakyReLU(Conv2d 1x1(cat(skip, up)) + b_m)                          (conv_merge[0], backbone.py:24-32,76)
+//
+// A 2x2 / stride-2 transposed convolution has no overlap between taps — output pixel (y, x) is a Cc x Cu GEMV of its
+// parent pixel (y/2, x/2) with the weight slice of its position (y&1, x&1) — and the 1x1 conv that follows is another
+// per-pixel GEMV, so the up-sampled tensor never has to exist: per output pixel this kernel reads the skip pixel and the
+// parent pixel, keeps `up` in registers, and writes the merged pixel.  As two launches the pair moved the up-sampled
+// tensor through HBM twice (1.1 GB per step at the finest level: 0.31 ms deconvolution + 0.27 ms 1x1).
+// One thread = two pixels of one output row, 256 columns apart (same column parity => same weight slice, so every
+// 128-bit weight broadcast feeds both pixels); the row parity is the block's.  Packed FFMA2, weights in shared memory.
+#include "common.cuh"
+
+namespace {
+
+struct UmP {
+    const float* coarse; int ldc, Cc;     // [N, H/2, W/2, Cc] NHWC
+    const float* skip;   int lds, Cs;     // [N, H, W, Cs] NHWC
+    const float* w_up;                    // packed [4 positions dy*2+dx][Cc][Cu]
+    const float* b_up;                    // [Cu]
+    const float* w_m;                     // packed [Cs + Cu][Co]   (1x1: cat order = skip first)
+    const float* b_m;                     // [Co]
+    float* out; int ldo;                  // [N, H, W, Co] NHWC
+    int N, H, W;
+};
+
+constexpr int UM_THREADS = 256;
+constexpr int UM_PX = 2;
+
+template <int CU, int CO>
+__global__ void __launch_bounds__(UM_THREADS) upmerge_kernel(UmP p) {
+    extern __shared__ float4 um_smem4[];
+    float* s_wu = reinterpret_cast<float*>(um_smem4);        // [4][Cc][CU]
+    float* s_wm = s_wu + 4 * p.Cc * CU;                      // [Cs + CU][CO]
+    float* s_bu = s_wm + (p.Cs + CU) * CO;                   // [CU]
+    float* s_bm = s_bu + CU;                                 // [CO]
+    for (int i = threadIdx.x; i < 4 * p.Cc * CU; i += UM_THREADS) s_wu[i] = __ldg(p.w_up + i);
+    for (int i = threadIdx.x; i < (p.Cs + CU) * CO; i += UM_THREADS) s_wm[i] = __ldg(p.w_m + i);
+    for (int i = threadIdx.x; i < CU; i += UM_THREADS) s_bu[i] = __ldg(p.b_up + i);
+    for (int i = threadIdx.x; i < CO; i += UM_THREADS) s_bm[i] = __ldg(p.b_m + i);
+    __syncthreads();
+
+    const int y = blockIdx.y, n = blockIdx.z;
+    const int x0 = blockIdx.x * (UM_THREADS * UM_PX) + threadIdx.x;
+    if (x0 >= p.W) return;
+    int x[UM_PX];
+    bool ok[UM_PX];
+#pragma unroll
+    for (int q = 0; q < UM_PX; ++q) {
+        ok[q] = x0 + q * UM_THREADS < p.W;
+        x[q] = ok[q] ? x0 + q * UM_THREADS : x0;           // (a clamped duplicate: computed, not stored)
+    }
+    const int pos = ((y & 1) << 1) | (x0 & 1);              // UM_THREADS is even: both pixels share the column parity
+    const int Hc = p.H >> 1, Wc = p.W >> 1;
+
+    // ---- up = LeakyReLU(W_up[pos]^T * parent + b_up)
+    __align__(8) float up[UM_PX][CU];
+#pragma unroll
+    for (int q = 0; q < UM_PX; ++q)
+#pragma unroll
+        for (int c = 0; c < CU; ++c) up[q][c] = s_bu[c];
+    {
+        const float* cp[UM_PX];
+#pragma unroll
+        for (int q = 0; q < UM_PX; ++q) cp[q] = p.coarse + (((size_t)n * Hc + (y >> 1)) * Wc + (x[q] >> 1)) * p.ldc;
+        const float* wbase = s_wu + pos * p.Cc * CU;
+        for (int c = 0; c < p.Cc; c += 4) {
+            float4 a[UM_PX];
+#pragma unroll
+            for (int q = 0; q < UM_PX; ++q) a[q] = ldg4(cp[q] + c);
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                const float* wp = wbase + (c + cc) * CU;
+#pragma unroll
+                for (int o4 = 0; o4 < CU / 4; ++o4) {
+                    const float4 wv = *reinterpret_cast<const float4*>(wp + o4 * 4);
+#pragma unroll
+                    for (int q = 0; q < UM_PX; ++q) {
+                        const float av = cc == 0 ? a[q].x : cc == 1 ? a[q].y : cc == 2 ? a[q].z : a[q].w;
+                        fma4(&up[q][o4 * 4], av, wv);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < UM_PX; ++q)
+#pragma unroll
+            for (int c = 0; c < CU; ++c) up[q][c] = fmaxf(up[q][c], 0.f) + CODD_LEAKY_SLOPE * fminf(up[q][c], 0.f);
+    }
+
+    // ---- out = LeakyReLU(W_m^T * cat(skip, up) + b_m)
+    __align__(8) float acc[UM_PX][CO];
+#pragma unroll
+    for (int q = 0; q < UM_PX; ++q)
+#pragma unroll
+        for (int c = 0; c < CO; ++c) acc[q][c] = s_bm[c];
+    {
+        const float* sp[UM_PX];
+#pragma unroll
+        for (int q = 0; q < UM_PX; ++q) sp[q] = p.skip + (((size_t)n * p.H + y) * p.W + x[q]) * p.lds;
+        for (int c = 0; c < p.Cs; c += 4) {
+            float4 a[UM_PX];
+#pragma unroll
+            for (int q = 0; q < UM_PX; ++q) a[q] = ldg4(sp[q] + c);
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                const float* wp = s_wm + (c + cc) * CO;
+#pragma unroll
+                for (int o4 = 0; o4 < CO / 4; ++o4) {
+                    const float4 wv = *reinterpret_cast<const float4*>(wp + o4 * 4);
+#pragma unroll
+                    for (int q = 0; q < UM_PX; ++q) {
+                        const float av = cc == 0 ? a[q].x : cc == 1 ? a[q].y : cc == 2 ? a[q].z : a[q].w;
+                        fma4(&acc[q][o4 * 4], av, wv);
+                    }
+                }
+            }
+        }
+        const float* wmu = s_wm + p.Cs * CO;
+#pragma unroll
+        for (int cu = 0; cu < CU; ++cu) {
+            const float* wp = wmu + cu * CO;
+#pragma unroll
+            for (int o4 = 0; o4 < CO / 4; ++o4) {
+                const float4 wv = *reinterpret_cast<const float4*>(wp + o4 * 4);
+#pragma unroll
+                for (int q = 0; q < UM_PX; ++q) fma4(&acc[q][o4 * 4], up[q][cu], wv);
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < UM_PX; ++q) {
+        if (!ok[q]) continue;
+        float* op = p.out + (((size_t)n * p.H + y) * p.W + x[q]) * p.ldo;
+#pragma unroll
+        for (int o4 = 0; o4 < CO / 4; ++o4) {
+            float4 v = make_float4(acc[q][o4 * 4], acc[q][o4 * 4 + 1], acc[q][o4 * 4 + 2], acc[q][o4 * 4 + 3]);
+            v.x = fmaxf(v.x, 0.f) + CODD_LEAKY_SLOPE * fminf(v.x, 0.f);
+            v.y = fmaxf(v.y, 0.f) + CODD_LEAKY_SLOPE * fminf(v.y, 0.f);
+            v.z = fmaxf(v.z, 0.f) + CODD_LEAKY_SLOPE * fminf(v.z, 0.f);
+            v.w = fmaxf(v.w, 0.f) + CODD_LEAKY_SLOPE * fminf(v.w, 0.f);
+            *reinterpret_cast<float4*>(op + o4 * 4) = v;
+        }
+    }
+}
+
+template <int CU, int CO>
+int um_launch(const UmP& p, cudaStream_t s) {
+    const size_t smem = ((size_t)4 * p.Cc * CU + (size_t)(p.Cs + CU) * CO + CU + CO) * sizeof(float);
+    if (smem > 48 * 1024) return CODD_E_UNSUPPORTED;
+    dim3 grid((unsigned)codd_ceil_div(p.W, UM_THREADS * UM_PX), (unsigned)p.H, (unsigned)p.N);
+    upmerge_kernel<CU, CO><<<grid, UM_THREADS, smem, s>>>(p);
+    CODD_RETURN_IF_CUDA_ERROR();
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int codd_upmerge_nhwc(const float* coarse, int ldc, int cc, const float* skip, int lds, int cs,
+                                 const float* w_up, const float* b_up, int cu, const float* w_merge, const float* b_merge,
+                                 int co, int n, int h, int w, float* out, int ldo, void* stream) {
+    if (!coarse || !skip || !w_up || !b_up || !w_merge || !b_merge || !out || n <= 0 || h <= 0 || w <= 0) return CODD_E_BADARG;
+    if ((h & 1) || (w & 1) || cc <= 0 || cs <= 0 || cc % 4 || cs % 4 || ldc < cc || lds < cs || ldc % 4 || lds % 4 ||
+        ldo < co || ldo % 4 || h > 65535 || n > 65535)
+        return CODD_E_SHAPE;
+    if (!codd_aligned16(coarse) || !codd_aligned16(skip) || !codd_aligned16(out)) return CODD_E_ALIGN;
+    UmP p;
+    p.coarse = coarse; p.ldc = ldc; p.Cc = cc; p.skip = skip; p.lds = lds; p.Cs = cs;
+    p.w_up = w_up; p.b_up = b_up; p.w_m = w_merge; p.b_m = b_merge; p.out = out; p.ldo = ldo;
+    p.N = n; p.H = h; p.W = w;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (cu == 16 && co == 16) return um_launch<16, 16>(p, s);
+    if (cu == 24 && co == 24) return um_launch<24, 24>(p, s);
+    return CODD_E_UNSUPPORTED;
+}

@@ -35,6 +35,8 @@ SIGNATURES = {
     "codd_conv3x3_tc_ring": (c_int, [_FP, c_int, c_int, c_int, c_int, c_int, _FP, _FP, _FP, c_int, c_int, c_int, c_int,
                                      _FP, c_int, c_void_p]),
     "codd_conv4x4s2_tc": (c_int, [_FP, c_int, c_int, c_int, c_int, c_int, _FP, _FP, c_int, c_int, _FP, c_int, c_void_p]),
+    "codd_upmerge_nhwc": (c_int, [_FP, c_int, c_int, _FP, c_int, c_int, _FP, _FP, c_int, _FP, _FP, c_int, c_int, c_int, c_int,
+                                  _FP, c_int, c_void_p]),
     "codd_tile_features_tc": (c_int, [_FP, c_int, c_int, c_int, c_int, c_int, _FP, _FP, _FP, _FP, c_int, _FP, c_void_p]),
     "codd_conv3x3_image": (c_int, [_FP, _FP, c_int, c_int, c_int, _FP, _FP, c_int, _FP, c_int, c_void_p]),
     "codd_deconv2x2_nhwc": (c_int, [_FP, c_int, c_int, c_int, c_int, c_int, _FP, _FP, c_int, _FP, c_int, c_int,

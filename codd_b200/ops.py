@@ -371,6 +371,26 @@ def conv3x3_image(left, right, wp, bias, cout):
     return out
 
 
+def upmerge_eligible(coarse, skip, cu, co):
+    return (cu, co) in ((16, 16), (24, 24)) and coarse.shape[1] % 4 == 0 and skip.shape[1] % 4 == 0 and \
+        skip.shape[2] == 2 * coarse.shape[2] and skip.shape[3] == 2 * coarse.shape[3]
+
+
+def upmerge(coarse, skip, w_up, b_up, cu, w_merge, b_merge, co):
+    """LeakyReLU(conv1x1(cat(skip, LeakyReLU(deconv2x2(coarse))))) in one kernel (backbone.py:17-32,75-88): the
+    up-sampled tensor is never written.  w_up from pack_deconv_weight, w_merge from pack_conv_weight."""
+    _require_cuda(coarse, skip, w_up, b_up, w_merge, b_merge)
+    n, cs, h, w = skip.shape
+    cc = coarse.shape[1]
+    out = empty_nhwc(n, co, h, w, skip.device)
+    nbytes = 4 * (n * h * w * (cs + co) + coarse.numel())
+    rc = _run(f"upmerge_cc{cc}_cs{cs}_co{co}", nbytes, lambda: _lib.load().codd_upmerge_nhwc(
+        coarse.data_ptr(), ld_of(coarse), cc, skip.data_ptr(), ld_of(skip), cs, w_up.data_ptr(), b_up.data_ptr(), cu,
+        w_merge.data_ptr(), b_merge.data_ptr(), co, n, h, w, out.data_ptr(), ld_of(out), _stream()))
+    _lib.check(rc, "codd_upmerge_nhwc")
+    return out
+
+
 def deconv2x2(x, wp, bias, cout, act=ACT_LEAKY):
     _require_cuda(x, wp, bias)
     n, cin, h, w = x.shape

@@ -67,6 +67,17 @@ class HITUNet(nn.Module):
     def _merge(self, seq, skip, up):
         return self._c(seq[4], self._c(seq[2], self._c(seq[0], skip, up)))
 
+    def _up_merge(self, up_seq, merge_seq, skip, coarse):
+        """conv_up followed by conv_merge (backbone.py:17-32,75-88); the deconvolution and the 1x1 that consumes it run as
+        one kernel that never writes the up-sampled tensor."""
+        cu, co = up_seq[0].out_channels, merge_seq[0].out_channels
+        if ops.upmerge_eligible(coarse, skip, cu, co):
+            wu, bu = self._pw.deconv(up_seq[0])
+            wm, bm = self._pw.conv(merge_seq[0])
+            x = ops.upmerge(coarse, skip, wu, bu, cu, wm, bm, co)
+            return self._c(merge_seq[4], self._c(merge_seq[2], x))
+        return self._merge(merge_seq, skip, self._up(up_seq, coarse))
+
     def _features(self, left, right):
         wp, b = self._pw.conv(self.conv1[0])
         x0 = ops.conv3x3_image(left, right, wp, b, 16)
@@ -75,10 +86,10 @@ class HITUNet(nn.Module):
         x3 = self._down(self.down3, x2)
         x4 = self._down(self.down4[0], x3)
         x4 = self._c(self.down4[3], self._c(self.down4[1], x4))
-        u4 = self._merge(self.merge4, x3, self._up(self.up4, x4))
-        u3 = self._merge(self.merge3, x2, self._up(self.up3, u4))
-        u2 = self._merge(self.merge2, x1, self._up(self.up2, u3))
-        u1 = self._merge(self.merge1, x0, self._up(self.up1, u2))
+        u4 = self._up_merge(self.up4, self.merge4, x3, x4)
+        u3 = self._up_merge(self.up3, self.merge3, x2, u4)
+        u2 = self._up_merge(self.up2, self.merge2, x1, u3)
+        u1 = self._up_merge(self.up1, self.merge1, x0, u2)
         return [x4, u4, u3, u2, u1]
 
     # -- public ------------------------------------------------------------------------------

@@ -122,6 +122,24 @@ def test_conv3x3_head1_residual_relu(ops):
     torch.testing.assert_close(back(ops, out), ref, rtol=CONV_RTOL, atol=CONV_ATOL)
 
 
+@pytest.mark.parametrize("cc,cs,cu,co,n,h,w", [(16, 16, 16, 16, 2, 20, 600), (24, 16, 16, 16, 1, 6, 1030), (24, 24, 24, 24, 2, 10, 70),
+                                                (32, 24, 24, 24, 1, 4, 514), (16, 16, 16, 16, 1, 2, 2)])
+def test_upmerge_fused(ops, cc, cs, cu, co, n, h, w):
+    """conv_up + conv_merge[0] in one kernel (backbone.py:17-32,75-88) against the two torch ops it replaces."""
+    g = gen(cc * 10 + cs + h + w)
+    coarse = torch.randn(n, cc, h // 2, w // 2, generator=g)
+    skip = torch.randn(n, cs, h, w, generator=g)
+    wu = torch.randn(cc, cu, 2, 2, generator=g) / cc ** 0.5
+    bu = torch.randn(cu, generator=g)
+    wm = torch.randn(co, cs + cu, 1, 1, generator=g) / (cs + cu) ** 0.5
+    bm = torch.randn(co, generator=g)
+    up = F.leaky_relu(F.conv_transpose2d(coarse, wu, bu, stride=2), 0.2)
+    ref = F.leaky_relu(F.conv2d(torch.cat((skip, up), 1), wm, bm), 0.2)
+    out = ops.upmerge(nhwc(ops, coarse), nhwc(ops, skip), ops.pack_deconv_weight(wu).cuda(), bu.cuda(), cu,
+                      ops.pack_conv_weight(wm).cuda(), bm.cuda(), co)
+    torch.testing.assert_close(back(ops, out), ref, rtol=CONV_RTOL, atol=CONV_ATOL)
+
+
 @pytest.mark.parametrize("c,n,h,w", [(16, 2, 64, 256), (16, 1, 128, 132), (16, 1, 4, 4), (16, 2, 36, 520), (24, 2, 72, 120),
                                       (24, 1, 36, 264), (32, 2, 36, 60), (32, 1, 8, 520)])
 def test_tile_features_tensor_core(ops, c, n, h, w):
