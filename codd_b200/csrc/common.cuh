@@ -113,4 +113,19 @@ __device__ __forceinline__ void fma4(float* acc, float a, const float4& w) {
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256).  A thread that owns >= 32 contiguous bytes of an NHWC pixel moves
+// them as whole 32-byte sectors: half the memory instructions of the float4 form and no half-written sectors — the
+// lane-strided float4 epilogues cost ~8 L1 wavefronts per instruction.  `p` must be 32-byte aligned.
+__device__ __forceinline__ void stg8(float* p, const float* v) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+                 "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void ldg8(const float* p, float* v) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+}
+static inline bool codd_aligned32(const void* p) { return (((uintptr_t)p) & 31u) == 0; }
+
 static inline int codd_ceil_div(int a, int b) { return (a + b - 1) / b; }

@@ -58,6 +58,7 @@ __device__ __forceinline__ float4 conv_load4(const ConvP& p, size_t pix, int c) 
 // unrolled over 64 accumulators, made these kernels instruction-fetch bound.
 struct EpiFast {
     bool ok, res_vec, res_b;
+    bool v8;     // 32-byte sectors per thread (stg8 / ldg8): rows, channel base and pointers 32-byte aligned
     float slope, slope0;
 };
 __device__ __forceinline__ EpiFast epi_fast_setup(const ConvP& p, int cbase, int nc) {
@@ -69,12 +70,38 @@ __device__ __forceinline__ EpiFast epi_fast_setup(const ConvP& p, int cbase, int
            (!e.res_vec || (((p.ldr & 3) == 0) && ((((uintptr_t)p.res) & 15u) == 0)));
     e.slope = p.act == CODD_ACT_LEAKY ? CODD_LEAKY_SLOPE : (p.act == CODD_ACT_RELU ? 0.f : 1.f);
     e.slope0 = (p.act == CODD_ACT_RELU || p.act == CODD_ACT_RELU_CH0) ? 0.f : e.slope;
+    e.v8 = e.ok && (nc % 8 == 0) && ((cbase & 7) == 0) && ((p.ldo & 7) == 0) && ((((uintptr_t)p.out) & 31u) == 0) &&
+           (!e.res_vec || (((p.ldr & 7) == 0) && ((((uintptr_t)p.res) & 31u) == 0)));
     return e;
 }
 template <int NC>
 __device__ __forceinline__ void epi_fast_store(const ConvP& p, const EpiFast& e, const float* acc, size_t opix, int cbase) {
     float* op = p.out + opix * p.ldo + cbase;
     const float rb = e.res_b ? __ldg(p.res + opix * p.ldr) : 0.f;
+    if (NC % 8 == 0 && e.v8) {
+#pragma unroll
+        for (int o8 = 0; o8 < NC / 8; ++o8) {
+            float v[8], r[8];
+            if (e.res_vec) ldg8(p.res + opix * p.ldr + cbase + o8 * 8, r);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias) b = ldg4(p.bias + cbase + o8 * 8 + h * 4);
+                v[h * 4 + 0] = acc[o8 * 8 + h * 4 + 0] + b.x;
+                v[h * 4 + 1] = acc[o8 * 8 + h * 4 + 1] + b.y;
+                v[h * 4 + 2] = acc[o8 * 8 + h * 4 + 2] + b.z;
+                v[h * 4 + 3] = acc[o8 * 8 + h * 4 + 3] + b.w;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                v[k] += e.res_vec ? r[k] : rb;
+                const float sl = (cbase + o8 * 8 + k == 0) ? e.slope0 : e.slope;
+                v[k] = fmaxf(v[k], 0.f) + sl * fminf(v[k], 0.f);
+            }
+            stg8(op + o8 * 8, v);
+        }
+        return;
+    }
 #pragma unroll
     for (int o4 = 0; o4 < NC / 4; ++o4) {
         float4 v = make_float4(acc[o4 * 4], acc[o4 * 4 + 1], acc[o4 * 4 + 2], acc[o4 * 4 + 3]);
@@ -288,7 +315,7 @@ int dispatch_cout(const ConvP& p, cudaStream_t s) {
 // the whole [Cin][Cout] weight matrix sits in shared memory and is read as warp-uniform
 // broadcasts.  HBM-bound (AI = 2*Cin*Cout / (4*(Cin+Cout)) < 12 flop/B for every layer here).
 // ---------------------------------------------------------------------------------------------
-template <int CO, int PX_T>
+template <int CO, int PX_T, bool V8IN>
 __global__ void __launch_bounds__(256, 2) pointwise_kernel(ConvP p, size_t npix) {
     extern __shared__ float4 smem4[];
     float* s_w = reinterpret_cast<float*>(smem4);  // [Cin][CO]
@@ -308,22 +335,43 @@ __global__ void __launch_bounds__(256, 2) pointwise_kernel(ConvP p, size_t npix)
 #pragma unroll
     for (int q = 0; q < PX_T; ++q) pix[q] = min(base + (size_t)q * blockDim.x, npix - 1);
 
-    for (int c = 0; c < Cin; c += 4) {
-        float4 a[PX_T];
-        const bool first = c < p.C0;
+    if (V8IN) {
+        // 8 channels per step as one 256-bit load per pixel (whole 32-byte sectors; see ldg8)
+        for (int c = 0; c < Cin; c += 8) {
+            float a[PX_T][8];
+            const bool first = c < p.C0;
 #pragma unroll
-        for (int q = 0; q < PX_T; ++q)
-            a[q] = first ? ldg4(p.in0 + pix[q] * p.ld0 + c) : ldg4(p.in1 + pix[q] * p.ld1 + (c - p.C0));
+            for (int q = 0; q < PX_T; ++q)
+                ldg8(first ? p.in0 + pix[q] * p.ld0 + c : p.in1 + pix[q] * p.ld1 + (c - p.C0), a[q]);
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-            const float* wp = s_w + (c + cc) * CO;
+            for (int cc = 0; cc < 8; ++cc) {
+                const float* wp = s_w + (c + cc) * CO;
 #pragma unroll
-            for (int o4 = 0; o4 < CO / 4; ++o4) {
-                const float4 wv = *reinterpret_cast<const float4*>(wp + o4 * 4);
+                for (int o4 = 0; o4 < CO / 4; ++o4) {
+                    const float4 wv = *reinterpret_cast<const float4*>(wp + o4 * 4);
 #pragma unroll
-                for (int q = 0; q < PX_T; ++q) {
-                    const float av = cc == 0 ? a[q].x : cc == 1 ? a[q].y : cc == 2 ? a[q].z : a[q].w;
-                    fma4(&acc[q][o4 * 4], av, wv);
+                    for (int q = 0; q < PX_T; ++q) fma4(&acc[q][o4 * 4], a[q][cc], wv);
+                }
+            }
+        }
+    } else {
+        for (int c = 0; c < Cin; c += 4) {
+            float4 a[PX_T];
+            const bool first = c < p.C0;
+#pragma unroll
+            for (int q = 0; q < PX_T; ++q)
+                a[q] = first ? ldg4(p.in0 + pix[q] * p.ld0 + c) : ldg4(p.in1 + pix[q] * p.ld1 + (c - p.C0));
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                const float* wp = s_w + (c + cc) * CO;
+#pragma unroll
+                for (int o4 = 0; o4 < CO / 4; ++o4) {
+                    const float4 wv = *reinterpret_cast<const float4*>(wp + o4 * 4);
+#pragma unroll
+                    for (int q = 0; q < PX_T; ++q) {
+                        const float av = cc == 0 ? a[q].x : cc == 1 ? a[q].y : cc == 2 ? a[q].z : a[q].w;
+                        fma4(&acc[q][o4 * 4], av, wv);
+                    }
                 }
             }
         }
@@ -375,7 +423,11 @@ int launch_pointwise(const ConvP& p, cudaStream_t s) {
     const size_t npix = (size_t)p.N * p.H * p.W;
     const size_t smem = (size_t)(p.C0 + p.C1) * CO * sizeof(float);
     const unsigned grid = (unsigned)((npix + 256 * PX_T - 1) / (256 * PX_T));
-    pointwise_kernel<CO, PX_T><<<grid, 256, smem, s>>>(p, npix);
+    // 256-bit input loads when both sources are made of whole, 32-byte aligned 8-channel groups
+    const bool v8 = (p.C0 % 8 == 0) && (p.C1 % 8 == 0) && (p.ld0 % 8 == 0) && codd_aligned32(p.in0) &&
+                    (p.C1 == 0 || ((p.ld1 % 8 == 0) && codd_aligned32(p.in1)));
+    if (v8) pointwise_kernel<CO, PX_T, true><<<grid, 256, smem, s>>>(p, npix);
+    else pointwise_kernel<CO, PX_T, false><<<grid, 256, smem, s>>>(p, npix);
     CODD_RETURN_IF_CUDA_ERROR();
     return 0;
 }

@@ -340,6 +340,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const __grid_
         const bool full_vec = (p.Cout == NP) && ((p.ldo & 3) == 0) && ((((uintptr_t)p.out) & 15u) == 0);
         const bool res_vec = p.res && !p.res_bcast && (p.Cout == NP) && ((p.ldr & 3) == 0) &&
                              ((((uintptr_t)p.res) & 15u) == 0);
+        const bool full_vec8 = full_vec && ((p.ldo & 7) == 0) && ((((uintptr_t)p.out) & 31u) == 0);   // see stg8
+        const bool res_vec8 = res_vec && ((p.ldr & 7) == 0) && ((((uintptr_t)p.res) & 31u) == 0);
         float biasr[NP];                              // bias lives in registers for the whole kernel
 #pragma unroll
         for (int c = 0; c < NP; ++c) biasr[c] = (p.bias && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
@@ -384,6 +386,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const __grid_
                         const float rb = __ldg(rp);
 #pragma unroll
                         for (int c = 0; c < NP; ++c) v[c] += rb;
+                    } else if (res_vec8) {
+#pragma unroll
+                        for (int c8 = 0; c8 < NP; c8 += 8) {
+                            float r8[8];
+                            ldg8(rp + c8, r8);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) v[c8 + e] += r8[e];
+                        }
                     } else if (res_vec) {
 #pragma unroll
                         for (int c4 = 0; c4 < NP; c4 += 4) {
@@ -408,7 +418,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const __grid_
                     for (int c = 0; c < NP; ++c) v[c] = codd_act(v[c], p.act, c);
                 }
                 if (!(p.diag & 1)) {
-                    if (full_vec) {
+                    if (full_vec8) {
+#pragma unroll
+                        for (int c8 = 0; c8 < NP; c8 += 8) stg8(op + c8, &v[c8]);
+                    } else if (full_vec) {
 #pragma unroll
                         for (int c4 = 0; c4 < NP; c4 += 4)
                             *reinterpret_cast<float4*>(op + c4) = make_float4(v[c4], v[c4 + 1], v[c4 + 2], v[c4 + 3]);

@@ -457,6 +457,9 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
         const bool full_vec = (p.Cout == NP) && ((p.ldo & 3) == 0) && ((((uintptr_t)p.out) & 15u) == 0);
         const bool res_vec = p.res && !p.res_bcast && (p.Cout == NP) && ((p.ldr & 3) == 0) &&
                              ((((uintptr_t)p.res) & 15u) == 0);
+        // whole 32-byte sectors per thread where the pixel pitch allows (see stg8)
+        const bool full_vec8 = full_vec && ((p.ldo & 7) == 0) && ((((uintptr_t)p.out) & 31u) == 0);
+        const bool res_vec8 = res_vec && ((p.ldr & 7) == 0) && ((((uintptr_t)p.res) & 31u) == 0);
         float biasr[NP];
 #pragma unroll
         for (int c = 0; c < NP; ++c) biasr[c] = (p.bias && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
@@ -495,6 +498,14 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
                         const float rb = __ldg(rp);
 #pragma unroll
                         for (int c = 0; c < NP; ++c) v[c] += rb;
+                    } else if (res_vec8) {
+#pragma unroll
+                        for (int c8 = 0; c8 < NP; c8 += 8) {
+                            float r8[8];
+                            ldg8(rp + c8, r8);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) v[c8 + e] += r8[e];
+                        }
                     } else if (res_vec) {
 #pragma unroll
                         for (int c4 = 0; c4 < NP; c4 += 4) {
@@ -517,7 +528,10 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
 #pragma unroll
                     for (int c = 0; c < NP; ++c) v[c] = codd_act(v[c], p.act, c);
                 }
-                if (full_vec) {
+                if (full_vec8) {
+#pragma unroll
+                    for (int c8 = 0; c8 < NP; c8 += 8) stg8(op + c8, &v[c8]);
+                } else if (full_vec) {
 #pragma unroll
                     for (int c4 = 0; c4 < NP; c4 += 4)
                         *reinterpret_cast<float4*>(op + c4) = make_float4(v[c4], v[c4 + 1], v[c4 + 2], v[c4 + 3]);

@@ -231,6 +231,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) conv4x4s2_tc_kernel(const __gri
         const float slope = p.act == CODD_ACT_LEAKY ? CODD_LEAKY_SLOPE : (p.act == CODD_ACT_RELU ? 0.f : 1.f);
         const float slope0 = (p.act == CODD_ACT_RELU || p.act == CODD_ACT_RELU_CH0) ? 0.f : slope;
         const bool full_vec = ((p.ldo & 3) == 0) && ((((uintptr_t)p.out) & 15u) == 0) && (p.Cout % 4 == 0);
+        const bool full_vec8 = full_vec && ((p.ldo & 7) == 0) && ((((uintptr_t)p.out) & 31u) == 0) && (p.Cout % 8 == 0);
         float biasr[NP];
 #pragma unroll
         for (int c = 0; c < NP; ++c) biasr[c] = (p.bias && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
@@ -288,7 +289,11 @@ __global__ void __launch_bounds__(S2_THREADS, 1) conv4x4s2_tc_kernel(const __gri
 #pragma unroll
                 for (int c = 0; c < NP; ++c) v[c] = codd_act(v[c], p.act, c);
             }
-            if (full_vec) {
+            if (full_vec8) {
+#pragma unroll
+                for (int c8 = 0; c8 < NP; c8 += 8)
+                    if (c8 < p.Cout) stg8(op + c8, &v[c8]);
+            } else if (full_vec) {
 #pragma unroll
                 for (int c4 = 0; c4 < NP; c4 += 4)
                     if (c4 < p.Cout) *reinterpret_cast<float4*>(op + c4) = make_float4(v[c4], v[c4 + 1], v[c4 + 2], v[c4 + 3]);

@@ -23,6 +23,7 @@ struct UmP {
     const float* b_m;                     // [Co]
     float* out; int ldo;                  // [N, H, W, Co] NHWC
     int N, H, W;
+    int v8;                               // 256-bit output stores allowed
 };
 
 constexpr int UM_THREADS = 256;
@@ -133,6 +134,13 @@ __global__ void __launch_bounds__(UM_THREADS) upmerge_kernel(UmP p) {
     for (int q = 0; q < UM_PX; ++q) {
         if (!ok[q]) continue;
         float* op = p.out + (((size_t)n * p.H + y) * p.W + x[q]) * p.ldo;
+        if (p.v8) {   // whole 32-byte sectors per thread (see stg8)
+#pragma unroll
+            for (int c = 0; c < CO; ++c) acc[q][c] = fmaxf(acc[q][c], 0.f) + CODD_LEAKY_SLOPE * fminf(acc[q][c], 0.f);
+#pragma unroll
+            for (int o8 = 0; o8 < CO / 8; ++o8) stg8(op + o8 * 8, &acc[q][o8 * 8]);
+            continue;
+        }
 #pragma unroll
         for (int o4 = 0; o4 < CO / 4; ++o4) {
             float4 v = make_float4(acc[q][o4 * 4], acc[q][o4 * 4 + 1], acc[q][o4 * 4 + 2], acc[q][o4 * 4 + 3]);
@@ -169,6 +177,7 @@ extern "C" int codd_upmerge_nhwc(const float* coarse, int ldc, int cc, const flo
     p.coarse = coarse; p.ldc = ldc; p.Cc = cc; p.skip = skip; p.lds = lds; p.Cs = cs;
     p.w_up = w_up; p.b_up = b_up; p.w_m = w_merge; p.b_m = b_merge; p.out = out; p.ldo = ldo;
     p.N = n; p.H = h; p.W = w;
+    p.v8 = (ldo % 8 == 0) && codd_aligned32(out);
     cudaStream_t s = (cudaStream_t)stream;
     if (cu == 16 && co == 16) return um_launch<16, 16>(p, s);
     if (cu == 24 && co == 24) return um_launch<24, 24>(p, s);
