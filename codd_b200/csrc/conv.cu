@@ -458,6 +458,7 @@ __global__ void __launch_bounds__(128) conv3x3_image_kernel(const float* __restr
     if (x0 >= w) return;
     const float* img = (s < n ? left + (size_t)s * 3 * h * w : right + (size_t)(s - n) * 3 * h * w);
     const bool vec = (ldo & 3) == 0 && cout == CO && ((((uintptr_t)out) & 15u) == 0);
+    const bool vec8 = vec && (CO % 8 == 0) && (ldo & 7) == 0 && ((((uintptr_t)out) & 31u) == 0);
     const int y_end = min(h, (int)(blockIdx.y + 1) * IMG_ROWS);
 #pragma unroll 1
     for (int y = blockIdx.y * IMG_ROWS; y < y_end; ++y) {
@@ -495,7 +496,12 @@ __global__ void __launch_bounds__(128) conv3x3_image_kernel(const float* __restr
         for (int q = 0; q < PXI; ++q) {
             if (x0 + q >= w) break;
             float* op = out + (((size_t)s * h + y) * w + x0 + q) * ldo;
-            if (vec) {
+            if (vec8) {
+#pragma unroll
+                for (int i = 0; i < CO; ++i) acc[q][i] = fmaxf(acc[q][i], 0.f) + CODD_LEAKY_SLOPE * fminf(acc[q][i], 0.f);
+#pragma unroll
+                for (int o8 = 0; o8 < CO / 8; ++o8) stg8(op + o8 * 8, &acc[q][o8 * 8]);
+            } else if (vec) {
 #pragma unroll
                 for (int o4 = 0; o4 < CO / 4; ++o4) {
                     float4 v = make_float4(acc[q][o4 * 4], acc[q][o4 * 4 + 1], acc[q][o4 * 4 + 2], acc[q][o4 * 4 + 3]);
@@ -620,6 +626,7 @@ __global__ void __launch_bounds__(128) deconv2x2_kernel(const float* __restrict_
         }
     }
     const bool vec = (ldo & 3) == 0 && (cout & 3) == 0 && ((((uintptr_t)out) & 15u) == 0) && ((((uintptr_t)bias) & 15u) == 0);
+    const bool vec8 = vec && (CO % 8 == 0) && (ldo & 7) == 0 && (cout & 7) == 0 && ((((uintptr_t)out) & 31u) == 0);
     const ActSel asel = codd_act_sel(act);
 #pragma unroll
     for (int q = 0; q < DC_PX; ++q) {
@@ -628,7 +635,25 @@ __global__ void __launch_bounds__(128) deconv2x2_kernel(const float* __restrict_
         float* op = out + (((size_t)s * 2 * h + oy) * 2 * w + 2 * x) * ldo;
 #pragma unroll
         for (int d = 0; d < 2; ++d) {
-            if (vec && asel.simple) {
+            if (vec8 && asel.simple) {
+#pragma unroll
+                for (int o8 = 0; o8 < CO / 8; ++o8) {
+                    if (o8 * 8 >= cout) break;
+                    float r[8];
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const float4 b4 = ldg4(bias + o8 * 8 + hh * 4);
+                        r[hh * 4 + 0] = acc[q][d][o8 * 8 + hh * 4 + 0] + b4.x;
+                        r[hh * 4 + 1] = acc[q][d][o8 * 8 + hh * 4 + 1] + b4.y;
+                        r[hh * 4 + 2] = acc[q][d][o8 * 8 + hh * 4 + 2] + b4.z;
+                        r[hh * 4 + 3] = acc[q][d][o8 * 8 + hh * 4 + 3] + b4.w;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        r[k] = fmaxf(r[k], 0.f) + ((o8 == 0 && k == 0) ? asel.slope0 : asel.slope) * fminf(r[k], 0.f);
+                    stg8(op + d * ldo + o8 * 8, r);
+                }
+            } else if (vec && asel.simple) {
 #pragma unroll
                 for (int o4 = 0; o4 < CO / 4; ++o4) {
                     if (o4 * 4 >= cout) break;

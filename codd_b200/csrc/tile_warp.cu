@@ -42,6 +42,7 @@ struct W2P {
     const float* fl;
     const float* fr;      // NHWC [n][H][W][ldfr]
     int ldfl, ldfr;
+    int fl_v8;            // left-feature rows allow 256-bit loads (pitch and base 32-byte aligned)
     const float* cur;
     int ldc;
     const float* prev;
@@ -305,11 +306,21 @@ __global__ void __launch_bounds__(W2_THREADS, 2) tile_warp_cost2_kernel(const __
     float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f), q4 = c4;
     if (on) {
         const float* flp = p.fl + (((size_t)n * H + y) * W + x) * p.ldfl;
+        if (p.fl_v8) {           // whole 32-byte sectors per thread (see ldg8)
 #pragma unroll
-        for (int c = 0; c < C; c += 4) {
-            const float4 l4 = ldg4(flp + c);
-            lp[c / 2] = make_float2(l4.x, l4.y);
-            lp[c / 2 + 1] = make_float2(l4.z, l4.w);
+            for (int c = 0; c < C; c += 8) {
+                float l8[8];
+                ldg8(flp + c, l8);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) lp[c / 2 + e] = make_float2(l8[2 * e], l8[2 * e + 1]);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < C; c += 4) {
+                const float4 l4 = ldg4(flp + c);
+                lp[c / 2] = make_float2(l4.x, l4.y);
+                lp[c / 2 + 1] = make_float2(l4.z, l4.w);
+            }
         }
         c4 = ldg4(p.cur + (((size_t)n * p.h + i) * p.w + j) * p.ldc);
         if (NSETS == 2) {
@@ -607,6 +618,7 @@ int codd_tile_warp_cost2(const float* fea_l, int ldfl, const float* fea_r, int l
     if (r != CUDA_SUCCESS) return CODD_E_UNSUPPORTED;
     W2P p;
     p.fl = fea_l; p.ldfl = ldfl; p.fr = fea_r; p.ldfr = ldfr;
+    p.fl_v8 = (c % 8 == 0) && (ldfl % 8 == 0) && codd_aligned32(fea_l);
     p.cur = cur; p.ldc = ldc; p.prev = prev; p.ldp = ldp;
     p.dec_w = dec_w; p.dec_b = dec_b; p.N = n; p.h = h; p.w = w;
     p.aug = aug; p.ldaug = ldaug; p.raw = raw_cv;

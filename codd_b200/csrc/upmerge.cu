@@ -29,7 +29,18 @@ struct UmP {
 constexpr int UM_THREADS = 256;
 constexpr int UM_PX = 2;
 
-template <int CU, int CO>
+// 8 channels of one pixel: one 256-bit load when rows and base are 32-byte aligned (V8), else two 128-bit loads
+template <bool V8>
+__device__ __forceinline__ void um_load8(const float* p, float* v) {
+    if (V8) {
+        ldg8(p, v);
+    } else {
+        const float4 a = ldg4(p), b = ldg4(p + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+}
+
+template <int CU, int CO, bool V8>
 __global__ void __launch_bounds__(UM_THREADS) upmerge_kernel(UmP p) {
     extern __shared__ float4 um_smem4[];
     float* s_wu = reinterpret_cast<float*>(um_smem4);        // [4][Cc][CU]
@@ -66,21 +77,18 @@ __global__ void __launch_bounds__(UM_THREADS) upmerge_kernel(UmP p) {
 #pragma unroll
         for (int q = 0; q < UM_PX; ++q) cp[q] = p.coarse + (((size_t)n * Hc + (y >> 1)) * Wc + (x[q] >> 1)) * p.ldc;
         const float* wbase = s_wu + pos * p.Cc * CU;
-        for (int c = 0; c < p.Cc; c += 4) {
-            float4 a[UM_PX];
+        for (int c = 0; c < p.Cc; c += 8) {       // channel counts are multiples of 8 (checked by the entry point)
+            float a[UM_PX][8];
 #pragma unroll
-            for (int q = 0; q < UM_PX; ++q) a[q] = ldg4(cp[q] + c);
+            for (int q = 0; q < UM_PX; ++q) um_load8<V8>(cp[q] + c, a[q]);
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
+            for (int cc = 0; cc < 8; ++cc) {
                 const float* wp = wbase + (c + cc) * CU;
 #pragma unroll
                 for (int o4 = 0; o4 < CU / 4; ++o4) {
                     const float4 wv = *reinterpret_cast<const float4*>(wp + o4 * 4);
 #pragma unroll
-                    for (int q = 0; q < UM_PX; ++q) {
-                        const float av = cc == 0 ? a[q].x : cc == 1 ? a[q].y : cc == 2 ? a[q].z : a[q].w;
-                        fma4(&up[q][o4 * 4], av, wv);
-                    }
+                    for (int q = 0; q < UM_PX; ++q) fma4(&up[q][o4 * 4], a[q][cc], wv);
                 }
             }
         }
@@ -100,21 +108,18 @@ __global__ void __launch_bounds__(UM_THREADS) upmerge_kernel(UmP p) {
         const float* sp[UM_PX];
 #pragma unroll
         for (int q = 0; q < UM_PX; ++q) sp[q] = p.skip + (((size_t)n * p.H + y) * p.W + x[q]) * p.lds;
-        for (int c = 0; c < p.Cs; c += 4) {
-            float4 a[UM_PX];
+        for (int c = 0; c < p.Cs; c += 8) {
+            float a[UM_PX][8];
 #pragma unroll
-            for (int q = 0; q < UM_PX; ++q) a[q] = ldg4(sp[q] + c);
+            for (int q = 0; q < UM_PX; ++q) um_load8<V8>(sp[q] + c, a[q]);
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
+            for (int cc = 0; cc < 8; ++cc) {
                 const float* wp = s_wm + (c + cc) * CO;
 #pragma unroll
                 for (int o4 = 0; o4 < CO / 4; ++o4) {
                     const float4 wv = *reinterpret_cast<const float4*>(wp + o4 * 4);
 #pragma unroll
-                    for (int q = 0; q < UM_PX; ++q) {
-                        const float av = cc == 0 ? a[q].x : cc == 1 ? a[q].y : cc == 2 ? a[q].z : a[q].w;
-                        fma4(&acc[q][o4 * 4], av, wv);
-                    }
+                    for (int q = 0; q < UM_PX; ++q) fma4(&acc[q][o4 * 4], a[q][cc], wv);
                 }
             }
         }
@@ -158,7 +163,9 @@ int um_launch(const UmP& p, cudaStream_t s) {
     const size_t smem = ((size_t)4 * p.Cc * CU + (size_t)(p.Cs + CU) * CO + CU + CO) * sizeof(float);
     if (smem > 48 * 1024) return CODD_E_UNSUPPORTED;
     dim3 grid((unsigned)codd_ceil_div(p.W, UM_THREADS * UM_PX), (unsigned)p.H, (unsigned)p.N);
-    upmerge_kernel<CU, CO><<<grid, UM_THREADS, smem, s>>>(p);
+    const bool v8in = (p.ldc % 8 == 0) && (p.lds % 8 == 0) && codd_aligned32(p.coarse) && codd_aligned32(p.skip);
+    if (v8in) upmerge_kernel<CU, CO, true><<<grid, UM_THREADS, smem, s>>>(p);
+    else upmerge_kernel<CU, CO, false><<<grid, UM_THREADS, smem, s>>>(p);
     CODD_RETURN_IF_CUDA_ERROR();
     return 0;
 }
@@ -169,7 +176,7 @@ extern "C" int codd_upmerge_nhwc(const float* coarse, int ldc, int cc, const flo
                                  const float* w_up, const float* b_up, int cu, const float* w_merge, const float* b_merge,
                                  int co, int n, int h, int w, float* out, int ldo, void* stream) {
     if (!coarse || !skip || !w_up || !b_up || !w_merge || !b_merge || !out || n <= 0 || h <= 0 || w <= 0) return CODD_E_BADARG;
-    if ((h & 1) || (w & 1) || cc <= 0 || cs <= 0 || cc % 4 || cs % 4 || ldc < cc || lds < cs || ldc % 4 || lds % 4 ||
+    if ((h & 1) || (w & 1) || cc <= 0 || cs <= 0 || cc % 8 || cs % 8 || ldc < cc || lds < cs || ldc % 4 || lds % 4 ||
         ldo < co || ldo % 4 || h > 65535 || n > 65535)
         return CODD_E_SHAPE;
     if (!codd_aligned16(coarse) || !codd_aligned16(skip) || !codd_aligned16(out)) return CODD_E_ALIGN;

@@ -372,7 +372,7 @@ def conv3x3_image(left, right, wp, bias, cout):
 
 
 def upmerge_eligible(coarse, skip, cu, co):
-    return (cu, co) in ((16, 16), (24, 24)) and coarse.shape[1] % 4 == 0 and skip.shape[1] % 4 == 0 and \
+    return (cu, co) in ((16, 16), (24, 24)) and coarse.shape[1] % 8 == 0 and skip.shape[1] % 8 == 0 and \
         skip.shape[2] == 2 * coarse.shape[2] and skip.shape[3] == 2 * coarse.shape[3]
 
 

@@ -138,7 +138,7 @@ CODD_API int codd_deconv2x2_nhwc(const float* in, int ldi, int n, int h, int w, 
  *   out = LeakyReLU(conv1x1(cat(skip, LeakyReLU(deconv2x2(coarse) + b_up))) + b_merge)
  * without materialising the up-sampled tensor (csrc/upmerge.cu).  coarse [n,h/2,w/2,cc] (ldc), skip [n,h,w,cs] (lds),
  * w_up PACKED [4][cc][cu] (as codd_deconv2x2_nhwc), w_merge PACKED [cs+cu][co] (as codd_conv2d_nhwc for a 1x1), out
- * [n,h,w,co] (ldo).  (cu, co) in {(16,16), (24,24)}; CODD_E_UNSUPPORTED otherwise. */
+ * [n,h,w,co] (ldo).  cc and cs multiples of 8; (cu, co) in {(16,16), (24,24)}; CODD_E_UNSUPPORTED otherwise. */
 CODD_API int codd_upmerge_nhwc(const float* coarse, int ldc, int cc, const float* skip, int lds, int cs,
                                const float* w_up, const float* b_up, int cu, const float* w_merge,
                                const float* b_merge, int co, int n, int h, int w, float* out, int ldo, void* stream);
