@@ -224,6 +224,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
     __shared__ __align__(8) unsigned long long bars[2 * NBUF + 2 * NH + 2 * RING];
     __shared__ uint32_t tmem_base_slot;
     __shared__ int a_issued_s;      // staged rows whose pass A is in the tensor queue (written by the pass-A thread)
+    __shared__ __align__(16) float s_bias[NP];   // fast epilogue: bias as shared broadcasts (frees NP registers)
 
     const uint32_t sbase = (s_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gbase = smem_raw + (sbase - s_u32(smem_raw));
@@ -254,6 +255,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
             mbar_init(HBAR(HEMPTY, b), 1);
         }
         a_issued_s = 0;
+        for (int c = 0; c < NP; ++c) s_bias[c] = (p.bias && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
         for (int b = 0; b < RING; ++b) {
             mbar_init(ABAR(ACCF, b), 1);
             mbar_init(ABAR(ACCE, b), RG_EPI_THREADS);
@@ -460,11 +462,78 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
         // whole 32-byte sectors per thread where the pixel pitch allows (see stg8)
         const bool full_vec8 = full_vec && ((p.ldo & 7) == 0) && ((((uintptr_t)p.out) & 31u) == 0);
         const bool res_vec8 = res_vec && ((p.ldr & 7) == 0) && ((((uintptr_t)p.res) & 31u) == 0);
-        float biasr[NP];
-#pragma unroll
-        for (int c = 0; c < NP; ++c) biasr[c] = (p.bias && c < p.Cout) ? __ldg(p.bias + c) : 0.f;
         int orow = 0;
         long long w_accf = 0;
+        // Fast path (full channel group, 32-byte aligned rows, branch-free activation): the epilogue warps are the
+        // critical path of this kernel (cycle counters: ~85 % busy, the MMA threads wait for drained slots), so the row
+        // is drained in 16-channel chunks — the TMEM loads of chunk g+1 and its residual loads are in flight while
+        // chunk g is combined (packed fp32x2: hi + 2^-10 lo, + bias, + residual, max(v, slope*v)) and stored as
+        // 256-bit sectors; the slot is released as soon as the last TMEM load has landed.
+        const bool fast = full_vec8 && (!p.res || p.res_bcast || res_vec8) && (p.act <= CODD_ACT_RELU_CH0) && !(p.diag & 4);
+        if (fast) {
+            constexpr int NCH = NP / 16;
+            const float2 sl2 = make_float2(slope, slope), sl20 = make_float2(slope0, slope);
+            const float2 un = make_float2(1.f / RG_LO_SCALE, 1.f / RG_LO_SCALE);
+            const bool rvec = p.res && !p.res_bcast;
+            for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+                int q = item;
+                const int sg = q % p.nseg;
+                q /= p.nseg;
+                const int tx = q % p.tilesX;
+                const int n = q / p.tilesX;
+                const int y0 = sg * p.seg;
+                const int rows = min(p.seg, p.H - y0);
+                const int x = tx * RG_TW + quarter * 32 + lane;
+                const bool xin = x < p.W;
+                const int xc = xin ? x : p.W - 1;          // clamped: loads stay in bounds, stores are predicated
+                for (int r = 0; r < rows; ++r, ++orow) {
+                    const int slot = RING - 1 - (orow % RING);
+                    const size_t opix = ((size_t)n * p.H + (y0 + r)) * p.W + xc;
+                    float* op = p.out + opix * p.ldo;
+                    const float* rp = p.res ? p.res + opix * p.ldr : nullptr;
+                    const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * SLOT);
+                    float hi[2][16], lo[2][16], rr[2][16];
+                    mbar_wait_t(ABAR(ACCF, slot), ((uint32_t)(orow / RING)) & 1u, w_accf, timing);
+                    tc_fence_after();
+                    tc_ld16(tbase, hi[0]);
+                    tc_ld16(tbase + NP, lo[0]);
+                    if (rvec) { ldg8(rp, &rr[0][0]); ldg8(rp + 8, &rr[0][8]); }
+                    const float rb = (p.res && p.res_bcast) ? __ldg(rp) : 0.f;
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int g = 0; g < NCH; ++g) {
+                        const int cur = g & 1, nxt = cur ^ 1;
+                        if (g + 1 < NCH) {
+                            tc_ld16(tbase + (g + 1) * 16, hi[nxt]);
+                            tc_ld16(tbase + NP + (g + 1) * 16, lo[nxt]);
+                            if (rvec) { ldg8(rp + (g + 1) * 16, &rr[nxt][0]); ldg8(rp + (g + 1) * 16 + 8, &rr[nxt][8]); }
+                        } else {
+                            tc_fence_before();
+                            mbar_arrive(ABAR(ACCE, slot));      // every TMEM load of this row has completed
+                        }
+                        float v[16];
+#pragma unroll
+                        for (int c = 0; c < 16; c += 2) {
+                            float2 t = __ffma2_rn(make_float2(lo[cur][c], lo[cur][c + 1]), un, make_float2(hi[cur][c], hi[cur][c + 1]));
+                            t = __fadd2_rn(t, *reinterpret_cast<const float2*>(&s_bias[g * 16 + c]));
+                            if (p.res) t = __fadd2_rn(t, rvec ? make_float2(rr[cur][c], rr[cur][c + 1]) : make_float2(rb, rb));
+                            const float2 m = __fmul2_rn(t, (g == 0 && c == 0) ? sl20 : sl2);
+                            v[c] = fmaxf(t.x, m.x);
+                            v[c + 1] = fmaxf(t.y, m.y);
+                        }
+                        if (xin) {
+                            stg8(op + g * 16, &v[0]);
+                            stg8(op + g * 16 + 8, &v[8]);
+                        }
+                        if (g + 1 < NCH) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    }
+                }
+            }
+            if (p.dbg && tid == 256) p.dbg[blockIdx.x * 8 + 6] = w_accf;
+        } else {
+        float biasr[NP];
+#pragma unroll
+        for (int c = 0; c < NP; ++c) biasr[c] = s_bias[c];
         for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
             int q = item;
             const int sg = q % p.nseg;
@@ -543,6 +612,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
             }
         }
         if (p.dbg && tid == 256) p.dbg[blockIdx.x * 8 + 6] = w_accf;
+        }   // general path
     } else {
         // ===================== x_lo stage of a staged row (warps 0-3: even rows, warps 4-7: odd rows) =====================
         constexpr int UNITS = RG_BOXW * (KC / 8);                  // one unit = 8 channels of one pixel
