@@ -243,6 +243,28 @@ def conv3x3_tc_ring(x, wring, bias, cout, act=ACT_NONE, residual=None, res_bcast
     return out
 
 
+def ring2_eligible(x, cmid, cout, residual=None):
+    """Two stacked 16-channel 3x3 convolutions in one launch (codd_conv3x3x2_tc_ring): the same per-sample size rule as
+    the ring kernel, 32-byte aligned NHWC rows."""
+    return (x.shape[1] == 16 and cmid == 16 and cout == 16 and x.shape[2] * x.shape[3] >= 4096
+            and (residual is None or (ld_of(residual) % 8 == 0 and residual.data_ptr() % 32 == 0)))
+
+
+def conv3x3x2_tc_ring(x, wring_a, bias_a, act_a, wring_b, bias_b, act_b, residual=None):
+    """act_b(conv_b(act_a(conv_a(x))) [+ residual]) for 16 -> 16 -> 16 channels, the intermediate kept on chip."""
+    _require_cuda(x, wring_a, bias_a, wring_b, bias_b, residual)
+    n, cin, h, w = x.shape
+    out = empty_nhwc(n, 16, h, w, x.device)
+    nbytes = 4 * (n * h * w * (32 + (0 if residual is None else 16)) + wring_a.numel() + wring_b.numel())
+    rc = _run("conv3x3x2ring_c16", nbytes, lambda: _lib.load().codd_conv3x3x2_tc_ring(
+        x.data_ptr(), ld_of(x), n, h, w, wring_a.data_ptr(), None if bias_a is None else bias_a.data_ptr(), act_a,
+        wring_b.data_ptr(), None if bias_b is None else bias_b.data_ptr(),
+        None if residual is None else residual.data_ptr(), 0 if residual is None else ld_of(residual), act_b,
+        out.data_ptr(), ld_of(out), _stream()))
+    _lib.check(rc, "codd_conv3x3x2_tc_ring")
+    return out
+
+
 def pack_conv_weight_gemm(w):
     """torch [Cout,Cin,KH,KW] -> (B_hi, B_lo), each [Cout][KH*KW*Cin] (k = tap*Cin + ch), tf32 halves for codd_gemm_tc."""
     cout = w.shape[0]

@@ -15,6 +15,8 @@ from .. import ops
 USE_TC = os.environ.get("CODD_TC", "1") != "0"
 # dilation-1 layers use the rolling-ring tcgen05 kernel (csrc/conv_tc_ring.cu) unless CODD_TC_RING=0
 USE_RING = os.environ.get("CODD_TC_RING", "1") != "0"
+# stacked 16-channel 3x3 pairs run as one fused ring launch (csrc/conv_tc_ring2.cu) unless CODD_TC_RING2=0
+USE_RING2 = os.environ.get("CODD_TC_RING2", "1") != "0"
 
 
 def run_conv(pw, conv, x, act, x2=None, residual=None, res_bcast=False, head=None):
@@ -54,6 +56,22 @@ def run_conv(pw, conv, x, act, x2=None, residual=None, res_bcast=False, head=Non
         return ops.conv3x3_tc(x, ws, b, cout, act, residual=residual, res_bcast=res_bcast, dil=dl)
     wp, b = pw.conv(conv) if head is None else pw.conv_head(conv, head)
     return ops.conv2d(x, wp, b, cout, k, st, pd, dl, act, x2=x2, residual=residual, res_bcast=res_bcast)
+
+
+def run_conv_pair(pw, conv_a, act_a, conv_b, act_b, x, residual=None):
+    """act_b(conv_b(act_a(conv_a(x))) [+ residual]) for two stacked 3x3 convolutions: one fused rolling-ring launch when
+    both are 16 -> 16 (codd_conv3x3x2_tc_ring keeps the intermediate tensor on chip and is bit-identical to the two
+    launches it replaces), two ``run_conv`` calls otherwise."""
+    def plain3x3(c):
+        return (c.kernel_size == (3, 3) and c.stride == (1, 1) and c.padding == (1, 1) and c.dilation == (1, 1)
+                and c.in_channels == 16 and c.out_channels == 16)
+    if (USE_TC and USE_RING and USE_RING2 and plain3x3(conv_a) and plain3x3(conv_b) and max(act_a, act_b) <= ops.ACT_RELU_CH0
+            and ops.ring2_eligible(x, 16, 16, residual)):
+        wa, ba = pw.conv_ring(conv_a, None)
+        wb, bb = pw.conv_ring(conv_b, None)
+        return ops.conv3x3x2_tc_ring(x, wa, ba, act_a, wb, bb, act_b, residual=residual)
+    y = run_conv(pw, conv_a, x, act_a)
+    return run_conv(pw, conv_b, y, act_b, residual=residual)
 
 
 class PackedWeights:

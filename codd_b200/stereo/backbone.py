@@ -11,7 +11,7 @@ import torch.nn as nn
 from .. import ops
 from ..lib import ACT_LEAKY
 from ..registry import BACKBONES
-from ._params import PackedWeights, run_conv
+from ._params import PackedWeights, run_conv, run_conv_pair
 
 
 def _conv_down(inp, oup):
@@ -65,7 +65,7 @@ class HITUNet(nn.Module):
         return ops.deconv2x2(x, wp, b, seq[0].out_channels, ACT_LEAKY)
 
     def _merge(self, seq, skip, up):
-        return self._c(seq[4], self._c(seq[2], self._c(seq[0], skip, up)))
+        return run_conv_pair(self._pw, seq[2], ACT_LEAKY, seq[4], ACT_LEAKY, self._c(seq[0], skip, up))
 
     def _up_merge(self, up_seq, merge_seq, skip, coarse):
         """conv_up followed by conv_merge (backbone.py:17-32,75-88); the deconvolution and the 1x1 that consumes it run as
@@ -75,7 +75,7 @@ class HITUNet(nn.Module):
             wu, bu = self._pw.deconv(up_seq[0])
             wm, bm = self._pw.conv(merge_seq[0])
             x = ops.upmerge(coarse, skip, wu, bu, cu, wm, bm, co)
-            return self._c(merge_seq[4], self._c(merge_seq[2], x))
+            return run_conv_pair(self._pw, merge_seq[2], ACT_LEAKY, merge_seq[4], ACT_LEAKY, x)
         return self._merge(merge_seq, skip, self._up(up_seq, coarse))
 
     def _features(self, left, right):

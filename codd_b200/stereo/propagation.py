@@ -11,7 +11,7 @@ import torch.nn as nn
 from .. import ops
 from ..lib import ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_RELU_CH0
 from ..registry import MODELS
-from ._params import PackedWeights, run_conv
+from ._params import PackedWeights, run_conv, run_conv_pair
 
 
 def _convbn(cin, cout, k, stride, pad, dilation):
@@ -43,8 +43,7 @@ class _Runner:
     def _res(self, blk, x):
         """Sequential(BasicBlock, LeakyReLU): lrelu(conv2(lrelu(conv1(x))) + x)."""
         bb = blk[0]
-        y = self._conv(bb.conv1[0][0], x, ACT_LEAKY)
-        return self._conv(bb.conv2[0], y, ACT_LEAKY, residual=x)
+        return run_conv_pair(self._pw, bb.conv1[0][0], ACT_LEAKY, bb.conv2[0], ACT_LEAKY, x, residual=x)
 
 
 class TileUpdate0(nn.Module, _Runner):

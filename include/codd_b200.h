@@ -113,6 +113,17 @@ CODD_API int codd_conv3x3_tc_ring(const float* in, int ldi, int cin, int n, int 
                                   const float* bias, const float* residual, int ldr, int res_bcast, int cout, int act,
                                   float* out, int ldo, void* stream);
 
+/* Two stacked 3x3 / stride 1 / pad 1 convolutions, 16 -> 16 -> 16 channels, in one rolling-ring launch
+ * (csrc/conv_tc_ring2.cu):  out = act_b(conv_b(act_a(conv_a(in) + bias_a)) + bias_b [+ residual]).  The intermediate
+ * tensor never leaves the SM (TMEM -> fp16 operand tile in shared memory).  Replaces HITUNet conv_merge's 3x3 pair
+ * (backbone.py:17-32) and the 16-channel ResBlocks (propagation.py:103-121, residual = in).  Bit-identical to two
+ * codd_conv3x3_tc_ring launches.  weight_ring_a / _b as codd_conv3x3_tc_ring (cin = cout = 16); act_a, act_b in
+ * {NONE, LEAKY, RELU, RELU_CH0}; ldo (and ldr) multiples of 8 floats, out / residual 32-byte aligned;
+ * CODD_E_UNSUPPORTED / CODD_E_SHAPE / CODD_E_ALIGN otherwise (callers then issue the two launches). */
+CODD_API int codd_conv3x3x2_tc_ring(const float* in, int ldi, int n, int h, int w, const float* weight_ring_a,
+                                    const float* bias_a, int act_a, const float* weight_ring_b, const float* bias_b,
+                                    const float* residual, int ldr, int act_b, float* out, int ldo, void* stream);
+
 /* 4x4 / stride 2 / pad 1 convolution (HITUNet conv_down first layer, backbone.py:8-14) on the tensor cores, Cin = 16,
  * Cout <= 32, even H and W: implicit GEMM over TMA boxes of same-parity columns (csrc/conv_tc_s2.cu), 3xTF32.
  * weight_split (host: ops.pack_conv_weight_tc4) = [2][16 taps][NP][16], pass 0 = tf32 hi, pass 1 = lo, NP = 16 | 32.

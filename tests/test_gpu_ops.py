@@ -459,6 +459,41 @@ def test_conv3x3_tensor_core_ring(ops, cin, cout, h, w):
     torch.testing.assert_close(got, ref, rtol=CONV_RTOL, atol=CONV_ATOL)
 
 
+@pytest.mark.parametrize("n,h,w,res,acts", [(2, 40, 300, True, (1, 1)), (1, 1, 100, False, (1, 1)), (3, 2, 126, True, (1, 0)),
+                                              (1, 3, 127, False, (2, 1)), (2, 70, 64, True, (1, 3)), (1, 9, 253, True, (0, 1)),
+                                              (1, 130, 260, False, (1, 1)), (2, 17, 1, True, (1, 1))])
+def test_conv3x3_pair_fused_ring(ops, n, h, w, res, acts):
+    """Two stacked 16-channel 3x3 convolutions in one rolling-ring launch (conv_merge tail / ResBlock): fp32-class vs
+    torch, and BIT-IDENTICAL to two single-conv ring launches (same operand split, MMA order and epilogue arithmetic);
+    strips of 126 columns (ragged widths around 126 / 252), one-row and multi-segment heights, image-border zero rows
+    of the intermediate tensor."""
+    g = gen(n * 1000 + h * 10 + w)
+    x = torch.randn(n, 16, h, w, generator=g)
+    wa = torch.randn(16, 16, 3, 3, generator=g) / 12.0
+    wb = torch.randn(16, 16, 3, 3, generator=g) / 12.0
+    ba, bb = torch.randn(16, generator=g), torch.randn(16, generator=g)
+    act_a, act_b = acts
+    xn = nhwc(ops, x)
+    pa, pb = ops.pack_conv_weight_ring(wa.cuda()), ops.pack_conv_weight_ring(wb.cuda())
+    assert ops.ring2_eligible(xn, 16, 16, xn if res else None) or h * w < 4096
+    got = ops.conv3x3x2_tc_ring(xn, pa, ba.cuda(), act_a, pb, bb.cuda(), act_b, residual=xn if res else None)
+    t = ops.conv3x3_tc_ring(xn, pa, ba.cuda(), 16, act_a)
+    two = ops.conv3x3_tc_ring(t, pb, bb.cuda(), 16, act_b, residual=xn if res else None)
+    torch.cuda.synchronize()
+
+    def act(v, a):
+        if a == 1:
+            return F.leaky_relu(v, 0.2)
+        if a == 2:
+            return F.relu(v)
+        if a == 3:
+            return torch.cat([F.relu(v[:, :1]), v[:, 1:]], 1)
+        return v
+    ref = act(F.conv2d(act(F.conv2d(x, wa, ba, padding=1), act_a), wb, bb, padding=1) + (x if res else 0), act_b)
+    torch.testing.assert_close(back(ops, got), ref, rtol=CONV_RTOL, atol=CONV_ATOL)
+    assert torch.equal(back(ops, got), back(ops, two))
+
+
 @pytest.mark.parametrize("cin,cout,n,h,w", [(16, 16, 2, 64, 256), (16, 24, 1, 130, 330), (16, 16, 1, 2, 2), (16, 32, 2, 36, 600),
                                              (16, 3, 1, 70, 258), (16, 16, 3, 128, 128), (24, 24, 2, 72, 120),
                                              (24, 32, 1, 36, 300), (32, 16, 1, 20, 260), (32, 32, 2, 18, 30)])
