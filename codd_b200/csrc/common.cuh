@@ -129,3 +129,27 @@ __device__ __forceinline__ void ldg8(const float* p, float* v) {
 static inline bool codd_aligned32(const void* p) { return (((uintptr_t)p) & 31u) == 0; }
 
 static inline int codd_ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Programmatic dependent launch (PDL).  A kernel launched through codd_launch_pdl may start while the previous kernel
+// of the stream is still running: its CTAs become resident as SMs free up and run their prologue (barrier set-up, TMEM
+// allocation, weight staging — nothing the previous kernel writes) before they block in codd_pdl_wait(), which
+// returns once every earlier kernel has completed and flushed.  Such a kernel MUST call codd_pdl_wait() before its
+// first read of activations and before any global write.  codd_pdl_trigger() lets the NEXT kernel do the same with
+// respect to this one.  Works under stream capture (the graph gets programmatic edges).
+__device__ __forceinline__ void codd_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void codd_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline cudaError_t codd_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                          Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}

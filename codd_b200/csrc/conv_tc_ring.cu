@@ -176,6 +176,10 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_slot;
+    // everything above touched only weights / bias (constant inputs): the previous kernel of the stream may still be
+    // running (programmatic dependent launch); from here on its outputs are read and this kernel's outputs written
+    codd_pdl_trigger();
+    codd_pdl_wait();
 
     if (warp == 12) {
         // ===================== TMA producer: one staged row per step =====================
@@ -615,7 +619,7 @@ int launch_ring(const CUtensorMap& tmap, RgP p, cudaStream_t s) {
     p.nseg = codd_ceil_div(p.H, p.seg);
     p.nitems = strips * p.nseg;
     const int grid = p.nitems < sms ? p.nitems : sms;
-    kern<<<grid, RG_THREADS, smem, s>>>(tmap, p);
+    if (cudaError_t e = codd_launch_pdl(kern, dim3(grid), dim3(RG_THREADS), smem, s, tmap, p)) return (int)e;
     CODD_RETURN_IF_CUDA_ERROR();
     return 0;
 }

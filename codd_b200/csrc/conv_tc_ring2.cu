@@ -281,6 +281,8 @@ __global__ void __launch_bounds__(R2_THREADS, 1) conv3x3x2_tc_ring_kernel(const 
     tc_fence_after();
     const uint32_t tmem = tmem_base_slot;
     const uint32_t tmem_a = tmem, tmem_b = tmem + RING * SLOT;
+    codd_pdl_trigger();      // prologue above reads weights / bias only (see common.cuh)
+    codd_pdl_wait();
 
     if (warp == 12) {
         // ===================== TMA producer: one staged input row per step =====================
@@ -545,7 +547,9 @@ extern "C" int codd_conv3x3x2_tc_ring(const float* in, int ldi, int n, int h, in
     p.nseg = codd_ceil_div(p.H, p.seg);
     p.nitems = strips * p.nseg;
     const int grid = p.nitems < sms ? p.nitems : sms;
-    conv3x3x2_tc_ring_kernel<<<grid, R2_THREADS, smem, (cudaStream_t)stream>>>(tmap, p);
+    if (cudaError_t e = codd_launch_pdl(conv3x3x2_tc_ring_kernel, dim3(grid), dim3(R2_THREADS), smem, (cudaStream_t)stream,
+                                        tmap, p))
+        return (int)e;
     CODD_RETURN_IF_CUDA_ERROR();
     return 0;
 }
