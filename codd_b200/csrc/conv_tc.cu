@@ -262,6 +262,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const __grid_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_slot;
+    codd_pdl_trigger();      // prologue above reads weights / bias only (programmatic dependent launch, common.cuh)
+    codd_pdl_wait();
 
     if (warp == 12) {
         // ===================== TMA producer =====================
@@ -505,7 +507,7 @@ int launch_tc(const CUtensorMap& tmap, TcP p, cudaStream_t s) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = p.ntiles < sms ? p.ntiles : sms;
-    kern<<<grid, TC_THREADS, smem, s>>>(tmap, p);
+    if (cudaError_t e = codd_launch_pdl(kern, dim3(grid), dim3(TC_THREADS), smem, s, tmap, p)) return (int)e;
     CODD_RETURN_IF_CUDA_ERROR();
     return 0;
 }

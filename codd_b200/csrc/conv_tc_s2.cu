@@ -145,6 +145,8 @@ __global__ void __launch_bounds__(S2_THREADS, 1) conv4x4s2_tc_kernel(const __gri
     __syncthreads();
     s2_fence_after();
     const uint32_t tmem = tmem_base_slot;
+    codd_pdl_trigger();      // prologue above reads weights / bias only (programmatic dependent launch, common.cuh)
+    codd_pdl_wait();
 
     // stage counter `it` = 4 * (tile index of this CTA) + ky
     if (warp == 12) {
@@ -370,7 +372,7 @@ int s2_launch(const CUtensorMap& tmap, S2P p, cudaStream_t s) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = p.ntiles < sms ? p.ntiles : sms;
-    kern<<<grid, S2_THREADS, smem, s>>>(tmap, p);
+    if (cudaError_t e = codd_launch_pdl(kern, dim3(grid), dim3(S2_THREADS), smem, s, tmap, p)) return (int)e;
     CODD_RETURN_IF_CUDA_ERROR();
     return 0;
 }
