@@ -8,8 +8,8 @@
 // per-pixel GEMV, so the up-sampled tensor never has to exist: per output pixel this kernel reads the skip pixel and the
 // parent pixel, keeps `up` in registers, and writes the merged pixel.  As two launches the pair moved the up-sampled
 // tensor through HBM twice (1.1 GB per step at the finest level: 0.31 ms deconvolution + 0.27 ms 1x1).
-// One thread = two pixels of one output row, 256 columns apart (same column parity => same weight slice, so every
-// 128-bit weight broadcast feeds both pixels); the row parity is the block's.  Packed FFMA2, weights in shared memory.
+// One thread = NPAR parent pixels and their 2 x 2 x NPAR output pixels (see upmerge_kernel).  Packed FFMA2, weights in
+// shared memory.
 #include "common.cuh"
 
 namespace {
@@ -26,8 +26,7 @@ struct UmP {
     int v8;                               // 256-bit output stores allowed
 };
 
-constexpr int UM_THREADS = 256;
-constexpr int UM_PX = 2;
+constexpr int UM_THREADS = 128;
 
 // 8 channels of one pixel: one 256-bit load when rows and base are 32-byte aligned (V8), else two 128-bit loads
 template <bool V8>
@@ -40,8 +39,17 @@ __device__ __forceinline__ void um_load8(const float* p, float* v) {
     }
 }
 
-template <int CU, int CO, bool V8>
+// Second decomposition (round 2): PARENT-centric.  The first one gave a thread two output pixels of one row, 256 columns
+// apart; adjacent lanes then had different column parities, i.e. two weight slices per warp-wide shared load, and only
+// two pixels per weight broadcast: ncu showed the L1 / shared data pipe 85 % busy (81 M wavefronts, 20 M of them bank
+// conflicts) with the fp32 pipe at 21 %.  Now a thread owns NPAR parent pixels (128 columns apart) and produces their
+// 2 x NPAR output pixels of row 2*yp + dy, then the same for the other dy: both column parities live in one thread, so
+// every deconvolution weight load (two slices, warp-uniform addresses) feeds 2*NPAR pixels and every merge weight load
+// 2*NPAR pixels — 256 instead of ~450 shared wavefront pairs per four pixels — and a parent is fetched once per CTA row
+// pair instead of four times.
+template <int CU, int CO, int NPAR, bool V8>
 __global__ void __launch_bounds__(UM_THREADS) upmerge_kernel(UmP p) {
+    constexpr int NPX = 2 * NPAR;
     extern __shared__ float4 um_smem4[];
     float* s_wu = reinterpret_cast<float*>(um_smem4);        // [4][Cc][CU]
     float* s_wm = s_wu + 4 * p.Cc * CU;                      // [Cs + CU][CO]
@@ -53,65 +61,69 @@ __global__ void __launch_bounds__(UM_THREADS) upmerge_kernel(UmP p) {
     for (int i = threadIdx.x; i < CO; i += UM_THREADS) s_bm[i] = __ldg(p.b_m + i);
     __syncthreads();
 
-    const int y = blockIdx.y, n = blockIdx.z;
-    const int x0 = blockIdx.x * (UM_THREADS * UM_PX) + threadIdx.x;
-    if (x0 >= p.W) return;
-    int x[UM_PX];
-    bool ok[UM_PX];
-#pragma unroll
-    for (int q = 0; q < UM_PX; ++q) {
-        ok[q] = x0 + q * UM_THREADS < p.W;
-        x[q] = ok[q] ? x0 + q * UM_THREADS : x0;           // (a clamped duplicate: computed, not stored)
-    }
-    const int pos = ((y & 1) << 1) | (x0 & 1);              // UM_THREADS is even: both pixels share the column parity
     const int Hc = p.H >> 1, Wc = p.W >> 1;
+    const int yp = blockIdx.y, n = blockIdx.z;
+    const int xp0 = blockIdx.x * (UM_THREADS * NPAR) + threadIdx.x;
+    if (xp0 >= Wc) return;
+    int xp[NPAR];
+    bool ok[NPAR];
+    const float* cp[NPAR];
+#pragma unroll
+    for (int q = 0; q < NPAR; ++q) {
+        ok[q] = xp0 + q * UM_THREADS < Wc;
+        xp[q] = ok[q] ? xp0 + q * UM_THREADS : xp0;          // (a clamped duplicate: computed, not stored)
+        cp[q] = p.coarse + (((size_t)n * Hc + yp) * Wc + xp[q]) * p.ldc;
+    }
 
-    // ---- up = LeakyReLU(W_up[pos]^T * parent + b_up)
-    __align__(8) float up[UM_PX][CU];
+#pragma unroll 1
+    for (int dy = 0; dy < 2; ++dy) {
+        const int y = 2 * yp + dy;
+        // ---- up[2q + dx] = LeakyReLU(W_up[dy][dx]^T * parent_q + b_up)
+        __align__(8) float up[NPX][CU];
 #pragma unroll
-    for (int q = 0; q < UM_PX; ++q)
+        for (int j = 0; j < NPX; ++j)
 #pragma unroll
-        for (int c = 0; c < CU; ++c) up[q][c] = s_bu[c];
-    {
-        const float* cp[UM_PX];
+            for (int c = 0; c < CU; ++c) up[j][c] = s_bu[c];
+        {
+            const float* w0 = s_wu + (dy * 2 + 0) * p.Cc * CU;
+            const float* w1 = s_wu + (dy * 2 + 1) * p.Cc * CU;
+            for (int c = 0; c < p.Cc; c += 8) {             // channel counts are multiples of 8 (checked by the entry point)
+                float a[NPAR][8];
 #pragma unroll
-        for (int q = 0; q < UM_PX; ++q) cp[q] = p.coarse + (((size_t)n * Hc + (y >> 1)) * Wc + (x[q] >> 1)) * p.ldc;
-        const float* wbase = s_wu + pos * p.Cc * CU;
-        for (int c = 0; c < p.Cc; c += 8) {       // channel counts are multiples of 8 (checked by the entry point)
-            float a[UM_PX][8];
+                for (int q = 0; q < NPAR; ++q) um_load8<V8>(cp[q] + c, a[q]);
 #pragma unroll
-            for (int q = 0; q < UM_PX; ++q) um_load8<V8>(cp[q] + c, a[q]);
+                for (int cc = 0; cc < 8; ++cc) {
 #pragma unroll
-            for (int cc = 0; cc < 8; ++cc) {
-                const float* wp = wbase + (c + cc) * CU;
+                    for (int o4 = 0; o4 < CU / 4; ++o4) {
+                        const float4 u = *reinterpret_cast<const float4*>(w0 + (c + cc) * CU + o4 * 4);
+                        const float4 v = *reinterpret_cast<const float4*>(w1 + (c + cc) * CU + o4 * 4);
 #pragma unroll
-                for (int o4 = 0; o4 < CU / 4; ++o4) {
-                    const float4 wv = *reinterpret_cast<const float4*>(wp + o4 * 4);
-#pragma unroll
-                    for (int q = 0; q < UM_PX; ++q) fma4(&up[q][o4 * 4], a[q][cc], wv);
+                        for (int q = 0; q < NPAR; ++q) {
+                            fma4(&up[2 * q][o4 * 4], a[q][cc], u);
+                            fma4(&up[2 * q + 1][o4 * 4], a[q][cc], v);
+                        }
+                    }
                 }
             }
+#pragma unroll
+            for (int j = 0; j < NPX; ++j)
+#pragma unroll
+                for (int c = 0; c < CU; ++c) up[j][c] = fmaxf(up[j][c], 0.f) + CODD_LEAKY_SLOPE * fminf(up[j][c], 0.f);
         }
-#pragma unroll
-        for (int q = 0; q < UM_PX; ++q)
-#pragma unroll
-            for (int c = 0; c < CU; ++c) up[q][c] = fmaxf(up[q][c], 0.f) + CODD_LEAKY_SLOPE * fminf(up[q][c], 0.f);
-    }
 
-    // ---- out = LeakyReLU(W_m^T * cat(skip, up) + b_m)
-    __align__(8) float acc[UM_PX][CO];
+        // ---- out = LeakyReLU(W_m^T * cat(skip, up) + b_m)
+        __align__(8) float acc[NPX][CO];
 #pragma unroll
-    for (int q = 0; q < UM_PX; ++q)
+        for (int j = 0; j < NPX; ++j)
 #pragma unroll
-        for (int c = 0; c < CO; ++c) acc[q][c] = s_bm[c];
-    {
-        const float* sp[UM_PX];
+            for (int c = 0; c < CO; ++c) acc[j][c] = s_bm[c];
+        const float* sp[NPAR];                               // skip pixels 2*xp, 2*xp + 1 are adjacent: sp[q] + dx * lds
 #pragma unroll
-        for (int q = 0; q < UM_PX; ++q) sp[q] = p.skip + (((size_t)n * p.H + y) * p.W + x[q]) * p.lds;
+        for (int q = 0; q < NPAR; ++q) sp[q] = p.skip + (((size_t)n * p.H + y) * p.W + 2 * xp[q]) * p.lds;
         for (int c = 0; c < p.Cs; c += 8) {
-            float a[UM_PX][8];
+            float a[NPX][8];
 #pragma unroll
-            for (int q = 0; q < UM_PX; ++q) um_load8<V8>(sp[q] + c, a[q]);
+            for (int j = 0; j < NPX; ++j) um_load8<V8>(sp[j >> 1] + (j & 1) * p.lds + c, a[j]);
 #pragma unroll
             for (int cc = 0; cc < 8; ++cc) {
                 const float* wp = s_wm + (c + cc) * CO;
@@ -119,7 +131,7 @@ __global__ void __launch_bounds__(UM_THREADS) upmerge_kernel(UmP p) {
                 for (int o4 = 0; o4 < CO / 4; ++o4) {
                     const float4 wv = *reinterpret_cast<const float4*>(wp + o4 * 4);
 #pragma unroll
-                    for (int q = 0; q < UM_PX; ++q) fma4(&acc[q][o4 * 4], a[q][cc], wv);
+                    for (int j = 0; j < NPX; ++j) fma4(&acc[j][o4 * 4], a[j][cc], wv);
                 }
             }
         }
@@ -131,41 +143,36 @@ __global__ void __launch_bounds__(UM_THREADS) upmerge_kernel(UmP p) {
             for (int o4 = 0; o4 < CO / 4; ++o4) {
                 const float4 wv = *reinterpret_cast<const float4*>(wp + o4 * 4);
 #pragma unroll
-                for (int q = 0; q < UM_PX; ++q) fma4(&acc[q][o4 * 4], up[q][cu], wv);
+                for (int j = 0; j < NPX; ++j) fma4(&acc[j][o4 * 4], up[j][cu], wv);
             }
         }
-    }
 #pragma unroll
-    for (int q = 0; q < UM_PX; ++q) {
-        if (!ok[q]) continue;
-        float* op = p.out + (((size_t)n * p.H + y) * p.W + x[q]) * p.ldo;
-        if (p.v8) {   // whole 32-byte sectors per thread (see stg8)
+        for (int j = 0; j < NPX; ++j) {
+            if (!ok[j >> 1]) continue;
+            float* op = p.out + (((size_t)n * p.H + y) * p.W + 2 * xp[j >> 1] + (j & 1)) * p.ldo;
 #pragma unroll
-            for (int c = 0; c < CO; ++c) acc[q][c] = fmaxf(acc[q][c], 0.f) + CODD_LEAKY_SLOPE * fminf(acc[q][c], 0.f);
+            for (int c = 0; c < CO; ++c) acc[j][c] = fmaxf(acc[j][c], 0.f) + CODD_LEAKY_SLOPE * fminf(acc[j][c], 0.f);
+            if (p.v8) {   // whole 32-byte sectors per thread (see stg8)
 #pragma unroll
-            for (int o8 = 0; o8 < CO / 8; ++o8) stg8(op + o8 * 8, &acc[q][o8 * 8]);
-            continue;
-        }
+                for (int o8 = 0; o8 < CO / 8; ++o8) stg8(op + o8 * 8, &acc[j][o8 * 8]);
+            } else {
 #pragma unroll
-        for (int o4 = 0; o4 < CO / 4; ++o4) {
-            float4 v = make_float4(acc[q][o4 * 4], acc[q][o4 * 4 + 1], acc[q][o4 * 4 + 2], acc[q][o4 * 4 + 3]);
-            v.x = fmaxf(v.x, 0.f) + CODD_LEAKY_SLOPE * fminf(v.x, 0.f);
-            v.y = fmaxf(v.y, 0.f) + CODD_LEAKY_SLOPE * fminf(v.y, 0.f);
-            v.z = fmaxf(v.z, 0.f) + CODD_LEAKY_SLOPE * fminf(v.z, 0.f);
-            v.w = fmaxf(v.w, 0.f) + CODD_LEAKY_SLOPE * fminf(v.w, 0.f);
-            *reinterpret_cast<float4*>(op + o4 * 4) = v;
+                for (int o4 = 0; o4 < CO / 4; ++o4)
+                    *reinterpret_cast<float4*>(op + o4 * 4) =
+                        make_float4(acc[j][o4 * 4], acc[j][o4 * 4 + 1], acc[j][o4 * 4 + 2], acc[j][o4 * 4 + 3]);
+            }
         }
     }
 }
 
-template <int CU, int CO>
+template <int CU, int CO, int NPAR>
 int um_launch(const UmP& p, cudaStream_t s) {
     const size_t smem = ((size_t)4 * p.Cc * CU + (size_t)(p.Cs + CU) * CO + CU + CO) * sizeof(float);
     if (smem > 48 * 1024) return CODD_E_UNSUPPORTED;
-    dim3 grid((unsigned)codd_ceil_div(p.W, UM_THREADS * UM_PX), (unsigned)p.H, (unsigned)p.N);
+    dim3 grid((unsigned)codd_ceil_div(p.W / 2, UM_THREADS * NPAR), (unsigned)(p.H / 2), (unsigned)p.N);
     const bool v8in = (p.ldc % 8 == 0) && (p.lds % 8 == 0) && codd_aligned32(p.coarse) && codd_aligned32(p.skip);
-    if (v8in) upmerge_kernel<CU, CO, true><<<grid, UM_THREADS, smem, s>>>(p);
-    else upmerge_kernel<CU, CO, false><<<grid, UM_THREADS, smem, s>>>(p);
+    if (v8in) upmerge_kernel<CU, CO, NPAR, true><<<grid, UM_THREADS, smem, s>>>(p);
+    else upmerge_kernel<CU, CO, NPAR, false><<<grid, UM_THREADS, smem, s>>>(p);
     CODD_RETURN_IF_CUDA_ERROR();
     return 0;
 }
@@ -186,7 +193,10 @@ extern "C" int codd_upmerge_nhwc(const float* coarse, int ldc, int cc, const flo
     p.N = n; p.H = h; p.W = w;
     p.v8 = (ldo % 8 == 0) && codd_aligned32(out);
     cudaStream_t s = (cudaStream_t)stream;
-    if (cu == 16 && co == 16) return um_launch<16, 16>(p, s);
-    if (cu == 24 && co == 24) return um_launch<24, 24>(p, s);
+    // two parents per thread when a row of parents fills the 128-thread blocks that way (>= 3/4 of the slots used)
+    const int wc = w / 2;
+    const bool two = (wc % 256 == 0) || (wc % 256 > 192) || (wc > 256 && wc % 256 > 128);
+    if (cu == 16 && co == 16) return two ? um_launch<16, 16, 2>(p, s) : um_launch<16, 16, 1>(p, s);
+    if (cu == 24 && co == 24) return um_launch<24, 24, 1>(p, s);
     return CODD_E_UNSUPPORTED;
 }
