@@ -82,3 +82,30 @@ def test_round2_kernels_use_the_blackwell_paths():
                          check=True).stdout
     for name, usage in re.findall(r"Function (\S+):\s*\n\s*(.*)", res):
         assert int(re.search(r"STACK:(\d+)", usage).group(1)) == 0, (name, usage)
+
+
+@needs_build
+def test_late_round2_kernels():
+    """The fused two-convolution ring kernel (conv_tc_ring2.cu): tcgen05.mma kind::f16 for both convolutions, TMA input
+    rows, TMEM loads in both epilogues, 256-bit global accesses, packed fp32x2 epilogue arithmetic, the programmatic
+    dependent launch pair (PREEXIT = griddepcontrol.launch_dependents, ACQBULK = griddepcontrol.wait), no stack frame.
+    The four tcgen05 kernels carry the dependent-launch pair; the 1x1 convolution moves 256-bit sectors."""
+    text = "\n".join(l for v in _functions(_sass("conv_tc_ring2.o")).values() for l in v)
+    assert text.count("UTCHMMA") >= 80 and "UTMALDG" in text and text.count("LDTM") >= 4
+    assert "STG.E.ENL2.256" in text and "LDG.E.ENL2.256" in text
+    assert "FFMA2" in text and "FMUL2" in text and "FADD2" in text
+    res = subprocess.run(["cuobjdump", "-res-usage", os.path.join(BUILD, "conv_tc_ring2.o")], capture_output=True, text=True,
+                         check=True).stdout
+    for name, usage in re.findall(r"Function (\S+):\s*\n\s*(.*)", res):
+        assert int(re.search(r"STACK:(\d+)", usage).group(1)) == 0, (name, usage)
+        assert int(re.search(r"REG:(\d+)", usage).group(1)) <= 96, (name, usage)       # 672 threads per CTA
+    for obj, kern in (("conv_tc_ring.o", "conv3x3_tc_ring_kernel"), ("conv_tc_ring2.o", "conv3x3x2_tc_ring_kernel"),
+                      ("conv_tc.o", "conv3x3_tc_kernel"), ("conv_tc_s2.o", "conv4x4s2_tc_kernel")):
+        for name, lines in _functions(_sass(obj)).items():
+            if kern in name:
+                t = "\n".join(lines)
+                assert "PREEXIT" in t and "ACQBULK" in t, name
+    pw = {k: "\n".join(v) for k, v in _functions(_sass("conv.o")).items() if "pointwise_kernel" in k and "Lb1" in k}
+    assert pw
+    for name, t in pw.items():
+        assert "LDG.E.ENL2.256" in t and "STG.E.ENL2.256" in t, name
