@@ -15,6 +15,12 @@
  *     slice of a wider buffer (how the reference's torch.cat inputs are avoided).
  *     Images enter as NCHW (the reference's layout); cost volumes are [N,D,h,w] planar.
  *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises.
+ *     The tcgen05 convolutions (codd_conv3x3_tc*, codd_conv3x3x2_tc_ring, codd_conv4x4s2_tc, codd_tile_features_tc) are
+ *     launched with programmatic stream serialization: their prologue (barrier set-up, TMEM allocation, weight / bias
+ *     staging) may overlap the tail of the previous kernel of the same stream, but they read activations and write
+ *     outputs only after that kernel has completed (griddepcontrol.wait) — stream order is what a caller observes.
+ *     Consequence for callers: weight / bias buffers passed to these entry points must not be written by the kernel
+ *     that immediately precedes the call on the same stream unless that kernel is an ordinary (non-triggering) launch.
  *   - return value: 0 success; < 0 argument error (CODD_E_*); > 0 a cudaError_t.
  *   - no mutable state behind the ABI except the one-time, per-device kernel attribute set-up (an atomic bit per
  *     device ordinal under a mutex, csrc/common.cuh: CoddDeviceOnce), and no environment switches: concurrent calls
