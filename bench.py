@@ -637,7 +637,16 @@ def run_b200(args):
         }
     if world == 1 and not args.no_full_codd:
         line["full_codd"] = full_codd_leg(dev)
+    dominant["note"] = ("dominant kernel of the step by time; in round 1 this was the 16-channel ring conv (0.52 of HBM), whose "
+                        "pairs now run fused (conv3x3x2ring_c16) — the 32-channel ring conv is bound by the L1/shared-memory "
+                        "data pipe (tensor-core operand reads + epilogue stores), see DESIGN.md")
     line["roofline"] = dominant
+    # the whole step against the same roof: algorithmic bytes of every launch of one step / graph-replayed step time
+    step_bytes = sum(k["bytes"] for k in kernels)
+    step_gbs = step_bytes / (ms / args.steps * 1e-3) / 1e9
+    line["roofline_step"] = {"bound": "hbm", "achieved": round(step_gbs, 1), "peak": peak_gbs, "unit": "GB/s",
+                             "frac": round(step_gbs / peak_gbs, 4), "algorithmic_bytes_per_step": step_bytes,
+                             "what": "sum of the algorithmic bytes of all launches of one step / timed ms_per_step"}
     line["roofline_named_kernels"] = named
     line["top_kernels"] = [{"kernel": k["kernel"], "ms": round(k["ms"], 4), "launches": k["launches"],
                             "share": round(k["ms"] / total_ms, 4)} for k in kernels[:8]]
