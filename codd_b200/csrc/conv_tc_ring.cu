@@ -50,6 +50,10 @@ constexpr int RG_SPLIT_GROUP = 128;     // split warps 0-3 take the even staged 
 // warps 0-7 split, 8-11 epilogue, 12 TMA, 13 MMA pass A (even rows), 14 MMA pass B, 15 MMA pass A (odd rows)
 constexpr int RG_THREADS = 128 + RG_EPI_THREADS + RG_SPLIT_THREADS;
 
+// alignment of one fp16 operand tile: the swizzle pattern of 64-byte rows (KC = 32) repeats every 512 bytes
+template <int KC>
+__host__ __device__ constexpr uint32_t RG_H_ALIGN() { return KC == 32 ? 512u : 1024u; }
+
 struct RgP {
     const float* wpk;   // [2 pass][3 kx][6*NP rows][KC]: pass 0 rows per ky = [w_hi | w_lo], pass 1 = [w_hi | 0]
     const float* bias;
@@ -57,6 +61,7 @@ struct RgP {
     float* out;
     int N, H, W, Cout, ldo, ldr, res_bcast, act;
     int tilesX, nseg, seg, nitems;
+    int tstore;       // 32-channel outputs: the output tensor map is valid, rows leave through TMA stores
     long long* dbg;   // optional [grid][8] cycle counters (role wait times), NULL in production
     int diag;         // CODD_RING_DIAG probe bits (results are WRONG when set): 1 no pass-B MMAs, 2 no split work,
                       // 4 no epilogue global traffic, 8 pass A issues kx = 0 only, 16 no TMA loads
@@ -95,11 +100,28 @@ struct Cursor {
     }
 };
 
+// 16 residual channels [c0, c0 + 16) of one pixel as 256-bit loads; channels >= cout (a multiple of 8) read as zero
+__device__ __forceinline__ void res_load16(const float* rp, int c0, int cout, float* r) {
+    if (c0 < cout) {
+        ldg8(rp + c0, r);
+    } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) r[e] = 0.f;
+    }
+    if (c0 + 8 < cout) {
+        ldg8(rp + c0 + 8, r + 8);
+    } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) r[8 + e] = 0.f;
+    }
+}
+
 // NBUF fp32 row stages (TMA -> pass A + split warps) and NH fp16 x_lo stages (split warps -> pass B) are separate rings:
 // a raw row is released as soon as pass A and the split have read it, so the TMA producer runs ahead of pass B
 // (which trails pass A by two rows for the deterministic accumulation order).
 template <int KC, int NP, int NBUF, int NH>
-__global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __grid_constant__ CUtensorMap tmap, RgP p) {
+__global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                        const __grid_constant__ CUtensorMap omap, RgP p) {
     constexpr int SLOT = 2 * NP;                 // TMEM columns of one output row: [hi NP | lo NP]
     constexpr int RING = 512 / SLOT;             // 16 (NP = 16) or 8 (NP = 32) output rows in flight
     constexpr uint32_t ROWB = KC * 4;
@@ -107,7 +129,13 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
     constexpr uint32_t A_STRIDE = (A_BYTES + 1023u) & ~1023u;
     constexpr uint32_t ROWH = KC * 2;            // fp16 operand rows (both passes)
     constexpr uint32_t H_BYTES = RG_BOXW * ROWH;
-    constexpr uint32_t H_STRIDE = (H_BYTES + 1023u) & ~1023u;   // one fp16 tile (x_hi or x_lo) of a staged row
+    // one fp16 tile (x_hi or x_lo) of a staged row; 64-byte rows use SWIZZLE_64B, whose pattern repeats every 512 bytes
+    constexpr uint32_t H_ALIGN = RG_H_ALIGN<KC>();
+    constexpr uint32_t H_STRIDE = (H_BYTES + H_ALIGN - 1u) & ~(H_ALIGN - 1u);
+    // 32-channel outputs leave through TMA: each epilogue warp stages its 32 pixels x 128 bytes in a swizzled 4 KB tile
+    // and one lane issues cp.async.bulk.tensor (the lane-strided 256-bit stores cost ~1 L1 wavefront per sector:
+    // ~500 of the ~1800 cycles a staged row takes)
+    constexpr bool TSTORE = (NP == 32);
     constexpr uint32_t HL_STRIDE = 2 * H_STRIDE;                // operand stage = [x_hi tile | x_lo tile]
     constexpr uint32_t WBLKH = 6 * NP * ROWH;    // one kx weight block: 3 ky x [2*NP rows], fp16
     static_assert(NBUF >= 4 && NH >= 4, "stage depth: pass B trails pass A by 2 rows");
@@ -129,6 +157,8 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
     const uint32_t sB = sH + NH * HL_STRIDE;                 // pass-A weights, then pass-B weights (both fp16)
     uint8_t* gB = gH + NH * HL_STRIDE;
     const uint32_t sBH = sB + 3 * WBLKH;
+    const uint32_t sE = sB + 6 * WBLKH;                      // epilogue staging (TSTORE): 4 warps x 4 KB, 1024-aligned
+    uint8_t* gE = gB + 6 * WBLKH;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool timing = p.dbg != nullptr;
@@ -369,7 +399,12 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
         // is drained in 16-channel chunks — the TMEM loads of chunk g+1 and its residual loads are in flight while
         // chunk g is combined (packed fp32x2: hi + 2^-10 lo, + bias, + residual, max(v, slope*v)) and stored as
         // 256-bit sectors; the slot is released as soon as the last TMEM load has landed.
-        const bool fast = full_vec8 && (!p.res || p.res_bcast || res_vec8) && (p.act <= CODD_ACT_RELU_CH0) && !(p.diag & 4);
+        // (through TMA the channel count may be any multiple of 8 up to NP: the hardware clips channels >= Cout, so the
+        // 24-channel layers take this path too instead of 24 scalar stores per pixel)
+        const bool res8 = p.res && !p.res_bcast && ((p.ldr & 7) == 0) && ((((uintptr_t)p.res) & 31u) == 0);
+        const bool fast_t = TSTORE && p.tstore && (p.Cout % 8 == 0) && (!p.res || p.res_bcast || res8);
+        const bool fast = (fast_t || (full_vec8 && (!p.res || p.res_bcast || res_vec8))) &&
+                          (p.act <= CODD_ACT_RELU_CH0) && !(p.diag & 4);
         if (fast) {
             constexpr int NCH = NP / 16;
             const float2 sl2 = make_float2(slope, slope), sl20 = make_float2(slope0, slope);
@@ -397,7 +432,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
                     tc_fence_after();
                     tc_ld16(tbase, hi[0]);
                     tc_ld16(tbase + NP, lo[0]);
-                    if (rvec) { ldg8(rp, &rr[0][0]); ldg8(rp + 8, &rr[0][8]); }
+                    if (rvec) { res_load16(rp, 0, p.Cout, rr[0]); }
                     const float rb = (p.res && p.res_bcast) ? __ldg(rp) : 0.f;
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
@@ -406,7 +441,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
                         if (g + 1 < NCH) {
                             tc_ld16(tbase + (g + 1) * 16, hi[nxt]);
                             tc_ld16(tbase + NP + (g + 1) * 16, lo[nxt]);
-                            if (rvec) { ldg8(rp + (g + 1) * 16, &rr[nxt][0]); ldg8(rp + (g + 1) * 16 + 8, &rr[nxt][8]); }
+                            if (rvec) res_load16(rp, (g + 1) * 16, p.Cout, rr[nxt]);
                         } else {
                             tc_fence_before();
                             mbar_arrive(ABAR(ACCE, slot));      // every TMEM load of this row has completed
@@ -421,7 +456,29 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
                             v[c] = fmaxf(t.x, m.x);
                             v[c + 1] = fmaxf(t.y, m.y);
                         }
-                        if (xin) {
+                        if (TSTORE && fast_t) {
+                            if (g == 0) {      // the previous row's TMA store must have finished reading the staging tile
+                                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                                __syncwarp();
+                            }
+                            uint8_t* e8 = gE + quarter * 4096;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                *reinterpret_cast<float4*>(e8 + swz_off<32>(lane, g * 4 + j)) =
+                                    make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            if (g + 1 == NCH) {
+                                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                                __syncwarp();
+                                const int xw = tx * RG_TW + quarter * 32;
+                                if (lane == 0 && xw < p.W) {
+                                    asm volatile(
+                                        "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                                        ::"l"(&omap), "r"(sE + (uint32_t)quarter * 4096u), "r"(0), "r"(xw), "r"(y0 + r), "r"(n)
+                                        : "memory");
+                                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                                }
+                            }
+                        } else if (xin) {
                             stg8(op + g * 16, &v[0]);
                             stg8(op + g * 16 + 8, &v[8]);
                         }
@@ -429,6 +486,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
                     }
                 }
             }
+            if (TSTORE && fast_t && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
             if (p.dbg && tid == 256) p.dbg[blockIdx.x * 8 + 6] = w_accf;
         } else {
         float biasr[NP];
@@ -586,13 +644,14 @@ long long* g_rg_dbg = nullptr;   // diagnostic builds only (make DIAG=1): cycle-
 #endif
 
 template <int KC, int NP, int NBUF, int NH>
-int launch_ring(const CUtensorMap& tmap, RgP p, cudaStream_t s) {
+int launch_ring(const CUtensorMap& tmap, const CUtensorMap& omap, RgP p, cudaStream_t s) {
     constexpr uint32_t ROWB = KC * 4;
     constexpr uint32_t A_STRIDE = ((RG_BOXW * ROWB) + 1023u) & ~1023u;
-    constexpr uint32_t H_STRIDE = ((RG_BOXW * KC * 2) + 1023u) & ~1023u;
+    constexpr uint32_t H_STRIDE = ((RG_BOXW * KC * 2) + RG_H_ALIGN<KC>() - 1u) & ~(RG_H_ALIGN<KC>() - 1u);
     constexpr uint32_t B_BYTES = 2 * 3 * 6 * NP * KC * 2;
-    const size_t smem = NBUF * A_STRIDE + NH * 2 * H_STRIDE + B_BYTES + 1024;
-    static_assert(NBUF * A_STRIDE + NH * 2 * H_STRIDE + B_BYTES + 1024 + 2048 <= 232448, "shared memory budget");
+    constexpr uint32_t E_BYTES = (NP == 32) ? 4 * 4096 : 0;     // epilogue staging tiles (TMA store)
+    const size_t smem = NBUF * A_STRIDE + NH * 2 * H_STRIDE + B_BYTES + E_BYTES + 1024;
+    static_assert(NBUF * A_STRIDE + NH * 2 * H_STRIDE + B_BYTES + E_BYTES + 1024 + 1024 <= 232448, "shared memory budget");
     auto kern = conv3x3_tc_ring_kernel<KC, NP, NBUF, NH>;
     static CoddDeviceOnce once;   // one per template instantiation
     if (int rc = codd_once_per_device(once, [&] {
@@ -619,7 +678,7 @@ int launch_ring(const CUtensorMap& tmap, RgP p, cudaStream_t s) {
     p.nseg = codd_ceil_div(p.H, p.seg);
     p.nitems = strips * p.nseg;
     const int grid = p.nitems < sms ? p.nitems : sms;
-    if (cudaError_t e = codd_launch_pdl(kern, dim3(grid), dim3(RG_THREADS), smem, s, tmap, p)) return (int)e;
+    if (cudaError_t e = codd_launch_pdl(kern, dim3(grid), dim3(RG_THREADS), smem, s, tmap, omap, p)) return (int)e;
     CODD_RETURN_IF_CUDA_ERROR();
     return 0;
 }
@@ -660,9 +719,23 @@ extern "C" int codd_conv3x3_tc_ring(const float* in, int ldi, int cin, int n, in
     p.diag = 0;
 #endif
     cudaStream_t s = (cudaStream_t)stream;
-    if (KC == 32 && NP == 32) return launch_ring<32, 32, 4, 4>(tmap, p, s);
-    if (KC == 32 && NP == 16) return launch_ring<32, 16, 4, 6>(tmap, p, s);
-    return launch_ring<16, 16, 6, 10>(tmap, p, s);
+    // 32-channel outputs: tensor map of the output for the epilogue's TMA stores (boxes of 32 pixels x 32 channels;
+    // channels >= cout and columns >= w are clipped by the hardware)
+    CUtensorMap omap = tmap;
+    p.tstore = 0;
+    if (NP == 32 && codd_aligned16(out) && ldo % 4 == 0) {
+        const cuuint64_t odim[4] = {(cuuint64_t)cout, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+        const cuuint64_t ostr[3] = {(cuuint64_t)ldo * 4, (cuuint64_t)w * ldo * 4, (cuuint64_t)h * w * ldo * 4};
+        const cuuint32_t obox[4] = {32u, 32u, 1u, 1u};
+        if (enc(&omap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)out, odim, ostr, obox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+            p.tstore = 1;
+        else
+            omap = tmap;
+    }
+    if (KC == 32 && NP == 32) return launch_ring<32, 32, 4, 4>(tmap, omap, p, s);
+    if (KC == 32 && NP == 16) return launch_ring<32, 16, 4, 6>(tmap, omap, p, s);
+    return launch_ring<16, 16, 6, 10>(tmap, omap, p, s);
 }
 
 // diagnostic: device buffer of [grid][8] int64 cycle counters filled by the next codd_conv3x3_tc_ring launches
