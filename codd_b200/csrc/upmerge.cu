@@ -10,7 +10,10 @@
 // tensor through HBM twice (1.1 GB per step at the finest level: 0.31 ms deconvolution + 0.27 ms 1x1).
 // One thread = NPAR parent pixels and their 2 x 2 x NPAR output pixels (see upmerge_kernel).  Packed FFMA2, weights in
 // shared memory.
+#include <cuda.h>
+
 #include "common.cuh"
+#include "ring_util.cuh"
 
 namespace {
 
@@ -165,6 +168,174 @@ __global__ void __launch_bounds__(UM_THREADS) upmerge_kernel(UmP p) {
     }
 }
 
+// Third decomposition, for the all-16-channel case (the finest level, 60 % of this op's time): activations staged by TMA.
+// ncu of the kernel above: L1 data pipe 74 % busy, 56 M of its 96 M wavefronts from the lane-strided global loads and
+// stores (~1 wavefront per 32-byte sector).  Here a CTA of 64 threads owns 128 parents of one parent row: three
+// cp.async.bulk.tensor loads bring the parent pixels (8 KB) and the two skip rows (2 x 256 pixels, 32 KB) into SWIZZLE_64B
+// tiles while the threads stage the weights; every thread computes its two parents' 2 x 2 outputs for both rows as above,
+// reading activations with 128-bit shared loads, overwrites its own skip pixels with the results, and two bulk tensor
+// stores write the rows back (columns >= W clipped by the hardware).  Same FMA order as above: bit-identical results.
+constexpr int UT_THREADS = 64, UT_PAR = 128, UT_PX = 2 * UT_PAR;
+__global__ void __launch_bounds__(UT_THREADS) upmerge_tma_kernel(const __grid_constant__ CUtensorMap cmap,
+                                                                const __grid_constant__ CUtensorMap smap,
+                                                                const __grid_constant__ CUtensorMap omap, UmP p) {
+    constexpr int C = 16;
+    extern __shared__ uint8_t ut_raw[];
+    __shared__ __align__(8) unsigned long long bar;
+    const uint32_t sbase = (s_u32(ut_raw) + 1023u) & ~1023u;
+    uint8_t* gbase = ut_raw + (sbase - s_u32(ut_raw));
+    // [coarse 128 px x 64 B | skip row 0: 256 px x 64 B | skip row 1 | weights]
+    constexpr uint32_t OFF_S0 = UT_PAR * 64, OFF_S1 = OFF_S0 + UT_PX * 64, OFF_W = OFF_S1 + UT_PX * 64;
+    float* s_wu = reinterpret_cast<float*>(gbase + OFF_W);   // [4][C][C]
+    float* s_wm = s_wu + 4 * C * C;                          // [2C][C]
+    float* s_bu = s_wm + 2 * C * C;
+    float* s_bm = s_bu + C;
+    const int tid = threadIdx.x;
+    const int xp0 = blockIdx.x * UT_PAR, yp = blockIdx.y, n = blockIdx.z;
+    const uint32_t b = s_u32(&bar);
+    if (tid == 0) {
+        mbar_init(b, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(b, (uint32_t)(UT_PAR * 64 + 2 * UT_PX * 64));
+        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                     ::"r"(sbase), "l"(&cmap), "r"(b), "r"(0), "r"(xp0), "r"(yp), "r"(n) : "memory");
+        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                     ::"r"(sbase + OFF_S0), "l"(&smap), "r"(b), "r"(0), "r"(2 * xp0), "r"(2 * yp), "r"(n) : "memory");
+        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                     ::"r"(sbase + OFF_S1), "l"(&smap), "r"(b), "r"(0), "r"(2 * xp0), "r"(2 * yp + 1), "r"(n) : "memory");
+    }
+    for (int i = tid; i < 4 * C * C; i += UT_THREADS) s_wu[i] = __ldg(p.w_up + i);
+    for (int i = tid; i < 2 * C * C; i += UT_THREADS) s_wm[i] = __ldg(p.w_m + i);
+    if (tid < C) { s_bu[tid] = __ldg(p.b_up + tid); s_bm[tid] = __ldg(p.b_m + tid); }
+    __syncthreads();
+    mbar_wait(b, 0);
+
+    constexpr int NPAR = 2, NPX = 4;
+    int lp[NPAR];                                             // local parent index
+#pragma unroll
+    for (int q = 0; q < NPAR; ++q) lp[q] = tid + q * UT_THREADS;
+#pragma unroll 1
+    for (int dy = 0; dy < 2; ++dy) {
+        __align__(8) float up[NPX][C];
+#pragma unroll
+        for (int j = 0; j < NPX; ++j)
+#pragma unroll
+            for (int c = 0; c < C; ++c) up[j][c] = s_bu[c];
+        {
+            const float* w0 = s_wu + (dy * 2 + 0) * C * C;
+            const float* w1 = s_wu + (dy * 2 + 1) * C * C;
+#pragma unroll
+            for (int c4 = 0; c4 < C / 4; ++c4) {
+                float4 a[NPAR];
+#pragma unroll
+                for (int q = 0; q < NPAR; ++q) a[q] = *reinterpret_cast<const float4*>(gbase + swz_off<16>(lp[q], c4));
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+#pragma unroll
+                    for (int o4 = 0; o4 < C / 4; ++o4) {
+                        const float4 u = *reinterpret_cast<const float4*>(w0 + (c4 * 4 + cc) * C + o4 * 4);
+                        const float4 v = *reinterpret_cast<const float4*>(w1 + (c4 * 4 + cc) * C + o4 * 4);
+#pragma unroll
+                        for (int q = 0; q < NPAR; ++q) {
+                            const float av = cc == 0 ? a[q].x : cc == 1 ? a[q].y : cc == 2 ? a[q].z : a[q].w;
+                            fma4(&up[2 * q][o4 * 4], av, u);
+                            fma4(&up[2 * q + 1][o4 * 4], av, v);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < NPX; ++j)
+#pragma unroll
+                for (int c = 0; c < C; ++c) up[j][c] = fmaxf(up[j][c], 0.f) + CODD_LEAKY_SLOPE * fminf(up[j][c], 0.f);
+        }
+        __align__(8) float acc[NPX][C];
+#pragma unroll
+        for (int j = 0; j < NPX; ++j)
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[j][c] = s_bm[c];
+        uint8_t* srow = gbase + (dy ? OFF_S1 : OFF_S0);
+#pragma unroll
+        for (int c4 = 0; c4 < C / 4; ++c4) {
+            float4 a[NPX];
+#pragma unroll
+            for (int j = 0; j < NPX; ++j)
+                a[j] = *reinterpret_cast<const float4*>(srow + swz_off<16>(2 * lp[j >> 1] + (j & 1), c4));
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                const float* wp = s_wm + (c4 * 4 + cc) * C;
+#pragma unroll
+                for (int o4 = 0; o4 < C / 4; ++o4) {
+                    const float4 wv = *reinterpret_cast<const float4*>(wp + o4 * 4);
+#pragma unroll
+                    for (int j = 0; j < NPX; ++j) {
+                        const float av = cc == 0 ? a[j].x : cc == 1 ? a[j].y : cc == 2 ? a[j].z : a[j].w;
+                        fma4(&acc[j][o4 * 4], av, wv);
+                    }
+                }
+            }
+        }
+        const float* wmu = s_wm + C * C;
+#pragma unroll
+        for (int cu = 0; cu < C; ++cu) {
+            const float* wp = wmu + cu * C;
+#pragma unroll
+            for (int o4 = 0; o4 < C / 4; ++o4) {
+                const float4 wv = *reinterpret_cast<const float4*>(wp + o4 * 4);
+#pragma unroll
+                for (int j = 0; j < NPX; ++j) fma4(&acc[j][o4 * 4], up[j][cu], wv);
+            }
+        }
+        // results overwrite this thread's own skip pixels (read above, by this thread only)
+#pragma unroll
+        for (int j = 0; j < NPX; ++j) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[j][c] = fmaxf(acc[j][c], 0.f) + CODD_LEAKY_SLOPE * fminf(acc[j][c], 0.f);
+#pragma unroll
+            for (int c4 = 0; c4 < C / 4; ++c4)
+                *reinterpret_cast<float4*>(srow + swz_off<16>(2 * lp[j >> 1] + (j & 1), c4)) =
+                    make_float4(acc[j][c4 * 4], acc[j][c4 * 4 + 1], acc[j][c4 * 4 + 2], acc[j][c4 * 4 + 3]);
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                     ::"l"(&omap), "r"(sbase + OFF_S0), "r"(0), "r"(2 * xp0), "r"(2 * yp), "r"(n) : "memory");
+        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                     ::"l"(&omap), "r"(sbase + OFF_S1), "r"(0), "r"(2 * xp0), "r"(2 * yp + 1), "r"(n) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+}
+
+int um_launch_tma(const UmP& p, cudaStream_t s) {
+    PFN_tmapEncodeTiled enc = rg_get_encode();
+    if (!enc) return CODD_E_UNSUPPORTED;
+    const int Hc = p.H / 2, Wc = p.W / 2;
+    auto make = [&](CUtensorMap* m, const float* base, int ld, int w, int h, int boxw) {
+        const cuuint64_t dim[4] = {16u, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)p.N};
+        const cuuint64_t str[3] = {(cuuint64_t)ld * 4, (cuuint64_t)w * ld * 4, (cuuint64_t)h * w * ld * 4};
+        const cuuint32_t box[4] = {16u, (cuuint32_t)boxw, 1u, 1u}, es[4] = {1u, 1u, 1u, 1u};
+        return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dim, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    };
+    CUtensorMap cmap, smap, omap;
+    if (!make(&cmap, p.coarse, p.ldc, Wc, Hc, UT_PAR) || !make(&smap, p.skip, p.lds, p.W, p.H, UT_PX) ||
+        !make(&omap, p.out, p.ldo, p.W, p.H, UT_PX))
+        return CODD_E_UNSUPPORTED;
+    const size_t smem = (size_t)UT_PAR * 64 + 2 * UT_PX * 64 + (4 * 256 + 2 * 256 + 32) * sizeof(float) + 1024;
+    static CoddDeviceOnce once;
+    if (int rc = codd_once_per_device(once, [&] {
+            return cudaFuncSetAttribute(upmerge_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        }))
+        return rc;
+    dim3 grid((unsigned)codd_ceil_div(Wc, UT_PAR), (unsigned)Hc, (unsigned)p.N);
+    upmerge_tma_kernel<<<grid, UT_THREADS, smem, s>>>(cmap, smap, omap, p);
+    CODD_RETURN_IF_CUDA_ERROR();
+    return 0;
+}
+
 template <int CU, int CO, int NPAR>
 int um_launch(const UmP& p, cudaStream_t s) {
     const size_t smem = ((size_t)4 * p.Cc * CU + (size_t)(p.Cs + CU) * CO + CU + CO) * sizeof(float);
@@ -196,6 +367,11 @@ extern "C" int codd_upmerge_nhwc(const float* coarse, int ldc, int cc, const flo
     // two parents per thread when a row of parents fills the 128-thread blocks that way (>= 3/4 of the slots used)
     const int wc = w / 2;
     const bool two = (wc % 256 == 0) || (wc % 256 > 192) || (wc > 256 && wc % 256 > 128);
+    // the all-16-channel case at sizes that fill 128-parent CTAs: TMA-staged variant
+    if (cu == 16 && co == 16 && cc == 16 && cs == 16 && wc >= 96) {
+        const int rc = um_launch_tma(p, s);
+        if (rc != CODD_E_UNSUPPORTED) return rc;
+    }
     if (cu == 16 && co == 16) return two ? um_launch<16, 16, 2>(p, s) : um_launch<16, 16, 1>(p, s);
     if (cu == 24 && co == 24) return um_launch<24, 24, 1>(p, s);
     return CODD_E_UNSUPPORTED;

@@ -123,7 +123,8 @@ def test_conv3x3_head1_residual_relu(ops):
 
 
 @pytest.mark.parametrize("cc,cs,cu,co,n,h,w", [(16, 16, 16, 16, 2, 20, 600), (24, 16, 16, 16, 1, 6, 1030), (24, 24, 24, 24, 2, 10, 70),
-                                                (32, 24, 24, 24, 1, 4, 514), (16, 16, 16, 16, 1, 2, 2)])
+                                                (32, 24, 24, 24, 1, 4, 514), (16, 16, 16, 16, 1, 2, 2), (16, 16, 16, 16, 3, 6, 1000),
+                                                (16, 16, 16, 16, 1, 4, 192)])
 def test_upmerge_fused(ops, cc, cs, cu, co, n, h, w):
     """conv_up + conv_merge[0] in one kernel (backbone.py:17-32,75-88) against the two torch ops it replaces."""
     g = gen(cc * 10 + cs + h + w)
