@@ -27,6 +27,7 @@ struct UmP {
     float* out; int ldo;                  // [N, H, W, Co] NHWC
     int N, H, W;
     int v8;                               // 256-bit output stores allowed
+    int w_bulk;                           // weights / biases are 16-byte aligned: staged by 1-D bulk copies (TMA variant)
 };
 
 constexpr int UM_THREADS = 128;
@@ -58,11 +59,34 @@ __global__ void __launch_bounds__(UM_THREADS) upmerge_kernel(UmP p) {
     float* s_wm = s_wu + 4 * p.Cc * CU;                      // [Cs + CU][CO]
     float* s_bu = s_wm + (p.Cs + CU) * CO;                   // [CU]
     float* s_bm = s_bu + CU;                                 // [CO]
-    for (int i = threadIdx.x; i < 4 * p.Cc * CU; i += UM_THREADS) s_wu[i] = __ldg(p.w_up + i);
-    for (int i = threadIdx.x; i < (p.Cs + CU) * CO; i += UM_THREADS) s_wm[i] = __ldg(p.w_m + i);
-    for (int i = threadIdx.x; i < CU; i += UM_THREADS) s_bu[i] = __ldg(p.b_up + i);
-    for (int i = threadIdx.x; i < CO; i += UM_THREADS) s_bm[i] = __ldg(p.b_m + i);
-    __syncthreads();
+    if (p.w_bulk) {
+        // weights and biases by four 1-D bulk copies: staged by the threads (12-24 scalar loads each, per CTA) they were a
+        // fifth of this kernel's time
+        __shared__ __align__(8) unsigned long long wbar;
+        const uint32_t b = s_u32(&wbar);
+        if (threadIdx.x == 0) {
+            mbar_init(b, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            const uint32_t nwu = 4 * p.Cc * CU * 4, nwm = (p.Cs + CU) * CO * 4;
+            mbar_expect_tx(b, nwu + nwm + (CU + CO) * 4);
+            auto bulk = [&](const float* dst, const float* src, uint32_t bytes) {
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(s_u32(dst)), "l"(src), "r"(bytes), "r"(b) : "memory");
+            };
+            bulk(s_wu, p.w_up, nwu);
+            bulk(s_wm, p.w_m, nwm);
+            bulk(s_bu, p.b_up, CU * 4);
+            bulk(s_bm, p.b_m, CO * 4);
+        }
+        __syncthreads();
+        mbar_wait(b, 0);
+    } else {
+        for (int i = threadIdx.x; i < 4 * p.Cc * CU; i += UM_THREADS) s_wu[i] = __ldg(p.w_up + i);
+        for (int i = threadIdx.x; i < (p.Cs + CU) * CO; i += UM_THREADS) s_wm[i] = __ldg(p.w_m + i);
+        for (int i = threadIdx.x; i < CU; i += UM_THREADS) s_bu[i] = __ldg(p.b_up + i);
+        for (int i = threadIdx.x; i < CO; i += UM_THREADS) s_bm[i] = __ldg(p.b_m + i);
+        __syncthreads();
+    }
 
     const int Hc = p.H >> 1, Wc = p.W >> 1;
     const int yp = blockIdx.y, n = blockIdx.z;
@@ -196,7 +220,17 @@ __global__ void __launch_bounds__(UT_THREADS) upmerge_tma_kernel(const __grid_co
     if (tid == 0) {
         mbar_init(b, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        mbar_expect_tx(b, (uint32_t)(UT_PAR * 64 + 2 * UT_PX * 64));
+        mbar_expect_tx(b, (uint32_t)(UT_PAR * 64 + 2 * UT_PX * 64 + (p.w_bulk ? (4 * C * C + 2 * C * C + 2 * C) * 4 : 0)));
+        if (p.w_bulk) {       // weights and biases as four 1-D bulk copies (16-byte aligned sources): no thread touches them
+            auto bulk = [&](const float* dst, const float* src, uint32_t bytes) {
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(s_u32(dst)), "l"(src), "r"(bytes), "r"(b) : "memory");
+            };
+            bulk(s_wu, p.w_up, 4 * C * C * 4);
+            bulk(s_wm, p.w_m, 2 * C * C * 4);
+            bulk(s_bu, p.b_up, C * 4);
+            bulk(s_bm, p.b_m, C * 4);
+        }
         asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                      ::"r"(sbase), "l"(&cmap), "r"(b), "r"(0), "r"(xp0), "r"(yp), "r"(n) : "memory");
         asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -204,9 +238,11 @@ __global__ void __launch_bounds__(UT_THREADS) upmerge_tma_kernel(const __grid_co
         asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                      ::"r"(sbase + OFF_S1), "l"(&smap), "r"(b), "r"(0), "r"(2 * xp0), "r"(2 * yp + 1), "r"(n) : "memory");
     }
-    for (int i = tid; i < 4 * C * C; i += UT_THREADS) s_wu[i] = __ldg(p.w_up + i);
-    for (int i = tid; i < 2 * C * C; i += UT_THREADS) s_wm[i] = __ldg(p.w_m + i);
-    if (tid < C) { s_bu[tid] = __ldg(p.b_up + tid); s_bm[tid] = __ldg(p.b_m + tid); }
+    if (!p.w_bulk) {
+        for (int i = tid; i < 4 * C * C; i += UT_THREADS) s_wu[i] = __ldg(p.w_up + i);
+        for (int i = tid; i < 2 * C * C; i += UT_THREADS) s_wm[i] = __ldg(p.w_m + i);
+        if (tid < C) { s_bu[tid] = __ldg(p.b_up + tid); s_bm[tid] = __ldg(p.b_m + tid); }
+    }
     __syncthreads();
     mbar_wait(b, 0);
 
@@ -363,6 +399,7 @@ extern "C" int codd_upmerge_nhwc(const float* coarse, int ldc, int cc, const flo
     p.w_up = w_up; p.b_up = b_up; p.w_m = w_merge; p.b_m = b_merge; p.out = out; p.ldo = ldo;
     p.N = n; p.H = h; p.W = w;
     p.v8 = (ldo % 8 == 0) && codd_aligned32(out);
+    p.w_bulk = codd_aligned16(w_up) && codd_aligned16(w_merge) && codd_aligned16(b_up) && codd_aligned16(b_merge);
     cudaStream_t s = (cudaStream_t)stream;
     // two parents per thread when a row of parents fills the 128-thread blocks that way (>= 3/4 of the slots used)
     const int wc = w / 2;
