@@ -316,15 +316,35 @@ int dispatch_cout(const ConvP& p, cudaStream_t s) {
 // broadcasts.  HBM-bound (AI = 2*Cin*Cout / (4*(Cin+Cout)) < 12 flop/B for every layer here).
 // ---------------------------------------------------------------------------------------------
 template <int CO, int PX_T, bool V8IN>
-__global__ void __launch_bounds__(256, 2) pointwise_kernel(ConvP p, size_t npix) {
+__global__ void __launch_bounds__(256, 2) pointwise_kernel(ConvP p, size_t npix, int wbulk) {
     extern __shared__ float4 smem4[];
     float* s_w = reinterpret_cast<float*>(smem4);  // [Cin][CO]
     const int Cin = p.C0 + p.C1;
-    for (int i = threadIdx.x; i < Cin * CO; i += blockDim.x) {
-        const int co = i % CO, ci = i / CO;
-        s_w[i] = co < p.Cout ? __ldg(p.w + (size_t)ci * p.wld + co) : 0.f;
+    if (wbulk) {
+        // the packed weight IS the shared image (Cout == CO == row stride, 16-byte aligned): one 1-D bulk copy instead of
+        // 2-8 scalar loads per thread and CTA (a CTA only covers 256 * PX_T pixels)
+        __shared__ __align__(8) unsigned long long wbar;
+        const uint32_t b = (uint32_t)__cvta_generic_to_shared(&wbar);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            const uint32_t bytes = (uint32_t)(Cin * CO * 4);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"((uint32_t)__cvta_generic_to_shared(s_w)), "l"(p.w), "r"(bytes), "r"(b) : "memory");
+        }
+        __syncthreads();
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+                         : "=r"(done) : "r"(b), "r"(0) : "memory");
+    } else {
+        for (int i = threadIdx.x; i < Cin * CO; i += blockDim.x) {
+            const int co = i % CO, ci = i / CO;
+            s_w[i] = co < p.Cout ? __ldg(p.w + (size_t)ci * p.wld + co) : 0.f;
+        }
+        __syncthreads();
     }
-    __syncthreads();
     const size_t base = (size_t)blockIdx.x * (blockDim.x * PX_T) + threadIdx.x;
     __align__(8) float acc[PX_T][CO];
 #pragma unroll
@@ -426,8 +446,9 @@ int launch_pointwise(const ConvP& p, cudaStream_t s) {
     // 256-bit input loads when both sources are made of whole, 32-byte aligned 8-channel groups
     const bool v8 = (p.C0 % 8 == 0) && (p.C1 % 8 == 0) && (p.ld0 % 8 == 0) && codd_aligned32(p.in0) &&
                     (p.C1 == 0 || ((p.ld1 % 8 == 0) && codd_aligned32(p.in1)));
-    if (v8) pointwise_kernel<CO, PX_T, true><<<grid, 256, smem, s>>>(p, npix);
-    else pointwise_kernel<CO, PX_T, false><<<grid, 256, smem, s>>>(p, npix);
+    const int wbulk = (p.Cout == CO) && (p.wld == CO) && codd_aligned16(p.w) && (((p.C0 + p.C1) * CO) % 4 == 0);
+    if (v8) pointwise_kernel<CO, PX_T, true><<<grid, 256, smem, s>>>(p, npix, wbulk);
+    else pointwise_kernel<CO, PX_T, false><<<grid, 256, smem, s>>>(p, npix, wbulk);
     CODD_RETURN_IF_CUDA_ERROR();
     return 0;
 }
