@@ -43,7 +43,7 @@
 namespace {
 
 constexpr int RG_TW = 128;              // output columns per strip (= MMA M)
-constexpr int RG_BOXW = RG_TW + 2;      // staged pixels per row
+// staged pixels per row: RG_TW + 2 * DIL
 constexpr int RG_EPI_THREADS = 128;
 constexpr int RG_SPLIT_THREADS = 256;
 constexpr int RG_SPLIT_GROUP = 128;     // split warps 0-3 take the even staged rows, warps 4-7 the odd ones
@@ -62,6 +62,8 @@ struct RgP {
     int N, H, W, Cout, ldo, ldr, res_bcast, act;
     int tilesX, nseg, seg, nitems;
     int tstore;       // 32-channel outputs: the output tensor map is valid, rows leave through TMA stores
+    int dil, Hphys;   // dilation d (1 or 3): N and H above are then the d*N row-phase sub-images of H/d rows each (rows
+                      // y = d*r + phase of one image see each other at distance 1), Hphys the image height
     long long* dbg;   // optional [grid][8] cycle counters (role wait times), NULL in production
     int diag;         // CODD_RING_DIAG probe bits (results are WRONG when set): 1 no pass-B MMAs, 2 no split work,
                       // 4 no epilogue global traffic, 8 pass A issues kx = 0 only, 16 no TMA loads
@@ -119,16 +121,22 @@ __device__ __forceinline__ void res_load16(const float* rp, int c0, int cout, fl
 // NBUF fp32 row stages (TMA -> pass A + split warps) and NH fp16 x_lo stages (split warps -> pass B) are separate rings:
 // a raw row is released as soon as pass A and the split have read it, so the TMA producer runs ahead of pass B
 // (which trails pass A by two rows for the deterministic accumulation order).
-template <int KC, int NP, int NBUF, int NH>
+// DIL = 3 (the dilated ResBlocks of tile_update4_1 / tile_update5, propagation.py:258-280): in y a dilation-3 convolution
+// is three independent dilation-1 convolutions on the row phases y mod 3, so the host presents every phase as its own
+// "sample" (tensor-map row stride 3*W, sample-dimension stride W: index n*H + phase) and the row schedule below is
+// unchanged; in x the taps are 3 pixels apart: the staged row is 128 + 6 pixels and the A operand of tap kx starts
+// 3*kx pixel rows into it.
+template <int KC, int NP, int NBUF, int NH, int DIL>
 __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                         const __grid_constant__ CUtensorMap omap, RgP p) {
     constexpr int SLOT = 2 * NP;                 // TMEM columns of one output row: [hi NP | lo NP]
     constexpr int RING = 512 / SLOT;             // 16 (NP = 16) or 8 (NP = 32) output rows in flight
     constexpr uint32_t ROWB = KC * 4;
-    constexpr uint32_t A_BYTES = RG_BOXW * ROWB;
+    constexpr int BOXW = RG_TW + 2 * DIL;
+    constexpr uint32_t A_BYTES = BOXW * ROWB;
     constexpr uint32_t A_STRIDE = (A_BYTES + 1023u) & ~1023u;
     constexpr uint32_t ROWH = KC * 2;            // fp16 operand rows (both passes)
-    constexpr uint32_t H_BYTES = RG_BOXW * ROWH;
+    constexpr uint32_t H_BYTES = BOXW * ROWH;
     // one fp16 tile (x_hi or x_lo) of a staged row; 64-byte rows use SWIZZLE_64B, whose pattern repeats every 512 bytes
     constexpr uint32_t H_ALIGN = RG_H_ALIGN<KC>();
     constexpr uint32_t H_STRIDE = (H_BYTES + H_ALIGN - 1u) & ~(H_ALIGN - 1u);
@@ -221,11 +229,12 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
                 mbar_wait_t(SBAR(EMPTY, sb), (((uint32_t)(c.g / NBUF)) & 1u) ^ 1u, w0, timing);
                 if (p.diag & 16) { mbar_arrive(SBAR(FULL, sb)); continue; }
                 mbar_expect_tx(SBAR(FULL, sb), A_BYTES);
-                const int cx = c.x0 - 1, cy = c.y0 - 1 + c.t;
+                const int cx = c.x0 - DIL, cy = c.y0 - 1 + c.t;
+                const int cq = DIL == 1 ? c.n : (c.n / DIL) * p.Hphys + c.n % DIL;     // sample / row-phase coordinate
                 asm volatile(
                     "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
                     "%6}], [%2];" ::"r"(sbase + sb * A_STRIDE),
-                    "l"(&tmap), "r"(SBAR(FULL, sb)), "r"(0), "r"(cx), "r"(cy), "r"(c.n)
+                    "l"(&tmap), "r"(SBAR(FULL, sb)), "r"(0), "r"(cx), "r"(cy), "r"(cq)
                     : "memory");
             }
             if (p.dbg) p.dbg[blockIdx.x * 8 + 0] = w0;
@@ -300,7 +309,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
                         if (kx > 0 && (p.diag & 8)) break;
 #pragma unroll
                         for (int k = 0; k < KSP; ++k) {
-                            const uint32_t a_k = a_desc + (((uint32_t)kx * RB + (uint32_t)k * 32u) >> 4);
+                            const uint32_t a_k = a_desc + (((uint32_t)(kx * DIL) * RB + (uint32_t)k * 32u) >> 4);
                             const uint32_t b_k = b_pass + (((uint32_t)kx * WB + (uint32_t)k * 32u) >> 4);
                             const bool first = (kx == 0 && k == 0);
                             if (first && PASS == 0) {
@@ -346,7 +355,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
                 for (int kx = 0; kx < 3; ++kx) {
 #pragma unroll
                     for (int k = 0; k < KSP; ++k) {
-                        const uint32_t a_k = a_desc + (((uint32_t)kx * RB + (uint32_t)k * 32u) >> 4);
+                        const uint32_t a_k = a_desc + (((uint32_t)(kx * DIL) * RB + (uint32_t)k * 32u) >> 4);
 #pragma unroll
                         for (int ky = 0; ky < 3; ++ky) {
                             if (runn[ky] == 0) continue;
@@ -423,7 +432,9 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
                 const int xc = xin ? x : p.W - 1;          // clamped: loads stay in bounds, stores are predicated
                 for (int r = 0; r < rows; ++r, ++orow) {
                     const int slot = RING - 1 - (orow % RING);
-                    const size_t opix = ((size_t)n * p.H + (y0 + r)) * p.W + xc;
+                    // physical pixel: row DIL * (row within the phase) + phase of image n / DIL
+                    const size_t opix = DIL == 1 ? ((size_t)n * p.H + (y0 + r)) * p.W + xc
+                                                 : ((size_t)(n / DIL) * p.Hphys + (size_t)(y0 + r) * DIL + n % DIL) * p.W + xc;
                     float* op = p.out + opix * p.ldo;
                     const float* rp = p.res ? p.res + opix * p.ldr : nullptr;
                     const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * SLOT);
@@ -473,7 +484,8 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
                                 if (lane == 0 && xw < p.W) {
                                     asm volatile(
                                         "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                                        ::"l"(&omap), "r"(sE + (uint32_t)quarter * 4096u), "r"(0), "r"(xw), "r"(y0 + r), "r"(n)
+                                        ::"l"(&omap), "r"(sE + (uint32_t)quarter * 4096u), "r"(0), "r"(xw), "r"(y0 + r),
+                                          "r"(DIL == 1 ? n : (n / DIL) * p.Hphys + n % DIL)
                                         : "memory");
                                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                                 }
@@ -514,7 +526,8 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
                 mbar_arrive(ABAR(ACCE, slot));
                 const int y = y0 + r;
                 if (x >= p.W || (p.diag & 4)) continue;
-                const size_t opix = ((size_t)n * p.H + y) * p.W + x;
+                const size_t opix = DIL == 1 ? ((size_t)n * p.H + y) * p.W + x
+                                             : ((size_t)(n / DIL) * p.Hphys + (size_t)y * DIL + n % DIL) * p.W + x;
                 float* op = p.out + opix * p.ldo;
                 float v[NP];
 #pragma unroll
@@ -573,7 +586,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
         }   // general path
     } else {
         // ===================== x_lo stage of a staged row (warps 0-3: even rows, warps 4-7: odd rows) =====================
-        constexpr int UNITS = RG_BOXW * (KC / 8);                  // one unit = 8 channels of one pixel
+        constexpr int UNITS = BOXW * (KC / 8);                     // one unit = 8 channels of one pixel
         constexpr int UMAX = (UNITS + RG_SPLIT_GROUP - 1) / RG_SPLIT_GROUP;
         const int gt = tid & (RG_SPLIT_GROUP - 1);
         Cursor c;
@@ -643,16 +656,17 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv3x3_tc_ring_kernel(const __
 long long* g_rg_dbg = nullptr;   // diagnostic builds only (make DIAG=1): cycle-counter buffer
 #endif
 
-template <int KC, int NP, int NBUF, int NH>
+template <int KC, int NP, int NBUF, int NH, int DIL = 1>
 int launch_ring(const CUtensorMap& tmap, const CUtensorMap& omap, RgP p, cudaStream_t s) {
     constexpr uint32_t ROWB = KC * 4;
-    constexpr uint32_t A_STRIDE = ((RG_BOXW * ROWB) + 1023u) & ~1023u;
-    constexpr uint32_t H_STRIDE = ((RG_BOXW * KC * 2) + RG_H_ALIGN<KC>() - 1u) & ~(RG_H_ALIGN<KC>() - 1u);
+    constexpr int BOXW = RG_TW + 2 * DIL;
+    constexpr uint32_t A_STRIDE = ((BOXW * ROWB) + 1023u) & ~1023u;
+    constexpr uint32_t H_STRIDE = ((BOXW * KC * 2) + RG_H_ALIGN<KC>() - 1u) & ~(RG_H_ALIGN<KC>() - 1u);
     constexpr uint32_t B_BYTES = 2 * 3 * 6 * NP * KC * 2;
     constexpr uint32_t E_BYTES = (NP == 32) ? 4 * 4096 : 0;     // epilogue staging tiles (TMA store)
     const size_t smem = NBUF * A_STRIDE + NH * 2 * H_STRIDE + B_BYTES + E_BYTES + 1024;
     static_assert(NBUF * A_STRIDE + NH * 2 * H_STRIDE + B_BYTES + E_BYTES + 1024 + 1024 <= 232448, "shared memory budget");
-    auto kern = conv3x3_tc_ring_kernel<KC, NP, NBUF, NH>;
+    auto kern = conv3x3_tc_ring_kernel<KC, NP, NBUF, NH, DIL>;
     static CoddDeviceOnce once;   // one per template instantiation
     if (int rc = codd_once_per_device(once, [&] {
             return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -685,9 +699,9 @@ int launch_ring(const CUtensorMap& tmap, const CUtensorMap& omap, RgP p, cudaStr
 
 }  // namespace
 
-extern "C" int codd_conv3x3_tc_ring(const float* in, int ldi, int cin, int n, int h, int w, const float* weight_ring,
-                                    const float* bias, const float* residual, int ldr, int res_bcast, int cout, int act,
-                                    float* out, int ldo, void* stream) {
+namespace {
+int ring_entry(const float* in, int ldi, int cin, int n, int h, int w, const float* weight_ring, const float* bias,
+               const float* residual, int ldr, int res_bcast, int cout, int act, float* out, int ldo, int dil, void* stream) {
     if (!in || !weight_ring || !out || n <= 0 || h <= 0 || w <= 0 || cin <= 0 || cout <= 0) return CODD_E_BADARG;
     if (cin > 32 || cout > 32 || cin % 4 != 0 || ldi % 4 != 0 || ldi < cin || ldo < cout) return CODD_E_SHAPE;
     if (!codd_aligned16(in)) return CODD_E_ALIGN;
@@ -696,10 +710,16 @@ extern "C" int codd_conv3x3_tc_ring(const float* in, int ldi, int cin, int n, in
     const int KC = cin <= 16 ? 16 : 32;
     const int NP = cout <= 16 ? 16 : 32;
     if (KC == 16 && NP == 32) return CODD_E_UNSUPPORTED;
+    if (dil != 1 && !(dil == 3 && KC == 32 && NP == 32 && h % 3 == 0)) return CODD_E_UNSUPPORTED;
+    // dilation d: the d row phases of an image are presented as d "samples" of h/d rows (row stride d*w pixels); the
+    // sample-dimension index n*h + phase with stride w pixels addresses phase `phase` of image n (h*w = (h/d) * d*w)
+    const int he = h / dil, ne = n * dil;
+    const cuuint64_t nq = dil == 1 ? (cuuint64_t)n : (cuuint64_t)n * h;
     CUtensorMap tmap;
-    const cuuint64_t gdim[4] = {(cuuint64_t)cin, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
-    const cuuint64_t gstr[3] = {(cuuint64_t)ldi * 4, (cuuint64_t)w * ldi * 4, (cuuint64_t)h * w * ldi * 4};
-    const cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)RG_BOXW, 1u, 1u};
+    const cuuint64_t gdim[4] = {(cuuint64_t)cin, (cuuint64_t)w, (cuuint64_t)he, nq};
+    const cuuint64_t gstr[3] = {(cuuint64_t)ldi * 4, (cuuint64_t)dil * w * ldi * 4,
+                                dil == 1 ? (cuuint64_t)h * w * ldi * 4 : (cuuint64_t)w * ldi * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)(RG_TW + 2 * dil), 1u, 1u};
     const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
     const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)in, gdim, gstr, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, KC == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
@@ -707,7 +727,8 @@ extern "C" int codd_conv3x3_tc_ring(const float* in, int ldi, int cin, int n, in
     if (r != CUDA_SUCCESS) return CODD_E_SHAPE;
     RgP p;
     p.wpk = weight_ring; p.bias = bias; p.res = residual; p.out = out;
-    p.N = n; p.H = h; p.W = w; p.Cout = cout; p.ldo = ldo; p.ldr = ldr; p.res_bcast = res_bcast; p.act = act;
+    p.N = ne; p.H = he; p.W = w; p.Cout = cout; p.ldo = ldo; p.ldr = ldr; p.res_bcast = res_bcast; p.act = act;
+    p.dil = dil; p.Hphys = h;
     p.tilesX = codd_ceil_div(w, RG_TW);
     p.nseg = p.seg = p.nitems = 0;
 #ifdef CODD_DIAG
@@ -720,12 +741,13 @@ extern "C" int codd_conv3x3_tc_ring(const float* in, int ldi, int cin, int n, in
 #endif
     cudaStream_t s = (cudaStream_t)stream;
     // 32-channel outputs: tensor map of the output for the epilogue's TMA stores (boxes of 32 pixels x 32 channels;
-    // channels >= cout and columns >= w are clipped by the hardware)
+    // channels >= cout and columns >= w are clipped by the hardware); same row-phase view as the input
     CUtensorMap omap = tmap;
     p.tstore = 0;
     if (NP == 32 && codd_aligned16(out) && ldo % 4 == 0) {
-        const cuuint64_t odim[4] = {(cuuint64_t)cout, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
-        const cuuint64_t ostr[3] = {(cuuint64_t)ldo * 4, (cuuint64_t)w * ldo * 4, (cuuint64_t)h * w * ldo * 4};
+        const cuuint64_t odim[4] = {(cuuint64_t)cout, (cuuint64_t)w, (cuuint64_t)he, nq};
+        const cuuint64_t ostr[3] = {(cuuint64_t)ldo * 4, (cuuint64_t)dil * w * ldo * 4,
+                                    dil == 1 ? (cuuint64_t)h * w * ldo * 4 : (cuuint64_t)w * ldo * 4};
         const cuuint32_t obox[4] = {32u, 32u, 1u, 1u};
         if (enc(&omap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)out, odim, ostr, obox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
@@ -733,9 +755,24 @@ extern "C" int codd_conv3x3_tc_ring(const float* in, int ldi, int cin, int n, in
         else
             omap = tmap;
     }
+    if (dil == 3) return launch_ring<32, 32, 4, 4, 3>(tmap, omap, p, s);
     if (KC == 32 && NP == 32) return launch_ring<32, 32, 4, 4>(tmap, omap, p, s);
     if (KC == 32 && NP == 16) return launch_ring<32, 16, 4, 6>(tmap, omap, p, s);
     return launch_ring<16, 16, 6, 10>(tmap, omap, p, s);
+}
+}  // namespace
+
+extern "C" int codd_conv3x3_tc_ring(const float* in, int ldi, int cin, int n, int h, int w, const float* weight_ring,
+                                    const float* bias, const float* residual, int ldr, int res_bcast, int cout, int act,
+                                    float* out, int ldo, void* stream) {
+    return ring_entry(in, ldi, cin, n, h, w, weight_ring, bias, residual, ldr, res_bcast, cout, act, out, ldo, 1, stream);
+}
+
+/* see include/codd_b200.h */
+extern "C" int codd_conv3x3_tc_ring_dil(const float* in, int ldi, int cin, int n, int h, int w, const float* weight_ring,
+                                        const float* bias, const float* residual, int ldr, int res_bcast, int cout, int act,
+                                        float* out, int ldo, int dil, void* stream) {
+    return ring_entry(in, ldi, cin, n, h, w, weight_ring, bias, residual, ldr, res_bcast, cout, act, out, ldo, dil, stream);
 }
 
 // diagnostic: device buffer of [grid][8] int64 cycle counters filled by the next codd_conv3x3_tc_ring launches

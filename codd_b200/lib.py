@@ -34,6 +34,8 @@ SIGNATURES = {
                                     _FP, c_int, c_int, c_int, c_void_p]),
     "codd_conv3x3_tc_ring": (c_int, [_FP, c_int, c_int, c_int, c_int, c_int, _FP, _FP, _FP, c_int, c_int, c_int, c_int,
                                      _FP, c_int, c_void_p]),
+    "codd_conv3x3_tc_ring_dil": (c_int, [_FP, c_int, c_int, c_int, c_int, c_int, _FP, _FP, _FP, c_int, c_int, c_int, c_int,
+                                         _FP, c_int, c_int, c_void_p]),
     "codd_conv3x3x2_tc_ring": (c_int, [_FP, c_int, c_int, c_int, c_int, _FP, _FP, c_int, _FP, _FP, _FP, c_int, c_int, _FP,
                                        c_int, c_void_p]),
     "codd_conv4x4s2_tc": (c_int, [_FP, c_int, c_int, c_int, c_int, c_int, _FP, _FP, c_int, c_int, _FP, c_int, c_void_p]),

@@ -226,20 +226,27 @@ def pack_conv_weight_ring(w):
     return torch.cat([pa.reshape(-1), pb.reshape(-1)]).contiguous().view(torch.float32)
 
 
-def conv3x3_tc_ring(x, wring, bias, cout, act=ACT_NONE, residual=None, res_bcast=False, out=None):
-    """3x3 s1 p1 conv on the tensor cores, rolling-ring kernel (3 fp16 products, fp32 accumulation).  ``wring`` from
-    pack_conv_weight_ring; ``out``: optional NHWC-backed destination (e.g. a channel slice of a wider buffer)."""
+def ring_dil3_eligible(x, cout):
+    """Dilation-3 layers the rolling-ring kernel takes (32 -> 32 channels, image height a multiple of 3)."""
+    return x.shape[1] == 32 and cout == 32 and x.shape[2] % 3 == 0
+
+
+def conv3x3_tc_ring(x, wring, bias, cout, act=ACT_NONE, residual=None, res_bcast=False, out=None, dil=1):
+    """3x3 s1 conv (pad = dil) on the tensor cores, rolling-ring kernel (3 fp16 products, fp32 accumulation).  ``wring``
+    from pack_conv_weight_ring; ``out``: optional NHWC-backed destination (e.g. a channel slice of a wider buffer);
+    ``dil`` = 3 needs ring_dil3_eligible."""
     _require_cuda(x, wring, bias, residual, out)
     n, cin, h, w = x.shape
     if out is None:
         out = empty_nhwc(n, cout, h, w, x.device)
     nbytes = 4 * (n * h * w * (cin + cout) + wring.numel()
                   + (0 if residual is None else n * h * w * (1 if res_bcast else cout)))
-    rc = _run(f"conv3x3ring_cin{cin}_cout{cout}", nbytes, lambda: _lib.load().codd_conv3x3_tc_ring(
+    tag = f"conv3x3ring_cin{cin}_cout{cout}" + ("" if dil == 1 else f"_d{dil}")
+    rc = _run(tag, nbytes, lambda: _lib.load().codd_conv3x3_tc_ring_dil(
         x.data_ptr(), ld_of(x), cin, n, h, w, wring.data_ptr(), None if bias is None else bias.data_ptr(),
         None if residual is None else residual.data_ptr(), 0 if residual is None else ld_of(residual),
-        1 if res_bcast else 0, cout, act, out.data_ptr(), ld_of(out), _stream()))
-    _lib.check(rc, f"codd_conv3x3_tc_ring(cin={cin}, cout={cout})")
+        1 if res_bcast else 0, cout, act, out.data_ptr(), ld_of(out), dil, _stream()))
+    _lib.check(rc, f"codd_conv3x3_tc_ring_dil(cin={cin}, cout={cout}, dil={dil})")
     return out
 
 

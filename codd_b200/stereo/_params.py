@@ -51,6 +51,11 @@ def run_conv(pw, conv, x, act, x2=None, residual=None, res_bcast=False, head=Non
     if USE_TC and USE_RING and big and dl == 1 and ops.tc_eligible(cin, cout, k, st, pd, dl, x2):
         ws, b = pw.conv_ring(conv, head)
         return ops.conv3x3_tc_ring(x, ws, b, cout, act, residual=residual, res_bcast=res_bcast)
+    if (USE_TC and USE_RING and big and dl == 3 and head is None and ops.tc_eligible(cin, cout, k, st, pd, dl, x2)
+            and ops.ring_dil3_eligible(x, cout)):
+        # dilated ResBlocks (propagation.py:258-280): the ring kernel on the three row phases of the image
+        ws, b = pw.conv_ring(conv, None)
+        return ops.conv3x3_tc_ring(x, ws, b, cout, act, residual=residual, res_bcast=res_bcast, dil=3)
     if USE_TC and ops.tc_eligible(cin, cout, k, st, pd, dl, x2):
         ws, b = pw.conv_tc(conv, head)
         return ops.conv3x3_tc(x, ws, b, cout, act, residual=residual, res_bcast=res_bcast, dil=dl)

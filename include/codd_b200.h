@@ -119,6 +119,14 @@ CODD_API int codd_conv3x3_tc_ring(const float* in, int ldi, int cin, int n, int 
                                   const float* bias, const float* residual, int ldr, int res_bcast, int cout, int act,
                                   float* out, int ldo, void* stream);
 
+/* The same with dilation `dil` (pad = dil): dil = 1 is codd_conv3x3_tc_ring; dil = 3 (the dilated ResBlocks of
+ * tile_update4_1 / tile_update5, propagation.py:258-280) runs for 32 -> 32 channels and h % 3 == 0 — in y the three row
+ * phases of an image are walked as independent dilation-1 sub-images (tensor-map strides), in x the taps are 3 pixels apart
+ * in the staged row.  CODD_E_UNSUPPORTED otherwise (callers then use codd_conv3x3_tc_dil). */
+CODD_API int codd_conv3x3_tc_ring_dil(const float* in, int ldi, int cin, int n, int h, int w, const float* weight_ring,
+                                      const float* bias, const float* residual, int ldr, int res_bcast, int cout, int act,
+                                      float* out, int ldo, int dil, void* stream);
+
 /* Two stacked 3x3 / stride 1 / pad 1 convolutions, 16 -> 16 -> 16 channels, in one rolling-ring launch
  * (csrc/conv_tc_ring2.cu):  out = act_b(conv_b(act_a(conv_a(in) + bias_a)) + bias_b [+ residual]).  The intermediate
  * tensor never leaves the SM (TMEM -> fp16 operand tile in shared memory).  Replaces HITUNet conv_merge's 3x3 pair

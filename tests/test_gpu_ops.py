@@ -520,6 +520,24 @@ def test_conv4x4_stride2_tensor_core(ops, cin, cout, n, h, w):
     assert torch.equal(back(ops, out2), got)
 
 
+@pytest.mark.parametrize("n,h,w,res", [(2, 9, 200, True), (1, 3, 128, False), (3, 36, 131, True), (1, 72, 260, True),
+                                        (2, 6, 7, False)])
+def test_conv3x3_ring_dilated(ops, n, h, w, res):
+    """dilation 3 / pad 3, 32 -> 32 on the rolling-ring kernel (row phases as sub-images, taps 3 pixels apart): fp32-class
+    against torch; one- and many-row phases, ragged strip widths, with and without the ResBlock residual."""
+    from codd_b200.lib import ACT_LEAKY
+    g = gen(3000 + h * w + n)
+    x = torch.randn(n, 32, h, w, generator=g)
+    wt = torch.randn(32, 32, 3, 3, generator=g) / (32 * 9) ** 0.5
+    b = torch.randn(32, generator=g)
+    r = torch.randn(n, 32, h, w, generator=g)
+    ref = F.leaky_relu(F.conv2d(x, wt, b, padding=3, dilation=3) + (r if res else 0), 0.2)
+    assert ops.ring_dil3_eligible(nhwc(ops, x), 32)
+    out = ops.conv3x3_tc_ring(nhwc(ops, x), ops.pack_conv_weight_ring(wt.cuda()), b.cuda(), 32, ACT_LEAKY,
+                              residual=nhwc(ops, r) if res else None, dil=3)
+    torch.testing.assert_close(back(ops, out), ref, rtol=CONV_RTOL, atol=CONV_ATOL)
+
+
 @pytest.mark.parametrize("h,w", [(9, 200), (5, 128), (20, 131), (3, 7)])
 def test_conv3x3_tensor_core_dilated(ops, h, w):
     """dilation 3 / pad 3, 32 -> 32 (the dilated resblocks of tile_update4_1 / tile_update5)."""

@@ -31,7 +31,7 @@ def _functions(sass):
 @needs_build
 def test_ring_conv_uses_tcgen05_tma_and_uniform_issue():
     fns = {k: v for k, v in _functions(_sass("conv_tc_ring.o")).items() if "conv3x3_tc_ring_kernel" in k}
-    assert len(fns) == 3                                          # <16,16>, <32,16>, <32,32>
+    assert len(fns) == 4                                          # <16,16>, <32,16>, <32,32>, <32,32> dilation 3
     for name, lines in fns.items():
         text = "\n".join(lines)
         assert "UTCHMMA" in text, name                            # tcgen05.mma kind::f16
