@@ -15,9 +15,13 @@
 //     shifted by one pixel (the swizzle is a function of the address) — every input element is loaded once per
 //     output row, no im2col, and out-of-range coordinates (left / right / top / bottom padding) arrive as zeros;
 //   * a stage = the two parity slots of ONE input row (one ky); a tile consumes 4 stages; NBUF stages in flight;
-//   * precision 3xTF32 exactly as conv_tc.cu: pass A multiplies the raw fp32 stage (the MMA datapath reads the top 19
-//     bits = x_hi) by [w_hi | w_lo] (N = 2 NP), the split warps then rewrite the stage as x_lo = x - x_hi in place and
-//     pass B multiplies it by w_hi (N = NP), LAG stages behind pass A so the tensor pipe never waits for the split;
+//   * precision: three fp16 products with fp32 accumulation, as the rolling-ring kernel (conv_tc_ring.cu): the split
+//     warps rewrite every staged pixel row IN PLACE from KC fp32 values to [x_hi = fp16(x) (KC halves) | fp16(2^10 (x -
+//     x_hi)) (KC halves)] — the same bytes — so that the row's first half is the pass-A operand and its second half the
+//     pass-B operand of kind::f16 MMAs (K = 16 per MMA: half the MMAs and half the shared-memory operand reads of the
+//     3xTF32 version this replaced, which was bound by exactly those reads).  Pass A: x_hi x [w_hi | 2^10 w_lo] into
+//     columns [0, 2 NP); pass B: 2^10 x_lo x w_hi into columns [NP, 2 NP); the epilogue adds hi + 2^-10 lo.  |x|, |w| are
+//     clamped to the fp16 range (65504);
 //   * accumulators in TMEM (NACC tiles x 2 NP columns), epilogue warps read them with tcgen05.ld (lane = pixel), add
 //     the bias, apply the activation and store NHWC.
 //
@@ -27,6 +31,8 @@
 // shifted by kx pixels; the padding is TMA's out-of-bounds fill), followed in the epilogue by LeakyReLU, the 16x16 1x1
 // conv, LeakyReLU and a PLANAR store (what the cost-volume kernel reads).  General rule: input column
 // xi = SW*xo + kx - PW = SW*(xo + s) + r with r = (kx - PW) mod SW, s = floor((kx - PW) / SW): slot r, pixel shift s.
+#include <cuda_fp16.h>
+
 #include "tc_util.cuh"
 
 namespace {
@@ -67,7 +73,7 @@ static_assert(K4Geo<2, 1, 16>::cls(0) == 1 && K4Geo<2, 1, 16>::shift(0) == 0 && 
 static_assert(K4Geo<4, 0, 16>::cls(3) == 3 && K4Geo<4, 0, 16>::shift(3) == 0 && K4Geo<4, 0, 16>::BOXP == 128, "stride-4 geometry");
 static_assert(K4Geo<1, 0, 16>::cls(3) == 0 && K4Geo<1, 0, 16>::shift(3) == 3 && K4Geo<1, 0, 16>::BOXP == 136, "stride-1 geometry");
 struct S2P {
-    const float* wpk;   // [2][16 taps][NP][16] fp32: pass 0 = tf32 hi, pass 1 = lo
+    const float* wpk;   // fp16 data: [16 taps][2 NP rows: w_hi (NP) | 2^10 w_lo (NP)][KC halves] (ops.pack_conv_weight_tc4)
     const float* bias;
     float* out;
     int N, Ho, Wo, Cout, ldo, act;
@@ -86,10 +92,12 @@ __global__ void __launch_bounds__(S2_THREADS, 1) conv4x4s2_tc_kernel(const __gri
     constexpr uint32_t S2_ROWB = KC * 4;
     constexpr int S2_BOXP = G::BOXP;
     constexpr uint32_t S2_SLOT = G::SLOT, S2_STAGE = G::STAGE;
-    constexpr uint32_t ACC_COLS = 2 * NP;          // per tile: [0,NP) = x_hi*w_hi + x_lo*w_hi, [NP,2NP) = x_hi*w_lo
+    constexpr uint32_t ACC_COLS = 2 * NP;          // per tile: [0,NP) = x_hi*w_hi, [NP,2NP) = 2^10 (x_hi*w_lo + x_lo*w_hi)
     constexpr uint32_t TMEM_COLS = (NACC * ACC_COLS <= 128) ? 128u : (NACC * ACC_COLS <= 256) ? 256u : 512u;
-    constexpr uint32_t B_TAP = 2 * NP * S2_ROWB;   // per tap: NP rows of w_hi followed by NP rows of w_lo
-    constexpr uint32_t IDESC_BASE = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 4) << 24);   // f32 acc, tf32 x tf32, M = 128
+    constexpr uint32_t B_TAP = 2 * NP * S2_ROWB;   // per tap: NP rows of w_hi followed by NP rows of 2^10 w_lo; a row holds
+                                                   // KC halves in its first S2_ROWB / 2 bytes (same pitch and swizzle as A)
+    constexpr uint32_t IDESC_BASE = (1u << 4) | ((128u >> 4) << 24);                            // f32 acc, f16 x f16, M = 128
+    constexpr uint32_t LO_OFF = S2_ROWB / 2;       // byte offset of the x_lo halves inside a staged pixel row
     constexpr uint32_t IDESC2 = IDESC_BASE | ((uint32_t)((2 * NP) >> 3) << 17);
     constexpr uint32_t IDESC1 = IDESC_BASE | ((uint32_t)(NP >> 3) << 17);
     constexpr uint32_t BOX_BYTES = S2_BOXP * S2_ROWB;
@@ -129,14 +137,13 @@ __global__ void __launch_bounds__(S2_THREADS, 1) conv4x4s2_tc_kernel(const __gri
                      "r"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
-    // weights -> swizzled shared image (once per CTA): [tap][w_hi rows | w_lo rows][16]
-    for (int idx = tid; idx < 2 * 16 * NP * (S2_KC / 4); idx += S2_THREADS) {
-        const int j = idx % (S2_KC / 4);
-        const int r = (idx / (S2_KC / 4)) % NP;
-        const int pt = idx / ((S2_KC / 4) * NP);          // pass * 16 + tap
-        const float4 v = ldg4(p.wpk + ((size_t)pt * NP + r) * S2_KC + j * 4);
-        const int pass = pt >> 4, tap = pt & 15;
-        *reinterpret_cast<float4*>(gB + tap * B_TAP + s2_swz<KC>(r + pass * NP, j)) = v;
+    // weights -> swizzled shared image (once per CTA): [tap][w_hi rows | 2^10 w_lo rows], KC halves per row
+    for (int idx = tid; idx < 16 * 2 * NP * (S2_KC / 8); idx += S2_THREADS) {
+        const int j = idx % (S2_KC / 8);
+        const int r = (idx / (S2_KC / 8)) % (2 * NP);
+        const int tap = idx / ((S2_KC / 8) * 2 * NP);
+        const float4 v = ldg4(p.wpk + ((size_t)tap * 2 * NP + r) * (S2_KC / 2) + j * 4);
+        *reinterpret_cast<float4*>(gB + tap * B_TAP + s2_swz<KC>(r, j)) = v;
     }
     if (TILEF)
         for (int idx = tid; idx < 256; idx += S2_THREADS) s_w1[(idx & 15) * 16 + (idx >> 4)] = __ldg(p.w1 + idx);
@@ -182,50 +189,40 @@ __global__ void __launch_bounds__(S2_THREADS, 1) conv4x4s2_tc_kernel(const __gri
         // ===================== MMA issuer =====================
         if (codd_elect_one()) {
             const uint64_t b_desc = s2_desc<KC>(sB);
-            // pass B of stage j: x_lo * w_hi into columns [0, NP) of its tile's accumulator
-            auto pass_b = [&](int j) {
-                const int sb = j % NBUF, ky = j & 3, ab = (j >> 2) % NACC;
-                s2_mbar_wait<false>(SBAR(LO, sb), ((uint32_t)(j / NBUF)) & 1u);
-                s2_fence_after();
-                const uint64_t a_desc = s2_desc<KC>(sbase + sb * S2_STAGE);
-                const uint32_t d_tmem = tmem + (uint32_t)ab * ACC_COLS;
-#pragma unroll
-                for (int kx = 0; kx < 4; ++kx)
-#pragma unroll
-                    for (int k = 0; k < S2_KC / 8; ++k) {
-                        const uint32_t aoff = (uint32_t)G::cls(kx) * S2_SLOT + (uint32_t)G::shift(kx) * S2_ROWB + k * 32;
-                        const uint32_t boff = (uint32_t)(ky * 4 + kx) * B_TAP + k * 32;
-                        s2_mma_tf32<true>(d_tmem, a_desc + (aoff >> 4), b_desc + (boff >> 4), IDESC1);
-                    }
-                s2_commit(SBAR(EMPTY, sb));                  // stage buffer free -> producer
-                if (ky == 3) s2_commit(ABAR(ACCF, ab));      // the tile's accumulators are complete -> epilogue
-            };
             int it = 0;
             for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
                 for (int ky = 0; ky < 4; ++ky, ++it) {
                     const int sb = it % NBUF, ti = it >> 2, ab = ti % NACC;
-                    s2_mbar_wait<false>(SBAR(FULL, sb), ((uint32_t)(it / NBUF)) & 1u);
+                    s2_mbar_wait<false>(SBAR(LO, sb), ((uint32_t)(it / NBUF)) & 1u);          // operands written by the split warps
                     if (ky == 0) s2_mbar_wait<false>(ABAR(ACCE, ab), (((uint32_t)(ti / NACC)) & 1u) ^ 1u);
                     s2_fence_after();
                     const uint64_t a_desc = s2_desc<KC>(sbase + sb * S2_STAGE);
                     const uint32_t d_tmem = tmem + (uint32_t)ab * ACC_COLS;
-                    // pass A: x_hi * [w_hi | w_lo] (raw fp32 stage: the MMA reads the top 19 bits)
+                    // pass A: x_hi * [w_hi | 2^10 w_lo]
 #pragma unroll
                     for (int kx = 0; kx < 4; ++kx)
 #pragma unroll
-                        for (int k = 0; k < S2_KC / 8; ++k) {
+                        for (int k = 0; k < S2_KC / 16; ++k) {
                             const uint32_t aoff = (uint32_t)G::cls(kx) * S2_SLOT + (uint32_t)G::shift(kx) * S2_ROWB + k * 32;
                             const uint32_t boff = (uint32_t)(ky * 4 + kx) * B_TAP + k * 32;
                             if (ky == 0 && kx == 0 && k == 0)
-                                s2_mma_tf32<false>(d_tmem, a_desc + (aoff >> 4), b_desc + (boff >> 4), IDESC2);
+                                s2_mma_f16<false>(d_tmem, a_desc + (aoff >> 4), b_desc + (boff >> 4), IDESC2);
                             else
-                                s2_mma_tf32<true>(d_tmem, a_desc + (aoff >> 4), b_desc + (boff >> 4), IDESC2);
+                                s2_mma_f16<true>(d_tmem, a_desc + (aoff >> 4), b_desc + (boff >> 4), IDESC2);
                         }
-                    s2_commit(SBAR(P12, sb));
-                    if (it >= LAG) pass_b(it - LAG);
+                    // pass B: 2^10 x_lo * w_hi into the scaled half
+#pragma unroll
+                    for (int kx = 0; kx < 4; ++kx)
+#pragma unroll
+                        for (int k = 0; k < S2_KC / 16; ++k) {
+                            const uint32_t aoff = (uint32_t)G::cls(kx) * S2_SLOT + (uint32_t)G::shift(kx) * S2_ROWB + LO_OFF + k * 32;
+                            const uint32_t boff = (uint32_t)(ky * 4 + kx) * B_TAP + k * 32;
+                            s2_mma_f16<true>(d_tmem + NP, a_desc + (aoff >> 4), b_desc + (boff >> 4), IDESC1);
+                        }
+                    s2_commit(SBAR(EMPTY, sb));                  // stage buffer free -> producer
+                    if (ky == 3) s2_commit(ABAR(ACCF, ab));      // the tile's accumulators are complete -> epilogue
                 }
             }
-            for (int j = (it > LAG ? it - LAG : 0); j < it; ++j) pass_b(j);
         }
     } else if (warp >= 8) {
         // ===================== epilogue (warps 8-11) =====================
@@ -258,7 +255,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) conv4x4s2_tc_kernel(const __gri
             if (xo >= p.Wo) continue;
             float v[NP];
 #pragma unroll
-            for (int c = 0; c < NP; ++c) v[c] = (acc[c] + acc[NP + c]) + biasr[c];
+            for (int c = 0; c < NP; ++c) v[c] = fmaf(acc[NP + c], 1.f / 1024.f, acc[c]) + biasr[c];
             if (TILEF) {
                 // initialization.py:119-124: LeakyReLU -> 1x1 conv (16 -> 16) -> LeakyReLU, planar [n,16,Ho,Wo]
 #pragma unroll
@@ -306,40 +303,54 @@ __global__ void __launch_bounds__(S2_THREADS, 1) conv4x4s2_tc_kernel(const __gri
             }
         }
     } else {
-        // ===================== in-place hi/lo split of the stage (warps 0-7) =====================
+        // ===================== in-place fp32 -> [fp16 hi | fp16 2^10 lo] conversion of the stage (warps 0-7) =====================
+        // one thread owns whole pixel rows (the conversion permutes bytes inside a row, never across rows)
+        constexpr int NPIX = G::NSLOT * S2_BOXP;                                      // pixel rows per stage
+        constexpr int ITERS = (NPIX + S2_SPLIT_THREADS - 1) / S2_SPLIT_THREADS;
+        constexpr int NCH = S2_KC / 4;                                                // 16-byte chunks per row
         int it = 0;
         for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
             for (int ky = 0; ky < 4; ++ky, ++it) {
                 const int sb = it % NBUF;
-                s2_mbar_wait<true, 128>(SBAR(P12, sb), ((uint32_t)(it / NBUF)) & 1u);   // pass A has consumed the raw stage
-                s2_fence_after();
-                // all loads of a stage first (up to NSLOT * 3 independent 128-bit reads in flight per thread), then the
-                // conversions and the stores: the split warps are the pacing role of this kernel (ncu: 36 % of the samples)
-                constexpr int PER_SLOT = (int)(BOX_BYTES / 16);
-                constexpr int ITERS = (PER_SLOT + S2_SPLIT_THREADS - 1) / S2_SPLIT_THREADS;
-                float4 v[G::NSLOT][ITERS];
+                s2_mbar_wait<true, 64>(SBAR(FULL, sb), ((uint32_t)(it / NBUF)) & 1u);     // the raw rows have landed
+                float4 v[ITERS][NCH];
 #pragma unroll
-                for (int r = 0; r < G::NSLOT; ++r) {
-                    const float4* a4 = reinterpret_cast<const float4*>(gbase + sb * S2_STAGE + r * S2_SLOT);
+                for (int i = 0; i < ITERS; ++i) {
+                    const int idx = tid + i * S2_SPLIT_THREADS;
+                    if (idx < NPIX) {
+                        const int r = idx / S2_BOXP, px = idx - r * S2_BOXP;
+                        const uint8_t* row = gbase + sb * S2_STAGE + r * S2_SLOT;
 #pragma unroll
-                    for (int i = 0; i < ITERS; ++i) {
-                        const int idx = tid + i * S2_SPLIT_THREADS;
-                        if (idx < PER_SLOT) v[r][i] = a4[idx];
+                        for (int j = 0; j < NCH; ++j) v[i][j] = *reinterpret_cast<const float4*>(row + s2_swz<KC>(px, j));
                     }
                 }
 #pragma unroll
-                for (int r = 0; r < G::NSLOT; ++r) {
-                    float4* a4 = reinterpret_cast<float4*>(gbase + sb * S2_STAGE + r * S2_SLOT);
+                for (int i = 0; i < ITERS; ++i) {
+                    const int idx = tid + i * S2_SPLIT_THREADS;
+                    if (idx < NPIX) {
+                        const int r = idx / S2_BOXP, px = idx - r * S2_BOXP;
+                        uint8_t* row = gbase + sb * S2_STAGE + r * S2_SLOT;
+                        uint32_t hi2[NCH * 2], lo2[NCH * 2];
 #pragma unroll
-                    for (int i = 0; i < ITERS; ++i) {
-                        const int idx = tid + i * S2_SPLIT_THREADS;
-                        if (idx < PER_SLOT) {
-                            float4 q = v[r][i];
-                            q.x = __fsub_rn(q.x, __uint_as_float(__float_as_uint(q.x) & 0xFFFFE000u));
-                            q.y = __fsub_rn(q.y, __uint_as_float(__float_as_uint(q.y) & 0xFFFFE000u));
-                            q.z = __fsub_rn(q.z, __uint_as_float(__float_as_uint(q.z) & 0xFFFFE000u));
-                            q.w = __fsub_rn(q.w, __uint_as_float(__float_as_uint(q.w) & 0xFFFFE000u));
-                            a4[idx] = q;
+                        for (int j = 0; j < NCH; ++j) {
+                            const float xs[4] = {v[i][j].x, v[i][j].y, v[i][j].z, v[i][j].w};
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const float a = fminf(fmaxf(xs[2 * e], -65504.f), 65504.f);
+                                const float b = fminf(fmaxf(xs[2 * e + 1], -65504.f), 65504.f);
+                                const __half2 h = __floats2half2_rn(a, b);
+                                const float2 hf = __half22float2(h);
+                                const __half2 l = __floats2half2_rn((a - hf.x) * 1024.f, (b - hf.y) * 1024.f);
+                                hi2[2 * j + e] = *reinterpret_cast<const uint32_t*>(&h);
+                                lo2[2 * j + e] = *reinterpret_cast<const uint32_t*>(&l);
+                            }
+                        }
+#pragma unroll
+                        for (int jj = 0; jj < NCH / 2; ++jj) {
+                            *reinterpret_cast<uint4*>(row + s2_swz<KC>(px, jj)) =
+                                make_uint4(hi2[4 * jj], hi2[4 * jj + 1], hi2[4 * jj + 2], hi2[4 * jj + 3]);
+                            *reinterpret_cast<uint4*>(row + s2_swz<KC>(px, NCH / 2 + jj)) =
+                                make_uint4(lo2[4 * jj], lo2[4 * jj + 1], lo2[4 * jj + 2], lo2[4 * jj + 3]);
                         }
                     }
                 }

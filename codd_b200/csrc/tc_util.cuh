@@ -54,6 +54,24 @@ __device__ __forceinline__ void s2_mma_tf32(uint32_t tmem_d, uint64_t da, uint64
             : "memory");
     }
 }
+template <bool ACC>
+__device__ __forceinline__ void s2_mma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc) {
+    if (ACC) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.eq.u32 p, 1, 1;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.eq.u32 p, 1, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc)
+            : "memory");
+    }
+}
 __device__ __forceinline__ void s2_ld16(uint32_t taddr, float* v) {
     uint32_t r[16];
     asm volatile(

@@ -169,17 +169,20 @@ def pack_conv_weight_tc(w):
 
 
 def pack_conv_weight_tc4(w):
-    """torch [Cout,Cin,4,4] -> [2][16][NP][KC] hi/lo split for codd_conv4x4s2_tc / codd_tile_features_tc (3xTF32),
-    tap = ky*4 + kx, KC = 16 (Cin = 16) or 32 (Cin = 24, 32: zero-padded), NP = 16 | 32."""
+    """torch [Cout,Cin,4,4] -> fp16 [16 taps][2 NP rows][KC] for codd_conv4x4s2_tc / codd_tile_features_tc (returned
+    viewed as float32): per tap NP rows of w_hi = fp16(w) followed by NP rows of fp16(2^10 (w - w_hi)); tap = ky*4 + kx,
+    KC = 16 (Cin = 16) or 32 (Cin = 24, 32: zero-padded), NP = 16 | 32.  Same three-product scheme as
+    pack_conv_weight_ring."""
     cout, cin, kh, kw = w.shape
     assert kh == 4 and kw == 4 and cin in (16, 24, 32) and cout <= 32
     npad = 16 if cout <= 16 else 32
     kc = 16 if cin <= 16 else 32
     wt = torch.zeros((16, npad, kc), dtype=torch.float32, device=w.device)
     wt[:, :cout, :cin] = w.detach().float().permute(2, 3, 0, 1).reshape(16, cout, cin)
-    hi = _tf32_round(wt)
-    lo = _tf32_round(wt - hi)
-    return torch.stack([hi, lo]).contiguous()
+    wt = wt.clamp(-65504.0, 65504.0)
+    hi = wt.half()
+    lo = ((wt - hi.float()) * 1024.0).half()
+    return torch.cat([hi, lo], dim=1).contiguous().view(torch.float32)     # [16][2 NP][KC / 2] as float32
 
 
 def tc4_eligible(x, cout, k, stride, pad, dil, x2, residual):
@@ -195,7 +198,7 @@ def conv4x4s2_tc(x, wsplit, bias, cout, act=ACT_NONE):
     _require_cuda(x, wsplit, bias)
     n, cin, h, w = x.shape
     out = empty_nhwc(n, cout, h // 2, w // 2, x.device)
-    nbytes = 4 * (n * h * w * cin + n * (h // 2) * (w // 2) * cout + wsplit.numel() // 2)
+    nbytes = 4 * (n * h * w * cin + n * (h // 2) * (w // 2) * cout + wsplit.numel())
     rc = _run(f"conv4x4s2tc_cin{cin}_cout{cout}", nbytes, lambda: _lib.load().codd_conv4x4s2_tc(
         x.data_ptr(), ld_of(x), cin, n, h, w, wsplit.data_ptr(), None if bias is None else bias.data_ptr(), cout, act,
         out.data_ptr(), ld_of(out), _stream()))

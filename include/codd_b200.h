@@ -138,9 +138,11 @@ CODD_API int codd_conv3x3x2_tc_ring(const float* in, int ldi, int n, int h, int 
                                     const float* bias_a, int act_a, const float* weight_ring_b, const float* bias_b,
                                     const float* residual, int ldr, int act_b, float* out, int ldo, void* stream);
 
-/* 4x4 / stride 2 / pad 1 convolution (HITUNet conv_down first layer, backbone.py:8-14) on the tensor cores, Cin = 16,
- * Cout <= 32, even H and W: implicit GEMM over TMA boxes of same-parity columns (csrc/conv_tc_s2.cu), 3xTF32.
- * weight_split (host: ops.pack_conv_weight_tc4) = [2][16 taps][NP][16], pass 0 = tf32 hi, pass 1 = lo, NP = 16 | 32.
+/* 4x4 / stride 2 / pad 1 convolution (HITUNet conv_down first layer, backbone.py:8-14) on the tensor cores, Cin in
+ * {16, 24, 32}, Cout <= 32, even H and W: implicit GEMM over TMA boxes of same-parity columns (csrc/conv_tc_s2.cu), three
+ * fp16 products with fp32 accumulation (x = x_hi + x_lo, w = w_hi + w_lo as in codd_conv3x3_tc_ring: fp32-class accuracy).
+ * weight_split (host: ops.pack_conv_weight_tc4) holds fp16 data [16 taps][2 NP rows][KC]: per tap NP rows of w_hi = fp16(w)
+ * followed by NP rows of fp16(2^10 (w - w_hi)), NP = 16 | 32 >= cout, KC = 16 | 32 >= cin, zero padded.
  * out [n, h/2, w/2, cout] NHWC (ldo).  CODD_E_UNSUPPORTED for other geometries (callers fall back to codd_conv2d_nhwc). */
 CODD_API int codd_conv4x4s2_tc(const float* in, int ldi, int cin, int n, int h, int w, const float* weight_split,
                                const float* bias, int cout, int act, float* out, int ldo, void* stream);
@@ -180,9 +182,9 @@ CODD_API int codd_tile_features(const float* in, int ldi, int cin, int n, int h_
                                 const float* w0, const float* b0, const float* w1, const float* b1,
                                 int right, float* out, void* stream);
 
-/* The same on the tensor cores for cin = 16 (csrc/conv_tc_s2.cu: the 4x4 conv as a tcgen05 implicit GEMM over TMA boxes of
- * column residue classes, 3xTF32; LeakyReLU, the 1x1 conv, LeakyReLU and the planar store in the epilogue).
- * w0_split (host: ops.pack_conv_weight_tc4) = [2][16 taps][16][16] tf32 hi / lo.  CODD_E_UNSUPPORTED for cin != 16. */
+/* The same on the tensor cores (csrc/conv_tc_s2.cu: the 4x4 conv as a tcgen05 implicit GEMM over TMA boxes of column
+ * residue classes, three fp16 products as codd_conv4x4s2_tc; LeakyReLU, the 1x1 conv, LeakyReLU and the planar store in the
+ * epilogue).  w0_split from ops.pack_conv_weight_tc4 (fp16 [16 taps][32 rows: w_hi | 2^10 w_lo][KC]), cin in {16, 24, 32}. */
 CODD_API int codd_tile_features_tc(const float* in, int ldi, int cin, int n, int h_in, int w_in,
                                    const float* w0_split, const float* b0, const float* w1, const float* b1,
                                    int right, float* out, void* stream);
