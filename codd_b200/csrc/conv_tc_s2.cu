@@ -82,7 +82,8 @@ struct S2P {
     const float* b1;
 };
 
-// NBUF stage buffers, NACC accumulator buffers, pass B trails pass A by LAG stages (LAG < NBUF).
+// NBUF stage buffers (as many as shared memory allows: a buffer's cycle — TMA latency, conversion, MMAs, commit — is
+// ~3 us, so the stages in flight set the throughput), NACC accumulator buffers; LAG is unused since the fp16 conversion.
 // SW / SH: strides, PW / PH: left / top padding, TILEF: tile-feature epilogue (LeakyReLU, 1x1, LeakyReLU, planar store)
 template <int SW, int SH, int PW, int PH, int KC, int NP, int NBUF, int NACC, int LAG, bool TILEF>
 __global__ void __launch_bounds__(S2_THREADS, 1) conv4x4s2_tc_kernel(const __grid_constant__ CUtensorMap tmap, S2P p) {
@@ -425,11 +426,11 @@ extern "C" int codd_conv4x4s2_tc(const float* in, int ldi, int cin, int n, int h
     p.ntiles = (int)nt;
     cudaStream_t s = (cudaStream_t)stream;
     if (kc == 16) {
-        if (cout <= 16) return s2_launch<2, 2, 1, 1, 16, 16, 6, 4, 2, false>(tmap, p, s);
-        return s2_launch<2, 2, 1, 1, 16, 32, 6, 4, 2, false>(tmap, p, s);
+        if (cout <= 16) return s2_launch<2, 2, 1, 1, 16, 16, 10, 4, 2, false>(tmap, p, s);
+        return s2_launch<2, 2, 1, 1, 16, 32, 8, 4, 2, false>(tmap, p, s);
     }
     // Cin = 24 / 32 (down3, down4): 128 KB of weights leave room for two stages
-    if (cout <= 16) return s2_launch<2, 2, 1, 1, 32, 16, 3, 4, 1, false>(tmap, p, s);
+    if (cout <= 16) return s2_launch<2, 2, 1, 1, 32, 16, 4, 4, 1, false>(tmap, p, s);
     return s2_launch<2, 2, 1, 1, 32, 32, 2, 4, 1, false>(tmap, p, s);
 }
 
@@ -456,9 +457,9 @@ extern "C" int codd_tile_features_tc(const float* in, int ldi, int cin, int n, i
     p.ntiles = (int)nt;
     cudaStream_t s = (cudaStream_t)stream;
     if (kc == 16) {
-        if (right) return s2_launch<1, 4, 0, 0, 16, 16, 6, 4, 2, true>(tmap, p, s);
-        return s2_launch<4, 4, 0, 0, 16, 16, 4, 4, 2, true>(tmap, p, s);
+        if (right) return s2_launch<1, 4, 0, 0, 16, 16, 12, 4, 2, true>(tmap, p, s);
+        return s2_launch<4, 4, 0, 0, 16, 16, 5, 4, 2, true>(tmap, p, s);
     }
-    if (right) return s2_launch<1, 4, 0, 0, 32, 16, 4, 4, 2, true>(tmap, p, s);
+    if (right) return s2_launch<1, 4, 0, 0, 32, 16, 8, 4, 2, true>(tmap, p, s);
     return s2_launch<4, 4, 0, 0, 32, 16, 2, 4, 1, true>(tmap, p, s);
 }
