@@ -88,6 +88,10 @@ struct S2P {
 template <int SW, int SH, int PW, int PH, int KC, int NP, int NBUF, int NACC, int LAG, bool TILEF>
 __global__ void __launch_bounds__(S2_THREADS, 1) conv4x4s2_tc_kernel(const __grid_constant__ CUtensorMap tmap, S2P p) {
     static_assert(LAG >= 1 && LAG < NBUF && NACC >= 2, "pipeline depths");
+    // the two conversion groups take alternate stages: with an even ring depth a stage barrier is always waited on by
+    // the same group, which then sees every phase of it; with an odd depth a group would see every other phase and the
+    // one-bit parity wait could pass a phase early (the hazard documented in conv_tc_ring.cu; found here as a hang)
+    static_assert(NBUF % 2 == 0, "stage ring depth must be even");
     using G = K4Geo<SW, PW, KC>;
     constexpr int S2_KC = KC;
     constexpr uint32_t S2_ROWB = KC * 4;
@@ -125,7 +129,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) conv4x4s2_tc_kernel(const __gri
             s2_mbar_init(SBAR(FULL, b), 1);
             s2_mbar_init(SBAR(EMPTY, b), 1);
             s2_mbar_init(SBAR(P12, b), 1);
-            s2_mbar_init(SBAR(LO, b), S2_SPLIT_THREADS);
+            s2_mbar_init(SBAR(LO, b), S2_SPLIT_THREADS / 2);
         }
         for (int b = 0; b < NACC; ++b) {
             s2_mbar_init(ABAR(ACCF, b), 1);
@@ -307,17 +311,22 @@ __global__ void __launch_bounds__(S2_THREADS, 1) conv4x4s2_tc_kernel(const __gri
         // ===================== in-place fp32 -> [fp16 hi | fp16 2^10 lo] conversion of the stage (warps 0-7) =====================
         // one thread owns whole pixel rows (the conversion permutes bytes inside a row, never across rows)
         constexpr int NPIX = G::NSLOT * S2_BOXP;                                      // pixel rows per stage
-        constexpr int ITERS = (NPIX + S2_SPLIT_THREADS - 1) / S2_SPLIT_THREADS;
+        // two groups of four warps take alternate stages (a stage's conversion is a latency chain: wait, loads,
+        // conversions, stores, proxy fence, arrive — two of them in flight)
+        constexpr int GT = S2_SPLIT_THREADS / 2;
+        constexpr int ITERS = (NPIX + GT - 1) / GT;
         constexpr int NCH = S2_KC / 4;                                                // 16-byte chunks per row
+        const int grp = warp >> 2, gtid = tid & (GT - 1);
         int it = 0;
         for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
             for (int ky = 0; ky < 4; ++ky, ++it) {
+                if ((it & 1) != grp) continue;
                 const int sb = it % NBUF;
                 s2_mbar_wait<true, 64>(SBAR(FULL, sb), ((uint32_t)(it / NBUF)) & 1u);     // the raw rows have landed
                 float4 v[ITERS][NCH];
 #pragma unroll
                 for (int i = 0; i < ITERS; ++i) {
-                    const int idx = tid + i * S2_SPLIT_THREADS;
+                    const int idx = gtid + i * GT;
                     if (idx < NPIX) {
                         const int r = idx / S2_BOXP, px = idx - r * S2_BOXP;
                         const uint8_t* row = gbase + sb * S2_STAGE + r * S2_SLOT;
@@ -327,7 +336,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) conv4x4s2_tc_kernel(const __gri
                 }
 #pragma unroll
                 for (int i = 0; i < ITERS; ++i) {
-                    const int idx = tid + i * S2_SPLIT_THREADS;
+                    const int idx = gtid + i * GT;
                     if (idx < NPIX) {
                         const int r = idx / S2_BOXP, px = idx - r * S2_BOXP;
                         uint8_t* row = gbase + sb * S2_STAGE + r * S2_SLOT;
@@ -458,7 +467,7 @@ extern "C" int codd_tile_features_tc(const float* in, int ldi, int cin, int n, i
     cudaStream_t s = (cudaStream_t)stream;
     if (kc == 16) {
         if (right) return s2_launch<1, 4, 0, 0, 16, 16, 12, 4, 2, true>(tmap, p, s);
-        return s2_launch<4, 4, 0, 0, 16, 16, 5, 4, 2, true>(tmap, p, s);
+        return s2_launch<4, 4, 0, 0, 16, 16, 4, 4, 2, true>(tmap, p, s);
     }
     if (right) return s2_launch<1, 4, 0, 0, 32, 16, 8, 4, 2, true>(tmap, p, s);
     return s2_launch<4, 4, 0, 0, 32, 16, 2, 4, 1, true>(tmap, p, s);
