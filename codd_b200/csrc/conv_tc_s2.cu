@@ -323,44 +323,50 @@ __global__ void __launch_bounds__(S2_THREADS, 1) conv4x4s2_tc_kernel(const __gri
                 if ((it & 1) != grp) continue;
                 const int sb = it % NBUF;
                 s2_mbar_wait<true, 64>(SBAR(FULL, sb), ((uint32_t)(it / NBUF)) & 1u);     // the raw rows have landed
-                float4 v[ITERS][NCH];
+                // rows in batches of BR (all loads of a batch first, then its conversions and stores): the whole stage at
+                // once for 64-byte rows, two rows at a time for 128-byte rows (register budget)
+                constexpr int BR = (NCH == 8) ? 2 : ITERS;
 #pragma unroll
-                for (int i = 0; i < ITERS; ++i) {
-                    const int idx = gtid + i * GT;
-                    if (idx < NPIX) {
-                        const int r = idx / S2_BOXP, px = idx - r * S2_BOXP;
-                        const uint8_t* row = gbase + sb * S2_STAGE + r * S2_SLOT;
+                for (int i0 = 0; i0 < ITERS; i0 += BR) {
+                    float4 v[BR][NCH];
 #pragma unroll
-                        for (int j = 0; j < NCH; ++j) v[i][j] = *reinterpret_cast<const float4*>(row + s2_swz<KC>(px, j));
-                    }
-                }
+                    for (int ib = 0; ib < BR; ++ib) {
+                        const int idx = gtid + (i0 + ib) * GT;
+                        if (i0 + ib < ITERS && idx < NPIX) {
+                            const int r = idx / S2_BOXP, px = idx - r * S2_BOXP;
+                            const uint8_t* row = gbase + sb * S2_STAGE + r * S2_SLOT;
 #pragma unroll
-                for (int i = 0; i < ITERS; ++i) {
-                    const int idx = gtid + i * GT;
-                    if (idx < NPIX) {
-                        const int r = idx / S2_BOXP, px = idx - r * S2_BOXP;
-                        uint8_t* row = gbase + sb * S2_STAGE + r * S2_SLOT;
-                        uint32_t hi2[NCH * 2], lo2[NCH * 2];
-#pragma unroll
-                        for (int j = 0; j < NCH; ++j) {
-                            const float xs[4] = {v[i][j].x, v[i][j].y, v[i][j].z, v[i][j].w};
-#pragma unroll
-                            for (int e = 0; e < 2; ++e) {
-                                const float a = fminf(fmaxf(xs[2 * e], -65504.f), 65504.f);
-                                const float b = fminf(fmaxf(xs[2 * e + 1], -65504.f), 65504.f);
-                                const __half2 h = __floats2half2_rn(a, b);
-                                const float2 hf = __half22float2(h);
-                                const __half2 l = __floats2half2_rn((a - hf.x) * 1024.f, (b - hf.y) * 1024.f);
-                                hi2[2 * j + e] = *reinterpret_cast<const uint32_t*>(&h);
-                                lo2[2 * j + e] = *reinterpret_cast<const uint32_t*>(&l);
-                            }
+                            for (int j = 0; j < NCH; ++j) v[ib][j] = *reinterpret_cast<const float4*>(row + s2_swz<KC>(px, j));
                         }
+                    }
 #pragma unroll
-                        for (int jj = 0; jj < NCH / 2; ++jj) {
-                            *reinterpret_cast<uint4*>(row + s2_swz<KC>(px, jj)) =
-                                make_uint4(hi2[4 * jj], hi2[4 * jj + 1], hi2[4 * jj + 2], hi2[4 * jj + 3]);
-                            *reinterpret_cast<uint4*>(row + s2_swz<KC>(px, NCH / 2 + jj)) =
-                                make_uint4(lo2[4 * jj], lo2[4 * jj + 1], lo2[4 * jj + 2], lo2[4 * jj + 3]);
+                    for (int ib = 0; ib < BR; ++ib) {
+                        const int idx = gtid + (i0 + ib) * GT;
+                        if (i0 + ib < ITERS && idx < NPIX) {
+                            const int r = idx / S2_BOXP, px = idx - r * S2_BOXP;
+                            uint8_t* row = gbase + sb * S2_STAGE + r * S2_SLOT;
+                            uint32_t hi2[NCH * 2], lo2[NCH * 2];
+#pragma unroll
+                            for (int j = 0; j < NCH; ++j) {
+                                const float xs[4] = {v[ib][j].x, v[ib][j].y, v[ib][j].z, v[ib][j].w};
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) {
+                                    const float a = fminf(fmaxf(xs[2 * e], -65504.f), 65504.f);
+                                    const float b = fminf(fmaxf(xs[2 * e + 1], -65504.f), 65504.f);
+                                    const __half2 h = __floats2half2_rn(a, b);
+                                    const float2 hf = __half22float2(h);
+                                    const __half2 l = __floats2half2_rn((a - hf.x) * 1024.f, (b - hf.y) * 1024.f);
+                                    hi2[2 * j + e] = *reinterpret_cast<const uint32_t*>(&h);
+                                    lo2[2 * j + e] = *reinterpret_cast<const uint32_t*>(&l);
+                                }
+                            }
+#pragma unroll
+                            for (int jj = 0; jj < NCH / 2; ++jj) {
+                                *reinterpret_cast<uint4*>(row + s2_swz<KC>(px, jj)) =
+                                    make_uint4(hi2[4 * jj], hi2[4 * jj + 1], hi2[4 * jj + 2], hi2[4 * jj + 3]);
+                                *reinterpret_cast<uint4*>(row + s2_swz<KC>(px, NCH / 2 + jj)) =
+                                    make_uint4(lo2[4 * jj], lo2[4 * jj + 1], lo2[4 * jj + 2], lo2[4 * jj + 3]);
+                            }
                         }
                     }
                 }
