@@ -15,7 +15,10 @@
 // fp32 FMA accumulation (tolerance-level parity with the reference, see tests/).
 #include <cstdlib>
 
+#include <cuda.h>
+
 #include "common.cuh"
+#include "ring_util.cuh"
 
 namespace {
 
@@ -826,10 +829,120 @@ extern "C" int codd_conv2d_nhwc(const codd_conv_desc* d, const float* in0, const
     return 0;
 }
 
+namespace {
+// TMA-staged variant of conv3x3_image_kernel: ncu of the kernel above shows the L1 data pipe 77 % busy with 61 M
+// sectors of scalar input loads for a 106 MB image pair (six 4-byte loads per row and channel, lanes 16 bytes apart).
+// Here ONE bulk tensor load brings the CTA's (8 + 2) x (256 + 8) x 3 input tile (zero-filled outside the image = the
+// padding) into shared memory; a thread reads its four pixels as one 128-bit shared load plus the two neighbours.
+// Weights and bias arrive by bulk copies on the same mbarrier.  Arithmetic and its order are unchanged.
+// (a TMA box is at most 256 elements wide: each of the CTA's two warps gets its own 128 + 8 column tile)
+constexpr int IT_THREADS = 64, IT_PX = 4, IT_TW = IT_THREADS * IT_PX, IT_BOXW = 32 * IT_PX + 8, IT_BOXH = IMG_ROWS + 2;
+constexpr int IT_TILE = (3 * IT_BOXH * IT_BOXW + 31) & ~31;      // floats per warp tile, padded to 128 bytes (TMA destination)
+__global__ void __launch_bounds__(IT_THREADS) conv3x3_image_tma_kernel(const __grid_constant__ CUtensorMap lmap,
+                                                                      const __grid_constant__ CUtensorMap rmap, int n, int h,
+                                                                      int w, const float* __restrict__ wgt,
+                                                                      const float* __restrict__ bias, float* __restrict__ out,
+                                                                      int ldo) {
+    constexpr int CO = 16, PXI = IT_PX;
+    extern __shared__ uint8_t it_raw[];
+    __shared__ __align__(8) unsigned long long bar;
+    const uint32_t sbase = (s_u32(it_raw) + 127u) & ~127u;
+    float* tile = reinterpret_cast<float*>(it_raw + (sbase - s_u32(it_raw)));     // [2 warps][3][IT_BOXH][IT_BOXW]
+    float* s_w = tile + 2 * IT_TILE;                                               // [27][CO]
+    float* s_b = s_w + 27 * CO;
+    const int tid = threadIdx.x;
+    const int xc0 = blockIdx.x * IT_TW, y0 = blockIdx.y * IMG_ROWS, s = blockIdx.z;
+    const uint32_t b = s_u32(&bar);
+    if (tid == 0) {
+        mbar_init(b, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(b, (uint32_t)((2 * 3 * IT_BOXH * IT_BOXW + 27 * CO + CO) * 4));
+#pragma unroll
+        for (int wv = 0; wv < 2; ++wv)
+            asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                         ::"r"(sbase + (uint32_t)wv * (IT_TILE * 4)), "l"(s < n ? &lmap : &rmap), "r"(b),
+                           "r"(xc0 + wv * 32 * PXI - 4), "r"(y0 - 1), "r"(0), "r"(s < n ? s : s - n)
+                         : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(s_u32(s_w)), "l"(wgt), "r"(27 * CO * 4), "r"(b) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(s_u32(s_b)), "l"(bias), "r"(CO * 4), "r"(b) : "memory");
+    }
+    __syncthreads();
+    mbar_wait(b, 0);
+    const int x0 = xc0 + tid * PXI;
+    if (x0 >= w) return;
+    const int y_end = min(h, y0 + IMG_ROWS);
+#pragma unroll 1
+    for (int y = y0; y < y_end; ++y) {
+        __align__(8) float acc[PXI][CO];
+#pragma unroll
+        for (int q = 0; q < PXI; ++q)
+#pragma unroll
+            for (int i = 0; i < CO; ++i) acc[q][i] = s_b[i];
+#pragma unroll 1
+        for (int ky = 0; ky < 3; ++ky) {
+            const int yy = y + ky - 1;
+            if (yy < 0 || yy >= h) continue;       // (zero rows: skipped as in the kernel above, same FMA sequence)
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) {
+                const float* rp = tile + (tid >> 5) * IT_TILE + (ci * IT_BOXH + (y - y0 + ky)) * IT_BOXW + 4 + (tid & 31) * PXI;   // -> pixel x0
+                const float4 m = *reinterpret_cast<const float4*>(rp);
+                const float a[PXI + 2] = {rp[-1], m.x, m.y, m.z, m.w, rp[4]};
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float* wp = s_w + ((ky * 3 + kx) * 3 + ci) * CO;
+#pragma unroll
+                    for (int o4 = 0; o4 < CO / 4; ++o4) {
+                        const float4 wv = *reinterpret_cast<const float4*>(wp + o4 * 4);
+#pragma unroll
+                        for (int q = 0; q < PXI; ++q) fma4(&acc[q][o4 * 4], a[q + kx], wv);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < PXI; ++q) {
+            if (x0 + q >= w) break;
+            float* op = out + (((size_t)s * h + y) * w + x0 + q) * ldo;
+#pragma unroll
+            for (int i = 0; i < CO; ++i) acc[q][i] = fmaxf(acc[q][i], 0.f) + CODD_LEAKY_SLOPE * fminf(acc[q][i], 0.f);
+            stg8(op, &acc[q][0]);
+            stg8(op + 8, &acc[q][8]);
+        }
+    }
+}
+
+int conv3x3_image_tma(const float* left, const float* right, int n, int h, int w, const float* weight, const float* bias,
+                      float* out, int ldo, cudaStream_t s) {
+    PFN_tmapEncodeTiled enc = rg_get_encode();
+    if (!enc) return CODD_E_UNSUPPORTED;
+    auto make = [&](CUtensorMap* m, const float* base) {
+        const cuuint64_t dim[4] = {(cuuint64_t)w, (cuuint64_t)h, 3u, (cuuint64_t)n};
+        const cuuint64_t str[3] = {(cuuint64_t)w * 4, (cuuint64_t)h * w * 4, (cuuint64_t)3 * h * w * 4};
+        const cuuint32_t box[4] = {(cuuint32_t)IT_BOXW, (cuuint32_t)IT_BOXH, 3u, 1u}, es[4] = {1u, 1u, 1u, 1u};
+        return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dim, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    };
+    CUtensorMap lmap, rmap;
+    if (!make(&lmap, left) || !make(&rmap, right ? right : left)) return CODD_E_UNSUPPORTED;
+    const size_t smem = (size_t)(2 * IT_TILE + 27 * 16 + 16) * 4 + 128;
+    dim3 grid(codd_ceil_div(w, IT_TW), codd_ceil_div(h, IMG_ROWS), right ? 2 * n : n);
+    conv3x3_image_tma_kernel<<<grid, IT_THREADS, smem, s>>>(lmap, rmap, n, h, w, weight, bias, out, ldo);
+    CODD_RETURN_IF_CUDA_ERROR();
+    return 0;
+}
+}  // namespace
+
 extern "C" int codd_conv3x3_image(const float* left, const float* right, int n, int h, int w, const float* weight,
                                   const float* bias, int cout, float* out, int ldo, void* stream) {
     if (!left || !weight || !bias || !out || n <= 0 || h <= 0 || w <= 0) return CODD_E_BADARG;
     if (cout <= 0 || cout > 16 || ldo < cout) return CODD_E_SHAPE;
+    if (cout == 16 && w % 4 == 0 && w >= 64 && ldo % 8 == 0 && codd_aligned32(out) && codd_aligned16(left) &&
+        (!right || codd_aligned16(right)) && codd_aligned16(weight) && codd_aligned16(bias)) {
+        const int rc = conv3x3_image_tma(left, right, n, h, w, weight, bias, out, ldo, (cudaStream_t)stream);
+        if (rc != CODD_E_UNSUPPORTED) return rc;
+    }
     dim3 block(64);
     dim3 grid(codd_ceil_div(w, 64 * 4), codd_ceil_div(h, IMG_ROWS), right ? 2 * n : n);
     conv3x3_image_kernel<16><<<grid, block, 0, (cudaStream_t)stream>>>(left, right ? right : left, n, h, w, weight,

@@ -197,6 +197,22 @@ def test_tile_features_fused(ops, cin, h, w):
     torch.testing.assert_close(out_r.cpu(), ref_r, rtol=CONV_RTOL, atol=CONV_ATOL)
 
 
+@pytest.mark.parametrize("n,h,w", [(2, 21, 260), (1, 8, 64), (1, 40, 1000), (3, 9, 256), (1, 17, 132)])
+def test_image_conv_tma_staged(ops, n, h, w):
+    """conv1 of HITUNet (backbone.py:35-39) through the TMA-staged kernel (width a multiple of 4): ragged last CTA, image
+    heights that are not a multiple of the 8-row tile, the zero padding delivered by TMA's out-of-bounds fill."""
+    g = gen(n * 100 + h + w)
+    l = torch.randn(n, 3, h, w, generator=g)
+    r = torch.randn(n, 3, h, w, generator=g)
+    wt = torch.randn(16, 3, 3, 3, generator=g) / 5
+    b = torch.randn(16, generator=g)
+    ref = F.leaky_relu(F.conv2d(torch.cat([l, r]), wt, b, padding=1), 0.2)
+    out = ops.conv3x3_image(l.cuda(), r.cuda(), ops.pack_conv_weight(wt).cuda(), b.cuda(), 16)
+    torch.testing.assert_close(back(ops, out), ref, rtol=CONV_RTOL, atol=CONV_ATOL)
+    out1 = ops.conv3x3_image(l.cuda(), None, ops.pack_conv_weight(wt).cuda(), b.cuda(), 16)
+    torch.testing.assert_close(back(ops, out1), ref[:n], rtol=CONV_RTOL, atol=CONV_ATOL)
+
+
 def test_image_conv_and_deconv(ops):
     g = gen(9)
     l = torch.randn(2, 3, 21, 45, generator=g)
