@@ -200,6 +200,9 @@ __global__ void __launch_bounds__(UM_THREADS) upmerge_kernel(UmP p) {
 // reading activations with 128-bit shared loads, overwrites its own skip pixels with the results, and two bulk tensor
 // stores write the rows back (columns >= W clipped by the hardware).  Same FMA order as above: bit-identical results.
 constexpr int UT_THREADS = 64, UT_PAR = 128, UT_PX = 2 * UT_PAR;
+// CC = coarse channels: 16 (SWIZZLE_64B tile, as the skip rows) or 24 (96-byte pixel rows, unswizzled: the 128-bit reads of
+// neighbouring lanes then conflict two ways, on 6 of ~280 shared loads per thread and row)
+template <int CC>
 __global__ void __launch_bounds__(UT_THREADS) upmerge_tma_kernel(const __grid_constant__ CUtensorMap cmap,
                                                                 const __grid_constant__ CUtensorMap smap,
                                                                 const __grid_constant__ CUtensorMap omap, UmP p) {
@@ -208,10 +211,10 @@ __global__ void __launch_bounds__(UT_THREADS) upmerge_tma_kernel(const __grid_co
     __shared__ __align__(8) unsigned long long bar;
     const uint32_t sbase = (s_u32(ut_raw) + 1023u) & ~1023u;
     uint8_t* gbase = ut_raw + (sbase - s_u32(ut_raw));
-    // [coarse 128 px x 64 B | skip row 0: 256 px x 64 B | skip row 1 | weights]
-    constexpr uint32_t OFF_S0 = UT_PAR * 64, OFF_S1 = OFF_S0 + UT_PX * 64, OFF_W = OFF_S1 + UT_PX * 64;
-    float* s_wu = reinterpret_cast<float*>(gbase + OFF_W);   // [4][C][C]
-    float* s_wm = s_wu + 4 * C * C;                          // [2C][C]
+    // [coarse 128 px x CC*4 B | skip row 0: 256 px x 64 B | skip row 1 | weights]
+    constexpr uint32_t OFF_S0 = (UT_PAR * CC * 4 + 1023u) & ~1023u, OFF_S1 = OFF_S0 + UT_PX * 64, OFF_W = OFF_S1 + UT_PX * 64;
+    float* s_wu = reinterpret_cast<float*>(gbase + OFF_W);   // [4][CC][C]
+    float* s_wm = s_wu + 4 * CC * C;                         // [2C][C]
     float* s_bu = s_wm + 2 * C * C;
     float* s_bm = s_bu + C;
     const int tid = threadIdx.x;
@@ -220,13 +223,13 @@ __global__ void __launch_bounds__(UT_THREADS) upmerge_tma_kernel(const __grid_co
     if (tid == 0) {
         mbar_init(b, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        mbar_expect_tx(b, (uint32_t)(UT_PAR * 64 + 2 * UT_PX * 64 + (p.w_bulk ? (4 * C * C + 2 * C * C + 2 * C) * 4 : 0)));
+        mbar_expect_tx(b, (uint32_t)(UT_PAR * CC * 4 + 2 * UT_PX * 64 + (p.w_bulk ? (4 * CC * C + 2 * C * C + 2 * C) * 4 : 0)));
         if (p.w_bulk) {       // weights and biases as four 1-D bulk copies (16-byte aligned sources): no thread touches them
             auto bulk = [&](const float* dst, const float* src, uint32_t bytes) {
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                              ::"r"(s_u32(dst)), "l"(src), "r"(bytes), "r"(b) : "memory");
             };
-            bulk(s_wu, p.w_up, 4 * C * C * 4);
+            bulk(s_wu, p.w_up, 4 * CC * C * 4);
             bulk(s_wm, p.w_m, 2 * C * C * 4);
             bulk(s_bu, p.b_up, C * 4);
             bulk(s_bm, p.b_m, C * 4);
@@ -239,7 +242,7 @@ __global__ void __launch_bounds__(UT_THREADS) upmerge_tma_kernel(const __grid_co
                      ::"r"(sbase + OFF_S1), "l"(&smap), "r"(b), "r"(0), "r"(2 * xp0), "r"(2 * yp + 1), "r"(n) : "memory");
     }
     if (!p.w_bulk) {
-        for (int i = tid; i < 4 * C * C; i += UT_THREADS) s_wu[i] = __ldg(p.w_up + i);
+        for (int i = tid; i < 4 * CC * C; i += UT_THREADS) s_wu[i] = __ldg(p.w_up + i);
         for (int i = tid; i < 2 * C * C; i += UT_THREADS) s_wm[i] = __ldg(p.w_m + i);
         if (tid < C) { s_bu[tid] = __ldg(p.b_up + tid); s_bm[tid] = __ldg(p.b_m + tid); }
     }
@@ -258,13 +261,15 @@ __global__ void __launch_bounds__(UT_THREADS) upmerge_tma_kernel(const __grid_co
 #pragma unroll
             for (int c = 0; c < C; ++c) up[j][c] = s_bu[c];
         {
-            const float* w0 = s_wu + (dy * 2 + 0) * C * C;
-            const float* w1 = s_wu + (dy * 2 + 1) * C * C;
+            const float* w0 = s_wu + (dy * 2 + 0) * CC * C;
+            const float* w1 = s_wu + (dy * 2 + 1) * CC * C;
 #pragma unroll
-            for (int c4 = 0; c4 < C / 4; ++c4) {
+            for (int c4 = 0; c4 < CC / 4; ++c4) {
                 float4 a[NPAR];
 #pragma unroll
-                for (int q = 0; q < NPAR; ++q) a[q] = *reinterpret_cast<const float4*>(gbase + swz_off<16>(lp[q], c4));
+                for (int q = 0; q < NPAR; ++q)
+                    a[q] = *reinterpret_cast<const float4*>(gbase + (CC == 16 ? swz_off<16>(lp[q], c4)
+                                                                             : (uint32_t)(lp[q] * CC * 4 + c4 * 16)));
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) {
 #pragma unroll
@@ -345,29 +350,32 @@ __global__ void __launch_bounds__(UT_THREADS) upmerge_tma_kernel(const __grid_co
     }
 }
 
+template <int CC>
 int um_launch_tma(const UmP& p, cudaStream_t s) {
     PFN_tmapEncodeTiled enc = rg_get_encode();
     if (!enc) return CODD_E_UNSUPPORTED;
     const int Hc = p.H / 2, Wc = p.W / 2;
-    auto make = [&](CUtensorMap* m, const float* base, int ld, int w, int h, int boxw) {
-        const cuuint64_t dim[4] = {16u, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)p.N};
+    auto make = [&](CUtensorMap* m, const float* base, int c, int ld, int w, int h, int boxw) {
+        const cuuint64_t dim[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)p.N};
         const cuuint64_t str[3] = {(cuuint64_t)ld * 4, (cuuint64_t)w * ld * 4, (cuuint64_t)h * w * ld * 4};
-        const cuuint32_t box[4] = {16u, (cuuint32_t)boxw, 1u, 1u}, es[4] = {1u, 1u, 1u, 1u};
+        const cuuint32_t box[4] = {(cuuint32_t)c, (cuuint32_t)boxw, 1u, 1u}, es[4] = {1u, 1u, 1u, 1u};
         return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dim, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+                   c == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
     };
     CUtensorMap cmap, smap, omap;
-    if (!make(&cmap, p.coarse, p.ldc, Wc, Hc, UT_PAR) || !make(&smap, p.skip, p.lds, p.W, p.H, UT_PX) ||
-        !make(&omap, p.out, p.ldo, p.W, p.H, UT_PX))
+    if (!make(&cmap, p.coarse, CC, p.ldc, Wc, Hc, UT_PAR) || !make(&smap, p.skip, 16, p.lds, p.W, p.H, UT_PX) ||
+        !make(&omap, p.out, 16, p.ldo, p.W, p.H, UT_PX))
         return CODD_E_UNSUPPORTED;
-    const size_t smem = (size_t)UT_PAR * 64 + 2 * UT_PX * 64 + (4 * 256 + 2 * 256 + 32) * sizeof(float) + 1024;
+    const size_t smem = (((size_t)UT_PAR * CC * 4 + 1023) & ~(size_t)1023) + 2 * UT_PX * 64 +
+                        (4 * CC * 16 + 2 * 256 + 32) * sizeof(float) + 1024;
     static CoddDeviceOnce once;
     if (int rc = codd_once_per_device(once, [&] {
-            return cudaFuncSetAttribute(upmerge_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            return cudaFuncSetAttribute(upmerge_tma_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         }))
         return rc;
     dim3 grid((unsigned)codd_ceil_div(Wc, UT_PAR), (unsigned)Hc, (unsigned)p.N);
-    upmerge_tma_kernel<<<grid, UT_THREADS, smem, s>>>(cmap, smap, omap, p);
+    upmerge_tma_kernel<CC><<<grid, UT_THREADS, smem, s>>>(cmap, smap, omap, p);
     CODD_RETURN_IF_CUDA_ERROR();
     return 0;
 }
@@ -405,8 +413,8 @@ extern "C" int codd_upmerge_nhwc(const float* coarse, int ldc, int cc, const flo
     const int wc = w / 2;
     const bool two = (wc % 256 == 0) || (wc % 256 > 192) || (wc > 256 && wc % 256 > 128);
     // the all-16-channel case at sizes that fill 128-parent CTAs: TMA-staged variant
-    if (cu == 16 && co == 16 && cc == 16 && cs == 16 && wc >= 96) {
-        const int rc = um_launch_tma(p, s);
+    if (cu == 16 && co == 16 && (cc == 16 || cc == 24) && cs == 16 && wc >= 96) {
+        const int rc = cc == 16 ? um_launch_tma<16>(p, s) : um_launch_tma<24>(p, s);
         if (rc != CODD_E_UNSUPPORTED) return rc;
     }
     if (cu == 16 && co == 16) return two ? um_launch<16, 16, 2>(p, s) : um_launch<16, 16, 1>(p, s);
