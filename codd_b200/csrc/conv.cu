@@ -593,6 +593,62 @@ __global__ void __launch_bounds__(H1_TW * H1_TH) conv3x3_head1_kernel(const floa
     out[opix * ldo] = codd_act(acc, act, 0);
 }
 
+// Two-output 3x3 head, 32 input channels: the two confidence filters of TileUpdate.lastconv (propagation.py:190-199,
+// channels 32 and 33 of a 34-channel layer whose first 32 filters run on the tensor cores).  Same scheme as the
+// single-output head: a (32+2) x (4+2) NHWC tile in shared memory (pixel pitch CIN+4), one thread per output pixel, both
+// filters from one activation read.  As a general direct convolution with two live filters this took 48 us per launch.
+constexpr int H2_TW = 32, H2_TH = 4;
+template <int CIN>
+__global__ void __launch_bounds__(H2_TW * H2_TH) conv3x3_head2_kernel(const float* __restrict__ in, int ldi, int n, int h,
+                                                                      int w, const float* __restrict__ wgt, int wld,
+                                                                      const float* __restrict__ bias,
+                                                                      const float* __restrict__ res, int ldr, int res_bcast,
+                                                                      int act, float* __restrict__ out, int ldo) {
+    constexpr int PITCH = CIN + 4;
+    __shared__ __align__(16) float s_t[(H2_TH + 2) * (H2_TW + 2) * PITCH];
+    __shared__ __align__(16) float s_w[9 * 2 * CIN];                                  // [tap][filter][cin]
+    const int tid = threadIdx.y * H2_TW + threadIdx.x;
+    const int x0 = blockIdx.x * H2_TW, y0 = blockIdx.y * H2_TH, s = blockIdx.z;
+    for (int i = tid; i < 9 * 2 * CIN; i += H2_TW * H2_TH) {
+        const int ci = i % CIN, co = (i / CIN) & 1, tap = i / (2 * CIN);
+        s_w[i] = __ldg(wgt + ((size_t)tap * CIN + ci) * wld + co);                    // packed [tap][cin][wld]
+    }
+    for (int i = tid; i < (H2_TH + 2) * (H2_TW + 2) * (CIN / 4); i += H2_TW * H2_TH) {
+        const int c4 = i % (CIN / 4), pix = i / (CIN / 4);
+        const int px = pix % (H2_TW + 2), py = pix / (H2_TW + 2);
+        const int gx = x0 + px - 1, gy = y0 + py - 1;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gx >= 0 && gx < w && gy >= 0 && gy < h) v = ldg4(in + (((size_t)s * h + gy) * w + gx) * ldi + c4 * 4);
+        *reinterpret_cast<float4*>(s_t + pix * PITCH + c4 * 4) = v;
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x >= w || y >= h) return;
+    float a0 = bias ? __ldg(bias) : 0.f, a1 = bias ? __ldg(bias + 1) : 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const float* tp = s_t + ((threadIdx.y + ky) * (H2_TW + 2) + threadIdx.x + kx) * PITCH;
+            const float* wp = s_w + (ky * 3 + kx) * 2 * CIN;
+#pragma unroll
+            for (int c4 = 0; c4 < CIN / 4; ++c4) {
+                const float4 a = *reinterpret_cast<const float4*>(tp + c4 * 4);
+                const float4 u = *reinterpret_cast<const float4*>(wp + c4 * 4);
+                const float4 v = *reinterpret_cast<const float4*>(wp + CIN + c4 * 4);
+                a0 = fmaf(a.x, u.x, a0); a0 = fmaf(a.y, u.y, a0); a0 = fmaf(a.z, u.z, a0); a0 = fmaf(a.w, u.w, a0);
+                a1 = fmaf(a.x, v.x, a1); a1 = fmaf(a.y, v.y, a1); a1 = fmaf(a.z, v.z, a1); a1 = fmaf(a.w, v.w, a1);
+            }
+        }
+    const size_t opix = ((size_t)s * h + y) * w + x;
+    if (res) {
+        a0 += __ldg(res + opix * ldr);
+        a1 += __ldg(res + opix * ldr + (res_bcast ? 0 : 1));
+    }
+    out[opix * ldo] = codd_act(a0, act, 0);
+    out[opix * ldo + 1] = codd_act(a1, act, 1);
+}
+
 // ---------------------------------------------------------------------------------------------
 // ConvTranspose2d k=2 s=2: every output pixel sees exactly one input pixel and one of 4 taps
 // ---------------------------------------------------------------------------------------------
@@ -768,6 +824,14 @@ int conv_dispatch(const ConvP& p, const codd_conv_desc* d, cudaStream_t s) {
         dim3 grid(codd_ceil_div(p.W, H1_TW), codd_ceil_div(p.H, H1_TH), p.N), block(H1_TW, H1_TH);
         conv3x3_head1_kernel<16><<<grid, block, 0, s>>>(p.in0, p.ld0, p.N, p.H, p.W, p.w, p.bias, p.res, p.ldr, p.act,
                                                         p.out, p.ldo);
+        CODD_RETURN_IF_CUDA_ERROR();
+        return 0;
+    }
+    if (kh == 3 && kw == 3 && sh == 1 && sw == 1 && dil == 1 && p.Cout == 2 && p.C0 == 32 && p.C1 == 0 && p.vec0 &&
+        d->ph == 1 && d->pw == 1 && d->ho == d->h && d->wo == d->w && !p.res_after) {
+        dim3 grid(codd_ceil_div(p.W, H2_TW), codd_ceil_div(p.H, H2_TH), p.N), block(H2_TW, H2_TH);
+        conv3x3_head2_kernel<32><<<grid, block, 0, s>>>(p.in0, p.ld0, p.N, p.H, p.W, p.w, p.wld, p.bias, p.res, p.ldr,
+                                                        p.res_bcast, p.act, p.out, p.ldo);
         CODD_RETURN_IF_CUDA_ERROR();
         return 0;
     }

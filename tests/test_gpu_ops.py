@@ -57,7 +57,7 @@ CONV_CASES = [
     (3, 1, 1, 1, 16, 3, 20, 50), (3, 1, 1, 1, 16, 1, 20, 50), (3, 1, 1, 1, 32, 16, 33, 31), (3, 1, 1, 1, 8, 8, 6, 6),
     (3, 1, 3, 3, 32, 32, 36, 60), (4, 2, 1, 1, 16, 16, 32, 64), (4, 2, 1, 1, 16, 24, 36, 60), (4, 2, 1, 1, 24, 32, 18, 30),
     (4, 4, 0, 1, 16, 16, 36, 60), (4, 4, 0, 1, 32, 16, 8, 140), (7, 1, 3, 1, 2, 32, 20, 30), (7, 1, 3, 1, 64, 30, 12, 34),
-    (1, 1, 0, 1, 31, 64, 10, 10), (3, 1, 1, 1, 17, 5, 7, 9),
+    (1, 1, 0, 1, 31, 64, 10, 10), (3, 1, 1, 1, 17, 5, 7, 9), (3, 1, 1, 1, 32, 2, 9, 15), (3, 1, 1, 1, 32, 2, 37, 70),
 ]
 
 
@@ -72,6 +72,23 @@ def test_conv2d_vs_torch_cpu(ops, k, s, p, d, cin, cout, h, w):
     out = ops.conv2d(nhwc(ops, x), ops.pack_conv_weight(wt).cuda(), b.cuda(), cout, k, s, p, d, ACT_LEAKY)
     assert out.shape == ref.shape
     torch.testing.assert_close(back(ops, out), ref, rtol=CONV_RTOL, atol=CONV_ATOL)
+
+
+def test_conv3x3_two_filter_head_into_slice(ops):
+    """The two confidence filters of TileUpdate.lastconv (32 -> 2 of a 34-channel layer) through the two-output head kernel,
+    written into channels [32, 34) of a 36-wide buffer, weights a column slice semantics of the packed layer."""
+    from codd_b200.lib import ACT_NONE
+    g = gen(77)
+    x = torch.randn(2, 32, 21, 45, generator=g)
+    wt = torch.randn(34, 32, 3, 3, generator=g) / 17
+    b = torch.randn(34, generator=g)
+    ref = F.conv2d(x, wt, b, padding=1)[:, 32:34]
+    out = ops.empty_nhwc(2, 34, 21, 45, "cuda", 36)
+    out.zero_()
+    ops.conv2d(nhwc(ops, x), ops.pack_conv_weight(wt[32:34]).cuda(), b[32:34].cuda().contiguous(), 2, 3, 1, 1, 1, ACT_NONE,
+               out=out[:, 32:34])
+    torch.testing.assert_close(back(ops, out[:, 32:34]), ref, rtol=CONV_RTOL, atol=CONV_ATOL)
+    assert float(out[:, :32].abs().max()) == 0.0
 
 
 def test_conv2d_dual_input_residual_slices(ops):
