@@ -334,11 +334,13 @@ def tc_eligible(cin, cout, k, stride, pad, dil, x2):
     return dil == 1 and cin in (16, 24, 32) and cout <= 32 and not (cin <= 16 and cout > 16)
 
 
-def conv3x3_tc(x, wsplit, bias, cout, act=ACT_NONE, residual=None, res_bcast=False, flags=0, dil=1):
-    """3x3 s1 conv (pad = dil) on the tensor cores (3xTF32).  ``wsplit`` from pack_conv_weight_tc."""
-    _require_cuda(x, wsplit, bias, residual)
+def conv3x3_tc(x, wsplit, bias, cout, act=ACT_NONE, residual=None, res_bcast=False, flags=0, dil=1, out=None):
+    """3x3 s1 conv (pad = dil) on the tensor cores (3xTF32).  ``wsplit`` from pack_conv_weight_tc; ``out``: optional
+    NHWC-backed destination (e.g. a channel slice of a wider buffer)."""
+    _require_cuda(x, wsplit, bias, residual, out)
     n, cin, h, w = x.shape
-    out = empty_nhwc(n, cout, h, w, x.device)
+    if out is None:
+        out = empty_nhwc(n, cout, h, w, x.device)
     nbytes = 4 * (n * h * w * (cin + cout) + wsplit.numel() // 2
                   + (0 if residual is None else n * h * w * (1 if res_bcast else cout)))
     tag = f"conv3x3tc_cin{cin}_cout{cout}" + ("" if dil == 1 else f"_d{dil}")

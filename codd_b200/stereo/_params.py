@@ -48,6 +48,15 @@ def run_conv(pw, conv, x, act, x2=None, residual=None, res_bcast=False, head=Non
         wp, b2 = pw.conv_range(conv, 32, 34)
         ops.conv2d(x, wp, b2, 2, k, st, pd, dl, act, out=out[:, 32:34])
         return out
+    if (USE_TC and not big and cout == 34 and cin == 32 and x2 is None and residual is None and dl == 1
+            and act != ops.ACT_RELU_CH0 and ops.tc_eligible(cin, 32, k, st, pd, dl, x2)):
+        # the same layer at the coarse levels: halo-tile tensor-core kernel for the first 32 filters + the two-output head
+        out = ops.empty_nhwc(x.shape[0], 34, x.shape[2], x.shape[3], x.device, 36)
+        ws, b = pw.conv_tc(conv, 32)
+        ops.conv3x3_tc(x, ws, b, 32, act, out=out[:, :32])
+        wp, b2 = pw.conv_range(conv, 32, 34)
+        ops.conv2d(x, wp, b2, 2, k, st, pd, dl, act, out=out[:, 32:34])
+        return out
     if USE_TC and USE_RING and big and dl == 1 and ops.tc_eligible(cin, cout, k, st, pd, dl, x2):
         ws, b = pw.conv_ring(conv, head)
         return ops.conv3x3_tc_ring(x, ws, b, cout, act, residual=residual, res_bcast=res_bcast)
