@@ -215,6 +215,62 @@ __global__ void __launch_bounds__(64) corr_lookup_kernel(CorrP p) {
     }
 }
 
+// Cooperative variant (C a multiple of 32): in the kernel above every lane walks its own neighbour's C floats, so a warp-wide
+// 128-bit load touches 32 different lines (one sector each) — the kernel is bound by L1 tag / data-pipe wavefronts (0.93 ms
+// per call, 16 calls per frame).  Here EIGHT lanes share one window position and read a contiguous 128-byte segment of it
+// per step (a warp instruction covers 4 positions = 4 full lines), accumulate their part of the dot product over the C / 32
+// segments and combine with three shuffles.  Same bilinear blend; the dot products are summed in a different order.
+__global__ void __launch_bounds__(64) corr_lookup_coop_kernel(CorrP p) {
+    __shared__ __align__(16) float s_f1[CORR_MAXC];
+    __shared__ float s_g[8][8];   // [x index][y index]
+    const int pix = blockIdx.x;
+    const int n = pix / (p.h * p.w);
+    const int t = threadIdx.x, lane = t & 31, wv = t >> 5;
+    for (int c = t; c < p.C; c += 64) s_f1[c] = __ldg(p.f1 + (size_t)pix * p.ld1 + c) * (1.f / 16.f);   // (f1/4).(f2/4)
+    const float cx = __ldg(p.coords + (size_t)pix * p.ldc), cy = __ldg(p.coords + (size_t)pix * p.ldc + 1);
+    const int rd = 2 * p.radius + 1;
+    const int sub = lane & 7;                 // 16-byte chunk of the 128-byte segment
+    const int nseg = p.C >> 5;
+    __syncthreads();
+    for (int l = 0; l < p.levels; ++l) {
+        const int hl = p.h >> l, wl = p.w >> l;
+        const float sc = 1.f / (float)(1 << l);
+        const float x = cx * sc, y = cy * sc;
+        const float fx = floorf(x), fy = floorf(y);
+        const float dx = x - fx, dy = y - fy;
+#pragma unroll 2
+        for (int g = 0; g < 8; ++g) {
+            const int pos = wv * 32 + g * 4 + (lane >> 3);     // window position of this lane's group of eight
+            const int gi = pos & 7, gj = pos >> 3;
+            float dot = 0.f;
+            if (gi <= rd && gj <= rd) {
+                const float xf = fx - (float)p.radius + (float)gi, yf = fy - (float)p.radius + (float)gj;
+                if (xf >= 0.f && xf < (float)wl && yf >= 0.f && yf < (float)hl) {
+                    const float* q = p.f2[l] + (((size_t)n * hl + (int)yf) * wl + (int)xf) * p.ld2[l] + sub * 4;
+                    const float* f = s_f1 + sub * 4;
+                    for (int sg = 0; sg < nseg; ++sg) {
+                        const float4 v = ldg4(q + sg * 32);
+                        const float4 a = *reinterpret_cast<const float4*>(f + sg * 32);
+                        dot = fmaf(a.x, v.x, dot); dot = fmaf(a.y, v.y, dot); dot = fmaf(a.z, v.z, dot); dot = fmaf(a.w, v.w, dot);
+                    }
+                }
+            }
+            dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+            dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+            dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+            if (sub == 0) s_g[gi][gj] = dot;
+        }
+        __syncthreads();
+        if (t < rd * rd) {
+            const int i = t / rd, j = t - i * rd;   // i: x offset, j: y offset
+            const float v = (1.f - dx) * (1.f - dy) * s_g[i][j] + dx * (1.f - dy) * s_g[i + 1][j] +
+                            (1.f - dx) * dy * s_g[i][j + 1] + dx * dy * s_g[i + 1][j + 1];
+            p.out[(size_t)pix * p.ldo + l * rd * rd + t] = v;
+        }
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // K12: one warp per centre pixel.  Lanes stride over the (2R+1)^2 window, each accumulating the 21
 // unique entries of J^T W J and the 6 of J^T W r; warp reduction; damping (lm*H + ep) on the
@@ -498,7 +554,10 @@ extern "C" int codd_corr_lookup(const float* fmap1, int ld1, const float* const*
     for (int l = 0; l < 4; ++l) { p.f2[l] = l < levels ? fmap2_pyramid[l] : nullptr; p.ld2[l] = l < levels ? ld2[l] : 0; }
     p.coords = coords; p.ldc = ldc; p.N = n; p.h = h; p.w = w; p.C = c; p.levels = levels; p.radius = radius;
     p.out = out; p.ldo = ldo;
-    corr_lookup_kernel<<<(unsigned)(n * h * w), 64, 0, (cudaStream_t)stream>>>(p);
+    bool coop = (c % 32 == 0) && (ld1 % 4 == 0) && codd_aligned16(fmap1);
+    for (int l = 0; l < levels; ++l) coop = coop && (ld2[l] % 4 == 0) && codd_aligned16(fmap2_pyramid[l]);
+    if (coop) corr_lookup_coop_kernel<<<(unsigned)(n * h * w), 64, 0, (cudaStream_t)stream>>>(p);
+    else corr_lookup_kernel<<<(unsigned)(n * h * w), 64, 0, (cudaStream_t)stream>>>(p);
     CODD_RETURN_IF_CUDA_ERROR();
     return 0;
 }
