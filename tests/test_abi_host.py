@@ -149,3 +149,21 @@ def test_ring_weight_packing_reconstructs_weights():
         assert torch.allclose(rec, ref, rtol=0, atol=float(ref.abs().max()) * 2.0 ** -21)
         assert torch.equal(pb[:, :, 1], pa[:, :, 0]) and not pb[:, :, 0].any()
         assert not pa[:, :, :, cout:].any() and not pa[:, :, :, :, cin:].any()
+
+
+def test_tc4_weight_packing_reconstructs_weights():
+    """ops.pack_conv_weight_tc4 (host side of codd_conv4x4s2_tc / codd_tile_features_tc): per tap NP rows of fp16(w) followed
+    by NP rows of fp16(2^10 (w - fp16(w))); hi + lo / 1024 reproduces w to 2^-21 relative, padding is zero."""
+    import torch
+    from codd_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    for cout, cin in [(16, 16), (24, 16), (24, 24), (32, 24), (16, 32), (3, 16)]:
+        w = torch.randn(cout, cin, 4, 4, generator=g) * 0.3
+        buf = ops.pack_conv_weight_tc4(w)
+        kc = 16 if cin <= 16 else 32
+        npad = 16 if cout <= 16 else 32
+        h = buf.view(torch.float16).view(16, 2, npad, kc).float()          # [tap][hi|lo][cout][cin]
+        rec = (h[:, 0] + h[:, 1] / 1024.0)[:, :cout, :cin]
+        ref = w.permute(2, 3, 0, 1).reshape(16, cout, cin)
+        assert torch.allclose(rec, ref, rtol=0, atol=float(ref.abs().max()) * 2.0 ** -21)
+        assert not h[:, :, cout:].any() and not h[:, :, :, cin:].any()
