@@ -194,7 +194,7 @@ def tc4_eligible(x, cout, k, stride, pad, dil, x2, residual):
 
 
 def conv4x4s2_tc(x, wsplit, bias, cout, act=ACT_NONE):
-    """4x4 s2 p1 conv on the tensor cores (3xTF32).  ``wsplit`` from pack_conv_weight_tc4."""
+    """4x4 s2 p1 conv on the tensor cores (three fp16 products, fp32 accumulation).  ``wsplit`` from pack_conv_weight_tc4."""
     _require_cuda(x, wsplit, bias)
     n, cin, h, w = x.shape
     out = empty_nhwc(n, cout, h // 2, w // 2, x.device)
